@@ -1,0 +1,60 @@
+// Error plumbing and device checks shared by every C-ABI entry point.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace dfb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what, const char* file, int line) {
+    if (e == cudaSuccess) return 0;
+    const char* base = strrchr(file, '/');
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), base ? base + 1 : file, line, what);
+    return (int)e;
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            return 148;
+    }
+    return cached;
+}
+
+}  // namespace dfb
+
+extern "C" int dfb_abi_version(void) { return DFB_ABI_VERSION; }
+
+extern "C" const char* dfb_last_error_string(void) { return dfb::g_err; }
+
+extern "C" int dfb_device_check(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        dfb::set_error("no CUDA device available (%s); deepfit_b200 has no CPU fallback", cudaGetErrorString(e));
+        return DFB_E_NODEVICE;
+    }
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess || major != 10) {
+        cudaGetLastError();
+        dfb::set_error("device %d has compute capability major %d; this library is built for sm_100a only", dev, major);
+        return DFB_E_NODEVICE;
+    }
+    return DFB_OK;
+}

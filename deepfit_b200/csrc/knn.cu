@@ -1,0 +1,540 @@
+// Stage 1: exact k-nearest-neighbour search on a Morton-ordered multi-level uniform grid.
+//
+// Replaces scipy.spatial.cKDTree(points, 10) + query(points[i], k) (reference
+// tutorial/tutorial_utils.py:16,21; dataset.py:32,293).  Results are bit-identical to cKDTree after
+// distance-then-index tie-breaking: the ranking key is (fp64 d^2, index) with
+// d^2 = ((double)px-(double)qx)^2 + (..y)^2 + (..z)^2 accumulated in that order without FMA
+// contraction, exactly what cKDTree evaluates on float32 inputs promoted to double.
+//
+// Structure
+//   build : bounding cube -> 2^b cells per axis; points counting-sorted by the Morton code of their
+//           finest cell, so a cell of ANY coarser level l is one contiguous range
+//           [tab[m << 3l], tab[(m+1) << 3l]) of the sorted array -- one table serves all levels.
+//   query : one warp per query.  Climb levels until the 3x3x3 block of cells around the query holds
+//           >= 3k points, stream the block's points (coalesced float4 reads), keep the k best in a
+//           shared-memory list + insertion buffer (bitonic sort when the buffer fills, cells farther
+//           than the current k-th distance are skipped), and accept when the k-th distance is
+//           strictly inside the block's guaranteed margin; otherwise retry one level up with the
+//           k-th key as the starting threshold.  The top level covers the whole cloud, so the
+//           search always terminates with the exact answer.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace dfb {
+namespace {
+
+constexpr int kMaxLevelBits = 10;
+constexpr float kCellSlack = 2e-3f;  // bound (in cells) on the float error of cell coordinates
+
+__host__ __device__ __forceinline__ uint32_t spread3(uint32_t v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__host__ __device__ __forceinline__ uint32_t morton3(uint32_t x, uint32_t y, uint32_t z) {
+    return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2);
+}
+
+struct GridParams {
+    float minx, miny, minz;
+    float inv_cell;  // cells per unit length at the finest level
+    float cell;      // finest cell edge
+    int bits;        // finest level has 2^bits cells per axis
+    long long n;
+};
+
+// Continuous cell coordinate of a point at the finest level.  Build and query share this function,
+// so cell membership is consistent and monotone in the coordinate.
+__device__ __forceinline__ float cell_coord(float p, float mn, float inv_cell) { return (p - mn) * inv_cell; }
+__device__ __forceinline__ int cell_index(float u, int g) {
+    int i = (int)floorf(u);
+    return i < 0 ? 0 : (i >= g ? g - 1 : i);
+}
+
+// ---------------------------------------------------------------------------------------- build
+
+__device__ __forceinline__ unsigned f2ord(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(unsigned u) {
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+
+__global__ void bbox_kernel(const float* __restrict__ pts, long long n, unsigned* __restrict__ out6) {
+    unsigned mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const unsigned o = f2ord(pts[i * 3 + a]);
+            mn[a] = min(mn[a], o);
+            mx[a] = max(mx[a], o);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = min(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(out6 + a, mn[a]);
+            atomicMax(out6 + 3 + a, mx[a]);
+        }
+    }
+}
+
+__global__ void count_kernel(const float* __restrict__ pts, GridParams g, uint32_t* __restrict__ code,
+                             uint32_t* __restrict__ tab) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    const int G = 1 << g.bits;
+    const uint32_t m = morton3(cell_index(cell_coord(pts[i * 3 + 0], g.minx, g.inv_cell), G),
+                               cell_index(cell_coord(pts[i * 3 + 1], g.miny, g.inv_cell), G),
+                               cell_index(cell_coord(pts[i * 3 + 2], g.minz, g.inv_cell), G));
+    code[i] = m;
+    atomicAdd(tab + 1 + m, 1u);
+}
+
+// Exclusive scan of tab[1..ncell] in place (tab[0] stays 0 and tab[c+1] becomes start of cell c,
+// then the scatter turns it into the end of cell c == start of cell c+1).
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__global__ void scan_tile_sums(const uint32_t* __restrict__ v, long long n, uint32_t* __restrict__ sums) {
+    __shared__ uint32_t s[kScanThreads / 32];
+    const long long base = (long long)blockIdx.x * kScanTile;
+    uint32_t t = 0;
+    for (int j = 0; j < kScanItems; ++j) {
+        const long long i = base + (long long)j * kScanThreads + threadIdx.x;
+        if (i < n) t += v[i];
+    }
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t a = 0;
+        for (int w = 0; w < kScanThreads / 32; ++w) a += s[w];
+        sums[blockIdx.x] = a;
+    }
+}
+
+__global__ void scan_sums_serial(uint32_t* __restrict__ sums, long long m) {
+    // single block; m <= 2^30 / 4096 = 262144
+    __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_w[32];
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (long long base = 0; base < m; base += blockDim.x) {
+        const long long i = base + threadIdx.x;
+        const uint32_t v = i < m ? sums[i] : 0u;
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = threadIdx.x < (blockDim.x >> 5) ? s_w[threadIdx.x] : 0u;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += y;
+            }
+            s_w[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const uint32_t warp_off = (threadIdx.x >> 5) ? s_w[(threadIdx.x >> 5) - 1] : 0u;
+        const uint32_t incl = x + warp_off + s_carry;
+        if (i < m) sums[i] = incl - v;  // exclusive
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = incl;
+        __syncthreads();
+    }
+}
+
+__global__ void scan_apply(uint32_t* __restrict__ v, long long n, const uint32_t* __restrict__ sums) {
+    // exclusive scan inside each tile: thread-strided layout -> do it via shared memory in item order
+    __shared__ uint32_t s[kScanTile];
+    __shared__ uint32_t s_w[kScanThreads / 32];
+    const long long base = (long long)blockIdx.x * kScanTile;
+    for (int j = 0; j < kScanItems; ++j) {
+        const int li = j * kScanThreads + threadIdx.x;
+        s[li] = (base + li < n) ? v[base + li] : 0u;
+    }
+    __syncthreads();
+    // each thread owns kScanItems consecutive items
+    uint32_t loc[kScanItems];
+    uint32_t t = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        loc[j] = t;
+        t += s[threadIdx.x * kScanItems + j];
+    }
+    uint32_t x = t;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = x;
+    __syncthreads();
+    uint32_t off = sums[blockIdx.x] + (x - t);
+    for (int w = 0; w < (threadIdx.x >> 5); ++w) off += s_w[w];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) s[threadIdx.x * kScanItems + j] = loc[j] + off;
+    __syncthreads();
+    for (int j = 0; j < kScanItems; ++j) {
+        const int li = j * kScanThreads + threadIdx.x;
+        if (base + li < n) v[base + li] = s[li];
+    }
+}
+
+__global__ void scatter_kernel(const float* __restrict__ pts, long long n, const uint32_t* __restrict__ code,
+                               uint32_t* __restrict__ tab, float4* __restrict__ sorted) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t pos = atomicAdd(tab + 1 + code[i], 1u);
+    sorted[pos] = make_float4(pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2], __int_as_float((int)i));
+}
+
+// ---------------------------------------------------------------------------------------- query
+
+struct Key {
+    double d2;
+    int idx;
+};
+__device__ __forceinline__ bool key_less(double a, int ai, double b, int bi) { return a < b || (a == b && ai < bi); }
+
+// Ascending bitonic sort of cap (power of two) entries held in shared memory by one warp.
+__device__ __forceinline__ void warp_bitonic_sort(double* sd, int* si, int cap, int lane) {
+    for (int size = 2; size <= cap; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = lane; t < (cap >> 1); t += 32) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const double a = sd[lo], b = sd[hi];
+                const int ai = si[lo], bi = si[hi];
+                const bool sw = up ? key_less(b, bi, a, ai) : key_less(a, ai, b, bi);
+                if (sw) {
+                    sd[lo] = b; sd[hi] = a;
+                    si[lo] = bi; si[hi] = ai;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+struct KnnArgs {
+    const float4* sorted;
+    const uint32_t* tab;
+    const float* pts;  // original order, f32[n,3]
+    GridParams g;
+    const int* query;
+    long long q_begin, q_count;
+    int k, kcap;  // kcap = capacity of the shared list (power of two >= 2k, >= 64)
+    int* out_idx;
+    double* out_dist;
+    double* out_rad;
+};
+
+constexpr int kKnnWarps = 4;
+
+__global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* sd = reinterpret_cast<double*>(smem_raw) + (size_t)warp * a.kcap;
+    int* si = reinterpret_cast<int*>(smem_raw + (size_t)kKnnWarps * a.kcap * sizeof(double)) + (size_t)warp * a.kcap;
+    const int G = 1 << a.g.bits;
+    const int k = a.k, cap = a.kcap;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+
+    for (long long qw = (long long)blockIdx.x * kKnnWarps + warp; qw < a.q_count; qw += (long long)gridDim.x * kKnnWarps) {
+        const long long qi = a.query ? (long long)a.query[qw] : a.q_begin + qw;
+        const float qxf = a.pts[qi * 3], qyf = a.pts[qi * 3 + 1], qzf = a.pts[qi * 3 + 2];
+        const double qx = qxf, qy = qyf, qz = qzf;
+        const float ux = cell_coord(qxf, a.g.minx, a.g.inv_cell), uy = cell_coord(qyf, a.g.miny, a.g.inv_cell),
+                    uz = cell_coord(qzf, a.g.minz, a.g.inv_cell);
+        const int ix = cell_index(ux, G), iy = cell_index(uy, G), iz = cell_index(uz, G);
+
+        // threshold: candidates must satisfy key <= T when thr_incl (carried over from a failed
+        // level) or key < T otherwise (T = current k-th best of the list)
+        double Td = INF;
+        int Ti = 0x7fffffff;
+        bool thr_incl = true;
+
+        for (int l = 0; l <= a.g.bits; ++l) {
+            const int Gl = G >> l;
+            const int cx = ix >> l, cy = iy >> l, cz = iz >> l;
+            // 27 neighbour cells, one per lane
+            uint32_t lo = 0, hi = 0;
+            float cmin2 = 0.f;  // conservative squared distance from the query to the cell (world units)
+            if (lane < 27) {
+                const int ex = cx + (lane % 3) - 1, ey = cy + ((lane / 3) % 3) - 1, ez = cz + (lane / 9) - 1;
+                if (ex >= 0 && ey >= 0 && ez >= 0 && ex < Gl && ey < Gl && ez < Gl) {
+                    const uint32_t m = morton3(ex, ey, ez);
+                    const int sh = 3 * l;
+                    if (sh >= 30) {  // single top-level cell
+                        lo = 0;
+                        hi = (uint32_t)a.g.n;
+                    } else {
+                        lo = a.tab[(size_t)m << sh];
+                        hi = a.tab[((size_t)m + 1) << sh];
+                    }
+                    const float w = (float)(1 << l);
+                    float dd[3];
+                    const float uu[3] = {ux, uy, uz};
+                    const int ee[3] = {ex, ey, ez};
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        const float c0 = (float)ee[t] * w, c1 = c0 + w;
+                        float d = 0.f;
+                        if (uu[t] < c0) d = c0 - uu[t] - kCellSlack;
+                        else if (uu[t] > c1) d = uu[t] - c1 - kCellSlack;
+                        dd[t] = fmaxf(d, 0.f);
+                    }
+                    const float dc = a.g.cell * (1.f - 1e-5f);
+                    cmin2 = (dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]) * dc * dc * (1.f - 1e-5f);
+                }
+            }
+            unsigned total = hi - lo;
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            const bool top = (l == a.g.bits);
+            if (!top && (long long)total < min((long long)3 * k, a.g.n)) continue;
+
+            // guaranteed-complete radius of the block (world units), strict
+            double margin2 = INF;
+            if (!top) {
+                const float w = (float)(1 << l);
+                float mrg = 3.0e38f;
+                const float uu[3] = {ux, uy, uz};
+                const int cc[3] = {cx, cy, cz};
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    if (cc[t] - 1 > 0) mrg = fminf(mrg, uu[t] - (float)(cc[t] - 1) * w - kCellSlack);
+                    if (cc[t] + 2 < Gl) mrg = fminf(mrg, (float)(cc[t] + 2) * w - uu[t] - kCellSlack);
+                }
+                if (mrg < 3.0e38f) {
+                    const double mm = (double)fmaxf(mrg, 0.f) * (double)a.g.cell * (1.0 - 1e-6);
+                    margin2 = mm * mm;
+                }
+            }
+
+            // (re)start the list
+            int count = 0;
+            bool full_once = false;  // list has been cut to k at least once => threshold is strict on list[k-1]
+            for (int c = 0; c < 27; ++c) {
+                const uint32_t clo = __shfl_sync(0xffffffffu, lo, c), chi = __shfl_sync(0xffffffffu, hi, c);
+                const float cm2 = __shfl_sync(0xffffffffu, cmin2, c);
+                if (chi <= clo) continue;
+                if ((double)cm2 > Td) continue;
+                for (uint32_t j0 = clo; j0 < chi; j0 += 32) {
+                    const uint32_t j = j0 + lane;
+                    bool take = false;
+                    double d2 = 0.0;
+                    int pidx = 0;
+                    if (j < chi) {
+                        const float4 p = __ldg(a.sorted + j);
+                        const double dx = (double)p.x - qx, dy = (double)p.y - qy, dz = (double)p.z - qz;
+                        d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                        pidx = __float_as_int(p.w);
+                        take = thr_incl ? !key_less(Td, Ti, d2, pidx) : key_less(d2, pidx, Td, Ti);
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, take);
+                    if (bal == 0u) continue;
+                    if (count + 32 > cap) {
+                        // pad, sort, keep the k best
+                        for (int t = count + lane; t < cap; t += 32) { sd[t] = INF; si[t] = 0x7fffffff; }
+                        __syncwarp();
+                        warp_bitonic_sort(sd, si, cap, lane);
+                        count = k;
+                        Td = sd[k - 1];
+                        Ti = si[k - 1];
+                        thr_incl = false;
+                        full_once = true;
+                        __syncwarp();
+                        // re-evaluate this batch against the tighter threshold
+                        take = (j < chi) && key_less(d2, pidx, Td, Ti);
+                        const unsigned bal2 = __ballot_sync(0xffffffffu, take);
+                        if (bal2 == 0u) continue;
+                        const int pos = count + __popc(bal2 & ((1u << lane) - 1u));
+                        if (take) { sd[pos] = d2; si[pos] = pidx; }
+                        count += __popc(bal2);
+                        __syncwarp();
+                        continue;
+                    }
+                    const int pos = count + __popc(bal & ((1u << lane) - 1u));
+                    if (take) { sd[pos] = d2; si[pos] = pidx; }
+                    count += __popc(bal);
+                    __syncwarp();
+                }
+            }
+            (void)full_once;
+            // final sort of what we have
+            for (int t = count + lane; t < cap; t += 32) { sd[t] = INF; si[t] = 0x7fffffff; }
+            __syncwarp();
+            warp_bitonic_sort(sd, si, cap, lane);
+            const bool have_k = count >= k;
+            const double dk2 = have_k ? sd[k - 1] : INF;
+            if (top || (have_k && dk2 < margin2)) {
+                int* oi = a.out_idx + qw * (long long)k;
+                for (int t = lane; t < k; t += 32) {
+                    oi[t] = si[t];
+                    if (a.out_dist) a.out_dist[qw * (long long)k + t] = sqrt(sd[t]);
+                }
+                if (a.out_rad && lane == 0) a.out_rad[qw] = sqrt(sd[k - 1]);
+                __syncwarp();
+                break;
+            }
+            // failed: carry the k-th key (an upper bound of the true k-th key) to the next level
+            if (have_k) {
+                Td = sd[k - 1];
+                Ti = si[k - 1];
+            } else {
+                Td = INF;
+                Ti = 0x7fffffff;
+            }
+            thr_incl = true;
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace
+}  // namespace dfb
+
+struct dfb_grid {
+    dfb::GridParams g;
+    float* pts;        // device copy, original order
+    float4* sorted;    // device, Morton order (x, y, z, original index)
+    uint32_t* tab;     // device, 8^bits + 1 entries
+    size_t ncell;
+};
+
+extern "C" int dfb_grid_create(const float* d_points, int64_t n, dfb_stream stream, dfb_grid** out) {
+    using namespace dfb;
+    DFB_REQUIRE(out != nullptr, DFB_E_ARG, "dfb_grid_create: out is NULL");
+    *out = nullptr;
+    DFB_REQUIRE(d_points != nullptr && n >= 1 && n < (1LL << 31), DFB_E_ARG, "dfb_grid_create: bad arguments (n=%lld)", (long long)n);
+    int rc = dfb_device_check();
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+
+    unsigned* d_bb = nullptr;
+    DFB_CUDA(cudaMalloc(&d_bb, 6 * sizeof(unsigned)));
+    unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    DFB_CUDA(cudaMemcpyAsync(d_bb, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const int bb_blocks = (int)((n + 255) / 256 < (int64_t)sm_count() * 8 ? (n + 255) / 256 : (int64_t)sm_count() * 8);
+    bbox_kernel<<<bb_blocks, 256, 0, st>>>(d_points, (long long)n, d_bb);
+    unsigned hb[6];
+    DFB_CUDA(cudaMemcpyAsync(hb, d_bb, sizeof(hb), cudaMemcpyDeviceToHost, st));
+    DFB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_bb);
+    float mn[3], mx[3];
+    for (int a = 0; a < 3; ++a) { mn[a] = ord2f(hb[a]); mx[a] = ord2f(hb[3 + a]); }
+    float ext = 0.f;
+    for (int a = 0; a < 3; ++a) {
+        DFB_REQUIRE(isfinite(mn[a]) && isfinite(mx[a]), DFB_E_ARG, "dfb_grid_create: non-finite coordinates");
+        ext = fmaxf(ext, mx[a] - mn[a]);
+    }
+    if (!(ext > 0.f)) ext = 1.f;
+    ext *= 1.0001f;
+
+    // finest level: about sqrt(n/8) cells per axis for surface-like clouds, 2^5 .. 2^10
+    int bits = (int)ceil(0.5 * log2((double)n / 8.0 + 1.0));
+    if (bits < 5) bits = 5;
+    if (bits > kMaxLevelBits) bits = kMaxLevelBits;
+
+    dfb_grid* g = new dfb_grid();
+    g->g.minx = mn[0]; g->g.miny = mn[1]; g->g.minz = mn[2];
+    g->g.bits = bits;
+    g->g.inv_cell = (float)(1 << bits) / ext;
+    g->g.cell = ext / (float)(1 << bits);
+    g->g.n = (long long)n;
+    g->ncell = (size_t)1 << (3 * bits);
+    g->pts = nullptr; g->sorted = nullptr; g->tab = nullptr;
+    uint32_t* code = nullptr;
+    uint32_t* sums = nullptr;
+    const long long ntile = (long long)((g->ncell + kScanTile - 1) / kScanTile);
+    cudaError_t e;
+    if ((e = cudaMalloc(&g->pts, (size_t)n * 3 * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&g->sorted, (size_t)n * sizeof(float4))) != cudaSuccess ||
+        (e = cudaMalloc(&g->tab, (g->ncell + 1) * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&code, (size_t)n * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&sums, (size_t)ntile * sizeof(uint32_t))) != cudaSuccess) {
+        cudaFree(code); cudaFree(sums);
+        dfb_grid_destroy(g);
+        return check_cuda(e, "dfb_grid_create allocations", __FILE__, __LINE__);
+    }
+    cudaMemcpyAsync(g->pts, d_points, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    cudaMemsetAsync(g->tab, 0, (g->ncell + 1) * sizeof(uint32_t), st);
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    count_kernel<<<nb, 256, 0, st>>>(g->pts, g->g, code, g->tab);
+    scan_tile_sums<<<(unsigned)ntile, kScanThreads, 0, st>>>(g->tab + 1, (long long)g->ncell, sums);
+    scan_sums_serial<<<1, 1024, 0, st>>>(sums, ntile);
+    scan_apply<<<(unsigned)ntile, kScanThreads, 0, st>>>(g->tab + 1, (long long)g->ncell, sums);
+    scatter_kernel<<<nb, 256, 0, st>>>(g->pts, (long long)n, code, g->tab, g->sorted);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(code);
+    cudaFree(sums);
+    if (e != cudaSuccess) {
+        dfb_grid_destroy(g);
+        return check_cuda(e, "dfb_grid_create build kernels", __FILE__, __LINE__);
+    }
+    *out = g;
+    return DFB_OK;
+}
+
+extern "C" int dfb_grid_destroy(dfb_grid* g) {
+    if (!g) return DFB_OK;
+    cudaFree(g->pts);
+    cudaFree(g->sorted);
+    cudaFree(g->tab);
+    delete g;
+    return DFB_OK;
+}
+
+extern "C" int dfb_knn(const dfb_grid* grid, const int32_t* d_query, int64_t q_begin, int64_t q_count, int32_t k,
+                       int32_t* d_idx, double* d_dist, double* d_rad, dfb_stream stream) {
+    using namespace dfb;
+    DFB_REQUIRE(grid != nullptr, DFB_E_ARG, "dfb_knn: grid is NULL");
+    DFB_REQUIRE(k >= 1 && k <= 1024 && (long long)k <= grid->g.n, DFB_E_ARG,
+                "dfb_knn: k=%d out of range (1..min(n=%lld,1024))", k, grid->g.n);
+    DFB_REQUIRE(q_count >= 0 && (q_count == 0 || d_idx != nullptr), DFB_E_ARG, "dfb_knn: bad output arguments");
+    DFB_REQUIRE(d_query != nullptr || (q_begin >= 0 && q_begin + q_count <= grid->g.n), DFB_E_ARG,
+                "dfb_knn: query range [%lld,%lld) outside the cloud", (long long)q_begin, (long long)(q_begin + q_count));
+    if (q_count == 0) return DFB_OK;
+    int kcap = 64;
+    while (kcap < 2 * k) kcap <<= 1;
+    KnnArgs a;
+    a.sorted = grid->sorted; a.tab = grid->tab; a.pts = grid->pts; a.g = grid->g;
+    a.query = d_query; a.q_begin = q_begin; a.q_count = q_count;
+    a.k = k; a.kcap = kcap;
+    a.out_idx = d_idx; a.out_dist = d_dist; a.out_rad = d_rad;
+    const size_t smem = (size_t)kKnnWarps * kcap * (sizeof(double) + sizeof(int));
+    static bool attr_set = false;
+    if (!attr_set) {
+        DFB_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    long long blocks = (q_count + kKnnWarps - 1) / kKnnWarps;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    knn_kernel<<<(unsigned)blocks, kKnnWarps * 32, smem, as_stream(stream)>>>(a);
+    return check_cuda(cudaGetLastError(), "knn_kernel launch", __FILE__, __LINE__);
+}

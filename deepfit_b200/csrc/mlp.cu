@@ -1,0 +1,972 @@
+// Stage 3: the point-weight network on the 5th-generation tensor cores (tcgen05 + TMEM + TMA bulk
+// copies), sm_100a only.
+//
+// Replaces DeepFit.forward up to the weights (reference models/DeepFit.py:301-316; PointNetFeatures
+// :180-208, PointNetEncoder :229-237, STN :353-380, QSTN :410-441; batch_quat_to_rotmat
+// utils/normal_estimation_utils.py:365-390) with eval-mode BatchNorm folded by the host.
+//
+// Operand format ("tiled"): every bf16 GEMM operand -- weights and the activations this pipeline
+// produces for itself -- lives in HBM in exactly the shared-memory image tcgen05.mma consumes:
+// 128-row x 64-column blocks of 16 KB, inside a block 8x8 "core matrices" of 128 contiguous bytes
+// ordered [k-chunk j][row-group i] (K-major, no swizzle: LBO = 2048 B between k-chunks, SBO = 128 B
+// between 8-row groups).  A block is therefore ONE contiguous 16 KB TMA bulk copy
+// (cp.async.bulk.shared.global + mbarrier complete_tx), needs no tensor map, and epilogue stores of
+// a warp (32 consecutive rows x 16 B) are 512 contiguous bytes.
+//
+// Precision: the 0.01 degree parity gate needs fp32-grade products (measured: plain bf16 is ~0.2 deg
+// off on the seeded network), so every operand is kept as a hi/lo bf16 pair (x = hi + lo, 16 mantissa
+// bits) and each k-step issues three MMAs (hi*hi + hi*lo + lo*hi) into the same fp32 TMEM accumulator
+// (DFB_PRECISION_BF16X3).  DFB_PRECISION_BF16 issues only hi*hi.
+//
+// Two orientations share one mainloop:
+//   N ("points are rows"): D[128 points, n] = X[128 x K] * W[n x K]^T, epilogue thread == point:
+//      bias (+per-patch bias), ReLU, re-split to hi/lo bf16, 16-byte stores in tiled format.
+//   T ("channels are rows"): D[128 channels, k points] = W * X^T, epilogue thread == channel:
+//      the max-pool over the patch's points is a register max over TMEM columns, so the
+//      [k,1024] activations of the three 128->1024 layers never leave the SM.
+#include "common.cuh"
+
+#include <cuda_bf16.h>
+
+#include <string.h>
+
+#include <vector>
+
+namespace dfb {
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int kBlkRows = 128;
+constexpr int kBlkCols = 64;
+constexpr int kBlkElems = kBlkRows * kBlkCols;  // 8192 bf16 = 16 KB
+constexpr int kBlkBytes = kBlkElems * 2;
+constexpr uint32_t kLBO = 2048;  // bytes between adjacent 16-byte k-chunks (core matrices along K)
+constexpr uint32_t kSBO = 128;   // bytes between adjacent 8-row groups (core matrices along M/N)
+
+__host__ __device__ __forceinline__ size_t tiled_offset(long long row, int col, int KB) {
+    // element offset of (row, col) inside a tiled matrix with KB 64-column blocks per row tile
+    const long long rt = row >> 7;
+    const int r = (int)(row & 127);
+    const int kb = col >> 6, c = col & 63;
+    return ((size_t)rt * KB + kb) * kBlkElems + (size_t)(c >> 3) * 1024 + (size_t)(r >> 3) * 64 + (size_t)(r & 7) * 8 + (c & 7);
+}
+
+// -------------------------------------------------------------------------------------------- PTX
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a pipeline bug must never hang the GPU.  Returns false (and records `code`) on time-out.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return true;
+        if (clock64() - t0 > (1LL << 31)) {
+            atomicCAS(err, 0, code);
+            return false;
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = (uint64_t)((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
+    return d;
+}
+// instruction descriptor, kind::f16: BF16 x BF16 -> F32, both operands K-major, M = 128
+__host__ __device__ __forceinline__ uint32_t umma_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack2(bf16 a, bf16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// ------------------------------------------------------------------------------------------ GEMM
+
+enum { EPI_ACT = 0, EPI_MAX = 1, EPI_T2 = 2, EPI_DOT = 3 };
+
+struct GemmArgs {
+    const bf16* A;       // tiled operand whose row tile is the MMA "M" side
+    const bf16* B;       // tiled operand providing the N side (NT row tiles per CTA)
+    size_t a_plane;      // element offset of the lo plane (hi at 0)
+    size_t b_plane;
+    int KB;              // 64-column k-blocks
+    int nprod;           // 1 (bf16) or 3 (hi*hi + hi*lo + lo*hi)
+    int n_mma;           // N of each UMMA (64 or 128)
+    int tmode;           // 0: N orientation (A = activations), 1: T orientation (A = weights)
+    int rows_per_patch;  // points per patch (N mode, activations) or 0 when rows are patches
+    long long b_patch_tiles;  // N mode: B row-tile offset per patch (per-patch B operand), else 0
+    const float* bias;   // N: per output column; T: per output row (channel)
+    long long bias_patch_stride;  // N mode: floats between per-patch bias vectors (0 = shared)
+    int relu;
+    long long m_valid;   // rows (N mode) / patches (T mode) that are real
+    int n_valid;         // valid output columns (N mode)
+    // outputs
+    bf16* out_t;         // tiled (hi plane), may be NULL
+    size_t out_plane;
+    int out_KB;
+    float* out_f;        // fp32 row-major, may be NULL
+    long long ldo;
+    // EPI_DOT
+    const float* w4;
+    float b4;
+    int weight_mode;
+    // EPI_T2
+    float* trans2;       // fp32 [patch,64,64], may be NULL
+    uint32_t lbo, sbo;   // descriptor strides (debug-switchable)
+    int* err;
+};
+
+constexpr int kGemmThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
+template <int NT, int EPI>
+__global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, const int stages) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_full[8], s_empty[8], s_done;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_bias[NT * 128];
+    __shared__ float s_w4[EPI == EPI_DOT ? 128 : 1];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int planes = g.nprod > 1 ? 2 : 1;
+    const uint32_t stage_bytes = (uint32_t)planes * (1 + NT) * kBlkBytes;
+    constexpr uint32_t kTmemCols = NT == 1 ? 128 : (NT == 2 ? 256 : 512);
+
+    // tile coordinates
+    long long a_tile, b_tile0, patch;
+    if (g.tmode) {
+        a_tile = blockIdx.x;                       // channel tile
+        patch = blockIdx.y;
+        b_tile0 = patch * NT;                      // the patch's NT activation row tiles
+    } else {
+        a_tile = blockIdx.x;                       // activation row tile
+        patch = g.rows_per_patch ? (a_tile * 128) / g.rows_per_patch : 0;
+        b_tile0 = (long long)blockIdx.y * NT + patch * g.b_patch_tiles;
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(&s_full[s]), 1);
+            mbar_init(smem_u32(&s_empty[s]), 1);
+        }
+        mbar_init(smem_u32(&s_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(&s_tmem), kTmemCols);
+        tmem_relinquish();
+    }
+    if (warp >= 2) {
+        const int t = threadIdx.x - 64;  // 0..127
+        if (!g.tmode) {
+            for (int c = t; c < NT * 128; c += 128) {
+                const long long col = (long long)blockIdx.y * NT * 128 + c;
+                s_bias[c] = (g.bias && col < g.n_valid) ? g.bias[patch * g.bias_patch_stride + col] : 0.f;
+            }
+        }
+        if (EPI == EPI_DOT) s_w4[t] = g.w4[t];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+    const uint32_t smem_base = smem_u32(smem);
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < g.KB; ++kb) {
+                const int s = kb % stages;
+                const uint32_t it = (uint32_t)(kb / stages);
+                if (!mbar_wait(smem_u32(&s_empty[s]), (it & 1u) ^ 1u, g.err, 1)) break;
+                const uint32_t full = smem_u32(&s_full[s]);
+                mbar_expect_tx(full, stage_bytes);
+                uint32_t dst = smem_base + (uint32_t)s * stage_bytes;
+                for (int pl = 0; pl < planes; ++pl) {
+                    bulk_g2s(dst, g.A + (size_t)pl * g.a_plane + ((size_t)a_tile * g.KB + kb) * kBlkElems, kBlkBytes, full);
+                    dst += kBlkBytes;
+                    for (int t = 0; t < NT; ++t) {
+                        bulk_g2s(dst, g.B + (size_t)pl * g.b_plane + ((size_t)(b_tile0 + t) * g.KB + kb) * kBlkElems,
+                                 kBlkBytes, full);
+                        dst += kBlkBytes;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(g.n_mma);
+            bool ok = true;
+            for (int kb = 0; kb < g.KB && ok; ++kb) {
+                const int s = kb % stages;
+                const uint32_t it = (uint32_t)(kb / stages);
+                ok = mbar_wait(smem_u32(&s_full[s]), it & 1u, g.err, 2);
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t sa_hi = smem_base + (uint32_t)s * stage_bytes;
+                const uint32_t sa_lo = sa_hi + (uint32_t)(1 + NT) * kBlkBytes;  // only valid when planes == 2
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const uint32_t sb_hi = sa_hi + (uint32_t)(1 + t) * kBlkBytes;
+                    const uint32_t sb_lo = sa_lo + (uint32_t)(1 + t) * kBlkBytes;
+                    const uint32_t d = tmem_base + (uint32_t)t * 128;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t koff = (uint32_t)ks * 2 * g.lbo;  // 16 elements = two 16-byte k-chunks
+                        const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+                        umma_bf16(d, umma_desc(sa_hi + koff, g.lbo, g.sbo), umma_desc(sb_hi + koff, g.lbo, g.sbo), idesc, first);
+                        if (g.nprod > 1) {
+                            umma_bf16(d, umma_desc(sa_hi + koff, g.lbo, g.sbo), umma_desc(sb_lo + koff, g.lbo, g.sbo), idesc, 1u);
+                            umma_bf16(d, umma_desc(sa_lo + koff, g.lbo, g.sbo), umma_desc(sb_hi + koff, g.lbo, g.sbo), idesc, 1u);
+                        }
+                    }
+                }
+                umma_commit(smem_u32(&s_empty[s]));  // frees the stage when these MMAs have read it
+            }
+            umma_commit(smem_u32(&s_done));  // accumulators complete
+        }
+    } else {
+        // ===================== epilogue (4 warps, one TMEM lane quadrant each) =====================
+        const int q = warp & 3;
+        const int lrow = q * 32 + lane;  // row of the 128-row accumulator tile owned by this thread
+        const bool ok = mbar_wait(smem_u32(&s_done), 0u, g.err, 3);
+        tc_fence_after();
+        if (ok) {
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+            uint32_t v[32];
+            if (EPI == EPI_MAX) {
+                float m = -3.402823466e38f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < NT * 128; c0 += 32) {
+                    tmem_ld32(tbase + (uint32_t)c0, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+                }
+                const long long ch = a_tile * 128 + lrow;
+                float r = m + (g.bias ? g.bias[ch] : 0.f);
+                if (g.relu) r = fmaxf(r, 0.f);
+                if (patch < g.m_valid) {
+                    if (g.out_f) g.out_f[patch * g.ldo + ch] = r;
+                    if (g.out_t) {
+                        bf16 hi, lo;
+                        split_bf16(r, hi, lo);
+                        const size_t o = tiled_offset(patch, (int)ch, g.out_KB);
+                        g.out_t[o] = hi;
+                        g.out_t[g.out_plane + o] = lo;
+                    }
+                }
+            } else {
+                const long long row = a_tile * 128 + lrow;
+                float dot = 0.f;
+#pragma unroll 1
+                for (int t = 0; t < NT; ++t) {
+#pragma unroll 1
+                    for (int c0 = 0; c0 < g.n_mma; c0 += 32) {
+                        tmem_ld32(tbase + (uint32_t)(t * 128 + c0), v);
+                        const int cl = t * 128 + c0;                                   // column inside the CTA
+                        const long long col0 = (long long)blockIdx.y * NT * 128 + cl;  // global output column
+                        float f[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float x = __uint_as_float(v[i]) + s_bias[cl + i];
+                            if (g.relu) x = fmaxf(x, 0.f);
+                            f[i] = x;
+                        }
+                        if (EPI == EPI_DOT) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) dot = fmaf(f[i], s_w4[cl + i], dot);
+                            continue;
+                        }
+                        if (col0 >= g.n_valid || row >= g.m_valid) continue;
+                        if (EPI == EPI_ACT) {
+                            if (g.out_t) {
+#pragma unroll
+                                for (int c8 = 0; c8 < 4; ++c8) {
+                                    uint32_t ph[4], plo[4];
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        bf16 h0, l0, h1, l1;
+                                        split_bf16(f[c8 * 8 + 2 * e], h0, l0);
+                                        split_bf16(f[c8 * 8 + 2 * e + 1], h1, l1);
+                                        ph[e] = pack2(h0, h1);
+                                        plo[e] = pack2(l0, l1);
+                                    }
+                                    const size_t o = tiled_offset(row, (int)col0 + c8 * 8, g.out_KB);
+                                    *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                                    if (g.nprod > 1)
+                                        *reinterpret_cast<uint4*>(g.out_t + g.out_plane + o) = make_uint4(plo[0], plo[1], plo[2], plo[3]);
+                                }
+                            }
+                            if (g.out_f) {
+                                float4* dstf = reinterpret_cast<float4*>(g.out_f + row * g.ldo + col0);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) dstf[e] = make_float4(f[4 * e], f[4 * e + 1], f[4 * e + 2], f[4 * e + 3]);
+                            }
+                        } else if (EPI == EPI_T2) {
+                            // output column = n*64 + kk (fc3 rows were permuted on the host): per-patch
+                            // B operand  T2^T[n][kk]  in tiled form, one 128-row block per patch
+#pragma unroll
+                            for (int c8 = 0; c8 < 4; ++c8) {
+                                const int col = (int)col0 + c8 * 8;
+                                const int n = col >> 6, kk = col & 63;
+                                uint32_t ph[4], plo[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    bf16 h0, l0, h1, l1;
+                                    split_bf16(f[c8 * 8 + 2 * e], h0, l0);
+                                    split_bf16(f[c8 * 8 + 2 * e + 1], h1, l1);
+                                    ph[e] = pack2(h0, h1);
+                                    plo[e] = pack2(l0, l1);
+                                }
+                                const size_t o = (size_t)row * kBlkElems + (size_t)(kk >> 3) * 1024 + (size_t)(n >> 3) * 64 + (size_t)(n & 7) * 8;
+                                *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                                if (g.nprod > 1)
+                                    *reinterpret_cast<uint4*>(g.out_t + g.out_plane + o) = make_uint4(plo[0], plo[1], plo[2], plo[3]);
+                                if (g.trans2) {
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) g.trans2[(size_t)row * 4096 + (size_t)(kk + e) * 64 + n] = f[c8 * 8 + e];
+                                }
+                            }
+                        }
+                    }
+                }
+                if (EPI == EPI_DOT && row < g.m_valid) {
+                    const float a = dot + g.b4;
+                    float w;
+                    if (g.weight_mode == DFB_WEIGHT_MODE_SIGMOID) w = 0.01f + 1.f / (1.f + expf(-a));
+                    else w = (0.01f + 1.f + tanhf(a)) * 0.5f;
+                    g.out_f[row] = w;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// --------------------------------------------------------------------------- small CUDA-core kernels
+
+// fp32 row-major [rows, cols] (ld) -> tiled hi/lo planes; rows/cols beyond the source are zero.
+__global__ void pack_tiled_kernel(const float* __restrict__ src, long long rows, int cols, long long ld,
+                                  long long rows_pad, int cols_pad, bf16* __restrict__ dst, size_t plane, int split) {
+    const long long total = rows_pad * (cols_pad / 8);
+    const int KB = cols_pad / 64;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i % rows_pad;  // consecutive threads -> consecutive rows -> contiguous 16 B chunks
+        const int c8 = (int)(i / rows_pad);
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float a = 0.f, b = 0.f;
+            const int c = c8 * 8 + 2 * e;
+            if (r < rows && c < cols) a = src[r * ld + c];
+            if (r < rows && c + 1 < cols) b = src[r * ld + c + 1];
+            bf16 h0, l0, h1, l1;
+            split_bf16(a, h0, l0);
+            split_bf16(b, h1, l1);
+            ph[e] = pack2(h0, h1);
+            pl[e] = pack2(l0, l1);
+        }
+        const size_t o = tiled_offset(r, c8 * 8, KB);
+        *reinterpret_cast<uint4*>(dst + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        if (split) *reinterpret_cast<uint4*>(dst + plane + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
+}
+
+// tiled (hi [+ lo]) -> fp32 row-major, for tests
+__global__ void unpack_tiled_kernel(const bf16* __restrict__ src, size_t plane, int split, long long rows, int cols,
+                                    int KB, float* __restrict__ dst) {
+    const long long total = rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols;
+        const int c = (int)(i % cols);
+        const size_t o = tiled_offset(r, c, KB);
+        float v = __bfloat162float(src[o]);
+        if (split) v += __bfloat162float(src[plane + o]);
+        dst[i] = v;
+    }
+}
+
+// K=3 first layers on CUDA cores: optional rotation P' = P R (DeepFit.py:188-190), then
+// relu(W p + b) for 64 channels, written as a tiled hi/lo operand.  One thread per point.
+__global__ void __launch_bounds__(128) pointwise3_kernel(const float* __restrict__ patch, const float* __restrict__ R,
+                                                         long long n_patch, int k, const float* __restrict__ W,
+                                                         const float* __restrict__ bvec, bf16* __restrict__ out,
+                                                         size_t plane, int split, float* __restrict__ pts_out) {
+    __shared__ float sW[64 * 3 + 64];
+    for (int i = threadIdx.x; i < 64 * 3; i += blockDim.x) sW[i] = W[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) sW[192 + i] = bvec[i];
+    __syncthreads();
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = n_patch * k;
+    if (row >= total) return;
+    const long long p = row / k;
+    const int j = (int)(row - p * k);
+    const float* base = patch + p * 3LL * k;
+    float x = base[j], y = base[k + j], z = base[2 * k + j];
+    if (R) {
+        const float* r = R + p * 9;
+        const float xr = fmaf(z, r[6], fmaf(y, r[3], x * r[0]));
+        const float yr = fmaf(z, r[7], fmaf(y, r[4], x * r[1]));
+        const float zr = fmaf(z, r[8], fmaf(y, r[5], x * r[2]));
+        x = xr; y = yr; z = zr;
+        if (pts_out) {
+            float* po = pts_out + p * 3LL * k;
+            po[j] = x; po[k + j] = y; po[2 * k + j] = z;
+        }
+    }
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float f[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int c = c8 * 8 + 2 * e + u;
+                float a = fmaf(sW[c * 3 + 2], z, fmaf(sW[c * 3 + 1], y, fmaf(sW[c * 3], x, sW[192 + c])));
+                f[u] = fmaxf(a, 0.f);
+            }
+            bf16 h0, l0, h1, l1;
+            split_bf16(f[0], h0, l0);
+            split_bf16(f[1], h1, l1);
+            ph[e] = pack2(h0, h1);
+            pl[e] = pack2(l0, l1);
+        }
+        const size_t o = tiled_offset(row, c8 * 8, 1);
+        *reinterpret_cast<uint4*>(out + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        if (split) *reinterpret_cast<uint4*>(out + plane + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
+}
+
+// QSTN tail: q = fc3(f) + (1,0,0,0); R = quat_to_rotmat(q)  (DeepFit.py:432-439,
+// utils/normal_estimation_utils.py:365-390).  One warp per patch.
+__global__ void quat_kernel(const float* __restrict__ f, long long n, const float* __restrict__ W, const float* __restrict__ b,
+                            float* __restrict__ R) {
+    const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (p >= n) return;
+    float q[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = lane; j < 256; j += 32) {
+        const float x = f[p * 256 + j];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) q[c] = fmaf(W[c * 256 + j], x, q[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) q[c] = warp_sum(q[c]) + b[c];
+    if (lane == 0) {
+        q[0] += 1.f;
+        const float s = 2.f / (q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        float* o = R + p * 9;
+        o[0] = 1.f - (q[2] * q[2] + q[3] * q[3]) * s;
+        o[1] = (q[1] * q[2] - q[3] * q[0]) * s;
+        o[2] = (q[1] * q[3] + q[2] * q[0]) * s;
+        o[3] = (q[1] * q[2] + q[3] * q[0]) * s;
+        o[4] = 1.f - (q[1] * q[1] + q[3] * q[3]) * s;
+        o[5] = (q[2] * q[3] - q[1] * q[0]) * s;
+        o[6] = (q[1] * q[3] - q[2] * q[0]) * s;
+        o[7] = (q[2] * q[3] + q[1] * q[0]) * s;
+        o[8] = 1.f - (q[1] * q[1] + q[2] * q[2]) * s;
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+
+int g_swap_lbo_sbo = 0;  // debug switch (dfb_dbg_set)
+
+template <int NT, int EPI>
+int launch_gemm_t(GemmArgs g, dim3 grid, cudaStream_t st) {
+    const int planes = g.nprod > 1 ? 2 : 1;
+    const size_t stage_bytes = (size_t)planes * (1 + NT) * kBlkBytes;
+    int stages = (int)((200 * 1024) / stage_bytes);
+    if (stages > g.KB) stages = g.KB;
+    if (stages > 8) stages = 8;
+    if (stages < 1) stages = 1;
+    const size_t smem = stages * stage_bytes;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return check_cuda(e, "gemm smem attribute", __FILE__, __LINE__);
+        attr_done = true;
+    }
+    g.lbo = g_swap_lbo_sbo ? kSBO : kLBO;
+    g.sbo = g_swap_lbo_sbo ? kLBO : kSBO;
+    gemm_kernel<NT, EPI><<<grid, kGemmThreads, smem, st>>>(g, stages);
+    return check_cuda(cudaGetLastError(), "gemm_kernel launch", __FILE__, __LINE__);
+}
+
+int launch_gemm(const GemmArgs& g, int NT, int epi, dim3 grid, cudaStream_t st) {
+#define DFB_CASE(nt, ep) if (NT == nt && epi == ep) return launch_gemm_t<nt, ep>(g, grid, st)
+    DFB_CASE(1, EPI_ACT); DFB_CASE(2, EPI_ACT);
+    DFB_CASE(1, EPI_MAX); DFB_CASE(2, EPI_MAX); DFB_CASE(3, EPI_MAX); DFB_CASE(4, EPI_MAX);
+    DFB_CASE(1, EPI_T2); DFB_CASE(1, EPI_DOT);
+#undef DFB_CASE
+    set_error("launch_gemm: unsupported configuration NT=%d epi=%d", NT, epi);
+    return DFB_E_INTERNAL;
+}
+
+struct TiledBuf {
+    bf16* p = nullptr;
+    size_t plane = 0;  // elements per plane
+    int KB = 0;
+    long long rows_pad = 0;
+};
+
+int alloc_tiled(TiledBuf& t, long long rows, int cols) {
+    t.rows_pad = (rows + 127) / 128 * 128;
+    t.KB = (cols + 63) / 64;
+    t.plane = (size_t)t.rows_pad * t.KB * 64;
+    DFB_CUDA(cudaMalloc(&t.p, t.plane * 2 * sizeof(bf16)));
+    return 0;
+}
+
+struct PackedLayer {
+    TiledBuf w;        // tiled weights [out_pad, in_pad]
+    float* bias = nullptr;  // device fp32 [out]
+    int in = 0, out = 0;
+};
+
+}  // namespace
+}  // namespace dfb
+
+struct dfb_model {
+    int k = 0, weight_mode = 0, nprod = 3, max_batch = 0;
+    float b4 = 0.f;  // conv4 bias
+    dfb::PackedLayer L[DFB_NUM_LAYERS];
+    dfb::PackedLayer head_global;  // HEAD_CONV1 columns 0..1023  (bias = folded conv1 bias)
+    dfb::PackedLayer head_point;   // HEAD_CONV1 columns 1024..1087 (no bias of its own)
+    float* w_small[DFB_NUM_LAYERS] = {nullptr};  // raw fp32 weights of the CUDA-core layers
+    // workspace
+    dfb::TiledBuf x64a, x64b, x64c, x128, h512, h256, gfeat, f512, f256, t2blk;
+    float* f256_f = nullptr;  // fp32 [max_batch,256]
+    float* hg = nullptr;      // fp32 [max_batch,512]
+    int* err = nullptr;       // device error flag
+    std::vector<void*> allocs;
+};
+
+namespace dfb {
+namespace {
+
+int upload_pack(const float* h_w, int out, int in, int col0, int ncols, long long ldw, PackedLayer& pl, cudaStream_t st,
+                const int* row_perm = nullptr) {
+    // host fp32 [out, ldw] (columns col0..col0+ncols) -> device tiled hi/lo
+    std::vector<float> tmp((size_t)out * ncols);
+    for (int r = 0; r < out; ++r) {
+        const int src = row_perm ? row_perm[r] : r;
+        for (int c = 0; c < ncols; ++c) tmp[(size_t)r * ncols + c] = h_w[(size_t)src * ldw + col0 + c];
+    }
+    float* d_tmp = nullptr;
+    DFB_CUDA(cudaMalloc(&d_tmp, tmp.size() * sizeof(float)));
+    DFB_CUDA(cudaMemcpyAsync(d_tmp, tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = alloc_tiled(pl.w, out, ncols);
+    if (rc) return rc;
+    pl.in = ncols;
+    pl.out = out;
+    const long long total = pl.w.rows_pad * (pl.w.KB * 8);
+    pack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_tmp, out, ncols, ncols, pl.w.rows_pad, pl.w.KB * 64,
+                                                                        pl.w.p, pl.w.plane, 1);
+    DFB_CUDA(cudaGetLastError());
+    DFB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_tmp);
+    return 0;
+}
+
+int upload_f32(const float* h, size_t n, float** d, cudaStream_t st) {
+    DFB_CUDA(cudaMalloc(d, n * sizeof(float)));
+    DFB_CUDA(cudaMemcpyAsync(*d, h, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    DFB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+GemmArgs base_args(const dfb_model* m) {
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.nprod = m->nprod;
+    g.n_mma = 128;
+    g.err = m->err;
+    g.weight_mode = m->weight_mode;
+    g.b4 = m->b4;
+    return g;
+}
+
+// N orientation: out = act(X W^T + b).  X tiled [rows, K], rows = n_rows (multiple of 128 in storage).
+int gemm_n(const dfb_model* m, const TiledBuf& X, long long n_rows, const PackedLayer& W, int relu, TiledBuf* out,
+           float* out_f, long long ldo, int rows_per_patch, const float* bias_override, long long bias_patch_stride,
+           cudaStream_t st, int epi = EPI_ACT, const TiledBuf* perpatch_B = nullptr, float* trans2 = nullptr) {
+    GemmArgs g = base_args(m);
+    g.A = X.p; g.a_plane = X.plane; g.KB = X.KB;
+    if (perpatch_B) {
+        g.B = perpatch_B->p; g.b_plane = perpatch_B->plane; g.b_patch_tiles = 1;
+    } else {
+        g.B = W.w.p; g.b_plane = W.w.plane;
+    }
+    g.tmode = 0;
+    g.rows_per_patch = rows_per_patch;
+    g.bias = bias_override ? bias_override : W.bias;
+    g.bias_patch_stride = bias_patch_stride;
+    g.relu = relu;
+    g.m_valid = n_rows;
+    const int n_out = perpatch_B ? 64 : W.out;
+    g.n_valid = n_out;
+    g.n_mma = n_out < 128 ? 64 : 128;
+    if (out) { g.out_t = out->p; g.out_plane = out->plane; g.out_KB = out->KB; }
+    g.out_f = out_f; g.ldo = ldo;
+    g.trans2 = trans2;
+    if (epi == EPI_DOT) { g.w4 = m->w_small[DFB_L_HEAD_CONV4]; }
+    const int col_tiles = (n_out + 127) / 128;
+    int NT = (epi == EPI_ACT && col_tiles % 2 == 0 && rows_per_patch != 0) ? 2 : 1;
+    dim3 grid((unsigned)((n_rows + 127) / 128), (unsigned)(col_tiles / NT));
+    return launch_gemm(g, NT, epi, grid, st);
+}
+
+// T orientation with fused max-pool: g[p, c] = act(max_j (W X_p^T)[c, j] + b[c])
+int gemm_t_max(const dfb_model* m, const PackedLayer& W, const TiledBuf& X, long long n_patch, int relu, TiledBuf* out,
+               float* out_f, cudaStream_t st) {
+    GemmArgs g = base_args(m);
+    g.A = W.w.p; g.a_plane = W.w.plane; g.KB = W.w.KB;
+    g.B = X.p; g.b_plane = X.plane;
+    g.tmode = 1;
+    g.bias = W.bias;
+    g.relu = relu;
+    g.m_valid = n_patch;
+    g.n_valid = W.out;
+    if (out) { g.out_t = out->p; g.out_plane = out->plane; g.out_KB = out->KB; }
+    g.out_f = out_f; g.ldo = W.out;
+    const int NT = m->k / 128;
+    dim3 grid((unsigned)(W.out / 128), (unsigned)n_patch);
+    return launch_gemm(g, NT, EPI_MAX, grid, st);
+}
+
+}  // namespace
+}  // namespace dfb
+
+extern "C" DFB_API int dfb_dbg_set(int key, int value) {
+    if (key == 0) dfb::g_swap_lbo_sbo = value;
+    return DFB_OK;
+}
+
+extern "C" int dfb_model_destroy(dfb_model* m) {
+    if (!m) return DFB_OK;
+    for (void* p : m->allocs) cudaFree(p);
+    delete m;
+    return DFB_OK;
+}
+
+extern "C" int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, dfb_model** out) {
+    using namespace dfb;
+    DFB_REQUIRE(desc && out, DFB_E_ARG, "dfb_model_create: NULL argument");
+    *out = nullptr;
+    DFB_REQUIRE(desc->k >= 128 && desc->k <= 512 && desc->k % 128 == 0, DFB_E_UNSUPPORTED,
+                "dfb_model_create: k=%d; the tensor-core path needs k in {128,256,384,512}", desc->k);
+    DFB_REQUIRE(desc->weight_mode == DFB_WEIGHT_MODE_SIGMOID || desc->weight_mode == DFB_WEIGHT_MODE_TANH, DFB_E_UNSUPPORTED,
+                "dfb_model_create: unsupported weight_mode %d", desc->weight_mode);
+    static const int expect[DFB_NUM_LAYERS][2] = {{3, 64},     {64, 128},  {128, 1024}, {1024, 512}, {512, 256}, {256, 4},
+                                                  {3, 64},     {64, 64},   {64, 64},    {64, 128},   {128, 1024}, {1024, 512},
+                                                  {512, 256},  {256, 4096}, {64, 128},  {128, 1024}, {1088, 512}, {512, 256},
+                                                  {256, 128},  {128, 1}};
+    for (int i = 0; i < DFB_NUM_LAYERS; ++i) {
+        DFB_REQUIRE(desc->layers[i].h_weight && desc->layers[i].h_bias, DFB_E_ARG, "dfb_model_create: layer %d has NULL data", i);
+        DFB_REQUIRE(desc->layers[i].in_features == expect[i][0] && desc->layers[i].out_features == expect[i][1], DFB_E_ARG,
+                    "dfb_model_create: layer %d is %dx%d, expected %dx%d", i, desc->layers[i].out_features,
+                    desc->layers[i].in_features, expect[i][1], expect[i][0]);
+    }
+    int rc = dfb_device_check();
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    dfb_model* m = new dfb_model();
+    m->k = desc->k;
+    m->weight_mode = desc->weight_mode;
+    m->nprod = desc->precision == DFB_PRECISION_BF16 ? 1 : 3;
+    m->max_batch = desc->max_batch > 0 ? (desc->max_batch + 127) / 128 * 128 : 1024;
+#define DFB_TRY(expr)                     \
+    do {                                  \
+        rc = (expr);                      \
+        if (rc) {                         \
+            dfb_model_destroy(m);         \
+            return rc;                    \
+        }                                 \
+    } while (0)
+    auto track = [&](void* p) { m->allocs.push_back(p); };
+    for (int i = 0; i < DFB_NUM_LAYERS; ++i) {
+        const dfb_layer& l = desc->layers[i];
+        DFB_TRY(upload_f32(l.h_bias, l.out_features, &m->L[i].bias, st));
+        track(m->L[i].bias);
+        m->L[i].in = l.in_features;
+        m->L[i].out = l.out_features;
+        const bool small = (i == DFB_L_QSTN_CONV1 || i == DFB_L_PF_CONV1 || i == DFB_L_QSTN_FC3 || i == DFB_L_HEAD_CONV4);
+        if (i == DFB_L_HEAD_CONV4) m->b4 = l.h_bias[0];
+        if (small) {
+            DFB_TRY(upload_f32(l.h_weight, (size_t)l.in_features * l.out_features, &m->w_small[i], st));
+            track(m->w_small[i]);
+        } else if (i == DFB_L_HEAD_CONV1) {
+            DFB_TRY(upload_pack(l.h_weight, 512, 1088, 0, 1024, 1088, m->head_global, st));
+            track(m->head_global.w.p);
+            DFB_TRY(upload_pack(l.h_weight, 512, 1088, 1024, 64, 1088, m->head_point, st));
+            track(m->head_point.w.p);
+            m->head_global.bias = m->L[i].bias;
+            m->head_point.bias = nullptr;
+        } else if (i == DFB_L_STN_FC3) {
+            // emit T2^T: output column n*64+kk takes the reference's row kk*64+n; +I is symmetric
+            std::vector<int> perm(4096);
+            std::vector<float> hb(4096);
+            for (int n = 0; n < 64; ++n)
+                for (int kk = 0; kk < 64; ++kk) {
+                    perm[n * 64 + kk] = kk * 64 + n;
+                    hb[n * 64 + kk] = l.h_bias[kk * 64 + n] + (n == kk ? 1.f : 0.f);
+                }
+            DFB_TRY(upload_pack(l.h_weight, 4096, 256, 0, 256, 256, m->L[i], st, perm.data()));
+            track(m->L[i].w.p);
+            DFB_TRY(check_cuda(cudaMemcpyAsync(m->L[i].bias, hb.data(), 4096 * sizeof(float), cudaMemcpyHostToDevice, st),
+                               "stn fc3 bias", __FILE__, __LINE__));
+            DFB_TRY(check_cuda(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__));
+        } else {
+            float* keep_bias = m->L[i].bias;
+            DFB_TRY(upload_pack(l.h_weight, l.out_features, l.in_features, 0, l.in_features, l.in_features, m->L[i], st));
+            m->L[i].bias = keep_bias;
+            track(m->L[i].w.p);
+        }
+    }
+    // workspace
+    const long long R = (long long)m->max_batch * m->k;
+    const long long Bp = m->max_batch;
+    TiledBuf* bufs[] = {&m->x64a, &m->x64b, &m->x64c, &m->x128, &m->h512, &m->h256};
+    const int widths[] = {64, 64, 64, 128, 512, 256};
+    for (int i = 0; i < 6; ++i) {
+        DFB_TRY(alloc_tiled(*bufs[i], R, widths[i]));
+        track(bufs[i]->p);
+    }
+    DFB_TRY(alloc_tiled(m->gfeat, Bp, 1024)); track(m->gfeat.p);
+    DFB_TRY(alloc_tiled(m->f512, Bp, 512)); track(m->f512.p);
+    DFB_TRY(alloc_tiled(m->f256, Bp, 256)); track(m->f256.p);
+    DFB_TRY(alloc_tiled(m->t2blk, Bp * 128, 64)); track(m->t2blk.p);
+    // padded rows of FC inputs and the unused half of each per-patch T2 block must be finite
+    DFB_TRY(check_cuda(cudaMemsetAsync(m->gfeat.p, 0, m->gfeat.plane * 2 * sizeof(bf16), st), "memset", __FILE__, __LINE__));
+    DFB_TRY(check_cuda(cudaMemsetAsync(m->f512.p, 0, m->f512.plane * 2 * sizeof(bf16), st), "memset", __FILE__, __LINE__));
+    DFB_TRY(check_cuda(cudaMemsetAsync(m->f256.p, 0, m->f256.plane * 2 * sizeof(bf16), st), "memset", __FILE__, __LINE__));
+    DFB_TRY(check_cuda(cudaMemsetAsync(m->t2blk.p, 0, m->t2blk.plane * 2 * sizeof(bf16), st), "memset", __FILE__, __LINE__));
+    DFB_TRY(check_cuda(cudaMalloc(&m->f256_f, (size_t)Bp * 256 * sizeof(float)), "malloc", __FILE__, __LINE__)); track(m->f256_f);
+    DFB_TRY(check_cuda(cudaMalloc(&m->hg, (size_t)Bp * 512 * sizeof(float)), "malloc", __FILE__, __LINE__)); track(m->hg);
+    DFB_TRY(check_cuda(cudaMalloc(&m->err, sizeof(int)), "malloc", __FILE__, __LINE__)); track(m->err);
+    DFB_TRY(check_cuda(cudaMemsetAsync(m->err, 0, sizeof(int), st), "memset", __FILE__, __LINE__));
+    DFB_TRY(check_cuda(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__));
+#undef DFB_TRY
+    *out = m;
+    return DFB_OK;
+}
+
+extern "C" int dfb_model_status(dfb_model* m, dfb_stream stream) {
+    using namespace dfb;
+    DFB_REQUIRE(m != nullptr, DFB_E_ARG, "dfb_model_status: NULL model");
+    int h = 0;
+    DFB_CUDA(cudaMemcpyAsync(&h, m->err, sizeof(int), cudaMemcpyDeviceToHost, as_stream(stream)));
+    DFB_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    if (h != 0) {
+        set_error("tensor-core pipeline time-out (mbarrier wait, role %d)", h);
+        return DFB_E_INTERNAL;
+    }
+    return DFB_OK;
+}
+
+extern "C" int dfb_model_forward(dfb_model* m, const float* d_patch, int64_t n, float* d_weights, float* d_trans,
+                                 float* d_trans2, float* d_points_rot, dfb_stream stream) {
+    using namespace dfb;
+    DFB_REQUIRE(m != nullptr, DFB_E_ARG, "dfb_model_forward: NULL model");
+    DFB_REQUIRE(n >= 0, DFB_E_ARG, "dfb_model_forward: negative n");
+    if (n == 0) return DFB_OK;
+    DFB_REQUIRE(d_patch && d_weights && d_trans, DFB_E_ARG, "dfb_model_forward: NULL pointer argument");
+    cudaStream_t st = as_stream(stream);
+    const int k = m->k;
+    const int split = m->nprod > 1 ? 1 : 0;
+    int rc;
+#define DFB_RUN(expr)       \
+    do {                    \
+        rc = (expr);        \
+        if (rc) return rc;  \
+    } while (0)
+    for (int64_t s = 0; s < n; s += m->max_batch) {
+        const long long B = (n - s < m->max_batch) ? (n - s) : m->max_batch;
+        const long long rows = B * k;
+        const float* patch = d_patch + s * 3LL * k;
+        float* trans = d_trans + s * 9;
+        const unsigned pw_blocks = (unsigned)((rows + 127) / 128);
+
+        // ---- QSTN (DeepFit.py:410-441) ----
+        pointwise3_kernel<<<pw_blocks, 128, 0, st>>>(patch, nullptr, B, k, m->w_small[DFB_L_QSTN_CONV1], m->L[DFB_L_QSTN_CONV1].bias,
+                                                     m->x64a.p, m->x64a.plane, split, nullptr);
+        DFB_RUN(gemm_n(m, m->x64a, rows, m->L[DFB_L_QSTN_CONV2], 1, &m->x128, nullptr, 0, k, nullptr, 0, st));
+        DFB_RUN(gemm_t_max(m, m->L[DFB_L_QSTN_CONV3], m->x128, B, 1, &m->gfeat, nullptr, st));
+        DFB_RUN(gemm_n(m, m->gfeat, B, m->L[DFB_L_QSTN_FC1], 1, &m->f512, nullptr, 0, 0, nullptr, 0, st));
+        DFB_RUN(gemm_n(m, m->f512, B, m->L[DFB_L_QSTN_FC2], 1, nullptr, m->f256_f, 256, 0, nullptr, 0, st));
+        quat_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(m->f256_f, B, m->w_small[DFB_L_QSTN_FC3], m->L[DFB_L_QSTN_FC3].bias, trans);
+
+        // ---- point features (DeepFit.py:188-197) ----
+        pointwise3_kernel<<<pw_blocks, 128, 0, st>>>(patch, trans, B, k, m->w_small[DFB_L_PF_CONV1], m->L[DFB_L_PF_CONV1].bias,
+                                                     m->x64a.p, m->x64a.plane, split,
+                                                     d_points_rot ? d_points_rot + s * 3LL * k : nullptr);
+        DFB_RUN(gemm_n(m, m->x64a, rows, m->L[DFB_L_PF_CONV2], 1, &m->x64b, nullptr, 0, k, nullptr, 0, st));
+
+        // ---- feature STN (DeepFit.py:353-380) ----
+        DFB_RUN(gemm_n(m, m->x64b, rows, m->L[DFB_L_STN_CONV1], 1, &m->x64c, nullptr, 0, k, nullptr, 0, st));
+        DFB_RUN(gemm_n(m, m->x64c, rows, m->L[DFB_L_STN_CONV2], 1, &m->x128, nullptr, 0, k, nullptr, 0, st));
+        DFB_RUN(gemm_t_max(m, m->L[DFB_L_STN_CONV3], m->x128, B, 1, &m->gfeat, nullptr, st));
+        DFB_RUN(gemm_n(m, m->gfeat, B, m->L[DFB_L_STN_FC1], 1, &m->f512, nullptr, 0, 0, nullptr, 0, st));
+        DFB_RUN(gemm_n(m, m->f512, B, m->L[DFB_L_STN_FC2], 1, &m->f256, nullptr, 0, 0, nullptr, 0, st));
+        DFB_RUN(gemm_n(m, m->f256, B, m->L[DFB_L_STN_FC3], 0, &m->t2blk, nullptr, 0, 0, nullptr, 0, st, EPI_T2, nullptr,
+                       d_trans2 ? d_trans2 + s * 4096 : nullptr));
+        // x' = x T2 (DeepFit.py:202-204): per-patch B operand
+        DFB_RUN(gemm_n(m, m->x64b, rows, m->head_point, 0, &m->x64c, nullptr, 0, k, nullptr, 0, st, EPI_ACT, &m->t2blk));
+
+        // ---- encoder (DeepFit.py:233-235) ----
+        DFB_RUN(gemm_n(m, m->x64c, rows, m->L[DFB_L_ENC_CONV2], 1, &m->x128, nullptr, 0, k, nullptr, 0, st));
+        DFB_RUN(gemm_t_max(m, m->L[DFB_L_ENC_CONV3], m->x128, B, 0, &m->gfeat, nullptr, st));
+
+        // ---- head (DeepFit.py:304-316): conv1 split into global (per patch) + point (per point) parts ----
+        DFB_RUN(gemm_n(m, m->gfeat, B, m->head_global, 0, nullptr, m->hg, 512, 0, nullptr, 0, st));
+        DFB_RUN(gemm_n(m, m->x64c, rows, m->head_point, 1, &m->h512, nullptr, 0, k, m->hg, 512, st));
+        DFB_RUN(gemm_n(m, m->h512, rows, m->L[DFB_L_HEAD_CONV2], 1, &m->h256, nullptr, 0, k, nullptr, 0, st));
+        DFB_RUN(gemm_n(m, m->h256, rows, m->L[DFB_L_HEAD_CONV3], 1, nullptr, d_weights + s * (long long)k, 0, k, nullptr, 0, st,
+                       EPI_DOT));
+        DFB_RUN(check_cuda(cudaGetLastError(), "model forward launches", __FILE__, __LINE__));
+    }
+#undef DFB_RUN
+    return DFB_OK;
+}
+
+// Test hook: unpack one workspace buffer of the last forward to fp32 row-major [rows, cols].
+// which: 0 x64a (pf conv1), 1 x64b (pf conv2), 2 x64c (x*T2), 3 x128 (enc conv2), 4 h512, 5 h256,
+//        6 gfeat, 7 f512, 8 f256
+extern "C" DFB_API int dfb_dbg_model_dump(dfb_model* m, int32_t which, int64_t rows, int32_t cols, float* d_out, dfb_stream stream) {
+    using namespace dfb;
+    DFB_REQUIRE(m && d_out, DFB_E_ARG, "dfb_dbg_model_dump: NULL argument");
+    TiledBuf* bufs[] = {&m->x64a, &m->x64b, &m->x64c, &m->x128, &m->h512, &m->h256, &m->gfeat, &m->f512, &m->f256};
+    DFB_REQUIRE(which >= 0 && which < 9, DFB_E_ARG, "dfb_dbg_model_dump: bad buffer id");
+    TiledBuf* t = bufs[which];
+    DFB_REQUIRE(rows <= t->rows_pad && cols <= t->KB * 64, DFB_E_ARG, "dfb_dbg_model_dump: shape exceeds the buffer");
+    const long long total = rows * (long long)cols;
+    unpack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(t->p, t->plane, m->nprod > 1, rows, cols, t->KB, d_out);
+    return check_cuda(cudaGetLastError(), "unpack", __FILE__, __LINE__);
+}
+
+// Test hook: C[M,N] = A[M,K] B[N,K]^T (+bias, relu) through the tcgen05 kernel, fp32 row-major in/out.
+// mode 0: N orientation, EPI_ACT, out [M,N];  mode 1: T orientation + max over groups of k_pts rows of A... see tests.
+extern "C" DFB_API int dfb_dbg_gemm(const float* d_A, const float* d_B, const float* d_bias, int64_t M, int32_t N, int32_t K,
+                                    int32_t mode, int32_t nprod, int32_t relu, int32_t k_pts, float* d_out,
+                                    float* d_out_tiled_unpacked, dfb_stream stream) {
+    using namespace dfb;
+    int rc = dfb_device_check();
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    dfb_model fake;
+    fake.nprod = nprod;
+    fake.k = k_pts;
+    DFB_CUDA(cudaMalloc(&fake.err, sizeof(int)));
+    DFB_CUDA(cudaMemsetAsync(fake.err, 0, sizeof(int), st));
+    TiledBuf tA, tB, tO;
+    rc = alloc_tiled(tA, M, K); if (rc) return rc;
+    rc = alloc_tiled(tB, N, K); if (rc) return rc;
+    auto pack = [&](const float* src, long long rows, int cols, TiledBuf& t) {
+        const long long total = t.rows_pad * (t.KB * 8);
+        pack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, rows, cols, cols, t.rows_pad, t.KB * 64, t.p, t.plane, 1);
+    };
+    pack(d_A, M, K, tA);
+    pack(d_B, N, K, tB);
+    PackedLayer W;
+    W.bias = const_cast<float*>(d_bias);
+    if (mode == 0) {
+        W.w = tB; W.in = K; W.out = N;
+        rc = alloc_tiled(tO, M, N); if (rc) return rc;
+        cudaMemsetAsync(tO.p, 0, tO.plane * 2 * sizeof(bf16), st);
+        rc = gemm_n(&fake, tA, M, W, relu, &tO, d_out, N, k_pts, nullptr, 0, st);
+        if (rc == 0 && d_out_tiled_unpacked) {
+            const long long total = M * (long long)N;
+            unpack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tO.p, tO.plane, nprod > 1, M, N, tO.KB, d_out_tiled_unpacked);
+        }
+    } else {
+        // A = activations [M = n_patch*k_pts, K], B = weights [N, K]; out [n_patch, N]
+        W.w = tB; W.in = K; W.out = N;
+        const long long n_patch = M / k_pts;
+        rc = alloc_tiled(tO, n_patch, N); if (rc) return rc;
+        cudaMemsetAsync(tO.p, 0, tO.plane * 2 * sizeof(bf16), st);
+        rc = gemm_t_max(&fake, W, tA, n_patch, relu, &tO, d_out, st);
+        if (rc == 0 && d_out_tiled_unpacked) {
+            const long long total = n_patch * (long long)N;
+            unpack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tO.p, tO.plane, nprod > 1, n_patch, N, tO.KB, d_out_tiled_unpacked);
+        }
+    }
+    int h = 0;
+    cudaError_t e = cudaMemcpyAsync(&h, fake.err, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(tA.p); cudaFree(tB.p); cudaFree(tO.p); cudaFree(fake.err);
+    if (e != cudaSuccess) return check_cuda(e, "dfb_dbg_gemm", __FILE__, __LINE__);
+    if (rc) return rc;
+    if (h != 0) {
+        set_error("dfb_dbg_gemm: pipeline time-out, role %d", h);
+        return DFB_E_INTERNAL;
+    }
+    return DFB_OK;
+}

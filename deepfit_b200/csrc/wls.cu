@@ -1,0 +1,413 @@
+// Stage 4+5: weighted n-jet fit, normal and principal curvatures in one kernel.
+//
+// Replaces fit_Wjet / solve_linear_system (reference models/DeepFit.py:11-154), the normal at :88,
+// compute_principal_curvatures (tutorial/tutorial_utils.py:196-226) and the caller epilogue
+// (tutorial/compute_normals.py:67,79; test_n_est.py:154-161).
+//
+// Design (memory-bound stage, roofline = HBM): the normal matrix of a monomial basis is a moment
+// matrix, so instead of materialising the Vandermonde matrix A [k,M] (10 KB/patch) and the 55/120
+// upper-triangle entries of A^T W A, each point contributes to the (2n+1)(2n+2)/2 distinct moments
+// sum w x^a y^b (a+b <= 2n) and the (n+1)(n+2)/2 moments sum w z x^a y^b (a+b <= n).
+//   phase 1: 8 lanes per patch (4 patches per warp, 128-bit coalesced loads of the planar
+//            x/y/z/w rows), register accumulators, 3 xor-shuffle steps, totals parked in shared
+//            memory; 8 rounds fill 32 patch slots per warp.
+//   phase 2: one lane per patch: CGAL-style preconditioning applied to the moments, XtX/XtY
+//            assembled in the reference's column order, unblocked fp32 Cholesky + two triangular
+//            solves in registers, D_inv, normal, closed-form curvature on the upper triangle of
+//            -I^{-1} II (what torch.symeig(upper=True) sees), back-rotation by trans^T and U^T.
+#include "common.cuh"
+
+namespace dfb {
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kSlotStride = 65;  // floats per patch slot (62 used at order 4), odd => conflict-free
+
+template <int ORDER>
+struct Jet {
+    static constexpr int D = 2 * ORDER;
+    static constexpr int NM = (D + 1) * (D + 2) / 2;          // moments of w x^a y^b
+    static constexpr int NZ = (ORDER + 1) * (ORDER + 2) / 2;  // moments of w z x^a y^b
+    static constexpr int M = NZ;                              // unknowns
+    __host__ __device__ static constexpr int mi(int a, int b) { return a * (D + 1) - a * (a - 1) / 2 + b; }
+    __host__ __device__ static constexpr int zi(int a, int b) { return a * (ORDER + 1) - a * (a - 1) / 2 + b; }
+};
+
+// Column monomials (power of x, power of y) in the reference's column order, DeepFit.py:51-76.
+template <int ORDER>
+__device__ __forceinline__ constexpr int colx(int i) {
+    constexpr int8_t t[4][15] = {{1, 0, 0}, {1, 0, 2, 0, 1, 0}, {1, 0, 2, 0, 1, 3, 0, 2, 1, 0},
+                                 {1, 0, 2, 0, 1, 3, 0, 2, 1, 4, 0, 3, 1, 2, 0}};
+    return t[ORDER - 1][i];
+}
+template <int ORDER>
+__device__ __forceinline__ constexpr int coly(int i) {
+    constexpr int8_t t[4][15] = {{0, 1, 0}, {0, 1, 0, 2, 1, 0}, {0, 1, 0, 2, 1, 0, 3, 1, 2, 0},
+                                 {0, 1, 0, 2, 1, 0, 3, 1, 2, 0, 4, 1, 3, 2, 0}};
+    return t[ORDER - 1][i];
+}
+
+template <int ORDER>
+struct Acc {
+    float m[Jet<ORDER>::NM];
+    float zm[Jet<ORDER>::NZ];
+    float sax, say;  // sum |x|, sum |y|
+    float nvalid;    // number of weights > 1e-3
+};
+
+template <int ORDER>
+__device__ __forceinline__ void acc_point(Acc<ORDER>& A, float x, float y, float z, float w, float wraw) {
+    using J = Jet<ORDER>;
+    float xp[J::D + 1], yp[J::D + 1];
+    xp[0] = w;
+    yp[0] = 1.f;
+#pragma unroll
+    for (int a = 1; a <= J::D; ++a) {
+        xp[a] = xp[a - 1] * x;
+        yp[a] = yp[a - 1] * y;
+    }
+#pragma unroll
+    for (int a = 0; a <= J::D; ++a)
+#pragma unroll
+        for (int b = 0; b <= J::D - a; ++b) A.m[J::mi(a, b)] = fmaf(xp[a], yp[b], A.m[J::mi(a, b)]);
+#pragma unroll
+    for (int a = 0; a <= ORDER; ++a) {
+        const float xz = xp[a] * z;
+#pragma unroll
+        for (int b = 0; b <= ORDER - a; ++b) A.zm[J::zi(a, b)] = fmaf(xz, yp[b], A.zm[J::zi(a, b)]);
+    }
+    A.sax += fabsf(x);
+    A.say += fabsf(y);
+    A.nvalid += (wraw > 1e-3f) ? 1.f : 0.f;
+}
+
+__device__ __forceinline__ void rotate(const float* R, float& x, float& y, float& z) {
+    // row vector times matrix, reference DeepFit.py:188-190 (bmm(points^T, trans))
+    const float xr = fmaf(z, R[6], fmaf(y, R[3], x * R[0]));
+    const float yr = fmaf(z, R[7], fmaf(y, R[4], x * R[1]));
+    const float zr = fmaf(z, R[8], fmaf(y, R[5], x * R[2]));
+    x = xr; y = yr; z = zr;
+}
+
+// Accumulate one patch with the 8 lanes of a group.  sub = lane & 7.
+template <int ORDER>
+__device__ __forceinline__ void acc_patch(Acc<ORDER>& A, const float* __restrict__ px, const float* __restrict__ pw,
+                                          const float* R, int k, int sub, bool use_w) {
+#pragma unroll
+    for (int i = 0; i < Jet<ORDER>::NM; ++i) A.m[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < Jet<ORDER>::NZ; ++i) A.zm[i] = 0.f;
+    A.sax = A.say = A.nvalid = 0.f;
+    const float* py = px + k;
+    const float* pz = px + 2 * k;
+    if ((k & 3) == 0) {
+        const float4* x4 = reinterpret_cast<const float4*>(px);
+        const float4* y4 = reinterpret_cast<const float4*>(py);
+        const float4* z4 = reinterpret_cast<const float4*>(pz);
+        const float4* w4 = reinterpret_cast<const float4*>(pw);
+        for (int c = sub; c < (k >> 2); c += 8) {
+            float4 X = __ldg(x4 + c), Y = __ldg(y4 + c), Z = __ldg(z4 + c);
+            float4 W = pw ? __ldg(w4 + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+            if (R) {
+                rotate(R, X.x, Y.x, Z.x); rotate(R, X.y, Y.y, Z.y);
+                rotate(R, X.z, Y.z, Z.z); rotate(R, X.w, Y.w, Z.w);
+            }
+            acc_point<ORDER>(A, X.x, Y.x, Z.x, use_w ? W.x : 1.f, W.x);
+            acc_point<ORDER>(A, X.y, Y.y, Z.y, use_w ? W.y : 1.f, W.y);
+            acc_point<ORDER>(A, X.z, Y.z, Z.z, use_w ? W.z : 1.f, W.z);
+            acc_point<ORDER>(A, X.w, Y.w, Z.w, use_w ? W.w : 1.f, W.w);
+        }
+    } else {
+        for (int j = sub; j < k; j += 8) {
+            float x = __ldg(px + j), y = __ldg(py + j), z = __ldg(pz + j);
+            const float w = pw ? __ldg(pw + j) : 1.f;
+            if (R) rotate(R, x, y, z);
+            acc_point<ORDER>(A, x, y, z, use_w ? w : 1.f, w);
+        }
+    }
+}
+
+__device__ __forceinline__ float group8_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+
+template <int ORDER>
+__device__ __forceinline__ void reduce_store(Acc<ORDER>& A, float* slot, int sub) {
+    using J = Jet<ORDER>;
+#pragma unroll
+    for (int i = 0; i < J::NM; ++i) {
+        const float t = group8_sum(A.m[i]);
+        if ((i & 7) == sub) slot[i] = t;
+    }
+#pragma unroll
+    for (int i = 0; i < J::NZ; ++i) {
+        const float t = group8_sum(A.zm[i]);
+        if ((i & 7) == sub) slot[J::NM + i] = t;
+    }
+    A.sax = group8_sum(A.sax);
+    A.say = group8_sum(A.say);
+    A.nvalid = group8_sum(A.nvalid);
+    if (sub == 0) {
+        slot[J::NM + J::NZ] = A.sax;
+        slot[J::NM + J::NZ + 1] = A.say;
+    }
+}
+
+// In-register unblocked Cholesky (lower, packed) + forward/backward substitution.
+// Failure criterion as LAPACK spotrf: pivot <= 0 or NaN.
+template <int M>
+__device__ __forceinline__ bool chol_solve(float (&a)[M * (M + 1) / 2], float (&b)[M]) {
+#define LIDX(i, j) ((i) * ((i) + 1) / 2 + (j))
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        float d = a[LIDX(j, j)];
+#pragma unroll
+        for (int t = 0; t < j; ++t) d = fmaf(-a[LIDX(j, t)], a[LIDX(j, t)], d);
+        if (!(d > 0.f)) ok = false;
+        const float l = sqrtf(d);
+        const float inv = 1.f / l;
+        a[LIDX(j, j)] = l;
+#pragma unroll
+        for (int i = j + 1; i < M; ++i) {
+            float s = a[LIDX(i, j)];
+#pragma unroll
+            for (int t = 0; t < j; ++t) s = fmaf(-a[LIDX(i, t)], a[LIDX(j, t)], s);
+            a[LIDX(i, j)] = s * inv;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        float s = b[i];
+#pragma unroll
+        for (int t = 0; t < i; ++t) s = fmaf(-a[LIDX(i, t)], b[t], s);
+        b[i] = s / a[LIDX(i, i)];
+    }
+#pragma unroll
+    for (int i = M - 1; i >= 0; --i) {
+        float s = b[i];
+#pragma unroll
+        for (int t = i + 1; t < M; ++t) s = fmaf(-a[LIDX(t, i)], b[t], s);
+        b[i] = s / a[LIDX(i, i)];
+    }
+#undef LIDX
+    return ok;
+}
+
+__device__ __forceinline__ void curvature_from_beta(float b0f, float b1f, float b2f, float b3f, float b4f,
+                                                    float& k1, float& k2) {
+    // tutorial_utils.py:207-223.  M = -I^{-1} II is not symmetric; torch.symeig(upper=True) reads
+    // (M00, M01, M11) only.  Evaluated in fp64 and rounded once.
+    const double b0 = b0f, b1 = b1f, b2 = b2f, b3 = b3f, b4 = b4f;
+    const double E = 1.0 + b0 * b0, G = 1.0 + b1 * b1, F = b1 * b0;
+    const double nrm = sqrt(b0 * b0 + b1 * b1 + 1.0);
+    const double e = 2.0 * b2 / nrm, f = b4 / nrm, g = 2.0 * b3 / nrm;
+    const double det = E * G - F * F;
+    const double m00 = -(G * e - F * f) / det;
+    const double m01 = -(G * f - F * g) / det;
+    const double m11 = -(E * g - F * f) / det;
+    const double mid = 0.5 * (m00 + m11);
+    const double hd = 0.5 * (m00 - m11);
+    const double r = sqrt(hd * hd + m01 * m01);
+    k1 = static_cast<float>(mid - r);
+    k2 = static_cast<float>(mid + r);
+}
+
+struct WlsArgs {
+    const float* patch;
+    const float* weights;
+    const float* trans;
+    const float* U;
+    const double* rad;
+    long long n;
+    int k;
+    float* beta;
+    float* n_local;
+    float* n_world;
+    float* curv;
+    double* curv_scaled;
+    int* info;
+};
+
+template <int ORDER>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) wls_kernel(WlsArgs p) {
+    using J = Jet<ORDER>;
+    constexpr int M = J::M;
+    __shared__ float s_mom[kWarpsPerBlock][32][kSlotStride];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane >> 3, sub = lane & 7;
+    const long long n_super = (p.n + 31) / 32;  // groups of 32 patches, one per warp iteration
+
+    for (long long sp = (long long)blockIdx.x * kWarpsPerBlock + warp; sp < n_super;
+         sp += (long long)gridDim.x * kWarpsPerBlock) {
+        const long long base = sp * 32;
+        // ---------------- phase 1 ----------------
+        for (int round = 0; round < 8; ++round) {
+            long long pi = base + round * 4 + grp;
+            const bool live = pi < p.n;
+            if (!live) pi = p.n - 1;
+            const float* px = p.patch + pi * 3LL * p.k;
+            const float* pw = p.weights ? p.weights + pi * (long long)p.k : nullptr;
+            float R[9];
+            const bool has_R = p.trans != nullptr;
+            if (has_R) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) R[i] = __ldg(p.trans + pi * 9 + i);
+            }
+            Acc<ORDER> A;
+            acc_patch<ORDER>(A, px, pw, has_R ? R : nullptr, p.k, sub, true);
+            // zero-weight guard, DeepFit.py:37-39: weights -> 1 unless more than 18 exceed 1e-3
+            bool redo = false;
+            if (pw) redo = group8_sum(A.nvalid) <= 18.f;
+            if (__any_sync(0xffffffffu, redo)) acc_patch<ORDER>(A, px, pw, has_R ? R : nullptr, p.k, sub, !redo);
+            reduce_store<ORDER>(A, s_mom[warp][round * 4 + grp], sub);
+        }
+        __syncwarp();
+        // ---------------- phase 2 ----------------
+        const long long pi = base + lane;
+        if (pi < p.n) {
+            const float* slot = s_mom[warp][lane];
+            const float invk = 1.f / (float)p.k;
+            float h = 1.f;
+            if (ORDER > 1) {
+                // DeepFit.py:43-46
+                h = (slot[J::NM + J::NZ] * invk + slot[J::NM + J::NZ + 1] * invk) * 0.5f;
+                if (fabsf(h) < 1e-4f) h = 0.1f;
+            }
+            const float ih = 1.f / h;
+            float ihp[J::D + 1];
+            ihp[0] = 1.f;
+#pragma unroll
+            for (int a = 1; a <= J::D; ++a) ihp[a] = ihp[a - 1] * ih;
+
+            float beta[M];
+            int info = 0;
+#pragma unroll 1
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                float a[M * (M + 1) / 2];
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) {
+                        const int ax = colx<ORDER>(i) + colx<ORDER>(j), by = coly<ORDER>(i) + coly<ORDER>(j);
+                        float v = slot[J::mi(ax, by)] * ihp[ax + by];
+                        if (attempt == 1 && i == j) v *= 1.01f;
+                        a[i * (i + 1) / 2 + j] = v;
+                    }
+                    beta[i] = slot[J::NM + J::zi(colx<ORDER>(i), coly<ORDER>(i))] * ihp[colx<ORDER>(i) + coly<ORDER>(i)];
+                }
+                const bool ok = chol_solve<M>(a, beta);
+                if (ok) break;
+                info = attempt + 1;
+            }
+            if (info == 2) {
+#pragma unroll
+                for (int i = 0; i < M; ++i) beta[i] = 0.f;
+            }
+            // D_inv, DeepFit.py:85-86
+#pragma unroll
+            for (int i = 0; i < M; ++i) beta[i] *= ihp[colx<ORDER>(i) + coly<ORDER>(i)];
+
+            if (p.beta) {
+#pragma unroll
+                for (int i = 0; i < M; ++i) p.beta[pi * M + i] = beta[i];
+            }
+            // normal, DeepFit.py:88
+            const float inv_n = 1.f / fmaxf(sqrtf(fmaf(beta[0], beta[0], fmaf(beta[1], beta[1], 1.f))), 1e-12f);
+            const float nx = -beta[0] * inv_n, ny = -beta[1] * inv_n, nz = inv_n;
+            if (p.n_local) {
+                p.n_local[pi * 3 + 0] = nx; p.n_local[pi * 3 + 1] = ny; p.n_local[pi * 3 + 2] = nz;
+            }
+            if (p.n_world) {
+                float vx = nx, vy = ny, vz = nz;
+                if (p.trans) {  // n * trans^T  (test_n_est.py:154-157)
+                    const float* R = p.trans + pi * 9;
+                    const float tx = vx * R[0] + vy * R[1] + vz * R[2];
+                    const float ty = vx * R[3] + vy * R[4] + vz * R[5];
+                    const float tz = vx * R[6] + vy * R[7] + vz * R[8];
+                    vx = tx; vy = ty; vz = tz;
+                }
+                if (p.U) {  // n * U^T  (compute_normals.py:67)
+                    const float* U = p.U + pi * 9;
+                    const float tx = vx * U[0] + vy * U[1] + vz * U[2];
+                    const float ty = vx * U[3] + vy * U[4] + vz * U[5];
+                    const float tz = vx * U[6] + vy * U[7] + vz * U[8];
+                    vx = tx; vy = ty; vz = tz;
+                }
+                p.n_world[pi * 3 + 0] = vx; p.n_world[pi * 3 + 1] = vy; p.n_world[pi * 3 + 2] = vz;
+            }
+            if (ORDER > 1 && (p.curv || p.curv_scaled)) {
+                float k1, k2;
+                curvature_from_beta(beta[0], beta[1], beta[2], beta[3], beta[4], k1, k2);
+                if (p.curv) { p.curv[pi * 2] = k1; p.curv[pi * 2 + 1] = k2; }
+                if (p.curv_scaled) {
+                    const double r = p.rad ? p.rad[pi] : 1.0;  // fp32 / fp64 -> fp64, compute_normals.py:79
+                    p.curv_scaled[pi * 2] = (double)k1 / r;
+                    p.curv_scaled[pi * 2 + 1] = (double)k2 / r;
+                }
+            }
+            if (p.info) p.info[pi] = info;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void curvature_kernel(const float* __restrict__ beta, long long n, int m, float* __restrict__ curv) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* b = beta + i * m;
+    float k1, k2;
+    curvature_from_beta(b[0], b[1], b[2], b[3], b[4], k1, k2);
+    curv[i * 2] = k1;
+    curv[i * 2 + 1] = k2;
+}
+
+template <int ORDER>
+int launch_wls(const WlsArgs& a, cudaStream_t st) {
+    const long long n_super = (a.n + 31) / 32;
+    long long blocks = (n_super + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    wls_kernel<ORDER><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+    return check_cuda(cudaGetLastError(), "wls_kernel launch", __FILE__, __LINE__);
+}
+
+}  // namespace
+}  // namespace dfb
+
+extern "C" int dfb_wls_fit(const float* d_patch, const float* d_weights, const float* d_trans, const float* d_U,
+                           const double* d_rad, int64_t n, int32_t k, int32_t order, float* d_beta,
+                           float* d_n_local, float* d_n_world, float* d_curv, double* d_curv_scaled,
+                           int32_t* d_info, dfb_stream stream) {
+    using namespace dfb;
+    DFB_REQUIRE(order >= 1 && order <= 4, DFB_E_ARG, "Polynomial order unsupported, please use 1..4 (got %d)", order);
+    DFB_REQUIRE(n >= 0 && k >= 1, DFB_E_ARG, "dfb_wls_fit: bad sizes n=%lld k=%d", (long long)n, k);
+    DFB_REQUIRE(d_patch != nullptr || n == 0, DFB_E_ARG, "dfb_wls_fit: d_patch is NULL");
+    DFB_REQUIRE(order > 1 || (d_curv == nullptr && d_curv_scaled == nullptr), DFB_E_ARG,
+                "Can't compute curvatures for jet with order less than 2");
+    if (n == 0) return DFB_OK;
+    int rc = dfb_device_check();
+    if (rc) return rc;
+    WlsArgs a{d_patch, d_weights, d_trans, d_U, d_rad, (long long)n, k,
+              d_beta,  d_n_local, d_n_world, d_curv, d_curv_scaled, d_info};
+    switch (order) {
+        case 1: return launch_wls<1>(a, as_stream(stream));
+        case 2: return launch_wls<2>(a, as_stream(stream));
+        case 3: return launch_wls<3>(a, as_stream(stream));
+        default: return launch_wls<4>(a, as_stream(stream));
+    }
+}
+
+extern "C" int dfb_principal_curvatures(const float* d_beta, int64_t n, int32_t m, float* d_curv, dfb_stream stream) {
+    using namespace dfb;
+    DFB_REQUIRE(m >= 5, DFB_E_ARG, "Can't compute curvatures for jet with order less than 2");
+    DFB_REQUIRE(n >= 0 && (n == 0 || (d_beta && d_curv)), DFB_E_ARG, "dfb_principal_curvatures: bad arguments");
+    if (n == 0) return DFB_OK;
+    int rc = dfb_device_check();
+    if (rc) return rc;
+    curvature_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(d_beta, (long long)n, m, d_curv);
+    return check_cuda(cudaGetLastError(), "curvature_kernel launch", __FILE__, __LINE__);
+}

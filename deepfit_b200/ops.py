@@ -1,0 +1,210 @@
+"""Torch-facing wrappers of the C ABI: one function per stage, device tensors in, device tensors out.
+
+PyTorch owns the memory and the stream; every computation happens in ``libdeepfit_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+JET_M = {1: 3, 2: 6, 3: 10, 4: 15}
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor: deepfit_b200 has no CPU path" % name)
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t.contiguous()
+
+
+class Grid:
+    """Search structure over a cloud (replaces ``scipy.spatial.cKDTree(points, 10)``,
+    reference tutorial/tutorial_utils.py:16)."""
+
+    def __init__(self, points: torch.Tensor):
+        points = _chk(points, torch.float32, "points")
+        if points.dim() != 2 or points.shape[1] != 3:
+            raise ValueError("points must be [N,3]")
+        self.n = int(points.shape[0])
+        self.device = points.device
+        self._h = C.c_void_p()
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.dfb_grid_create(_p(points), self.n, _stream(self.device), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.load().dfb_grid_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+    def query(self, k: int, q_begin: int = 0, q_count: Optional[int] = None, query: Optional[torch.Tensor] = None,
+              return_dist: bool = False):
+        """kNN of points ``q_begin .. q_begin+q_count`` (or of the int32 index tensor ``query``).
+        Returns (idx i32 [Q,k], rad f64 [Q][, dist f64 [Q,k]])."""
+        if query is not None:
+            query = _chk(query, torch.int32, "query")
+            q_count = int(query.numel())
+        elif q_count is None:
+            q_count = self.n - q_begin
+        idx = torch.empty((q_count, k), dtype=torch.int32, device=self.device)
+        rad = torch.empty((q_count,), dtype=torch.float64, device=self.device)
+        dist = torch.empty((q_count, k), dtype=torch.float64, device=self.device) if return_dist else None
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().dfb_knn(self._h, _p(query), q_begin, q_count, k, _p(idx), _p(dist), _p(rad),
+                                           _stream(self.device)))
+        return (idx, rad, dist) if return_dist else (idx, rad)
+
+
+def patch_pca(points: torch.Tensor, idx: torch.Tensor, rad: Optional[torch.Tensor], q_begin: int = 0,
+              query: Optional[torch.Tensor] = None, scale: bool = True, pca: bool = True):
+    """(points[idx] - points[centre]) / rad, PCA-aligned.  Returns (patch f32 [Q,3,k], U f32 [Q,3,3])."""
+    points = _chk(points, torch.float32, "points")
+    idx = _chk(idx, torch.int32, "idx")
+    q, k = int(idx.shape[0]), int(idx.shape[1])
+    if rad is not None:
+        rad = _chk(rad, torch.float64, "rad")
+    if query is not None:
+        query = _chk(query, torch.int32, "query")
+    patch = torch.empty((q, 3, k), dtype=torch.float32, device=points.device)
+    U = torch.empty((q, 3, 3), dtype=torch.float32, device=points.device)
+    flags = (1 if scale else 0) | (0 if pca else 2)
+    with torch.cuda.device(points.device):
+        _lib.check(_lib.load().dfb_patch_pca(_p(points), int(points.shape[0]), _p(idx), _p(query), q_begin, q, k,
+                                             _p(rad), flags, _p(patch), _p(U), _stream(points.device)))
+    return patch, U
+
+
+def wls_fit(patch: torch.Tensor, weights: Optional[torch.Tensor], order: int, trans: Optional[torch.Tensor] = None,
+            U: Optional[torch.Tensor] = None, rad: Optional[torch.Tensor] = None, want_curv: bool = True):
+    """Fused weighted jet fit + normal + curvature.  Returns a dict of device tensors:
+    beta [n,M], n_local [n,3], n_world [n,3] (if U or trans given), curv [n,2] f32 and
+    curv_scaled [n,2] f64 (order >= 2), info [n] i32."""
+    patch = _chk(patch, torch.float32, "points")
+    if patch.dim() != 3 or patch.shape[1] != 3:
+        raise ValueError("points must be [B,3,k]")
+    if order not in JET_M:
+        raise ValueError("Polynomial order unsupported, please use 1 or 2 ")
+    n, k = int(patch.shape[0]), int(patch.shape[2])
+    dev = patch.device
+    if weights is not None:
+        weights = _chk(weights, torch.float32, "weights").reshape(n, k)
+    if trans is not None:
+        trans = _chk(trans, torch.float32, "trans")
+    if U is not None:
+        U = _chk(U, torch.float32, "U")
+    if rad is not None:
+        rad = _chk(rad, torch.float64, "rad")
+    out = {
+        "beta": torch.empty((n, JET_M[order]), dtype=torch.float32, device=dev),
+        "n_local": torch.empty((n, 3), dtype=torch.float32, device=dev),
+        "info": torch.empty((n,), dtype=torch.int32, device=dev),
+    }
+    if U is not None or trans is not None:
+        out["n_world"] = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    if order > 1 and want_curv:
+        out["curv"] = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        out["curv_scaled"] = torch.empty((n, 2), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().dfb_wls_fit(_p(patch), _p(weights), _p(trans), _p(U), _p(rad), n, k, order,
+                                           _p(out["beta"]), _p(out["n_local"]), _p(out.get("n_world")),
+                                           _p(out.get("curv")), _p(out.get("curv_scaled")), _p(out["info"]),
+                                           _stream(dev)))
+    return out
+
+
+def principal_curvatures(beta: torch.Tensor) -> torch.Tensor:
+    beta = _chk(beta, torch.float32, "beta")
+    if beta.dim() != 2 or beta.shape[1] < 5:
+        raise ValueError("Can't compute curvatures for jet with order less than 2")
+    curv = torch.empty((beta.shape[0], 2), dtype=torch.float32, device=beta.device)
+    with torch.cuda.device(beta.device):
+        _lib.check(_lib.load().dfb_principal_curvatures(_p(beta), int(beta.shape[0]), int(beta.shape[1]), _p(curv),
+                                                        _stream(beta.device)))
+    return curv
+
+
+class WeightNetwork:
+    """Device-resident, pre-packed weight network (stage 3).  ``layers`` is a list of
+    (weight fp32 [out,in], bias fp32 [out]) CPU tensors in ``_lib.LAYER_NAMES`` order, BN folded."""
+
+    def __init__(self, layers, k: int, weight_mode: str = "sigmoid", precision: str = "bf16x3", max_batch: int = 0,
+                 device=None):
+        if weight_mode not in _lib.WEIGHT_MODE:
+            raise NotImplementedError(
+                "weight_mode %r: the reference's softmax branch is a batch-axis softmax (models/DeepFit.py:310) "
+                "and is not reproduced" % weight_mode)
+        if precision not in _lib.PRECISION:
+            raise ValueError("precision must be one of %s" % sorted(_lib.PRECISION))
+        self.device = torch.device(device if device is not None else "cuda")
+        self.k = int(k)
+        desc = _lib.DfbModelDesc()
+        desc.k = self.k
+        desc.weight_mode = _lib.WEIGHT_MODE[weight_mode]
+        desc.precision = _lib.PRECISION[precision]
+        desc.max_batch = int(max_batch)
+        keep = []
+        assert len(layers) == _lib.DFB_NUM_LAYERS
+        for i, (w, b) in enumerate(layers):
+            w = w.detach().to("cpu", torch.float32).contiguous()
+            b = b.detach().to("cpu", torch.float32).contiguous()
+            keep.append((w, b))
+            desc.layers[i].h_weight = w.data_ptr()
+            desc.layers[i].h_bias = b.data_ptr()
+            desc.layers[i].out_features = int(w.shape[0])
+            desc.layers[i].in_features = int(w.shape[1])
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().dfb_model_create(C.byref(desc), _stream(self.device), C.byref(self._h)))
+        del keep
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.load().dfb_model_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def status(self):
+        """Synchronise and raise if any tensor-core pipeline of this network timed out."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().dfb_model_status(self._h, _stream(self.device)))
+
+    def forward(self, patch: torch.Tensor, want_trans2: bool = True, want_points: bool = False):
+        """patch f32 [n,3,k] -> (weights [n,k], trans [n,3,3], trans2 [n,64,64] | None, points_rot | None)."""
+        patch = _chk(patch, torch.float32, "points")
+        n, k = int(patch.shape[0]), int(patch.shape[2])
+        if k != self.k:
+            raise ValueError("this network was built for %d points per patch (MaxPool1d(num_points), reference "
+                             "models/DeepFit.py:336,395), got %d" % (self.k, k))
+        dev = patch.device
+        weights = torch.empty((n, k), dtype=torch.float32, device=dev)
+        trans = torch.empty((n, 3, 3), dtype=torch.float32, device=dev)
+        trans2 = torch.empty((n, 64, 64), dtype=torch.float32, device=dev) if want_trans2 else None
+        pts = torch.empty((n, 3, k), dtype=torch.float32, device=dev) if want_points else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().dfb_model_forward(self._h, _p(patch), n, _p(weights), _p(trans), _p(trans2), _p(pts),
+                                                     _stream(dev)))
+        return weights, trans, trans2, pts

@@ -1,0 +1,144 @@
+"""Whole-cloud hot path: kNN -> centre/scale/PCA -> (weight network) -> jet fit -> normal + curvature.
+
+This is the loop of the reference's ``tutorial/compute_normals.py:56-81`` without the DataLoader: the
+cloud and the grid stay resident in HBM, queries are processed in chunks of point indices, and no
+intermediate leaves the device.  ``shard_range`` / ``gather_outputs`` implement the multi-GPU
+contract: each rank owns a contiguous point-index range of the replicated cloud and a single
+all-gather assembles the outputs in file order.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from .DeepFit import DeepFit, fold_batchnorm
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous, balanced point-index range [begin, end) of ``rank`` (first n % world ranks get one more)."""
+    base, rem = divmod(int(n), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def shard_capacity(n: int, world: int) -> int:
+    return (int(n) + int(world) - 1) // int(world)
+
+
+class NormalEstimator:
+    """Device-resident estimator for one cloud.
+
+    points : CUDA float32 [N,3] (already normalised the way the caller wants -- the tutorial dataset
+             normalises to the unit sphere, the PCPNet loader does not)
+    mode   : 'classic' (unweighted jet, compute_normals.py:72) or 'DeepFit'
+    model  : a ``deepfit_b200.DeepFit.DeepFit`` (DeepFit mode)
+    cancel_qstn : undo the QSTN rotation on the normals like test_n_est.py:154-157 (True) or
+                  reproduce the tutorial script's omission (False, ``--ref-compat``)
+    """
+
+    def __init__(self, points: torch.Tensor, k: int, jet_order: int = 3, mode: str = "classic",
+                 model: Optional[DeepFit] = None, chunk: int = 0, cancel_qstn: bool = True):
+        if mode not in ("classic", "DeepFit"):
+            raise ValueError("mode must be 'classic' or 'DeepFit'")
+        if mode == "DeepFit" and model is None:
+            raise ValueError("DeepFit mode needs a model")
+        self.points = points.contiguous()
+        self.n = int(points.shape[0])
+        self.k = int(k)
+        self.order = int(model.jet_order if mode == "DeepFit" else jet_order)
+        self.mode = mode
+        self.model = model
+        self.cancel_qstn = cancel_qstn
+        self.grid = ops.Grid(self.points)
+        self.chunk = int(chunk) if chunk else (8192 if mode == "DeepFit" else 65536)
+        self.net = model._network(points.device) if mode == "DeepFit" else None
+
+    def rebuild_grid(self):
+        self.grid.close()
+        self.grid = ops.Grid(self.points)
+
+    def run(self, begin: int = 0, end: Optional[int] = None, out_normals: Optional[torch.Tensor] = None,
+            out_curv: Optional[torch.Tensor] = None, extras: Optional[dict] = None):
+        """Normals f32 [Q,3] and curvatures f64 [Q,2] (k1<=k2, divided by the patch radius) for point
+        indices [begin, end).  ``extras`` (a dict) receives lists of per-chunk beta / weights / trans
+        when given (config-3 style full outputs)."""
+        end = self.n if end is None else int(end)
+        q = end - begin
+        dev = self.points.device
+        normals = out_normals if out_normals is not None else torch.empty((q, 3), dtype=torch.float32, device=dev)
+        want_curv = self.order > 1
+        curv = out_curv if out_curv is not None else (
+            torch.empty((q, 2), dtype=torch.float64, device=dev) if want_curv else None)
+        for s in range(begin, end, self.chunk):
+            c = min(self.chunk, end - s)
+            idx, rad = self.grid.query(self.k, q_begin=s, q_count=c)
+            patch, U = ops.patch_pca(self.points, idx, rad, q_begin=s)
+            if self.mode == "DeepFit":
+                weights, trans, trans2, _ = self.net.forward(patch, want_trans2=extras is not None)
+                out = ops.wls_fit(patch, weights, self.order, trans=trans, U=U, rad=rad, want_curv=want_curv)
+                if not self.cancel_qstn:
+                    # tutorial/compute_normals.py:67 applies only U^T to the normal of the rotated frame
+                    out["n_world"] = torch.bmm(out["n_local"].unsqueeze(1), U.transpose(2, 1)).squeeze(1)
+            else:
+                weights = trans = trans2 = None
+                out = ops.wls_fit(patch, None, self.order, U=U, rad=rad, want_curv=want_curv)
+            normals[s - begin:s - begin + c] = out["n_world"]
+            if want_curv:
+                curv[s - begin:s - begin + c] = out["curv_scaled"]
+            if extras is not None:
+                extras.setdefault("beta", []).append(out["beta"])
+                extras.setdefault("info", []).append(out["info"])
+                extras.setdefault("rad", []).append(rad)
+                extras.setdefault("U", []).append(U)
+                if weights is not None:
+                    extras.setdefault("weights", []).append(weights)
+                    extras.setdefault("trans", []).append(trans)
+                    extras.setdefault("trans2", []).append(trans2)
+        return normals, curv
+
+
+def gather_outputs(local_normals: torch.Tensor, local_curv: Optional[torch.Tensor], n: int, rank: int, world: int):
+    """All-gather per-rank outputs (ranges from ``shard_range``) into file order on every rank.
+
+    One collective: normals (3 x f32) and curvatures (2 x f64) are packed into one f64 [cap,5] buffer
+    per rank (padded to the common capacity), gathered with ``all_gather_into_tensor`` (NCCL over
+    NVLink on GPUs, gloo in the CPU tests), then the ragged tail is dropped."""
+    import torch.distributed as dist
+
+    cap = shard_capacity(n, world)
+    dev = local_normals.device
+    cols = 5 if local_curv is not None else 3
+    buf = torch.zeros((cap, cols), dtype=torch.float64, device=dev)
+    m = local_normals.shape[0]
+    buf[:m, :3] = local_normals.double()  # exact: f32 -> f64 -> f32 round trip is lossless
+    if local_curv is not None:
+        buf[:m, 3:] = local_curv
+    if world == 1:
+        full = buf.unsqueeze(0)
+    else:
+        full = torch.empty((world, cap, cols), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(full.view(world * cap, cols), buf)
+    pieces = []
+    for r in range(world):
+        b, e = shard_range(n, r, world)
+        pieces.append(full[r, :e - b])
+    allv = torch.cat(pieces, 0)
+    normals = allv[:, :3].float()
+    curv = allv[:, 3:].contiguous() if local_curv is not None else None
+    return normals, curv
+
+
+def model_from_state_dict(state_dict, num_points: int, jet_order: int = 3, weight_mode: str = "sigmoid",
+                          precision: str = "bf16x3", device="cuda") -> DeepFit:
+    m = DeepFit(k=1, num_points=num_points, use_point_stn=True, use_feat_stn=True, point_tuple=1, sym_op="max",
+                arch="simple", jet_order=jet_order, weight_mode=weight_mode, precision=precision)
+    m.load_state_dict(state_dict)
+    m.to(device)
+    m.eval()
+    return m
+
+
+__all__ = ["NormalEstimator", "shard_range", "shard_capacity", "gather_outputs", "model_from_state_dict",
+           "fold_batchnorm"]

@@ -1,0 +1,187 @@
+/*
+ * deepfit_b200 -- C ABI of the B200-native (sm_100a) DeepFit inference hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The reference
+ * (sitzikbs/DeepFit, pure Python) has no FFI of its own; each entry point below replaces the
+ * Python/PyTorch function cited next to it (paths relative to the reference root), and is what a
+ * ctypes binding on the reference side would bind (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, negative = usage error (DFB_E_*), positive = CUDA
+ *     runtime error code; dfb_last_error_string() returns the thread-local message.
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller (the host side allocates
+ *     with torch); the library never frees caller memory.  h_* are host pointers.
+ *   - every call takes the CUDA stream to launch on and is asynchronous w.r.t. the host unless
+ *     stated otherwise.  Handles are immutable after creation except for their private workspace,
+ *     so one handle must not be used from two streams at once.
+ *   - there is no CPU fallback: without an sm_100 device the compute calls fail with DFB_E_NODEVICE.
+ */
+#ifndef DEEPFIT_B200_H_
+#define DEEPFIT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DFB_API __attribute__((visibility("default")))
+#else
+#define DFB_API
+#endif
+
+#define DFB_OK 0
+#define DFB_E_ARG (-1)          /* bad argument (null pointer, size out of range) */
+#define DFB_E_UNSUPPORTED (-2)  /* valid in the reference but not supported here (see message) */
+#define DFB_E_NODEVICE (-3)     /* no CUDA device of compute capability 10.x is current */
+#define DFB_E_INTERNAL (-4)     /* a kernel reported an internal fault (e.g. pipeline time-out) */
+
+typedef void* dfb_stream; /* cudaStream_t */
+typedef struct dfb_grid dfb_grid;
+typedef struct dfb_model dfb_model;
+
+DFB_API int dfb_abi_version(void);
+DFB_API const char* dfb_last_error_string(void);
+/* 0 when the current device is compute capability 10.x; DFB_E_NODEVICE otherwise. */
+DFB_API int dfb_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 1 -- neighbourhood search.
+ * Replaces scipy.spatial.cKDTree(points, 10) built at tutorial/tutorial_utils.py:16 (and
+ * dataset.py:32) and its per-point query(points[i], k) at tutorial/tutorial_utils.py:21
+ * (dataset.py:293).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Build the search structure (Morton-ordered multi-level uniform grid) over d_points f32[n,3].
+ * The points are copied (re-ordered) into the handle; d_points may be released afterwards.
+ * Synchronises the stream once (bounding box read-back). */
+DFB_API int dfb_grid_create(const float* d_points, int64_t n, dfb_stream stream, dfb_grid** out);
+DFB_API int dfb_grid_destroy(dfb_grid* grid);
+
+/* Exact k nearest neighbours of q_count query points.  Queries are points of the cloud:
+ * d_query == NULL -> point indices q_begin .. q_begin+q_count-1, else d_query[0..q_count) (q_begin ignored).
+ * Ranking key: (fp64 squared distance accumulated x->y->z on fp32 coordinates, point index),
+ * i.e. cKDTree's result after distance-then-index tie-breaking.
+ *   d_idx  i32[q_count,k]  neighbour indices, ascending by the key (the query itself first)
+ *   d_dist f64[q_count,k]  Euclidean distances sqrt(d2), may be NULL
+ *   d_rad  f64[q_count]    distance of the k-th neighbour (`rad = max(point_distances)`,
+ *                          tutorial_utils.py:22), may be NULL
+ * Requires 1 <= k <= min(n, 1024). */
+DFB_API int dfb_knn(const dfb_grid* grid, const int32_t* d_query, int64_t q_begin, int64_t q_count, int32_t k,
+            int32_t* d_idx, double* d_dist, double* d_rad, dfb_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 2 -- patch centring, scaling and PCA alignment.
+ * Replaces SinglePointCloudDataset.__getitem__ lines tutorial/tutorial_utils.py:23-30 and
+ * pca_points :35-57 (dataset.py:320-366 for the PCPNet loader).
+ *   patch = (points[idx] - points[centre]) / rad  (fp32), U = principal axes by descending
+ *   variance (sign: largest-magnitude component of each axis positive), output patch * U.
+ *   d_patch f32[q_count,3,k] (planar x-row, y-row, z-row: the reference's [B,3,k])
+ *   d_U     f32[q_count,3,3] (`trans`)
+ * flags: bit 0 = divide by rad (0: keep world scale, d_rad may be NULL); bit 1 = skip the PCA
+ * (U = identity, patch = centred/scaled points), the reference's use_pca=False.
+ * ------------------------------------------------------------------------------------------ */
+DFB_API int dfb_patch_pca(const float* d_points, int64_t n_points, const int32_t* d_idx, const int32_t* d_query,
+                  int64_t q_begin, int64_t q_count, int32_t k, const double* d_rad, int32_t flags,
+                  float* d_patch, float* d_U, dfb_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 3 -- the point-weight network (QSTN + feature STN + PointNet encoder + weight head).
+ * Replaces DeepFit.forward up to the weights, models/DeepFit.py:301-316 (PointNetFeatures
+ * :180-208, PointNetEncoder :229-237, STN :353-380, QSTN :410-441, batch_quat_to_rotmat
+ * utils/normal_estimation_utils.py:365-390), eval-mode BatchNorm folded into the preceding layer
+ * by the host.  arch='simple', use_point_stn=1, use_feat_stn=True, point_tuple=1, sym_op='max'.
+ * ------------------------------------------------------------------------------------------ */
+enum dfb_layer_id {
+    DFB_L_QSTN_CONV1 = 0, /* 3    -> 64   feat.pointfeat.stn1.conv1 + bn1 */
+    DFB_L_QSTN_CONV2,     /* 64   -> 128  ...conv2 + bn2 */
+    DFB_L_QSTN_CONV3,     /* 128  -> 1024 ...conv3 + bn3 */
+    DFB_L_QSTN_FC1,       /* 1024 -> 512  ...fc1 + bn4 */
+    DFB_L_QSTN_FC2,       /* 512  -> 256  ...fc2 + bn5 */
+    DFB_L_QSTN_FC3,       /* 256  -> 4    ...fc3 */
+    DFB_L_PF_CONV1,       /* 3    -> 64   feat.pointfeat.conv1 + bn1 */
+    DFB_L_PF_CONV2,       /* 64   -> 64   feat.pointfeat.conv2 + bn2 */
+    DFB_L_STN_CONV1,      /* 64   -> 64   feat.pointfeat.stn2.conv1 + bn1 */
+    DFB_L_STN_CONV2,      /* 64   -> 128 */
+    DFB_L_STN_CONV3,      /* 128  -> 1024 */
+    DFB_L_STN_FC1,        /* 1024 -> 512 */
+    DFB_L_STN_FC2,        /* 512  -> 256 */
+    DFB_L_STN_FC3,        /* 256  -> 4096 */
+    DFB_L_ENC_CONV2,      /* 64   -> 128  feat.conv2 + bn2 */
+    DFB_L_ENC_CONV3,      /* 128  -> 1024 feat.conv3 + bn3 (no ReLU) */
+    DFB_L_HEAD_CONV1,     /* 1088 -> 512  conv1 + bn1 (columns 0..1023 global feature, 1024..1087 point feature) */
+    DFB_L_HEAD_CONV2,     /* 512  -> 256  conv2 + bn2 */
+    DFB_L_HEAD_CONV3,     /* 256  -> 128  conv3 + bn3 */
+    DFB_L_HEAD_CONV4,     /* 128  -> 1    conv4 */
+    DFB_NUM_LAYERS
+};
+
+typedef struct dfb_layer {
+    const float* h_weight; /* HOST fp32 [out_features, in_features] row-major, BatchNorm already folded */
+    const float* h_bias;   /* HOST fp32 [out_features] */
+    int32_t in_features;
+    int32_t out_features;
+} dfb_layer;
+
+#define DFB_WEIGHT_MODE_SIGMOID 0 /* w = 0.01 + sigmoid(a)      models/DeepFit.py:316 */
+#define DFB_WEIGHT_MODE_TANH 1    /* w = (1.01 + tanh(a)) / 2   models/DeepFit.py:313-314 */
+
+#define DFB_PRECISION_BF16X3 0 /* error-compensated split-BF16 tensor-core MMA (3 products), fp32-grade */
+#define DFB_PRECISION_BF16 1   /* single BF16 product, fp32 accumulate: 3x fewer tensor ops, ~0.2 deg */
+
+typedef struct dfb_model_desc {
+    int32_t k;           /* points per patch == num_points of the reference constructor; 128, 256, 384 or 512 */
+    int32_t weight_mode; /* DFB_WEIGHT_MODE_* */
+    int32_t precision;   /* DFB_PRECISION_* */
+    int32_t max_batch;   /* patches per internal chunk (workspace is sized for it); 0 = default */
+    dfb_layer layers[DFB_NUM_LAYERS];
+} dfb_model_desc;
+
+/* Packs the weights into the tensor-core operand layout on the device and allocates the
+ * activation workspace.  Synchronous. */
+DFB_API int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, dfb_model** out);
+DFB_API int dfb_model_destroy(dfb_model* model);
+
+/* d_patch f32[n,3,k] -> d_weights f32[n,k], d_trans f32[n,3,3] (QSTN rotation `trans`),
+ * d_trans2 f32[n,64,64] (feature transform, may be NULL), d_points_rot f32[n,3,k] (patch * trans,
+ * the points the jet is fitted to, may be NULL). */
+DFB_API int dfb_model_forward(dfb_model* model, const float* d_patch, int64_t n, float* d_weights, float* d_trans,
+                      float* d_trans2, float* d_points_rot, dfb_stream stream);
+
+/* Synchronises the stream and reports whether any tensor-core pipeline of this model timed out
+ * (DFB_E_INTERNAL); kernels never spin forever on a barrier. */
+DFB_API int dfb_model_status(dfb_model* model, dfb_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 4+5 -- weighted n-jet fit, normal, principal curvatures.
+ * Replaces fit_Wjet + solve_linear_system (models/DeepFit.py:11-154), the normal at :88,
+ * compute_principal_curvatures (tutorial/tutorial_utils.py:196-226 == models/DeepFit.py:444-474)
+ * and the caller epilogue tutorial/compute_normals.py:67,79 / test_n_est.py:154-161.
+ *   d_patch   f32[n,3,k]  PCA-aligned patch
+ *   d_weights f32[n,k]    NULL = classic unweighted fit (compute_normals.py:72)
+ *   d_trans   f32[n,3,3]  NULL or the QSTN rotation: the jet is fitted to patch * trans and the
+ *                         world normal is rotated back by trans^T
+ *   d_U       f32[n,3,3]  NULL or the PCA frame: n_world = (n_local * trans^T) * U^T
+ *   d_rad     f64[n]      NULL or patch radius: curv_scaled = curv / rad (fp64, compute_normals.py:79)
+ * outputs (each may be NULL):
+ *   d_beta f32[n,M] (M = 3,6,10,15 for order 1..4), d_n_local f32[n,3], d_n_world f32[n,3],
+ *   d_curv f32[n,2] ascending (order >= 2 only), d_curv_scaled f64[n,2],
+ *   d_info i32[n]: 0 ok, 1 = Cholesky failed and the deterministic ridge (diag *= 1.01) was used,
+ *                  2 = ridge failed too (beta = 0).
+ * All n rows are solved (the reference leaves rows >= 16*floor(n/16) at zero, :129-133).
+ * ------------------------------------------------------------------------------------------ */
+DFB_API int dfb_wls_fit(const float* d_patch, const float* d_weights, const float* d_trans, const float* d_U,
+                const double* d_rad, int64_t n, int32_t k, int32_t order, float* d_beta, float* d_n_local,
+                float* d_n_world, float* d_curv, double* d_curv_scaled, int32_t* d_info, dfb_stream stream);
+
+/* Principal curvatures from jet coefficients alone (order >= 2): d_beta f32[n,M] -> d_curv f32[n,2].
+ * Replaces compute_principal_curvatures (tutorial/tutorial_utils.py:196-226). */
+DFB_API int dfb_principal_curvatures(const float* d_beta, int64_t n, int32_t m, float* d_curv, dfb_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPFIT_B200_H_ */

@@ -1,0 +1,75 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads, exports every symbol that
+include/deepfit_b200.h declares, and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "deepfit_b200.h")).read()
+    return sorted(set(re.findall(r"DFB_API\s+[\w\s\*]+?\b(dfb_\w+)\s*\(", text)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = declared_symbols()
+    for s in ["dfb_grid_create", "dfb_grid_destroy", "dfb_knn", "dfb_patch_pca", "dfb_model_create",
+              "dfb_model_forward", "dfb_model_destroy", "dfb_wls_fit", "dfb_principal_curvatures",
+              "dfb_last_error_string", "dfb_abi_version", "dfb_device_check"]:
+        assert s in syms
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from deepfit_b200 import _lib
+    lib = _lib.load()
+    raw = ctypes.CDLL(_lib.lib_path())
+    for s in declared_symbols():
+        assert hasattr(raw, s), "missing export %s" % s
+    assert lib.dfb_abi_version() == 1
+    assert sorted(_lib.EXPORTS) == declared_symbols()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from deepfit_b200 import _lib, ops
+    with pytest.raises(_lib.DeepFitB200Error):
+        _lib.require_device()
+    with pytest.raises(ValueError):
+        ops.wls_fit(torch.zeros(1, 3, 32), None, 2)      # CPU tensors are rejected, not silently computed
+    from deepfit_b200 import DeepFit as D
+    m = D.DeepFit(k=1, num_points=256, use_point_stn=True, use_feat_stn=True, jet_order=3, weight_mode="sigmoid")
+    with pytest.raises(ValueError):
+        m.forward(torch.zeros(1, 3, 256))
+
+
+def test_usage_errors_match_reference_conventions():
+    import torch
+    from deepfit_b200 import DeepFit as D
+    # reference: ValueError for an unsupported order (models/DeepFit.py:78) and for curvature with M < 5
+    with pytest.raises(ValueError):
+        D.fit_Wjet(torch.zeros(1, 3, 32), torch.ones(1, 32), order=7)
+    with pytest.raises(ValueError):
+        D.compute_principal_curvatures(torch.zeros(4, 3))
+    with pytest.raises(NotImplementedError):
+        D.DeepFit(k=1, num_points=256, use_point_stn=True, use_feat_stn=True, weight_mode="softmax")
+    with pytest.raises(NotImplementedError):
+        D.DeepFit(k=1, num_points=256, use_point_stn=True, use_feat_stn=True, arch="3dmfv")
+
+
+def test_state_dict_contract():
+    """125 entries, the reference's key set."""
+    from deepfit_b200 import DeepFit as D
+    from oracle import deepfit_oracle as O
+    m = D.DeepFit(k=1, num_points=256, use_point_stn=True, use_feat_stn=True, jet_order=3, weight_mode="sigmoid")
+    sd = O.seeded_state_dict(0)
+    assert len(sd) == 125
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    m.load_state_dict(sd, strict=True)
+    layers = D.fold_batchnorm(m.state_dict())
+    assert len(layers) == 20
+    assert tuple(layers[16][0].shape) == (512, 1088) and tuple(layers[13][0].shape) == (4096, 256)

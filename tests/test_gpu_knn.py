@@ -1,0 +1,133 @@
+"""Stage 1 parity (gpu): dfb_knn vs the reference's cKDTree output (golden, canonicalised) and vs the
+oracle's exact (fp64 d^2, index) brute force.  Bit-exact: indices and fp64 distances must be equal."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import CLOUD_NAMES
+
+pytestmark = pytest.mark.gpu
+
+
+def _normalize(raw):
+    from oracle import deepfit_oracle as O
+    return O.normalize_cloud(raw)[0]
+
+
+def _query(points_np, q_np, k):
+    from deepfit_b200 import ops
+    pts = torch.from_numpy(np.ascontiguousarray(points_np)).cuda()
+    grid = ops.Grid(pts)
+    idx, rad, dist = grid.query(k, query=torch.from_numpy(q_np.astype(np.int32)).cuda(), return_dist=True)
+    torch.cuda.synchronize()
+    return idx.cpu().numpy(), rad.cpu().numpy(), dist.cpu().numpy()
+
+
+def _assert_equal_mod_boundary_ties(idx, dist, ref_idx, ref_dist):
+    """cKDTree picks an arbitrary member of a tie group that straddles the k-th place, so the SET may
+    differ there; everything else, and every distance, must be identical."""
+    assert np.array_equal(dist, ref_dist), "distances differ: max |d| = %g" % np.abs(dist - ref_dist).max()
+    for r in range(idx.shape[0]):
+        if np.array_equal(idx[r], ref_idx[r]):
+            continue
+        bad = np.nonzero(idx[r] != ref_idx[r])[0]
+        assert np.all(dist[r][bad] == dist[r][-1]), "row %d differs away from the boundary tie group" % r
+
+
+@pytest.mark.parametrize("name", CLOUD_NAMES)
+def test_knn_matches_reference_ckdtree_golden(golden, clouds, name):
+    pts = _normalize(clouds[name])
+    q = golden[name + "/query"]
+    idx, rad, dist = _query(pts, q, 256)
+    _assert_equal_mod_boundary_ties(idx, dist, golden[name + "/knn_idx"], golden[name + "/knn_dist"])
+    assert np.array_equal(rad, golden[name + "/rad"])
+    idx, rad, dist = _query(pts, q[:8], 512)
+    _assert_equal_mod_boundary_ties(idx, dist, golden[name + "/knn512_idx"], golden[name + "/knn512_dist"])
+
+
+@pytest.mark.parametrize("name", CLOUD_NAMES)
+def test_knn_matches_oracle_bruteforce_exactly(clouds, name):
+    from oracle import deepfit_oracle as O
+    pts = _normalize(clouds[name])
+    rng = np.random.default_rng(5)
+    q = rng.choice(len(pts), 96, replace=False)
+    ref_idx, ref_dist = O.knn_bruteforce(pts, q, 256)
+    idx, rad, dist = _query(pts, q, 256)
+    assert np.array_equal(idx, ref_idx.astype(np.int32))
+    assert np.array_equal(dist, ref_dist)
+
+
+def _adversarial_clouds():
+    rng = np.random.default_rng(11)
+    g = np.stack(np.meshgrid(np.arange(16), np.arange(16), np.arange(16), indexing="ij"), -1).reshape(-1, 3)
+    yield "lattice_exact_ties", g.astype(np.float32) * 0.125, 27
+    base = rng.normal(size=(1500, 3)).astype(np.float32)
+    yield "triplicated_points", np.concatenate([base, base, base])[rng.permutation(4500)], 64
+    yield "uniform_volume_k17", rng.random((50000, 3)).astype(np.float32), 17
+    dense = rng.normal(scale=0.003, size=(30000, 3))
+    sparse = rng.normal(scale=1.0, size=(3000, 3))
+    yield "variable_density", np.concatenate([dense, sparse]).astype(np.float32), 256
+    yield "n_equals_k", rng.random((300, 3)).astype(np.float32), 300
+    yield "k1", rng.random((1000, 3)).astype(np.float32), 1
+    yield "planar_sheet", np.concatenate([rng.random((20000, 2)), np.zeros((20000, 1))], 1).astype(np.float32), 100
+    yield "collinear", np.stack([np.linspace(0, 1, 5000), np.zeros(5000), np.zeros(5000)], 1).astype(np.float32), 33
+    yield "k1024", rng.normal(size=(20000, 3)).astype(np.float32), 1024
+
+
+@pytest.mark.parametrize("case", list(_adversarial_clouds()), ids=lambda c: c[0])
+def test_knn_adversarial_exact(case):
+    from oracle import deepfit_oracle as O
+    _, pts, k = case
+    rng = np.random.default_rng(3)
+    q = rng.choice(len(pts), min(64, len(pts)), replace=False)
+    ref_idx, ref_dist = O.knn_bruteforce(pts, q, k)
+    idx, rad, dist = _query(pts, q, k)
+    assert np.array_equal(idx, ref_idx.astype(np.int32))
+    assert np.array_equal(dist, ref_dist)
+    assert np.array_equal(rad, ref_dist[:, -1])
+
+
+def test_knn_full_size_properties():
+    """1M-point synthetic torus (BASELINE config 2 shape): every query, size-independent properties, plus
+    256 random queries against an fp64 brute force evaluated with torch on the device."""
+    from deepfit_b200 import ops, synthetic
+    pts_np = synthetic.torus_cloud(1_000_000, seed=1234)
+    pts = torch.from_numpy(pts_np).cuda()
+    grid = ops.Grid(pts)
+    k = 256
+    n = pts.shape[0]
+    rng = np.random.default_rng(0)
+    sample = torch.from_numpy(rng.choice(n, 256, replace=False).astype(np.int64)).cuda()
+    ar = torch.arange(n, device="cuda")
+    for s in range(0, n, 250_000):
+        idx, rad, dist = grid.query(k, q_begin=s, q_count=250_000, return_dist=True)
+        assert bool((dist[:, 1:] >= dist[:, :-1]).all())                 # sorted
+        assert bool((dist[:, 0] == 0).all())                             # self (or a duplicate) first
+        assert bool((rad == dist[:, -1]).all())
+        assert int(idx.min()) >= 0 and int(idx.max()) < n
+        srt = torch.sort(idx.long(), dim=1)[0]
+        assert bool((srt[:, 1:] != srt[:, :-1]).all())                   # no repeated neighbour
+        # recompute the distances of the reported neighbours exactly
+        qp = pts[s:s + 250_000].double()
+        nb = pts[idx.long().reshape(-1)].double().reshape(-1, k, 3)
+        dx = nb[:, :, 0] - qp[:, None, 0]
+        d2 = dx * dx
+        dy = nb[:, :, 1] - qp[:, None, 1]
+        d2 = d2 + dy * dy
+        dz = nb[:, :, 2] - qp[:, None, 2]
+        d2 = d2 + dz * dz
+        assert bool((torch.sqrt(d2) == dist).all())
+        del nb, dx, dy, dz, d2
+    pd = pts.double()
+    idx, rad, dist = grid.query(k, query=sample.int(), return_dist=True)
+    for j in range(sample.numel()):
+        qv = pd[sample[j]]
+        dx = pd[:, 0] - qv[0]
+        d2 = dx * dx
+        dy = pd[:, 1] - qv[1]
+        d2 = d2 + dy * dy
+        dz = pd[:, 2] - qv[2]
+        d2 = d2 + dz * dz
+        val, order = torch.sort(d2, stable=True)                         # stable => ties by ascending index
+        assert bool((order[:k] == idx[j].long()).all()), "query %d" % j
+        assert bool((torch.sqrt(val[:k]) == dist[j]).all())

@@ -1,0 +1,220 @@
+"""Stage 2 and stage 4+5 parity (gpu) against the reference's own outputs (golden) and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import CLOUD_NAMES
+
+pytestmark = pytest.mark.gpu
+
+ANGLE_TOL_DEG = 0.01     # BASELINE.json north_star: unoriented normals within 0.01 degrees
+CURV_TOL = 1e-3          # curvatures within 1e-3 relative (rectified: |d| / max(|ref|, 1))
+
+
+def _cloud(clouds, name):
+    from oracle import deepfit_oracle as O
+    return O.normalize_cloud(clouds[name])[0]
+
+
+@pytest.mark.parametrize("name", CLOUD_NAMES)
+def test_centre_scale_bit_exact(golden, clouds, name):
+    """(p[idx] - p[i]) / rad in fp32 must reproduce tutorial_utils.py:23-27 bit for bit."""
+    from deepfit_b200 import ops
+    from oracle import deepfit_oracle as O
+    pts_np = _cloud(clouds, name)
+    q = golden[name + "/query"]
+    idx = golden[name + "/knn_idx"]
+    rad = golden[name + "/rad"]
+    pts = torch.from_numpy(pts_np).cuda()
+    patch, U = ops.patch_pca(pts, torch.from_numpy(idx).cuda(), torch.from_numpy(rad).cuda(),
+                             query=torch.from_numpy(q.astype(np.int32)).cuda(), pca=False)
+    patch = patch.cpu()
+    for j in range(len(q)):
+        ref = O.extract_patch(pts_np, int(q[j]), idx[j], rad[j]).t()
+        assert torch.equal(patch[j], ref), "patch %d" % j
+    assert torch.equal(U.cpu(), torch.eye(3).expand(len(q), 3, 3))
+
+
+@pytest.mark.parametrize("name", CLOUD_NAMES)
+def test_pca_matches_reference_modulo_sign(golden, clouds, name):
+    from deepfit_b200 import ops
+    pts_np = _cloud(clouds, name)
+    q = golden[name + "/query"]
+    idx = torch.from_numpy(golden[name + "/knn_idx"]).cuda()
+    rad = torch.from_numpy(golden[name + "/rad"]).cuda()
+    pts = torch.from_numpy(pts_np).cuda()
+    qd = torch.from_numpy(q.astype(np.int32)).cuda()
+    patch, U = ops.patch_pca(pts, idx, rad, query=qd)
+    raw, _ = ops.patch_pca(pts, idx, rad, query=qd, pca=False)
+    patch, U, raw = patch.cpu().double(), U.cpu().double(), raw.cpu().double()
+    # orthonormal frame, and the output is exactly the raw patch in that frame
+    eye = torch.eye(3, dtype=torch.float64)
+    assert (U.transpose(1, 2) @ U - eye).abs().max() < 1e-6
+    assert (torch.bmm(raw.transpose(1, 2), U).transpose(1, 2) - patch).abs().max() < 2e-6
+    # U diagonalises the covariance with descending eigenvalues
+    c = raw - raw.mean(2, keepdim=True)
+    cov = c @ c.transpose(1, 2)
+    D = U.transpose(1, 2) @ cov @ U
+    off = D - torch.diag_embed(torch.diagonal(D, dim1=1, dim2=2))
+    assert off.abs().max() < 1e-5 * cov.abs().max()
+    ev = torch.diagonal(D, dim1=1, dim2=2)
+    assert bool((ev[:, 0] >= ev[:, 1] - 1e-9).all() and (ev[:, 1] >= ev[:, 2] - 1e-9).all())
+    # against the reference's torch.svd frame, per-column sign free, where the spectrum is separated
+    Uref = torch.from_numpy(golden[name + "/U"]).double()
+    Pref = torch.from_numpy(golden[name + "/patch"]).double()
+    gap_ok = ((ev[:, 0] - ev[:, 1]) > 0.05 * ev[:, 0]) & ((ev[:, 1] - ev[:, 2]) > 0.05 * ev[:, 0])
+    assert int(gap_ok.sum()) >= len(q) // 4
+    s = torch.sign((U * Uref).sum(1))                                    # [Q,3]
+    assert ((U * s[:, None, :] - Uref).abs().amax((1, 2))[gap_ok]).max() < 2e-4
+    assert ((patch * s[:, :, None] - Pref).abs().amax((1, 2))[gap_ok]).max() < 2e-4
+    # sign convention: largest-magnitude component of each axis is positive
+    big = torch.gather(U, 1, U.abs().argmax(1, keepdim=True))
+    assert bool((big > 0).all())
+
+
+def _fit(P, w, order, **kw):
+    from deepfit_b200 import ops
+    out = ops.wls_fit(P.cuda(), None if w is None else w.cuda(), order, **kw)
+    torch.cuda.synchronize()
+    return {k: v.cpu() for k, v in out.items()}
+
+
+@pytest.mark.parametrize("name", CLOUD_NAMES)
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_classic_fit_matches_reference_golden(golden, name, order):
+    from oracle import deepfit_oracle as O
+    P = torch.from_numpy(golden[name + "/patch"][:32])
+    out = _fit(P, None, order)
+    ref_beta = golden["%s/fit%d_beta" % (name, order)]
+    ref_n = golden["%s/fit%d_n" % (name, order)]
+    ok = out["info"].numpy() == 0
+    assert ok.all()
+    ang = O.unoriented_angle_deg(out["n_local"].numpy(), ref_n)
+    assert ang.max() <= ANGLE_TOL_DEG, "max angular deviation %g deg" % ang.max()
+    scale = np.maximum(np.abs(ref_beta), 1.0)
+    assert (np.abs(out["beta"].numpy() - ref_beta) / scale).max() < (2e-3 if order < 4 else 2e-2)
+    if order > 1:
+        err = O.rectified_rel_err(out["curv"].numpy(), golden["%s/fit%d_curv" % (name, order)])
+        assert err.max() <= CURV_TOL, "max curvature error %g" % err.max()
+
+
+@pytest.mark.parametrize("name", CLOUD_NAMES)
+def test_weighted_fit_matches_reference_golden(golden, name):
+    from oracle import deepfit_oracle as O
+    P = torch.from_numpy(golden[name + "/patch"][:32])
+    w = torch.from_numpy(golden[name + "/wfit3_w"])
+    out = _fit(P, w, 3)
+    ang = O.unoriented_angle_deg(out["n_local"].numpy(), golden[name + "/wfit3_n"])
+    assert ang.max() <= ANGLE_TOL_DEG
+    ref_beta = golden[name + "/wfit3_beta"]
+    assert (np.abs(out["beta"].numpy() - ref_beta) / np.maximum(np.abs(ref_beta), 1.0)).max() < 2e-3
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_known_answer_polynomial_surface(order):
+    """z = A(x,y) beta exactly => the fit of the same order recovers beta (the reference's synthetic
+    n-jet fixture, tutorial_utils.py:59-193)."""
+    from oracle import deepfit_oracle as O
+    g = torch.Generator().manual_seed(order)
+    B, k = 37, 200                                   # not multiples of 32 / 128 on purpose
+    xy = torch.rand(B, 2, k, generator=g) * 1.6 - 0.8
+    M = len(O.JET_COLUMNS[order])
+    beta = torch.rand(B, M, generator=g) - 0.5
+    A = O.jet_design_matrix(xy[:, 0].double(), xy[:, 1].double(), order)
+    z = (A @ beta.double()[:, :, None]).squeeze(-1).float()
+    P = torch.cat([xy, z[:, None, :]], 1).contiguous()
+    out = _fit(P, None, order)
+    assert (out["beta"] - beta).abs().max() < (5e-4 if order < 4 else 5e-3)
+    n_true = torch.nn.functional.normalize(torch.cat([-beta[:, :2], torch.ones(B, 1)], 1), dim=1)
+    assert O.unoriented_angle_deg(out["n_local"].numpy(), n_true.numpy()).max() < 0.02
+
+
+def test_ragged_sizes_weights_and_guard():
+    from oracle import deepfit_oracle as O
+    g = torch.Generator().manual_seed(3)
+    for B, k in [(1, 32), (5, 50), (33, 64), (130, 256), (7, 19)]:
+        xy = torch.rand(B, 2, k, generator=g) * 2 - 1
+        z = 0.3 * xy[:, 0] ** 2 - 0.2 * xy[:, 0] * xy[:, 1] + 0.05 * torch.randn(B, k, generator=g)
+        P = torch.cat([xy, z[:, None, :]], 1).contiguous()
+        w = torch.rand(B, k, generator=g) + 0.05
+        ref_b, ref_n = O.fit_wjet(P, w, 2)
+        out = _fit(P, w, 2)
+        assert O.unoriented_angle_deg(out["n_local"].numpy(), ref_n.numpy()).max() < ANGLE_TOL_DEG
+        assert (out["beta"] - ref_b).abs().max() < 2e-3
+    # zero-weight guard (models/DeepFit.py:37-39): fewer than 19 weights above 1e-3 => unweighted fit
+    B, k = 6, 64
+    xy = torch.rand(B, 2, k, generator=g) * 2 - 1
+    z = 0.1 * xy[:, 0] + 0.2 * xy[:, 1] ** 2
+    P = torch.cat([xy, z[:, None, :]], 1).contiguous()
+    w = torch.full((B, k), 1e-4)
+    w[:, :18] = 0.7
+    a = _fit(P, w, 2)
+    b = _fit(P, None, 2)
+    assert torch.equal(a["beta"], b["beta"])
+    w[:, :19] = 0.7                                   # 19 valid weights: guard does not fire
+    c = _fit(P, w, 2)
+    ref_b, _ = O.fit_wjet(P, w, 2)
+    assert (c["beta"] - ref_b).abs().max() < 5e-3
+
+
+def test_rank_deficient_patch_is_flagged_not_nan():
+    P = torch.zeros(4, 3, 64)
+    P[:, 0] = torch.linspace(-1, 1, 64)               # all points on a line: XtX singular at order 2
+    out = _fit(P, None, 2)
+    assert bool((out["info"] != 0).all())
+    assert bool(torch.isfinite(out["beta"]).all())
+
+
+def test_rotation_frames_and_scaled_curvature():
+    """trans / U / rad arguments: fit on P*trans, n_world = (n trans^T) U^T, curv / rad in fp64."""
+    from oracle import deepfit_oracle as O
+    g = torch.Generator().manual_seed(9)
+    B, k = 40, 256
+    xy = torch.rand(B, 2, k, generator=g) * 2 - 1
+    z = 0.2 * xy[:, 0] ** 2 + 0.1 * xy[:, 1] ** 2 + 0.01 * torch.randn(B, k, generator=g)
+    P = torch.cat([xy, z[:, None, :]], 1).contiguous()
+    q = torch.randn(B, 4, generator=g) * 0.05 + torch.tensor([1.0, 0, 0, 0])
+    R = O.quat_to_rotmat(q)
+    U = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))[0].contiguous()
+    rad = (torch.rand(B, generator=g, dtype=torch.float64) * 0.05 + 0.01)
+    out = _fit(P, None, 3, trans=R.cuda(), U=U.cuda(), rad=rad.cuda())
+    Prot = torch.bmm(P.transpose(1, 2), R).transpose(1, 2).contiguous()
+    ref_b, ref_n = O.fit_wjet(Prot, torch.ones(B, k), 3)
+    ref_w = O.world_normals(ref_n, U, R)
+    assert O.unoriented_angle_deg(out["n_local"].numpy(), ref_n.numpy()).max() < ANGLE_TOL_DEG
+    assert O.unoriented_angle_deg(out["n_world"].numpy(), ref_w.numpy()).max() < ANGLE_TOL_DEG
+    ref_c = O.principal_curvatures(ref_b).double() / rad[:, None]
+    assert O.rectified_rel_err(out["curv_scaled"].numpy(), ref_c.numpy()).max() < CURV_TOL
+    assert out["curv_scaled"].dtype == torch.float64
+    assert torch.equal(out["curv_scaled"], out["curv"].double() / rad[:, None])
+
+
+def test_principal_curvatures_upper_triangle_semantics(golden):
+    """compute_principal_curvatures: eigenvalues of the UPPER triangle of -I^-1 II (torch.symeig default)."""
+    from deepfit_b200 import DeepFit as D
+    from oracle import deepfit_oracle as O
+    name = CLOUD_NAMES[0]
+    beta = torch.from_numpy(golden[name + "/fit3_beta"])
+    curv, dirs = D.compute_principal_curvatures(beta.cuda())
+    assert O.rectified_rel_err(curv.cpu().numpy(), golden[name + "/fit3_curv"]).max() < 1e-5
+    assert tuple(dirs.shape) == (beta.shape[0], 2, 3)
+    assert bool((dirs[:, :, 2] == 0).all())
+    g = torch.Generator().manual_seed(1)
+    b = torch.randn(1000, 10, generator=g)
+    c2 = D.compute_principal_curvatures(b.cuda())[0].cpu()
+    assert O.rectified_rel_err(c2.numpy(), O.principal_curvatures(b).numpy()).max() < 1e-4
+    assert bool((c2[:, 0] <= c2[:, 1]).all())
+
+
+def test_sphere_curvature_known_answer():
+    """Points on a sphere of radius R: |k1| = |k2| = 1/R in the units of the indexed cloud."""
+    from deepfit_b200 import synthetic
+    from deepfit_b200.pipeline import NormalEstimator
+    R = 2.5
+    pts = torch.from_numpy(synthetic.sphere_cloud(60000, seed=3, radius=R)).cuda()
+    est = NormalEstimator(pts, k=64, jet_order=2, mode="classic")
+    normals, curv = est.run(0, 4096)
+    p = pts[:4096] / R
+    cosang = (normals * p).sum(1).abs()
+    assert float(cosang.min()) > 1 - 1e-4
+    assert float((curv.abs() - 1.0 / R).abs().max()) < 0.02 / R

@@ -1,0 +1,85 @@
+"""End-to-end (gpu): the whole hot path through the drop-in API against the oracle, sharding
+equivalence, and the drop-in CLI's output files."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_classic_pipeline_vs_oracle_on_tutorial_cloud(clouds, tmp_path):
+    from deepfit_b200 import tutorial_utils as tu
+    from deepfit_b200.pipeline import NormalEstimator
+    from oracle import deepfit_oracle as O
+    raw = clouds["Boxy_smooth100k"]
+    ds = tu.SinglePointCloudDataset(raw, 256)
+    ref_pts, ref_bb = O.normalize_cloud(raw)
+    assert np.array_equal(ds.points, ref_pts) and ds.bbdiag == ref_bb
+    est = NormalEstimator(ds.points_gpu, 256, jet_order=3, mode="classic")
+    normals, curv = est.run()
+    torch.cuda.synchronize()
+    assert tuple(normals.shape) == (100000, 3) and tuple(curv.shape) == (100000, 2) and curv.dtype == torch.float64
+    rng = np.random.default_rng(2)
+    q = np.sort(rng.choice(100000, 512, replace=False))
+    ref = O.compute_normals(ref_pts, q, 256, 3, mode="classic")
+    ang = O.unoriented_angle_deg(normals.cpu().numpy()[q], ref["normals"])
+    assert ang.max() <= 0.01, "max angular deviation %g deg" % ang.max()
+    # the PCA z-axis sign is library-defined in the reference: (k1,k2) -> (-k2,-k1) when it flips
+    c = curv.cpu().numpy()[q]
+    flipped = np.stack([-c[:, 1], -c[:, 0]], 1)
+    e1 = O.rectified_rel_err(c, ref["curv"]).max(1)
+    e2 = O.rectified_rel_err(flipped, ref["curv"]).max(1)
+    assert np.minimum(e1, e2).max() <= 1e-3, "max curvature error %g" % np.minimum(e1, e2).max()
+    # sharding: two half ranges computed separately are bit-identical to the single run
+    n1, c1 = est.run(0, 50000)
+    n2, c2 = est.run(50000, 100000)
+    assert torch.equal(torch.cat([n1, n2]), normals) and torch.equal(torch.cat([c1, c2]), curv)
+    # dataset API contract (tutorial_utils.py:19-30)
+    patch, trans, rad = ds[int(q[0])]
+    assert tuple(patch.shape) == (3, 256) and tuple(trans.shape) == (3, 3) and isinstance(rad, float)
+    assert rad == ref["rad"][0] and len(ds) == 100000
+
+
+def test_deepfit_pipeline_vs_oracle(clouds):
+    """DeepFit mode end to end.  The network is fed OUR PCA frame, so the oracle runs the reference
+    algebra on our patches (the sign-alignment protocol of SURVEY.md section 8c)."""
+    from deepfit_b200 import ops
+    from deepfit_b200.pipeline import NormalEstimator, model_from_state_dict
+    from oracle import deepfit_oracle as O
+    raw = clouds["Boxy_smooth100k"]
+    pts_np = O.normalize_cloud(raw)[0]
+    pts = torch.from_numpy(pts_np).cuda()
+    sd = O.seeded_state_dict(0)
+    model = model_from_state_dict(sd, 256, 3, "sigmoid", "bf16x3")
+    est = NormalEstimator(pts, 256, mode="DeepFit", model=model, chunk=1024)
+    normals, curv = est.run(1000, 1000 + 1536)
+    est.net.status()
+    idx, rad = est.grid.query(256, q_begin=1000, q_count=1536)
+    patch, U = ops.patch_pca(pts, idx, rad, q_begin=1000)
+    with torch.no_grad():
+        n, beta, w, trans, t2, _ = O.deepfit_forward(sd, patch.cpu(), 3)
+        ref_n = O.world_normals(n, U.cpu(), trans).numpy()
+        ref_c = (O.principal_curvatures(beta).double() / rad.cpu()[:, None]).numpy()
+    ang = O.unoriented_angle_deg(normals.cpu().numpy(), ref_n)
+    assert ang.max() <= 0.01, "max angular deviation %g deg (p99 %g)" % (ang.max(), np.quantile(ang, 0.99))
+    err = O.rectified_rel_err(curv.cpu().numpy(), ref_c)
+    assert err.max() <= 1e-3, "max curvature error %g" % err.max()
+
+
+def test_cli_writes_reference_format(clouds, tmp_path):
+    from deepfit_b200 import compute_normals
+    raw = clouds["Boxy_smooth100k"][:20000]
+    inp = tmp_path / "mini.xyz"
+    np.savetxt(inp, raw, fmt="%.6f")
+    compute_normals.main(["--input", str(inp), "--output_path", str(tmp_path / "out"), "--mode", "classic",
+                          "--k_neighbors", "64", "--jet_order", "2"])
+    nrm = np.loadtxt(tmp_path / "out" / "mini.normals")
+    crv = np.loadtxt(tmp_path / "out" / "mini.curv")
+    assert nrm.shape == (20000, 3) and crv.shape == (20000, 2)
+    assert np.allclose(np.linalg.norm(nrm, axis=1), 1.0, atol=1e-5)
+    assert (crv[:, 0] <= crv[:, 1]).all()
+    with pytest.raises(ValueError):   # the reference dies the same way for order 1 (tutorial_utils.py:204-205)
+        compute_normals.main(["--input", str(inp), "--output_path", str(tmp_path / "o1"), "--mode", "classic",
+                              "--k_neighbors", "64", "--jet_order", "1"])
