@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- DeepFit hot path throughput on B200 (normals + curvatures per second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json metric "normals/sec (DeepFit jet-3, k=256)"): a synthetic analytic-surface
+cloud (noisy torus, seeded) of ``--points`` points PER GPU (weak scaling: N GPUs index an N-times larger,
+replicated cloud and each rank owns a contiguous point-index range), DeepFit mode, jet order 3, k=256,
+seeded synthetic state_dict (the pretrained blob is missing from the reference checkout), parity-grade
+precision (split-BF16 tensor-core MMA).  One step = grid build + kNN + centre/scale/PCA + weight network
++ weighted jet fit + normal/curvature for every point of the rank's range (+ one NCCL all-gather of
+the outputs when N > 1).
+
+Prints ONE JSON line (see the driver contract).  ``value`` is measured with the cloud resident in HBM;
+``e2e`` includes the pinned-host -> device copy of the cloud and the device -> host read of the outputs.
+``--impl reference`` times the CPU restatement of the reference path (oracle port: scipy cKDTree +
+torch CPU, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "normals_per_sec_deepfit_jet3_k256"
+UNIT = "points/s"
+K = 256
+ORDER = 3
+MLP_FLOP_PER_PATCH = 326.9e6          # algorithmic (split head), SURVEY.md section 8d
+MAX_LAYER_FLOP_PER_PATCH = 2.0 * 128 * 1024 * K   # one 128->1024 layer over k points
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_cloud(total_points: int) -> np.ndarray:
+    from deepfit_b200 import synthetic
+    from deepfit_b200.tutorial_utils import normalize_cloud
+    raw = synthetic.torus_cloud(total_points, seed=1234, noise=0.005)
+    return np.ascontiguousarray(normalize_cloud(raw)[0], dtype=np.float32)
+
+
+def cpu_reference_rate(points: np.ndarray, sample: int, seed: int = 0):
+    """The reference's CPU path (oracle port) on `sample` query points of the same cloud, all host threads."""
+    from oracle import deepfit_oracle as O
+    sd = O.seeded_state_dict(0)
+    rng = np.random.default_rng(seed)
+    q = np.sort(rng.choice(points.shape[0], sample, replace=False))
+    import scipy.spatial as spatial
+    t0 = time.perf_counter()
+    tree = spatial.cKDTree(points, 10)                      # tutorial_utils.py:16 (amortised over the cloud in reality)
+    t_tree = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        dist, idx = tree.query(points[q], k=K, workers=-1)
+        out_n = []
+        for s in range(0, sample, 256):
+            items = [O.dataset_item(points, int(c), K, idx[s + j], dist[s + j]) for j, c in enumerate(q[s:s + 256])]
+            P = torch.stack([it[0] for it in items])
+            U = torch.stack([it[1] for it in items])
+            n, beta, w, trans, t2, _ = O.deepfit_forward(sd, P, ORDER)
+            out_n.append(O.world_normals(n, U, trans))
+            O.principal_curvatures(beta)
+    dt = time.perf_counter() - t0
+    return sample / dt, dt, t_tree
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pts = make_cloud(args.points * args.gpus)
+    sample = args.ref_sample
+    for _ in range(args.warmup):
+        cpu_reference_rate(pts, min(sample, 256))
+    rates, t_total = [], 0.0
+    for i in range(args.steps):
+        r, dt, _ = cpu_reference_rate(pts, sample, seed=i)
+        rates.append(r)
+        t_total += dt
+    value = sample * args.steps / t_total
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DeepFit jet-3 k=256, synthetic noisy torus, %d points/GPU" % args.points,
+                   "sample": "%d query points per step" % sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d random query points per step of the %d-point cloud; cKDTree(workers=-1) + torch CPU "
+                                   "(%d threads), eval-mode forward, batch 256; tree build excluded" % (sample, pts.shape[0], cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=262144, help="points per GPU")
+    ap.add_argument("--precision", type=str, default="bf16x3")
+    ap.add_argument("--chunk", type=int, default=4096)
+    ap.add_argument("--ref-sample", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    from deepfit_b200 import ops
+    from deepfit_b200.pipeline import NormalEstimator, gather_outputs, model_from_state_dict, shard_range
+    from oracle import deepfit_oracle as O   # only for the seeded weights + the cpu_baseline leg
+
+    n_total = args.points * world
+    pts_host = torch.from_numpy(make_cloud(n_total)).pin_memory()
+    pts = pts_host.to(dev, non_blocking=True)
+    model = model_from_state_dict(O.seeded_state_dict(0), K, ORDER, "sigmoid", args.precision, dev)
+    est = NormalEstimator(pts, K, ORDER, "DeepFit", model, chunk=args.chunk)
+    begin, end = shard_range(n_total, rank, world)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stage_ms = {"grid": 0.0, "knn": 0.0, "pca": 0.0, "network": 0.0, "wls": 0.0, "gather": 0.0}
+
+    def step(timed: bool, e2e: bool):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        flush.zero_()
+        barrier()
+        ev[0].record()
+        cloud = pts_host.to(dev, non_blocking=True) if e2e else pts
+        if e2e:
+            est.points = cloud
+        est.rebuild_grid()
+        normals, curv = est.run(begin, end)
+        if world > 1:
+            normals, curv = gather_outputs(normals, curv, n_total, rank, world)
+        if e2e:
+            b, e = (begin, end)
+            hn = normals[b:e].cpu() if world > 1 else normals.cpu()
+            hc = curv[b:e].cpu() if world > 1 else curv.cpu()
+            del hn, hc
+        ev[1].record()
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1])
+
+    def timed_region(e2e: bool, steps: int):
+        total = 0.0
+        for _ in range(steps):
+            total += step(True, e2e)
+        t = torch.tensor([total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step(False, False)
+    est.net.status()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.launch_count(reset=True)
+    est.net.profile(True)
+    ms_total = timed_region(False, args.steps)
+    prof = est.net.profile_read()
+    est.net.profile(False)
+    launches = ops.launch_count(reset=True)
+    clocks = sampler.stop() if rank == 0 else None
+    value = n_total * args.steps / (ms_total * 1e-3)
+
+    # per-stage split (one extra, untimed-for-the-headline pass with events between stages)
+    def staged_pass():
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        torch.cuda.synchronize()
+        evs[0].record()
+        est.rebuild_grid()
+        evs[1].record()
+        c = min(args.chunk, end - begin)
+        idx, rad = est.grid.query(K, q_begin=begin, q_count=c)
+        evs[2].record()
+        patch, U = ops.patch_pca(pts, idx, rad, q_begin=begin)
+        evs[3].record()
+        w, trans, _, _ = est.net.forward(patch, want_trans2=False)
+        evs[4].record()
+        ops.wls_fit(patch, w, ORDER, trans=trans, U=U, rad=rad)
+        evs[5].record()
+        torch.cuda.synchronize()
+        names = ["grid_build_ms", "knn_ms", "pca_ms", "network_ms", "wls_ms"]
+        d = {n_: evs[i].elapsed_time(evs[i + 1]) for i, n_ in enumerate(names)}
+        d["chunk_points"] = c
+        return d
+    est.points = pts
+    stages = staged_pass()
+
+    e2e_ms = timed_region(True, max(1, min(args.steps, 2)))
+    e2e_steps = max(1, min(args.steps, 2))
+    e2e_value = n_total * e2e_steps / (e2e_ms * 1e-3)
+    est.points = pts
+
+    if rank == 0:
+        hbm, tf_burst, tf_sus, which = measured_peaks()
+        gm_ms, gm_n = prof["gemm_max_128x1024"]
+        patches_per_launch = min(args.chunk, end - begin)
+        # chunks may be ragged: use the exact patch count of the timed region
+        n_patches_timed = (end - begin) * args.steps
+        achieved = (3 * n_patches_timed * MAX_LAYER_FLOP_PER_PATCH) / (gm_ms * 1e-3) / 1e12 if gm_ms > 0 else None
+        net_ms = sum(v[0] for v in prof.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (split-bf16 tensor-core MMA, fp32 accumulate)" if args.precision == "bf16x3" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": "DeepFit jet-3 k=256 (BASELINE configs[0] shape on the config-2 synthetic surface): "
+                                   "noisy torus, %d points per GPU, seeded state_dict, all five stages incl. grid build"
+                                   % args.points,
+                       "points_total": n_total, "k": K, "jet_order": ORDER, "precision": args.precision,
+                       "chunk": args.chunk, "l2": "256 MiB flush buffer written before every step",
+                       "sharding": "contiguous point-index ranges, replicated cloud+grid, one all-gather"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n_total * 12),
+                    "d2h_bytes_per_step": int((end - begin) * (12 + 16))},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "gemm_kernel<2,EPI_MAX> (128->1024 + max-pool, 3 per forward)",
+                         "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s",
+                         "frac": (achieved / tf_sus) if achieved else None, "traffic": None,
+                         "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained" % which,
+                         "note": "achieved = algorithmic FLOPs (2*128*1024*k per patch per layer); bf16x3 executes 3x that on the tensor pipe",
+                         "launches": int(gm_n), "avg_launch_ms": gm_ms / gm_n if gm_n else None,
+                         "share_of_network": gm_ms / net_ms if net_ms else None,
+                         "network_tflops_algorithmic": (n_patches_timed * MLP_FLOP_PER_PATCH) / (net_ms * 1e-3) / 1e12 if net_ms else None},
+            "kernel_ms": {k_: round(v[0], 3) for k_, v in prof.items()},
+            "stages_one_chunk": stages,
+        }
+        if not args.no_cpu_baseline:
+            r, dt, t_tree = cpu_reference_rate(pts_host.numpy(), args.ref_sample)
+            line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "%d random query points of the same cloud in %.1f s; cKDTree(workers=-1) + torch CPU, "
+                                              "eval-mode forward, batch 256; tree build (%.2f s) excluded" % (args.ref_sample, dt, t_tree)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

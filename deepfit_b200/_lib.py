@@ -28,6 +28,7 @@ EXPORTS = [
     "dfb_grid_create", "dfb_grid_destroy", "dfb_knn",
     "dfb_patch_pca",
     "dfb_model_create", "dfb_model_destroy", "dfb_model_forward", "dfb_model_status",
+    "dfb_model_profile", "dfb_model_profile_read", "dfb_launch_count",
     "dfb_wls_fit", "dfb_principal_curvatures",
 ]
 
@@ -82,6 +83,9 @@ def load():
     lib.dfb_model_destroy.argtypes = [vp]
     lib.dfb_model_forward.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]
     lib.dfb_model_status.argtypes = [vp, vp]
+    lib.dfb_model_profile.argtypes = [vp, i32]
+    lib.dfb_model_profile_read.argtypes = [vp, vp, vp, i32, vp]
+    lib.dfb_launch_count.argtypes = [i32]
     lib.dfb_dbg_set.argtypes = [C.c_int, C.c_int]
     lib.dfb_dbg_gemm.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.dfb_dbg_gemm.restype = C.c_int
@@ -91,7 +95,9 @@ def load():
     lib.dfb_principal_curvatures.argtypes = [vp, i64, i32, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name != "dfb_last_error_string":
+        if name == "dfb_launch_count":
+            fn.restype = C.c_int64
+        elif name != "dfb_last_error_string":
             fn.restype = C.c_int
     if lib.dfb_abi_version() != 1:
         raise ImportError("deepfit_b200: ABI version mismatch in %s" % path)

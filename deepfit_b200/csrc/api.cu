@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace dfb {
@@ -15,12 +17,18 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+long long launches(bool reset);
+
 int check_cuda(cudaError_t e, const char* what, const char* file, int line) {
     if (e == cudaSuccess) return 0;
     const char* base = strrchr(file, '/');
     set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), base ? base + 1 : file, line, what);
     return (int)e;
 }
+
+static std::atomic<long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches(bool reset) { return reset ? g_launches.exchange(0) : g_launches.load(); }
 
 int sm_count() {
     static int cached = 0;
@@ -58,3 +66,5 @@ extern "C" int dfb_device_check(void) {
     }
     return DFB_OK;
 }
+
+extern "C" int64_t dfb_launch_count(int32_t reset) { return dfb::launches(reset != 0); }

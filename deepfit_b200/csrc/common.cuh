@@ -30,6 +30,10 @@ int check_cuda(cudaError_t e, const char* what, const char* file, int line);
         }                                                                     \
     } while (0)
 
+// Every kernel launch of the library is counted (dfb_launch_count) so callers can report how many
+// of OUR kernels ran in a timed region.
+void note_launch(int n = 1);
+
 // Number of SMs of the current device (cached per process).
 int sm_count();
 

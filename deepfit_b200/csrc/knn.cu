@@ -440,6 +440,7 @@ extern "C" int dfb_grid_create(const float* d_points, int64_t n, dfb_stream stre
     DFB_CUDA(cudaMemcpyAsync(d_bb, init, sizeof(init), cudaMemcpyHostToDevice, st));
     const int bb_blocks = (int)((n + 255) / 256 < (int64_t)sm_count() * 8 ? (n + 255) / 256 : (int64_t)sm_count() * 8);
     bbox_kernel<<<bb_blocks, 256, 0, st>>>(d_points, (long long)n, d_bb);
+    note_launch();
     unsigned hb[6];
     DFB_CUDA(cudaMemcpyAsync(hb, d_bb, sizeof(hb), cudaMemcpyDeviceToHost, st));
     DFB_CUDA(cudaStreamSynchronize(st));
@@ -488,6 +489,7 @@ extern "C" int dfb_grid_create(const float* d_points, int64_t n, dfb_stream stre
     scan_sums_serial<<<1, 1024, 0, st>>>(sums, ntile);
     scan_apply<<<(unsigned)ntile, kScanThreads, 0, st>>>(g->tab + 1, (long long)g->ncell, sums);
     scatter_kernel<<<nb, 256, 0, st>>>(g->pts, (long long)n, code, g->tab, g->sorted);
+    note_launch(5);
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(code);
@@ -536,5 +538,6 @@ extern "C" int dfb_knn(const dfb_grid* grid, const int32_t* d_query, int64_t q_b
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     knn_kernel<<<(unsigned)blocks, kKnnWarps * 32, smem, as_stream(stream)>>>(a);
+    note_launch();
     return check_cuda(cudaGetLastError(), "knn_kernel launch", __FILE__, __LINE__);
 }

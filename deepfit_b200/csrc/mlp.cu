@@ -557,6 +557,7 @@ int launch_gemm_t(GemmArgs g, dim3 grid, cudaStream_t st) {
     g.lbo = g_swap_lbo_sbo ? kSBO : kLBO;
     g.sbo = g_swap_lbo_sbo ? kLBO : kSBO;
     gemm_kernel<NT, EPI><<<grid, kGemmThreads, smem, st>>>(g, stages);
+    note_launch();
     return check_cuda(cudaGetLastError(), "gemm_kernel launch", __FILE__, __LINE__);
 }
 
@@ -607,7 +608,46 @@ struct dfb_model {
     float* hg = nullptr;      // fp32 [max_batch,512]
     int* err = nullptr;       // device error flag
     std::vector<void*> allocs;
+    // optional per-kernel-class timing
+    struct ProfRec { int cls; cudaEvent_t e0, e1; };
+    bool prof = false;
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
 };
+
+namespace dfb {
+namespace {
+struct ProfScope {
+    dfb_model* m;
+    int cls;
+    cudaStream_t st;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    static cudaEvent_t get(dfb_model* m) {
+        if (!m->pool.empty()) {
+            cudaEvent_t e = m->pool.back();
+            m->pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    ProfScope(dfb_model* m_, int cls_, cudaStream_t st_) : m(m_), cls(cls_), st(st_) {
+        if (m->prof) {
+            e0 = get(m);
+            e1 = get(m);
+            cudaEventRecord(e0, st);
+        }
+    }
+    ~ProfScope() {
+        if (m->prof) {
+            cudaEventRecord(e1, st);
+            m->recs.push_back({cls, e0, e1});
+        }
+    }
+};
+}  // namespace
+}  // namespace dfb
 
 namespace dfb {
 namespace {
@@ -630,6 +670,7 @@ int upload_pack(const float* h_w, int out, int in, int col0, int ncols, long lon
     const long long total = pl.w.rows_pad * (pl.w.KB * 8);
     pack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_tmp, out, ncols, ncols, pl.w.rows_pad, pl.w.KB * 64,
                                                                         pl.w.p, pl.w.plane, 1);
+    note_launch();
     DFB_CUDA(cudaGetLastError());
     DFB_CUDA(cudaStreamSynchronize(st));
     cudaFree(d_tmp);
@@ -705,6 +746,30 @@ int gemm_t_max(const dfb_model* m, const PackedLayer& W, const TiledBuf& X, long
 }  // namespace
 }  // namespace dfb
 
+extern "C" int dfb_model_profile(dfb_model* m, int32_t enable) {
+    using namespace dfb;
+    DFB_REQUIRE(m != nullptr, DFB_E_ARG, "dfb_model_profile: NULL model");
+    m->prof = enable != 0;
+    return DFB_OK;
+}
+
+extern "C" int dfb_model_profile_read(dfb_model* m, double* ms, int64_t* launches, int32_t n_classes, dfb_stream stream) {
+    using namespace dfb;
+    DFB_REQUIRE(m && ms && launches && n_classes >= DFB_PROF_NUM, DFB_E_ARG, "dfb_model_profile_read: bad arguments");
+    DFB_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    for (auto& r : m->recs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) {
+            ms[r.cls] += t;
+            launches[r.cls] += 1;
+        }
+        m->pool.push_back(r.e0);
+        m->pool.push_back(r.e1);
+    }
+    m->recs.clear();
+    return DFB_OK;
+}
+
 extern "C" DFB_API int dfb_dbg_set(int key, int value) {
     if (key == 0) dfb::g_swap_lbo_sbo = value;
     return DFB_OK;
@@ -713,6 +778,8 @@ extern "C" DFB_API int dfb_dbg_set(int key, int value) {
 extern "C" int dfb_model_destroy(dfb_model* m) {
     if (!m) return DFB_OK;
     for (void* p : m->allocs) cudaFree(p);
+    for (auto& r : m->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto e : m->pool) cudaEventDestroy(e);
     delete m;
     return DFB_OK;
 }
@@ -856,41 +923,107 @@ extern "C" int dfb_model_forward(dfb_model* m, const float* d_patch, int64_t n, 
         const unsigned pw_blocks = (unsigned)((rows + 127) / 128);
 
         // ---- QSTN (DeepFit.py:410-441) ----
-        pointwise3_kernel<<<pw_blocks, 128, 0, st>>>(patch, nullptr, B, k, m->w_small[DFB_L_QSTN_CONV1], m->L[DFB_L_QSTN_CONV1].bias,
-                                                     m->x64a.p, m->x64a.plane, split, nullptr);
-        DFB_RUN(gemm_n(m, m->x64a, rows, m->L[DFB_L_QSTN_CONV2], 1, &m->x128, nullptr, 0, k, nullptr, 0, st));
-        DFB_RUN(gemm_t_max(m, m->L[DFB_L_QSTN_CONV3], m->x128, B, 1, &m->gfeat, nullptr, st));
-        DFB_RUN(gemm_n(m, m->gfeat, B, m->L[DFB_L_QSTN_FC1], 1, &m->f512, nullptr, 0, 0, nullptr, 0, st));
-        DFB_RUN(gemm_n(m, m->f512, B, m->L[DFB_L_QSTN_FC2], 1, nullptr, m->f256_f, 256, 0, nullptr, 0, st));
-        quat_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(m->f256_f, B, m->w_small[DFB_L_QSTN_FC3], m->L[DFB_L_QSTN_FC3].bias, trans);
+        {
+            ProfScope ps(m, DFB_PROF_POINTWISE, st);
+            pointwise3_kernel<<<pw_blocks, 128, 0, st>>>(patch, nullptr, B, k, m->w_small[DFB_L_QSTN_CONV1], m->L[DFB_L_QSTN_CONV1].bias,
+                                                         m->x64a.p, m->x64a.plane, split, nullptr);
+            note_launch();
+        }
+        {
+            ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
+            DFB_RUN(gemm_n(m, m->x64a, rows, m->L[DFB_L_QSTN_CONV2], 1, &m->x128, nullptr, 0, k, nullptr, 0, st));
+        }
+        {
+            ProfScope ps(m, DFB_PROF_GEMM_MAX, st);
+            DFB_RUN(gemm_t_max(m, m->L[DFB_L_QSTN_CONV3], m->x128, B, 1, &m->gfeat, nullptr, st));
+        }
+        {
+            ProfScope ps(m, DFB_PROF_FC, st);
+            DFB_RUN(gemm_n(m, m->gfeat, B, m->L[DFB_L_QSTN_FC1], 1, &m->f512, nullptr, 0, 0, nullptr, 0, st));
+        }
+        {
+            ProfScope ps(m, DFB_PROF_FC, st);
+            DFB_RUN(gemm_n(m, m->f512, B, m->L[DFB_L_QSTN_FC2], 1, nullptr, m->f256_f, 256, 0, nullptr, 0, st));
+        }
+        {
+            ProfScope ps(m, DFB_PROF_QUAT, st);
+            quat_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(m->f256_f, B, m->w_small[DFB_L_QSTN_FC3], m->L[DFB_L_QSTN_FC3].bias, trans);
+            note_launch();
+        }
 
         // ---- point features (DeepFit.py:188-197) ----
-        pointwise3_kernel<<<pw_blocks, 128, 0, st>>>(patch, trans, B, k, m->w_small[DFB_L_PF_CONV1], m->L[DFB_L_PF_CONV1].bias,
-                                                     m->x64a.p, m->x64a.plane, split,
-                                                     d_points_rot ? d_points_rot + s * 3LL * k : nullptr);
-        DFB_RUN(gemm_n(m, m->x64a, rows, m->L[DFB_L_PF_CONV2], 1, &m->x64b, nullptr, 0, k, nullptr, 0, st));
+        {
+            ProfScope ps(m, DFB_PROF_POINTWISE, st);
+            pointwise3_kernel<<<pw_blocks, 128, 0, st>>>(patch, trans, B, k, m->w_small[DFB_L_PF_CONV1], m->L[DFB_L_PF_CONV1].bias,
+                                                         m->x64a.p, m->x64a.plane, split,
+                                                         d_points_rot ? d_points_rot + s * 3LL * k : nullptr);
+            note_launch();
+        }
+        {
+            ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
+            DFB_RUN(gemm_n(m, m->x64a, rows, m->L[DFB_L_PF_CONV2], 1, &m->x64b, nullptr, 0, k, nullptr, 0, st));
+        }
 
         // ---- feature STN (DeepFit.py:353-380) ----
-        DFB_RUN(gemm_n(m, m->x64b, rows, m->L[DFB_L_STN_CONV1], 1, &m->x64c, nullptr, 0, k, nullptr, 0, st));
-        DFB_RUN(gemm_n(m, m->x64c, rows, m->L[DFB_L_STN_CONV2], 1, &m->x128, nullptr, 0, k, nullptr, 0, st));
-        DFB_RUN(gemm_t_max(m, m->L[DFB_L_STN_CONV3], m->x128, B, 1, &m->gfeat, nullptr, st));
-        DFB_RUN(gemm_n(m, m->gfeat, B, m->L[DFB_L_STN_FC1], 1, &m->f512, nullptr, 0, 0, nullptr, 0, st));
-        DFB_RUN(gemm_n(m, m->f512, B, m->L[DFB_L_STN_FC2], 1, &m->f256, nullptr, 0, 0, nullptr, 0, st));
-        DFB_RUN(gemm_n(m, m->f256, B, m->L[DFB_L_STN_FC3], 0, &m->t2blk, nullptr, 0, 0, nullptr, 0, st, EPI_T2, nullptr,
-                       d_trans2 ? d_trans2 + s * 4096 : nullptr));
+        {
+            ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
+            DFB_RUN(gemm_n(m, m->x64b, rows, m->L[DFB_L_STN_CONV1], 1, &m->x64c, nullptr, 0, k, nullptr, 0, st));
+        }
+        {
+            ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
+            DFB_RUN(gemm_n(m, m->x64c, rows, m->L[DFB_L_STN_CONV2], 1, &m->x128, nullptr, 0, k, nullptr, 0, st));
+        }
+        {
+            ProfScope ps(m, DFB_PROF_GEMM_MAX, st);
+            DFB_RUN(gemm_t_max(m, m->L[DFB_L_STN_CONV3], m->x128, B, 1, &m->gfeat, nullptr, st));
+        }
+        {
+            ProfScope ps(m, DFB_PROF_FC, st);
+            DFB_RUN(gemm_n(m, m->gfeat, B, m->L[DFB_L_STN_FC1], 1, &m->f512, nullptr, 0, 0, nullptr, 0, st));
+        }
+        {
+            ProfScope ps(m, DFB_PROF_FC, st);
+            DFB_RUN(gemm_n(m, m->f512, B, m->L[DFB_L_STN_FC2], 1, &m->f256, nullptr, 0, 0, nullptr, 0, st));
+        }
+        {
+            ProfScope ps(m, DFB_PROF_FC, st);
+            DFB_RUN(gemm_n(m, m->f256, B, m->L[DFB_L_STN_FC3], 0, &m->t2blk, nullptr, 0, 0, nullptr, 0, st, EPI_T2, nullptr,
+                           d_trans2 ? d_trans2 + s * 4096 : nullptr));
+        }
         // x' = x T2 (DeepFit.py:202-204): per-patch B operand
-        DFB_RUN(gemm_n(m, m->x64b, rows, m->head_point, 0, &m->x64c, nullptr, 0, k, nullptr, 0, st, EPI_ACT, &m->t2blk));
+        {
+            ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
+            DFB_RUN(gemm_n(m, m->x64b, rows, m->head_point, 0, &m->x64c, nullptr, 0, k, nullptr, 0, st, EPI_ACT, &m->t2blk));
+        }
 
         // ---- encoder (DeepFit.py:233-235) ----
-        DFB_RUN(gemm_n(m, m->x64c, rows, m->L[DFB_L_ENC_CONV2], 1, &m->x128, nullptr, 0, k, nullptr, 0, st));
-        DFB_RUN(gemm_t_max(m, m->L[DFB_L_ENC_CONV3], m->x128, B, 0, &m->gfeat, nullptr, st));
+        {
+            ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
+            DFB_RUN(gemm_n(m, m->x64c, rows, m->L[DFB_L_ENC_CONV2], 1, &m->x128, nullptr, 0, k, nullptr, 0, st));
+        }
+        {
+            ProfScope ps(m, DFB_PROF_GEMM_MAX, st);
+            DFB_RUN(gemm_t_max(m, m->L[DFB_L_ENC_CONV3], m->x128, B, 0, &m->gfeat, nullptr, st));
+        }
 
         // ---- head (DeepFit.py:304-316): conv1 split into global (per patch) + point (per point) parts ----
-        DFB_RUN(gemm_n(m, m->gfeat, B, m->head_global, 0, nullptr, m->hg, 512, 0, nullptr, 0, st));
-        DFB_RUN(gemm_n(m, m->x64c, rows, m->head_point, 1, &m->h512, nullptr, 0, k, m->hg, 512, st));
-        DFB_RUN(gemm_n(m, m->h512, rows, m->L[DFB_L_HEAD_CONV2], 1, &m->h256, nullptr, 0, k, nullptr, 0, st));
-        DFB_RUN(gemm_n(m, m->h256, rows, m->L[DFB_L_HEAD_CONV3], 1, nullptr, d_weights + s * (long long)k, 0, k, nullptr, 0, st,
-                       EPI_DOT));
+        {
+            ProfScope ps(m, DFB_PROF_FC, st);
+            DFB_RUN(gemm_n(m, m->gfeat, B, m->head_global, 0, nullptr, m->hg, 512, 0, nullptr, 0, st));
+        }
+        {
+            ProfScope ps(m, DFB_PROF_HEAD, st);
+            DFB_RUN(gemm_n(m, m->x64c, rows, m->head_point, 1, &m->h512, nullptr, 0, k, m->hg, 512, st));
+        }
+        {
+            ProfScope ps(m, DFB_PROF_HEAD, st);
+            DFB_RUN(gemm_n(m, m->h512, rows, m->L[DFB_L_HEAD_CONV2], 1, &m->h256, nullptr, 0, k, nullptr, 0, st));
+        }
+        {
+            ProfScope ps(m, DFB_PROF_HEAD, st);
+            DFB_RUN(gemm_n(m, m->h256, rows, m->L[DFB_L_HEAD_CONV3], 1, nullptr, d_weights + s * (long long)k, 0, k, nullptr, 0, st,
+                           EPI_DOT));
+        }
         DFB_RUN(check_cuda(cudaGetLastError(), "model forward launches", __FILE__, __LINE__));
     }
 #undef DFB_RUN

@@ -178,5 +178,6 @@ extern "C" int dfb_patch_pca(const float* d_points, int64_t n_points, const int3
     else if (npl <= 8) pca_kernel<8><<<(unsigned)blocks, kPcaWarps * 32, 0, st>>>(a);
     else if (npl <= 16) pca_kernel<16><<<(unsigned)blocks, kPcaWarps * 32, 0, st>>>(a);
     else pca_kernel<32><<<(unsigned)blocks, kPcaWarps * 32, 0, st>>>(a);
+    note_launch();
     return check_cuda(cudaGetLastError(), "pca_kernel launch", __FILE__, __LINE__);
 }

@@ -13,15 +13,22 @@
 //            memory; 8 rounds fill 32 patch slots per warp.
 //   phase 2: one lane per patch: CGAL-style preconditioning applied to the moments, XtX/XtY
 //            assembled in the reference's column order, unblocked fp32 Cholesky + two triangular
-//            solves in registers, D_inv, normal, closed-form curvature on the upper triangle of
-//            -I^{-1} II (what torch.symeig(upper=True) sees), back-rotation by trans^T and U^T.
+//            solves in registers, two steps of iterative refinement against the fp64 residual,
+//            D_inv, normal, closed-form curvature on the upper triangle of -I^{-1} II (what
+//            torch.symeig(upper=True) sees), back-rotation by trans^T and U^T.
+// Numerics: a moment matrix, unlike the Gram matrix A^T W A the reference forms, is not backward
+// stable in fp32 -- entry-wise rounding acts on the solution with cond(XtX) (up to 4e5 at order 4 on
+// the lidar tutorial cloud) instead of cond(A).  The moments are therefore accumulated in fp64
+// (B200 runs DFMA at half the FFMA rate, so the stage stays HBM-bound) and the fp32 Cholesky factor is
+// used as the preconditioner of an fp64-residual refinement; the result is the exact least-squares
+// solution of the fp32 inputs to ~1e-9, i.e. at most the reference's own rounding error away from it.
 #include "common.cuh"
 
 namespace dfb {
 namespace {
 
-constexpr int kWarpsPerBlock = 4;
-constexpr int kSlotStride = 65;  // floats per patch slot (62 used at order 4), odd => conflict-free
+constexpr int kWarpsPerBlock = 2;
+constexpr int kSlotStride = 65;  // doubles per patch slot (62 used at order 4), odd => conflict-free
 
 template <int ORDER>
 struct Jet {
@@ -49,8 +56,8 @@ __device__ __forceinline__ constexpr int coly(int i) {
 
 template <int ORDER>
 struct Acc {
-    float m[Jet<ORDER>::NM];
-    float zm[Jet<ORDER>::NZ];
+    double m[Jet<ORDER>::NM];
+    double zm[Jet<ORDER>::NZ];
     float sax, say;  // sum |x|, sum |y|
     float nvalid;    // number of weights > 1e-3
 };
@@ -58,23 +65,24 @@ struct Acc {
 template <int ORDER>
 __device__ __forceinline__ void acc_point(Acc<ORDER>& A, float x, float y, float z, float w, float wraw) {
     using J = Jet<ORDER>;
-    float xp[J::D + 1], yp[J::D + 1];
+    double xp[J::D + 1], yp[J::D + 1];
+    const double xd = x, yd = y, zd = z;
     xp[0] = w;
-    yp[0] = 1.f;
+    yp[0] = 1.0;
 #pragma unroll
     for (int a = 1; a <= J::D; ++a) {
-        xp[a] = xp[a - 1] * x;
-        yp[a] = yp[a - 1] * y;
+        xp[a] = xp[a - 1] * xd;
+        yp[a] = yp[a - 1] * yd;
     }
 #pragma unroll
     for (int a = 0; a <= J::D; ++a)
 #pragma unroll
-        for (int b = 0; b <= J::D - a; ++b) A.m[J::mi(a, b)] = fmaf(xp[a], yp[b], A.m[J::mi(a, b)]);
+        for (int b = 0; b <= J::D - a; ++b) A.m[J::mi(a, b)] = fma(xp[a], yp[b], A.m[J::mi(a, b)]);
 #pragma unroll
     for (int a = 0; a <= ORDER; ++a) {
-        const float xz = xp[a] * z;
+        const double xz = xp[a] * zd;
 #pragma unroll
-        for (int b = 0; b <= ORDER - a; ++b) A.zm[J::zi(a, b)] = fmaf(xz, yp[b], A.zm[J::zi(a, b)]);
+        for (int b = 0; b <= ORDER - a; ++b) A.zm[J::zi(a, b)] = fma(xz, yp[b], A.zm[J::zi(a, b)]);
     }
     A.sax += fabsf(x);
     A.say += fabsf(y);
@@ -94,9 +102,9 @@ template <int ORDER>
 __device__ __forceinline__ void acc_patch(Acc<ORDER>& A, const float* __restrict__ px, const float* __restrict__ pw,
                                           const float* R, int k, int sub, bool use_w) {
 #pragma unroll
-    for (int i = 0; i < Jet<ORDER>::NM; ++i) A.m[i] = 0.f;
+    for (int i = 0; i < Jet<ORDER>::NM; ++i) A.m[i] = 0.0;
 #pragma unroll
-    for (int i = 0; i < Jet<ORDER>::NZ; ++i) A.zm[i] = 0.f;
+    for (int i = 0; i < Jet<ORDER>::NZ; ++i) A.zm[i] = 0.0;
     A.sax = A.say = A.nvalid = 0.f;
     const float* py = px + k;
     const float* pz = px + 2 * k;
@@ -133,18 +141,24 @@ __device__ __forceinline__ float group8_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 4);
     return v;
 }
+__device__ __forceinline__ double group8_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
 
 template <int ORDER>
-__device__ __forceinline__ void reduce_store(Acc<ORDER>& A, float* slot, int sub) {
+__device__ __forceinline__ void reduce_store(Acc<ORDER>& A, double* slot, int sub) {
     using J = Jet<ORDER>;
 #pragma unroll
     for (int i = 0; i < J::NM; ++i) {
-        const float t = group8_sum(A.m[i]);
+        const double t = group8_sum(A.m[i]);
         if ((i & 7) == sub) slot[i] = t;
     }
 #pragma unroll
     for (int i = 0; i < J::NZ; ++i) {
-        const float t = group8_sum(A.zm[i]);
+        const double t = group8_sum(A.zm[i]);
         if ((i & 7) == sub) slot[J::NM + i] = t;
     }
     A.sax = group8_sum(A.sax);
@@ -156,11 +170,10 @@ __device__ __forceinline__ void reduce_store(Acc<ORDER>& A, float* slot, int sub
     }
 }
 
-// In-register unblocked Cholesky (lower, packed) + forward/backward substitution.
-// Failure criterion as LAPACK spotrf: pivot <= 0 or NaN.
-template <int M>
-__device__ __forceinline__ bool chol_solve(float (&a)[M * (M + 1) / 2], float (&b)[M]) {
+// In-register unblocked Cholesky (lower, packed).  Failure criterion as LAPACK spotrf: pivot <= 0 or NaN.
 #define LIDX(i, j) ((i) * ((i) + 1) / 2 + (j))
+template <int M>
+__device__ __forceinline__ bool chol_factor(float (&a)[M * (M + 1) / 2]) {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < M; ++j) {
@@ -179,6 +192,11 @@ __device__ __forceinline__ bool chol_solve(float (&a)[M * (M + 1) / 2], float (&
             a[LIDX(i, j)] = s * inv;
         }
     }
+    return ok;
+}
+// Solve L L^T x = b in place (b -> x) with the factor from chol_factor.
+template <int M>
+__device__ __forceinline__ void chol_substitute(const float (&a)[M * (M + 1) / 2], float (&b)[M]) {
 #pragma unroll
     for (int i = 0; i < M; ++i) {
         float s = b[i];
@@ -193,9 +211,8 @@ __device__ __forceinline__ bool chol_solve(float (&a)[M * (M + 1) / 2], float (&
         for (int t = i + 1; t < M; ++t) s = fmaf(-a[LIDX(t, i)], b[t], s);
         b[i] = s / a[LIDX(i, i)];
     }
-#undef LIDX
-    return ok;
 }
+#undef LIDX
 
 __device__ __forceinline__ void curvature_from_beta(float b0f, float b1f, float b2f, float b3f, float b4f,
                                                     float& k1, float& k2) {
@@ -236,7 +253,7 @@ template <int ORDER>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) wls_kernel(WlsArgs p) {
     using J = Jet<ORDER>;
     constexpr int M = J::M;
-    __shared__ float s_mom[kWarpsPerBlock][32][kSlotStride];
+    __shared__ double s_mom[kWarpsPerBlock][32][kSlotStride];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane >> 3, sub = lane & 7;
     const long long n_super = (p.n + 31) / 32;  // groups of 32 patches, one per warp iteration
@@ -269,47 +286,72 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) wls_kernel(WlsArgs p) {
         // ---------------- phase 2 ----------------
         const long long pi = base + lane;
         if (pi < p.n) {
-            const float* slot = s_mom[warp][lane];
-            const float invk = 1.f / (float)p.k;
+            const double* slot = s_mom[warp][lane];
             float h = 1.f;
             if (ORDER > 1) {
-                // DeepFit.py:43-46
-                h = (slot[J::NM + J::NZ] * invk + slot[J::NM + J::NZ + 1] * invk) * 0.5f;
+                // DeepFit.py:43-46 (fp32, like the reference)
+                const float invk = 1.f / (float)p.k;
+                h = ((float)slot[J::NM + J::NZ] * invk + (float)slot[J::NM + J::NZ + 1] * invk) * 0.5f;
                 if (fabsf(h) < 1e-4f) h = 0.1f;
             }
-            const float ih = 1.f / h;
-            float ihp[J::D + 1];
-            ihp[0] = 1.f;
+            const double ih = 1.0 / (double)h;
+            double ihp[J::D + 1];
+            ihp[0] = 1.0;
 #pragma unroll
             for (int a = 1; a <= J::D; ++a) ihp[a] = ihp[a - 1] * ih;
 
-            float beta[M];
+            double bsol[M];  // solution of the preconditioned system, refined in fp64
             int info = 0;
 #pragma unroll 1
             for (int attempt = 0; attempt < 2; ++attempt) {
                 float a[M * (M + 1) / 2];
+                float rhs[M];
 #pragma unroll
                 for (int i = 0; i < M; ++i) {
 #pragma unroll
                     for (int j = 0; j <= i; ++j) {
                         const int ax = colx<ORDER>(i) + colx<ORDER>(j), by = coly<ORDER>(i) + coly<ORDER>(j);
-                        float v = slot[J::mi(ax, by)] * ihp[ax + by];
-                        if (attempt == 1 && i == j) v *= 1.01f;
-                        a[i * (i + 1) / 2 + j] = v;
+                        double v = slot[J::mi(ax, by)] * ihp[ax + by];
+                        if (attempt == 1 && i == j) v *= 1.01;
+                        a[i * (i + 1) / 2 + j] = (float)v;
                     }
-                    beta[i] = slot[J::NM + J::zi(colx<ORDER>(i), coly<ORDER>(i))] * ihp[colx<ORDER>(i) + coly<ORDER>(i)];
+                    rhs[i] = (float)(slot[J::NM + J::zi(colx<ORDER>(i), coly<ORDER>(i))] * ihp[colx<ORDER>(i) + coly<ORDER>(i)]);
                 }
-                const bool ok = chol_solve<M>(a, beta);
-                if (ok) break;
-                info = attempt + 1;
-            }
-            if (info == 2) {
+                const bool ok = chol_factor<M>(a);
+                if (!ok) {
+                    info = attempt + 1;
+                    continue;
+                }
+                chol_substitute<M>(a, rhs);
 #pragma unroll
-                for (int i = 0; i < M; ++i) beta[i] = 0.f;
+                for (int i = 0; i < M; ++i) bsol[i] = (double)rhs[i];
+                // iterative refinement: residual of the (possibly ridged) fp64 system, correction through the
+                // fp32 factor; contracts by ~cond * 2^-24 per step
+#pragma unroll 1
+                for (int it = 0; it < 2; ++it) {
+#pragma unroll
+                    for (int i = 0; i < M; ++i) {
+                        double r = slot[J::NM + J::zi(colx<ORDER>(i), coly<ORDER>(i))] * ihp[colx<ORDER>(i) + coly<ORDER>(i)];
+#pragma unroll
+                        for (int j = 0; j < M; ++j) {
+                            const int ax = colx<ORDER>(i) + colx<ORDER>(j), by = coly<ORDER>(i) + coly<ORDER>(j);
+                            double v = slot[J::mi(ax, by)] * ihp[ax + by];
+                            if (attempt == 1 && i == j) v *= 1.01;
+                            r = fma(-v, bsol[j], r);
+                        }
+                        rhs[i] = (float)r;
+                    }
+                    chol_substitute<M>(a, rhs);
+#pragma unroll
+                    for (int i = 0; i < M; ++i) bsol[i] += (double)rhs[i];
+                }
+                break;
             }
+            float beta[M];
             // D_inv, DeepFit.py:85-86
 #pragma unroll
-            for (int i = 0; i < M; ++i) beta[i] *= ihp[colx<ORDER>(i) + coly<ORDER>(i)];
+            for (int i = 0; i < M; ++i)
+                beta[i] = (info == 2) ? 0.f : (float)(bsol[i] * ihp[colx<ORDER>(i) + coly<ORDER>(i)]);
 
             if (p.beta) {
 #pragma unroll
@@ -372,6 +414,7 @@ int launch_wls(const WlsArgs& a, cudaStream_t st) {
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     wls_kernel<ORDER><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+    note_launch();
     return check_cuda(cudaGetLastError(), "wls_kernel launch", __FILE__, __LINE__);
 }
 
@@ -409,5 +452,6 @@ extern "C" int dfb_principal_curvatures(const float* d_beta, int64_t n, int32_t 
     int rc = dfb_device_check();
     if (rc) return rc;
     curvature_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(d_beta, (long long)n, m, d_curv);
+    note_launch();
     return check_cuda(cudaGetLastError(), "curvature_kernel launch", __FILE__, __LINE__);
 }

@@ -131,6 +131,11 @@ def wls_fit(patch: torch.Tensor, weights: Optional[torch.Tensor], order: int, tr
     return out
 
 
+def launch_count(reset: bool = False) -> int:
+    """Number of CUDA kernels the library has launched in this process."""
+    return int(_lib.load().dfb_launch_count(1 if reset else 0))
+
+
 def principal_curvatures(beta: torch.Tensor) -> torch.Tensor:
     beta = _chk(beta, torch.float32, "beta")
     if beta.dim() != 2 or beta.shape[1] < 5:
@@ -186,6 +191,21 @@ class WeightNetwork:
             self.close()
         except Exception:  # noqa: BLE001
             pass
+
+    PROFILE_CLASSES = ["pointwise", "gemm_small", "gemm_max_128x1024", "fc", "head", "quat"]
+
+    def profile(self, enable: bool):
+        """Record per-kernel-class CUDA-event timings of subsequent forwards."""
+        _lib.check(_lib.load().dfb_model_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """Synchronise; returns {class: (milliseconds, launches)} accumulated since the last read."""
+        n = len(self.PROFILE_CLASSES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().dfb_model_profile_read(self._h, ms, cnt, n, _stream(self.device)))
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(self.PROFILE_CLASSES)}
 
     def status(self):
         """Synchronise and raise if any tensor-core pipeline of this network timed out."""

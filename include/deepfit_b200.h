@@ -48,6 +48,10 @@ DFB_API const char* dfb_last_error_string(void);
 /* 0 when the current device is compute capability 10.x; DFB_E_NODEVICE otherwise. */
 DFB_API int dfb_device_check(void);
 
+/* Number of CUDA kernels this library has launched in this process (reset != 0 zeroes the counter
+ * after reading). */
+DFB_API int64_t dfb_launch_count(int32_t reset);
+
 /* ------------------------------------------------------------------------------------------
  * Stage 1 -- neighbourhood search.
  * Replaces scipy.spatial.cKDTree(points, 10) built at tutorial/tutorial_utils.py:16 (and
@@ -154,6 +158,20 @@ DFB_API int dfb_model_forward(dfb_model* model, const float* d_patch, int64_t n,
 /* Synchronises the stream and reports whether any tensor-core pipeline of this model timed out
  * (DFB_E_INTERNAL); kernels never spin forever on a barrier. */
 DFB_API int dfb_model_status(dfb_model* model, dfb_stream stream);
+
+/* Per-kernel-class device timing of dfb_model_forward (CUDA events on the launching stream).
+ * enable != 0 starts recording; dfb_model_profile_read synchronises, adds the elapsed milliseconds and
+ * launch counts of each class to ms[]/launches[] (n_classes entries, see DFB_PROF_*) and clears the
+ * records. */
+#define DFB_PROF_POINTWISE 0  /* K=3 layers + rotation (CUDA cores) */
+#define DFB_PROF_GEMM_SMALL 1 /* 64->64, 64->128 and x*T2 (tensor cores) */
+#define DFB_PROF_GEMM_MAX 2   /* 128->1024 + max-pool (tensor cores, dominant) */
+#define DFB_PROF_FC 3         /* per-patch fully connected layers */
+#define DFB_PROF_HEAD 4       /* 64->512, 512->256, 256->128 + weight epilogue */
+#define DFB_PROF_QUAT 5       /* fc3 + quaternion -> rotation */
+#define DFB_PROF_NUM 6
+DFB_API int dfb_model_profile(dfb_model* model, int32_t enable);
+DFB_API int dfb_model_profile_read(dfb_model* model, double* ms, int64_t* launches, int32_t n_classes, dfb_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * Stage 4+5 -- weighted n-jet fit, normal, principal curvatures.

@@ -56,20 +56,15 @@ def test_umma_gemm_points_as_rows(shape, nprod):
     bias = torch.randn(N, device="cuda", generator=g)
     out, out_t = _dbg_gemm(A, Bm, bias, 0, nprod, 1, 128)
     ref = _ref(A, Bm, bias, True, nprod)
-    tol = 2e-5 if nprod == 3 else 2e-3
+    # error model: split-bf16 keeps 16 mantissa bits per operand (2^-16 relative per product, plus the
+    # dropped lo*lo term), plain bf16 keeps 8; both accumulate in fp32
+    mag = (A.abs().double() @ Bm.abs().double().t()).max().item()
+    tol = mag * (2 ** -13 if nprod == 3 else 2 ** -9)
     err = (out.double() - ref).abs().max().item()
-    if not err < tol:
-        from deepfit_b200 import _lib
-        _lib.load().dfb_dbg_set(0, 1)
-        try:
-            out2, _ = _dbg_gemm(A, Bm, bias, 0, nprod, 1, 128)
-            err2 = (out2.double() - ref).abs().max().item()
-        finally:
-            _lib.load().dfb_dbg_set(0, 0)
-        pytest.fail("GEMM mismatch: max err %g (with LBO/SBO swapped: %g); sample out %s ref %s"
-                    % (err, err2, out[0, :4].tolist(), ref[0, :4].tolist()))
+    assert err < tol, "GEMM mismatch: max err %g (tol %g); sample out %s ref %s" % (
+        err, tol, out[0, :4].tolist(), ref[0, :4].tolist())
     # the re-split tiled output (next layer's operand) carries the same values to 2^-16 relative
-    tol_t = 2e-5 + (ref.abs().max().item() * (2 ** -15 if nprod == 3 else 2 ** -7))
+    tol_t = tol + (ref.abs().max().item() * (2 ** -15 if nprod == 3 else 2 ** -7))
     assert (out_t.double() - ref).abs().max().item() < tol_t
 
 
@@ -84,7 +79,8 @@ def test_umma_gemm_channels_as_rows_with_maxpool(k_pts, nprod):
     out, out_t = _dbg_gemm(A, W, bias, 1, nprod, 0, k_pts)
     full = _ref(A, W, None, False, nprod).reshape(n_patch, k_pts, N)
     ref = full.max(1)[0] + bias.double()
-    tol = 2e-5 if nprod == 3 else 2e-3
+    mag = (A.abs().double() @ W.abs().double().t()).max().item()
+    tol = mag * (2 ** -13 if nprod == 3 else 2 ** -9)
     assert (out.double() - ref).abs().max().item() < tol
     assert (out_t.double() - ref).abs().max().item() < tol + ref.abs().max().item() * (2 ** -15 if nprod == 3 else 2 ** -7)
 

@@ -89,13 +89,23 @@ def test_classic_fit_matches_reference_golden(golden, name, order):
     ref_n = golden["%s/fit%d_n" % (name, order)]
     ok = out["info"].numpy() == 0
     assert ok.all()
+    # The reference solves in fp32; on ill-conditioned rows (cond(XtX) up to 4e5 at order 4 on the lidar
+    # cloud) ITS OWN distance from the exact least-squares solution exceeds the gate.  Per row the
+    # tolerance is therefore max(gate, 2 x the reference's own error), the latter measured against the
+    # fp64 solution of the same system.
+    ex_beta, ex_n = O.fit_wjet(P.double(), torch.ones(32, 256, dtype=torch.float64), order)
+    ref_err = O.unoriented_angle_deg(ref_n, ex_n.numpy())
     ang = O.unoriented_angle_deg(out["n_local"].numpy(), ref_n)
-    assert ang.max() <= ANGLE_TOL_DEG, "max angular deviation %g deg" % ang.max()
+    assert (ang <= np.maximum(ANGLE_TOL_DEG, 2 * ref_err)).all(), "max angular deviation %g deg" % ang.max()
+    assert O.unoriented_angle_deg(out["n_local"].numpy(), ex_n.numpy()).max() <= 1e-3   # ours vs exact
     scale = np.maximum(np.abs(ref_beta), 1.0)
-    assert (np.abs(out["beta"].numpy() - ref_beta) / scale).max() < (2e-3 if order < 4 else 2e-2)
+    ref_berr = (np.abs(ref_beta - ex_beta.numpy()) / scale).max(1)
+    assert ((np.abs(out["beta"].numpy() - ref_beta) / scale).max(1) <= np.maximum(2e-3, 2 * ref_berr)).all()
     if order > 1:
-        err = O.rectified_rel_err(out["curv"].numpy(), golden["%s/fit%d_curv" % (name, order)])
-        assert err.max() <= CURV_TOL, "max curvature error %g" % err.max()
+        ref_c = golden["%s/fit%d_curv" % (name, order)]
+        ref_cerr = O.rectified_rel_err(ref_c, O.principal_curvatures(ex_beta).numpy()).max(1)
+        err = O.rectified_rel_err(out["curv"].numpy(), ref_c).max(1)
+        assert (err <= np.maximum(CURV_TOL, 2 * ref_cerr)).all(), "max curvature error %g" % err.max()
 
 
 @pytest.mark.parametrize("name", CLOUD_NAMES)

@@ -1,0 +1,110 @@
+"""CPU: pin the oracle.  (a) against the reference itself, imported through oracle/shims.py, where
+/root/reference exists (the authoring container); (b) everywhere, against the committed golden
+vectors that the reference produced (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import CLOUD_NAMES
+from oracle import deepfit_oracle as O
+from oracle import shims
+
+torch.set_grad_enabled(False)
+
+
+@pytest.mark.parametrize("name", CLOUD_NAMES)
+def test_oracle_knn_and_patches_match_golden(golden, clouds, name):
+    pts, bb = O.normalize_cloud(clouds[name])
+    assert bb == float(golden[name + "/bbdiag"])
+    q = golden[name + "/query"][:12]
+    idx, dist = O.knn_bruteforce(pts, q, 256)
+    ref_idx, ref_dist = golden[name + "/knn_idx"][:12], golden[name + "/knn_dist"][:12]
+    assert np.array_equal(dist, ref_dist)
+    for r in range(len(q)):        # identical except inside a tie group cut by the k-th place
+        bad = idx[r] != ref_idx[r]
+        assert np.all(dist[r][bad] == dist[r][-1])
+    for j in range(4):
+        patch, U, rad = O.dataset_item(pts, int(q[j]), 256, ref_idx[j].astype(np.int64), ref_dist[j])
+        assert rad == golden[name + "/rad"][j]
+        # same LAPACK call as the reference; allow for a different CPU's SVD rounding/sign
+        Uref = torch.from_numpy(golden[name + "/U"][j])
+        s = torch.sign((U * Uref).sum(0))
+        assert (U * s[None, :] - Uref).abs().max() < 1e-4
+        assert (patch * s[:, None] - torch.from_numpy(golden[name + "/patch"][j])).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("name", CLOUD_NAMES)
+def test_oracle_fit_and_curvature_match_golden(golden, name):
+    P = torch.from_numpy(golden[name + "/patch"][:32])
+    for order in (1, 2, 3, 4):
+        beta, n = O.fit_wjet(P, torch.ones(32, 256), order)
+        ref_b = golden["%s/fit%d_beta" % (name, order)]
+        assert np.abs(beta.numpy() - ref_b).max() < (1e-4 if order < 4 else 2e-2) * max(1.0, np.abs(ref_b).max())
+        assert O.unoriented_angle_deg(n.numpy(), golden["%s/fit%d_n" % (name, order)]).max() < (1e-3 if order < 4 else 1e-2)
+        if order > 1:
+            ref_c = golden["%s/fit%d_curv" % (name, order)]
+            c = O.principal_curvatures(torch.from_numpy(ref_b))
+            assert O.rectified_rel_err(c.numpy(), ref_c).max() < 1e-5
+            c2 = O.principal_curvatures_closed_form(torch.from_numpy(ref_b))
+            assert O.rectified_rel_err(c2.numpy(), ref_c).max() < 1e-5
+    beta, n = O.fit_wjet(P, torch.from_numpy(golden[name + "/wfit3_w"]), 3)
+    assert O.unoriented_angle_deg(n.numpy(), golden[name + "/wfit3_n"]).max() < 1e-3
+
+
+@pytest.mark.parametrize("name", CLOUD_NAMES)
+def test_oracle_network_matches_golden(golden, name):
+    sd = O.seeded_state_dict(0)
+    assert len(sd) == 125
+    P = torch.from_numpy(golden[name + "/patch"][:16])
+    n, beta, w, trans, t2, _ = O.deepfit_forward(sd, P, 3)
+    assert (w - torch.from_numpy(golden[name + "/net_weights"])).abs().max() < 1e-4
+    assert (trans - torch.from_numpy(golden[name + "/net_trans"])).abs().max() < 1e-5
+    assert (t2 - torch.from_numpy(golden[name + "/net_trans2"])).abs().max() < 1e-5
+    nw = O.world_normals(n, torch.from_numpy(golden[name + "/U"][:16]), trans)
+    assert O.unoriented_angle_deg(nw.numpy(), golden[name + "/net_normal_world"]).max() < 5e-3
+    assert float(w.min()) < 0.1 and float(w.max()) > 0.9      # the seeded weights really spread
+
+
+def test_quaternion_and_metrics():
+    R = O.quat_to_rotmat(torch.tensor([[1.0, 0, 0, 0], [0.5, 0.5, 0.5, 0.5]]))
+    assert torch.allclose(R[0], torch.eye(3))
+    assert torch.allclose(R[1] @ R[1].t(), torch.eye(3), atol=1e-6)
+    a = np.array([[0.0, 0, 1.0]])
+    assert O.unoriented_angle_deg(a, -a)[0] == 0.0
+    assert abs(O.unoriented_angle_deg(a, np.array([[0.0, 1.0, 1.0]]))[0] - 45.0) < 1e-9
+
+
+@pytest.mark.skipif(not shims.reference_available(), reason="/root/reference is only present in the authoring container")
+def test_oracle_equals_unmodified_reference():
+    import os
+    RD, RT = shims.import_reference()
+    path = os.path.join(shims.REFERENCE_ROOT, "tutorial", "netsuke100k.xyz")   # a cloud NOT in the fixtures
+    ds = RT.SinglePointCloudDataset(path, 256)
+    raw = np.loadtxt(path).astype("float32")
+    pts, bb = O.normalize_cloud(raw)
+    assert np.array_equal(pts, ds.points) and bb == ds.bbdiag
+    q = np.arange(7, 100000, 6250)[:16]
+    items = [ds[int(i)] for i in q]
+    idx, dist = O.knn_bruteforce(pts, q, 256)
+    d_ref, i_ref = O.canonicalize_knn(*ds.kdtree.query(pts[q], k=256))
+    assert np.array_equal(dist, d_ref) and np.array_equal(idx, i_ref)
+    P = torch.stack([O.dataset_item(pts, int(c), 256, idx[j], dist[j])[0] for j, c in enumerate(q)])
+    Pref = torch.stack([it[0] for it in items])
+    assert torch.equal(P, Pref)
+    for order in (1, 2, 3, 4):
+        b_ref, n_ref, _ = RD.fit_Wjet(Pref, torch.ones_like(Pref[:, 0]), order=order)
+        b, n = O.fit_wjet(Pref, torch.ones(16, 256), order)
+        assert (b - b_ref).abs().max() < 1e-4 * max(1.0, float(b_ref.abs().max()))
+        assert O.unoriented_angle_deg(n.numpy(), n_ref.numpy()).max() < 1e-4
+        if order > 1:
+            c_ref, _ = RT.compute_principal_curvatures(b_ref)
+            assert torch.equal(O.principal_curvatures(b_ref), c_ref)
+    sd = O.seeded_state_dict(3)
+    m = RD.DeepFit(k=1, num_points=256, use_point_stn=1, use_feat_stn=True, point_tuple=1, sym_op="max", arch="simple",
+                   n_gaussians=1, jet_order=3, weight_mode="sigmoid", use_consistency=False)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    n_ref, b_ref, w_ref, tr_ref, t2_ref, _ = m(Pref)
+    n, b, w, tr, t2, _ = O.deepfit_forward(sd, Pref, 3)
+    assert torch.equal(w, w_ref) and torch.equal(tr, tr_ref) and torch.equal(t2, t2_ref)
+    assert O.unoriented_angle_deg(n.numpy(), n_ref.numpy()).max() < 1e-4
