@@ -200,14 +200,19 @@ class DeepFit(nn.Module):
     def _state_key(self, device):
         return (str(device), tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers())))
 
-    def _network(self, device):
+    def _network(self, device, max_batch=0):
+        """The packed device network for the current parameters (rebuilt when they change or when a
+        larger internal chunk is requested)."""
         key = self._state_key(device)
-        if self._net is None or self._net_key != key:
+        have = getattr(self, "_net_max_batch", 0)
+        if self._net is None or self._net_key != key or int(max_batch) > have:
             if self._net is not None:
                 self._net.close()
+            want = max(int(max_batch), have if self._net_key == key else 0) or 1024
             self._net = ops.WeightNetwork(fold_batchnorm(self.state_dict()), self.num_points, self.weight_mode,
-                                          self.precision, device=device)
+                                          self.precision, max_batch=want, device=device)
             self._net_key = key
+            self._net_max_batch = want
         return self._net
 
     def forward(self, points):

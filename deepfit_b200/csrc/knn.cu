@@ -95,8 +95,27 @@ __global__ void bbox_kernel(const float* __restrict__ pts, long long n, unsigned
     }
 }
 
-__global__ void count_kernel(const float* __restrict__ pts, GridParams g, uint32_t* __restrict__ code,
+// Bounding cube -> grid parameters, entirely on the device so (re)builds never synchronise the host.
+__global__ void params_kernel(unsigned* __restrict__ bb6, GridParams* __restrict__ gp, int bits, long long n) {
+    float mn[3], ext = 0.f;
+    for (int a = 0; a < 3; ++a) {
+        mn[a] = ord2f(bb6[a]);
+        const float mx = ord2f(bb6[3 + a]);
+        ext = fmaxf(ext, mx - mn[a]);
+    }
+    if (!(ext > 0.f) || !isfinite(ext)) ext = 1.f;
+    ext *= 1.0001f;
+    gp->minx = mn[0]; gp->miny = mn[1]; gp->minz = mn[2];
+    gp->bits = bits;
+    gp->inv_cell = (float)(1 << bits) / ext;
+    gp->cell = ext / (float)(1 << bits);
+    gp->n = n;
+    for (int a = 0; a < 3; ++a) { bb6[a] = 0xffffffffu; bb6[3 + a] = 0u; }  // re-arm for the next build
+}
+
+__global__ void count_kernel(const float* __restrict__ pts, const GridParams* __restrict__ gp, uint32_t* __restrict__ code,
                              uint32_t* __restrict__ tab) {
+    const GridParams g = *gp;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     const int G = 1 << g.bits;
@@ -243,7 +262,7 @@ struct KnnArgs {
     const float4* sorted;
     const uint32_t* tab;
     const float* pts;  // original order, f32[n,3]
-    GridParams g;
+    const GridParams* gp;
     const int* query;
     long long q_begin, q_count;
     int k, kcap;  // kcap = capacity of the shared list (power of two >= 2k, >= 64)
@@ -259,7 +278,8 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* sd = reinterpret_cast<double*>(smem_raw) + (size_t)warp * a.kcap;
     int* si = reinterpret_cast<int*>(smem_raw + (size_t)kKnnWarps * a.kcap * sizeof(double)) + (size_t)warp * a.kcap;
-    const int G = 1 << a.g.bits;
+    const GridParams gpar = *a.gp;
+    const int G = 1 << gpar.bits;
     const int k = a.k, cap = a.kcap;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
@@ -267,8 +287,8 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
         const long long qi = a.query ? (long long)a.query[qw] : a.q_begin + qw;
         const float qxf = a.pts[qi * 3], qyf = a.pts[qi * 3 + 1], qzf = a.pts[qi * 3 + 2];
         const double qx = qxf, qy = qyf, qz = qzf;
-        const float ux = cell_coord(qxf, a.g.minx, a.g.inv_cell), uy = cell_coord(qyf, a.g.miny, a.g.inv_cell),
-                    uz = cell_coord(qzf, a.g.minz, a.g.inv_cell);
+        const float ux = cell_coord(qxf, gpar.minx, gpar.inv_cell), uy = cell_coord(qyf, gpar.miny, gpar.inv_cell),
+                    uz = cell_coord(qzf, gpar.minz, gpar.inv_cell);
         const int ix = cell_index(ux, G), iy = cell_index(uy, G), iz = cell_index(uz, G);
 
         // threshold: candidates must satisfy key <= T when thr_incl (carried over from a failed
@@ -277,7 +297,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
         int Ti = 0x7fffffff;
         bool thr_incl = true;
 
-        for (int l = 0; l <= a.g.bits; ++l) {
+        for (int l = 0; l <= gpar.bits; ++l) {
             const int Gl = G >> l;
             const int cx = ix >> l, cy = iy >> l, cz = iz >> l;
             // 27 neighbour cells, one per lane
@@ -290,7 +310,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                     const int sh = 3 * l;
                     if (sh >= 30) {  // single top-level cell
                         lo = 0;
-                        hi = (uint32_t)a.g.n;
+                        hi = (uint32_t)gpar.n;
                     } else {
                         lo = a.tab[(size_t)m << sh];
                         hi = a.tab[((size_t)m + 1) << sh];
@@ -307,14 +327,14 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                         else if (uu[t] > c1) d = uu[t] - c1 - kCellSlack;
                         dd[t] = fmaxf(d, 0.f);
                     }
-                    const float dc = a.g.cell * (1.f - 1e-5f);
+                    const float dc = gpar.cell * (1.f - 1e-5f);
                     cmin2 = (dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]) * dc * dc * (1.f - 1e-5f);
                 }
             }
             unsigned total = hi - lo;
             for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-            const bool top = (l == a.g.bits);
-            if (!top && (long long)total < min((long long)3 * k, a.g.n)) continue;
+            const bool top = (l == gpar.bits);
+            if (!top && (long long)total < min((long long)3 * k, gpar.n)) continue;
 
             // guaranteed-complete radius of the block (world units), strict
             double margin2 = INF;
@@ -329,7 +349,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                     if (cc[t] + 2 < Gl) mrg = fminf(mrg, (float)(cc[t] + 2) * w - uu[t] - kCellSlack);
                 }
                 if (mrg < 3.0e38f) {
-                    const double mm = (double)fmaxf(mrg, 0.f) * (double)a.g.cell * (1.0 - 1e-6);
+                    const double mm = (double)fmaxf(mrg, 0.f) * (double)gpar.cell * (1.0 - 1e-6);
                     margin2 = mm * mm;
                 }
             }
@@ -418,12 +438,40 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
 }  // namespace dfb
 
 struct dfb_grid {
-    dfb::GridParams g;
-    float* pts;        // device copy, original order
-    float4* sorted;    // device, Morton order (x, y, z, original index)
-    uint32_t* tab;     // device, 8^bits + 1 entries
-    size_t ncell;
+    long long n = 0;
+    int bits = 0;
+    size_t ncell = 0;
+    long long ntile = 0;
+    float* pts = nullptr;              // device copy, original order
+    float4* sorted = nullptr;          // device, Morton order (x, y, z, original index)
+    uint32_t* tab = nullptr;           // device, 8^bits + 1 entries
+    uint32_t* code = nullptr;          // device, per-point Morton code (build scratch)
+    uint32_t* sums = nullptr;          // device, scan scratch
+    unsigned* bb = nullptr;            // device, ordered-int bounding box (6)
+    dfb::GridParams* params = nullptr; // device
 };
+
+namespace dfb {
+namespace {
+int grid_build(dfb_grid* g, const float* d_points, cudaStream_t st) {
+    const long long n = g->n;
+    const int bb_blocks = (int)((n + 255) / 256 < (long long)sm_count() * 8 ? (n + 255) / 256 : (long long)sm_count() * 8);
+    if (d_points != g->pts)
+        DFB_CUDA(cudaMemcpyAsync(g->pts, d_points, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DFB_CUDA(cudaMemsetAsync(g->tab, 0, (g->ncell + 1) * sizeof(uint32_t), st));
+    bbox_kernel<<<bb_blocks, 256, 0, st>>>(g->pts, n, g->bb);
+    params_kernel<<<1, 1, 0, st>>>(g->bb, g->params, g->bits, n);
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    count_kernel<<<nb, 256, 0, st>>>(g->pts, g->params, g->code, g->tab);
+    scan_tile_sums<<<(unsigned)g->ntile, kScanThreads, 0, st>>>(g->tab + 1, (long long)g->ncell, g->sums);
+    scan_sums_serial<<<1, 1024, 0, st>>>(g->sums, g->ntile);
+    scan_apply<<<(unsigned)g->ntile, kScanThreads, 0, st>>>(g->tab + 1, (long long)g->ncell, g->sums);
+    scatter_kernel<<<nb, 256, 0, st>>>(g->pts, n, g->code, g->tab, g->sorted);
+    note_launch(7);
+    return check_cuda(cudaGetLastError(), "grid build kernels", __FILE__, __LINE__);
+}
+}  // namespace
+}  // namespace dfb
 
 extern "C" int dfb_grid_create(const float* d_points, int64_t n, dfb_stream stream, dfb_grid** out) {
     using namespace dfb;
@@ -433,73 +481,46 @@ extern "C" int dfb_grid_create(const float* d_points, int64_t n, dfb_stream stre
     int rc = dfb_device_check();
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);
-
-    unsigned* d_bb = nullptr;
-    DFB_CUDA(cudaMalloc(&d_bb, 6 * sizeof(unsigned)));
-    unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
-    DFB_CUDA(cudaMemcpyAsync(d_bb, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    const int bb_blocks = (int)((n + 255) / 256 < (int64_t)sm_count() * 8 ? (n + 255) / 256 : (int64_t)sm_count() * 8);
-    bbox_kernel<<<bb_blocks, 256, 0, st>>>(d_points, (long long)n, d_bb);
-    note_launch();
-    unsigned hb[6];
-    DFB_CUDA(cudaMemcpyAsync(hb, d_bb, sizeof(hb), cudaMemcpyDeviceToHost, st));
-    DFB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_bb);
-    float mn[3], mx[3];
-    for (int a = 0; a < 3; ++a) { mn[a] = ord2f(hb[a]); mx[a] = ord2f(hb[3 + a]); }
-    float ext = 0.f;
-    for (int a = 0; a < 3; ++a) {
-        DFB_REQUIRE(isfinite(mn[a]) && isfinite(mx[a]), DFB_E_ARG, "dfb_grid_create: non-finite coordinates");
-        ext = fmaxf(ext, mx[a] - mn[a]);
-    }
-    if (!(ext > 0.f)) ext = 1.f;
-    ext *= 1.0001f;
-
     // finest level: about sqrt(n/8) cells per axis for surface-like clouds, 2^5 .. 2^10
     int bits = (int)ceil(0.5 * log2((double)n / 8.0 + 1.0));
     if (bits < 5) bits = 5;
     if (bits > kMaxLevelBits) bits = kMaxLevelBits;
-
     dfb_grid* g = new dfb_grid();
-    g->g.minx = mn[0]; g->g.miny = mn[1]; g->g.minz = mn[2];
-    g->g.bits = bits;
-    g->g.inv_cell = (float)(1 << bits) / ext;
-    g->g.cell = ext / (float)(1 << bits);
-    g->g.n = (long long)n;
+    g->n = (long long)n;
+    g->bits = bits;
     g->ncell = (size_t)1 << (3 * bits);
-    g->pts = nullptr; g->sorted = nullptr; g->tab = nullptr;
-    uint32_t* code = nullptr;
-    uint32_t* sums = nullptr;
-    const long long ntile = (long long)((g->ncell + kScanTile - 1) / kScanTile);
+    g->ntile = (long long)((g->ncell + kScanTile - 1) / kScanTile);
     cudaError_t e;
     if ((e = cudaMalloc(&g->pts, (size_t)n * 3 * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&g->sorted, (size_t)n * sizeof(float4))) != cudaSuccess ||
         (e = cudaMalloc(&g->tab, (g->ncell + 1) * sizeof(uint32_t))) != cudaSuccess ||
-        (e = cudaMalloc(&code, (size_t)n * sizeof(uint32_t))) != cudaSuccess ||
-        (e = cudaMalloc(&sums, (size_t)ntile * sizeof(uint32_t))) != cudaSuccess) {
-        cudaFree(code); cudaFree(sums);
+        (e = cudaMalloc(&g->code, (size_t)n * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&g->sums, (size_t)g->ntile * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&g->bb, 6 * sizeof(unsigned))) != cudaSuccess ||
+        (e = cudaMalloc(&g->params, sizeof(GridParams))) != cudaSuccess) {
         dfb_grid_destroy(g);
         return check_cuda(e, "dfb_grid_create allocations", __FILE__, __LINE__);
     }
-    cudaMemcpyAsync(g->pts, d_points, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToDevice, st);
-    cudaMemsetAsync(g->tab, 0, (g->ncell + 1) * sizeof(uint32_t), st);
-    const unsigned nb = (unsigned)((n + 255) / 256);
-    count_kernel<<<nb, 256, 0, st>>>(g->pts, g->g, code, g->tab);
-    scan_tile_sums<<<(unsigned)ntile, kScanThreads, 0, st>>>(g->tab + 1, (long long)g->ncell, sums);
-    scan_sums_serial<<<1, 1024, 0, st>>>(sums, ntile);
-    scan_apply<<<(unsigned)ntile, kScanThreads, 0, st>>>(g->tab + 1, (long long)g->ncell, sums);
-    scatter_kernel<<<nb, 256, 0, st>>>(g->pts, (long long)n, code, g->tab, g->sorted);
-    note_launch(5);
-    e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(code);
-    cudaFree(sums);
+    const unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    e = cudaMemcpyAsync(g->bb, init, sizeof(init), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `init` lives on this stack frame
     if (e != cudaSuccess) {
         dfb_grid_destroy(g);
-        return check_cuda(e, "dfb_grid_create build kernels", __FILE__, __LINE__);
+        return check_cuda(e, "dfb_grid_create init", __FILE__, __LINE__);
+    }
+    rc = grid_build(g, d_points, st);
+    if (rc) {
+        dfb_grid_destroy(g);
+        return rc;
     }
     *out = g;
     return DFB_OK;
+}
+
+extern "C" int dfb_grid_update(dfb_grid* g, const float* d_points, dfb_stream stream) {
+    using namespace dfb;
+    DFB_REQUIRE(g != nullptr && d_points != nullptr, DFB_E_ARG, "dfb_grid_update: NULL argument");
+    return grid_build(g, d_points, as_stream(stream));
 }
 
 extern "C" int dfb_grid_destroy(dfb_grid* g) {
@@ -507,6 +528,10 @@ extern "C" int dfb_grid_destroy(dfb_grid* g) {
     cudaFree(g->pts);
     cudaFree(g->sorted);
     cudaFree(g->tab);
+    cudaFree(g->code);
+    cudaFree(g->sums);
+    cudaFree(g->bb);
+    cudaFree(g->params);
     delete g;
     return DFB_OK;
 }
@@ -515,16 +540,16 @@ extern "C" int dfb_knn(const dfb_grid* grid, const int32_t* d_query, int64_t q_b
                        int32_t* d_idx, double* d_dist, double* d_rad, dfb_stream stream) {
     using namespace dfb;
     DFB_REQUIRE(grid != nullptr, DFB_E_ARG, "dfb_knn: grid is NULL");
-    DFB_REQUIRE(k >= 1 && k <= 1024 && (long long)k <= grid->g.n, DFB_E_ARG,
-                "dfb_knn: k=%d out of range (1..min(n=%lld,1024))", k, grid->g.n);
+    DFB_REQUIRE(k >= 1 && k <= 1024 && (long long)k <= grid->n, DFB_E_ARG,
+                "dfb_knn: k=%d out of range (1..min(n=%lld,1024))", k, grid->n);
     DFB_REQUIRE(q_count >= 0 && (q_count == 0 || d_idx != nullptr), DFB_E_ARG, "dfb_knn: bad output arguments");
-    DFB_REQUIRE(d_query != nullptr || (q_begin >= 0 && q_begin + q_count <= grid->g.n), DFB_E_ARG,
+    DFB_REQUIRE(d_query != nullptr || (q_begin >= 0 && q_begin + q_count <= grid->n), DFB_E_ARG,
                 "dfb_knn: query range [%lld,%lld) outside the cloud", (long long)q_begin, (long long)(q_begin + q_count));
     if (q_count == 0) return DFB_OK;
     int kcap = 64;
     while (kcap < 2 * k) kcap <<= 1;
     KnnArgs a;
-    a.sorted = grid->sorted; a.tab = grid->tab; a.pts = grid->pts; a.g = grid->g;
+    a.sorted = grid->sorted; a.tab = grid->tab; a.pts = grid->pts; a.gp = grid->params;
     a.query = d_query; a.q_begin = q_begin; a.q_count = q_count;
     a.k = k; a.kcap = kcap;
     a.out_idx = d_idx; a.out_dist = d_dist; a.out_rad = d_rad;

@@ -45,6 +45,14 @@ class Grid:
         with torch.cuda.device(self.device):
             _lib.check(lib.dfb_grid_create(_p(points), self.n, _stream(self.device), C.byref(self._h)))
 
+    def update(self, points: torch.Tensor):
+        """Rebuild in place for another cloud of the same size (asynchronous, no allocation)."""
+        points = _chk(points, torch.float32, "points")
+        if tuple(points.shape) != (self.n, 3):
+            raise ValueError("Grid.update needs a cloud of the same size [%d,3]" % self.n)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().dfb_grid_update(self._h, _p(points), _stream(self.device)))
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             _lib.load().dfb_grid_destroy(self._h)

@@ -52,12 +52,12 @@ class NormalEstimator:
         self.model = model
         self.cancel_qstn = cancel_qstn
         self.grid = ops.Grid(self.points)
-        self.chunk = int(chunk) if chunk else (8192 if mode == "DeepFit" else 65536)
-        self.net = model._network(points.device) if mode == "DeepFit" else None
+        self.chunk = int(chunk) if chunk else (4096 if mode == "DeepFit" else 65536)
+        self.net = model._network(points.device, max_batch=self.chunk) if mode == "DeepFit" else None
 
     def rebuild_grid(self):
-        self.grid.close()
-        self.grid = ops.Grid(self.points)
+        """Stage-1 build for the current ``self.points`` (same size): in place, asynchronous."""
+        self.grid.update(self.points)
 
     def run(self, begin: int = 0, end: Optional[int] = None, out_normals: Optional[torch.Tensor] = None,
             out_curv: Optional[torch.Tensor] = None, extras: Optional[dict] = None):

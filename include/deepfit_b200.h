@@ -60,9 +60,11 @@ DFB_API int64_t dfb_launch_count(int32_t reset);
  * ------------------------------------------------------------------------------------------ */
 
 /* Build the search structure (Morton-ordered multi-level uniform grid) over d_points f32[n,3].
- * The points are copied (re-ordered) into the handle; d_points may be released afterwards.
- * Synchronises the stream once (bounding box read-back). */
+ * The points are copied (and re-ordered) into the handle; d_points may be released afterwards.
+ * Allocates; the build kernels themselves are asynchronous on the stream. */
 DFB_API int dfb_grid_create(const float* d_points, int64_t n, dfb_stream stream, dfb_grid** out);
+/* Rebuild in place for a new cloud of the SAME size (no allocation, no host synchronisation). */
+DFB_API int dfb_grid_update(dfb_grid* grid, const float* d_points, dfb_stream stream);
 DFB_API int dfb_grid_destroy(dfb_grid* grid);
 
 /* Exact k nearest neighbours of q_count query points.  Queries are points of the cloud:

@@ -69,9 +69,10 @@ def test_umma_gemm_points_as_rows(shape, nprod):
 
 
 @pytest.mark.parametrize("nprod", [3, 1])
+@pytest.mark.parametrize("N", [256, 1024])
 @pytest.mark.parametrize("k_pts", [128, 256, 512])
-def test_umma_gemm_channels_as_rows_with_maxpool(k_pts, nprod):
-    n_patch, N, K = 5, 256, 128
+def test_umma_gemm_channels_as_rows_with_maxpool(k_pts, N, nprod):
+    n_patch, K = 5, 128
     g = torch.Generator(device="cuda").manual_seed(k_pts)
     A = torch.randn(n_patch * k_pts, K, device="cuda", generator=g)
     W = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
