@@ -298,7 +298,7 @@ def main():
                     "d2h_bytes_per_step": int((end - begin) * (12 + 16))},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm_kernel<2,EPI_MAX> (128->1024 + max-pool, 3 per forward)",
+            "roofline": {"bound": "tensor", "kernel": "gemm_max_resident_kernel<k/128> (128->1024 + max-pool, 3 per forward)",
                          "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s",
                          "frac": (achieved / tf_sus) if achieved else None, "traffic": None,
                          "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained" % which,
