@@ -127,10 +127,22 @@ def cpu_reference_rate(points: np.ndarray, sample: int, seed: int = 0):
     return sample / dt, dt, t_tree
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        pass
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     pts = make_cloud(args.points * args.gpus)
     sample = args.ref_sample
     for _ in range(args.warmup):
@@ -309,7 +321,8 @@ def main():
             "kernel_ms": {k_: round(v[0], 3) for k_, v in prof.items()},
             "stages_one_chunk": stages,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N=1 only
+            use_all_host_threads()
             r, dt, t_tree = cpu_reference_rate(pts_host.numpy(), args.ref_sample)
             line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": "%d random query points of the same cloud in %.1f s; cKDTree(workers=-1) + torch CPU, "
