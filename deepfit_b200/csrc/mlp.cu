@@ -557,6 +557,247 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_max_resident_kernel(const G
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ------------------------------------------------------------- fused head: 64->512 (+global bias) -> 512->256
+// One CTA per 128-point row tile.  The 512-wide activation h1 = relu(W1p pf + hg[patch]) never
+// leaves the SM: it is produced 64 channels at a time (MMA into one of two 64-column TMEM buffers,
+// epilogue adds the per-patch bias, applies ReLU, re-splits to hi/lo bf16 and writes the chunk into
+// shared memory in UMMA operand layout), and each chunk is immediately consumed as one k-block of
+// the 512->256 layer, whose accumulator (256 TMEM columns) lives for the whole tile.  W1p is streamed
+// in 64-row chunks (custom 8 KB blocks, LBO 1024), W2 in (k-block, n-tile) stages of 32 KB.
+// Saves writing and re-reading h1 (2 KB/point) and one kernel launch.
+struct HeadArgs {
+    const bf16* pf;      // tiled [rows, 64], hi plane; lo at +pf_plane
+    size_t pf_plane;
+    const bf16* w1c;     // 8 chunks x [hi 8 KB | lo 8 KB]
+    const bf16* w2;      // tiled [256, 512] hi; lo at +w2_plane
+    size_t w2_plane;
+    const float* hg;     // fp32 [patch, 512] per-patch bias of layer 1
+    const float* b2;     // fp32 [256]
+    int rows_per_patch;
+    long long m_valid;
+    int nprod;
+    bf16* out_t;         // tiled [rows, 256]
+    size_t out_plane;
+    int out_KB;
+    int* err;
+};
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs g) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_pf, s_w1f[2], s_w1e[2], s_w2f[3], s_w2e[3], s_d1f[2], s_d1e[2], s_h1f[2], s_h1e[2], s_d2f;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_hg[512];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int planes = g.nprod > 1 ? 2 : 1;
+    const long long tile = blockIdx.x;
+    const long long patch = (tile * 128) / g.rows_per_patch;
+    // shared-memory map (bytes); every region sized for two planes
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t PF = smem_base;                 // 32 KB : hi block | lo block
+    const uint32_t W1R = smem_base + 32 * 1024;    // 2 x 16 KB : [hi 8 KB | lo 8 KB]
+    const uint32_t H1R = smem_base + 64 * 1024;    // 2 x 32 KB : [hi 16 KB | lo 16 KB]
+    const uint32_t W2R = smem_base + 128 * 1024;   // 3 x 32 KB : [hi 16 KB | lo 16 KB]
+    constexpr uint32_t kTmemCols = 512;            // D2: [0,256)  D1 buffers: [256,320) [320,384)
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&s_pf), 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&s_w1f[i]), 1); mbar_init(smem_u32(&s_w1e[i]), 1);
+            mbar_init(smem_u32(&s_d1f[i]), 1); mbar_init(smem_u32(&s_d1e[i]), 4);
+            mbar_init(smem_u32(&s_h1f[i]), 4); mbar_init(smem_u32(&s_h1e[i]), 1);
+        }
+        for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&s_w2f[i]), 1); mbar_init(smem_u32(&s_w2e[i]), 1); }
+        mbar_init(smem_u32(&s_d2f), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(&s_tmem), kTmemCols);
+        tmem_relinquish();
+    }
+    if (warp >= 2) {
+        const int t = threadIdx.x - 64;
+        for (int c = t; c < 512; c += 128) s_hg[c] = g.hg[patch * 512 + c];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            bool ok = true;
+            {
+                const uint32_t bar = smem_u32(&s_pf);
+                mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
+                for (int pl = 0; pl < planes; ++pl)
+                    bulk_g2s(PF + (uint32_t)pl * kBlkBytes, g.pf + (size_t)pl * g.pf_plane + (size_t)tile * kBlkElems, kBlkBytes, bar);
+            }
+            auto load_w1 = [&](int c) {
+                const int s = c & 1;
+                if (!mbar_wait(smem_u32(&s_w1e[s]), ((uint32_t)(c >> 1) & 1u) ^ 1u, g.err, 1)) { ok = false; return; }
+                const uint32_t bar = smem_u32(&s_w1f[s]);
+                mbar_expect_tx(bar, (uint32_t)planes * 8192u);
+                bulk_g2s(W1R + (uint32_t)s * 16384u, g.w1c + (size_t)c * 8192, (uint32_t)planes * 8192u, bar);  // hi|lo contiguous
+            };
+            int w2i = 0;
+            auto load_w2 = [&](int c, int t) {
+                const int s = w2i % 3;
+                if (!mbar_wait(smem_u32(&s_w2e[s]), ((uint32_t)(w2i / 3) & 1u) ^ 1u, g.err, 1)) { ok = false; return; }
+                const uint32_t bar = smem_u32(&s_w2f[s]);
+                mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
+                for (int pl = 0; pl < planes; ++pl)
+                    bulk_g2s(W2R + (uint32_t)s * 32768u + (uint32_t)pl * kBlkBytes,
+                             g.w2 + (size_t)pl * g.w2_plane + ((size_t)t * 8 + c) * kBlkElems, kBlkBytes, bar);
+                ++w2i;
+            };
+            load_w1(0);
+            if (ok) load_w1(1);
+            for (int c = 0; c < 8 && ok; ++c) {
+                load_w2(c, 0);
+                if (ok) load_w2(c, 1);
+                if (ok && c + 2 < 8) load_w1(c + 2);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc64 = umma_idesc(64), idesc128 = umma_idesc(128);
+            bool ok = mbar_wait(smem_u32(&s_pf), 0u, g.err, 2);
+            auto mma1 = [&](int c) {   // D1[c&1] = pf * W1chunk(c)^T
+                const int b = c & 1;
+                const uint32_t use = (uint32_t)(c >> 1);
+                if (!mbar_wait(smem_u32(&s_w1f[b]), use & 1u, g.err, 2)) { ok = false; return; }
+                if (use > 0 && !mbar_wait(smem_u32(&s_d1e[b]), (use - 1u) & 1u, g.err, 4)) { ok = false; return; }
+                tc_fence_after();
+                const uint32_t d = tmem_base + 256u + (uint32_t)b * 64u;
+                const uint32_t w_hi = W1R + (uint32_t)b * 16384u, w_lo = w_hi + 8192u;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t ka = (uint32_t)ks * 2 * kLBO, kw = (uint32_t)ks * 2 * 1024u;
+                    umma_bf16(d, umma_desc(PF + ka, kLBO, kSBO), umma_desc(w_hi + kw, 1024u, kSBO), idesc64, ks ? 1u : 0u);
+                    if (g.nprod > 1) {
+                        umma_bf16(d, umma_desc(PF + ka, kLBO, kSBO), umma_desc(w_lo + kw, 1024u, kSBO), idesc64, 1u);
+                        umma_bf16(d, umma_desc(PF + kBlkBytes + ka, kLBO, kSBO), umma_desc(w_hi + kw, 1024u, kSBO), idesc64, 1u);
+                    }
+                }
+                umma_commit(smem_u32(&s_w1e[b]));
+                umma_commit(smem_u32(&s_d1f[b]));
+            };
+            int w2i = 0;
+            auto mma2 = [&](int c) {   // D2 += h1chunk(c) * W2[:, 64c..64c+64]^T
+                const int b = c & 1;
+                const uint32_t use = (uint32_t)(c >> 1);
+                if (!mbar_wait(smem_u32(&s_h1f[b]), use & 1u, g.err, 5)) { ok = false; return; }
+                const uint32_t a_hi = H1R + (uint32_t)b * 32768u, a_lo = a_hi + kBlkBytes;
+                for (int t = 0; t < 2; ++t) {
+                    const int s = w2i % 3;
+                    if (!mbar_wait(smem_u32(&s_w2f[s]), (uint32_t)(w2i / 3) & 1u, g.err, 2)) { ok = false; return; }
+                    tc_fence_after();
+                    const uint32_t b_hi = W2R + (uint32_t)s * 32768u, b_lo = b_hi + kBlkBytes;
+                    const uint32_t d = tmem_base + (uint32_t)t * 128u;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t koff = (uint32_t)ks * 2 * kLBO;
+                        umma_bf16(d, umma_desc(a_hi + koff, kLBO, kSBO), umma_desc(b_hi + koff, kLBO, kSBO), idesc128, (c == 0 && ks == 0) ? 0u : 1u);
+                        if (g.nprod > 1) {
+                            umma_bf16(d, umma_desc(a_hi + koff, kLBO, kSBO), umma_desc(b_lo + koff, kLBO, kSBO), idesc128, 1u);
+                            umma_bf16(d, umma_desc(a_lo + koff, kLBO, kSBO), umma_desc(b_hi + koff, kLBO, kSBO), idesc128, 1u);
+                        }
+                    }
+                    umma_commit(smem_u32(&s_w2e[s]));
+                    ++w2i;
+                }
+                umma_commit(smem_u32(&s_h1e[b]));
+            };
+            if (ok) mma1(0);
+            for (int c = 0; c < 8 && ok; ++c) {
+                if (c + 1 < 8) mma1(c + 1);
+                if (ok) mma2(c);
+            }
+            if (ok) umma_commit(smem_u32(&s_d2f));
+        }
+    } else {
+        const int q = warp & 3;
+        const int lrow = q * 32 + lane;
+        const long long row = tile * 128 + lrow;
+        const uint32_t tlane = (uint32_t)(q * 32) << 16;
+        uint32_t v[32];
+        bool ok = true;
+        for (int c = 0; c < 8 && ok; ++c) {
+            const int b = c & 1;
+            const uint32_t use = (uint32_t)(c >> 1);
+            ok = mbar_wait(smem_u32(&s_d1f[b]), use & 1u, g.err, 3);
+            if (!ok) break;
+            tc_fence_after();
+            float f[64];
+            tmem_ld32(tmem_base + tlane + 256u + (uint32_t)b * 64u, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + s_hg[c * 64 + i], 0.f);
+            tmem_ld32(tmem_base + tlane + 256u + (uint32_t)b * 64u + 32u, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[32 + i] = fmaxf(__uint_as_float(v[i]) + s_hg[c * 64 + 32 + i], 0.f);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_d1e[b]));
+            if (use > 0) {
+                ok = mbar_wait(smem_u32(&s_h1e[b]), (use - 1u) & 1u, g.err, 6);
+                if (!ok) break;
+            }
+            const uint32_t h_hi = H1R + (uint32_t)b * 32768u + (uint32_t)(lrow >> 3) * 128u + (uint32_t)(lrow & 7) * 16u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    bf16 h0, l0, h1, l1;
+                    split_bf16(f[j * 8 + 2 * e], h0, l0);
+                    split_bf16(f[j * 8 + 2 * e + 1], h1, l1);
+                    ph[e] = pack2(h0, h1);
+                    pl[e] = pack2(l0, l1);
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_hi + (uint32_t)j * 2048u), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
+                if (g.nprod > 1)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_hi + kBlkBytes + (uint32_t)j * 2048u), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
+            }
+            fence_async_smem();   // generic-proxy writes -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_h1f[b]));
+        }
+        if (ok) ok = mbar_wait(smem_u32(&s_d2f), 0u, g.err, 3);
+        tc_fence_after();
+        if (ok) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < 256; c0 += 32) {
+                tmem_ld32(tmem_base + tlane + (uint32_t)c0, v);
+                if (row >= g.m_valid) continue;
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    uint32_t ph[4], pl[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i0 = c8 * 8 + 2 * e;
+                        const float x0 = fmaxf(__uint_as_float(v[i0]) + __ldg(g.b2 + c0 + i0), 0.f);
+                        const float x1 = fmaxf(__uint_as_float(v[i0 + 1]) + __ldg(g.b2 + c0 + i0 + 1), 0.f);
+                        bf16 h0, l0, h1, l1;
+                        split_bf16(x0, h0, l0);
+                        split_bf16(x1, h1, l1);
+                        ph[e] = pack2(h0, h1);
+                        pl[e] = pack2(l0, l1);
+                    }
+                    const size_t o = tiled_offset(row, c0 + c8 * 8, g.out_KB);
+                    *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                    if (g.nprod > 1) *reinterpret_cast<uint4*>(g.out_t + g.out_plane + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 // --------------------------------------------------------------------------- small CUDA-core kernels
 
 // fp32 row-major [rows, cols] (ld) -> tiled hi/lo planes; rows/cols beyond the source are zero.
@@ -750,6 +991,7 @@ struct dfb_model {
     dfb::PackedLayer head_global;  // HEAD_CONV1 columns 0..1023  (bias = folded conv1 bias)
     dfb::PackedLayer head_point;   // HEAD_CONV1 columns 1024..1087 (no bias of its own)
     float* w_small[DFB_NUM_LAYERS] = {nullptr};  // raw fp32 weights of the CUDA-core layers
+    dfb::bf16* head_w1c = nullptr;               // HEAD_CONV1 point part in 64-row chunks for the fused head
     // workspace
     dfb::TiledBuf x64a, x64b, x64c, x128, h512, h256, gfeat, f512, f256, t2blk;
     float* f256_f = nullptr;  // fp32 [max_batch,256]
@@ -799,6 +1041,31 @@ struct ProfScope {
 
 namespace dfb {
 namespace {
+
+int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, const float* hg, const PackedLayer& W2,
+                      TiledBuf& out, cudaStream_t st) {
+    HeadArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pf = pf.p; a.pf_plane = pf.plane;
+    a.w1c = m->head_w1c;
+    a.w2 = W2.w.p; a.w2_plane = W2.w.plane;
+    a.hg = hg; a.b2 = W2.bias;
+    a.rows_per_patch = m->k;
+    a.m_valid = rows;
+    a.nprod = m->nprod;
+    a.out_t = out.p; a.out_plane = out.plane; a.out_KB = out.KB;
+    a.err = m->err;
+    const size_t smem = 224 * 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return check_cuda(e, "head_fused smem attribute", __FILE__, __LINE__);
+        attr_done = true;
+    }
+    head_fused_kernel<<<(unsigned)((rows + 127) / 128), kGemmThreads, smem, st>>>(a);
+    note_launch();
+    return check_cuda(cudaGetLastError(), "head_fused_kernel launch", __FILE__, __LINE__);
+}
 
 int upload_pack(const float* h_w, int out, int in, int col0, int ncols, long long ldw, PackedLayer& pl, cudaStream_t st,
                 const int* row_perm = nullptr) {
@@ -895,6 +1162,45 @@ int launch_max_resident(GemmArgs g, long long n_patch, cudaStream_t st) {
     return check_cuda(cudaGetLastError(), "gemm_max_resident_kernel launch", __FILE__, __LINE__);
 }
 
+int g_head_fused = 1;  // debug switch (dfb_dbg_set key 2): 0 = separate 64->512 and 512->256 launches
+
+static inline uint16_t host_bf16(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);  // round to nearest even
+    return (uint16_t)(u >> 16);
+}
+static inline float host_bf16_to_f(uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// HEAD_CONV1[:, 1024:1088] (512 x 64) -> 8 chunks of 64 output channels, each [hi 8 KB | lo 8 KB] in
+// K-major core-matrix order [k-chunk j][row-group i][8 rows][8 elements] (LBO 1024 B, SBO 128 B).
+int upload_head_w1_chunks(const float* h_w, long long ldw, int col0, bf16** d_out, cudaStream_t st) {
+    std::vector<uint16_t> buf((size_t)8 * 8192);
+    for (int c = 0; c < 8; ++c)
+        for (int r = 0; r < 64; ++r)
+            for (int kc = 0; kc < 64; ++kc) {
+                const float v = h_w[(size_t)(c * 64 + r) * ldw + col0 + kc];
+                const uint16_t hi = host_bf16(v);
+                const uint16_t lo = host_bf16(v - host_bf16_to_f(hi));
+                const size_t o = (size_t)c * 8192 + (size_t)(kc >> 3) * 512 + (size_t)(r >> 3) * 64 + (size_t)(r & 7) * 8 + (kc & 7);
+                buf[o] = hi;
+                buf[o + 4096] = lo;
+            }
+    DFB_CUDA(cudaMalloc(d_out, buf.size() * sizeof(uint16_t)));
+    DFB_CUDA(cudaMemcpyAsync(*d_out, buf.data(), buf.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    DFB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, const float* hg, const PackedLayer& W2,
+                      TiledBuf& out, cudaStream_t st);
+
 int g_max_resident = 1;  // debug switch (dfb_dbg_set key 1): 0 = one CTA per (patch, channel tile)
 
 // T orientation with fused max-pool: g[p, c] = act(max_j (W X_p^T)[c, j] + b[c])
@@ -956,6 +1262,7 @@ extern "C" int dfb_model_profile_read(dfb_model* m, double* ms, int64_t* launche
 extern "C" DFB_API int dfb_dbg_set(int key, int value) {
     if (key == 0) dfb::g_swap_lbo_sbo = value;
     if (key == 1) dfb::g_max_resident = value;
+    if (key == 2) dfb::g_head_fused = value;
     return DFB_OK;
 }
 
@@ -1021,6 +1328,8 @@ extern "C" int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, d
             track(m->head_point.w.p);
             m->head_global.bias = m->L[i].bias;
             m->head_point.bias = nullptr;
+            DFB_TRY(upload_head_w1_chunks(l.h_weight, 1088, 1024, &m->head_w1c, st));
+            track(m->head_w1c);
         } else if (i == DFB_L_STN_FC3) {
             // emit T2^T: output column n*64+kk takes the reference's row kk*64+n; +I is symmetric
             std::vector<int> perm(4096);
@@ -1195,13 +1504,18 @@ extern "C" int dfb_model_forward(dfb_model* m, const float* d_patch, int64_t n, 
             ProfScope ps(m, DFB_PROF_FC, st);
             DFB_RUN(gemm_n(m, m->gfeat, B, m->head_global, 0, nullptr, m->hg, 512, 0, nullptr, 0, st));
         }
-        {
+        if (g_head_fused) {
             ProfScope ps(m, DFB_PROF_HEAD, st);
-            DFB_RUN(gemm_n(m, m->x64c, rows, m->head_point, 1, &m->h512, nullptr, 0, k, m->hg, 512, st));
-        }
-        {
-            ProfScope ps(m, DFB_PROF_HEAD, st);
-            DFB_RUN(gemm_n(m, m->h512, rows, m->L[DFB_L_HEAD_CONV2], 1, &m->h256, nullptr, 0, k, nullptr, 0, st));
+            DFB_RUN(launch_head_fused(m, m->x64c, rows, m->hg, m->L[DFB_L_HEAD_CONV2], m->h256, st));
+        } else {
+            {
+                ProfScope ps(m, DFB_PROF_HEAD, st);
+                DFB_RUN(gemm_n(m, m->x64c, rows, m->head_point, 1, &m->h512, nullptr, 0, k, m->hg, 512, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_HEAD, st);
+                DFB_RUN(gemm_n(m, m->h512, rows, m->L[DFB_L_HEAD_CONV2], 1, &m->h256, nullptr, 0, k, nullptr, 0, st));
+            }
         }
         {
             ProfScope ps(m, DFB_PROF_HEAD, st);

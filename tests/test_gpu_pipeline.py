@@ -83,3 +83,57 @@ def test_cli_writes_reference_format(clouds, tmp_path):
     with pytest.raises(ValueError):   # the reference dies the same way for order 1 (tutorial_utils.py:204-205)
         compute_normals.main(["--input", str(inp), "--output_path", str(tmp_path / "o1"), "--mode", "classic",
                               "--k_neighbors", "64", "--jet_order", "1"])
+
+
+def test_deepfit_order4_k512_stress_shape(clouds):
+    """BASELINE config 4 shape (jet order 4, k=512) through the whole path vs the oracle on our patches."""
+    from deepfit_b200 import ops
+    from deepfit_b200.pipeline import NormalEstimator, model_from_state_dict
+    from oracle import deepfit_oracle as O
+    pts_np = O.normalize_cloud(clouds["Boxy_smooth100k"])[0]
+    pts = torch.from_numpy(pts_np).cuda()
+    sd = O.seeded_state_dict(2)
+    model = model_from_state_dict(sd, 512, 4, "sigmoid", "bf16x3")
+    est = NormalEstimator(pts, 512, mode="DeepFit", model=model, chunk=128)
+    begin, count = 40000, 192
+    normals, curv = est.run(begin, begin + count)
+    est.net.status()
+    idx, rad, dist = est.grid.query(512, q_begin=begin, q_count=count, return_dist=True)
+    ref_idx, ref_dist = O.knn_bruteforce(pts_np, np.arange(begin, begin + 32), 512)
+    assert np.array_equal(idx[:32].cpu().numpy(), ref_idx.astype(np.int32))
+    assert np.array_equal(dist[:32].cpu().numpy(), ref_dist)
+    patch, U = ops.patch_pca(pts, idx, rad, q_begin=begin)
+    with torch.no_grad():
+        n, beta, w, trans, t2, _ = O.deepfit_forward(sd, patch.cpu(), 4)
+        ref_n = O.world_normals(n, U.cpu(), trans).numpy()
+        # the exact (fp64) solution of the same weighted system bounds the reference's own fp32 error
+        w64, tr64 = w.double(), trans.double()
+        prot = torch.bmm(patch.cpu().double().transpose(1, 2), tr64).transpose(1, 2).contiguous()
+        _, n64 = O.fit_wjet(prot, w64, 4)
+        ex_n = O.world_normals(n64, U.cpu().double(), tr64).numpy()
+    ref_err = O.unoriented_angle_deg(ref_n, ex_n)
+    ang = O.unoriented_angle_deg(normals.cpu().numpy(), ref_n)
+    assert (ang <= np.maximum(0.01, 2 * ref_err)).all(), "max angular deviation %g deg" % ang.max()
+    assert tuple(curv.shape) == (count, 2) and bool(torch.isfinite(curv).all())
+
+
+def test_classic_orders_on_synthetic_sphere_and_torus():
+    """BASELINE config 2 shape at a reduced size: classic jet orders 1-4 on noisy analytic surfaces, every
+    point of the cloud; normals against the analytic ones, and bit-identical across chunk sizes."""
+    from deepfit_b200 import synthetic
+    from deepfit_b200.pipeline import NormalEstimator
+    raw = synthetic.torus_cloud(60000, seed=1234, noise=0.0)
+    pts = torch.from_numpy(raw).cuda()
+    u = np.arctan2(raw[:, 1], raw[:, 0])
+    centre = np.stack([np.cos(u), np.sin(u), np.zeros_like(u)], 1)
+    true_n = raw - centre
+    true_n /= np.linalg.norm(true_n, axis=1, keepdims=True)
+    for order in (1, 2, 3, 4):
+        est = NormalEstimator(pts, 64, jet_order=order, mode="classic", chunk=16384)
+        normals, curv = est.run()
+        cosang = np.abs((normals.cpu().numpy() * true_n).sum(1))
+        assert np.degrees(np.arccos(np.clip(cosang, 0, 1))).max() < (6.0 if order == 1 else 3.0)
+        assert (curv is None) == (order == 1)
+        est2 = NormalEstimator(pts, 64, jet_order=order, mode="classic", chunk=5000)
+        n2, c2 = est2.run()
+        assert torch.equal(normals, n2) and (curv is None or torch.equal(curv, c2))
