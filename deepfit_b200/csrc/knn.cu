@@ -273,6 +273,12 @@ struct KnnArgs {
 
 constexpr int kKnnWarps = 4;
 
+// Visiting order of the 27 cells of a block: the query's own cell first, then the 6 face, 12 edge and
+// 8 corner neighbours.  Near cells first tightens the k-th-distance threshold early, so most later
+// candidates are rejected before insertion and far cells are skipped whole.  Index = x + 3y + 9z.
+__device__ __constant__ unsigned char c_cell_order[27] = {13, 12, 14, 10, 16, 4, 22, 9, 11, 15, 17, 3, 5, 21, 23, 1, 7, 19, 25,
+                                                          0, 2, 6, 8, 18, 20, 24, 26};
+
 __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -357,7 +363,8 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
             // (re)start the list
             int count = 0;
             bool full_once = false;  // list has been cut to k at least once => threshold is strict on list[k-1]
-            for (int c = 0; c < 27; ++c) {
+            for (int ci = 0; ci < 27; ++ci) {
+                const int c = c_cell_order[ci];
                 const uint32_t clo = __shfl_sync(0xffffffffu, lo, c), chi = __shfl_sync(0xffffffffu, hi, c);
                 const float cm2 = __shfl_sync(0xffffffffu, cmin2, c);
                 if (chi <= clo) continue;
@@ -402,8 +409,20 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                     count += __popc(bal);
                     __syncwarp();
                 }
+                // once the own cell / the face neighbours are in and no threshold exists yet, pay one sort to
+                // get one: everything farther than the current k-th best is then rejected without insertion
+                if ((ci == 0 || ci == 6 || ci == 18) && !full_once && count >= k) {
+                    for (int t = count + lane; t < cap; t += 32) { sd[t] = INF; si[t] = 0x7fffffff; }
+                    __syncwarp();
+                    warp_bitonic_sort(sd, si, cap, lane);
+                    count = k;
+                    Td = sd[k - 1];
+                    Ti = si[k - 1];
+                    thr_incl = false;
+                    full_once = true;
+                    __syncwarp();
+                }
             }
-            (void)full_once;
             // final sort of what we have
             for (int t = count + lane; t < cap; t += 32) { sd[t] = INF; si[t] = 0x7fffffff; }
             __syncwarp();

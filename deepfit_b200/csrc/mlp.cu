@@ -44,12 +44,14 @@ constexpr int kBlkBytes = kBlkElems * 2;
 constexpr uint32_t kLBO = 2048;  // bytes between adjacent 16-byte k-chunks (core matrices along K)
 constexpr uint32_t kSBO = 128;   // bytes between adjacent 8-row groups (core matrices along M/N)
 
-__host__ __device__ __forceinline__ size_t tiled_offset(long long row, int col, int KB) {
-    // element offset of (row, col) inside a tiled matrix with KB 64-column blocks per row tile
-    const long long rt = row >> 7;
-    const int r = (int)(row & 127);
+__host__ __device__ __forceinline__ size_t tiled_offset(long long row, int col, int KB, int br = 128) {
+    // element offset of (row, col) inside a tiled matrix with KB 64-column blocks per row tile of `br`
+    // rows (128, or 256 when the consumer issues N=256 MMAs: k-chunk stride LBO = br*16 bytes)
+    const long long rt = row / br;
+    const int r = (int)(row - rt * br);
     const int kb = col >> 6, c = col & 63;
-    return ((size_t)rt * KB + kb) * kBlkElems + (size_t)(c >> 3) * 1024 + (size_t)(r >> 3) * 64 + (size_t)(r & 7) * 8 + (c & 7);
+    return ((size_t)rt * KB + kb) * ((size_t)br * 64) + (size_t)(c >> 3) * ((size_t)br * 8) + (size_t)(r >> 3) * 64 +
+           (size_t)(r & 7) * 8 + (c & 7);
 }
 
 // -------------------------------------------------------------------------------------------- PTX
@@ -167,6 +169,7 @@ struct GemmArgs {
     bf16* out_t;         // tiled (hi plane), may be NULL
     size_t out_plane;
     int out_KB;
+    int out_br;          // block rows of the tiled output (128 or 256)
     float* out_f;        // fp32 row-major, may be NULL
     long long ldo;
     // EPI_DOT
@@ -183,7 +186,7 @@ constexpr int kGemmThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer +
 
 template <int NT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, const int stages) {
-    extern __shared__ __align__(1024) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_full[8], s_empty[8], s_done;
     __shared__ uint32_t s_tmem;
     __shared__ float s_bias[NT * 128];
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
                                         ph[e] = pack2(h0, h1);
                                         plo[e] = pack2(l0, l1);
                                     }
-                                    const size_t o = tiled_offset(row, (int)col0 + c8 * 8, g.out_KB);
+                                    const size_t o = tiled_offset(row, (int)col0 + c8 * 8, g.out_KB, g.out_br);
                                     *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                                     if (g.nprod > 1)
                                         *reinterpret_cast<uint4*>(g.out_t + g.out_plane + o) = make_uint4(plo[0], plo[1], plo[2], plo[3]);
@@ -421,7 +424,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 template <int NT>
 __global__ void __launch_bounds__(kGemmThreads) gemm_max_resident_kernel(const GemmArgs g, const int wstages) {
-    extern __shared__ __align__(1024) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_xfull, s_wfull[4], s_wempty[4], s_tfull[2], s_tempty[2];
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -460,13 +463,13 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_max_resident_kernel(const G
         if (lane == 0) {
             const uint32_t xfull = smem_u32(&s_xfull);
             mbar_expect_tx(xfull, x_bytes);
+            // X is stored in blocks of NT*128 rows (one patch), so each (plane, k-block) is one copy
             uint32_t dst = smem_base;
             for (int pl = 0; pl < planes; ++pl)
-                for (int t = 0; t < NT; ++t)
-                    for (int kb = 0; kb < KB; ++kb) {
-                        bulk_g2s(dst, g.B + (size_t)pl * g.b_plane + ((size_t)(patch * NT + t) * KB + kb) * kBlkElems, kBlkBytes, xfull);
-                        dst += kBlkBytes;
-                    }
+                for (int kb = 0; kb < KB; ++kb) {
+                    bulk_g2s(dst, g.B + (size_t)pl * g.b_plane + ((size_t)patch * KB + kb) * ((size_t)NT * kBlkElems), NT * kBlkBytes, xfull);
+                    dst += NT * kBlkBytes;
+                }
             const int total = CT * KB;
             for (int i = 0; i < total; ++i) {
                 const int s = i % wstages;
@@ -481,7 +484,8 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_max_resident_kernel(const G
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc(128);
+            const uint32_t idesc = umma_idesc(NT * 128);   // one MMA spans the whole patch (N = k)
+            const uint32_t lbo_b = (uint32_t)NT * kLBO;
             bool ok = mbar_wait(smem_u32(&s_xfull), 0u, g.err, 2);
             for (int ct = 0; ct < CT && ok; ++ct) {
                 const int buf = ct & 1;
@@ -497,19 +501,18 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_max_resident_kernel(const G
                     tc_fence_after();
                     const uint32_t a_hi = w_base + (uint32_t)s * w_stage_bytes;
                     const uint32_t a_lo = a_hi + kBlkBytes;
-#pragma unroll
-                    for (int t = 0; t < NT; ++t) {
-                        const uint32_t b_hi = smem_base + (uint32_t)((0 * NT + t) * KB + kb) * kBlkBytes;
-                        const uint32_t b_lo = smem_base + (uint32_t)((1 * NT + t) * KB + kb) * kBlkBytes;
-                        const uint32_t d = tmem_base + (uint32_t)(buf * NT * 128 + t * 128);
+                    {
+                        const uint32_t b_hi = smem_base + (uint32_t)(0 * KB + kb) * (NT * kBlkBytes);
+                        const uint32_t b_lo = smem_base + (uint32_t)(1 * KB + kb) * (NT * kBlkBytes);
+                        const uint32_t d = tmem_base + (uint32_t)(buf * NT * 128);
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            const uint32_t koff = (uint32_t)ks * 2 * g.lbo;
+                            const uint32_t ka = (uint32_t)ks * 2 * kLBO, kb_off = (uint32_t)ks * 2 * lbo_b;
                             const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-                            umma_bf16(d, umma_desc(a_hi + koff, g.lbo, g.sbo), umma_desc(b_hi + koff, g.lbo, g.sbo), idesc, first);
+                            umma_bf16(d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(b_hi + kb_off, lbo_b, kSBO), idesc, first);
                             if (g.nprod > 1) {
-                                umma_bf16(d, umma_desc(a_hi + koff, g.lbo, g.sbo), umma_desc(b_lo + koff, g.lbo, g.sbo), idesc, 1u);
-                                umma_bf16(d, umma_desc(a_lo + koff, g.lbo, g.sbo), umma_desc(b_hi + koff, g.lbo, g.sbo), idesc, 1u);
+                                umma_bf16(d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(b_lo + kb_off, lbo_b, kSBO), idesc, 1u);
+                                umma_bf16(d, umma_desc(a_lo + ka, kLBO, kSBO), umma_desc(b_hi + kb_off, lbo_b, kSBO), idesc, 1u);
                             }
                         }
                     }
@@ -642,14 +645,16 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
                 bulk_g2s(W1R + (uint32_t)s * 16384u, g.w1c + (size_t)c * 8192, (uint32_t)planes * 8192u, bar);  // hi|lo contiguous
             };
             int w2i = 0;
-            auto load_w2 = [&](int c, int t) {
+            // W2 is packed in 256-row blocks (all 256 output channels of one 64-wide k-block = 32 KB per
+            // plane); a stage is half a block: k-chunks 4h..4h+3 = 16 KB per plane, contiguous
+            auto load_w2 = [&](int c, int h) {
                 const int s = w2i % 3;
                 if (!mbar_wait(smem_u32(&s_w2e[s]), ((uint32_t)(w2i / 3) & 1u) ^ 1u, g.err, 1)) { ok = false; return; }
                 const uint32_t bar = smem_u32(&s_w2f[s]);
                 mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
                 for (int pl = 0; pl < planes; ++pl)
                     bulk_g2s(W2R + (uint32_t)s * 32768u + (uint32_t)pl * kBlkBytes,
-                             g.w2 + (size_t)pl * g.w2_plane + ((size_t)t * 8 + c) * kBlkElems, kBlkBytes, bar);
+                             g.w2 + (size_t)pl * g.w2_plane + (size_t)c * (2 * kBlkElems) + (size_t)h * kBlkElems, kBlkBytes, bar);
                 ++w2i;
             };
             load_w1(0);
@@ -662,7 +667,7 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc64 = umma_idesc(64), idesc128 = umma_idesc(128);
+            const uint32_t idesc64 = umma_idesc(64), idesc256 = umma_idesc(256);
             bool ok = mbar_wait(smem_u32(&s_pf), 0u, g.err, 2);
             auto mma1 = [&](int c) {   // D1[c&1] = pf * W1chunk(c)^T
                 const int b = c & 1;
@@ -690,19 +695,21 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
                 const uint32_t use = (uint32_t)(c >> 1);
                 if (!mbar_wait(smem_u32(&s_h1f[b]), use & 1u, g.err, 5)) { ok = false; return; }
                 const uint32_t a_hi = H1R + (uint32_t)b * 32768u, a_lo = a_hi + kBlkBytes;
-                for (int t = 0; t < 2; ++t) {
+                for (int h = 0; h < 2; ++h) {
                     const int s = w2i % 3;
                     if (!mbar_wait(smem_u32(&s_w2f[s]), (uint32_t)(w2i / 3) & 1u, g.err, 2)) { ok = false; return; }
                     tc_fence_after();
                     const uint32_t b_hi = W2R + (uint32_t)s * 32768u, b_lo = b_hi + kBlkBytes;
-                    const uint32_t d = tmem_base + (uint32_t)t * 128u;
+                    const uint32_t d = tmem_base;   // one N=256 accumulator
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t koff = (uint32_t)ks * 2 * kLBO;
-                        umma_bf16(d, umma_desc(a_hi + koff, kLBO, kSBO), umma_desc(b_hi + koff, kLBO, kSBO), idesc128, (c == 0 && ks == 0) ? 0u : 1u);
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t ka = (uint32_t)(h * 4 + ks * 2) * kLBO;   // k-chunk 4h+2ks of the h1 block
+                        const uint32_t kw = (uint32_t)ks * 2 * (2 * kLBO);       // 256-row block: LBO = 4096
+                        umma_bf16(d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(b_hi + kw, 2 * kLBO, kSBO), idesc256,
+                                  (c == 0 && h == 0 && ks == 0) ? 0u : 1u);
                         if (g.nprod > 1) {
-                            umma_bf16(d, umma_desc(a_hi + koff, kLBO, kSBO), umma_desc(b_lo + koff, kLBO, kSBO), idesc128, 1u);
-                            umma_bf16(d, umma_desc(a_lo + koff, kLBO, kSBO), umma_desc(b_hi + koff, kLBO, kSBO), idesc128, 1u);
+                            umma_bf16(d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(b_lo + kw, 2 * kLBO, kSBO), idesc256, 1u);
+                            umma_bf16(d, umma_desc(a_lo + ka, kLBO, kSBO), umma_desc(b_hi + kw, 2 * kLBO, kSBO), idesc256, 1u);
                         }
                     }
                     umma_commit(smem_u32(&s_w2e[s]));
@@ -802,7 +809,7 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
 
 // fp32 row-major [rows, cols] (ld) -> tiled hi/lo planes; rows/cols beyond the source are zero.
 __global__ void pack_tiled_kernel(const float* __restrict__ src, long long rows, int cols, long long ld,
-                                  long long rows_pad, int cols_pad, bf16* __restrict__ dst, size_t plane, int split) {
+                                  long long rows_pad, int cols_pad, bf16* __restrict__ dst, size_t plane, int split, int br) {
     const long long total = rows_pad * (cols_pad / 8);
     const int KB = cols_pad / 64;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -821,7 +828,7 @@ __global__ void pack_tiled_kernel(const float* __restrict__ src, long long rows,
             ph[e] = pack2(h0, h1);
             pl[e] = pack2(l0, l1);
         }
-        const size_t o = tiled_offset(r, c8 * 8, KB);
+        const size_t o = tiled_offset(r, c8 * 8, KB, br);
         *reinterpret_cast<uint4*>(dst + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
         if (split) *reinterpret_cast<uint4*>(dst + plane + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
@@ -829,12 +836,12 @@ __global__ void pack_tiled_kernel(const float* __restrict__ src, long long rows,
 
 // tiled (hi [+ lo]) -> fp32 row-major, for tests
 __global__ void unpack_tiled_kernel(const bf16* __restrict__ src, size_t plane, int split, long long rows, int cols,
-                                    int KB, float* __restrict__ dst) {
+                                    int KB, float* __restrict__ dst, int br) {
     const long long total = rows * cols;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / cols;
         const int c = (int)(i % cols);
-        const size_t o = tiled_offset(r, c, KB);
+        const size_t o = tiled_offset(r, c, KB, br);
         float v = __bfloat162float(src[o]);
         if (split) v += __bfloat162float(src[plane + o]);
         dst[i] = v;
@@ -965,10 +972,12 @@ struct TiledBuf {
     size_t plane = 0;  // elements per plane
     int KB = 0;
     long long rows_pad = 0;
+    int br = 128;      // rows per block
 };
 
-int alloc_tiled(TiledBuf& t, long long rows, int cols) {
-    t.rows_pad = (rows + 127) / 128 * 128;
+int alloc_tiled(TiledBuf& t, long long rows, int cols, int br = 128) {
+    t.br = br;
+    t.rows_pad = (rows + br - 1) / br * br;
     t.KB = (cols + 63) / 64;
     t.plane = (size_t)t.rows_pad * t.KB * 64;
     DFB_CUDA(cudaMalloc(&t.p, t.plane * 2 * sizeof(bf16)));
@@ -992,6 +1001,7 @@ struct dfb_model {
     dfb::PackedLayer head_point;   // HEAD_CONV1 columns 1024..1087 (no bias of its own)
     float* w_small[DFB_NUM_LAYERS] = {nullptr};  // raw fp32 weights of the CUDA-core layers
     dfb::bf16* head_w1c = nullptr;               // HEAD_CONV1 point part in 64-row chunks for the fused head
+    dfb::PackedLayer head_w2_256;                // HEAD_CONV2 in 256-row blocks (N=256 MMAs of the fused head)
     // workspace
     dfb::TiledBuf x64a, x64b, x64c, x128, h512, h256, gfeat, f512, f256, t2blk;
     float* f256_f = nullptr;  // fp32 [max_batch,256]
@@ -1068,7 +1078,7 @@ int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, co
 }
 
 int upload_pack(const float* h_w, int out, int in, int col0, int ncols, long long ldw, PackedLayer& pl, cudaStream_t st,
-                const int* row_perm = nullptr) {
+                const int* row_perm = nullptr, int br = 128) {
     // host fp32 [out, ldw] (columns col0..col0+ncols) -> device tiled hi/lo
     std::vector<float> tmp((size_t)out * ncols);
     for (int r = 0; r < out; ++r) {
@@ -1078,13 +1088,13 @@ int upload_pack(const float* h_w, int out, int in, int col0, int ncols, long lon
     float* d_tmp = nullptr;
     DFB_CUDA(cudaMalloc(&d_tmp, tmp.size() * sizeof(float)));
     DFB_CUDA(cudaMemcpyAsync(d_tmp, tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-    int rc = alloc_tiled(pl.w, out, ncols);
+    int rc = alloc_tiled(pl.w, out, ncols, br);
     if (rc) return rc;
     pl.in = ncols;
     pl.out = out;
     const long long total = pl.w.rows_pad * (pl.w.KB * 8);
     pack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_tmp, out, ncols, ncols, pl.w.rows_pad, pl.w.KB * 64,
-                                                                        pl.w.p, pl.w.plane, 1);
+                                                                        pl.w.p, pl.w.plane, 1, pl.w.br);
     note_launch();
     DFB_CUDA(cudaGetLastError());
     DFB_CUDA(cudaStreamSynchronize(st));
@@ -1130,7 +1140,7 @@ int gemm_n(const dfb_model* m, const TiledBuf& X, long long n_rows, const Packed
     const int n_out = perpatch_B ? 64 : W.out;
     g.n_valid = n_out;
     g.n_mma = n_out < 128 ? 64 : 128;
-    if (out) { g.out_t = out->p; g.out_plane = out->plane; g.out_KB = out->KB; }
+    if (out) { g.out_t = out->p; g.out_plane = out->plane; g.out_KB = out->KB; g.out_br = out->br; }
     g.out_f = out_f; g.ldo = ldo;
     g.trans2 = trans2;
     if (epi == EPI_DOT) { g.w4 = m->w_small[DFB_L_HEAD_CONV4]; }
@@ -1214,12 +1224,16 @@ int gemm_t_max(const dfb_model* m, const PackedLayer& W, const TiledBuf& X, long
     g.relu = relu;
     g.m_valid = n_patch;
     g.n_valid = W.out;
-    if (out) { g.out_t = out->p; g.out_plane = out->plane; g.out_KB = out->KB; }
+    if (out) { g.out_t = out->p; g.out_plane = out->plane; g.out_KB = out->KB; g.out_br = out->br; }
     g.out_f = out_f; g.ldo = W.out;
     const int NT = m->k / 128;
     const size_t x_bytes = (size_t)(m->nprod > 1 ? 2 : 1) * NT * g.KB * kBlkBytes;
-    if (g_max_resident && NT <= 2 && x_bytes + 2 * (size_t)(m->nprod > 1 ? 2 : 1) * kBlkBytes <= 225 * 1024) {
+    if (g_max_resident && NT <= 2 && X.br == NT * 128 && x_bytes + 2 * (size_t)(m->nprod > 1 ? 2 : 1) * kBlkBytes <= 225 * 1024) {
         return NT == 1 ? launch_max_resident<1>(g, n_patch, st) : launch_max_resident<2>(g, n_patch, st);
+    }
+    if (X.br != 128) {
+        set_error("gemm_t_max: the non-resident kernel needs 128-row activation blocks");
+        return DFB_E_INTERNAL;
     }
     dim3 grid((unsigned)(W.out / 128), (unsigned)n_patch);
     return launch_gemm(g, NT, EPI_MAX, grid, st);
@@ -1345,6 +1359,12 @@ extern "C" int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, d
                                "stn fc3 bias", __FILE__, __LINE__));
             DFB_TRY(check_cuda(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__));
         } else {
+            if (i == DFB_L_HEAD_CONV2) {
+                DFB_TRY(upload_pack(l.h_weight, l.out_features, l.in_features, 0, l.in_features, l.in_features, m->head_w2_256, st,
+                                    nullptr, 256));
+                track(m->head_w2_256.w.p);
+                m->head_w2_256.bias = m->L[i].bias;
+            }
             float* keep_bias = m->L[i].bias;
             DFB_TRY(upload_pack(l.h_weight, l.out_features, l.in_features, 0, l.in_features, l.in_features, m->L[i], st));
             m->L[i].bias = keep_bias;
@@ -1357,7 +1377,8 @@ extern "C" int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, d
     TiledBuf* bufs[] = {&m->x64a, &m->x64b, &m->x64c, &m->x128, &m->h512, &m->h256};
     const int widths[] = {64, 64, 64, 128, 512, 256};
     for (int i = 0; i < 6; ++i) {
-        DFB_TRY(alloc_tiled(*bufs[i], R, widths[i]));
+        // x128 feeds the resident max-pool kernel, which issues N=256 MMAs over 256-row blocks at k=256
+        DFB_TRY(alloc_tiled(*bufs[i], R, widths[i], (bufs[i] == &m->x128 && m->k == 256) ? 256 : 128));
         track(bufs[i]->p);
     }
     DFB_TRY(alloc_tiled(m->gfeat, Bp, 1024)); track(m->gfeat.p);
@@ -1506,7 +1527,7 @@ extern "C" int dfb_model_forward(dfb_model* m, const float* d_patch, int64_t n, 
         }
         if (g_head_fused) {
             ProfScope ps(m, DFB_PROF_HEAD, st);
-            DFB_RUN(launch_head_fused(m, m->x64c, rows, m->hg, m->L[DFB_L_HEAD_CONV2], m->h256, st));
+            DFB_RUN(launch_head_fused(m, m->x64c, rows, m->hg, m->head_w2_256, m->h256, st));
         } else {
             {
                 ProfScope ps(m, DFB_PROF_HEAD, st);
@@ -1539,7 +1560,7 @@ extern "C" DFB_API int dfb_dbg_model_dump(dfb_model* m, int32_t which, int64_t r
     TiledBuf* t = bufs[which];
     DFB_REQUIRE(rows <= t->rows_pad && cols <= t->KB * 64, DFB_E_ARG, "dfb_dbg_model_dump: shape exceeds the buffer");
     const long long total = rows * (long long)cols;
-    unpack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(t->p, t->plane, m->nprod > 1, rows, cols, t->KB, d_out);
+    unpack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(t->p, t->plane, m->nprod > 1, rows, cols, t->KB, d_out, t->br);
     return check_cuda(cudaGetLastError(), "unpack", __FILE__, __LINE__);
 }
 
@@ -1558,11 +1579,11 @@ extern "C" DFB_API int dfb_dbg_gemm(const float* d_A, const float* d_B, const fl
     DFB_CUDA(cudaMalloc(&fake.err, sizeof(int)));
     DFB_CUDA(cudaMemsetAsync(fake.err, 0, sizeof(int), st));
     TiledBuf tA, tB, tO;
-    rc = alloc_tiled(tA, M, K); if (rc) return rc;
+    rc = alloc_tiled(tA, M, K, (mode == 1 && k_pts == 256) ? 256 : 128); if (rc) return rc;
     rc = alloc_tiled(tB, N, K); if (rc) return rc;
     auto pack = [&](const float* src, long long rows, int cols, TiledBuf& t) {
         const long long total = t.rows_pad * (t.KB * 8);
-        pack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, rows, cols, cols, t.rows_pad, t.KB * 64, t.p, t.plane, 1);
+        pack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, rows, cols, cols, t.rows_pad, t.KB * 64, t.p, t.plane, 1, t.br);
     };
     pack(d_A, M, K, tA);
     pack(d_B, N, K, tB);
@@ -1575,7 +1596,7 @@ extern "C" DFB_API int dfb_dbg_gemm(const float* d_A, const float* d_B, const fl
         rc = gemm_n(&fake, tA, M, W, relu, &tO, d_out, N, k_pts, nullptr, 0, st);
         if (rc == 0 && d_out_tiled_unpacked) {
             const long long total = M * (long long)N;
-            unpack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tO.p, tO.plane, nprod > 1, M, N, tO.KB, d_out_tiled_unpacked);
+            unpack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tO.p, tO.plane, nprod > 1, M, N, tO.KB, d_out_tiled_unpacked, tO.br);
         }
     } else {
         // A = activations [M = n_patch*k_pts, K], B = weights [N, K]; out [n_patch, N]
@@ -1586,7 +1607,7 @@ extern "C" DFB_API int dfb_dbg_gemm(const float* d_A, const float* d_B, const fl
         rc = gemm_t_max(&fake, W, tA, n_patch, relu, &tO, d_out, st);
         if (rc == 0 && d_out_tiled_unpacked) {
             const long long total = n_patch * (long long)N;
-            unpack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tO.p, tO.plane, nprod > 1, n_patch, N, tO.KB, d_out_tiled_unpacked);
+            unpack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tO.p, tO.plane, nprod > 1, n_patch, N, tO.KB, d_out_tiled_unpacked, tO.br);
         }
     }
     int h = 0;

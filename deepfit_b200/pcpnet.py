@@ -1,0 +1,163 @@
+"""PCPNet-style multi-shape inference with full outputs (BASELINE config 3).
+
+Mirrors the k-nearest-neighbour path of the reference's ``PointcloudPatchDataset`` (dataset.py:173-442:
+raw un-normalised points, ``center='point'``, patch scaled by the k-th neighbour distance, optional PCA,
+optional sparse ``.pidx`` centres, sequential order) and the export loop of ``test_c_est.py:104-218``
+(per shape ``.normals [P,3] .curv [P,2] .weights [P,k] .beta [P,M] .trans [P,9]`` via ``np.savetxt``).
+Ball-query neighbourhoods, point tuples, density jitter and ground-truth features are training-time
+options and raise.  Unlike the reference nothing is written next to the input data (it drops ``.npy``
+copies into the dataset directory, dataset.py:227-264).
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .DeepFit import DeepFit
+from .tutorial_utils import load_xyz
+
+
+class PointcloudPatchDataset:
+    def __init__(self, root, shape_list_filename, patch_radius=None, points_per_patch=256, patch_features=(),
+                 seed=None, identical_epochs=False, use_pca=False, center='point', point_tuple=1, cache_capacity=1,
+                 point_count_std=0.0, sparse_patches=False, neighbor_search_method='k', device="cuda"):
+        if neighbor_search_method != 'k':
+            raise NotImplementedError("only neighbor_search_method='k' is built (ball query is next, SURVEY 8f-3)")
+        if center != 'point':
+            raise NotImplementedError("only center='point' is built (the pretrained configuration)")
+        if point_tuple != 1 or point_count_std != 0.0:
+            raise NotImplementedError("point tuples / density jitter are training-time options")
+        self.root = root
+        self.points_per_patch = int(points_per_patch)
+        self.use_pca = bool(use_pca)
+        self.sparse_patches = bool(sparse_patches)
+        self.device = torch.device(device)
+        with open(os.path.join(root, shape_list_filename)) as f:
+            self.shape_names: List[str] = [x.strip() for x in f.readlines() if x.strip()]
+        self.shape_patch_count: List[int] = []
+        self._pidx = []
+        for name in self.shape_names:
+            if self.sparse_patches:
+                pidx = np.loadtxt(os.path.join(root, name + '.pidx')).astype('int64').reshape(-1)
+                self._pidx.append(pidx)
+                self.shape_patch_count.append(len(pidx))
+            else:
+                self._pidx.append(None)
+                self.shape_patch_count.append(None)   # filled when the shape is loaded
+        self._loaded = (-1, None, None)
+
+    def __len__(self):
+        return sum(self._count(i) for i in range(len(self.shape_names)))
+
+    def _count(self, shape_ind):
+        if self.shape_patch_count[shape_ind] is None:
+            self.load_shape(shape_ind)
+        return self.shape_patch_count[shape_ind]
+
+    def load_shape(self, shape_ind):
+        """Points (raw, float32) on the device + their search grid; one shape resident at a time."""
+        if self._loaded[0] != shape_ind:
+            pts = load_xyz(os.path.join(self.root, self.shape_names[shape_ind] + '.xyz'))
+            gpu = torch.from_numpy(np.ascontiguousarray(pts, dtype=np.float32)).to(self.device)
+            if self._loaded[2] is not None:
+                self._loaded[2].close()
+            self._loaded = (shape_ind, gpu, ops.Grid(gpu))
+            if self.shape_patch_count[shape_ind] is None:
+                self.shape_patch_count[shape_ind] = int(gpu.shape[0])
+        return self._loaded[1], self._loaded[2]
+
+    def centres(self, shape_ind) -> Optional[torch.Tensor]:
+        p = self._pidx[shape_ind]
+        return None if p is None else torch.from_numpy(p.astype(np.int32)).to(self.device)
+
+    def patches(self, shape_ind, start, count):
+        """Patches ``start .. start+count`` of a shape (in ``.pidx`` order when sparse):
+        (patch f32 [B,3,k], trans f32 [B,3,3], patch_scale f64 [B]) -- the reference returns [k,3] per item
+        and its callers transpose (test_c_est.py:131)."""
+        pts, grid = self.load_shape(shape_ind)
+        centres = self.centres(shape_ind)
+        k = self.points_per_patch
+        if centres is None:
+            idx, rad = grid.query(k, q_begin=start, q_count=count)
+            patch, trans = ops.patch_pca(pts, idx, rad, q_begin=start, pca=self.use_pca)
+        else:
+            q = centres[start:start + count].contiguous()
+            idx, rad = grid.query(k, query=q)
+            patch, trans = ops.patch_pca(pts, idx, rad, query=q, pca=self.use_pca)
+        return patch, trans, rad
+
+
+def estimate_shapes(dataset: PointcloudPatchDataset, model: Optional[DeepFit], output_dir: str, jet_order: int = 3,
+                    batch: int = 4096, use_point_stn: bool = True, write: bool = True):
+    """Run every shape of the dataset and export the five per-shape files of test_c_est.py:201-210.
+    ``model=None`` runs the classic unweighted fit (weights file of ones, identity trans).
+    Returns {shape_name: dict of numpy arrays}."""
+    if write:
+        os.makedirs(output_dir, exist_ok=True)
+    results = {}
+    k = dataset.points_per_patch
+    net = model._network(dataset.device, max_batch=batch) if model is not None else None
+    order = model.jet_order if model is not None else jet_order
+    for si, name in enumerate(dataset.shape_names):
+        n_patch = dataset._count(si)
+        normal_prop = torch.zeros((n_patch, 3), dtype=torch.float32, device=dataset.device)
+        curv_prop = torch.zeros((n_patch, 2), dtype=torch.float32, device=dataset.device)
+        weights_prop = torch.ones((n_patch, k), dtype=torch.float32, device=dataset.device)
+        beta_prop = torch.zeros((n_patch, ops.JET_M[order]), dtype=torch.float32, device=dataset.device)
+        trans_prop = torch.eye(3, device=dataset.device).reshape(1, 9).repeat(n_patch, 1)
+        for s in range(0, n_patch, batch):
+            c = min(batch, n_patch - s)
+            patch, data_trans, rad = dataset.patches(si, s, c)
+            if net is not None:
+                weights, trans, _, _ = net.forward(patch, want_trans2=False)
+                out = ops.wls_fit(patch, weights, order, trans=trans if use_point_stn else None,
+                                  U=data_trans if dataset.use_pca else None, rad=rad)
+                weights_prop[s:s + c] = weights
+                trans_prop[s:s + c] = trans.reshape(c, 9)
+            else:
+                out = ops.wls_fit(patch, None, order, U=data_trans if dataset.use_pca else None, rad=rad)
+            normal_prop[s:s + c] = out["n_world"] if "n_world" in out else out["n_local"]
+            beta_prop[s:s + c] = out["beta"]
+            if order > 1:
+                curv_prop[s:s + c] = out["curv_scaled"].float()     # the reference stores into a float32 buffer
+        res = {"normals": normal_prop.cpu().numpy(), "curv": curv_prop.cpu().numpy(),
+               "weights": weights_prop.cpu().numpy(), "beta": beta_prop.cpu().numpy(), "trans": trans_prop.cpu().numpy()}
+        results[name] = res
+        if write:
+            for ext, arr in res.items():
+                np.savetxt(os.path.join(output_dir, name + '.' + ext), arr)
+            print('saved normals for ' + name)
+    return results
+
+
+def main(argv=None):
+    import argparse
+
+    from .pipeline import model_from_state_dict
+    ap = argparse.ArgumentParser(description="PCPNet-style inference with full outputs (reference test_c_est.py)")
+    ap.add_argument('--indir', type=str, default='./pclouds', help='input folder (point clouds)')
+    ap.add_argument('--testset', type=str, default='testset_no_noise.txt', help='shape set file name')
+    ap.add_argument('--outdir', type=str, default='./results', help='output folder')
+    ap.add_argument('--trained_model_path', type=str, default='../trained_models/DeepFit')
+    ap.add_argument('--sparse_patches', type=int, default=False, help='evaluate on the .pidx subset')
+    ap.add_argument('--batchSize', type=int, default=4096)
+    ap.add_argument('--gpu_idx', type=int, default=0)
+    ap.add_argument('--precision', type=str, default='bf16x3')
+    args = ap.parse_args(argv)
+    dev = torch.device("cuda:%d" % args.gpu_idx)
+    torch.cuda.set_device(dev)
+    params = torch.load(os.path.join(args.trained_model_path, 'DeepFit_params.pth'), weights_only=False)
+    sd = torch.load(os.path.join(args.trained_model_path, 'DeepFit.pth'), map_location='cpu')
+    model = model_from_state_dict(sd, params.points_per_patch, params.jet_order, params.weight_mode, args.precision, dev)
+    ds = PointcloudPatchDataset(args.indir, args.testset, points_per_patch=params.points_per_patch,
+                                use_pca=params.use_pca, sparse_patches=bool(args.sparse_patches),
+                                neighbor_search_method=params.neighbor_search, device=dev)
+    estimate_shapes(ds, model, args.outdir, batch=args.batchSize, use_point_stn=bool(params.use_point_stn))
+
+
+if __name__ == '__main__':
+    main()

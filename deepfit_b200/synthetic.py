@@ -55,3 +55,49 @@ def variable_density_cloud(n: int, seed: int = 9876) -> np.ndarray:
     x, y = r * np.cos(th), r * np.sin(th)
     z = 0.3 * np.sin(0.4 * x) * np.cos(0.3 * y) + 0.02 * rng.normal(size=n)
     return np.stack([x, y, z], 1).astype(np.float32)
+
+
+def write_pcpnet_like(root: str, n_shapes: int = 20, n_points: int = 100000, n_sparse: int = 5000,
+                      noise_levels=(0.0, 0.0025, 0.012), list_name: str = "testset_synthetic.txt", seed0: int = 2000):
+    """BASELINE config 3: a PCPNet-shaped dataset -- per shape ``.xyz``, analytic ``.normals``, ``.pidx``
+    (sparse patch centres) and a list file; Gaussian noise of the named fractions of the bounding-box
+    diagonal along the normal; raw (un-normalised) coordinates like PCPNet's own files."""
+    import os
+    os.makedirs(root, exist_ok=True)
+    names = []
+    kinds = ["sphere", "torus", "ellipsoid", "sheet", "cylinder"]
+    for i in range(n_shapes):
+        rng = np.random.default_rng(seed0 + i)
+        kind = kinds[i % len(kinds)]
+        noise = noise_levels[i % len(noise_levels)]
+        if kind == "sphere":
+            v = rng.normal(size=(n_points, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+            p, nrm = 0.8 * v, v
+        elif kind == "torus":
+            u, w = rng.random(n_points) * 2 * np.pi, rng.random(n_points) * 2 * np.pi
+            p = np.stack([(1 + 0.3 * np.cos(w)) * np.cos(u), (1 + 0.3 * np.cos(w)) * np.sin(u), 0.3 * np.sin(w)], 1)
+            nrm = np.stack([np.cos(w) * np.cos(u), np.cos(w) * np.sin(u), np.sin(w)], 1)
+        elif kind == "ellipsoid":
+            v = rng.normal(size=(n_points, 3)); v /= np.linalg.norm(v, axis=1, keepdims=True)
+            ax = np.array([1.0, 0.7, 0.5])
+            p = v * ax
+            nrm = v / ax; nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        elif kind == "sheet":
+            xy = rng.random((n_points, 2)) * 2 - 1
+            z = 0.3 * np.sin(2 * xy[:, 0]) * np.cos(1.5 * xy[:, 1])
+            gx = 0.6 * np.cos(2 * xy[:, 0]) * np.cos(1.5 * xy[:, 1]); gy = -0.45 * np.sin(2 * xy[:, 0]) * np.sin(1.5 * xy[:, 1])
+            p = np.stack([xy[:, 0], xy[:, 1], z], 1)
+            nrm = np.stack([-gx, -gy, np.ones(n_points)], 1); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        else:
+            t, h = rng.random(n_points) * 2 * np.pi, rng.random(n_points) * 2 - 1
+            p = np.stack([0.5 * np.cos(t), 0.5 * np.sin(t), h], 1)
+            nrm = np.stack([np.cos(t), np.sin(t), np.zeros(n_points)], 1)
+        pts = _finish(p, nrm, noise, rng)
+        name = "%s%dk_%02d_noise_%.4f" % (kind, n_points // 1000, i, noise)
+        np.savetxt(os.path.join(root, name + ".xyz"), pts, fmt="%.6f")
+        np.savetxt(os.path.join(root, name + ".normals"), nrm, fmt="%.6f")
+        np.savetxt(os.path.join(root, name + ".pidx"), np.sort(rng.choice(n_points, min(n_sparse, n_points), replace=False)), fmt="%d")
+        names.append(name)
+    with open(os.path.join(root, list_name), "w") as fh:
+        fh.write("\n".join(names) + "\n")
+    return names

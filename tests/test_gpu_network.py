@@ -155,7 +155,6 @@ def test_network_stage_by_stage_vs_torch(golden, precision, fused, dbg_switch):
     from deepfit_b200 import DeepFit as D
     from deepfit_b200 import ops
     from oracle import deepfit_oracle as O
-    dbg_switch(1, fused, 1)      # resident max-pool kernel vs one CTA per (patch, channel tile)
     dbg_switch(2, fused, 1)      # fused head (64->512->256) vs two launches
     name = CLOUD_NAMES[0]
     P = torch.from_numpy(golden[name + "/patch"][:16]).cuda()

@@ -137,3 +137,43 @@ def test_classic_orders_on_synthetic_sphere_and_torus():
         est2 = NormalEstimator(pts, 64, jet_order=order, mode="classic", chunk=5000)
         n2, c2 = est2.run()
         assert torch.equal(normals, n2) and (curv is None or torch.equal(curv, c2))
+
+
+def test_pcpnet_style_full_outputs(tmp_path):
+    """BASELINE config 3 at a reduced size: multi-shape dataset with sparse .pidx centres on RAW points, full
+    test_c_est.py exports, against the oracle on the same neighbourhoods."""
+    from deepfit_b200 import pcpnet, synthetic
+    from deepfit_b200.pipeline import model_from_state_dict
+    from oracle import deepfit_oracle as O
+    root = str(tmp_path / "pclouds")
+    names = synthetic.write_pcpnet_like(root, n_shapes=3, n_points=6000, n_sparse=200)
+    sd = O.seeded_state_dict(0)
+    model = model_from_state_dict(sd, 256, 3, "sigmoid", "bf16x3")
+    ds = pcpnet.PointcloudPatchDataset(root, "testset_synthetic.txt", points_per_patch=256, use_pca=True,
+                                       sparse_patches=True, neighbor_search_method='k')
+    assert ds.shape_names == names and ds.shape_patch_count == [200, 200, 200]
+    res = pcpnet.estimate_shapes(ds, model, str(tmp_path / "results"), batch=128)
+    model._net.status()
+    for si, name in enumerate(names):
+        for ext, cols in (("normals", 3), ("curv", 2), ("weights", 256), ("beta", 10), ("trans", 9)):
+            arr = np.loadtxt(tmp_path / "results" / (name + "." + ext))
+            assert arr.shape == (200, cols)
+            assert np.array_equal(arr.astype(np.float32), res[name][ext])
+        pts = np.loadtxt(tmp_path / "pclouds" / (name + ".xyz")).astype("float32")    # raw, NOT normalised
+        pidx = np.loadtxt(tmp_path / "pclouds" / (name + ".pidx")).astype("int64")
+        ref_idx, ref_dist = O.knn_bruteforce(pts, pidx[:48], 256)
+        patch, U, rad = ds.patches(si, 0, 48)
+        assert np.array_equal(rad.cpu().numpy(), ref_dist[:, -1])
+        with torch.no_grad():
+            n, beta, w, trans, t2, _ = O.deepfit_forward(sd, patch.cpu(), 3)
+            ref_n = O.world_normals(n, U.cpu(), trans).numpy()
+            ref_c = (O.principal_curvatures(beta).double() / rad.cpu()[:, None]).numpy()
+        assert O.unoriented_angle_deg(res[name]["normals"][:48], ref_n).max() <= 0.01
+        assert O.rectified_rel_err(res[name]["curv"][:48], ref_c).max() <= 1e-3
+        assert np.abs(res[name]["weights"][:48] - w.numpy()).max() < 2e-3
+        assert np.abs(res[name]["trans"][:48] - trans.reshape(-1, 9).numpy()).max() < 1e-4
+        # exact patch extraction on raw coordinates (dataset.py:292-334)
+        raw_patch, _, _ = pcpnet.PointcloudPatchDataset(root, "testset_synthetic.txt", points_per_patch=256, use_pca=False,
+                                                         sparse_patches=True).patches(si, 0, 4)
+        for j in range(4):
+            assert torch.equal(raw_patch[j].cpu(), O.extract_patch(pts, int(pidx[j]), ref_idx[j], ref_dist[j, -1]).t())

@@ -108,3 +108,31 @@ def test_oracle_equals_unmodified_reference():
     n, b, w, tr, t2, _ = O.deepfit_forward(sd, Pref, 3)
     assert torch.equal(w, w_ref) and torch.equal(tr, tr_ref) and torch.equal(t2, t2_ref)
     assert O.unoriented_angle_deg(n.numpy(), n_ref.numpy()).max() < 1e-4
+
+
+@pytest.mark.skipif(not shims.reference_available(), reason="/root/reference is only present in the authoring container")
+def test_oracle_equals_reference_pcpnet_dataset(tmp_path):
+    """dataset.py:268-417 (k-mode, use_pca, sparse .pidx centres, raw points) == oracle.dataset_item on the raw cloud."""
+    import sys
+    from deepfit_b200 import synthetic
+    shims.apply_shims()
+    root = str(tmp_path)
+    names = synthetic.write_pcpnet_like(root, n_shapes=2, n_points=3000, n_sparse=40)
+    sys.path.insert(0, shims.REFERENCE_ROOT)
+    try:
+        import importlib
+        ref_dataset = importlib.import_module("dataset")
+    finally:
+        sys.path.remove(shims.REFERENCE_ROOT)
+    ds = ref_dataset.PointcloudPatchDataset(root=root, shape_list_filename="testset_synthetic.txt", patch_radius=[0.05],
+                                            points_per_patch=256, patch_features=[], seed=1, use_pca=True, center="point",
+                                            point_tuple=1, cache_capacity=2, sparse_patches=True, neighbor_search_method="k")
+    assert ds.shape_patch_count == [40, 40]
+    for gi in (0, 7, 39, 40, 79):
+        patch, trans, scale = ds[gi]
+        si, pi = divmod(gi, 40)
+        pts = np.loadtxt(tmp_path / (names[si] + ".xyz")).astype("float32")
+        pidx = np.loadtxt(tmp_path / (names[si] + ".pidx")).astype("int64")
+        p, U, rad = O.dataset_item(pts, int(pidx[pi]), 256)
+        assert rad == float(scale)
+        assert torch.equal(p.t(), patch) and torch.equal(U, trans)
