@@ -587,6 +587,10 @@ struct HeadArgs {
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// CL2: the two CTAs of a cluster work on adjacent row tiles and share every weight stage: each CTA
+// fetches half of it from L2 and TMA-multicasts it into both shared memories, and a stage is released
+// only when BOTH tensor cores have consumed it (commit multicast to both CTAs' empty barriers).
+template <bool CL2>
 __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs g) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_pf, s_w1f[2], s_w1e[2], s_w2f[3], s_w2e[3], s_d1f[2], s_d1e[2], s_h1f[2], s_h1e[2], s_d2f;
@@ -603,15 +607,18 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
     const uint32_t H1R = smem_base + 64 * 1024;    // 2 x 32 KB : [hi 16 KB | lo 16 KB]
     const uint32_t W2R = smem_base + 128 * 1024;   // 3 x 32 KB : [hi 16 KB | lo 16 KB]
     constexpr uint32_t kTmemCols = 512;            // D2: [0,256)  D1 buffers: [256,320) [320,384)
+    uint32_t cta_rank = 0;
+    if (CL2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    constexpr uint32_t kConsumers = CL2 ? 2u : 1u;
 
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&s_pf), 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(smem_u32(&s_w1f[i]), 1); mbar_init(smem_u32(&s_w1e[i]), 1);
+            mbar_init(smem_u32(&s_w1f[i]), 1); mbar_init(smem_u32(&s_w1e[i]), kConsumers);
             mbar_init(smem_u32(&s_d1f[i]), 1); mbar_init(smem_u32(&s_d1e[i]), 4);
             mbar_init(smem_u32(&s_h1f[i]), 4); mbar_init(smem_u32(&s_h1e[i]), 1);
         }
-        for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&s_w2f[i]), 1); mbar_init(smem_u32(&s_w2e[i]), 1); }
+        for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&s_w2f[i]), 1); mbar_init(smem_u32(&s_w2e[i]), kConsumers); }
         mbar_init(smem_u32(&s_d2f), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -625,6 +632,10 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
     }
     tc_fence_before();
     __syncthreads();
+    if (CL2) {   // the peer's barriers must be initialised before anything of ours can reach them
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
 
@@ -637,12 +648,26 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
                 for (int pl = 0; pl < planes; ++pl)
                     bulk_g2s(PF + (uint32_t)pl * kBlkBytes, g.pf + (size_t)pl * g.pf_plane + (size_t)tile * kBlkElems, kBlkBytes, bar);
             }
+            // one weight plane block: alone -> plain bulk copy; in a cluster -> this CTA fetches its half and
+            // multicasts it to both CTAs (the barrier at the same offset in each CTA gets the complete_tx)
+            auto shared_load = [&](uint32_t dst, const bf16* src, uint32_t bytes, uint32_t bar) {
+                if (CL2) {
+                    const uint32_t half = bytes >> 1;
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                        ::"r"(dst + cta_rank * half), "l"(reinterpret_cast<const char*>(src) + (size_t)cta_rank * half), "r"(half),
+                        "r"(bar), "h"((uint16_t)3)
+                        : "memory");
+                } else {
+                    bulk_g2s(dst, src, bytes, bar);
+                }
+            };
             auto load_w1 = [&](int c) {
                 const int s = c & 1;
                 if (!mbar_wait(smem_u32(&s_w1e[s]), ((uint32_t)(c >> 1) & 1u) ^ 1u, g.err, 1)) { ok = false; return; }
                 const uint32_t bar = smem_u32(&s_w1f[s]);
                 mbar_expect_tx(bar, (uint32_t)planes * 8192u);
-                bulk_g2s(W1R + (uint32_t)s * 16384u, g.w1c + (size_t)c * 8192, (uint32_t)planes * 8192u, bar);  // hi|lo contiguous
+                shared_load(W1R + (uint32_t)s * 16384u, g.w1c + (size_t)c * 8192, (uint32_t)planes * 8192u, bar);  // hi|lo contiguous
             };
             int w2i = 0;
             // W2 is packed in 256-row blocks (all 256 output channels of one 64-wide k-block = 32 KB per
@@ -653,8 +678,8 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
                 const uint32_t bar = smem_u32(&s_w2f[s]);
                 mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
                 for (int pl = 0; pl < planes; ++pl)
-                    bulk_g2s(W2R + (uint32_t)s * 32768u + (uint32_t)pl * kBlkBytes,
-                             g.w2 + (size_t)pl * g.w2_plane + (size_t)c * (2 * kBlkElems) + (size_t)h * kBlkElems, kBlkBytes, bar);
+                    shared_load(W2R + (uint32_t)s * 32768u + (uint32_t)pl * kBlkBytes,
+                                g.w2 + (size_t)pl * g.w2_plane + (size_t)c * (2 * kBlkElems) + (size_t)h * kBlkElems, kBlkBytes, bar);
                 ++w2i;
             };
             load_w1(0);
@@ -668,6 +693,13 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc64 = umma_idesc(64), idesc256 = umma_idesc(256);
+            auto release_weights = [&](uint32_t bar) {   // "these MMAs have read the stage" -> every CTA sharing it
+                if (CL2)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+                else
+                    umma_commit(bar);
+            };
             bool ok = mbar_wait(smem_u32(&s_pf), 0u, g.err, 2);
             auto mma1 = [&](int c) {   // D1[c&1] = pf * W1chunk(c)^T
                 const int b = c & 1;
@@ -686,7 +718,7 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
                         umma_bf16(d, umma_desc(PF + kBlkBytes + ka, kLBO, kSBO), umma_desc(w_hi + kw, 1024u, kSBO), idesc64, 1u);
                     }
                 }
-                umma_commit(smem_u32(&s_w1e[b]));
+                release_weights(smem_u32(&s_w1e[b]));
                 umma_commit(smem_u32(&s_d1f[b]));
             };
             int w2i = 0;
@@ -712,7 +744,7 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
                             umma_bf16(d, umma_desc(a_lo + ka, kLBO, kSBO), umma_desc(b_hi + kw, 2 * kLBO, kSBO), idesc256, 1u);
                         }
                     }
-                    umma_commit(smem_u32(&s_w2e[s]));
+                    release_weights(smem_u32(&s_w2e[s]));
                     ++w2i;
                 }
                 umma_commit(smem_u32(&s_h1e[b]));
@@ -801,6 +833,10 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
     }
     tc_fence_before();
     __syncthreads();
+    if (CL2) {   // neither CTA may retire while the other can still multicast into it
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     tc_fence_after();
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
@@ -1052,6 +1088,8 @@ struct ProfScope {
 namespace dfb {
 namespace {
 
+int g_head_cluster = 1;  // debug switch (dfb_dbg_set key 3): 0 = no cluster / multicast
+
 int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, const float* hg, const PackedLayer& W2,
                       TiledBuf& out, cudaStream_t st) {
     HeadArgs a;
@@ -1066,14 +1104,36 @@ int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, co
     a.out_t = out.p; a.out_plane = out.plane; a.out_KB = out.KB;
     a.err = m->err;
     const size_t smem = 224 * 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const unsigned tiles = (unsigned)((rows + 127) / 128);
+    const bool cl2 = g_head_cluster && (tiles % 2 == 0);
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[cl2]) {
+        cudaError_t e = cl2 ? cudaFuncSetAttribute(head_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(head_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return check_cuda(e, "head_fused smem attribute", __FILE__, __LINE__);
-        attr_done = true;
+        attr_done[cl2] = true;
     }
-    head_fused_kernel<<<(unsigned)((rows + 127) / 128), kGemmThreads, smem, st>>>(a);
-    note_launch();
+    if (cl2) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(tiles);
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, head_fused_kernel<true>, a);
+        note_launch();
+        if (e != cudaSuccess) return check_cuda(e, "head_fused_kernel<cluster 2> launch", __FILE__, __LINE__);
+    } else {
+        head_fused_kernel<false><<<tiles, kGemmThreads, smem, st>>>(a);
+        note_launch();
+    }
     return check_cuda(cudaGetLastError(), "head_fused_kernel launch", __FILE__, __LINE__);
 }
 
@@ -1277,6 +1337,7 @@ extern "C" DFB_API int dfb_dbg_set(int key, int value) {
     if (key == 0) dfb::g_swap_lbo_sbo = value;
     if (key == 1) dfb::g_max_resident = value;
     if (key == 2) dfb::g_head_fused = value;
+    if (key == 3) dfb::g_head_cluster = value;
     return DFB_OK;
 }
 

@@ -149,13 +149,15 @@ def dbg_switch():
         lib.dfb_dbg_set(key, default)
 
 
-@pytest.mark.parametrize("fused", [1, 0], ids=["fused", "unfused"])
+@pytest.mark.parametrize("variant", ["fused_cluster2", "fused", "unfused"])
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
-def test_network_stage_by_stage_vs_torch(golden, precision, fused, dbg_switch):
+def test_network_stage_by_stage_vs_torch(golden, precision, variant, dbg_switch):
     from deepfit_b200 import DeepFit as D
     from deepfit_b200 import ops
     from oracle import deepfit_oracle as O
-    dbg_switch(2, fused, 1)      # fused head (64->512->256) vs two launches
+    fused = 0 if variant == "unfused" else 1
+    dbg_switch(2, fused, 1)                                    # fused head (64->512->256) vs two launches
+    dbg_switch(3, 1 if variant == "fused_cluster2" else 0, 1)  # cluster of 2 with TMA multicast of the weights
     name = CLOUD_NAMES[0]
     P = torch.from_numpy(golden[name + "/patch"][:16]).cuda()
     layers = D.fold_batchnorm(O.seeded_state_dict(0))
