@@ -183,6 +183,8 @@ struct GemmArgs {
 };
 
 constexpr int kGemmThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kHeadEpiWarps = 8;
+constexpr int kHeadThreads = 64 + kHeadEpiWarps * 32;  // fused head: TMA, MMA, 8 epilogue warps
 
 template <int NT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, const int stages) {
@@ -591,7 +593,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // fetches half of it from L2 and TMA-multicasts it into both shared memories, and a stage is released
 // only when BOTH tensor cores have consumed it (commit multicast to both CTAs' empty barriers).
 template <bool CL2>
-__global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs g) {
+__global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs g) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_pf, s_w1f[2], s_w1e[2], s_w2f[3], s_w2e[3], s_d1f[2], s_d1e[2], s_h1f[2], s_h1e[2], s_d2f;
     __shared__ uint32_t s_tmem;
@@ -615,8 +617,8 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
         mbar_init(smem_u32(&s_pf), 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&s_w1f[i]), 1); mbar_init(smem_u32(&s_w1e[i]), kConsumers);
-            mbar_init(smem_u32(&s_d1f[i]), 1); mbar_init(smem_u32(&s_d1e[i]), 4);
-            mbar_init(smem_u32(&s_h1f[i]), 4); mbar_init(smem_u32(&s_h1e[i]), 1);
+            mbar_init(smem_u32(&s_d1f[i]), 1); mbar_init(smem_u32(&s_d1e[i]), kHeadEpiWarps);
+            mbar_init(smem_u32(&s_h1f[i]), kHeadEpiWarps); mbar_init(smem_u32(&s_h1e[i]), 1);
         }
         for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&s_w2f[i]), 1); mbar_init(smem_u32(&s_w2e[i]), kConsumers); }
         mbar_init(smem_u32(&s_d2f), 1);
@@ -628,7 +630,7 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
     }
     if (warp >= 2) {
         const int t = threadIdx.x - 64;
-        for (int c = t; c < 512; c += 128) s_hg[c] = g.hg[patch * 512 + c];
+        for (int c = t; c < 512; c += kHeadEpiWarps * 32) s_hg[c] = g.hg[patch * 512 + c];
     }
     tc_fence_before();
     __syncthreads();
@@ -757,7 +759,9 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
             if (ok) umma_commit(smem_u32(&s_d2f));
         }
     } else {
+        // 8 epilogue warps: TMEM lane quadrant q = warp & 3 (hardware rule), column half = (warp - 2) >> 2
         const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int lrow = q * 32 + lane;
         const long long row = tile * 128 + lrow;
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
@@ -769,13 +773,10 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
             ok = mbar_wait(smem_u32(&s_d1f[b]), use & 1u, g.err, 3);
             if (!ok) break;
             tc_fence_after();
-            float f[64];
-            tmem_ld32(tmem_base + tlane + 256u + (uint32_t)b * 64u, v);
+            float f[32];
+            tmem_ld32(tmem_base + tlane + 256u + (uint32_t)b * 64u + (uint32_t)half * 32u, v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + s_hg[c * 64 + i], 0.f);
-            tmem_ld32(tmem_base + tlane + 256u + (uint32_t)b * 64u + 32u, v);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[32 + i] = fmaxf(__uint_as_float(v[i]) + s_hg[c * 64 + 32 + i], 0.f);
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + s_hg[c * 64 + half * 32 + i], 0.f);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_d1e[b]));
@@ -783,9 +784,10 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
                 ok = mbar_wait(smem_u32(&s_h1e[b]), (use - 1u) & 1u, g.err, 6);
                 if (!ok) break;
             }
-            const uint32_t h_hi = H1R + (uint32_t)b * 32768u + (uint32_t)(lrow >> 3) * 128u + (uint32_t)(lrow & 7) * 16u;
+            const uint32_t h_hi = H1R + (uint32_t)b * 32768u + (uint32_t)(lrow >> 3) * 128u + (uint32_t)(lrow & 7) * 16u +
+                                  (uint32_t)half * 4u * 2048u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
                 uint32_t ph[4], pl[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -807,7 +809,7 @@ __global__ void __launch_bounds__(kGemmThreads) head_fused_kernel(const HeadArgs
         tc_fence_after();
         if (ok) {
 #pragma unroll 1
-            for (int c0 = 0; c0 < 256; c0 += 32) {
+            for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
                 tmem_ld32(tmem_base + tlane + (uint32_t)c0, v);
                 if (row >= g.m_valid) continue;
 #pragma unroll
@@ -1117,7 +1119,7 @@ int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, co
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(tiles);
-        cfg.blockDim = dim3(kGemmThreads);
+        cfg.blockDim = dim3(kHeadThreads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -1131,7 +1133,7 @@ int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, co
         note_launch();
         if (e != cudaSuccess) return check_cuda(e, "head_fused_kernel<cluster 2> launch", __FILE__, __LINE__);
     } else {
-        head_fused_kernel<false><<<tiles, kGemmThreads, smem, st>>>(a);
+        head_fused_kernel<false><<<tiles, kHeadThreads, smem, st>>>(a);
         note_launch();
     }
     return check_cuda(cudaGetLastError(), "head_fused_kernel launch", __FILE__, __LINE__);
