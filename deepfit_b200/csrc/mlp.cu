@@ -141,8 +141,14 @@ __device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
     hi = __float2bfloat16_rn(v);
     lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
-__device__ __forceinline__ uint32_t pack2(bf16 a, bf16 b) {
-    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+// Two values at once: one packed convert for the hi parts, one for the lo parts (x = hi + lo).
+// Element a lands in the low 16 bits, b in the high 16 bits (memory order a, b).
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // ------------------------------------------------------------------------------------------ GEMM
@@ -353,11 +359,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
                                     uint32_t ph[4], plo[4];
 #pragma unroll
                                     for (int e = 0; e < 4; ++e) {
-                                        bf16 h0, l0, h1, l1;
-                                        split_bf16(f[c8 * 8 + 2 * e], h0, l0);
-                                        split_bf16(f[c8 * 8 + 2 * e + 1], h1, l1);
-                                        ph[e] = pack2(h0, h1);
-                                        plo[e] = pack2(l0, l1);
+                                        split_pair(f[c8 * 8 + 2 * e], f[c8 * 8 + 2 * e + 1], ph[e], plo[e]);
                                     }
                                     const size_t o = tiled_offset(row, (int)col0 + c8 * 8, g.out_KB, g.out_br);
                                     *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -380,11 +382,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
                                 uint32_t ph[4], plo[4];
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
-                                    bf16 h0, l0, h1, l1;
-                                    split_bf16(f[c8 * 8 + 2 * e], h0, l0);
-                                    split_bf16(f[c8 * 8 + 2 * e + 1], h1, l1);
-                                    ph[e] = pack2(h0, h1);
-                                    plo[e] = pack2(l0, l1);
+                                    split_pair(f[c8 * 8 + 2 * e], f[c8 * 8 + 2 * e + 1], ph[e], plo[e]);
                                 }
                                 const size_t o = (size_t)row * kBlkElems + (size_t)(kk >> 3) * 1024 + (size_t)(n >> 3) * 64 + (size_t)(n & 7) * 8;
                                 *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -581,9 +579,18 @@ struct HeadArgs {
     int rows_per_patch;
     long long m_valid;
     int nprod;
-    bf16* out_t;         // tiled [rows, 256]
+    bf16* out_t;         // tiled [rows, 256] (only when layer 3 is not fused)
     size_t out_plane;
     int out_KB;
+    // layer 3 (256->128 + ReLU) + layer 4 (128->1) + weight map, fused behind layer 2
+    int fuse_l3;
+    const bf16* w3;      // tiled [128, 256] hi; lo at +w3_plane
+    size_t w3_plane;
+    const float* b3;     // fp32 [128]
+    const float* w4;     // fp32 [128]
+    float b4;
+    int weight_mode;
+    float* out_w;        // fp32 [rows]
     int* err;
 };
 
@@ -595,7 +602,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <bool CL2>
 __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs g) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t s_pf, s_w1f[2], s_w1e[2], s_w2f[3], s_w2e[3], s_d1f[2], s_d1e[2], s_h1f[2], s_h1e[2], s_d2f;
+    __shared__ __align__(8) uint64_t s_pf, s_w1f[2], s_w1e[2], s_w2f[3], s_w2e[3], s_d1f[2], s_d1e[2], s_h1f[2], s_h1e[2], s_d2f, s_w3f[2], s_w3e[2], s_h2f, s_d3f;
     __shared__ uint32_t s_tmem;
     __shared__ float s_hg[512];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -608,6 +615,9 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
     const uint32_t W1R = smem_base + 32 * 1024;    // 2 x 16 KB : [hi 8 KB | lo 8 KB]
     const uint32_t H1R = smem_base + 64 * 1024;    // 2 x 32 KB : [hi 16 KB | lo 16 KB]
     const uint32_t W2R = smem_base + 128 * 1024;   // 3 x 32 KB : [hi 16 KB | lo 16 KB]
+    // layer 3 re-uses the map once layer 2 has drained: h2 (A operand, K=256: 4 hi blocks | 4 lo blocks =
+    // 128 KB) over H1R + the first 64 KB of W2R, the W3 ring (2 x [hi 16 KB | lo 16 KB]) over PF + W1R
+    const uint32_t H2 = H1R;
     constexpr uint32_t kTmemCols = 512;            // D2: [0,256)  D1 buffers: [256,320) [320,384)
     uint32_t cta_rank = 0;
     if (CL2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
@@ -622,6 +632,9 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
         }
         for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&s_w2f[i]), 1); mbar_init(smem_u32(&s_w2e[i]), kConsumers); }
         mbar_init(smem_u32(&s_d2f), 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_w3f[i]), 1); mbar_init(smem_u32(&s_w3e[i]), kConsumers); }
+        mbar_init(smem_u32(&s_h2f), kHeadEpiWarps);
+        mbar_init(smem_u32(&s_d3f), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -691,6 +704,18 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 if (ok) load_w2(c, 1);
                 if (ok && c + 2 < 8) load_w1(c + 2);
             }
+            if (g.fuse_l3) {
+                for (int i = 0; i < 4 && ok; ++i) {
+                    const int s = i & 1;
+                    // phase 0 of w3e = "PF/W1R no longer read by any layer-1 MMA" (both CTAs in a cluster)
+                    if (!mbar_wait(smem_u32(&s_w3e[s]), (uint32_t)(i >> 1) & 1u, g.err, 1)) { ok = false; break; }
+                    const uint32_t bar = smem_u32(&s_w3f[s]);
+                    mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
+                    for (int pl = 0; pl < planes; ++pl)
+                        shared_load(smem_base + (uint32_t)s * 32768u + (uint32_t)pl * kBlkBytes,
+                                    g.w3 + (size_t)pl * g.w3_plane + (size_t)i * kBlkElems, kBlkBytes, bar);
+                }
+            }
         }
     } else if (warp == 1) {
         if (lane == 0) {
@@ -756,7 +781,35 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 if (c + 1 < 8) mma1(c + 1);
                 if (ok) mma2(c);
             }
+            if (ok && g.fuse_l3) {   // everything that reads PF / W1R has been issued: free them for the W3 ring
+                release_weights(smem_u32(&s_w3e[0]));
+                release_weights(smem_u32(&s_w3e[1]));
+            }
             if (ok) umma_commit(smem_u32(&s_d2f));
+            if (ok && g.fuse_l3) {
+                const uint32_t idesc128 = umma_idesc(128);
+                ok = mbar_wait(smem_u32(&s_h2f), 0u, g.err, 5);
+                for (int kb = 0; kb < 4 && ok; ++kb) {
+                    const int s = kb & 1;
+                    ok = mbar_wait(smem_u32(&s_w3f[s]), (uint32_t)(kb >> 1) & 1u, g.err, 2);
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t a_hi = H2 + (uint32_t)kb * kBlkBytes, a_lo = a_hi + 4u * kBlkBytes;
+                    const uint32_t b_hi = smem_base + (uint32_t)s * 32768u, b_lo = b_hi + kBlkBytes;
+                    const uint32_t d = tmem_base + 256u;   // D3 over the (drained) D1 buffers
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t koff = (uint32_t)ks * 2 * kLBO;
+                        umma_bf16(d, umma_desc(a_hi + koff, kLBO, kSBO), umma_desc(b_hi + koff, kLBO, kSBO), idesc128, (kb == 0 && ks == 0) ? 0u : 1u);
+                        if (g.nprod > 1) {
+                            umma_bf16(d, umma_desc(a_hi + koff, kLBO, kSBO), umma_desc(b_lo + koff, kLBO, kSBO), idesc128, 1u);
+                            umma_bf16(d, umma_desc(a_lo + koff, kLBO, kSBO), umma_desc(b_hi + koff, kLBO, kSBO), idesc128, 1u);
+                        }
+                    }
+                    release_weights(smem_u32(&s_w3e[s]));
+                }
+                if (ok) umma_commit(smem_u32(&s_d3f));
+            }
         }
     } else {
         // 8 epilogue warps: TMEM lane quadrant q = warp & 3 (hardware rule), column half = (warp - 2) >> 2
@@ -791,11 +844,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 uint32_t ph[4], pl[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    bf16 h0, l0, h1, l1;
-                    split_bf16(f[j * 8 + 2 * e], h0, l0);
-                    split_bf16(f[j * 8 + 2 * e + 1], h1, l1);
-                    ph[e] = pack2(h0, h1);
-                    pl[e] = pack2(l0, l1);
+                    split_pair(f[j * 8 + 2 * e], f[j * 8 + 2 * e + 1], ph[e], pl[e]);
                 }
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_hi + (uint32_t)j * 2048u), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
                 if (g.nprod > 1)
@@ -811,7 +860,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
 #pragma unroll 1
             for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
                 tmem_ld32(tmem_base + tlane + (uint32_t)c0, v);
-                if (row >= g.m_valid) continue;
+                if (!g.fuse_l3 && row >= g.m_valid) continue;
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8) {
                     uint32_t ph[4], pl[4];
@@ -820,15 +869,45 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                         const int i0 = c8 * 8 + 2 * e;
                         const float x0 = fmaxf(__uint_as_float(v[i0]) + __ldg(g.b2 + c0 + i0), 0.f);
                         const float x1 = fmaxf(__uint_as_float(v[i0 + 1]) + __ldg(g.b2 + c0 + i0 + 1), 0.f);
-                        bf16 h0, l0, h1, l1;
-                        split_bf16(x0, h0, l0);
-                        split_bf16(x1, h1, l1);
-                        ph[e] = pack2(h0, h1);
-                        pl[e] = pack2(l0, l1);
+                        split_pair(x0, x1, ph[e], pl[e]);
                     }
-                    const size_t o = tiled_offset(row, c0 + c8 * 8, g.out_KB);
-                    *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                    if (g.nprod > 1) *reinterpret_cast<uint4*>(g.out_t + g.out_plane + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    const int col = c0 + c8 * 8;
+                    if (g.fuse_l3) {   // h2 stays on chip as the A operand of layer 3
+                        const uint32_t o = H2 + (uint32_t)(col >> 6) * kBlkBytes + (uint32_t)((col & 63) >> 3) * 2048u +
+                                           (uint32_t)(lrow >> 3) * 128u + (uint32_t)(lrow & 7) * 16u;
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
+                        if (g.nprod > 1)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + 4u * kBlkBytes), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
+                    } else {
+                        const size_t o = tiled_offset(row, col, g.out_KB);
+                        *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                        if (g.nprod > 1) *reinterpret_cast<uint4*>(g.out_t + g.out_plane + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    }
+                }
+            }
+            if (g.fuse_l3) {
+                fence_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&s_h2f));
+                if (half == 0) {   // one warp per lane quadrant finishes the row: ReLU(conv3) . w4 + b4 -> weight
+                    ok = mbar_wait(smem_u32(&s_d3f), 0u, g.err, 3);
+                    tc_fence_after();
+                    if (ok) {
+                        float dot = 0.f;
+#pragma unroll 1
+                        for (int c0 = 0; c0 < 128; c0 += 32) {
+                            tmem_ld32(tmem_base + tlane + 256u + (uint32_t)c0, v);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                dot = fmaf(fmaxf(__uint_as_float(v[i]) + __ldg(g.b3 + c0 + i), 0.f), __ldg(g.w4 + c0 + i), dot);
+                        }
+                        if (row < g.m_valid) {
+                            const float a = dot + g.b4;
+                            g.out_w[row] = (g.weight_mode == DFB_WEIGHT_MODE_SIGMOID) ? 0.01f + 1.f / (1.f + expf(-a))
+                                                                                      : (0.01f + 1.f + tanhf(a)) * 0.5f;
+                        }
+                    }
                 }
             }
         }
@@ -860,11 +939,7 @@ __global__ void pack_tiled_kernel(const float* __restrict__ src, long long rows,
             const int c = c8 * 8 + 2 * e;
             if (r < rows && c < cols) a = src[r * ld + c];
             if (r < rows && c + 1 < cols) b = src[r * ld + c + 1];
-            bf16 h0, l0, h1, l1;
-            split_bf16(a, h0, l0);
-            split_bf16(b, h1, l1);
-            ph[e] = pack2(h0, h1);
-            pl[e] = pack2(l0, l1);
+            split_pair(a, b, ph[e], pl[e]);
         }
         const size_t o = tiled_offset(r, c8 * 8, KB, br);
         *reinterpret_cast<uint4*>(dst + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -926,11 +1001,7 @@ __global__ void __launch_bounds__(128) pointwise3_kernel(const float* __restrict
                 float a = fmaf(sW[c * 3 + 2], z, fmaf(sW[c * 3 + 1], y, fmaf(sW[c * 3], x, sW[192 + c])));
                 f[u] = fmaxf(a, 0.f);
             }
-            bf16 h0, l0, h1, l1;
-            split_bf16(f[0], h0, l0);
-            split_bf16(f[1], h1, l1);
-            ph[e] = pack2(h0, h1);
-            pl[e] = pack2(l0, l1);
+            split_pair(f[0], f[1], ph[e], pl[e]);
         }
         const size_t o = tiled_offset(row, c8 * 8, 1);
         *reinterpret_cast<uint4*>(out + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -1092,8 +1163,10 @@ namespace {
 
 int g_head_cluster = 1;  // debug switch (dfb_dbg_set key 3): 0 = no cluster / multicast
 
+int g_head_l3 = 1;  // debug switch (dfb_dbg_set key 4): 0 = layer 3 + weight epilogue as a separate launch
+
 int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, const float* hg, const PackedLayer& W2,
-                      TiledBuf& out, cudaStream_t st) {
+                      TiledBuf& out, float* out_w, cudaStream_t st) {
     HeadArgs a;
     memset(&a, 0, sizeof(a));
     a.pf = pf.p; a.pf_plane = pf.plane;
@@ -1104,6 +1177,13 @@ int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, co
     a.m_valid = rows;
     a.nprod = m->nprod;
     a.out_t = out.p; a.out_plane = out.plane; a.out_KB = out.KB;
+    a.fuse_l3 = out_w != nullptr;
+    a.w3 = m->L[DFB_L_HEAD_CONV3].w.p; a.w3_plane = m->L[DFB_L_HEAD_CONV3].w.plane;
+    a.b3 = m->L[DFB_L_HEAD_CONV3].bias;
+    a.w4 = m->w_small[DFB_L_HEAD_CONV4];
+    a.b4 = m->b4;
+    a.weight_mode = m->weight_mode;
+    a.out_w = out_w;
     a.err = m->err;
     const size_t smem = 224 * 1024;
     const unsigned tiles = (unsigned)((rows + 127) / 128);
@@ -1271,7 +1351,7 @@ int upload_head_w1_chunks(const float* h_w, long long ldw, int col0, bf16** d_ou
 }
 
 int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, const float* hg, const PackedLayer& W2,
-                      TiledBuf& out, cudaStream_t st);
+                      TiledBuf& out, float* out_w, cudaStream_t st);
 
 int g_max_resident = 1;  // debug switch (dfb_dbg_set key 1): 0 = one CTA per (patch, channel tile)
 
@@ -1340,6 +1420,7 @@ extern "C" DFB_API int dfb_dbg_set(int key, int value) {
     if (key == 1) dfb::g_max_resident = value;
     if (key == 2) dfb::g_head_fused = value;
     if (key == 3) dfb::g_head_cluster = value;
+    if (key == 4) dfb::g_head_l3 = value;
     return DFB_OK;
 }
 
@@ -1588,9 +1669,11 @@ extern "C" int dfb_model_forward(dfb_model* m, const float* d_patch, int64_t n, 
             ProfScope ps(m, DFB_PROF_FC, st);
             DFB_RUN(gemm_n(m, m->gfeat, B, m->head_global, 0, nullptr, m->hg, 512, 0, nullptr, 0, st));
         }
+        const bool head_all = g_head_fused && g_head_l3;
         if (g_head_fused) {
             ProfScope ps(m, DFB_PROF_HEAD, st);
-            DFB_RUN(launch_head_fused(m, m->x64c, rows, m->hg, m->head_w2_256, m->h256, st));
+            DFB_RUN(launch_head_fused(m, m->x64c, rows, m->hg, m->head_w2_256, m->h256,
+                                      head_all ? d_weights + s * (long long)k : nullptr, st));
         } else {
             {
                 ProfScope ps(m, DFB_PROF_HEAD, st);
@@ -1601,7 +1684,7 @@ extern "C" int dfb_model_forward(dfb_model* m, const float* d_patch, int64_t n, 
                 DFB_RUN(gemm_n(m, m->h512, rows, m->L[DFB_L_HEAD_CONV2], 1, &m->h256, nullptr, 0, k, nullptr, 0, st));
             }
         }
-        {
+        if (!head_all) {
             ProfScope ps(m, DFB_PROF_HEAD, st);
             DFB_RUN(gemm_n(m, m->h256, rows, m->L[DFB_L_HEAD_CONV3], 1, nullptr, d_weights + s * (long long)k, 0, k, nullptr, 0, st,
                            EPI_DOT));
