@@ -189,8 +189,9 @@ struct GemmArgs {
 };
 
 constexpr int kGemmThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-constexpr int kHeadEpiWarps = 8;
-constexpr int kHeadThreads = 64 + kHeadEpiWarps * 32;  // fused head: TMA, MMA, 8 epilogue warps
+constexpr int kHeadEpiWarps = 16;   // two groups of 8 (even / odd h1 chunks)
+constexpr int kHeadGroupWarps = 8;
+constexpr int kHeadThreads = 64 + kHeadEpiWarps * 32;  // fused head: TMA, MMA, 16 epilogue warps
 
 template <int NT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, const int stages) {
@@ -602,7 +603,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <bool CL2>
 __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs g) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t s_pf, s_w1f[2], s_w1e[2], s_w2f[3], s_w2e[3], s_d1f[2], s_d1e[2], s_h1f[2], s_h1e[2], s_d2f, s_w3f[2], s_w3e[2], s_h2f, s_d3f;
+    __shared__ __align__(8) uint64_t s_pf, s_w1f[2], s_w1e[2], s_w2f[3], s_w2e[3], s_d1f[4], s_d1e[4], s_h1f[2], s_h1e[2], s_d2f, s_w3f[2], s_w3e[2], s_h2f, s_d3f;
     __shared__ uint32_t s_tmem;
     __shared__ float s_hg[512];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -618,7 +619,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
     // layer 3 re-uses the map once layer 2 has drained: h2 (A operand, K=256: 4 hi blocks | 4 lo blocks =
     // 128 KB) over H1R + the first 64 KB of W2R, the W3 ring (2 x [hi 16 KB | lo 16 KB]) over PF + W1R
     const uint32_t H2 = H1R;
-    constexpr uint32_t kTmemCols = 512;            // D2: [0,256)  D1 buffers: [256,320) [320,384)
+    constexpr uint32_t kTmemCols = 512;            // D2: [0,256)  four D1 buffers of 64 columns: [256,512)
     uint32_t cta_rank = 0;
     if (CL2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
     constexpr uint32_t kConsumers = CL2 ? 2u : 1u;
@@ -627,9 +628,9 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
         mbar_init(smem_u32(&s_pf), 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&s_w1f[i]), 1); mbar_init(smem_u32(&s_w1e[i]), kConsumers);
-            mbar_init(smem_u32(&s_d1f[i]), 1); mbar_init(smem_u32(&s_d1e[i]), kHeadEpiWarps);
-            mbar_init(smem_u32(&s_h1f[i]), kHeadEpiWarps); mbar_init(smem_u32(&s_h1e[i]), 1);
+            mbar_init(smem_u32(&s_h1f[i]), kHeadGroupWarps); mbar_init(smem_u32(&s_h1e[i]), 1);
         }
+        for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&s_d1f[i]), 1); mbar_init(smem_u32(&s_d1e[i]), kHeadGroupWarps); }
         for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&s_w2f[i]), 1); mbar_init(smem_u32(&s_w2e[i]), kConsumers); }
         mbar_init(smem_u32(&s_d2f), 1);
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_w3f[i]), 1); mbar_init(smem_u32(&s_w3e[i]), kConsumers); }
@@ -699,10 +700,11 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             };
             load_w1(0);
             if (ok) load_w1(1);
-            for (int c = 0; c < 8 && ok; ++c) {
+            if (ok) load_w1(2);
+            for (int c = 0; c < 8 && ok; ++c) {   // same order as the MMA warp consumes
                 load_w2(c, 0);
                 if (ok) load_w2(c, 1);
-                if (ok && c + 2 < 8) load_w1(c + 2);
+                if (ok && c + 3 < 8) load_w1(c + 3);
             }
             if (g.fuse_l3) {
                 for (int i = 0; i < 4 && ok; ++i) {
@@ -728,13 +730,15 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                     umma_commit(bar);
             };
             bool ok = mbar_wait(smem_u32(&s_pf), 0u, g.err, 2);
-            auto mma1 = [&](int c) {   // D1[c&1] = pf * W1chunk(c)^T
-                const int b = c & 1;
+            auto mma1 = [&](int c) {   // D1[c&3] = pf * W1chunk(c)^T
+                const int b = c & 1;                       // W1 ring slot
                 const uint32_t use = (uint32_t)(c >> 1);
+                const int db = c & 3;                      // D1 buffer
+                const uint32_t duse = (uint32_t)(c >> 2);
                 if (!mbar_wait(smem_u32(&s_w1f[b]), use & 1u, g.err, 2)) { ok = false; return; }
-                if (use > 0 && !mbar_wait(smem_u32(&s_d1e[b]), (use - 1u) & 1u, g.err, 4)) { ok = false; return; }
+                if (duse > 0 && !mbar_wait(smem_u32(&s_d1e[db]), (duse - 1u) & 1u, g.err, 4)) { ok = false; return; }
                 tc_fence_after();
-                const uint32_t d = tmem_base + 256u + (uint32_t)b * 64u;
+                const uint32_t d = tmem_base + 256u + (uint32_t)db * 64u;
                 const uint32_t w_hi = W1R + (uint32_t)b * 16384u, w_lo = w_hi + 8192u;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
@@ -746,7 +750,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                     }
                 }
                 release_weights(smem_u32(&s_w1e[b]));
-                umma_commit(smem_u32(&s_d1f[b]));
+                umma_commit(smem_u32(&s_d1f[db]));
             };
             int w2i = 0;
             auto mma2 = [&](int c) {   // D2 += h1chunk(c) * W2[:, 64c..64c+64]^T
@@ -776,9 +780,13 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 }
                 umma_commit(smem_u32(&s_h1e[b]));
             };
+            // layer 1 runs three chunks ahead of layer 2 so that the two epilogue groups (even / odd chunks)
+            // each have two layer-2 periods to turn a D1 buffer into an h1 operand
             if (ok) mma1(0);
+            if (ok) mma1(1);
+            if (ok) mma1(2);
             for (int c = 0; c < 8 && ok; ++c) {
-                if (c + 1 < 8) mma1(c + 1);
+                if (c + 3 < 8) mma1(c + 3);
                 if (ok) mma2(c);
             }
             if (ok && g.fuse_l3) {   // everything that reads PF / W1R has been issued: free them for the W3 ring
@@ -812,27 +820,33 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             }
         }
     } else {
-        // 8 epilogue warps: TMEM lane quadrant q = warp & 3 (hardware rule), column half = (warp - 2) >> 2
+        // 16 epilogue warps in two groups: group = chunk parity (even / odd 64-channel chunks of h1), inside a
+        // group TMEM lane quadrant q = warp & 3 (hardware rule) and column half = bit 2 of the warp's index
+        const int ew = warp - 2;
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int grp = ew >> 3;
+        const int half = (ew >> 2) & 1;
+        const int quarter = ew >> 2;           // column quarter for the final 256-column pass
         const int lrow = q * 32 + lane;
         const long long row = tile * 128 + lrow;
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
         uint32_t v[32];
         bool ok = true;
-        for (int c = 0; c < 8 && ok; ++c) {
-            const int b = c & 1;
+        for (int c = grp; c < 8 && ok; c += 2) {
+            const int b = grp;                                // h1 buffer of this group
             const uint32_t use = (uint32_t)(c >> 1);
-            ok = mbar_wait(smem_u32(&s_d1f[b]), use & 1u, g.err, 3);
+            const int db = c & 3;
+            const uint32_t duse = (uint32_t)(c >> 2);
+            ok = mbar_wait(smem_u32(&s_d1f[db]), duse & 1u, g.err, 3);
             if (!ok) break;
             tc_fence_after();
             float f[32];
-            tmem_ld32(tmem_base + tlane + 256u + (uint32_t)b * 64u + (uint32_t)half * 32u, v);
+            tmem_ld32(tmem_base + tlane + 256u + (uint32_t)db * 64u + (uint32_t)half * 32u, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + s_hg[c * 64 + half * 32 + i], 0.f);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&s_d1e[b]));
+            if (lane == 0) mbar_arrive(smem_u32(&s_d1e[db]));
             if (use > 0) {
                 ok = mbar_wait(smem_u32(&s_h1e[b]), (use - 1u) & 1u, g.err, 6);
                 if (!ok) break;
@@ -843,9 +857,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             for (int j = 0; j < 4; ++j) {
                 uint32_t ph[4], pl[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    split_pair(f[j * 8 + 2 * e], f[j * 8 + 2 * e + 1], ph[e], pl[e]);
-                }
+                for (int e = 0; e < 4; ++e) split_pair(f[j * 8 + 2 * e], f[j * 8 + 2 * e + 1], ph[e], pl[e]);
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_hi + (uint32_t)j * 2048u), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
                 if (g.nprod > 1)
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_hi + kBlkBytes + (uint32_t)j * 2048u), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
@@ -858,7 +870,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
         tc_fence_after();
         if (ok) {
 #pragma unroll 1
-            for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
+            for (int c0 = quarter * 64; c0 < quarter * 64 + 64; c0 += 32) {
                 tmem_ld32(tmem_base + tlane + (uint32_t)c0, v);
                 if (!g.fuse_l3 && row >= g.m_valid) continue;
 #pragma unroll
@@ -890,7 +902,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&s_h2f));
-                if (half == 0) {   // one warp per lane quadrant finishes the row: ReLU(conv3) . w4 + b4 -> weight
+                if (quarter == 0) {   // one warp per lane quadrant finishes the row: ReLU(conv3) . w4 + b4 -> weight
                     ok = mbar_wait(smem_u32(&s_d3f), 0u, g.err, 3);
                     tc_fence_after();
                     if (ok) {
