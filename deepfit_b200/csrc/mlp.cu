@@ -934,6 +934,322 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ----------------------------------------------------------- fused chain: points -> ... -> 128 -> 1024 + max
+// One CTA per patch runs a whole per-point chain of the network without touching HBM in between:
+//   phase P : CUDA cores: optional rotation p' = p R, then the K=3 layer relu(W0 p' + b0) (64 channels),
+//             written straight into shared memory as a tcgen05 A operand (hi/lo planes);
+//   phase S : up to three 64-wide tensor-core layers (64->64, per-patch x*T2, 64->128), each
+//             MMA -> TMEM -> epilogue (bias, ReLU, re-split) -> shared-memory operand of the next layer;
+//             the last one writes the 128-channel activations in the 256-row block layout (N = k MMAs);
+//   phase M : the resident 128->1024 + max-pool loop of gemm_max_resident_kernel over those
+//             activations (weights streamed through a 3-stage ring, two TMEM accumulator buffers).
+// QSTN  : P -> [64->128] -> M.   STN : P(R) -> [64->64, 64->64, 64->128] -> M.
+// ENC   : P(R) -> [64->64, x*T2 (stored for the head), 64->128] -> M (no ReLU before the max).
+// Shared memory (split-bf16, k=256): X 128 KB | R 96 KB;  during P/S: ACT_A = R[0,64K), WBUF = R[64K,96K),
+// ACT_B = X[0,64K); during M: R is the weight ring.  Removes pointwise3 + 6 small GEMM launches per
+// forward and ~5 KB/point of HBM traffic.
+struct ChainLayer {
+    const bf16* w;            // tiled 128-row block(s), K = 64 (hi plane)
+    size_t w_plane;           // lo plane offset (elements)
+    long long w_patch_stride; // elements between per-patch operands (x*T2), 0 = shared weights
+    const float* bias;        // may be NULL
+    int relu;
+    int n_out;                // 64 or 128
+    bf16* store_t;            // optional global copy of the output (tiled, 128-row blocks, KB = 1)
+    size_t store_plane;
+};
+
+struct ChainArgs {
+    const float* patch;       // f32 [n,3,k]
+    const float* R;           // f32 [n,3,3] or NULL
+    float* pts_out;           // optional rotated points [n,3,k]
+    int k;
+    const float* w0;          // f32 [64,3]
+    const float* b0;          // f32 [64]
+    int n_layers;
+    ChainLayer L[3];
+    const bf16* w3;           // tiled [1024,128]
+    size_t w3_plane;
+    const float* bias3;
+    int relu3;
+    int n_ch;                 // 1024
+    bf16* out_t;              // tiled global-feature rows (patches)
+    size_t out_plane;
+    int out_KB;
+    float* out_f;             // optional fp32 [n, n_ch]
+    int nprod;
+    int* err;
+};
+
+constexpr int kChainEpiWarps = 8;
+constexpr int kChainThreads = 64 + kChainEpiWarps * 32;
+
+template <int NT>
+__global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArgs g) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_wf, s_we, s_act, s_acc, s_rf[3], s_re[3], s_tf[2], s_te[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_w0[64 * 3 + 64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int planes = g.nprod > 1 ? 2 : 1;
+    const long long patch = blockIdx.x;
+    constexpr int KB3 = 2;                                   // 128 input channels of the max layer
+    constexpr uint32_t kActBytes = 2u * NT * kBlkBytes;      // one 64-channel activation buffer, both planes
+    constexpr uint32_t kXBytes = 2u * NT * KB3 * kBlkBytes;  // the 128-channel activations, both planes
+    constexpr uint32_t kTmemCols = NT == 1 ? 256 : 512;
+    constexpr int kEpiActive = 4 * NT;                       // epilogue warps that own rows in phases P/S
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t XR = smem_base;
+    const uint32_t RR = smem_base + kXBytes;
+    const uint32_t ACT_A = RR, WBUF = RR + kActBytes, ACT_B = XR;
+    const int CT = g.n_ch / 128;
+    const int L = g.n_layers;
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&s_wf), 1);
+        mbar_init(smem_u32(&s_we), 1);
+        mbar_init(smem_u32(&s_act), kEpiActive);
+        mbar_init(smem_u32(&s_acc), 1);
+        for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&s_rf[i]), 1); mbar_init(smem_u32(&s_re[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_tf[i]), 1); mbar_init(smem_u32(&s_te[i]), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(&s_tmem), kTmemCols);
+        tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < 64 * 3; i += blockDim.x) s_w0[i] = g.w0[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_w0[192 + i] = g.b0[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+    // activation buffer read by small layer l (they alternate, and the last layer must read ACT_A because
+    // it writes X, which aliases ACT_B)
+    auto act_in = [&](int l) { return ((L - 1 - l) & 1) ? ACT_B : ACT_A; };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            bool ok = true;
+            for (int l = 0; l < L && ok; ++l) {
+                if (l > 0) ok = mbar_wait(smem_u32(&s_we), (uint32_t)(l - 1) & 1u, g.err, 1);   // WBUF free again
+                if (!ok) break;
+                const uint32_t bar = smem_u32(&s_wf);
+                mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
+                for (int pl = 0; pl < planes; ++pl)
+                    bulk_g2s(WBUF + (uint32_t)pl * kBlkBytes,
+                             g.L[l].w + (size_t)pl * g.L[l].w_plane + (size_t)patch * g.L[l].w_patch_stride, kBlkBytes, bar);
+            }
+            const int total = CT * KB3;
+            for (int i = 0; i < total && ok; ++i) {
+                const int s = i % 3;
+                // phase 0 of s_re = "the small layers no longer read region R" (committed by the MMA warp)
+                ok = mbar_wait(smem_u32(&s_re[s]), (uint32_t)(i / 3) & 1u, g.err, 1);
+                if (!ok) break;
+                const uint32_t bar = smem_u32(&s_rf[s]);
+                mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
+                for (int pl = 0; pl < planes; ++pl)
+                    bulk_g2s(RR + (uint32_t)s * (2u * kBlkBytes) + (uint32_t)pl * kBlkBytes,
+                             g.w3 + (size_t)pl * g.w3_plane + (size_t)i * kBlkElems, kBlkBytes, bar);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            bool ok = true;
+            for (int l = 0; l < L && ok; ++l) {
+                ok = mbar_wait(smem_u32(&s_wf), (uint32_t)l & 1u, g.err, 2);
+                if (ok) ok = mbar_wait(smem_u32(&s_act), (uint32_t)l & 1u, g.err, 5);
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t idesc = umma_idesc(g.L[l].n_out);
+                const uint32_t ain = act_in(l);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const uint32_t a_hi = ain + (uint32_t)t * kBlkBytes, a_lo = ain + (uint32_t)(NT + t) * kBlkBytes;
+                    const uint32_t d = tmem_base + (uint32_t)t * 128u;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t koff = (uint32_t)ks * 2 * kLBO;
+                        umma_bf16(d, umma_desc(a_hi + koff, kLBO, kSBO), umma_desc(WBUF + koff, kLBO, kSBO), idesc, ks ? 1u : 0u);
+                        if (g.nprod > 1) {
+                            umma_bf16(d, umma_desc(a_hi + koff, kLBO, kSBO), umma_desc(WBUF + kBlkBytes + koff, kLBO, kSBO), idesc, 1u);
+                            umma_bf16(d, umma_desc(a_lo + koff, kLBO, kSBO), umma_desc(WBUF + koff, kLBO, kSBO), idesc, 1u);
+                        }
+                    }
+                }
+                umma_commit(smem_u32(&s_we));
+                umma_commit(smem_u32(&s_acc));
+            }
+            if (ok) {   // region R (ACT_A, WBUF) is dead once everything issued so far has completed
+                for (int s = 0; s < 3; ++s) umma_commit(smem_u32(&s_re[s]));
+                ok = mbar_wait(smem_u32(&s_act), (uint32_t)L & 1u, g.err, 5);   // X written, TMEM drained
+            }
+            const uint32_t idesc = umma_idesc(NT * 128);
+            const uint32_t lbo_b = (uint32_t)NT * kLBO;
+            for (int ct = 0; ct < CT && ok; ++ct) {
+                const int buf = ct & 1;
+                const uint32_t use = (uint32_t)(ct >> 1);
+                if (use > 0) ok = mbar_wait(smem_u32(&s_te[buf]), (use - 1u) & 1u, g.err, 4);
+                if (!ok) break;
+                tc_fence_after();
+                for (int kb = 0; kb < KB3 && ok; ++kb) {
+                    const int i = ct * KB3 + kb;
+                    const int s = i % 3;
+                    ok = mbar_wait(smem_u32(&s_rf[s]), (uint32_t)(i / 3) & 1u, g.err, 2);
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t a_hi = RR + (uint32_t)s * (2u * kBlkBytes), a_lo = a_hi + kBlkBytes;
+                    const uint32_t b_hi = XR + (uint32_t)(0 * KB3 + kb) * (NT * kBlkBytes);
+                    const uint32_t b_lo = XR + (uint32_t)(1 * KB3 + kb) * (NT * kBlkBytes);
+                    const uint32_t d = tmem_base + (uint32_t)(buf * NT * 128);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t ka = (uint32_t)ks * 2 * kLBO, kbo = (uint32_t)ks * 2 * lbo_b;
+                        const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+                        umma_bf16(d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(b_hi + kbo, lbo_b, kSBO), idesc, first);
+                        if (g.nprod > 1) {
+                            umma_bf16(d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(b_lo + kbo, lbo_b, kSBO), idesc, 1u);
+                            umma_bf16(d, umma_desc(a_lo + ka, kLBO, kSBO), umma_desc(b_hi + kbo, lbo_b, kSBO), idesc, 1u);
+                        }
+                    }
+                    umma_commit(smem_u32(&s_re[s]));
+                }
+                if (ok) umma_commit(smem_u32(&s_tf[buf]));
+            }
+        }
+    } else {
+        // ===================== 8 epilogue warps =====================
+        const int ew = warp - 2;
+        const int q = warp & 3;                   // TMEM lane quadrant (hardware rule)
+        const int grp = ew >> 2;                  // phases P/S: row tile; phase M: channel-tile parity
+        const int lrow = q * 32 + lane;
+        const uint32_t tlane = (uint32_t)(q * 32) << 16;
+        const bool active = grp < NT;             // owns a row of the patch in phases P/S
+        const int k = g.k;
+        bool ok = true;
+        uint32_t v[32];
+        // element offset of (row lrow, 8-channel chunk j) inside a 128-row operand block
+        const uint32_t row_off = (uint32_t)(lrow >> 3) * 128u + (uint32_t)(lrow & 7) * 16u;
+        // ---- phase P ----
+        if (active) {
+            const int j = grp * 128 + lrow;       // point index inside the patch
+            const float* base = g.patch + patch * 3LL * k;
+            float x = base[j], y = base[k + j], z = base[2 * k + j];
+            if (g.R) {
+                const float* r = g.R + patch * 9;
+                const float xr = fmaf(z, r[6], fmaf(y, r[3], x * r[0]));
+                const float yr = fmaf(z, r[7], fmaf(y, r[4], x * r[1]));
+                const float zr = fmaf(z, r[8], fmaf(y, r[5], x * r[2]));
+                x = xr; y = yr; z = zr;
+                if (g.pts_out) {
+                    float* po = g.pts_out + patch * 3LL * k;
+                    po[j] = x; po[k + j] = y; po[2 * k + j] = z;
+                }
+            }
+            const uint32_t dst = act_in(0) + (uint32_t)grp * kBlkBytes + row_off;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = c8 * 8 + 2 * e;
+                    const float f0 = fmaxf(fmaf(s_w0[c * 3 + 2], z, fmaf(s_w0[c * 3 + 1], y, fmaf(s_w0[c * 3], x, s_w0[192 + c]))), 0.f);
+                    const float f1 = fmaxf(fmaf(s_w0[c * 3 + 5], z, fmaf(s_w0[c * 3 + 4], y, fmaf(s_w0[c * 3 + 3], x, s_w0[193 + c]))), 0.f);
+                    split_pair(f0, f1, ph[e], pl[e]);
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)c8 * 2048u), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
+                if (g.nprod > 1)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)NT * kBlkBytes + (uint32_t)c8 * 2048u), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_act));
+        }
+        // ---- phase S ----
+        for (int l = 0; l < L && ok && active; ++l) {
+            ok = mbar_wait(smem_u32(&s_acc), (uint32_t)l & 1u, g.err, 3);
+            if (!ok) break;
+            tc_fence_after();
+            const ChainLayer& Ly = g.L[l];
+            const bool last = (l == L - 1);
+            const long long grow = patch * k + grp * 128 + lrow;   // global row (point) index
+#pragma unroll 1
+            for (int c0 = 0; c0 < Ly.n_out; c0 += 32) {
+                tmem_ld32(tmem_base + tlane + (uint32_t)(grp * 128 + c0), v);
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    uint32_t ph[4], pl[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i0 = c8 * 8 + 2 * e;
+                        float x0 = __uint_as_float(v[i0]), x1 = __uint_as_float(v[i0 + 1]);
+                        if (Ly.bias) { x0 += __ldg(Ly.bias + c0 + i0); x1 += __ldg(Ly.bias + c0 + i0 + 1); }
+                        if (Ly.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                        split_pair(x0, x1, ph[e], pl[e]);
+                    }
+                    const int col = c0 + c8 * 8;
+                    uint32_t o, lo_off;
+                    if (last) {   // X: [plane][kb][NT*128 rows]: k-chunk stride NT*2048, plane stride KB3 blocks
+                        o = XR + (uint32_t)(col >> 6) * (NT * kBlkBytes) + (uint32_t)((col & 63) >> 3) * (NT * 2048u) +
+                            (uint32_t)grp * 2048u + row_off;
+                        lo_off = (uint32_t)KB3 * NT * kBlkBytes;
+                    } else {
+                        o = act_in(l + 1) + (uint32_t)grp * kBlkBytes + (uint32_t)(col >> 3) * 2048u + row_off;
+                        lo_off = (uint32_t)NT * kBlkBytes;
+                    }
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
+                    if (g.nprod > 1)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + lo_off), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
+                    if (Ly.store_t) {
+                        const size_t go = tiled_offset(grow, col, 1);
+                        *reinterpret_cast<uint4*>(Ly.store_t + go) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                        if (g.nprod > 1) *reinterpret_cast<uint4*>(Ly.store_t + Ly.store_plane + go) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    }
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_act));
+        }
+        // ---- phase M: group g takes the channel tiles of parity g ----
+        for (int ct = grp; ct < CT && ok; ct += 2) {
+            const int buf = ct & 1;                 // == grp
+            const uint32_t use = (uint32_t)(ct >> 1);
+            ok = mbar_wait(smem_u32(&s_tf[buf]), use & 1u, g.err, 3);
+            if (!ok) break;
+            tc_fence_after();
+            float mx = -3.402823466e38f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < NT * 128; c0 += 32) {
+                tmem_ld32(tmem_base + tlane + (uint32_t)(buf * NT * 128 + c0), v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_te[buf]));
+            const long long ch = (long long)ct * 128 + lrow;
+            float r = mx + (g.bias3 ? g.bias3[ch] : 0.f);
+            if (g.relu3) r = fmaxf(r, 0.f);
+            if (g.out_f) g.out_f[patch * (long long)g.n_ch + ch] = r;
+            if (g.out_t) {
+                bf16 hi, lo;
+                split_bf16(r, hi, lo);
+                const size_t o = tiled_offset(patch, (int)ch, g.out_KB);
+                g.out_t[o] = hi;
+                g.out_t[g.out_plane + o] = lo;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 // --------------------------------------------------------------------------- small CUDA-core kernels
 
 // fp32 row-major [rows, cols] (ld) -> tiled hi/lo planes; rows/cols beyond the source are zero.
@@ -1365,6 +1681,50 @@ int upload_head_w1_chunks(const float* h_w, long long ldw, int col0, bf16** d_ou
 int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, const float* hg, const PackedLayer& W2,
                       TiledBuf& out, float* out_w, cudaStream_t st);
 
+int g_chain = 1;  // debug switch (dfb_dbg_set key 5): 0 = separate pointwise / small-GEMM / max-pool launches
+
+struct ChainSpec {
+    int first_layer;            // DFB_L_* of the K=3 layer
+    const float* R;
+    float* pts_out;
+    int n_layers;
+    ChainLayer L[3];
+    const PackedLayer* W3;
+    int relu3;
+};
+
+ChainLayer chain_layer(const PackedLayer& pl, int relu) {
+    ChainLayer c;
+    memset(&c, 0, sizeof(c));
+    c.w = pl.w.p; c.w_plane = pl.w.plane; c.bias = pl.bias; c.relu = relu; c.n_out = pl.out;
+    return c;
+}
+
+int launch_chain(const dfb_model* m, const float* patch, long long n_patch, const ChainSpec& sp, TiledBuf& gfeat, cudaStream_t st) {
+    ChainArgs a;
+    memset(&a, 0, sizeof(a));
+    a.patch = patch; a.R = sp.R; a.pts_out = sp.pts_out; a.k = m->k;
+    a.w0 = m->w_small[sp.first_layer]; a.b0 = m->L[sp.first_layer].bias;
+    a.n_layers = sp.n_layers;
+    for (int i = 0; i < sp.n_layers; ++i) a.L[i] = sp.L[i];
+    a.w3 = sp.W3->w.p; a.w3_plane = sp.W3->w.plane; a.bias3 = sp.W3->bias; a.relu3 = sp.relu3; a.n_ch = sp.W3->out;
+    a.out_t = gfeat.p; a.out_plane = gfeat.plane; a.out_KB = gfeat.KB;
+    a.nprod = m->nprod; a.err = m->err;
+    const int NT = m->k / 128;
+    const size_t smem = (size_t)2 * NT * 2 * kBlkBytes + 96 * 1024;
+    static bool attr_done[3] = {false, false, false};
+    if (!attr_done[NT]) {
+        cudaError_t e = NT == 1 ? cudaFuncSetAttribute(chain_max_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                : cudaFuncSetAttribute(chain_max_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return check_cuda(e, "chain_max smem attribute", __FILE__, __LINE__);
+        attr_done[NT] = true;
+    }
+    if (NT == 1) chain_max_kernel<1><<<(unsigned)n_patch, kChainThreads, smem, st>>>(a);
+    else chain_max_kernel<2><<<(unsigned)n_patch, kChainThreads, smem, st>>>(a);
+    note_launch();
+    return check_cuda(cudaGetLastError(), "chain_max_kernel launch", __FILE__, __LINE__);
+}
+
 int g_max_resident = 1;  // debug switch (dfb_dbg_set key 1): 0 = one CTA per (patch, channel tile)
 
 // T orientation with fused max-pool: g[p, c] = act(max_j (W X_p^T)[c, j] + b[c])
@@ -1433,6 +1793,7 @@ extern "C" DFB_API int dfb_dbg_set(int key, int value) {
     if (key == 2) dfb::g_head_fused = value;
     if (key == 3) dfb::g_head_cluster = value;
     if (key == 4) dfb::g_head_l3 = value;
+    if (key == 5) dfb::g_chain = value;
     return DFB_OK;
 }
 
@@ -1592,88 +1953,165 @@ extern "C" int dfb_model_forward(dfb_model* m, const float* d_patch, int64_t n, 
         float* trans = d_trans + s * 9;
         const unsigned pw_blocks = (unsigned)((rows + 127) / 128);
 
-        // ---- QSTN (DeepFit.py:410-441) ----
-        {
-            ProfScope ps(m, DFB_PROF_POINTWISE, st);
-            pointwise3_kernel<<<pw_blocks, 128, 0, st>>>(patch, nullptr, B, k, m->w_small[DFB_L_QSTN_CONV1], m->L[DFB_L_QSTN_CONV1].bias,
-                                                         m->x64a.p, m->x64a.plane, split, nullptr);
-            note_launch();
-        }
-        {
-            ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
-            DFB_RUN(gemm_n(m, m->x64a, rows, m->L[DFB_L_QSTN_CONV2], 1, &m->x128, nullptr, 0, k, nullptr, 0, st));
-        }
-        {
-            ProfScope ps(m, DFB_PROF_GEMM_MAX, st);
-            DFB_RUN(gemm_t_max(m, m->L[DFB_L_QSTN_CONV3], m->x128, B, 1, &m->gfeat, nullptr, st));
-        }
-        {
-            ProfScope ps(m, DFB_PROF_FC, st);
-            DFB_RUN(gemm_n(m, m->gfeat, B, m->L[DFB_L_QSTN_FC1], 1, &m->f512, nullptr, 0, 0, nullptr, 0, st));
-        }
-        {
-            ProfScope ps(m, DFB_PROF_FC, st);
-            DFB_RUN(gemm_n(m, m->f512, B, m->L[DFB_L_QSTN_FC2], 1, nullptr, m->f256_f, 256, 0, nullptr, 0, st));
-        }
-        {
-            ProfScope ps(m, DFB_PROF_QUAT, st);
-            quat_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(m->f256_f, B, m->w_small[DFB_L_QSTN_FC3], m->L[DFB_L_QSTN_FC3].bias, trans);
-            note_launch();
-        }
+        const bool use_chain = g_chain && (k == 128 || k == 256);
+        if (use_chain) {
+            // ---- QSTN (DeepFit.py:410-441): points -> 64 -> 128 -> 1024 + max in one kernel ----
+            {
+                ProfScope ps(m, DFB_PROF_GEMM_MAX, st);
+                ChainSpec sp;
+                memset(&sp, 0, sizeof(sp));
+                sp.first_layer = DFB_L_QSTN_CONV1;
+                sp.n_layers = 1;
+                sp.L[0] = chain_layer(m->L[DFB_L_QSTN_CONV2], 1);
+                sp.W3 = &m->L[DFB_L_QSTN_CONV3];
+                sp.relu3 = 1;
+                DFB_RUN(launch_chain(m, patch, B, sp, m->gfeat, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_FC, st);
+                DFB_RUN(gemm_n(m, m->gfeat, B, m->L[DFB_L_QSTN_FC1], 1, &m->f512, nullptr, 0, 0, nullptr, 0, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_FC, st);
+                DFB_RUN(gemm_n(m, m->f512, B, m->L[DFB_L_QSTN_FC2], 1, nullptr, m->f256_f, 256, 0, nullptr, 0, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_QUAT, st);
+                quat_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(m->f256_f, B, m->w_small[DFB_L_QSTN_FC3], m->L[DFB_L_QSTN_FC3].bias, trans);
+                note_launch();
+            }
+            // ---- feature STN (DeepFit.py:188-197, 353-380): rotate -> 64 -> 64 -> 64 -> 128 -> 1024 + max ----
+            {
+                ProfScope ps(m, DFB_PROF_GEMM_MAX, st);
+                ChainSpec sp;
+                memset(&sp, 0, sizeof(sp));
+                sp.first_layer = DFB_L_PF_CONV1;
+                sp.R = trans;
+                sp.n_layers = 3;
+                sp.L[0] = chain_layer(m->L[DFB_L_PF_CONV2], 1);
+                sp.L[1] = chain_layer(m->L[DFB_L_STN_CONV1], 1);
+                sp.L[2] = chain_layer(m->L[DFB_L_STN_CONV2], 1);
+                sp.W3 = &m->L[DFB_L_STN_CONV3];
+                sp.relu3 = 1;
+                DFB_RUN(launch_chain(m, patch, B, sp, m->gfeat, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_FC, st);
+                DFB_RUN(gemm_n(m, m->gfeat, B, m->L[DFB_L_STN_FC1], 1, &m->f512, nullptr, 0, 0, nullptr, 0, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_FC, st);
+                DFB_RUN(gemm_n(m, m->f512, B, m->L[DFB_L_STN_FC2], 1, &m->f256, nullptr, 0, 0, nullptr, 0, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_FC, st);
+                DFB_RUN(gemm_n(m, m->f256, B, m->L[DFB_L_STN_FC3], 0, &m->t2blk, nullptr, 0, 0, nullptr, 0, st, EPI_T2, nullptr,
+                               d_trans2 ? d_trans2 + s * 4096 : nullptr));
+            }
+            // ---- encoder (DeepFit.py:202-204, 233-235): rotate -> 64 -> 64 -> x*T2 (kept for the head) -> 128 -> 1024 + max ----
+            {
+                ProfScope ps(m, DFB_PROF_GEMM_MAX, st);
+                ChainSpec sp;
+                memset(&sp, 0, sizeof(sp));
+                sp.first_layer = DFB_L_PF_CONV1;
+                sp.R = trans;
+                sp.pts_out = d_points_rot ? d_points_rot + s * 3LL * k : nullptr;
+                sp.n_layers = 3;
+                sp.L[0] = chain_layer(m->L[DFB_L_PF_CONV2], 1);
+                memset(&sp.L[1], 0, sizeof(ChainLayer));
+                sp.L[1].w = m->t2blk.p; sp.L[1].w_plane = m->t2blk.plane; sp.L[1].w_patch_stride = kBlkElems;
+                sp.L[1].n_out = 64;
+                sp.L[1].store_t = m->x64c.p; sp.L[1].store_plane = m->x64c.plane;
+                sp.L[2] = chain_layer(m->L[DFB_L_ENC_CONV2], 1);
+                sp.W3 = &m->L[DFB_L_ENC_CONV3];
+                sp.relu3 = 0;
+                DFB_RUN(launch_chain(m, patch, B, sp, m->gfeat, st));
+            }
+        } else {
+            // ---- QSTN (DeepFit.py:410-441) ----
+            {
+                ProfScope ps(m, DFB_PROF_POINTWISE, st);
+                pointwise3_kernel<<<pw_blocks, 128, 0, st>>>(patch, nullptr, B, k, m->w_small[DFB_L_QSTN_CONV1], m->L[DFB_L_QSTN_CONV1].bias,
+                                                             m->x64a.p, m->x64a.plane, split, nullptr);
+                note_launch();
+            }
+            {
+                ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
+                DFB_RUN(gemm_n(m, m->x64a, rows, m->L[DFB_L_QSTN_CONV2], 1, &m->x128, nullptr, 0, k, nullptr, 0, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_GEMM_MAX, st);
+                DFB_RUN(gemm_t_max(m, m->L[DFB_L_QSTN_CONV3], m->x128, B, 1, &m->gfeat, nullptr, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_FC, st);
+                DFB_RUN(gemm_n(m, m->gfeat, B, m->L[DFB_L_QSTN_FC1], 1, &m->f512, nullptr, 0, 0, nullptr, 0, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_FC, st);
+                DFB_RUN(gemm_n(m, m->f512, B, m->L[DFB_L_QSTN_FC2], 1, nullptr, m->f256_f, 256, 0, nullptr, 0, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_QUAT, st);
+                quat_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(m->f256_f, B, m->w_small[DFB_L_QSTN_FC3], m->L[DFB_L_QSTN_FC3].bias, trans);
+                note_launch();
+            }
 
-        // ---- point features (DeepFit.py:188-197) ----
-        {
-            ProfScope ps(m, DFB_PROF_POINTWISE, st);
-            pointwise3_kernel<<<pw_blocks, 128, 0, st>>>(patch, trans, B, k, m->w_small[DFB_L_PF_CONV1], m->L[DFB_L_PF_CONV1].bias,
-                                                         m->x64a.p, m->x64a.plane, split,
-                                                         d_points_rot ? d_points_rot + s * 3LL * k : nullptr);
-            note_launch();
-        }
-        {
-            ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
-            DFB_RUN(gemm_n(m, m->x64a, rows, m->L[DFB_L_PF_CONV2], 1, &m->x64b, nullptr, 0, k, nullptr, 0, st));
-        }
+            // ---- point features (DeepFit.py:188-197) ----
+            {
+                ProfScope ps(m, DFB_PROF_POINTWISE, st);
+                pointwise3_kernel<<<pw_blocks, 128, 0, st>>>(patch, trans, B, k, m->w_small[DFB_L_PF_CONV1], m->L[DFB_L_PF_CONV1].bias,
+                                                             m->x64a.p, m->x64a.plane, split,
+                                                             d_points_rot ? d_points_rot + s * 3LL * k : nullptr);
+                note_launch();
+            }
+            {
+                ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
+                DFB_RUN(gemm_n(m, m->x64a, rows, m->L[DFB_L_PF_CONV2], 1, &m->x64b, nullptr, 0, k, nullptr, 0, st));
+            }
 
-        // ---- feature STN (DeepFit.py:353-380) ----
-        {
-            ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
-            DFB_RUN(gemm_n(m, m->x64b, rows, m->L[DFB_L_STN_CONV1], 1, &m->x64c, nullptr, 0, k, nullptr, 0, st));
-        }
-        {
-            ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
-            DFB_RUN(gemm_n(m, m->x64c, rows, m->L[DFB_L_STN_CONV2], 1, &m->x128, nullptr, 0, k, nullptr, 0, st));
-        }
-        {
-            ProfScope ps(m, DFB_PROF_GEMM_MAX, st);
-            DFB_RUN(gemm_t_max(m, m->L[DFB_L_STN_CONV3], m->x128, B, 1, &m->gfeat, nullptr, st));
-        }
-        {
-            ProfScope ps(m, DFB_PROF_FC, st);
-            DFB_RUN(gemm_n(m, m->gfeat, B, m->L[DFB_L_STN_FC1], 1, &m->f512, nullptr, 0, 0, nullptr, 0, st));
-        }
-        {
-            ProfScope ps(m, DFB_PROF_FC, st);
-            DFB_RUN(gemm_n(m, m->f512, B, m->L[DFB_L_STN_FC2], 1, &m->f256, nullptr, 0, 0, nullptr, 0, st));
-        }
-        {
-            ProfScope ps(m, DFB_PROF_FC, st);
-            DFB_RUN(gemm_n(m, m->f256, B, m->L[DFB_L_STN_FC3], 0, &m->t2blk, nullptr, 0, 0, nullptr, 0, st, EPI_T2, nullptr,
-                           d_trans2 ? d_trans2 + s * 4096 : nullptr));
-        }
-        // x' = x T2 (DeepFit.py:202-204): per-patch B operand
-        {
-            ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
-            DFB_RUN(gemm_n(m, m->x64b, rows, m->head_point, 0, &m->x64c, nullptr, 0, k, nullptr, 0, st, EPI_ACT, &m->t2blk));
-        }
+            // ---- feature STN (DeepFit.py:353-380) ----
+            {
+                ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
+                DFB_RUN(gemm_n(m, m->x64b, rows, m->L[DFB_L_STN_CONV1], 1, &m->x64c, nullptr, 0, k, nullptr, 0, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
+                DFB_RUN(gemm_n(m, m->x64c, rows, m->L[DFB_L_STN_CONV2], 1, &m->x128, nullptr, 0, k, nullptr, 0, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_GEMM_MAX, st);
+                DFB_RUN(gemm_t_max(m, m->L[DFB_L_STN_CONV3], m->x128, B, 1, &m->gfeat, nullptr, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_FC, st);
+                DFB_RUN(gemm_n(m, m->gfeat, B, m->L[DFB_L_STN_FC1], 1, &m->f512, nullptr, 0, 0, nullptr, 0, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_FC, st);
+                DFB_RUN(gemm_n(m, m->f512, B, m->L[DFB_L_STN_FC2], 1, &m->f256, nullptr, 0, 0, nullptr, 0, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_FC, st);
+                DFB_RUN(gemm_n(m, m->f256, B, m->L[DFB_L_STN_FC3], 0, &m->t2blk, nullptr, 0, 0, nullptr, 0, st, EPI_T2, nullptr,
+                               d_trans2 ? d_trans2 + s * 4096 : nullptr));
+            }
+            // x' = x T2 (DeepFit.py:202-204): per-patch B operand
+            {
+                ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
+                DFB_RUN(gemm_n(m, m->x64b, rows, m->head_point, 0, &m->x64c, nullptr, 0, k, nullptr, 0, st, EPI_ACT, &m->t2blk));
+            }
 
-        // ---- encoder (DeepFit.py:233-235) ----
-        {
-            ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
-            DFB_RUN(gemm_n(m, m->x64c, rows, m->L[DFB_L_ENC_CONV2], 1, &m->x128, nullptr, 0, k, nullptr, 0, st));
-        }
-        {
-            ProfScope ps(m, DFB_PROF_GEMM_MAX, st);
-            DFB_RUN(gemm_t_max(m, m->L[DFB_L_ENC_CONV3], m->x128, B, 0, &m->gfeat, nullptr, st));
+            // ---- encoder (DeepFit.py:233-235) ----
+            {
+                ProfScope ps(m, DFB_PROF_GEMM_SMALL, st);
+                DFB_RUN(gemm_n(m, m->x64c, rows, m->L[DFB_L_ENC_CONV2], 1, &m->x128, nullptr, 0, k, nullptr, 0, st));
+            }
+            {
+                ProfScope ps(m, DFB_PROF_GEMM_MAX, st);
+                DFB_RUN(gemm_t_max(m, m->L[DFB_L_ENC_CONV3], m->x128, B, 0, &m->gfeat, nullptr, st));
+            }
+
         }
 
         // ---- head (DeepFit.py:304-316): conv1 split into global (per patch) + point (per point) parts ----
