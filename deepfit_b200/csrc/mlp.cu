@@ -945,8 +945,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
 //             activations (weights streamed through a 3-stage ring, two TMEM accumulator buffers).
 // QSTN  : P -> [64->128] -> M.   STN : P(R) -> [64->64, 64->64, 64->128] -> M.
 // ENC   : P(R) -> [64->64, x*T2 (stored for the head), 64->128] -> M (no ReLU before the max).
-// Shared memory (split-bf16, k=256): X 128 KB | R 96 KB;  during P/S: ACT_A = R[0,64K), WBUF = R[64K,96K),
-// ACT_B = X[0,64K); during M: R is the weight ring.  Removes pointwise3 + 6 small GEMM launches per
+// Shared memory (split-bf16, k=256): X 128 KB | R 96 KB;  during P/S: ACT_A = R[0,64K), ACT_B = X[0,64K), the
+// three small-layer weight slots R[64K,96K), X[64K,96K), X[96K,128K); during M: R is the weight ring.  Removes pointwise3 + 6 small GEMM launches per
 // forward and ~5 KB/point of HBM traffic.
 struct ChainLayer {
     const bf16* w;            // tiled 128-row block(s), K = 64 (hi plane)
@@ -987,7 +987,7 @@ constexpr int kChainThreads = 64 + kChainEpiWarps * 32;
 template <int NT>
 __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArgs g) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t s_wf, s_we, s_act, s_acc, s_rf[3], s_re[3], s_tf[2], s_te[2];
+    __shared__ __align__(8) uint64_t s_wf[3], s_act, s_acc, s_rf[3], s_re[3], s_tf[2], s_te[2];
     __shared__ uint32_t s_tmem;
     __shared__ float s_w0[64 * 3 + 64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1001,13 +1001,20 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t XR = smem_base;
     const uint32_t RR = smem_base + kXBytes;
-    const uint32_t ACT_A = RR, WBUF = RR + kActBytes, ACT_B = XR;
+    const uint32_t ACT_A = RR, ACT_B = XR;
+    // weights of the (up to three) small layers are all prefetched at kernel start: slot 0 behind ACT_A,
+    // slots 1-2 in the upper half of X, which stays unused until the last small layer's epilogue -- and
+    // that runs after the MMAs that read the slot have completed
+    auto wbuf = [&](int l) {
+        if (l == 0) return RR + kActBytes;
+        if (l == 1) return XR + kActBytes;
+        return NT == 2 ? XR + kActBytes + 2u * kBlkBytes : RR + kActBytes + 2u * kBlkBytes;   // k=128: X is only 64 KB
+    };
     const int CT = g.n_ch / 128;
     const int L = g.n_layers;
 
     if (threadIdx.x == 0) {
-        mbar_init(smem_u32(&s_wf), 1);
-        mbar_init(smem_u32(&s_we), 1);
+        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&s_wf[i]), 1);
         mbar_init(smem_u32(&s_act), kEpiActive);
         mbar_init(smem_u32(&s_acc), 1);
         for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&s_rf[i]), 1); mbar_init(smem_u32(&s_re[i]), 1); }
@@ -1032,13 +1039,11 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         // ===================== TMA producer =====================
         if (lane == 0) {
             bool ok = true;
-            for (int l = 0; l < L && ok; ++l) {
-                if (l > 0) ok = mbar_wait(smem_u32(&s_we), (uint32_t)(l - 1) & 1u, g.err, 1);   // WBUF free again
-                if (!ok) break;
-                const uint32_t bar = smem_u32(&s_wf);
+            for (int l = 0; l < L; ++l) {
+                const uint32_t bar = smem_u32(&s_wf[l]);
                 mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
                 for (int pl = 0; pl < planes; ++pl)
-                    bulk_g2s(WBUF + (uint32_t)pl * kBlkBytes,
+                    bulk_g2s(wbuf(l) + (uint32_t)pl * kBlkBytes,
                              g.L[l].w + (size_t)pl * g.L[l].w_plane + (size_t)patch * g.L[l].w_patch_stride, kBlkBytes, bar);
             }
             const int total = CT * KB3;
@@ -1059,12 +1064,13 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         if (lane == 0) {
             bool ok = true;
             for (int l = 0; l < L && ok; ++l) {
-                ok = mbar_wait(smem_u32(&s_wf), (uint32_t)l & 1u, g.err, 2);
+                ok = mbar_wait(smem_u32(&s_wf[l]), 0u, g.err, 2);
                 if (ok) ok = mbar_wait(smem_u32(&s_act), (uint32_t)l & 1u, g.err, 5);
                 if (!ok) break;
                 tc_fence_after();
                 const uint32_t idesc = umma_idesc(g.L[l].n_out);
                 const uint32_t ain = act_in(l);
+                const uint32_t WBUF = wbuf(l);
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
                     const uint32_t a_hi = ain + (uint32_t)t * kBlkBytes, a_lo = ain + (uint32_t)(NT + t) * kBlkBytes;
@@ -1079,7 +1085,6 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                         }
                     }
                 }
-                umma_commit(smem_u32(&s_we));
                 umma_commit(smem_u32(&s_acc));
             }
             if (ok) {   // region R (ACT_A, WBUF) is dead once everything issued so far has completed

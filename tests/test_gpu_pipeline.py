@@ -177,3 +177,27 @@ def test_pcpnet_style_full_outputs(tmp_path):
                                                          sparse_patches=True).patches(si, 0, 4)
         for j in range(4):
             assert torch.equal(raw_patch[j].cpu(), O.extract_patch(pts, int(pidx[j]), ref_idx[j], ref_dist[j, -1]).t())
+
+
+def test_deepfit_k128_single_tile_patches(clouds):
+    """k=128: one 128-row tile per patch (the NT=1 instantiation of every fused kernel) vs the oracle."""
+    from deepfit_b200 import ops
+    from deepfit_b200.pipeline import NormalEstimator, model_from_state_dict
+    from oracle import deepfit_oracle as O
+    pts_np = O.normalize_cloud(clouds["Boxy_smooth100k"])[0]
+    pts = torch.from_numpy(pts_np).cuda()
+    sd = O.seeded_state_dict(3)
+    model = model_from_state_dict(sd, 128, 2, "tanh", "bf16x3")
+    est = NormalEstimator(pts, 128, mode="DeepFit", model=model, chunk=256)
+    begin, count = 7000, 300          # odd tile count in the last chunk: exercises the non-cluster head kernel too
+    normals, curv = est.run(begin, begin + count)
+    est.net.status()
+    idx, rad = est.grid.query(128, q_begin=begin, q_count=count)
+    patch, U = ops.patch_pca(pts, idx, rad, q_begin=begin)
+    with torch.no_grad():
+        n, beta, w, trans, t2, _ = O.deepfit_forward(sd, patch.cpu(), 2, weight_mode="tanh")
+        ref_n = O.world_normals(n, U.cpu(), trans).numpy()
+        ref_c = (O.principal_curvatures(beta).double() / rad.cpu()[:, None]).numpy()
+    ang = O.unoriented_angle_deg(normals.cpu().numpy(), ref_n)
+    assert ang.max() <= 0.01, "max angular deviation %g deg" % ang.max()
+    assert O.rectified_rel_err(curv.cpu().numpy(), ref_c).max() <= 1e-3
