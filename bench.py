@@ -38,6 +38,9 @@ K = 256
 ORDER = 3
 MLP_FLOP_PER_PATCH = 326.9e6          # algorithmic (split head), SURVEY.md section 8d
 MAX_LAYER_FLOP_PER_PATCH = 2.0 * 128 * 1024 * K   # one 128->1024 layer over k points
+# the three fused chain kernels per patch: three 128->1024 layers + three 64->128 + four 64->64 (incl. x*T2)
+# + three K=3 layers, all over k points
+CHAIN_FLOP_PER_PATCH = 2.0 * K * (3 * 128 * 1024 + 3 * 64 * 128 + 4 * 64 * 64 + 3 * 3 * 64)
 
 
 def measured_peaks():
@@ -293,7 +296,7 @@ def main():
         patches_per_launch = min(args.chunk, end - begin)
         # chunks may be ragged: use the exact patch count of the timed region
         n_patches_timed = (end - begin) * args.steps
-        achieved = (3 * n_patches_timed * MAX_LAYER_FLOP_PER_PATCH) / (gm_ms * 1e-3) / 1e12 if gm_ms > 0 else None
+        achieved = (n_patches_timed * CHAIN_FLOP_PER_PATCH) / (gm_ms * 1e-3) / 1e12 if gm_ms > 0 else None
         net_ms = sum(v[0] for v in prof.values())
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -310,11 +313,13 @@ def main():
                     "d2h_bytes_per_step": int((end - begin) * (12 + 16))},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm_max_resident_kernel<k/128> (128->1024 + max-pool, 3 per forward)",
+            "roofline": {"bound": "tensor", "kernel": "chain_max_kernel<k/128> (points -> 64 -> [64 -> 64 ->] 128 -> 1024 + max-pool, "
+                                                      "one CTA per patch, 3 per forward)",
                          "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s",
                          "frac": (achieved / tf_sus) if achieved else None, "traffic": None,
                          "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained" % which,
-                         "note": "achieved = algorithmic FLOPs (2*128*1024*k per patch per layer); bf16x3 executes 3x that on the tensor pipe",
+                         "note": "achieved = algorithmic FLOPs of the three chain kernels (222.6 MFLOP/patch at k=256) / their CUDA-event "
+                                 "time; parity precision bf16x3 executes 3x that on the tensor pipe, so the ceiling of frac is 0.333",
                          "launches": int(gm_n), "avg_launch_ms": gm_ms / gm_n if gm_n else None,
                          "share_of_network": gm_ms / net_ms if net_ms else None,
                          "network_tflops_algorithmic": (n_patches_timed * MLP_FLOP_PER_PATCH) / (net_ms * 1e-3) / 1e12 if net_ms else None},

@@ -189,7 +189,7 @@ def test_deepfit_k128_single_tile_patches(clouds):
     sd = O.seeded_state_dict(3)
     model = model_from_state_dict(sd, 128, 2, "tanh", "bf16x3")
     est = NormalEstimator(pts, 128, mode="DeepFit", model=model, chunk=256)
-    begin, count = 7000, 300          # odd tile count in the last chunk: exercises the non-cluster head kernel too
+    begin, count = 7000, 301          # odd tile count in the last chunk: exercises the non-cluster head kernel too
     normals, curv = est.run(begin, begin + count)
     est.net.status()
     idx, rad = est.grid.query(128, q_begin=begin, q_count=count)
