@@ -196,8 +196,11 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    from deepfit_b200 import ops
+    from deepfit_b200 import _lib, ops
     from deepfit_b200.pipeline import NormalEstimator, gather_outputs, model_from_state_dict, shard_range
+    for kv in os.environ.get("DFB_DBG", "").split(","):     # kernel experiments, e.g. DFB_DBG=6:1 (never for reported numbers)
+        if ":" in kv:
+            _lib.load().dfb_dbg_set(int(kv.split(":")[0]), int(kv.split(":")[1]))
     from oracle import deepfit_oracle as O   # only for the seeded weights + the cpu_baseline leg
 
     n_total = args.points * world

@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libdeepfit_b200.so")
-SOURCES = ["api.cu", "knn.cu", "pca.cu", "wls.cu", "mlp.cu"]
+SOURCES = ["api.cu", "knn.cu", "pca.cu", "wls.cu", "mlp.cu", "textio.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

@@ -74,10 +74,10 @@ def main(argv=None):
     os.makedirs(args.output_path, exist_ok=True)
     stem = os.path.splitext(os.path.basename(args.input))[0]
     normals_output_file_name = os.path.join(args.output_path, stem + '.normals')
-    np.savetxt(normals_output_file_name, normals)
+    tu.savetxt(normals_output_file_name, normals)        # == np.savetxt(...), byte for byte
     print('Saved estimated normal vectors to ' + normals_output_file_name)
     curvatures_output_file_name = os.path.join(args.output_path, stem + '.curv')
-    np.savetxt(curvatures_output_file_name, curvatures)
+    tu.savetxt(curvatures_output_file_name, curvatures)
     print('Saved estimated principal curvatures to ' + curvatures_output_file_name)
 
 

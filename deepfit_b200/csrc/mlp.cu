@@ -592,6 +592,8 @@ struct HeadArgs {
     float b4;
     int weight_mode;
     float* out_w;        // fp32 [rows]
+    int dbg;             // profiling experiments only (dfb_dbg_set key 6): 1 = epilogues skip their math and
+                         // stores (results are garbage), 2 = layer-2 MMAs are not issued
     int* err;
 };
 
@@ -766,6 +768,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                     const uint32_t d = tmem_base;   // one N=256 accumulator
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
+                        if (g.dbg & 2) break;
                         const uint32_t ka = (uint32_t)(h * 4 + ks * 2) * kLBO;   // k-chunk 4h+2ks of the h1 block
                         const uint32_t kw = (uint32_t)ks * 2 * (2 * kLBO);       // 256-row block: LBO = 4096
                         umma_bf16(d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(b_hi + kw, 2 * kLBO, kSBO), idesc256,
@@ -840,6 +843,16 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             ok = mbar_wait(smem_u32(&s_d1f[db]), duse & 1u, g.err, 3);
             if (!ok) break;
             tc_fence_after();
+            if (g.dbg & 1) {   // experiment: synchronisation skeleton only
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&s_d1e[db]));
+                if (use > 0 && !mbar_wait(smem_u32(&s_h1e[b]), (use - 1u) & 1u, g.err, 6)) { ok = false; break; }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&s_h1f[b]));
+                continue;
+            }
             float f[32];
             tmem_ld32(tmem_base + tlane + 256u + (uint32_t)db * 64u + (uint32_t)half * 32u, v);
 #pragma unroll
@@ -1496,6 +1509,7 @@ namespace {
 
 int g_head_cluster = 1;  // debug switch (dfb_dbg_set key 3): 0 = no cluster / multicast
 
+int g_head_dbg = 0;  // profiling experiments (dfb_dbg_set key 6), see HeadArgs::dbg
 int g_head_l3 = 1;  // debug switch (dfb_dbg_set key 4): 0 = layer 3 + weight epilogue as a separate launch
 
 int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, const float* hg, const PackedLayer& W2,
@@ -1517,6 +1531,7 @@ int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, co
     a.b4 = m->b4;
     a.weight_mode = m->weight_mode;
     a.out_w = out_w;
+    a.dbg = g_head_dbg;
     a.err = m->err;
     const size_t smem = 224 * 1024;
     const unsigned tiles = (unsigned)((rows + 127) / 128);
@@ -1799,6 +1814,7 @@ extern "C" DFB_API int dfb_dbg_set(int key, int value) {
     if (key == 3) dfb::g_head_cluster = value;
     if (key == 4) dfb::g_head_l3 = value;
     if (key == 5) dfb::g_chain = value;
+    if (key == 6) dfb::g_head_dbg = value;
     return DFB_OK;
 }
 

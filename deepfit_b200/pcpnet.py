@@ -18,7 +18,7 @@ import torch
 
 from . import ops
 from .DeepFit import DeepFit
-from .tutorial_utils import load_xyz
+from .tutorial_utils import load_xyz, savetxt
 
 
 class PointcloudPatchDataset:
@@ -129,7 +129,7 @@ def estimate_shapes(dataset: PointcloudPatchDataset, model: Optional[DeepFit], o
         results[name] = res
         if write:
             for ext, arr in res.items():
-                np.savetxt(os.path.join(output_dir, name + '.' + ext), arr)
+                savetxt(os.path.join(output_dir, name + '.' + ext), arr)
             print('saved normals for ' + name)
     return results
 

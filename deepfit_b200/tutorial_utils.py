@@ -8,20 +8,51 @@ multi-process ``DataLoader``.  ``compute_principal_curvatures`` mirrors :196-226
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
 from . import ops
 from .DeepFit import compute_principal_curvatures  # noqa: F401  (same function, as in the reference)
 
-__all__ = ["SinglePointCloudDataset", "compute_principal_curvatures", "load_xyz", "normalize_cloud"]
+__all__ = ["SinglePointCloudDataset", "compute_principal_curvatures", "load_xyz", "loadtxt_f32", "savetxt", "normalize_cloud"]
+
+
+def loadtxt_f32(filename) -> np.ndarray:
+    """``np.loadtxt(filename).astype('float32')`` (reference tutorial_utils.py:13) with all host threads."""
+    import ctypes as C
+
+    from . import _lib
+    lib = _lib.load()
+    rows, cols = C.c_int64(0), C.c_int32(0)
+    path = os.fsencode(str(filename))
+    _lib.check(lib.dfb_loadtxt_f32(path, None, 0, C.byref(rows), C.byref(cols)))
+    out = np.empty((rows.value, cols.value), dtype=np.float32)
+    _lib.check(lib.dfb_loadtxt_f32(path, out.ctypes.data, out.size, C.byref(rows), C.byref(cols)))
+    return out
+
+
+def savetxt(filename, array) -> None:
+    """``np.savetxt(filename, array)`` with numpy's default format, byte for byte, with all host threads."""
+    from . import _lib
+    lib = _lib.load()
+    a = np.ascontiguousarray(array)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    if a.dtype == np.float32:
+        fn = lib.dfb_savetxt_f32
+    else:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        fn = lib.dfb_savetxt_f64
+    _lib.check(fn(os.fsencode(str(filename)), a.ctypes.data, a.shape[0], a.shape[1]))
 
 
 def load_xyz(point_filename) -> np.ndarray:
     """Text ``.xyz`` (N x >=3 columns) -> float32 [N,3]; ``.npy`` is accepted as a binary side channel."""
     if str(point_filename).endswith(".npy"):
         return np.load(point_filename).astype("float32")[:, :3]
-    return np.loadtxt(point_filename).astype("float32")[:, :3]
+    return np.ascontiguousarray(loadtxt_f32(point_filename)[:, :3])
 
 
 def normalize_cloud(points: np.ndarray):

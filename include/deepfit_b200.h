@@ -201,6 +201,18 @@ DFB_API int dfb_wls_fit(const float* d_patch, const float* d_weights, const floa
  * Replaces compute_principal_curvatures (tutorial/tutorial_utils.py:196-226). */
 DFB_API int dfb_principal_curvatures(const float* d_beta, int64_t n, int32_t m, float* d_curv, dfb_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Host-side text I/O (all host threads; no GPU needed).  Byte-compatible with numpy's defaults.
+ * dfb_savetxt_*: replaces np.savetxt(path, array) (tutorial/compute_normals.py:87,91;
+ *   test_c_est.py:201-210): "%.18e", ' ' delimiter, '\n' newline.  float32 values are widened first,
+ *   as numpy does.
+ * dfb_loadtxt_f32: replaces np.loadtxt(path).astype('float32') (tutorial/tutorial_utils.py:13):
+ *   call with h_out == NULL to get rows/cols, then with a buffer of rows*cols floats.
+ * ------------------------------------------------------------------------------------------ */
+DFB_API int dfb_savetxt_f32(const char* path, const float* h_data, int64_t rows, int32_t cols);
+DFB_API int dfb_savetxt_f64(const char* path, const double* h_data, int64_t rows, int32_t cols);
+DFB_API int dfb_loadtxt_f32(const char* path, float* h_out, int64_t capacity, int64_t* rows_out, int32_t* cols_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,3 +73,28 @@ def test_state_dict_contract():
     layers = D.fold_batchnorm(m.state_dict())
     assert len(layers) == 20
     assert tuple(layers[16][0].shape) == (512, 1088) and tuple(layers[13][0].shape) == (4096, 256)
+
+
+def test_text_io_is_byte_compatible_with_numpy(tmp_path):
+    """the multi-threaded savetxt / loadtxt replacements equal numpy's defaults."""
+    import numpy as np
+    from deepfit_b200 import tutorial_utils as tu
+    rng = np.random.default_rng(0)
+    for shape, dtype in (((5000, 3), np.float32), ((7001, 2), np.float64), ((3, 10), np.float32), ((1, 1), np.float64)):
+        a = (rng.normal(size=shape) * 10.0 ** rng.integers(-8, 8, size=shape)).astype(dtype)
+        a.flat[0] = 0.0
+        if a.size > 2:
+            a.flat[1] = -1.0
+            a.flat[2] = np.float32(1e-40) if dtype == np.float32 else 5e-324
+        tu.savetxt(tmp_path / "ours.txt", a)
+        np.savetxt(tmp_path / "numpy.txt", a)
+        assert open(tmp_path / "ours.txt", "rb").read() == open(tmp_path / "numpy.txt", "rb").read()
+    pts = (rng.normal(size=(6000, 3)) * 3).round(6)
+    np.savetxt(tmp_path / "cloud.xyz", pts, fmt="%.6f")
+    with open(tmp_path / "cloud.xyz", "a") as fh:
+        fh.write("# trailing comment\n\n")
+    ref = np.loadtxt(tmp_path / "cloud.xyz").astype("float32")
+    got = tu.loadtxt_f32(tmp_path / "cloud.xyz")
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    np.savetxt(tmp_path / "sci.xyz", pts * 1e-3)           # scientific notation, 18 digits
+    assert np.array_equal(tu.loadtxt_f32(tmp_path / "sci.xyz"), np.loadtxt(tmp_path / "sci.xyz").astype("float32"))
