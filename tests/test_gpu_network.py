@@ -158,7 +158,7 @@ def test_network_stage_by_stage_vs_torch(golden, precision, variant, dbg_switch)
     fused = 0 if variant == "unfused" else 1
     l3 = 1 if variant in ("fused_cluster2", "fused") else 0
     dbg_switch(2, fused, 1)                                    # fused head (64->512->256) vs two launches
-    dbg_switch(3, 0 if variant == "fused" else 1, 1)           # cluster of 2 with TMA multicast of the weights
+    dbg_switch(3, 0 if variant == "fused" else 1, 0)           # cluster of 2 with TMA multicast of the weights
     dbg_switch(4, l3, 1)                                       # 256->128->1 + weight map fused behind it
     chain = 0 if variant == "unfused" else 1
     dbg_switch(5, chain, 1)                                    # points -> ... -> 1024+max chains in one kernel each
