@@ -288,6 +288,8 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
     const int G = 1 << gpar.bits;
     const int k = a.k, cap = a.kcap;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    int level_hint = 0;   // consecutive queries of a warp are usually neighbours in density: start one level below
+                          // the level that answered the previous query (any level passing the margin test is exact)
 
     for (long long qw = (long long)blockIdx.x * kKnnWarps + warp; qw < a.q_count; qw += (long long)gridDim.x * kKnnWarps) {
         const long long qi = a.query ? (long long)a.query[qw] : a.q_begin + qw;
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
         int Ti = 0x7fffffff;
         bool thr_incl = true;
 
-        for (int l = 0; l <= gpar.bits; ++l) {
+        for (int l = level_hint; l <= gpar.bits; ++l) {
             const int Gl = G >> l;
             const int cx = ix >> l, cy = iy >> l, cz = iz >> l;
             // 27 neighbour cells, one per lane
@@ -436,6 +438,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                     if (a.out_dist) a.out_dist[qw * (long long)k + t] = sqrt(sd[t]);
                 }
                 if (a.out_rad && lane == 0) a.out_rad[qw] = sqrt(sd[k - 1]);
+                level_hint = l > 0 ? l - 1 : 0;
                 __syncwarp();
                 break;
             }

@@ -1472,6 +1472,21 @@ struct dfb_model {
 
 namespace dfb {
 namespace {
+// Activation buffers of the unfused (debug / k=384,512) paths, allocated when first needed.
+int ensure_unfused_buffers(dfb_model* m) {
+    if (m->x64a.p) return 0;
+    const long long R = (long long)m->max_batch * m->k;
+    TiledBuf* bufs[] = {&m->x64a, &m->x64b, &m->x128, &m->h512, &m->h256};
+    const int widths[] = {64, 64, 128, 512, 256};
+    for (int i = 0; i < 5; ++i) {
+        // x128 feeds the resident max-pool kernel, which issues N=256 MMAs over 256-row blocks at k=256
+        int rc = alloc_tiled(*bufs[i], R, widths[i], (bufs[i] == &m->x128 && m->k == 256) ? 256 : 128);
+        if (rc) return rc;
+        m->allocs.push_back(bufs[i]->p);
+    }
+    return 0;
+}
+
 struct ProfScope {
     dfb_model* m;
     int cls;
@@ -1916,13 +1931,10 @@ extern "C" int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, d
     // workspace
     const long long R = (long long)m->max_batch * m->k;
     const long long Bp = m->max_batch;
-    TiledBuf* bufs[] = {&m->x64a, &m->x64b, &m->x64c, &m->x128, &m->h512, &m->h256};
-    const int widths[] = {64, 64, 64, 128, 512, 256};
-    for (int i = 0; i < 6; ++i) {
-        // x128 feeds the resident max-pool kernel, which issues N=256 MMAs over 256-row blocks at k=256
-        DFB_TRY(alloc_tiled(*bufs[i], R, widths[i], (bufs[i] == &m->x128 && m->k == 256) ? 256 : 128));
-        track(bufs[i]->p);
-    }
+    // only x*T2 (x64c: encoder chain -> head) is materialised by the fused kernels; the activation buffers of
+    // the unfused A/B-test paths (x64a, x64b, x128, h512, h256: ~1 MB per patch) are allocated on first use
+    DFB_TRY(alloc_tiled(m->x64c, R, 64));
+    track(m->x64c.p);
     DFB_TRY(alloc_tiled(m->gfeat, Bp, 1024)); track(m->gfeat.p);
     DFB_TRY(alloc_tiled(m->f512, Bp, 512)); track(m->f512.p);
     DFB_TRY(alloc_tiled(m->f256, Bp, 256)); track(m->f256.p);
@@ -1979,6 +1991,8 @@ extern "C" int dfb_model_forward(dfb_model* m, const float* d_patch, int64_t n, 
         const unsigned pw_blocks = (unsigned)((rows + 127) / 128);
 
         const bool use_chain = g_chain && (k == 128 || k == 256);
+        const bool head_all = g_head_fused && g_head_l3;
+        if (!use_chain || !head_all) DFB_RUN(ensure_unfused_buffers(m));
         if (use_chain) {
             // ---- QSTN (DeepFit.py:410-441): points -> 64 -> 128 -> 1024 + max in one kernel ----
             {
@@ -2144,7 +2158,6 @@ extern "C" int dfb_model_forward(dfb_model* m, const float* d_patch, int64_t n, 
             ProfScope ps(m, DFB_PROF_FC, st);
             DFB_RUN(gemm_n(m, m->gfeat, B, m->head_global, 0, nullptr, m->hg, 512, 0, nullptr, 0, st));
         }
-        const bool head_all = g_head_fused && g_head_l3;
         if (g_head_fused) {
             ProfScope ps(m, DFB_PROF_HEAD, st);
             DFB_RUN(launch_head_fused(m, m->x64c, rows, m->hg, m->head_w2_256, m->h256,
@@ -2179,6 +2192,7 @@ extern "C" DFB_API int dfb_dbg_model_dump(dfb_model* m, int32_t which, int64_t r
     TiledBuf* bufs[] = {&m->x64a, &m->x64b, &m->x64c, &m->x128, &m->h512, &m->h256, &m->gfeat, &m->f512, &m->f256};
     DFB_REQUIRE(which >= 0 && which < 9, DFB_E_ARG, "dfb_dbg_model_dump: bad buffer id");
     TiledBuf* t = bufs[which];
+    DFB_REQUIRE(t->p != nullptr, DFB_E_ARG, "dfb_dbg_model_dump: buffer %d is not materialised in this configuration", which);
     DFB_REQUIRE(rows <= t->rows_pad && cols <= t->KB * 64, DFB_E_ARG, "dfb_dbg_model_dump: shape exceeds the buffer");
     const long long total = rows * (long long)cols;
     unpack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(t->p, t->plane, m->nprod > 1, rows, cols, t->KB, d_out, t->br);
