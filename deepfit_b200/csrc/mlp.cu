@@ -1000,7 +1000,7 @@ constexpr int kChainThreads = 64 + kChainEpiWarps * 32;
 template <int NT>
 __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArgs g) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t s_wf[3], s_act, s_acc, s_rf[3], s_re[3], s_tf[2], s_te[2];
+    __shared__ __align__(8) uint64_t s_wf[3], s_act[2], s_acc[2], s_rf[3], s_re[3], s_tf[2], s_te[2];
     __shared__ uint32_t s_tmem;
     __shared__ float s_w0[64 * 3 + 64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1010,7 +1010,6 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
     constexpr uint32_t kActBytes = 2u * NT * kBlkBytes;      // one 64-channel activation buffer, both planes
     constexpr uint32_t kXBytes = 2u * NT * KB3 * kBlkBytes;  // the 128-channel activations, both planes
     constexpr uint32_t kTmemCols = NT == 1 ? 256 : 512;
-    constexpr int kEpiActive = 4 * NT;                       // epilogue warps that own rows in phases P/S
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t XR = smem_base;
     const uint32_t RR = smem_base + kXBytes;
@@ -1018,18 +1017,21 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
     // weights of the (up to three) small layers are all prefetched at kernel start: slot 0 behind ACT_A,
     // slots 1-2 in the upper half of X, which stays unused until the last small layer's epilogue -- and
     // that runs after the MMAs that read the slot have completed
+    // The LAST small layer's slot must not alias X (its epilogue for one row tile writes X while the MMAs of
+    // the other tile still read the weights), so it lives behind ACT_A; earlier layers use the free part of X
+    // (k=128: X is only 64 KB, the second spare slot is in R).
     auto wbuf = [&](int l) {
-        if (l == 0) return RR + kActBytes;
-        if (l == 1) return XR + kActBytes;
-        return NT == 2 ? XR + kActBytes + 2u * kBlkBytes : RR + kActBytes + 2u * kBlkBytes;   // k=128: X is only 64 KB
+        const int d = g.n_layers - 1 - l;
+        if (d == 0) return RR + kActBytes;
+        if (d == 1) return NT == 2 ? XR + kActBytes : RR + kActBytes + 2u * kBlkBytes;
+        return NT == 2 ? XR + kActBytes + 2u * kBlkBytes : XR + kActBytes;
     };
     const int CT = g.n_ch / 128;
     const int L = g.n_layers;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&s_wf[i]), 1);
-        mbar_init(smem_u32(&s_act), kEpiActive);
-        mbar_init(smem_u32(&s_acc), 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_act[i]), 4); mbar_init(smem_u32(&s_acc[i]), 1); }
         for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&s_rf[i]), 1); mbar_init(smem_u32(&s_re[i]), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_tf[i]), 1); mbar_init(smem_u32(&s_te[i]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1076,16 +1078,20 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         // ===================== MMA issuer =====================
         if (lane == 0) {
             bool ok = true;
+            // the row tiles are independent through all small layers, so they are software-pipelined: while the
+            // epilogue group of tile t turns layer l's accumulator into the next operand, the MMAs of the other
+            // tile run (per-tile barriers s_act[t] / s_acc[t])
             for (int l = 0; l < L && ok; ++l) {
                 ok = mbar_wait(smem_u32(&s_wf[l]), 0u, g.err, 2);
-                if (ok) ok = mbar_wait(smem_u32(&s_act), (uint32_t)l & 1u, g.err, 5);
                 if (!ok) break;
-                tc_fence_after();
                 const uint32_t idesc = umma_idesc(g.L[l].n_out);
                 const uint32_t ain = act_in(l);
                 const uint32_t WBUF = wbuf(l);
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
+                    ok = ok && mbar_wait(smem_u32(&s_act[t]), (uint32_t)l & 1u, g.err, 5);
+                    if (!ok) break;
+                    tc_fence_after();
                     const uint32_t a_hi = ain + (uint32_t)t * kBlkBytes, a_lo = ain + (uint32_t)(NT + t) * kBlkBytes;
                     const uint32_t d = tmem_base + (uint32_t)t * 128u;
 #pragma unroll
@@ -1097,12 +1103,13 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                             umma_bf16(d, umma_desc(a_lo + koff, kLBO, kSBO), umma_desc(WBUF + koff, kLBO, kSBO), idesc, 1u);
                         }
                     }
+                    umma_commit(smem_u32(&s_acc[t]));
                 }
-                umma_commit(smem_u32(&s_acc));
             }
             if (ok) {   // region R (ACT_A, WBUF) is dead once everything issued so far has completed
                 for (int s = 0; s < 3; ++s) umma_commit(smem_u32(&s_re[s]));
-                ok = mbar_wait(smem_u32(&s_act), (uint32_t)L & 1u, g.err, 5);   // X written, TMEM drained
+                for (int t = 0; t < NT && ok; ++t)
+                    ok = mbar_wait(smem_u32(&s_act[t]), (uint32_t)L & 1u, g.err, 5);   // X written, TMEM drained
             }
             const uint32_t idesc = umma_idesc(NT * 128);
             const uint32_t lbo_b = (uint32_t)NT * kLBO;
@@ -1183,11 +1190,11 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
             }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&s_act));
+            if (lane == 0) mbar_arrive(smem_u32(&s_act[grp]));
         }
         // ---- phase S ----
         for (int l = 0; l < L && ok && active; ++l) {
-            ok = mbar_wait(smem_u32(&s_acc), (uint32_t)l & 1u, g.err, 3);
+            ok = mbar_wait(smem_u32(&s_acc[grp]), (uint32_t)l & 1u, g.err, 3);
             if (!ok) break;
             tc_fence_after();
             const ChainLayer& Ly = g.L[l];
@@ -1230,7 +1237,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
             fence_async_smem();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&s_act));
+            if (lane == 0) mbar_arrive(smem_u32(&s_act[grp]));
         }
         // ---- phase M: group g takes the channel tiles of parity g ----
         for (int ct = grp; ct < CT && ok; ct += 2) {
