@@ -592,8 +592,9 @@ struct HeadArgs {
     float b4;
     int weight_mode;
     float* out_w;        // fp32 [rows]
-    int dbg;             // profiling experiments only (dfb_dbg_set key 6): 1 = epilogues skip their math and
-                         // stores (results are garbage), 2 = layer-2 MMAs are not issued
+    int dbg;             // profiling experiments only (dfb_dbg_set key 6; results are garbage): bit 0 = epilogues skip
+                         // their math and stores, bit 1 = no layer-2 MMAs, bit 2 = no layer-2 weight loads,
+                         // bit 3 = no layer-1 MMAs
     int* err;
 };
 
@@ -694,6 +695,11 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 const int s = w2i % 3;
                 if (!mbar_wait(smem_u32(&s_w2e[s]), ((uint32_t)(w2i / 3) & 1u) ^ 1u, g.err, 1)) { ok = false; return; }
                 const uint32_t bar = smem_u32(&s_w2f[s]);
+                if (g.dbg & 4) {   // experiment: no layer-2 weight traffic
+                    mbar_arrive(bar);
+                    ++w2i;
+                    return;
+                }
                 mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
                 for (int pl = 0; pl < planes; ++pl)
                     shared_load(W2R + (uint32_t)s * 32768u + (uint32_t)pl * kBlkBytes,
@@ -744,6 +750,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 const uint32_t w_hi = W1R + (uint32_t)b * 16384u, w_lo = w_hi + 8192u;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
+                    if (g.dbg & 8) break;   // experiment: no layer-1 MMAs
                     const uint32_t ka = (uint32_t)ks * 2 * kLBO, kw = (uint32_t)ks * 2 * 1024u;
                     umma_bf16(d, umma_desc(PF + ka, kLBO, kSBO), umma_desc(w_hi + kw, 1024u, kSBO), idesc64, ks ? 1u : 0u);
                     if (g.nprod > 1) {
