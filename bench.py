@@ -319,7 +319,12 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "chain_max_kernel<k/128> (points -> 64 -> [64 -> 64 ->] 128 -> 1024 + max-pool, "
                                                       "one CTA per patch, 3 per forward)",
                          "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s",
-                         "frac": (achieved / tf_sus) if achieved else None, "traffic": None,
+                         "frac": (achieved / tf_sus) if achieved else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch of 4096 patches, mean over the three chain
+                         # kernels of one forward (13.2 / 13.4 / 378.8 MB), from profiles/r1_ncu_full_chain_and_head.csv;
+                         # algorithmic bytes: 12.6 MB of patches (+ 128 MB per-patch T2 operands read and 256 MB x*T2
+                         # written by the encoder chain)
+                         "traffic": 135.1e6 if args.chunk == 4096 else None,
                          "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained" % which,
                          "note": "achieved = algorithmic FLOPs of the three chain kernels (222.6 MFLOP/patch at k=256) / their CUDA-event "
                                  "time; parity precision bf16x3 executes 3x that on the tensor pipe, so the ceiling of frac is 0.333",
