@@ -191,7 +191,7 @@ struct GemmArgs {
 constexpr int kGemmThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int kHeadEpiWarps = 16;   // two groups of 8 (even / odd h1 chunks)
 constexpr int kHeadGroupWarps = 8;
-constexpr int kHeadThreads = 64 + kHeadEpiWarps * 32;  // fused head: TMA, MMA, 16 epilogue warps
+constexpr int kHeadThreads = 96 + kHeadEpiWarps * 32;  // fused head: TMA, layer-2/3 MMA, layer-1 MMA, 16 epilogue warps
 
 template <int NT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, const int stages) {
@@ -645,8 +645,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
         tmem_alloc(smem_u32(&s_tmem), kTmemCols);
         tmem_relinquish();
     }
-    if (warp >= 2) {
-        const int t = threadIdx.x - 64;
+    if (warp >= 3) {
+        const int t = threadIdx.x - 96;
         for (int c = t; c < 512; c += kHeadEpiWarps * 32) s_hg[c] = g.hg[patch * 512 + c];
     }
     tc_fence_before();
@@ -727,9 +727,11 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 2) {
+        // ===================== layer-1 MMA issuer (its own thread: tcgen05.commit tracks per-thread groups, so
+        // layer 1 runs ahead, throttled only by the four D1 buffers, and never delays the layer-2 issue loop)
         if (lane == 0) {
-            const uint32_t idesc64 = umma_idesc(64), idesc256 = umma_idesc(256);
+            const uint32_t idesc64 = umma_idesc(64);
             auto release_weights = [&](uint32_t bar) {   // "these MMAs have read the stage" -> every CTA sharing it
                 if (CL2)
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -761,6 +763,24 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 release_weights(smem_u32(&s_w1e[b]));
                 umma_commit(smem_u32(&s_d1f[db]));
             };
+            for (int c = 0; c < 8 && ok; ++c) mma1(c);
+            if (ok && g.fuse_l3) {   // everything that reads PF / W1R has been issued: free them for the W3 ring
+                release_weights(smem_u32(&s_w3e[0]));
+                release_weights(smem_u32(&s_w3e[1]));
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== layer-2 / layer-3 MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc256 = umma_idesc(256);
+            auto release_weights = [&](uint32_t bar) {   // "these MMAs have read the stage" -> every CTA sharing it
+                if (CL2)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+                else
+                    umma_commit(bar);
+            };
+            bool ok = true;
             int w2i = 0;
             auto mma2 = [&](int c) {   // D2 += h1chunk(c) * W2[:, 64c..64c+64]^T
                 const int b = c & 1;
@@ -790,19 +810,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 }
                 umma_commit(smem_u32(&s_h1e[b]));
             };
-            // layer 1 runs three chunks ahead of layer 2 so that the two epilogue groups (even / odd chunks)
-            // each have two layer-2 periods to turn a D1 buffer into an h1 operand
-            if (ok) mma1(0);
-            if (ok) mma1(1);
-            if (ok) mma1(2);
-            for (int c = 0; c < 8 && ok; ++c) {
-                if (c + 3 < 8) mma1(c + 3);
-                if (ok) mma2(c);
-            }
-            if (ok && g.fuse_l3) {   // everything that reads PF / W1R has been issued: free them for the W3 ring
-                release_weights(smem_u32(&s_w3e[0]));
-                release_weights(smem_u32(&s_w3e[1]));
-            }
+            for (int c = 0; c < 8 && ok; ++c) mma2(c);
             if (ok) umma_commit(smem_u32(&s_d2f));
             if (ok && g.fuse_l3) {
                 const uint32_t idesc128 = umma_idesc(128);
@@ -832,7 +840,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
     } else {
         // 16 epilogue warps in two groups: group = chunk parity (even / odd 64-channel chunks of h1), inside a
         // group TMEM lane quadrant q = warp & 3 (hardware rule) and column half = bit 2 of the warp's index
-        const int ew = warp - 2;
+        const int ew = warp - 3;
         const int q = warp & 3;
         const int grp = ew >> 3;
         const int half = (ew >> 2) & 1;
