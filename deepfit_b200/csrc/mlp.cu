@@ -1015,7 +1015,7 @@ constexpr int kChainThreads = 64 + kChainEpiWarps * 32;
 template <int NT>
 __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArgs g) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t s_wf[3], s_act[2], s_acc[2], s_free, s_rf[3], s_re[3], s_tf[2], s_te[2];
+    __shared__ __align__(8) uint64_t s_wf[3], s_act[2], s_acc[2], s_rf[3], s_re[3], s_tf[2], s_te[2];
     __shared__ uint32_t s_tmem;
     __shared__ float s_w0[64 * 3 + 64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1047,7 +1047,6 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
     if (threadIdx.x == 0) {
         for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&s_wf[i]), 1);
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_act[i]), 4); mbar_init(smem_u32(&s_acc[i]), 1); }
-        mbar_init(smem_u32(&s_free), NT);
         for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&s_rf[i]), 1); mbar_init(smem_u32(&s_re[i]), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_tf[i]), 1); mbar_init(smem_u32(&s_te[i]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1066,37 +1065,6 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
     // it writes X, which aliases ACT_B)
     auto act_in = [&](int l) { return ((L - 1 - l) & 1) ? ACT_B : ACT_A; };
 
-    // Small layers of ONE row tile: wait for the tile's operand, issue the layer's MMAs, hand the accumulator to the
-    // tile's epilogue group.  The two tiles are independent through all small layers, so each gets its own issuing
-    // thread (tcgen05.commit tracks per-thread groups): tile 0 -> the MMA warp, tile 1 -> the TMA producer, which
-    // has nothing else to do until region R is free for the weight ring.
-    auto small_layers = [&](int t) {
-        bool ok = true;
-        for (int l = 0; l < L && ok; ++l) {
-            ok = mbar_wait(smem_u32(&s_wf[l]), 0u, g.err, 2);
-            if (ok) ok = mbar_wait(smem_u32(&s_act[t]), (uint32_t)l & 1u, g.err, 5);
-            if (!ok) break;
-            tc_fence_after();
-            const uint32_t idesc = umma_idesc(g.L[l].n_out);
-            const uint32_t ain = act_in(l);
-            const uint32_t WBUF = wbuf(l);
-            const uint32_t a_hi = ain + (uint32_t)t * kBlkBytes, a_lo = ain + (uint32_t)(NT + t) * kBlkBytes;
-            const uint32_t d = tmem_base + (uint32_t)t * 128u;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t koff = (uint32_t)ks * 2 * kLBO;
-                umma_bf16(d, umma_desc(a_hi + koff, kLBO, kSBO), umma_desc(WBUF + koff, kLBO, kSBO), idesc, ks ? 1u : 0u);
-                if (g.nprod > 1) {
-                    umma_bf16(d, umma_desc(a_hi + koff, kLBO, kSBO), umma_desc(WBUF + kBlkBytes + koff, kLBO, kSBO), idesc, 1u);
-                    umma_bf16(d, umma_desc(a_lo + koff, kLBO, kSBO), umma_desc(WBUF + koff, kLBO, kSBO), idesc, 1u);
-                }
-            }
-            umma_commit(smem_u32(&s_acc[t]));
-        }
-        if (ok) umma_commit(smem_u32(&s_free));   // this tile's reads of region R (ACT_A, last weight slot) are done
-        return ok;
-    };
-
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
@@ -1108,12 +1076,11 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                     bulk_g2s(wbuf(l) + (uint32_t)pl * kBlkBytes,
                              g.L[l].w + (size_t)pl * g.L[l].w_plane + (size_t)patch * g.L[l].w_patch_stride, kBlkBytes, bar);
             }
-            if (NT == 2) ok = small_layers(1);
-            if (ok) ok = mbar_wait(smem_u32(&s_free), 0u, g.err, 1);   // region R dead: every tile's small layers completed
             const int total = CT * KB3;
             for (int i = 0; i < total && ok; ++i) {
                 const int s = i % 3;
-                ok = mbar_wait(smem_u32(&s_re[s]), ((uint32_t)(i / 3) & 1u) ^ 1u, g.err, 1);
+                // phase 0 of s_re = "the small layers no longer read region R" (committed by the MMA warp)
+                ok = mbar_wait(smem_u32(&s_re[s]), (uint32_t)(i / 3) & 1u, g.err, 1);
                 if (!ok) break;
                 const uint32_t bar = smem_u32(&s_rf[s]);
                 mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
@@ -1126,9 +1093,39 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         // ===================== MMA issuer =====================
         if (lane == 0) {
             bool ok = true;
-            ok = small_layers(0);
-            for (int t = 0; t < NT && ok; ++t)
-                ok = mbar_wait(smem_u32(&s_act[t]), (uint32_t)L & 1u, g.err, 5);   // X written, TMEM drained
+            // the row tiles are independent through all small layers, so they are software-pipelined: while the
+            // epilogue group of tile t turns layer l's accumulator into the next operand, the MMAs of the other
+            // tile run (per-tile barriers s_act[t] / s_acc[t])
+            for (int l = 0; l < L && ok; ++l) {
+                ok = mbar_wait(smem_u32(&s_wf[l]), 0u, g.err, 2);
+                if (!ok) break;
+                const uint32_t idesc = umma_idesc(g.L[l].n_out);
+                const uint32_t ain = act_in(l);
+                const uint32_t WBUF = wbuf(l);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    ok = ok && mbar_wait(smem_u32(&s_act[t]), (uint32_t)l & 1u, g.err, 5);
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t a_hi = ain + (uint32_t)t * kBlkBytes, a_lo = ain + (uint32_t)(NT + t) * kBlkBytes;
+                    const uint32_t d = tmem_base + (uint32_t)t * 128u;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t koff = (uint32_t)ks * 2 * kLBO;
+                        umma_bf16(d, umma_desc(a_hi + koff, kLBO, kSBO), umma_desc(WBUF + koff, kLBO, kSBO), idesc, ks ? 1u : 0u);
+                        if (g.nprod > 1) {
+                            umma_bf16(d, umma_desc(a_hi + koff, kLBO, kSBO), umma_desc(WBUF + kBlkBytes + koff, kLBO, kSBO), idesc, 1u);
+                            umma_bf16(d, umma_desc(a_lo + koff, kLBO, kSBO), umma_desc(WBUF + koff, kLBO, kSBO), idesc, 1u);
+                        }
+                    }
+                    umma_commit(smem_u32(&s_acc[t]));
+                }
+            }
+            if (ok) {   // region R (ACT_A, WBUF) is dead once everything issued so far has completed
+                for (int s = 0; s < 3; ++s) umma_commit(smem_u32(&s_re[s]));
+                for (int t = 0; t < NT && ok; ++t)
+                    ok = mbar_wait(smem_u32(&s_act[t]), (uint32_t)L & 1u, g.err, 5);   // X written, TMEM drained
+            }
             const uint32_t idesc = umma_idesc(NT * 128);
             const uint32_t lbo_b = (uint32_t)NT * kLBO;
             for (int ct = 0; ct < CT && ok; ++ct) {
