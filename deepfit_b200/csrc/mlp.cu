@@ -600,14 +600,6 @@ struct HeadArgs {
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Set-up barrier that lets the TMA producer warp run ahead: it only ARRIVES (its own thread initialised the
-// mbarriers, and it needs neither the TMEM address nor the staged biases), so its first loads are in flight while
-// the other warps are still allocating TMEM and staging constants.
-__device__ __forceinline__ void setup_sync(bool producer_warp, int nthreads) {
-    if (producer_warp) asm volatile("bar.arrive 1, %0;" ::"r"(nthreads) : "memory");
-    else asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-}
-
 // CL2: the two CTAs of a cluster work on adjacent row tiles and share every weight stage: each CTA
 // fetches half of it from L2 and TMA-multicasts it into both shared memories, and a stage is released
 // only when BOTH tensor cores have consumed it (commit multicast to both CTAs' empty barriers).
@@ -658,8 +650,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
         for (int c = t; c < 512; c += kHeadEpiWarps * 32) s_hg[c] = g.hg[patch * 512 + c];
     }
     tc_fence_before();
-    if (CL2) __syncthreads();
-    else setup_sync(warp == 0, kHeadThreads);
+    __syncthreads();
     if (CL2) {   // the peer's barriers must be initialised before anything of ours can reach them
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -1064,12 +1055,10 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         tmem_alloc(smem_u32(&s_tmem), kTmemCols);
         tmem_relinquish();
     }
-    if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < 64 * 3; i += kChainEpiWarps * 32) s_w0[i] = g.w0[i];
-        for (int i = threadIdx.x - 64; i < 64; i += kChainEpiWarps * 32) s_w0[192 + i] = g.b0[i];
-    }
+    for (int i = threadIdx.x; i < 64 * 3; i += blockDim.x) s_w0[i] = g.w0[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_w0[192 + i] = g.b0[i];
     tc_fence_before();
-    setup_sync(warp == 0, kChainThreads);
+    __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
     // activation buffer read by small layer l (they alternate, and the last layer must read ACT_A because
