@@ -63,7 +63,10 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if not os.path.isfile(path) or (not _build.is_current() and os.environ.get("DEEPFIT_B200_NO_REBUILD") != "1"):
+    override = os.environ.get("DEEPFIT_B200_LIB")   # A/B experiments with another build of the same ABI
+    if override:
+        path = override
+    elif not os.path.isfile(path) or (not _build.is_current() and os.environ.get("DEEPFIT_B200_NO_REBUILD") != "1"):
         try:
             _build.build()
         except Exception as e:  # noqa: BLE001 - re-raised with context below when no library exists
