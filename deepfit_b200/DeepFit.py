@@ -13,7 +13,7 @@ Same names, argument meaning and error behaviour as the reference (sitzikbs/Deep
 Documented deviations: BatchNorm always runs in eval mode (folded into the
 preceding layer); all B rows are solved (the reference leaves the last ``B mod 16`` rows at zero);
 a failed Cholesky is retried with a deterministic ridge and flagged instead of random noise;
-``weight_mode='softmax'``, ``arch='3dmfv'``, ``point_tuple>1`` and ``use_consistency=True`` raise.
+``weight_mode='softmax'``, ``arch='3dmfv'`` and ``point_tuple>1`` raise.
 All tensors must live on a CUDA device: there is no CPU fallback.
 """
 from __future__ import annotations
@@ -28,21 +28,19 @@ __all__ = ["fit_Wjet", "compute_principal_curvatures", "DeepFit", "fold_batchnor
 
 def fit_Wjet(points, weights, order=2, compute_neighbor_normals=False):
     """Fit an n-jet to weighted, PCA-aligned patches.  points [B,3,k], weights [B,k] (ones for the
-    classic fit).  Returns (beta [B,M], n_est [B,3], neighbor_normals=None) like the reference."""
+    classic fit).  Returns (beta [B,M], n_est [B,3], neighbor_normals [B,k,3] or None) like the reference."""
     if order not in ops.JET_M:
         raise ValueError("Polynomial order unsupported, please use 1 or 2 ")
-    if compute_neighbor_normals:
-        raise NotImplementedError("compute_neighbor_normals=True (training-time consistency branch, reference "
-                                  "models/DeepFit.py:90-115) is outside the inference hot path")
     squeeze = points.dim() == 2
     if squeeze:
         points = points.unsqueeze(0)
         weights = weights.reshape(1, -1)
     out = ops.wls_fit(points, weights, order, want_curv=False)
     beta, n_est = out["beta"], out["n_local"]
+    neighbor_normals = ops.neighbor_normals(points, beta, order) if compute_neighbor_normals else None
     if squeeze:
         beta = beta.squeeze(0)
-    return beta, n_est, None
+    return beta, n_est, neighbor_normals
 
 
 def compute_principal_curvatures(beta):
@@ -160,8 +158,6 @@ class DeepFit(nn.Module):
         if sym_op != 'max':
             raise NotImplementedError("sym_op=%r: only 'max' is implemented (the reference's STNs hard-code "
                                       "MaxPool1d too)" % (sym_op,))
-        if use_consistency:
-            raise NotImplementedError("use_consistency=True (neighbour normals) is training-only")
         if k != 1:
             raise NotImplementedError("k (weights per point) must be 1")
         if not (use_point_stn and use_feat_stn):
@@ -227,4 +223,7 @@ class DeepFit(nn.Module):
         net = self._network(points.device)
         weights, trans, trans2, _ = net.forward(points.float(), want_trans2=True)
         out = ops.wls_fit(points.float(), weights, self.jet_order, trans=trans, want_curv=False)
-        return out["n_local"], out["beta"], weights, trans, trans2, None
+        neighbor_normals = None
+        if self.compute_neighbor_normals:   # use_consistency=True: normals of the jet at every (rotated) neighbour
+            neighbor_normals = ops.neighbor_normals(points.float(), out["beta"], self.jet_order, trans=trans)
+        return out["n_local"], out["beta"], weights, trans, trans2, neighbor_normals

@@ -29,7 +29,7 @@ EXPORTS = [
     "dfb_patch_pca",
     "dfb_model_create", "dfb_model_destroy", "dfb_model_forward", "dfb_model_status",
     "dfb_model_profile", "dfb_model_profile_read", "dfb_launch_count",
-    "dfb_wls_fit", "dfb_principal_curvatures",
+    "dfb_wls_fit", "dfb_principal_curvatures", "dfb_neighbor_normals",
     "dfb_savetxt_f32", "dfb_savetxt_f64", "dfb_loadtxt_f32",
 ]
 
@@ -98,6 +98,7 @@ def load():
     lib.dfb_dbg_model_dump.restype = C.c_int
     lib.dfb_wls_fit.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.dfb_principal_curvatures.argtypes = [vp, i64, i32, vp, vp]
+    lib.dfb_neighbor_normals.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
     lib.dfb_savetxt_f32.argtypes = [C.c_char_p, vp, i64, i32]
     lib.dfb_savetxt_f64.argtypes = [C.c_char_p, vp, i64, i32]
     lib.dfb_loadtxt_f32.argtypes = [C.c_char_p, vp, i64, C.POINTER(i64), C.POINTER(i32)]

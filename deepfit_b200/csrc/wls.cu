@@ -407,6 +407,62 @@ __global__ void curvature_kernel(const float* __restrict__ beta, long long n, in
     curv[i * 2 + 1] = k2;
 }
 
+// Analytic normals of the fitted jet at every neighbour (fit_Wjet(..., compute_neighbor_normals=True),
+// reference models/DeepFit.py:90-115).  The reference evaluates the gradient with the PRECONDITIONED
+// coordinates x/h, y/h but the un-preconditioned beta; that quirk is reproduced.  One warp per patch.
+__global__ void __launch_bounds__(256) neighbor_normals_kernel(const float* __restrict__ patch, const float* __restrict__ trans,
+                                                               const float* __restrict__ beta, long long n, int k, int order,
+                                                               float* __restrict__ out) {
+    const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (p >= n) return;
+    const float* px = patch + p * 3LL * k;
+    float R[9];
+    if (trans) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = __ldg(trans + p * 9 + i);
+    }
+    float sax = 0.f, say = 0.f;
+    for (int j = lane; j < k; j += 32) {
+        float x = px[j], y = px[k + j], z = px[2 * k + j];
+        if (trans) rotate(R, x, y, z);
+        sax += fabsf(x);
+        say += fabsf(y);
+    }
+    sax = warp_sum(sax);
+    say = warp_sum(say);
+    float h = 1.f;
+    if (order > 1) {
+        h = (sax / (float)k + say / (float)k) * 0.5f;
+        if (fabsf(h) < 1e-4f) h = 0.1f;
+    }
+    const int M = (order + 1) * (order + 2) / 2;
+    float b[15];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) b[i] = i < M ? __ldg(beta + p * M + i) : 0.f;
+    for (int j = lane; j < k; j += 32) {
+        float x = px[j], y = px[k + j], z = px[2 * k + j];
+        if (trans) rotate(R, x, y, z);
+        if (order > 1) { x = x / h; y = y / h; }
+        float gx = b[0], gy = b[1];
+        if (order >= 2) {
+            gx += 2.f * b[2] * x + b[4] * y;
+            gy += 2.f * b[3] * y + b[4] * x;
+        }
+        if (order >= 3) {
+            gx += 3.f * b[5] * x * x + 2.f * b[7] * x * y + b[8] * y * y;
+            gy += 3.f * b[6] * y * y + b[7] * x * x + 2.f * b[8] * x * y;
+        }
+        if (order >= 4) {
+            gx += 4.f * b[9] * x * x * x + 3.f * b[11] * x * x * y + b[12] * y * y * y + 2.f * b[13] * y * y * x;
+            gy += 4.f * b[10] * y * y * y + b[11] * x * x * x + 3.f * b[12] * x * y * y + 2.f * b[13] * y * x * x;
+        }
+        const float inv = 1.f / fmaxf(sqrtf(gx * gx + gy * gy + 1.f), 1e-12f);
+        float* o = out + (p * k + j) * 3;
+        o[0] = -gx * inv; o[1] = -gy * inv; o[2] = inv;
+    }
+}
+
 template <int ORDER>
 int launch_wls(const WlsArgs& a, cudaStream_t st) {
     const long long n_super = (a.n + 31) / 32;
@@ -454,4 +510,17 @@ extern "C" int dfb_principal_curvatures(const float* d_beta, int64_t n, int32_t 
     curvature_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(d_beta, (long long)n, m, d_curv);
     note_launch();
     return check_cuda(cudaGetLastError(), "curvature_kernel launch", __FILE__, __LINE__);
+}
+
+extern "C" int dfb_neighbor_normals(const float* d_patch, const float* d_trans, const float* d_beta, int64_t n, int32_t k,
+                                    int32_t order, float* d_out, dfb_stream stream) {
+    using namespace dfb;
+    DFB_REQUIRE(order >= 1 && order <= 4, DFB_E_ARG, "Polynomial order unsupported, please use 1..4 (got %d)", order);
+    DFB_REQUIRE(n >= 0 && k >= 1 && (n == 0 || (d_patch && d_beta && d_out)), DFB_E_ARG, "dfb_neighbor_normals: bad arguments");
+    if (n == 0) return DFB_OK;
+    int rc = dfb_device_check();
+    if (rc) return rc;
+    neighbor_normals_kernel<<<(unsigned)((n + 7) / 8), 256, 0, as_stream(stream)>>>(d_patch, d_trans, d_beta, (long long)n, k, order, d_out);
+    note_launch();
+    return check_cuda(cudaGetLastError(), "neighbor_normals_kernel launch", __FILE__, __LINE__);
 }

@@ -139,6 +139,19 @@ def wls_fit(patch: torch.Tensor, weights: Optional[torch.Tensor], order: int, tr
     return out
 
 
+def neighbor_normals(patch: torch.Tensor, beta: torch.Tensor, order: int, trans: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-neighbour analytic normals of the fitted jet, [n,k,3] (reference models/DeepFit.py:90-115)."""
+    patch = _chk(patch, torch.float32, "points")
+    beta = _chk(beta, torch.float32, "beta")
+    if trans is not None:
+        trans = _chk(trans, torch.float32, "trans")
+    n, k = int(patch.shape[0]), int(patch.shape[2])
+    out = torch.empty((n, k, 3), dtype=torch.float32, device=patch.device)
+    with torch.cuda.device(patch.device):
+        _lib.check(_lib.load().dfb_neighbor_normals(_p(patch), _p(trans), _p(beta), n, k, order, _p(out), _stream(patch.device)))
+    return out
+
+
 def launch_count(reset: bool = False) -> int:
     """Number of CUDA kernels the library has launched in this process."""
     return int(_lib.load().dfb_launch_count(1 if reset else 0))

@@ -201,6 +201,13 @@ DFB_API int dfb_wls_fit(const float* d_patch, const float* d_weights, const floa
  * Replaces compute_principal_curvatures (tutorial/tutorial_utils.py:196-226). */
 DFB_API int dfb_principal_curvatures(const float* d_beta, int64_t n, int32_t m, float* d_curv, dfb_stream stream);
 
+/* Analytic normals of the fitted jet at every neighbour: fit_Wjet(..., compute_neighbor_normals=True),
+ * models/DeepFit.py:90-115 (gradient evaluated at the preconditioned x/h, y/h with the un-preconditioned
+ * beta, as the reference does).  d_patch f32[n,3,k], d_trans NULL or f32[n,3,3] (the jet was fitted to
+ * patch * trans), d_beta f32[n,M] -> d_out f32[n,k,3]. */
+DFB_API int dfb_neighbor_normals(const float* d_patch, const float* d_trans, const float* d_beta, int64_t n, int32_t k,
+                                 int32_t order, float* d_out, dfb_stream stream);
+
 /* ------------------------------------------------------------------------------------------
  * Host-side text I/O (all host threads; no GPU needed).  Byte-compatible with numpy's defaults.
  * dfb_savetxt_*: replaces np.savetxt(path, array) (tutorial/compute_normals.py:87,91;

@@ -373,6 +373,29 @@ def fit_wjet(points: torch.Tensor, weights: torch.Tensor, order: int = 2, return
     return beta, n
 
 
+def neighbor_normals(points: torch.Tensor, beta: torch.Tensor, order: int) -> torch.Tensor:
+    """fit_Wjet(..., compute_neighbor_normals=True), models/DeepFit.py:90-115: normals of the jet at every
+    neighbour.  The reference evaluates the gradient at the PRECONDITIONED x/h, y/h (:48-49) with the
+    un-preconditioned beta (:85-86); restated as is.  points [B,3,k], beta [B,M] -> [B,k,3]."""
+    x, y = points[:, 0, :], points[:, 1, :]
+    if order > 1:
+        h = (x.abs().mean(1) + y.abs().mean(1)) / 2
+        h = torch.where(h.abs() < 1e-4, torch.full_like(h, 0.1), h)
+        x, y = x / h[:, None], y / h[:, None]
+    b = [beta[:, i:i + 1] for i in range(beta.shape[1])]
+    gx, gy = b[0].expand_as(x).clone(), b[1].expand_as(x).clone()
+    if order >= 2:
+        gx = gx + 2 * b[2] * x + b[4] * y
+        gy = gy + 2 * b[3] * y + b[4] * x
+    if order >= 3:
+        gx = gx + 3 * b[5] * x * x + 2 * b[7] * x * y + b[8] * y * y
+        gy = gy + 3 * b[6] * y * y + b[7] * x * x + 2 * b[8] * x * y
+    if order >= 4:
+        gx = gx + 4 * b[9] * x ** 3 + 3 * b[11] * x * x * y + b[12] * y ** 3 + 2 * b[13] * y * y * x
+        gy = gy + 4 * b[10] * y ** 3 + b[11] * x ** 3 + 3 * b[12] * x * y * y + 2 * b[13] * y * x * x
+    return F.normalize(torch.stack([-gx, -gy, torch.ones_like(gx)], -1), p=2, dim=-1)
+
+
 # ----------------------------------------------------------------------------------------
 # Stage 5: principal curvatures -- tutorial/tutorial_utils.py:196-226 (= models/DeepFit.py:444-474)
 # ----------------------------------------------------------------------------------------

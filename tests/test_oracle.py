@@ -65,6 +65,18 @@ def test_oracle_network_matches_golden(golden, name):
     assert float(w.min()) < 0.1 and float(w.max()) > 0.9      # the seeded weights really spread
 
 
+@pytest.mark.parametrize("name", CLOUD_NAMES)
+def test_oracle_neighbor_normals_match_golden(golden, name):
+    """fit_Wjet(..., compute_neighbor_normals=True): gradient at x/h, y/h with the un-preconditioned beta."""
+    P = torch.from_numpy(golden[name + "/patch"][:8])
+    for order in (1, 2, 3, 4):
+        beta = torch.from_numpy(golden["%s/fit%d_beta" % (name, order)][:8])
+        nn_ = O.neighbor_normals(P, beta, order)
+        ref = torch.from_numpy(golden["%s/nn%d" % (name, order)])
+        assert tuple(nn_.shape) == (8, 256, 3)
+        assert (nn_ - ref).abs().max() < 2e-5
+
+
 def test_quaternion_and_metrics():
     R = O.quat_to_rotmat(torch.tensor([[1.0, 0, 0, 0], [0.5, 0.5, 0.5, 0.5]]))
     assert torch.allclose(R[0], torch.eye(3))
