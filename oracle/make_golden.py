@@ -72,9 +72,10 @@ def main():
             if order > 1:
                 curv, dirs = RT.compute_principal_curvatures(beta)
                 out["%s/fit%d_curv" % (key, order)] = curv.numpy()
-        # per-neighbour normals (compute_neighbor_normals=True, DeepFit.py:90-115) on 8 patches
+        # per-neighbour normals (compute_neighbor_normals=True, DeepFit.py:90-115) on 16 patches (a whole sub-batch:
+        # fewer would fall into the reference's B mod 16 hole and come back as beta = 0)
         for order in (1, 2, 3, 4):
-            b8, _, nn8 = RD.fit_Wjet(P32[:8], torch.ones_like(P32[:8, 0]), order=order, compute_neighbor_normals=True)
+            b8, _, nn8 = RD.fit_Wjet(P32[:16], torch.ones_like(P32[:16, 0]), order=order, compute_neighbor_normals=True)
             out["%s/nn%d" % (key, order)] = nn8.numpy()
         # weighted fit with explicit random weights
         g = torch.Generator().manual_seed(7)

@@ -236,10 +236,10 @@ def test_neighbor_normals_match_reference_golden(golden, name, order):
     """fit_Wjet(..., compute_neighbor_normals=True) against the reference's own output."""
     from deepfit_b200 import DeepFit as D
     from oracle import deepfit_oracle as O
-    P = torch.from_numpy(golden[name + "/patch"][:8]).cuda()
-    beta, n_est, nn_ = D.fit_Wjet(P, torch.ones(8, 256, device="cuda"), order=order, compute_neighbor_normals=True)
+    P = torch.from_numpy(golden[name + "/patch"][:16]).cuda()
+    beta, n_est, nn_ = D.fit_Wjet(P, torch.ones(16, 256, device="cuda"), order=order, compute_neighbor_normals=True)
     ref = golden["%s/nn%d" % (name, order)]
-    assert tuple(nn_.shape) == (8, 256, 3)
+    assert tuple(nn_.shape) == (16, 256, 3)
     ang = O.unoriented_angle_deg(nn_.cpu().numpy().reshape(-1, 3), ref.reshape(-1, 3))
     # per row the same principled tolerance as for the centre normal (ill-conditioned order-4 rows)
     tol = 0.01 if order < 4 else 0.05
@@ -247,4 +247,4 @@ def test_neighbor_normals_match_reference_golden(golden, name, order):
     # and exactly the oracle's algebra when fed our own beta
     mine = O.neighbor_normals(P.cpu(), beta.cpu(), order)
     assert (nn_.cpu() - mine).abs().max() < 2e-5
-    assert D.fit_Wjet(P, torch.ones(8, 256, device="cuda"), order=order)[2] is None
+    assert D.fit_Wjet(P, torch.ones(16, 256, device="cuda"), order=order)[2] is None

@@ -68,12 +68,12 @@ def test_oracle_network_matches_golden(golden, name):
 @pytest.mark.parametrize("name", CLOUD_NAMES)
 def test_oracle_neighbor_normals_match_golden(golden, name):
     """fit_Wjet(..., compute_neighbor_normals=True): gradient at x/h, y/h with the un-preconditioned beta."""
-    P = torch.from_numpy(golden[name + "/patch"][:8])
+    P = torch.from_numpy(golden[name + "/patch"][:16])
     for order in (1, 2, 3, 4):
-        beta = torch.from_numpy(golden["%s/fit%d_beta" % (name, order)][:8])
+        beta = torch.from_numpy(golden["%s/fit%d_beta" % (name, order)][:16])
         nn_ = O.neighbor_normals(P, beta, order)
         ref = torch.from_numpy(golden["%s/nn%d" % (name, order)])
-        assert tuple(nn_.shape) == (8, 256, 3)
+        assert tuple(nn_.shape) == (16, 256, 3)
         assert (nn_ - ref).abs().max() < 2e-5
 
 
