@@ -241,9 +241,13 @@ def test_neighbor_normals_match_reference_golden(golden, name, order):
     ref = golden["%s/nn%d" % (name, order)]
     assert tuple(nn_.shape) == (16, 256, 3)
     ang = O.unoriented_angle_deg(nn_.cpu().numpy().reshape(-1, 3), ref.reshape(-1, 3))
-    # per row the same principled tolerance as for the centre normal (ill-conditioned order-4 rows)
-    tol = 0.01 if order < 4 else 0.05
-    assert ang.max() <= tol, "max angular deviation %g deg" % ang.max()
+    # the same principled per-point tolerance as for the centre normal: max(gate, 2 x the reference's own
+    # distance from the exact fp64 solution) -- far neighbours amplify its fp32 beta error at order 4
+    ex_beta, _ = O.fit_wjet(P.cpu().double(), torch.ones(16, 256, dtype=torch.float64), order)
+    ex = O.neighbor_normals(P.cpu().double(), ex_beta, order).numpy().reshape(-1, 3)
+    ref_err = O.unoriented_angle_deg(ref.reshape(-1, 3), ex)
+    assert (ang <= np.maximum(0.01, 2 * ref_err)).all(), "max angular deviation %g deg" % ang.max()
+    assert O.unoriented_angle_deg(nn_.cpu().numpy().reshape(-1, 3), ex).max() <= 5e-3   # ours vs exact
     # and exactly the oracle's algebra when fed our own beta
     mine = O.neighbor_normals(P.cpu(), beta.cpu(), order)
     assert (nn_.cpu() - mine).abs().max() < 2e-5

@@ -201,3 +201,38 @@ def test_deepfit_k128_single_tile_patches(clouds):
     ang = O.unoriented_angle_deg(normals.cpu().numpy(), ref_n)
     assert ang.max() <= 0.01, "max angular deviation %g deg" % ang.max()
     assert O.rectified_rel_err(curv.cpu().numpy(), ref_c).max() <= 1e-3
+
+
+def test_cli_deepfit_mode_with_saved_model(clouds, tmp_path):
+    """The drop-in CLI in DeepFit mode: reads <trained_model_path>/DeepFit_params.pth (pickled Namespace) and
+    DeepFit.pth (state_dict) exactly like tutorial/compute_normals.py:34-42, writes .normals / .curv."""
+    import argparse
+    from deepfit_b200 import compute_normals
+    from deepfit_b200.pipeline import NormalEstimator, model_from_state_dict
+    from deepfit_b200 import tutorial_utils as tu
+    from oracle import deepfit_oracle as O
+    mdir = tmp_path / "trained_models" / "DeepFit"
+    mdir.mkdir(parents=True)
+    sd = O.seeded_state_dict(0)
+    torch.save(sd, mdir / "DeepFit.pth")
+    params = argparse.Namespace(jet_order=3, use_point_stn=1, use_feat_stn=True, point_tuple=1, sym_op="max", arch="simple",
+                                n_gaussians=1, weight_mode="sigmoid", points_per_patch=256)
+    torch.save(params, mdir / "DeepFit_params.pth")
+    raw = clouds["Boxy_smooth100k"][:6000]
+    inp = tmp_path / "part.xyz"
+    np.savetxt(inp, raw, fmt="%.6f")
+    compute_normals.main(["--input", str(inp), "--output_path", str(tmp_path / "out"), "--mode", "DeepFit",
+                          "--trained_model_path", str(mdir), "--k_neighbors", "256"])
+    nrm = np.loadtxt(tmp_path / "out" / "part.normals")
+    crv = np.loadtxt(tmp_path / "out" / "part.curv")
+    assert nrm.shape == (6000, 3) and crv.shape == (6000, 2)
+    ds = tu.SinglePointCloudDataset(str(inp), 256)
+    model = model_from_state_dict(sd, 256, 3, "sigmoid", "bf16x3")
+    n2, c2 = NormalEstimator(ds.points_gpu, 256, mode="DeepFit", model=model).run()
+    assert np.array_equal(nrm.astype(np.float32), n2.cpu().numpy())       # '%.18e' round-trips exactly
+    assert np.array_equal(crv, c2.cpu().numpy())
+    # --ref-compat reproduces the shipped script's omission of the QSTN cancellation (compute_normals.py:67)
+    compute_normals.main(["--input", str(inp), "--output_path", str(tmp_path / "out2"), "--mode", "DeepFit",
+                          "--trained_model_path", str(mdir), "--k_neighbors", "256", "--ref-compat"])
+    nrm2 = np.loadtxt(tmp_path / "out2" / "part.normals")
+    assert O.unoriented_angle_deg(nrm, nrm2).max() > 0.1
