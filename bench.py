@@ -105,10 +105,11 @@ def make_cloud(total_points: int) -> np.ndarray:
     return np.ascontiguousarray(normalize_cloud(raw)[0], dtype=np.float32)
 
 
-def cpu_reference_rate(points: np.ndarray, sample: int, seed: int = 0):
+def cpu_reference_rate(points: np.ndarray, sample: int, seed: int = 0, sd=None):
     """The reference's CPU path (oracle port) on `sample` query points of the same cloud, all host threads."""
     from oracle import deepfit_oracle as O
-    sd = O.seeded_state_dict(0)
+    if sd is None:
+        sd = O.seeded_state_dict(0)
     rng = np.random.default_rng(seed)
     q = np.sort(rng.choice(points.shape[0], sample, replace=False))
     import scipy.spatial as spatial
@@ -201,12 +202,13 @@ def main():
     for kv in os.environ.get("DFB_DBG", "").split(","):     # kernel experiments, e.g. DFB_DBG=6:1 (never for reported numbers)
         if ":" in kv:
             _lib.load().dfb_dbg_set(int(kv.split(":")[0]), int(kv.split(":")[1]))
-    from oracle import deepfit_oracle as O   # only for the seeded weights + the cpu_baseline leg
+    from deepfit_b200.synthetic import synthetic_state_dict
 
     n_total = args.points * world
     pts_host = torch.from_numpy(make_cloud(n_total)).pin_memory()
     pts = pts_host.to(dev, non_blocking=True)
-    model = model_from_state_dict(O.seeded_state_dict(0), K, ORDER, "sigmoid", args.precision, dev)
+    state_dict = synthetic_state_dict(0, K, ORDER, device=dev)   # DeepFit.pth is not shipped with the reference
+    model = model_from_state_dict(state_dict, K, ORDER, "sigmoid", args.precision, dev)
     est = NormalEstimator(pts, K, ORDER, "DeepFit", model, chunk=args.chunk)
     begin, end = shard_range(n_total, rank, world)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
@@ -333,10 +335,20 @@ def main():
                          "network_tflops_algorithmic": (n_patches_timed * MLP_FLOP_PER_PATCH) / (net_ms * 1e-3) / 1e12 if net_ms else None},
             "kernel_ms": {k_: round(v[0], 3) for k_, v in prof.items()},
             "stages_one_chunk": stages,
+            # HBM-bound stages against SURVEY.md section 8(d)'s algorithmic bytes per patch at k=256: kNN + gather/PCA
+            # 7 224 B unfused convention (kNN selection itself is instruction-bound), jet fit + epilogue 4 240 B
+            "stage_rooflines": {
+                "knn_pca": {"bound": "hbm", "bytes_per_patch": 7224, "unit": "GB/s", "peak": hbm,
+                            "achieved": stages["chunk_points"] * 7224 / ((stages["knn_ms"] + stages["pca_ms"]) * 1e-3) / 1e9},
+                "wls": {"bound": "hbm", "bytes_per_patch": 4240, "unit": "GB/s", "peak": hbm,
+                        "achieved": stages["chunk_points"] * 4240 / (stages["wls_ms"] * 1e-3) / 1e9},
+            },
         }
+        for v in line["stage_rooflines"].values():
+            v["frac"] = v["achieved"] / v["peak"]
         if not args.no_cpu_baseline and world == 1:   # reported on rank 0 at N=1 only
             use_all_host_threads()
-            r, dt, t_tree = cpu_reference_rate(pts_host.numpy(), args.ref_sample)
+            r, dt, t_tree = cpu_reference_rate(pts_host.numpy(), args.ref_sample, sd={k_: v.cpu() for k_, v in state_dict.items()})
             line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": "%d random query points of the same cloud in %.1f s; cKDTree(workers=-1) + torch CPU, "
                                               "eval-mode forward, batch 256; tree build (%.2f s) excluded" % (args.ref_sample, dt, t_tree)}

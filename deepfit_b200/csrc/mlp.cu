@@ -569,6 +569,11 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_max_resident_kernel(const G
 // the 512->256 layer, whose accumulator (256 TMEM columns) lives for the whole tile.  W1p is streamed
 // in 64-row chunks (custom 8 KB blocks, LBO 1024), W2 in (k-block, n-tile) stages of 32 KB.
 // Saves writing and re-reading h1 (2 KB/point) and one kernel launch.
+// Optional per-CTA timeline (profiling aid, dfb_dbg_set key 7 = CTA index to trace, -1 = off): single lanes of the
+// traced CTA drop clock64() stamps into a 64-slot region per kernel (chains 0-2, head 3), read by dfb_dbg_timeline.
+__device__ long long g_tl_dev[4 * 64];
+#define DFB_TL(slot) do { if (g.tl && (int)blockIdx.x == g.tl_cta) g.tl[slot] = clock64(); } while (0)
+
 struct HeadArgs {
     const bf16* pf;      // tiled [rows, 64], hi plane; lo at +pf_plane
     size_t pf_plane;
@@ -592,6 +597,8 @@ struct HeadArgs {
     float b4;
     int weight_mode;
     float* out_w;        // fp32 [rows]
+    long long* tl;       // timeline region or NULL
+    int tl_cta;
     int dbg;             // profiling experiments only (dfb_dbg_set key 6; results are garbage): bit 0 = epilogues skip
                          // their math and stores, bit 1 = no layer-2 MMAs, bit 2 = no layer-2 weight loads,
                          // bit 3 = no layer-1 MMAs
@@ -628,6 +635,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
     constexpr uint32_t kConsumers = CL2 ? 2u : 1u;
 
     if (threadIdx.x == 0) {
+        DFB_TL(0);
         mbar_init(smem_u32(&s_pf), 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&s_w1f[i]), 1); mbar_init(smem_u32(&s_w1e[i]), kConsumers);
@@ -657,6 +665,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
     }
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
+    if (threadIdx.x == 0) DFB_TL(1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -719,6 +728,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                     const int s = i & 1;
                     // phase 0 of w3e = "PF/W1R no longer read by any layer-1 MMA" (both CTAs in a cluster)
                     if (!mbar_wait(smem_u32(&s_w3e[s]), (uint32_t)(i >> 1) & 1u, g.err, 1)) { ok = false; break; }
+                    if (i == 0) DFB_TL(59);
                     const uint32_t bar = smem_u32(&s_w3f[s]);
                     mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
                     for (int pl = 0; pl < planes; ++pl)
@@ -740,6 +750,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                     umma_commit(bar);
             };
             bool ok = mbar_wait(smem_u32(&s_pf), 0u, g.err, 2);
+            DFB_TL(2);
             auto mma1 = [&](int c) {   // D1[c&3] = pf * W1chunk(c)^T
                 const int b = c & 1;                       // W1 ring slot
                 const uint32_t use = (uint32_t)(c >> 1);
@@ -748,6 +759,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 if (!mbar_wait(smem_u32(&s_w1f[b]), use & 1u, g.err, 2)) { ok = false; return; }
                 if (duse > 0 && !mbar_wait(smem_u32(&s_d1e[db]), (duse - 1u) & 1u, g.err, 4)) { ok = false; return; }
                 tc_fence_after();
+                DFB_TL(4 + c * 6);
                 const uint32_t d = tmem_base + 256u + (uint32_t)db * 64u;
                 const uint32_t w_hi = W1R + (uint32_t)b * 16384u, w_lo = w_hi + 8192u;
 #pragma unroll
@@ -786,6 +798,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 const int b = c & 1;
                 const uint32_t use = (uint32_t)(c >> 1);
                 if (!mbar_wait(smem_u32(&s_h1f[b]), use & 1u, g.err, 5)) { ok = false; return; }
+                DFB_TL(4 + c * 6 + 4);
                 const uint32_t a_hi = H1R + (uint32_t)b * 32768u, a_lo = a_hi + kBlkBytes;
                 for (int h = 0; h < 2; ++h) {
                     const int s = w2i % 3;
@@ -809,12 +822,14 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                     ++w2i;
                 }
                 umma_commit(smem_u32(&s_h1e[b]));
+                DFB_TL(4 + c * 6 + 5);
             };
             for (int c = 0; c < 8 && ok; ++c) mma2(c);
             if (ok) umma_commit(smem_u32(&s_d2f));
             if (ok && g.fuse_l3) {
                 const uint32_t idesc128 = umma_idesc(128);
                 ok = mbar_wait(smem_u32(&s_h2f), 0u, g.err, 5);
+                DFB_TL(54);
                 for (int kb = 0; kb < 4 && ok; ++kb) {
                     const int s = kb & 1;
                     ok = mbar_wait(smem_u32(&s_w3f[s]), (uint32_t)(kb >> 1) & 1u, g.err, 2);
@@ -835,6 +850,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                     release_weights(smem_u32(&s_w3e[s]));
                 }
                 if (ok) umma_commit(smem_u32(&s_d3f));
+                DFB_TL(55);
             }
         }
     } else {
@@ -850,6 +866,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
         uint32_t v[32];
         bool ok = true;
+        const bool tl_lane = lane == 0 && (ew & 7) == 0;   // one stamping lane per epilogue group
         for (int c = grp; c < 8 && ok; c += 2) {
             const int b = grp;                                // h1 buffer of this group
             const uint32_t use = (uint32_t)(c >> 1);
@@ -858,6 +875,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             ok = mbar_wait(smem_u32(&s_d1f[db]), duse & 1u, g.err, 3);
             if (!ok) break;
             tc_fence_after();
+            if (tl_lane) DFB_TL(4 + c * 6 + 1);
             if (g.dbg & 1) {   // experiment: synchronisation skeleton only
                 tc_fence_before();
                 __syncwarp();
@@ -879,6 +897,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 ok = mbar_wait(smem_u32(&s_h1e[b]), (use - 1u) & 1u, g.err, 6);
                 if (!ok) break;
             }
+            if (tl_lane) DFB_TL(4 + c * 6 + 2);
             const uint32_t h_hi = H1R + (uint32_t)b * 32768u + (uint32_t)(lrow >> 3) * 128u + (uint32_t)(lrow & 7) * 16u +
                                   (uint32_t)half * 4u * 2048u;
 #pragma unroll
@@ -893,9 +912,11 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             fence_async_smem();   // generic-proxy writes -> visible to the tensor core's async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_h1f[b]));
+            if (tl_lane) DFB_TL(4 + c * 6 + 3);
         }
         if (ok) ok = mbar_wait(smem_u32(&s_d2f), 0u, g.err, 3);
         tc_fence_after();
+        if (tl_lane && grp == 0) DFB_TL(52);
         if (ok) {
 #pragma unroll 1
             for (int c0 = quarter * 64; c0 < quarter * 64 + 64; c0 += 32) {
@@ -930,9 +951,11 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&s_h2f));
+                if (tl_lane && grp == 0) DFB_TL(53);
                 if (quarter == 0) {   // one warp per lane quadrant finishes the row: ReLU(conv3) . w4 + b4 -> weight
                     ok = mbar_wait(smem_u32(&s_d3f), 0u, g.err, 3);
                     tc_fence_after();
+                    if (tl_lane) DFB_TL(56);
                     if (ok) {
                         float dot = 0.f;
 #pragma unroll 1
@@ -948,12 +971,14 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                                                                                       : (0.01f + 1.f + tanhf(a)) * 0.5f;
                         }
                     }
+                    if (tl_lane) DFB_TL(57);
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) DFB_TL(58);
     if (CL2) {   // neither CTA may retire while the other can still multicast into it
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -985,6 +1010,7 @@ struct ChainLayer {
     int n_out;                // 64 or 128
     bf16* store_t;            // optional global copy of the output (tiled, 128-row blocks, KB = 1)
     size_t store_plane;
+    const float* h_bias;      // host copy of bias (launch_chain copies it into ChainArgs::biasc; unused on the device)
 };
 
 struct ChainArgs {
@@ -992,8 +1018,11 @@ struct ChainArgs {
     const float* R;           // f32 [n,3,3] or NULL
     float* pts_out;           // optional rotated points [n,3,k]
     int k;
-    const float* w0;          // f32 [64,3]
-    const float* b0;          // f32 [64]
+    // the K=3 layer and every small-layer bias travel in the kernel parameters: constant-bank operands cost no
+    // load instruction and no cold-L1 miss at the start of every CTA
+    float w0c[64 * 3];        // f32 [64,3]
+    float b0c[64];
+    float biasc[3][128];      // bias of small layer l (zeros when the layer has none)
     int n_layers;
     ChainLayer L[3];
     const bf16* w3;           // tiled [1024,128]
@@ -1006,10 +1035,31 @@ struct ChainArgs {
     int out_KB;
     float* out_f;             // optional fp32 [n, n_ch]
     int nprod;
+    long long* tl;            // timeline region or NULL
+    int tl_cta;
     int* err;
 };
 
-constexpr int kChainEpiWarps = 8;
+constexpr int kChainEpiWarps = 16;
+
+// relu(W0 p + b0) for 32 of the 64 channels (HALF selects which), straight into the A operand (hi/lo planes)
+template <int HALF>
+__device__ __forceinline__ void chain_first_layer(const ChainArgs& g, float x, float y, float z, uint32_t dst, uint32_t lo_off) {
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = HALF * 32 + c8 * 8 + 2 * e;
+            const float f0 = fmaxf(fmaf(g.w0c[c * 3 + 2], z, fmaf(g.w0c[c * 3 + 1], y, fmaf(g.w0c[c * 3], x, g.b0c[c]))), 0.f);
+            const float f1 = fmaxf(fmaf(g.w0c[c * 3 + 5], z, fmaf(g.w0c[c * 3 + 4], y, fmaf(g.w0c[c * 3 + 3], x, g.b0c[c + 1]))), 0.f);
+            split_pair(f0, f1, ph[e], pl[e]);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)c8 * 2048u), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
+        if (g.nprod > 1)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + lo_off + (uint32_t)c8 * 2048u), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
+    }
+}
 constexpr int kChainThreads = 64 + kChainEpiWarps * 32;
 
 template <int NT>
@@ -1017,7 +1067,6 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_wf[3], s_act[2], s_acc[2], s_rf[3], s_re[3], s_tf[2], s_te[2];
     __shared__ uint32_t s_tmem;
-    __shared__ float s_w0[64 * 3 + 64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int planes = g.nprod > 1 ? 2 : 1;
     const long long patch = blockIdx.x;
@@ -1044,9 +1093,17 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
     const int CT = g.n_ch / 128;
     const int L = g.n_layers;
 
+    // the epilogue warps fetch their point before the set-up barrier so the DRAM latency overlaps the TMEM allocation
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (warp >= 2 && (((warp - 2) >> 2) & 1) < NT) {
+        const int j = (((warp - 2) >> 2) & 1) * 128 + (warp & 3) * 32 + lane;
+        const float* base = g.patch + patch * 3LL * g.k;
+        px = __ldg(base + j); py = __ldg(base + g.k + j); pz = __ldg(base + 2 * g.k + j);
+    }
     if (threadIdx.x == 0) {
+        DFB_TL(0);
         for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&s_wf[i]), 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_act[i]), 4); mbar_init(smem_u32(&s_acc[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_act[i]), 8); mbar_init(smem_u32(&s_acc[i]), 1); }
         for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&s_rf[i]), 1); mbar_init(smem_u32(&s_re[i]), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_tf[i]), 1); mbar_init(smem_u32(&s_te[i]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1055,12 +1112,11 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         tmem_alloc(smem_u32(&s_tmem), kTmemCols);
         tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < 64 * 3; i += blockDim.x) s_w0[i] = g.w0[i];
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) s_w0[192 + i] = g.b0[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
+    if (threadIdx.x == 0) DFB_TL(1);
     // activation buffer read by small layer l (they alternate, and the last layer must read ACT_A because
     // it writes X, which aliases ACT_B)
     auto act_in = [&](int l) { return ((L - 1 - l) & 1) ? ACT_B : ACT_A; };
@@ -1082,6 +1138,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                 // phase 0 of s_re = "the small layers no longer read region R" (committed by the MMA warp)
                 ok = mbar_wait(smem_u32(&s_re[s]), (uint32_t)(i / 3) & 1u, g.err, 1);
                 if (!ok) break;
+                if (i == 0) DFB_TL(43);
                 const uint32_t bar = smem_u32(&s_rf[s]);
                 mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
                 for (int pl = 0; pl < planes; ++pl)
@@ -1107,6 +1164,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                     ok = ok && mbar_wait(smem_u32(&s_act[t]), (uint32_t)l & 1u, g.err, 5);
                     if (!ok) break;
                     tc_fence_after();
+                    DFB_TL(4 + (l * 2 + t) * 3);
                     const uint32_t a_hi = ain + (uint32_t)t * kBlkBytes, a_lo = ain + (uint32_t)(NT + t) * kBlkBytes;
                     const uint32_t d = tmem_base + (uint32_t)t * 128u;
 #pragma unroll
@@ -1125,6 +1183,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                 for (int s = 0; s < 3; ++s) umma_commit(smem_u32(&s_re[s]));
                 for (int t = 0; t < NT && ok; ++t)
                     ok = mbar_wait(smem_u32(&s_act[t]), (uint32_t)L & 1u, g.err, 5);   // X written, TMEM drained
+                DFB_TL(22);
             }
             const uint32_t idesc = umma_idesc(NT * 128);
             const uint32_t lbo_b = (uint32_t)NT * kLBO;
@@ -1140,6 +1199,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                     ok = mbar_wait(smem_u32(&s_rf[s]), (uint32_t)(i / 3) & 1u, g.err, 2);
                     if (!ok) break;
                     tc_fence_after();
+                    if (i == 0) DFB_TL(23);
                     const uint32_t a_hi = RR + (uint32_t)s * (2u * kBlkBytes), a_lo = a_hi + kBlkBytes;
                     const uint32_t b_hi = XR + (uint32_t)(0 * KB3 + kb) * (NT * kBlkBytes);
                     const uint32_t b_lo = XR + (uint32_t)(1 * KB3 + kb) * (NT * kBlkBytes);
@@ -1157,66 +1217,62 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                     umma_commit(smem_u32(&s_re[s]));
                 }
                 if (ok) umma_commit(smem_u32(&s_tf[buf]));
+                DFB_TL(24 + (ct & 7));
             }
         }
     } else {
-        // ===================== 8 epilogue warps =====================
+        // ===================== 16 epilogue warps =====================
+        // phases P/S: 4 lane quadrants x 2 row tiles x 2 column halves (the per-layer epilogue is the serial part of
+        // the prologue, so it gets every issue slot it can use); phase M: the column-half-0 warps only (max over all
+        // columns of a lane; the MMAs bound that phase)
         const int ew = warp - 2;
         const int q = warp & 3;                   // TMEM lane quadrant (hardware rule)
-        const int grp = ew >> 2;                  // phases P/S: row tile; phase M: channel-tile parity
+        const int grp = (ew >> 2) & 1;            // phases P/S: row tile; phase M: channel-tile parity
+        const int half = ew >> 3;                 // phases P/S: column half
         const int lrow = q * 32 + lane;
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
         const bool active = grp < NT;             // owns a row of the patch in phases P/S
         const int k = g.k;
         bool ok = true;
         uint32_t v[32];
+        const bool tl_lane = lane == 0 && q == 0 && half == 0;   // one stamping lane per epilogue group
         // element offset of (row lrow, 8-channel chunk j) inside a 128-row operand block
         const uint32_t row_off = (uint32_t)(lrow >> 3) * 128u + (uint32_t)(lrow & 7) * 16u;
         // ---- phase P ----
         if (active) {
             const int j = grp * 128 + lrow;       // point index inside the patch
-            const float* base = g.patch + patch * 3LL * k;
-            float x = base[j], y = base[k + j], z = base[2 * k + j];
+            float x = px, y = py, z = pz;
             if (g.R) {
                 const float* r = g.R + patch * 9;
                 const float xr = fmaf(z, r[6], fmaf(y, r[3], x * r[0]));
                 const float yr = fmaf(z, r[7], fmaf(y, r[4], x * r[1]));
                 const float zr = fmaf(z, r[8], fmaf(y, r[5], x * r[2]));
                 x = xr; y = yr; z = zr;
-                if (g.pts_out) {
+                if (g.pts_out && half == 0) {
                     float* po = g.pts_out + patch * 3LL * k;
                     po[j] = x; po[k + j] = y; po[2 * k + j] = z;
                 }
             }
-            const uint32_t dst = act_in(0) + (uint32_t)grp * kBlkBytes + row_off;
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-                uint32_t ph[4], pl[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int c = c8 * 8 + 2 * e;
-                    const float f0 = fmaxf(fmaf(s_w0[c * 3 + 2], z, fmaf(s_w0[c * 3 + 1], y, fmaf(s_w0[c * 3], x, s_w0[192 + c]))), 0.f);
-                    const float f1 = fmaxf(fmaf(s_w0[c * 3 + 5], z, fmaf(s_w0[c * 3 + 4], y, fmaf(s_w0[c * 3 + 3], x, s_w0[193 + c]))), 0.f);
-                    split_pair(f0, f1, ph[e], pl[e]);
-                }
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)c8 * 2048u), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
-                if (g.nprod > 1)
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)NT * kBlkBytes + (uint32_t)c8 * 2048u), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
-            }
+            const uint32_t dst = act_in(0) + (uint32_t)grp * kBlkBytes + row_off + (uint32_t)half * 4u * 2048u;
+            if (half == 0) chain_first_layer<0>(g, x, y, z, dst, (uint32_t)NT * kBlkBytes);
+            else chain_first_layer<1>(g, x, y, z, dst, (uint32_t)NT * kBlkBytes);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_act[grp]));
+            if (tl_lane) DFB_TL(2 + grp);
         }
         // ---- phase S ----
         for (int l = 0; l < L && ok && active; ++l) {
             ok = mbar_wait(smem_u32(&s_acc[grp]), (uint32_t)l & 1u, g.err, 3);
             if (!ok) break;
             tc_fence_after();
+            if (tl_lane) DFB_TL(4 + (l * 2 + grp) * 3 + 1);
             const ChainLayer& Ly = g.L[l];
             const bool last = (l == L - 1);
             const long long grow = patch * k + grp * 128 + lrow;   // global row (point) index
+            const int cbeg = half * (Ly.n_out >> 1);
 #pragma unroll 1
-            for (int c0 = 0; c0 < Ly.n_out; c0 += 32) {
+            for (int c0 = cbeg; c0 < cbeg + (Ly.n_out >> 1); c0 += 32) {
                 tmem_ld32(tmem_base + tlane + (uint32_t)(grp * 128 + c0), v);
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8) {
@@ -1225,7 +1281,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                     for (int e = 0; e < 4; ++e) {
                         const int i0 = c8 * 8 + 2 * e;
                         float x0 = __uint_as_float(v[i0]), x1 = __uint_as_float(v[i0 + 1]);
-                        if (Ly.bias) { x0 += __ldg(Ly.bias + c0 + i0); x1 += __ldg(Ly.bias + c0 + i0 + 1); }
+                        x0 += g.biasc[l][c0 + i0]; x1 += g.biasc[l][c0 + i0 + 1];
                         if (Ly.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
                         split_pair(x0, x1, ph[e], pl[e]);
                     }
@@ -1253,14 +1309,16 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_act[grp]));
+            if (tl_lane) DFB_TL(4 + (l * 2 + grp) * 3 + 2);
         }
         // ---- phase M: group g takes the channel tiles of parity g ----
-        for (int ct = grp; ct < CT && ok; ct += 2) {
+        for (int ct = grp; ct < CT && ok && half == 0; ct += 2) {
             const int buf = ct & 1;                 // == grp
             const uint32_t use = (uint32_t)(ct >> 1);
             ok = mbar_wait(smem_u32(&s_tf[buf]), use & 1u, g.err, 3);
             if (!ok) break;
             tc_fence_after();
+            if (tl_lane) DFB_TL(32 + (ct & 7));
             float mx = -3.402823466e38f;
 #pragma unroll 1
             for (int c0 = 0; c0 < NT * 128; c0 += 32) {
@@ -1283,10 +1341,12 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                 g.out_t[g.out_plane + o] = lo;
             }
         }
+        if (tl_lane) DFB_TL(40 + grp);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (threadIdx.x == 0) DFB_TL(42);
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
@@ -1464,6 +1524,7 @@ int alloc_tiled(TiledBuf& t, long long rows, int cols, int br = 128) {
 struct PackedLayer {
     TiledBuf w;        // tiled weights [out_pad, in_pad]
     float* bias = nullptr;  // device fp32 [out]
+    std::vector<float> h_bias;  // host copy (kernel-parameter constants of the fused chain kernels)
     int in = 0, out = 0;
 };
 
@@ -1477,6 +1538,7 @@ struct dfb_model {
     dfb::PackedLayer head_global;  // HEAD_CONV1 columns 0..1023  (bias = folded conv1 bias)
     dfb::PackedLayer head_point;   // HEAD_CONV1 columns 1024..1087 (no bias of its own)
     float* w_small[DFB_NUM_LAYERS] = {nullptr};  // raw fp32 weights of the CUDA-core layers
+    std::vector<float> h_w_small[DFB_NUM_LAYERS];  // host copies of the two K=3 layers
     dfb::bf16* head_w1c = nullptr;               // HEAD_CONV1 point part in 64-row chunks for the fused head
     dfb::PackedLayer head_w2_256;                // HEAD_CONV2 in 256-row blocks (N=256 MMAs of the fused head)
     // workspace
@@ -1550,6 +1612,13 @@ namespace {
 // lock-step of the pair.  Off by default; dfb_dbg_set key 3 turns it on.
 int g_head_cluster = 0;
 
+int g_tl_cta = -1;   // dfb_dbg_set key 7: CTA whose timeline is recorded (-1 = off)
+long long* timeline_region(int region) {
+    if (g_tl_cta < 0) return nullptr;
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_tl_dev) != cudaSuccess) return nullptr;
+    return static_cast<long long*>(p) + region * 64;
+}
 int g_head_dbg = 0;  // profiling experiments (dfb_dbg_set key 6), see HeadArgs::dbg
 int g_head_l3 = 1;  // debug switch (dfb_dbg_set key 4): 0 = layer 3 + weight epilogue as a separate launch
 
@@ -1573,6 +1642,7 @@ int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, co
     a.weight_mode = m->weight_mode;
     a.out_w = out_w;
     a.dbg = g_head_dbg;
+    a.tl = timeline_region(3); a.tl_cta = g_tl_cta;
     a.err = m->err;
     const size_t smem = 224 * 1024;
     const unsigned tiles = (unsigned)((rows + 127) / 128);
@@ -1758,6 +1828,7 @@ ChainLayer chain_layer(const PackedLayer& pl, int relu) {
     ChainLayer c;
     memset(&c, 0, sizeof(c));
     c.w = pl.w.p; c.w_plane = pl.w.plane; c.bias = pl.bias; c.relu = relu; c.n_out = pl.out;
+    c.h_bias = pl.h_bias.empty() ? nullptr : pl.h_bias.data();
     return c;
 }
 
@@ -1765,12 +1836,17 @@ int launch_chain(const dfb_model* m, const float* patch, long long n_patch, cons
     ChainArgs a;
     memset(&a, 0, sizeof(a));
     a.patch = patch; a.R = sp.R; a.pts_out = sp.pts_out; a.k = m->k;
-    a.w0 = m->w_small[sp.first_layer]; a.b0 = m->L[sp.first_layer].bias;
+    memcpy(a.w0c, m->h_w_small[sp.first_layer].data(), sizeof(a.w0c));
+    memcpy(a.b0c, m->L[sp.first_layer].h_bias.data(), sizeof(a.b0c));
     a.n_layers = sp.n_layers;
-    for (int i = 0; i < sp.n_layers; ++i) a.L[i] = sp.L[i];
+    for (int i = 0; i < sp.n_layers; ++i) {
+        a.L[i] = sp.L[i];
+        if (sp.L[i].h_bias) memcpy(a.biasc[i], sp.L[i].h_bias, sizeof(float) * sp.L[i].n_out);
+    }
     a.w3 = sp.W3->w.p; a.w3_plane = sp.W3->w.plane; a.bias3 = sp.W3->bias; a.relu3 = sp.relu3; a.n_ch = sp.W3->out;
     a.out_t = gfeat.p; a.out_plane = gfeat.plane; a.out_KB = gfeat.KB;
     a.nprod = m->nprod; a.err = m->err;
+    a.tl = timeline_region(sp.n_layers == 1 ? 0 : (sp.relu3 ? 1 : 2)); a.tl_cta = g_tl_cta;
     const int NT = m->k / 128;
     const size_t smem = (size_t)2 * NT * 2 * kBlkBytes + 96 * 1024;
     static bool attr_done[3] = {false, false, false};
@@ -1856,6 +1932,16 @@ extern "C" DFB_API int dfb_dbg_set(int key, int value) {
     if (key == 4) dfb::g_head_l3 = value;
     if (key == 5) dfb::g_chain = value;
     if (key == 6) dfb::g_head_dbg = value;
+    if (key == 7) dfb::g_tl_cta = value;
+    return DFB_OK;
+}
+
+// Profiling aid: copies the 4 x 64 clock64() stamps (chains 0-2, head) of the traced CTA to the host.
+extern "C" DFB_API int dfb_dbg_timeline(long long* host_out, int n) {
+    using namespace dfb;
+    DFB_REQUIRE(host_out && n >= 4 * 64, DFB_E_ARG, "dfb_dbg_timeline: need room for 256 stamps");
+    DFB_CUDA(cudaDeviceSynchronize());
+    DFB_CUDA(cudaMemcpyFromSymbol(host_out, g_tl_dev, sizeof(long long) * 4 * 64));
     return DFB_OK;
 }
 
@@ -1909,6 +1995,8 @@ extern "C" int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, d
         track(m->L[i].bias);
         m->L[i].in = l.in_features;
         m->L[i].out = l.out_features;
+        m->L[i].h_bias.assign(l.h_bias, l.h_bias + l.out_features);
+        if (i == DFB_L_QSTN_CONV1 || i == DFB_L_PF_CONV1) m->h_w_small[i].assign(l.h_weight, l.h_weight + 3 * 64);
         const bool small = (i == DFB_L_QSTN_CONV1 || i == DFB_L_PF_CONV1 || i == DFB_L_QSTN_FC3 || i == DFB_L_HEAD_CONV4);
         if (i == DFB_L_HEAD_CONV4) m->b4 = l.h_bias[0];
         if (small) {

@@ -1,5 +1,7 @@
 """Seeded synthetic analytic-surface clouds of the sizes BASELINE.json names.
-Pure numpy on the host: these are inputs, not part of the hot path."""
+Pure numpy on the host: these are inputs, not part of the hot path.  ``synthetic_state_dict`` is the seeded
+stand-in for the missing ``trained_models/DeepFit/DeepFit.pth`` used by bench.py and tools/ (the tests use the
+oracle's own generator and the golden fixtures made with it).  Nothing here imports ``oracle/``."""
 from __future__ import annotations
 
 import numpy as np
@@ -101,3 +103,60 @@ def write_pcpnet_like(root: str, n_shapes: int = 20, n_points: int = 100000, n_s
     with open(os.path.join(root, list_name), "w") as fh:
         fh.write("\n".join(names) + "\n")
     return names
+
+
+def synthetic_state_dict(seed: int = 0, num_points: int = 256, jet_order: int = 3, head_gain: float = 2.0,
+                         device="cuda"):
+    """A reproducible random ``state_dict`` with the reference's 125 keys (models/DeepFit.py constructors):
+    He-uniform conv/fc weights, randomised BatchNorm affine + running statistics, transform heads shrunk
+    so the predicted rotations stay near identity, and the last layer rescaled so the predicted weights
+    spread over (0.01, 1.01).  The rescaling runs the network itself -- on the GPU, through the CUDA
+    library (there is no CPU path) -- on eight synthetic paraboloid patches and reads the logits back from
+    the sigmoid weights."""
+    import math
+    from collections import OrderedDict
+
+    import torch
+
+    from .DeepFit import DeepFit
+    g = torch.Generator().manual_seed(int(seed))
+
+    def U(shape, bound):
+        return (torch.rand(tuple(shape), generator=g) * 2 - 1) * bound
+
+    model = DeepFit(k=1, num_points=num_points, use_point_stn=True, use_feat_stn=True, point_tuple=1, sym_op="max",
+                    arch="simple", jet_order=jet_order, weight_mode="sigmoid")
+    sd = OrderedDict()
+    for name, t in model.state_dict().items():
+        leaf = name.rsplit(".", 1)[1]
+        is_bn = ".bn" in name or name.startswith("bn")
+        if leaf == "num_batches_tracked":
+            sd[name] = torch.tensor(100, dtype=torch.long)
+        elif is_bn:
+            sd[name] = {"weight": lambda: 1.0 + U(t.shape, 0.25), "bias": lambda: U(t.shape, 0.1),
+                        "running_mean": lambda: U(t.shape, 0.1), "running_var": lambda: 1.0 + U(t.shape, 0.5)}[leaf]()
+        elif leaf == "weight":
+            sd[name] = U(t.shape, math.sqrt(6.0 / t.shape[1]))
+        else:
+            sd[name] = U(t.shape, 0.1)
+    for p, shrink in (("feat.pointfeat.stn1.fc3", 0.02), ("feat.pointfeat.stn2.fc3", 0.01)):
+        sd[p + ".weight"] *= shrink
+        sd[p + ".bias"] *= shrink
+    sd["conv1.weight"][:, 1024:, :] *= 4.0           # let the per-point branch matter next to the 1024 global channels
+    sd["conv4.weight"] *= 0.05                       # keep the uncalibrated logits well inside the sigmoid's linear range
+    sd["conv4.bias"] *= 0.0
+    k = num_points
+    xy = torch.rand((8, 2, k), generator=g) * 1.4 - 0.7
+    c = torch.rand((8, 3, 1), generator=g) - 0.5
+    zz = 0.3 * (c[:, 0:1] * xy[:, 0:1] ** 2 + c[:, 1:2] * xy[:, 1:2] ** 2 + c[:, 2:3] * xy[:, 0:1] * xy[:, 1:2])
+    zz = zz + 0.02 * (torch.rand((8, 1, k), generator=g) - 0.5)
+    model.load_state_dict(sd)
+    model.to(device).eval()
+    with torch.no_grad():
+        w = model(torch.cat([xy, zz], 1).to(device))[2].double().cpu() - 0.01
+    w = w.clamp(1e-6, 1 - 1e-6)
+    a = torch.log(w / (1 - w))
+    scale = head_gain / float(a.std())
+    sd["conv4.bias"] = ((sd["conv4.bias"].double() - a.mean()) * scale).float()
+    sd["conv4.weight"] = (sd["conv4.weight"].double() * scale).float()
+    return sd

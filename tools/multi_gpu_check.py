@@ -23,12 +23,12 @@ def main():
     from deepfit_b200 import synthetic
     from deepfit_b200.pipeline import NormalEstimator, gather_outputs, model_from_state_dict, shard_range
     from deepfit_b200.tutorial_utils import normalize_cloud
-    from oracle import deepfit_oracle as O
+    from deepfit_b200.synthetic import synthetic_state_dict
     n = 30011  # deliberately not divisible by the world size
     pts = torch.from_numpy(np.ascontiguousarray(normalize_cloud(synthetic.torus_cloud(n, seed=5, noise=0.003))[0])).cuda()
     ok = True
     for mode in ("classic", "DeepFit"):
-        model = model_from_state_dict(O.seeded_state_dict(0), 256, 3, "sigmoid", "bf16x3", "cuda") if mode == "DeepFit" else None
+        model = model_from_state_dict(synthetic_state_dict(0), 256, 3, "sigmoid", "bf16x3", "cuda") if mode == "DeepFit" else None
         est = NormalEstimator(pts, 256, 3, mode, model, chunk=2048)
         b, e = shard_range(n, rank, world)
         nl, cl = est.run(b, e)

@@ -1,0 +1,74 @@
+"""Per-CTA phase timeline of the two fused network kernels (profiling aid; clock64 stamps, see DFB_TL in mlp.cu).
+
+    python tools/timeline.py [--cta 2000] [--batch 4096]
+
+Prints, for one traced CTA of each chain kernel (QSTN / STN / encoder) and of the head kernel, the cycle offsets
+of the phase boundaries relative to the CTA's first instruction."""
+import argparse
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CHAIN = {0: "entry", 1: "setup done", 2: "P done t0", 3: "P done t1", 22: "M start (X ready)", 23: "first W3 stage landed",
+         40: "epi grp0 end", 41: "epi grp1 end", 42: "exit", 43: "TMA: ring free (first W3 issue)"}
+for l in range(3):
+    for t in range(2):
+        b = 4 + (l * 2 + t) * 3
+        CHAIN[b] = "L%d t%d mma issue" % (l, t)
+        CHAIN[b + 1] = "L%d t%d acc ready" % (l, t)
+        CHAIN[b + 2] = "L%d t%d epi done" % (l, t)
+for ct in range(8):
+    CHAIN[24 + ct] = "M ct%d issued" % ct
+    CHAIN[32 + ct] = "M ct%d acc ready" % ct
+HEAD = {0: "entry", 1: "setup done", 2: "PF landed", 52: "D2 ready", 53: "h2 written", 54: "mma: h2 ready", 55: "mma: L3 issued",
+        56: "D3 ready", 57: "epi end", 58: "exit", 59: "TMA: first W3 issue"}
+for c in range(8):
+    b = 4 + c * 6
+    for i, nm in enumerate(["mma1 issue", "D1 ready", "h1 slot free", "h1 written", "mma2 start", "mma2 issued"]):
+        HEAD[b + i] = "c%d %s" % (c, nm)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cta", type=int, default=2000)
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--precision", type=str, default="bf16x3")
+    args = ap.parse_args()
+    from deepfit_b200 import _lib
+    from deepfit_b200.pipeline import model_from_state_dict
+    from deepfit_b200.synthetic import synthetic_state_dict
+    lib = _lib.load()
+    model = model_from_state_dict(synthetic_state_dict(0), 256, jet_order=3, precision=args.precision)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    patch = torch.randn(args.batch, 3, 256, device="cuda", generator=g) * 0.3
+    net = model._network(patch.device, args.batch)
+    for _ in range(3):
+        net.forward(patch)
+    torch.cuda.synchronize()
+    lib.dfb_dbg_set(7, args.cta)
+    net.forward(patch)
+    torch.cuda.synchronize()
+    buf = (C.c_longlong * 256)()
+    lib.dfb_dbg_timeline.argtypes = [C.POINTER(C.c_longlong), C.c_int]
+    rc = lib.dfb_dbg_timeline(buf, 256)
+    lib.dfb_dbg_set(7, -1)
+    assert rc == 0
+    tl = np.array(buf[:], dtype=np.int64).reshape(4, 64)
+    for region, name, names in ((0, "QSTN chain", CHAIN), (1, "STN chain", CHAIN), (2, "encoder chain", CHAIN), (3, "head", HEAD)):
+        t0 = tl[region, 0]
+        print("== %s, CTA %d" % (name, args.cta))
+        rows = sorted(((int(tl[region, s] - t0), nm) for s, nm in names.items() if tl[region, s] != 0))
+        prev = 0
+        for t, nm in rows:
+            print("%8d  (+%6d)  %s" % (t, t - prev, nm))
+            prev = t
+
+
+if __name__ == "__main__":
+    main()
