@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=262144, help="points per GPU")
     ap.add_argument("--precision", type=str, default="bf16x3")
-    ap.add_argument("--chunk", type=int, default=4096)
+    ap.add_argument("--chunk", type=int, default=16384)
     ap.add_argument("--ref-sample", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -326,7 +326,7 @@ def main():
                          # kernels of one forward (13.2 / 13.4 / 378.8 MB), from profiles/r1_ncu_full_chain_and_head.csv;
                          # algorithmic bytes: 12.6 MB of patches (+ 128 MB per-patch T2 operands read and 256 MB x*T2
                          # written by the encoder chain)
-                         "traffic": 135.1e6 if args.chunk == 4096 else None,
+                         "traffic": 135.1e6 * args.chunk / 4096,   # captured at 4096 patches per launch; every term scales with the patch count
                          "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained" % which,
                          "note": "achieved = algorithmic FLOPs of the three chain kernels (222.6 MFLOP/patch at k=256) / their CUDA-event "
                                  "time; parity precision bf16x3 executes 3x that on the tensor pipe, so the ceiling of frac is 0.333",

@@ -83,6 +83,17 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
         }
     }
 }
+// One lane of a converged warp (elect.sync): unlike `lane == 0`, the compiler knows the guarded code is single-threaded
+// and feeds tcgen05.mma its uniform-register operands without an ELECT / BRA.U.ANY loop around every instruction.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -107,6 +118,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
         "l"(da), "l"(db), "r"(idesc), "r"(accum)
         : "memory");
 }
+// A operand from tensor memory (lane = row, each 32-bit column holds two consecutive K elements), B from shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -119,6 +145,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
           "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -248,7 +285,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = 0; kb < g.KB; ++kb) {
                 const int s = kb % stages;
                 const uint32_t it = (uint32_t)(kb / stages);
@@ -269,7 +306,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc(g.n_mma);
             bool ok = true;
             for (int kb = 0; kb < g.KB && ok; ++kb) {
@@ -461,7 +498,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_max_resident_kernel(const G
     const uint32_t w_base = smem_base + x_bytes;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t xfull = smem_u32(&s_xfull);
             mbar_expect_tx(xfull, x_bytes);
             // X is stored in blocks of NT*128 rows (one patch), so each (plane, k-block) is one copy
@@ -484,7 +521,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_max_resident_kernel(const G
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc(NT * 128);   // one MMA spans the whole patch (N = k)
             const uint32_t lbo_b = (uint32_t)NT * kLBO;
             bool ok = mbar_wait(smem_u32(&s_xfull), 0u, g.err, 2);
@@ -572,6 +609,13 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_max_resident_kernel(const G
 // Optional per-CTA timeline (profiling aid, dfb_dbg_set key 7 = CTA index to trace, -1 = off): single lanes of the
 // traced CTA drop clock64() stamps into a 64-slot region per kernel (chains 0-2, head 3), read by dfb_dbg_timeline.
 __device__ long long g_tl_dev[4 * 64];
+// dfb_dbg_set key 9 = 1: every CTA of the head kernel also records (SM id, globaltimer at entry, at exit)
+__device__ long long g_cta_trace[3 * 16384];
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 #define DFB_TL(slot) do { if (g.tl && (int)blockIdx.x == g.tl_cta) g.tl[slot] = clock64(); } while (0)
 
 struct HeadArgs {
@@ -595,10 +639,16 @@ struct HeadArgs {
     const float* b3;     // fp32 [128]
     const float* w4;     // fp32 [128]
     float b4;
+    // the same three vectors as kernel-parameter constants for the fused layer-3 path (no load instruction, no
+    // cold-L1 miss in every CTA)
+    float b2c[256];
+    float b3c[128];
+    float w4c[128];
     int weight_mode;
     float* out_w;        // fp32 [rows]
     long long* tl;       // timeline region or NULL
     int tl_cta;
+    long long* cta_trace;  // NULL or [3 * gridDim.x]
     int dbg;             // profiling experiments only (dfb_dbg_set key 6; results are garbage): bit 0 = epilogues skip
                          // their math and stores, bit 1 = no layer-2 MMAs, bit 2 = no layer-2 weight loads,
                          // bit 3 = no layer-1 MMAs
@@ -613,7 +663,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <bool CL2>
 __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs g) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t s_pf, s_w1f[2], s_w1e[2], s_w2f[3], s_w2e[3], s_d1f[4], s_d1e[4], s_h1f[2], s_h1e[2], s_d2f, s_w3f[2], s_w3e[2], s_h2f, s_d3f;
+    __shared__ __align__(8) uint64_t s_pf, s_w1f[2], s_w1e[2], s_w2f[3], s_w2e[3], s_d1f[4], s_d1e[4], s_h1f[2], s_h1e[2], s_d2f, s_w3f[4], s_w3e[4], s_h2f[4], s_d3f;
     __shared__ uint32_t s_tmem;
     __shared__ float s_hg[512];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -626,16 +676,25 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
     const uint32_t W1R = smem_base + 32 * 1024;    // 2 x 16 KB : [hi 8 KB | lo 8 KB]
     const uint32_t H1R = smem_base + 64 * 1024;    // 2 x 32 KB : [hi 16 KB | lo 16 KB]
     const uint32_t W2R = smem_base + 128 * 1024;   // 3 x 32 KB : [hi 16 KB | lo 16 KB]
-    // layer 3 re-uses the map once layer 2 has drained: h2 (A operand, K=256: 4 hi blocks | 4 lo blocks =
-    // 128 KB) over H1R + the first 64 KB of W2R, the W3 ring (2 x [hi 16 KB | lo 16 KB]) over PF + W1R
-    const uint32_t H2 = H1R;
+    // layer 3: h2 never touches shared memory -- the epilogue writes it back into tensor memory as the bf16 hi / lo
+    // A operand (over the drained D1 buffers) and the MMAs read A from there, so they only stream W3 from shared
+    // memory (an N=128 MMA with both operands in shared memory is bandwidth-bound).  All four W3 k-blocks
+    // ([hi 16 KB | lo 16 KB] each) get their own slot in regions the earlier layers have finished with.
+    auto w3_slot = [&](int s) { return s == 0 ? PF : (s == 1 ? W1R : (s == 2 ? W2R + 2u * 32768u : H1R)); };
     constexpr uint32_t kTmemCols = 512;            // D2: [0,256)  four D1 buffers of 64 columns: [256,512)
+                                                   // tail: h2 hi [256,384) | h2 lo [384,512), D3 over D2's [0,128)
     uint32_t cta_rank = 0;
     if (CL2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
     constexpr uint32_t kConsumers = CL2 ? 2u : 1u;
 
     if (threadIdx.x == 0) {
         DFB_TL(0);
+        if (g.cta_trace && blockIdx.x < 16384) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            g.cta_trace[3 * blockIdx.x] = smid;
+            g.cta_trace[3 * blockIdx.x + 1] = global_ns();
+        }
         mbar_init(smem_u32(&s_pf), 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&s_w1f[i]), 1); mbar_init(smem_u32(&s_w1e[i]), kConsumers);
@@ -644,8 +703,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
         for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&s_d1f[i]), 1); mbar_init(smem_u32(&s_d1e[i]), kHeadGroupWarps); }
         for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&s_w2f[i]), 1); mbar_init(smem_u32(&s_w2e[i]), kConsumers); }
         mbar_init(smem_u32(&s_d2f), 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_w3f[i]), 1); mbar_init(smem_u32(&s_w3e[i]), kConsumers); }
-        mbar_init(smem_u32(&s_h2f), kHeadEpiWarps);
+        for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&s_w3f[i]), 1); mbar_init(smem_u32(&s_w3e[i]), kConsumers); }
+        for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s_h2f[i]), kHeadEpiWarps);
         mbar_init(smem_u32(&s_d3f), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -668,7 +727,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
     if (threadIdx.x == 0) DFB_TL(1);
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             bool ok = true;
             {
                 const uint32_t bar = smem_u32(&s_pf);
@@ -725,14 +784,15 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             }
             if (g.fuse_l3) {
                 for (int i = 0; i < 4 && ok; ++i) {
-                    const int s = i & 1;
-                    // phase 0 of w3e = "PF/W1R no longer read by any layer-1 MMA" (both CTAs in a cluster)
-                    if (!mbar_wait(smem_u32(&s_w3e[s]), (uint32_t)(i >> 1) & 1u, g.err, 1)) { ok = false; break; }
+                    const int s = i;
+                    // w3e = "the slot's previous tenant is no longer read": PF / W1R by the layer-1 MMAs, the last W2
+                    // stage and the first h1 buffer by the layer-2 MMAs (both CTAs in a cluster)
+                    if (!mbar_wait(smem_u32(&s_w3e[s]), 0u, g.err, 1)) { ok = false; break; }
                     if (i == 0) DFB_TL(59);
                     const uint32_t bar = smem_u32(&s_w3f[s]);
                     mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
                     for (int pl = 0; pl < planes; ++pl)
-                        shared_load(smem_base + (uint32_t)s * 32768u + (uint32_t)pl * kBlkBytes,
+                        shared_load(w3_slot(s) + (uint32_t)pl * kBlkBytes,
                                     g.w3 + (size_t)pl * g.w3_plane + (size_t)i * kBlkElems, kBlkBytes, bar);
                 }
             }
@@ -740,7 +800,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
     } else if (warp == 2) {
         // ===================== layer-1 MMA issuer (its own thread: tcgen05.commit tracks per-thread groups, so
         // layer 1 runs ahead, throttled only by the four D1 buffers, and never delays the layer-2 issue loop)
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc64 = umma_idesc(64);
             auto release_weights = [&](uint32_t bar) {   // "these MMAs have read the stage" -> every CTA sharing it
                 if (CL2)
@@ -783,7 +843,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
         }
     } else if (warp == 1) {
         // ===================== layer-2 / layer-3 MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc256 = umma_idesc(256);
             auto release_weights = [&](uint32_t bar) {   // "these MMAs have read the stage" -> every CTA sharing it
                 if (CL2)
@@ -826,28 +886,36 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             };
             for (int c = 0; c < 8 && ok; ++c) mma2(c);
             if (ok) umma_commit(smem_u32(&s_d2f));
+            if (ok && g.fuse_l3) {   // the last W2 stage and the h1 buffers become W3 slots
+                release_weights(smem_u32(&s_w3e[2]));
+                release_weights(smem_u32(&s_w3e[3]));
+            }
             if (ok && g.fuse_l3) {
                 const uint32_t idesc128 = umma_idesc(128);
-                ok = mbar_wait(smem_u32(&s_h2f), 0u, g.err, 5);
-                DFB_TL(54);
                 for (int kb = 0; kb < 4 && ok; ++kb) {
-                    const int s = kb & 1;
-                    ok = mbar_wait(smem_u32(&s_w3f[s]), (uint32_t)(kb >> 1) & 1u, g.err, 2);
+                    // k-block kb of h2 is written by all 16 epilogue warps in their round kb, so layer 3 starts while
+                    // the rest of the layer-2 accumulator is still being converted; D3 overlays D2's columns [0,128),
+                    // which rounds 0 and 1 have read
+                    ok = mbar_wait(smem_u32(&s_h2f[kb]), 0u, g.err, 5);
+                    if (kb == 0) {
+                        ok = ok && mbar_wait(smem_u32(&s_h2f[1]), 0u, g.err, 5);
+                        DFB_TL(54);
+                    }
+                    ok = ok && mbar_wait(smem_u32(&s_w3f[kb]), 0u, g.err, 2);
                     if (!ok) break;
                     tc_fence_after();
-                    const uint32_t a_hi = H2 + (uint32_t)kb * kBlkBytes, a_lo = a_hi + 4u * kBlkBytes;
-                    const uint32_t b_hi = smem_base + (uint32_t)s * 32768u, b_lo = b_hi + kBlkBytes;
-                    const uint32_t d = tmem_base + 256u;   // D3 over the (drained) D1 buffers
+                    const uint32_t a_hi = tmem_base + 256u + (uint32_t)kb * 32u, a_lo = a_hi + 128u;
+                    const uint32_t b_hi = w3_slot(kb), b_lo = b_hi + kBlkBytes;
+                    const uint32_t d = tmem_base;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint32_t koff = (uint32_t)ks * 2 * kLBO;
-                        umma_bf16(d, umma_desc(a_hi + koff, kLBO, kSBO), umma_desc(b_hi + koff, kLBO, kSBO), idesc128, (kb == 0 && ks == 0) ? 0u : 1u);
+                        umma_bf16_ts(d, a_hi + (uint32_t)ks * 8u, umma_desc(b_hi + koff, kLBO, kSBO), idesc128, (kb == 0 && ks == 0) ? 0u : 1u);
                         if (g.nprod > 1) {
-                            umma_bf16(d, umma_desc(a_hi + koff, kLBO, kSBO), umma_desc(b_lo + koff, kLBO, kSBO), idesc128, 1u);
-                            umma_bf16(d, umma_desc(a_lo + koff, kLBO, kSBO), umma_desc(b_hi + koff, kLBO, kSBO), idesc128, 1u);
+                            umma_bf16_ts(d, a_hi + (uint32_t)ks * 8u, umma_desc(b_lo + koff, kLBO, kSBO), idesc128, 1u);
+                            umma_bf16_ts(d, a_lo + (uint32_t)ks * 8u, umma_desc(b_hi + koff, kLBO, kSBO), idesc128, 1u);
                         }
                     }
-                    release_weights(smem_u32(&s_w3e[s]));
                 }
                 if (ok) umma_commit(smem_u32(&s_d3f));
                 DFB_TL(55);
@@ -917,68 +985,78 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
         if (ok) ok = mbar_wait(smem_u32(&s_d2f), 0u, g.err, 3);
         tc_fence_after();
         if (tl_lane && grp == 0) DFB_TL(52);
-        if (ok) {
+        if (!g.fuse_l3) {
+            if (ok) {   // h2 goes to HBM for a separate layer-3 launch (A/B-test path)
 #pragma unroll 1
-            for (int c0 = quarter * 64; c0 < quarter * 64 + 64; c0 += 32) {
-                tmem_ld32(tmem_base + tlane + (uint32_t)c0, v);
-                if (!g.fuse_l3 && row >= g.m_valid) continue;
+                for (int c0 = quarter * 64; c0 < quarter * 64 + 64; c0 += 32) {
+                    tmem_ld32(tmem_base + tlane + (uint32_t)c0, v);
+                    if (row >= g.m_valid) continue;
 #pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) {
-                    uint32_t ph[4], pl[4];
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        uint32_t ph[4], pl[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int i0 = c8 * 8 + 2 * e;
-                        const float x0 = fmaxf(__uint_as_float(v[i0]) + __ldg(g.b2 + c0 + i0), 0.f);
-                        const float x1 = fmaxf(__uint_as_float(v[i0 + 1]) + __ldg(g.b2 + c0 + i0 + 1), 0.f);
-                        split_pair(x0, x1, ph[e], pl[e]);
-                    }
-                    const int col = c0 + c8 * 8;
-                    if (g.fuse_l3) {   // h2 stays on chip as the A operand of layer 3
-                        const uint32_t o = H2 + (uint32_t)(col >> 6) * kBlkBytes + (uint32_t)((col & 63) >> 3) * 2048u +
-                                           (uint32_t)(lrow >> 3) * 128u + (uint32_t)(lrow & 7) * 16u;
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
-                        if (g.nprod > 1)
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + 4u * kBlkBytes), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
-                    } else {
-                        const size_t o = tiled_offset(row, col, g.out_KB);
+                        for (int e = 0; e < 4; ++e) {
+                            const int i0 = c8 * 8 + 2 * e;
+                            const float x0 = fmaxf(__uint_as_float(v[i0]) + __ldg(g.b2 + c0 + i0), 0.f);
+                            const float x1 = fmaxf(__uint_as_float(v[i0 + 1]) + __ldg(g.b2 + c0 + i0 + 1), 0.f);
+                            split_pair(x0, x1, ph[e], pl[e]);
+                        }
+                        const size_t o = tiled_offset(row, c0 + c8 * 8, g.out_KB);
                         *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                         if (g.nprod > 1) *reinterpret_cast<uint4*>(g.out_t + g.out_plane + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                     }
                 }
             }
-            if (g.fuse_l3) {
-                fence_async_smem();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&s_h2f));
-                if (tl_lane && grp == 0) DFB_TL(53);
-                if (quarter == 0) {   // one warp per lane quadrant finishes the row: ReLU(conv3) . w4 + b4 -> weight
-                    ok = mbar_wait(smem_u32(&s_d3f), 0u, g.err, 3);
-                    tc_fence_after();
-                    if (tl_lane) DFB_TL(56);
-                    if (ok) {
-                        float dot = 0.f;
+        } else {
+            // h2 stays on chip as the A operand of layer 3.  Round r: all 16 warps convert k-block r (64 channels,
+            // 16 per warp) and hand it to the MMA warp, so layer 3 runs one k-block behind the conversion.
 #pragma unroll 1
-                        for (int c0 = 0; c0 < 128; c0 += 32) {
-                            tmem_ld32(tmem_base + tlane + 256u + (uint32_t)c0, v);
+            for (int r = 0; r < 4; ++r) {
+                if (ok) {
+                    uint32_t v16[16], ph[8], pl[8];
+                    const int c0 = r * 64 + quarter * 16;
+                    tmem_ld16(tmem_base + tlane + (uint32_t)c0, v16);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                dot = fmaf(fmaxf(__uint_as_float(v[i]) + __ldg(g.b3 + c0 + i), 0.f), __ldg(g.w4 + c0 + i), dot);
-                        }
-                        if (row < g.m_valid) {
-                            const float a = dot + g.b4;
-                            g.out_w[row] = (g.weight_mode == DFB_WEIGHT_MODE_SIGMOID) ? 0.01f + 1.f / (1.f + expf(-a))
-                                                                                      : (0.01f + 1.f + tanhf(a)) * 0.5f;
-                        }
+                    for (int e = 0; e < 8; ++e) {
+                        const float x0 = fmaxf(__uint_as_float(v16[2 * e]) + g.b2c[c0 + 2 * e], 0.f);
+                        const float x1 = fmaxf(__uint_as_float(v16[2 * e + 1]) + g.b2c[c0 + 2 * e + 1], 0.f);
+                        split_pair(x0, x1, ph[e], pl[e]);
                     }
-                    if (tl_lane) DFB_TL(57);
+                    tmem_st8(tmem_base + tlane + 256u + (uint32_t)(c0 >> 1), ph);
+                    if (g.nprod > 1) tmem_st8(tmem_base + tlane + 384u + (uint32_t)(c0 >> 1), pl);
+                    tmem_st_wait();
+                    tc_fence_before();
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&s_h2f[r]));
             }
+            if (tl_lane && grp == 0) DFB_TL(53);
+            // ReLU(conv3) . w4: every warp takes 32 of the 128 layer-3 channels of its rows, the partial sums meet
+            // in shared memory (s_hg is dead by now) and the column-quarter-0 warps finish the weight map
+            if (ok) ok = mbar_wait(smem_u32(&s_d3f), 0u, g.err, 3);
+            tc_fence_after();
+            if (tl_lane && grp == 0) DFB_TL(56);
+            float dot = 0.f;
+            if (ok) {
+                const int c0 = quarter * 32;
+                tmem_ld32(tmem_base + tlane + (uint32_t)c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) dot = fmaf(fmaxf(__uint_as_float(v[i]) + g.b3c[c0 + i], 0.f), g.w4c[c0 + i], dot);
+            }
+            s_hg[quarter * 128 + lrow] = dot;
+            asm volatile("bar.sync 1, %0;" ::"n"(kHeadEpiWarps * 32) : "memory");   // the 16 epilogue warps only
+            if (quarter == 0 && ok && row < g.m_valid) {
+                const float a = ((s_hg[lrow] + s_hg[128 + lrow]) + (s_hg[256 + lrow] + s_hg[384 + lrow])) + g.b4;
+                g.out_w[row] = (g.weight_mode == DFB_WEIGHT_MODE_SIGMOID) ? 0.01f + 1.f / (1.f + expf(-a))
+                                                                          : (0.01f + 1.f + tanhf(a)) * 0.5f;
+            }
+            if (tl_lane && grp == 0) DFB_TL(57);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) DFB_TL(58);
+    if (threadIdx.x == 0 && g.cta_trace && blockIdx.x < 16384) g.cta_trace[3 * blockIdx.x + 2] = global_ns();
     if (CL2) {   // neither CTA may retire while the other can still multicast into it
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -1123,7 +1201,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             bool ok = true;
             for (int l = 0; l < L; ++l) {
                 const uint32_t bar = smem_u32(&s_wf[l]);
@@ -1148,7 +1226,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             bool ok = true;
             // the row tiles are independent through all small layers, so they are software-pipelined: while the
             // epilogue group of tile t turns layer l's accumulator into the next operand, the MMAs of the other
@@ -1538,7 +1616,7 @@ struct dfb_model {
     dfb::PackedLayer head_global;  // HEAD_CONV1 columns 0..1023  (bias = folded conv1 bias)
     dfb::PackedLayer head_point;   // HEAD_CONV1 columns 1024..1087 (no bias of its own)
     float* w_small[DFB_NUM_LAYERS] = {nullptr};  // raw fp32 weights of the CUDA-core layers
-    std::vector<float> h_w_small[DFB_NUM_LAYERS];  // host copies of the two K=3 layers
+    std::vector<float> h_w_small[DFB_NUM_LAYERS];  // host copies of the two K=3 layers and of conv4
     dfb::bf16* head_w1c = nullptr;               // HEAD_CONV1 point part in 64-row chunks for the fused head
     dfb::PackedLayer head_w2_256;                // HEAD_CONV2 in 256-row blocks (N=256 MMAs of the fused head)
     // workspace
@@ -1619,6 +1697,7 @@ long long* timeline_region(int region) {
     if (cudaGetSymbolAddress(&p, g_tl_dev) != cudaSuccess) return nullptr;
     return static_cast<long long*>(p) + region * 64;
 }
+int g_cta_trace_on = 0;   // dfb_dbg_set key 9
 int g_head_dbg = 0;  // profiling experiments (dfb_dbg_set key 6), see HeadArgs::dbg
 int g_head_l3 = 1;  // debug switch (dfb_dbg_set key 4): 0 = layer 3 + weight epilogue as a separate launch
 
@@ -1638,10 +1717,17 @@ int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, co
     a.w3 = m->L[DFB_L_HEAD_CONV3].w.p; a.w3_plane = m->L[DFB_L_HEAD_CONV3].w.plane;
     a.b3 = m->L[DFB_L_HEAD_CONV3].bias;
     a.w4 = m->w_small[DFB_L_HEAD_CONV4];
+    memcpy(a.b2c, m->L[DFB_L_HEAD_CONV2].h_bias.data(), sizeof(a.b2c));
+    memcpy(a.b3c, m->L[DFB_L_HEAD_CONV3].h_bias.data(), sizeof(a.b3c));
+    memcpy(a.w4c, m->h_w_small[DFB_L_HEAD_CONV4].data(), sizeof(a.w4c));
     a.b4 = m->b4;
     a.weight_mode = m->weight_mode;
     a.out_w = out_w;
     a.dbg = g_head_dbg;
+    if (g_cta_trace_on) {
+        void* tp = nullptr;
+        if (cudaGetSymbolAddress(&tp, g_cta_trace) == cudaSuccess) a.cta_trace = static_cast<long long*>(tp);
+    }
     a.tl = timeline_region(3); a.tl_cta = g_tl_cta;
     a.err = m->err;
     const size_t smem = 224 * 1024;
@@ -1933,6 +2019,16 @@ extern "C" DFB_API int dfb_dbg_set(int key, int value) {
     if (key == 5) dfb::g_chain = value;
     if (key == 6) dfb::g_head_dbg = value;
     if (key == 7) dfb::g_tl_cta = value;
+    if (key == 9) dfb::g_cta_trace_on = value;
+    return DFB_OK;
+}
+
+// Profiling aid: (SM id, entry ns, exit ns) of the first n CTAs of the last traced head launch.
+extern "C" DFB_API int dfb_dbg_cta_trace(long long* host_out, int n_cta) {
+    using namespace dfb;
+    DFB_REQUIRE(host_out && n_cta > 0 && n_cta <= 16384, DFB_E_ARG, "dfb_dbg_cta_trace: bad arguments");
+    DFB_CUDA(cudaDeviceSynchronize());
+    DFB_CUDA(cudaMemcpyFromSymbol(host_out, g_cta_trace, sizeof(long long) * 3 * n_cta));
     return DFB_OK;
 }
 
@@ -1997,6 +2093,7 @@ extern "C" int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, d
         m->L[i].out = l.out_features;
         m->L[i].h_bias.assign(l.h_bias, l.h_bias + l.out_features);
         if (i == DFB_L_QSTN_CONV1 || i == DFB_L_PF_CONV1) m->h_w_small[i].assign(l.h_weight, l.h_weight + 3 * 64);
+        if (i == DFB_L_HEAD_CONV4) m->h_w_small[i].assign(l.h_weight, l.h_weight + 128);
         const bool small = (i == DFB_L_QSTN_CONV1 || i == DFB_L_PF_CONV1 || i == DFB_L_QSTN_FC3 || i == DFB_L_HEAD_CONV4);
         if (i == DFB_L_HEAD_CONV4) m->b4 = l.h_bias[0];
         if (small) {

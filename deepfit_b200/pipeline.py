@@ -52,7 +52,7 @@ class NormalEstimator:
         self.model = model
         self.cancel_qstn = cancel_qstn
         self.grid = ops.Grid(self.points)
-        self.chunk = int(chunk) if chunk else (4096 if mode == "DeepFit" else 65536)
+        self.chunk = int(chunk) if chunk else (16384 if mode == "DeepFit" else 65536)
         self.net = model._network(points.device, max_batch=self.chunk) if mode == "DeepFit" else None
 
     def rebuild_grid(self):

@@ -51,14 +51,33 @@ def main():
     for _ in range(3):
         net.forward(patch)
     torch.cuda.synchronize()
+    if os.environ.get("DFB_HEAD_DBG"):
+        lib.dfb_dbg_set(6, int(os.environ["DFB_HEAD_DBG"]))   # head experiment bits (results are garbage, timing only)
     lib.dfb_dbg_set(7, args.cta)
+    lib.dfb_dbg_set(9, 1)
     net.forward(patch)
     torch.cuda.synchronize()
     buf = (C.c_longlong * 256)()
     lib.dfb_dbg_timeline.argtypes = [C.POINTER(C.c_longlong), C.c_int]
     rc = lib.dfb_dbg_timeline(buf, 256)
     lib.dfb_dbg_set(7, -1)
+    lib.dfb_dbg_set(9, 0)
     assert rc == 0
+    n_cta = min(16384, args.batch * 2)
+    tr = (C.c_longlong * (3 * n_cta))()
+    lib.dfb_dbg_cta_trace.argtypes = [C.POINTER(C.c_longlong), C.c_int]
+    assert lib.dfb_dbg_cta_trace(tr, n_cta) == 0
+    tr = np.array(tr[:], dtype=np.int64).reshape(n_cta, 3)
+    dur, gap = [], []
+    for sm in np.unique(tr[:, 0]):
+        rows = tr[tr[:, 0] == sm]
+        rows = rows[np.argsort(rows[:, 1])]
+        dur.extend((rows[:, 2] - rows[:, 1]).tolist())
+        gap.extend((rows[1:, 1] - rows[:-1, 2]).tolist())
+    print("== head kernel, all %d CTAs: resident %.2f us median (p10 %.2f, p90 %.2f); gap between consecutive CTAs on one SM "
+          "%.2f us median (p10 %.2f, p90 %.2f); kernel span %.1f us"
+          % (n_cta, np.median(dur) / 1e3, np.percentile(dur, 10) / 1e3, np.percentile(dur, 90) / 1e3, np.median(gap) / 1e3,
+             np.percentile(gap, 10) / 1e3, np.percentile(gap, 90) / 1e3, (tr[:, 2].max() - tr[:, 1].min()) / 1e3))
     tl = np.array(buf[:], dtype=np.int64).reshape(4, 64)
     for region, name, names in ((0, "QSTN chain", CHAIN), (1, "STN chain", CHAIN), (2, "encoder chain", CHAIN), (3, "head", HEAD)):
         t0 = tl[region, 0]
