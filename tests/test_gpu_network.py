@@ -149,16 +149,15 @@ def dbg_switch():
         lib.dfb_dbg_set(key, default)
 
 
-@pytest.mark.parametrize("variant", ["fused_cluster2", "fused", "fused_l12_only", "unfused"])
+@pytest.mark.parametrize("variant", ["fused", "fused_l12_only", "unfused"])
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
 def test_network_stage_by_stage_vs_torch(golden, precision, variant, dbg_switch):
     from deepfit_b200 import DeepFit as D
     from deepfit_b200 import ops
     from oracle import deepfit_oracle as O
     fused = 0 if variant == "unfused" else 1
-    l3 = 1 if variant in ("fused_cluster2", "fused") else 0
+    l3 = 1 if variant == "fused" else 0
     dbg_switch(2, fused, 1)                                    # fused head (64->512->256) vs two launches
-    dbg_switch(3, 0 if variant == "fused" else 1, 0)           # cluster of 2 with TMA multicast of the weights
     dbg_switch(4, l3, 1)                                       # 256->128->1 + weight map fused behind it
     chain = 0 if variant == "unfused" else 1
     dbg_switch(5, chain, 1)                                    # points -> ... -> 1024+max chains in one kernel each
