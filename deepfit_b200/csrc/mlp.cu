@@ -30,6 +30,7 @@
 
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 namespace dfb {
@@ -77,10 +78,13 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* er
             : "r"(bar), "r"(parity)
             : "memory");
         if (ok) return true;
-        if (clock64() - t0 > (1LL << 31)) {
+        const long long waited = clock64() - t0;
+        if (waited > (1LL << 31)) {
             atomicCAS(err, 0, code);
             return false;
         }
+        // someone else already timed out: give up at once (persistent CTAs would otherwise stack up time-outs)
+        if (waited > (1LL << 20) && *reinterpret_cast<volatile int*>(err) != 0) return false;
     }
 }
 // One lane of a converged warp (elect.sync): unlike `lane == 0`, the compiler knows the guarded code is single-threaded
@@ -625,6 +629,7 @@ struct HeadArgs {
     int out_KB;
     // layer 3 (256->128 + ReLU) + layer 4 (128->1) + weight map, fused behind layer 2
     int fuse_l3;
+    int n_tiles;         // 128-row tiles; the grid is min(n_tiles, #SMs) persistent CTAs
     const bf16* w3;      // tiled [128, 256] hi; lo at +w3_plane
     size_t w3_plane;
     const float* b3;     // fp32 [128]
@@ -693,8 +698,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
     __shared__ float s_hg[512];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int planes = g.nprod > 1 ? 2 : 1;
-    const long long tile = blockIdx.x;
-    const long long patch = (tile * 128) / g.rows_per_patch;
+    const int n_tiles = g.n_tiles;   // persistent CTAs: tile = blockIdx.x, blockIdx.x + gridDim.x, ...
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t W3A = smem_base;
     const uint32_t W1R = smem_base + 32 * 1024;
@@ -708,11 +712,11 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
     // DRAM latency overlaps the TMEM allocation: warp (q, sub) takes rows 32q..32q+31, plane sub & 1, K half sub >> 1
     uint32_t pfr[16];
     float hg_reg = 0.f;
-    if (warp >= 3) {
-        const int ew = warp - 3, sub = ew >> 2;
+    auto fetch_tile = [&](long long tile) {   // epilogue warps only
+        const int sub = (warp - 3) >> 2;
         const int lrow = (warp & 3) * 32 + lane;
         const int plane = sub & 1, khalf = sub >> 1;
-        hg_reg = g.hg[patch * 512 + (threadIdx.x - 96)];
+        hg_reg = g.hg[((tile * 128) / g.rows_per_patch) * 512 + (threadIdx.x - 96)];
         if (plane < planes) {
             const bf16* src = g.pf + (size_t)plane * g.pf_plane + (size_t)tile * kBlkElems + (size_t)(lrow >> 3) * 64 + (size_t)(lrow & 7) * 8;
 #pragma unroll
@@ -721,15 +725,9 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 pfr[4 * j] = t.x; pfr[4 * j + 1] = t.y; pfr[4 * j + 2] = t.z; pfr[4 * j + 3] = t.w;
             }
         }
-    }
+    };
+    if (warp >= 3 && (int)blockIdx.x < n_tiles) fetch_tile(blockIdx.x);
     if (threadIdx.x == 0) {
-        DFB_TL(0);
-        if (g.cta_trace && blockIdx.x < 16384) {
-            uint32_t smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            g.cta_trace[3 * blockIdx.x] = smid;
-            g.cta_trace[3 * blockIdx.x + 1] = global_ns();
-        }
         mbar_init(smem_u32(&s_pf), kHeadEpiWarps);
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_w1f[i]), 1); mbar_init(smem_u32(&s_w1e[i]), 1); }
         for (int i = 0; i < 3; ++i) {
@@ -750,7 +748,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
-    if (threadIdx.x == 0) DFB_TL(1);
+#define HTL(slot) do { if (g.tl && tile == g.tl_cta) g.tl[slot] = clock64(); } while (0)
 
     if (warp == 0) {
         // ===================== TMA producer: weights only =====================
@@ -769,7 +767,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 mbar_expect_tx(bar, (uint32_t)planes * 8192u);
                 bulk_g2s(W1R + (uint32_t)s * 16384u, g.w1c + (size_t)c * 8192, (uint32_t)planes * 8192u, bar);  // hi|lo contiguous
             };
-            int w2i = 0;
+            int w2i = 0;   // runs across tiles: the W2 ring never stops
             // W2 is packed in 256-row blocks (all 256 output channels of one 64-wide k-block = 32 KB per
             // plane); a stage is half a block: k-chunks 4h..4h+3 = 16 KB per plane, contiguous
             auto load_w2 = [&](int c, int h) {
@@ -787,26 +785,33 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                              g.w2 + (size_t)pl * g.w2_plane + (size_t)c * (2 * kBlkElems) + (size_t)h * kBlkElems, kBlkBytes, bar);
                 ++w2i;
             };
-            load_w1(0);
-            if (ok) load_w1(1);
-            if (ok) load_w2(0, 0);
-            if (ok) load_w2(0, 1);
-            if (ok) load_w1(2);
-            for (int c = 1; c < 8 && ok; ++c) {   // same order as the MMA warps consume
-                load_w2(c, 0);
-                if (ok) load_w2(c, 1);
-                if (ok && c + 2 < 8) load_w1(c + 2);
-                if (ok && c == 1 && g.fuse_l3) {   // three W3 k-blocks have a home from the start; fetched once the
-                    load_w3(0);                   // loop's own weights are on their way
-                    load_w3(1);
-                    load_w3(2);
+            for (int it = 0, tile = blockIdx.x; tile < n_tiles && ok; ++it, tile += gridDim.x) {
+                const uint32_t ip = (uint32_t)it & 1u;
+                // the W2 ring is nobody else's: its first stages are fetched while the previous tile is still in its tail
+                load_w2(0, 0);
+                if (ok) load_w2(0, 1);
+                // W1R, W3A and W3B still hold the previous tile's W3 until its layer 3 has completed
+                if (ok && it > 0 && g.fuse_l3) ok = mbar_wait(smem_u32(&s_d3f), ip ^ 1u, g.err, 1);
+                if (ok) load_w1(0);
+                if (ok) load_w1(1);
+                if (ok) load_w1(2);
+                for (int c = 1; c < 8 && ok; ++c) {   // same order as the MMA warps consume
+                    load_w2(c, 0);
+                    if (ok) load_w2(c, 1);
+                    if (ok && c + 2 < 8) load_w1(c + 2);
+                    if (ok && c == 1 && g.fuse_l3) {   // three W3 k-blocks have a home of their own; fetched once the
+                        load_w3(0);                   // loop's weights are on their way
+                        load_w3(1);
+                        load_w3(2);
+                    }
                 }
-            }
-            if (g.fuse_l3 && ok) {
-                // the W1 ring becomes the last W3 slot once every layer-1 MMA has completed
-                if (mbar_wait(smem_u32(&s_w3e), 0u, g.err, 1)) {
-                    DFB_TL(59);
-                    load_w3(3);
+                if (g.fuse_l3 && ok) {
+                    // the W1 ring becomes the last W3 slot once every layer-1 MMA of the tile has completed
+                    ok = mbar_wait(smem_u32(&s_w3e), ip, g.err, 1);
+                    if (ok) {
+                        HTL(59);
+                        load_w3(3);
+                    }
                 }
             }
         }
@@ -815,17 +820,20 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
         // layer 1 runs ahead, throttled only by the three D1/h1 buffers, and never delays the layer-2 issue loop)
         if (elect_one()) {
             const uint32_t idesc64 = umma_idesc(64);
-            bool ok = mbar_wait(smem_u32(&s_pf), 0u, g.err, 2);
+            bool ok = true;
+            for (int it = 0, tile = blockIdx.x; tile < n_tiles && ok; ++it, tile += gridDim.x) {
+            // pf written => every epilogue warp has left the previous tile => its layer 3 no longer reads h2 / D1
+            ok = mbar_wait(smem_u32(&s_pf), (uint32_t)it & 1u, g.err, 2);
             tc_fence_after();
-            DFB_TL(2);
-            for (int c = 0; c < 8 && ok; ++c) {   // D1[c % 3] = pf * W1chunk(c)^T
-                const int s = c & 1, b = c % 3;
-                const uint32_t u = (uint32_t)(c / 3);
+            HTL(2);
+            for (int c = 0; c < 8 && ok; ++c) {   // D1[cc % 3] = pf * W1chunk(c)^T, cc = chunk count across tiles
+                const int s = c & 1, b = (it * 8 + c) % 3;
+                const uint32_t u = (uint32_t)((it * 8 + c) / 3);
                 ok = mbar_wait(smem_u32(&s_w1f[s]), (uint32_t)(c >> 1) & 1u, g.err, 2);
                 if (ok && u > 0) ok = mbar_wait(smem_u32(&s_h1e[b]), (u - 1u) & 1u, g.err, 4);   // layer 2 has read the buffer
                 if (!ok) break;
                 tc_fence_after();
-                DFB_TL(4 + c * 6);
+                HTL(4 + c * 6);
                 const uint32_t d = tmem_base + kBuf0 + (uint32_t)b * 64u;
                 const uint32_t w_hi = W1R + (uint32_t)s * 16384u, w_lo = w_hi + 8192u;
 #pragma unroll
@@ -843,6 +851,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 umma_commit(smem_u32(&s_d1f[b]));
             }
             if (ok && g.fuse_l3) umma_commit(smem_u32(&s_w3e));   // the W1 ring is free for the last W3 k-block
+            }
         }
     } else if (warp == 1) {
         // ===================== layer-2 / layer-3 MMA issuer =====================
@@ -850,11 +859,13 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             const uint32_t idesc256 = umma_idesc(256);
             bool ok = true;
             int w2i = 0;
+            for (int it = 0, tile = blockIdx.x; tile < n_tiles && ok; ++it, tile += gridDim.x) {
+            const uint32_t ip = (uint32_t)it & 1u;
             for (int c = 0; c < 8 && ok; ++c) {   // D2 += h1chunk(c) * W2[:, 64c..64c+64]^T, A = the converted D1 buffer
-                const int b = c % 3;
-                ok = mbar_wait(smem_u32(&s_h1f[b]), (uint32_t)(c / 3) & 1u, g.err, 5);
+                const int b = (it * 8 + c) % 3;
+                ok = mbar_wait(smem_u32(&s_h1f[b]), (uint32_t)((it * 8 + c) / 3) & 1u, g.err, 5);
                 if (!ok) break;
-                DFB_TL(4 + c * 6 + 4);
+                HTL(4 + c * 6 + 4);
                 const uint32_t buf = tmem_base + kBuf0 + (uint32_t)b * 64u;
                 for (int h = 0; h < 2 && ok; ++h) {
                     const int s = w2i % 3;
@@ -879,7 +890,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                     ++w2i;
                 }
                 if (ok) umma_commit(smem_u32(&s_h1e[b]));
-                DFB_TL(4 + c * 6 + 5);
+                HTL(4 + c * 6 + 5);
             }
             if (ok) umma_commit(smem_u32(&s_d2f));
             if (ok && g.fuse_l3) {
@@ -888,9 +899,9 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                     // k-blocks 2r, 2r+1 of h2 are written by all 16 epilogue warps in their round r, so layer 3 starts
                     // while the second half of the layer-2 accumulator is still being converted; D3 overlays D2's
                     // columns [0,128), which round 0 has read
-                    ok = mbar_wait(smem_u32(&s_h2f[kb >> 1]), 0u, g.err, 5);
-                    if (kb == 0) DFB_TL(54);
-                    ok = ok && mbar_wait(smem_u32(&s_w3f[kb]), 0u, g.err, 2);
+                    ok = mbar_wait(smem_u32(&s_h2f[kb >> 1]), ip, g.err, 5);
+                    if (kb == 0) HTL(54);
+                    ok = ok && mbar_wait(smem_u32(&s_w3f[kb]), ip, g.err, 2);
                     if (!ok) break;
                     tc_fence_after();
                     const uint32_t a_hi = tmem_base + 256u + (uint32_t)kb * 32u, a_lo = a_hi + 128u;
@@ -907,7 +918,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                     }
                 }
                 if (ok) umma_commit(smem_u32(&s_d3f));
-                DFB_TL(55);
+                HTL(55);
+            }
             }
         }
     } else {
@@ -919,13 +931,25 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
         const int half = (ew >> 2) & 1;
         const int quarter = ew >> 2;           // column quarter for the final 256-column pass
         const int lrow = q * 32 + lane;
-        const long long row = tile * 128 + lrow;
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
         uint32_t v[32];
-        bool ok = true;
+        bool ok = true;   // after a time-out the warp keeps walking its tiles (the named barriers need all 16 warps) but
+                          // skips every wait and all the work
         const bool tl_lane = lane == 0 && (ew & 7) == 0;   // one stamping lane per epilogue group
-        {   // the tile's point features become the TMEM A operand of layer 1 (the set-up barrier above did not wait
-            // for these loads: the weight pipeline is already running)
+        for (int it = 0, tile = blockIdx.x; tile < n_tiles; ++it, tile += gridDim.x) {
+        const uint32_t ip = (uint32_t)it & 1u;
+        const long long row = (long long)tile * 128 + lrow;
+        if (tl_lane && grp == 0) {
+            HTL(0);
+            if (g.cta_trace && tile < 16384) {
+                uint32_t smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                g.cta_trace[3 * tile] = smid;
+                g.cta_trace[3 * tile + 1] = global_ns();
+            }
+        }
+        {   // the tile's point features (fetched during the previous tile) become the TMEM A operand of layer 1; every
+            // warp is past the previous tile's layer 3 here, so pf / h2 / D1 columns are free
             s_hg[threadIdx.x - 96] = hg_reg;
             asm volatile("bar.sync 1, %0;" ::"n"(kHeadEpiWarps * 32) : "memory");   // the 16 epilogue warps only
             const int plane = quarter & 1, khalf = quarter >> 1;
@@ -936,13 +960,14 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_pf));
+            if (tile + (int)gridDim.x < n_tiles) fetch_tile(tile + gridDim.x);   // in flight for the whole tile
         }
         for (int c = grp; c < 8 && ok; c += 2) {
-            const int b = c % 3;
-            ok = mbar_wait(smem_u32(&s_d1f[b]), (uint32_t)(c / 3) & 1u, g.err, 3);
+            const int b = (it * 8 + c) % 3;
+            ok = mbar_wait(smem_u32(&s_d1f[b]), (uint32_t)((it * 8 + c) / 3) & 1u, g.err, 3);
             if (!ok) break;
             tc_fence_after();
-            if (tl_lane) DFB_TL(4 + c * 6 + 1);
+            if (tl_lane) HTL(4 + c * 6 + 1);
             // bias + ReLU + split, in place: this warp's 32 accumulator columns become [hi 16 | lo 16] packed columns
             const uint32_t cols = tmem_base + tlane + kBuf0 + (uint32_t)b * 64u + (uint32_t)half * 32u;
             tmem_ld32(cols, v);
@@ -959,11 +984,11 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_h1f[b]));
-            if (tl_lane) DFB_TL(4 + c * 6 + 3);
+            if (tl_lane) HTL(4 + c * 6 + 3);
         }
-        if (ok) ok = mbar_wait(smem_u32(&s_d2f), 0u, g.err, 3);
+        if (ok) ok = mbar_wait(smem_u32(&s_d2f), ip, g.err, 3);
         tc_fence_after();
-        if (tl_lane && grp == 0) DFB_TL(52);
+        if (tl_lane && grp == 0) HTL(52);
         if (!g.fuse_l3) {
             if (ok) {   // h2 goes to HBM for a separate layer-3 launch (A/B-test path)
 #pragma unroll 1
@@ -1007,12 +1032,12 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&s_h2f[r]));
             }
-            if (tl_lane && grp == 0) DFB_TL(53);
+            if (tl_lane && grp == 0) HTL(53);
             // ReLU(conv3) . w4: every warp takes 32 of the 128 layer-3 channels of its rows, the partial sums meet
             // in shared memory (s_hg is dead by now) and the column-quarter-0 warps finish the weight map
-            if (ok) ok = mbar_wait(smem_u32(&s_d3f), 0u, g.err, 3);
+            if (ok) ok = mbar_wait(smem_u32(&s_d3f), ip, g.err, 3);
             tc_fence_after();
-            if (tl_lane && grp == 0) DFB_TL(56);
+            if (tl_lane && grp == 0) HTL(56);
             float dot = 0.f;
             if (ok) {
                 switch (quarter) {
@@ -1029,13 +1054,16 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 g.out_w[row] = (g.weight_mode == DFB_WEIGHT_MODE_SIGMOID) ? 0.01f + 1.f / (1.f + expf(-a))
                                                                           : (0.01f + 1.f + tanhf(a)) * 0.5f;
             }
-            if (tl_lane && grp == 0) DFB_TL(57);
+            if (tl_lane && grp == 0) HTL(57);
+        }
+        // every warp is done with s_hg (bias vector, partial sums) and with D2 / D3 before any of them starts the next tile
+        asm volatile("bar.sync 1, %0;" ::"n"(kHeadEpiWarps * 32) : "memory");
+        if (tl_lane && grp == 0 && g.cta_trace && tile < 16384) g.cta_trace[3 * tile + 2] = global_ns();
         }
     }
+#undef HTL
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x == 0) DFB_TL(58);
-    if (threadIdx.x == 0 && g.cta_trace && blockIdx.x < 16384) g.cta_trace[3 * blockIdx.x + 2] = global_ns();
     tc_fence_after();
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
@@ -1672,6 +1700,7 @@ long long* timeline_region(int region) {
     return static_cast<long long*>(p) + region * 64;
 }
 int g_cta_trace_on = 0;   // dfb_dbg_set key 9
+int g_head_persistent = 1;  // dfb_dbg_set key 8: 0 = one CTA per tile
 int g_head_dbg = 0;  // profiling experiments (dfb_dbg_set key 6), see HeadArgs::dbg
 int g_head_l3 = 1;  // debug switch (dfb_dbg_set key 4): 0 = layer 3 + weight epilogue as a separate launch
 
@@ -1712,7 +1741,9 @@ int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, co
         if (e != cudaSuccess) return check_cuda(e, "head_fused smem attribute", __FILE__, __LINE__);
         attr_done = true;
     }
-    head_fused_kernel<<<tiles, kHeadThreads, smem, st>>>(a);
+    a.n_tiles = (int)tiles;
+    const unsigned grid = g_head_persistent ? std::min<unsigned>(tiles, (unsigned)sm_count()) : tiles;
+    head_fused_kernel<<<grid, kHeadThreads, smem, st>>>(a);
     note_launch();
     return check_cuda(cudaGetLastError(), "head_fused_kernel launch", __FILE__, __LINE__);
 }
@@ -1972,6 +2003,7 @@ extern "C" DFB_API int dfb_dbg_set(int key, int value) {
     if (key == 5) dfb::g_chain = value;
     if (key == 6) dfb::g_head_dbg = value;
     if (key == 7) dfb::g_tl_cta = value;
+    if (key == 8) dfb::g_head_persistent = value;
     if (key == 9) dfb::g_cta_trace_on = value;
     return DFB_OK;
 }

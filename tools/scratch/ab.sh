@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_network.py -m gpu -x -q -p no:cacheprovider --timeout 300 2>&1 | tail -3
-timeout 300 python tools/timeline.py > gpurun_out/timeline7.log 2>&1; echo "exit $?" >> gpurun_out/timeline7.log
-for v in "" "ab_libs/lib_head_old.so" "" "ab_libs/lib_head_old.so"; do DEEPFIT_B200_LIB=$v timeout 300 python bench.py --no-cpu-baseline --chunk 4096 2>/dev/null | tail -1 | python -c "import sys,json; l=json.loads(sys.stdin.read()); print('lib=$v', round(l['value']), l['kernel_ms'])"; done
-timeout 300 python bench.py --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; l=json.loads(sys.stdin.read()); print('default', round(l['value']), l['kernel_ms'], l['stage_rooflines'])"
+timeout 300 python tools/timeline.py > gpurun_out/timeline8.log 2>&1; echo "exit $?" >> gpurun_out/timeline8.log
+for v in "" "8:0" "" "8:0"; do DFB_DBG=$v timeout 300 python bench.py --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; l=json.loads(sys.stdin.read()); print('dbg=$v', round(l['value']), l['kernel_ms'])"; done

@@ -26,11 +26,11 @@ for l in range(3):
 for ct in range(8):
     CHAIN[24 + ct] = "M ct%d issued" % ct
     CHAIN[32 + ct] = "M ct%d acc ready" % ct
-HEAD = {0: "entry", 1: "setup done", 2: "PF landed", 52: "D2 ready", 53: "h2 written", 54: "mma: h2 ready", 55: "mma: L3 issued",
+HEAD = {0: "tile start", 2: "pf in TMEM", 52: "D2 ready", 53: "h2 written", 54: "mma: h2 ready", 55: "mma: L3 issued",
         56: "D3 ready", 57: "epi end", 58: "exit", 59: "TMA: first W3 issue"}
 for c in range(8):
     b = 4 + c * 6
-    for i, nm in enumerate(["mma1 issue", "D1 ready", "h1 slot free", "h1 written", "mma2 start", "mma2 issued"]):
+    for i, nm in enumerate(["mma1 issue", "D1 ready", "-", "h1 written", "mma2 start", "mma2 issued"]):
         HEAD[b + i] = "c%d %s" % (c, nm)
 
 
@@ -74,7 +74,7 @@ def main():
         rows = rows[np.argsort(rows[:, 1])]
         dur.extend((rows[:, 2] - rows[:, 1]).tolist())
         gap.extend((rows[1:, 1] - rows[:-1, 2]).tolist())
-    print("== head kernel, all %d CTAs: resident %.2f us median (p10 %.2f, p90 %.2f); gap between consecutive CTAs on one SM "
+    print("== head kernel, all %d tiles: resident %.2f us median (p10 %.2f, p90 %.2f); gap between consecutive tiles on one SM "
           "%.2f us median (p10 %.2f, p90 %.2f); kernel span %.1f us"
           % (n_cta, np.median(dur) / 1e3, np.percentile(dur, 10) / 1e3, np.percentile(dur, 90) / 1e3, np.median(gap) / 1e3,
              np.percentile(gap, 10) / 1e3, np.percentile(gap, 90) / 1e3, (tr[:, 2].max() - tr[:, 1].min()) / 1e3))
