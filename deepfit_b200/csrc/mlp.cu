@@ -1111,6 +1111,7 @@ struct ChainArgs {
     const float* bias3;
     int relu3;
     int n_ch;                 // 1024
+    int n_patch;              // patches; the grid is min(n_patch, #SMs) persistent CTAs
     bf16* out_t;              // tiled global-feature rows (patches)
     size_t out_plane;
     int out_KB;
@@ -1150,7 +1151,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int planes = g.nprod > 1 ? 2 : 1;
-    const long long patch = blockIdx.x;
+    const int n_patch = g.n_patch;   // persistent CTAs: patch = blockIdx.x, blockIdx.x + gridDim.x, ...
     constexpr int KB3 = 2;                                   // 128 input channels of the max layer
     constexpr uint32_t kActBytes = 2u * NT * kBlkBytes;      // one 64-channel activation buffer, both planes
     constexpr uint32_t kXBytes = 2u * NT * KB3 * kBlkBytes;  // the 128-channel activations, both planes
@@ -1173,16 +1174,22 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
     };
     const int CT = g.n_ch / 128;
     const int L = g.n_layers;
+    const int TPB = CT / 2;          // channel tiles per TMEM buffer and patch
+    const int total = CT * KB3;      // W3 ring stages per patch
+    // completions per patch of the ring barriers: slot s serves stages s, s+3, ...; s_re also gets the "region R is
+    // free" commit that ends the small layers.  n-th completion of a barrier <-> parity (n & 1)
+    auto stages_in_slot = [&](int s) { return (total - s + 2) / 3; };
+#define CTL(slot) do { if (g.tl && patch == g.tl_cta) g.tl[slot] = clock64(); } while (0)
 
     // the epilogue warps fetch their point before the set-up barrier so the DRAM latency overlaps the TMEM allocation
     float px = 0.f, py = 0.f, pz = 0.f;
-    if (warp >= 2 && (((warp - 2) >> 2) & 1) < NT) {
+    auto fetch_point = [&](long long patch) {   // epilogue warps that own a row in phases P/S
         const int j = (((warp - 2) >> 2) & 1) * 128 + (warp & 3) * 32 + lane;
         const float* base = g.patch + patch * 3LL * g.k;
         px = __ldg(base + j); py = __ldg(base + g.k + j); pz = __ldg(base + 2 * g.k + j);
-    }
+    };
+    if (warp >= 2 && (((warp - 2) >> 2) & 1) < NT && (int)blockIdx.x < n_patch) fetch_point(blockIdx.x);
     if (threadIdx.x == 0) {
-        DFB_TL(0);
         for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&s_wf[i]), 1);
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_act[i]), 8); mbar_init(smem_u32(&s_acc[i]), 1); }
         for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&s_rf[i]), 1); mbar_init(smem_u32(&s_re[i]), 1); }
@@ -1197,7 +1204,6 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
-    if (threadIdx.x == 0) DFB_TL(1);
     // activation buffer read by small layer l (they alternate, and the last layer must read ACT_A because
     // it writes X, which aliases ACT_B)
     auto act_in = [&](int l) { return ((L - 1 - l) & 1) ? ACT_B : ACT_A; };
@@ -1206,6 +1212,10 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         // ===================== TMA producer =====================
         if (elect_one()) {
             bool ok = true;
+            for (int it = 0, patch = blockIdx.x; patch < n_patch && ok; ++it, patch += gridDim.x) {
+            // regions R and X still feed the previous patch's max-pool layer until its last MMA has completed
+            if (it > 0) ok = mbar_wait(smem_u32(&s_tf[(CT - 1) & 1]), (uint32_t)(it * TPB - 1) & 1u, g.err, 1);
+            if (!ok) break;
             for (int l = 0; l < L; ++l) {
                 const uint32_t bar = smem_u32(&s_wf[l]);
                 mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
@@ -1213,18 +1223,18 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                     bulk_g2s(wbuf(l) + (uint32_t)pl * kBlkBytes,
                              g.L[l].w + (size_t)pl * g.L[l].w_plane + (size_t)patch * g.L[l].w_patch_stride, kBlkBytes, bar);
             }
-            const int total = CT * KB3;
             for (int i = 0; i < total && ok; ++i) {
                 const int s = i % 3;
-                // phase 0 of s_re = "the small layers no longer read region R" (committed by the MMA warp)
-                ok = mbar_wait(smem_u32(&s_re[s]), (uint32_t)(i / 3) & 1u, g.err, 1);
+                // first completion of s_re in a patch = "the small layers no longer read region R" (MMA warp)
+                ok = mbar_wait(smem_u32(&s_re[s]), (uint32_t)(it * (stages_in_slot(s) + 1) + i / 3) & 1u, g.err, 1);
                 if (!ok) break;
-                if (i == 0) DFB_TL(43);
+                if (i == 0) CTL(43);
                 const uint32_t bar = smem_u32(&s_rf[s]);
                 mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
                 for (int pl = 0; pl < planes; ++pl)
                     bulk_g2s(RR + (uint32_t)s * (2u * kBlkBytes) + (uint32_t)pl * kBlkBytes,
                              g.w3 + (size_t)pl * g.w3_plane + (size_t)i * kBlkElems, kBlkBytes, bar);
+            }
             }
         }
     } else if (warp == 1) {
@@ -1234,8 +1244,11 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
             // the row tiles are independent through all small layers, so they are software-pipelined: while the
             // epilogue group of tile t turns layer l's accumulator into the next operand, the MMAs of the other
             // tile run (per-tile barriers s_act[t] / s_acc[t])
+            for (int it = 0, patch = blockIdx.x; patch < n_patch && ok; ++it, patch += gridDim.x) {
+            // the small layers accumulate in TMEM buffer 0, which the previous patch's max-pool epilogue may still read
+            if (it > 0) ok = mbar_wait(smem_u32(&s_te[0]), (uint32_t)(it * TPB - 1) & 1u, g.err, 4);
             for (int l = 0; l < L && ok; ++l) {
-                ok = mbar_wait(smem_u32(&s_wf[l]), 0u, g.err, 2);
+                ok = mbar_wait(smem_u32(&s_wf[l]), (uint32_t)it & 1u, g.err, 2);
                 if (!ok) break;
                 const uint32_t idesc = umma_idesc(g.L[l].n_out);
                 const uint32_t ain = act_in(l);
@@ -1245,7 +1258,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                     ok = ok && mbar_wait(smem_u32(&s_act[t]), (uint32_t)l & 1u, g.err, 5);
                     if (!ok) break;
                     tc_fence_after();
-                    DFB_TL(4 + (l * 2 + t) * 3);
+                    CTL(4 + (l * 2 + t) * 3);
                     const uint32_t a_hi = ain + (uint32_t)t * kBlkBytes, a_lo = ain + (uint32_t)(NT + t) * kBlkBytes;
                     const uint32_t d = tmem_base + (uint32_t)t * 128u;
 #pragma unroll
@@ -1264,23 +1277,23 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                 for (int s = 0; s < 3; ++s) umma_commit(smem_u32(&s_re[s]));
                 for (int t = 0; t < NT && ok; ++t)
                     ok = mbar_wait(smem_u32(&s_act[t]), (uint32_t)L & 1u, g.err, 5);   // X written, TMEM drained
-                DFB_TL(22);
+                CTL(22);
             }
             const uint32_t idesc = umma_idesc(NT * 128);
             const uint32_t lbo_b = (uint32_t)NT * kLBO;
             for (int ct = 0; ct < CT && ok; ++ct) {
                 const int buf = ct & 1;
-                const uint32_t use = (uint32_t)(ct >> 1);
+                const uint32_t use = (uint32_t)(it * TPB + (ct >> 1));   // n-th tile into this buffer, across patches
                 if (use > 0) ok = mbar_wait(smem_u32(&s_te[buf]), (use - 1u) & 1u, g.err, 4);
                 if (!ok) break;
                 tc_fence_after();
                 for (int kb = 0; kb < KB3 && ok; ++kb) {
                     const int i = ct * KB3 + kb;
                     const int s = i % 3;
-                    ok = mbar_wait(smem_u32(&s_rf[s]), (uint32_t)(i / 3) & 1u, g.err, 2);
+                    ok = mbar_wait(smem_u32(&s_rf[s]), (uint32_t)(it * stages_in_slot(s) + i / 3) & 1u, g.err, 2);
                     if (!ok) break;
                     tc_fence_after();
-                    if (i == 0) DFB_TL(23);
+                    if (i == 0) CTL(23);
                     const uint32_t a_hi = RR + (uint32_t)s * (2u * kBlkBytes), a_lo = a_hi + kBlkBytes;
                     const uint32_t b_hi = XR + (uint32_t)(0 * KB3 + kb) * (NT * kBlkBytes);
                     const uint32_t b_lo = XR + (uint32_t)(1 * KB3 + kb) * (NT * kBlkBytes);
@@ -1298,7 +1311,8 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                     umma_commit(smem_u32(&s_re[s]));
                 }
                 if (ok) umma_commit(smem_u32(&s_tf[buf]));
-                DFB_TL(24 + (ct & 7));
+                CTL(24 + (ct & 7));
+            }
             }
         }
     } else {
@@ -1319,18 +1333,24 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         const bool tl_lane = lane == 0 && q == 0 && half == 0;   // one stamping lane per epilogue group
         // element offset of (row lrow, 8-channel chunk j) inside a 128-row operand block
         const uint32_t row_off = (uint32_t)(lrow >> 3) * 128u + (uint32_t)(lrow & 7) * 16u;
+        for (int it = 0, patch = blockIdx.x; patch < n_patch && ok; ++it, patch += gridDim.x) {
+        if (tl_lane && grp == 0) CTL(0);
         // ---- phase P ----
+        // region R (the first activation buffer) is the previous patch's weight ring until its last MMA has completed
+        if (it > 0) ok = mbar_wait(smem_u32(&s_tf[(CT - 1) & 1]), (uint32_t)(it * TPB - 1) & 1u, g.err, 3);
+        if (!ok) break;
         if (active) {
             const int j = grp * 128 + lrow;       // point index inside the patch
             float x = px, y = py, z = pz;
+            if (patch + (int)gridDim.x < n_patch) fetch_point(patch + gridDim.x);   // next patch's point, in flight all along
             if (g.R) {
-                const float* r = g.R + patch * 9;
+                const float* r = g.R + (long long)patch * 9;
                 const float xr = fmaf(z, r[6], fmaf(y, r[3], x * r[0]));
                 const float yr = fmaf(z, r[7], fmaf(y, r[4], x * r[1]));
                 const float zr = fmaf(z, r[8], fmaf(y, r[5], x * r[2]));
                 x = xr; y = yr; z = zr;
                 if (g.pts_out && half == 0) {
-                    float* po = g.pts_out + patch * 3LL * k;
+                    float* po = g.pts_out + (long long)patch * 3LL * k;
                     po[j] = x; po[k + j] = y; po[2 * k + j] = z;
                 }
             }
@@ -1340,17 +1360,17 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_act[grp]));
-            if (tl_lane) DFB_TL(2 + grp);
+            if (tl_lane) CTL(2 + grp);
         }
         // ---- phase S ----
         for (int l = 0; l < L && ok && active; ++l) {
-            ok = mbar_wait(smem_u32(&s_acc[grp]), (uint32_t)l & 1u, g.err, 3);
+            ok = mbar_wait(smem_u32(&s_acc[grp]), (uint32_t)(it * L + l) & 1u, g.err, 3);
             if (!ok) break;
             tc_fence_after();
-            if (tl_lane) DFB_TL(4 + (l * 2 + grp) * 3 + 1);
+            if (tl_lane) CTL(4 + (l * 2 + grp) * 3 + 1);
             const ChainLayer& Ly = g.L[l];
             const bool last = (l == L - 1);
-            const long long grow = patch * k + grp * 128 + lrow;   // global row (point) index
+            const long long grow = (long long)patch * k + grp * 128 + lrow;   // global row (point) index
             const int cbeg = half * (Ly.n_out >> 1);
 #pragma unroll 1
             for (int c0 = cbeg; c0 < cbeg + (Ly.n_out >> 1); c0 += 32) {
@@ -1390,16 +1410,16 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_act[grp]));
-            if (tl_lane) DFB_TL(4 + (l * 2 + grp) * 3 + 2);
+            if (tl_lane) CTL(4 + (l * 2 + grp) * 3 + 2);
         }
         // ---- phase M: group g takes the channel tiles of parity g ----
         for (int ct = grp; ct < CT && ok && half == 0; ct += 2) {
             const int buf = ct & 1;                 // == grp
-            const uint32_t use = (uint32_t)(ct >> 1);
+            const uint32_t use = (uint32_t)(it * TPB + (ct >> 1));
             ok = mbar_wait(smem_u32(&s_tf[buf]), use & 1u, g.err, 3);
             if (!ok) break;
             tc_fence_after();
-            if (tl_lane) DFB_TL(32 + (ct & 7));
+            if (tl_lane) CTL(32 + (ct & 7));
             float mx = -3.402823466e38f;
 #pragma unroll 1
             for (int c0 = 0; c0 < NT * 128; c0 += 32) {
@@ -1413,7 +1433,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
             const long long ch = (long long)ct * 128 + lrow;
             float r = mx + (g.bias3 ? g.bias3[ch] : 0.f);
             if (g.relu3) r = fmaxf(r, 0.f);
-            if (g.out_f) g.out_f[patch * (long long)g.n_ch + ch] = r;
+            if (g.out_f) g.out_f[(long long)patch * g.n_ch + ch] = r;
             if (g.out_t) {
                 bf16 hi, lo;
                 split_bf16(r, hi, lo);
@@ -1422,12 +1442,13 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                 g.out_t[g.out_plane + o] = lo;
             }
         }
-        if (tl_lane) DFB_TL(40 + grp);
+        if (tl_lane) CTL(40 + grp);
+        }
     }
+#undef CTL
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (threadIdx.x == 0) DFB_TL(42);
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
@@ -1882,6 +1903,7 @@ int upload_head_w1_chunks(const float* h_w, long long ldw, int col0, bf16** d_ou
 int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, const float* hg, const PackedLayer& W2,
                       TiledBuf& out, float* out_w, cudaStream_t st);
 
+int g_chain_persistent = 1;  // dfb_dbg_set key 10: 0 = one CTA per patch
 int g_chain = 1;  // debug switch (dfb_dbg_set key 5): 0 = separate pointwise / small-GEMM / max-pool launches
 
 struct ChainSpec {
@@ -1926,8 +1948,12 @@ int launch_chain(const dfb_model* m, const float* patch, long long n_patch, cons
         if (e != cudaSuccess) return check_cuda(e, "chain_max smem attribute", __FILE__, __LINE__);
         attr_done[NT] = true;
     }
-    if (NT == 1) chain_max_kernel<1><<<(unsigned)n_patch, kChainThreads, smem, st>>>(a);
-    else chain_max_kernel<2><<<(unsigned)n_patch, kChainThreads, smem, st>>>(a);
+    a.n_patch = (int)n_patch;
+    // the per-tile barriers of the small layers complete n_layers + 1 times per patch: persistence needs that even
+    const bool persistent = g_chain_persistent && (sp.n_layers & 1) && (sp.W3->out / 128) % 2 == 0;
+    const unsigned grid = persistent ? std::min<unsigned>((unsigned)n_patch, (unsigned)sm_count()) : (unsigned)n_patch;
+    if (NT == 1) chain_max_kernel<1><<<grid, kChainThreads, smem, st>>>(a);
+    else chain_max_kernel<2><<<grid, kChainThreads, smem, st>>>(a);
     note_launch();
     return check_cuda(cudaGetLastError(), "chain_max_kernel launch", __FILE__, __LINE__);
 }
@@ -2005,6 +2031,7 @@ extern "C" DFB_API int dfb_dbg_set(int key, int value) {
     if (key == 7) dfb::g_tl_cta = value;
     if (key == 8) dfb::g_head_persistent = value;
     if (key == 9) dfb::g_cta_trace_on = value;
+    if (key == 10) dfb::g_chain_persistent = value;
     return DFB_OK;
 }
 
