@@ -1147,7 +1147,7 @@ constexpr int kChainThreads = 64 + kChainEpiWarps * 32;
 template <int NT>
 __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArgs g) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t s_wf[3], s_act[2], s_acc[2], s_rf[3], s_re[3], s_tf[2], s_te[2];
+    __shared__ __align__(8) uint64_t s_wf[3], s_act[2], s_acc[2], s_rf[3], s_re[3], s_tf[2], s_te[2], s_md;
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int planes = g.nprod > 1 ? 2 : 1;
@@ -1194,6 +1194,8 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_act[i]), 8); mbar_init(smem_u32(&s_acc[i]), 1); }
         for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&s_rf[i]), 1); mbar_init(smem_u32(&s_re[i]), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_tf[i]), 1); mbar_init(smem_u32(&s_te[i]), 4); }
+        mbar_init(smem_u32(&s_md), 1);   // "every MMA of the patch has completed": one phase per patch (a parity wait
+                                         // on s_tf would alias for a thread that does not follow each of its phases)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -1214,7 +1216,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
             bool ok = true;
             for (int it = 0, patch = blockIdx.x; patch < n_patch && ok; ++it, patch += gridDim.x) {
             // regions R and X still feed the previous patch's max-pool layer until its last MMA has completed
-            if (it > 0) ok = mbar_wait(smem_u32(&s_tf[(CT - 1) & 1]), (uint32_t)(it * TPB - 1) & 1u, g.err, 1);
+            if (it > 0) ok = mbar_wait(smem_u32(&s_md), (uint32_t)(it - 1) & 1u, g.err, 1);
             if (!ok) break;
             for (int l = 0; l < L; ++l) {
                 const uint32_t bar = smem_u32(&s_wf[l]);
@@ -1313,6 +1315,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                 if (ok) umma_commit(smem_u32(&s_tf[buf]));
                 CTL(24 + (ct & 7));
             }
+            if (ok) umma_commit(smem_u32(&s_md));
             }
         }
     } else {
@@ -1337,7 +1340,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         if (tl_lane && grp == 0) CTL(0);
         // ---- phase P ----
         // region R (the first activation buffer) is the previous patch's weight ring until its last MMA has completed
-        if (it > 0) ok = mbar_wait(smem_u32(&s_tf[(CT - 1) & 1]), (uint32_t)(it * TPB - 1) & 1u, g.err, 3);
+        if (it > 0) ok = mbar_wait(smem_u32(&s_md), (uint32_t)(it - 1) & 1u, g.err, 3);
         if (!ok) break;
         if (active) {
             const int j = grp * 128 + lrow;       // point index inside the patch
