@@ -454,6 +454,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {   // one thread standing in for n arrivals
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
+}
 
 template <int NT>
 __global__ void __launch_bounds__(kGemmThreads) gemm_max_resident_kernel(const GemmArgs g, const int wstages) {
@@ -1124,22 +1127,14 @@ struct ChainArgs {
 
 constexpr int kChainEpiWarps = 16;
 
-// relu(W0 p + b0) for 32 of the 64 channels (HALF selects which), straight into the A operand (hi/lo planes)
-template <int HALF>
-__device__ __forceinline__ void chain_first_layer(const ChainArgs& g, float x, float y, float z, uint32_t dst, uint32_t lo_off) {
+// relu(W0 p + b0), all 64 channels of one point, as packed bf16 hi / lo pairs (every weight a constant-bank operand)
+__device__ __forceinline__ void chain_first_layer(const ChainArgs& g, float x, float y, float z, uint32_t (&ph)[32], uint32_t (&pl)[32]) {
 #pragma unroll
-    for (int c8 = 0; c8 < 4; ++c8) {
-        uint32_t ph[4], pl[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int c = HALF * 32 + c8 * 8 + 2 * e;
-            const float f0 = fmaxf(fmaf(g.w0c[c * 3 + 2], z, fmaf(g.w0c[c * 3 + 1], y, fmaf(g.w0c[c * 3], x, g.b0c[c]))), 0.f);
-            const float f1 = fmaxf(fmaf(g.w0c[c * 3 + 5], z, fmaf(g.w0c[c * 3 + 4], y, fmaf(g.w0c[c * 3 + 3], x, g.b0c[c + 1]))), 0.f);
-            split_pair(f0, f1, ph[e], pl[e]);
-        }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)c8 * 2048u), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
-        if (g.nprod > 1)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + lo_off + (uint32_t)c8 * 2048u), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
+    for (int e = 0; e < 32; ++e) {
+        const int c = 2 * e;
+        const float f0 = fmaxf(fmaf(g.w0c[c * 3 + 2], z, fmaf(g.w0c[c * 3 + 1], y, fmaf(g.w0c[c * 3], x, g.b0c[c]))), 0.f);
+        const float f1 = fmaxf(fmaf(g.w0c[c * 3 + 5], z, fmaf(g.w0c[c * 3 + 4], y, fmaf(g.w0c[c * 3 + 3], x, g.b0c[c + 1]))), 0.f);
+        split_pair(f0, f1, ph[e], pl[e]);
     }
 }
 constexpr int kChainThreads = 64 + kChainEpiWarps * 32;
@@ -1188,7 +1183,9 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         const float* base = g.patch + patch * 3LL * g.k;
         px = __ldg(base + j); py = __ldg(base + g.k + j); pz = __ldg(base + 2 * g.k + j);
     };
-    if (warp >= 2 && (((warp - 2) >> 2) & 1) < NT && (int)blockIdx.x < n_patch) fetch_point(blockIdx.x);
+    // phase P belongs to the eight warps that sit out the max-pool phase (column half 1)
+    const bool p_warp = warp >= 10 && (((warp - 2) >> 2) & 1) < NT;
+    if (p_warp && (int)blockIdx.x < n_patch) fetch_point(blockIdx.x);
     if (threadIdx.x == 0) {
         for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&s_wf[i]), 1);
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_act[i]), 8); mbar_init(smem_u32(&s_acc[i]), 1); }
@@ -1339,10 +1336,10 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         for (int it = 0, patch = blockIdx.x; patch < n_patch && ok; ++it, patch += gridDim.x) {
         if (tl_lane && grp == 0) CTL(0);
         // ---- phase P ----
-        // region R (the first activation buffer) is the previous patch's weight ring until its last MMA has completed
-        if (it > 0) ok = mbar_wait(smem_u32(&s_md), (uint32_t)(it - 1) & 1u, g.err, 3);
-        if (!ok) break;
-        if (active) {
+        // done by the warps that have no share in the max-pool phase: they compute the first layer of the NEXT patch
+        // while the tensor core is still busy with this one, and only the stores wait for region R (the first
+        // activation buffer doubles as the previous patch's weight ring until its last MMA has completed)
+        if (p_warp) {
             const int j = grp * 128 + lrow;       // point index inside the patch
             float x = px, y = py, z = pz;
             if (patch + (int)gridDim.x < n_patch) fetch_point(patch + gridDim.x);   // next patch's point, in flight all along
@@ -1352,18 +1349,26 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                 const float yr = fmaf(z, r[7], fmaf(y, r[4], x * r[1]));
                 const float zr = fmaf(z, r[8], fmaf(y, r[5], x * r[2]));
                 x = xr; y = yr; z = zr;
-                if (g.pts_out && half == 0) {
+                if (g.pts_out) {
                     float* po = g.pts_out + (long long)patch * 3LL * k;
                     po[j] = x; po[k + j] = y; po[2 * k + j] = z;
                 }
             }
-            const uint32_t dst = act_in(0) + (uint32_t)grp * kBlkBytes + row_off + (uint32_t)half * 4u * 2048u;
-            if (half == 0) chain_first_layer<0>(g, x, y, z, dst, (uint32_t)NT * kBlkBytes);
-            else chain_first_layer<1>(g, x, y, z, dst, (uint32_t)NT * kBlkBytes);
+            uint32_t ph[32], pl[32];
+            chain_first_layer(g, x, y, z, ph, pl);
+            if (it > 0) ok = mbar_wait(smem_u32(&s_md), (uint32_t)(it - 1) & 1u, g.err, 3);
+            if (!ok) break;
+            const uint32_t dst = act_in(0) + (uint32_t)grp * kBlkBytes + row_off;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)c8 * 2048u), "r"(ph[4 * c8]), "r"(ph[4 * c8 + 1]), "r"(ph[4 * c8 + 2]), "r"(ph[4 * c8 + 3]) : "memory");
+                if (g.nprod > 1)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)NT * kBlkBytes + (uint32_t)c8 * 2048u), "r"(pl[4 * c8]), "r"(pl[4 * c8 + 1]), "r"(pl[4 * c8 + 2]), "r"(pl[4 * c8 + 3]) : "memory");
+            }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&s_act[grp]));
-            if (tl_lane) CTL(2 + grp);
+            if (lane == 0) mbar_arrive_n(smem_u32(&s_act[grp]), 2u);   // the barrier counts the 8 warps of the S-phase epilogues
+            if (lane == 0 && q == 0) CTL(2 + grp);
         }
         // ---- phase S ----
         for (int l = 0; l < L && ok && active; ++l) {
