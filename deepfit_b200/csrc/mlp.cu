@@ -1372,38 +1372,41 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         }
         // ---- phase S ----
         for (int l = 0; l < L && ok && active; ++l) {
-            ok = mbar_wait(smem_u32(&s_acc[grp]), (uint32_t)(it * L + l) & 1u, g.err, 3);
-            if (!ok) break;
-            tc_fence_after();
-            if (tl_lane) CTL(4 + (l * 2 + grp) * 3 + 1);
             const ChainLayer& Ly = g.L[l];
             const bool last = (l == L - 1);
             const long long grow = (long long)patch * k + grp * 128 + lrow;   // global row (point) index
             const int cbeg = half * (Ly.n_out >> 1);
+            // everything that does not depend on the accumulator happens before the wait: the bias of the first 32
+            // columns (constant bank -> registers) and a branch-free form of the output address.  64-channel
+            // operand: block of 16 KB, 8-channel chunks 2 KB apart; X (last layer): [plane][kb][NT*128 rows]
+            float bias_r[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bias_r[i] = g.biasc[l][cbeg + i];
+            const float floor_v = Ly.relu ? 0.f : -3.402823466e38f;
+            const uint32_t obase = (last ? XR + (uint32_t)grp * 2048u : act_in(l + 1) + (uint32_t)grp * kBlkBytes) + row_off;
+            const uint32_t bstride = last ? (uint32_t)NT * kBlkBytes : kBlkBytes;
+            const uint32_t cstride = last ? (uint32_t)NT * 2048u : 2048u;
+            const uint32_t lo_off = (last ? (uint32_t)KB3 : 1u) * (uint32_t)NT * kBlkBytes;
+            ok = mbar_wait(smem_u32(&s_acc[grp]), (uint32_t)(it * L + l) & 1u, g.err, 3);
+            if (!ok) break;
+            tc_fence_after();
+            if (tl_lane) CTL(4 + (l * 2 + grp) * 3 + 1);
 #pragma unroll 1
             for (int c0 = cbeg; c0 < cbeg + (Ly.n_out >> 1); c0 += 32) {
                 tmem_ld32(tmem_base + tlane + (uint32_t)(grp * 128 + c0), v);
+                if (tl_lane && l == 0 && grp == 0) CTL(44);
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8) {
                     uint32_t ph[4], pl[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int i0 = c8 * 8 + 2 * e;
-                        float x0 = __uint_as_float(v[i0]), x1 = __uint_as_float(v[i0 + 1]);
-                        x0 += g.biasc[l][c0 + i0]; x1 += g.biasc[l][c0 + i0 + 1];
-                        if (Ly.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                        const float x0 = fmaxf(__uint_as_float(v[i0]) + bias_r[i0], floor_v);
+                        const float x1 = fmaxf(__uint_as_float(v[i0 + 1]) + bias_r[i0 + 1], floor_v);
                         split_pair(x0, x1, ph[e], pl[e]);
                     }
                     const int col = c0 + c8 * 8;
-                    uint32_t o, lo_off;
-                    if (last) {   // X: [plane][kb][NT*128 rows]: k-chunk stride NT*2048, plane stride KB3 blocks
-                        o = XR + (uint32_t)(col >> 6) * (NT * kBlkBytes) + (uint32_t)((col & 63) >> 3) * (NT * 2048u) +
-                            (uint32_t)grp * 2048u + row_off;
-                        lo_off = (uint32_t)KB3 * NT * kBlkBytes;
-                    } else {
-                        o = act_in(l + 1) + (uint32_t)grp * kBlkBytes + (uint32_t)(col >> 3) * 2048u + row_off;
-                        lo_off = (uint32_t)NT * kBlkBytes;
-                    }
+                    const uint32_t o = obase + (uint32_t)(col >> 6) * bstride + (uint32_t)((col & 63) >> 3) * cstride;
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
                     if (g.nprod > 1)
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + lo_off), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
@@ -1413,8 +1416,14 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                         if (g.nprod > 1) *reinterpret_cast<uint4*>(Ly.store_t + Ly.store_plane + go) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                     }
                 }
+                if (c0 + 32 < cbeg + (Ly.n_out >> 1)) {   // 128-channel layer: the second 32 columns' bias
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) bias_r[i] = g.biasc[l][c0 + 32 + i];
+                }
             }
+            if (tl_lane && l == 0 && grp == 0) CTL(45);
             fence_async_smem();
+            if (tl_lane && l == 0 && grp == 0) CTL(46);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_act[grp]));

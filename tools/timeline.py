@@ -16,6 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 CHAIN = {0: "entry", 1: "setup done", 2: "P done t0", 3: "P done t1", 22: "M start (X ready)", 23: "first W3 stage landed",
+         44: "  L0 t0 epi: tmem_ld done", 45: "  L0 t0 epi: stores issued", 46: "  L0 t0 epi: proxy fence done",
          40: "epi grp0 end", 41: "epi grp1 end", 42: "exit", 43: "TMA: ring free (first W3 issue)"}
 for l in range(3):
     for t in range(2):
