@@ -66,18 +66,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded wait: a pipeline bug must never hang the GPU.  Returns false (and records `code`) on time-out.
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug sets the error flag (dfb_model_status reports it) instead of hanging the GPU.  The
+// clock is only read once the first probe has failed, so a wait on a completed phase costs one instruction.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+    if (mbar_try(bar, parity)) return true;
     const long long t0 = clock64();
     for (;;) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) return true;
+        if (mbar_try(bar, parity)) return true;
         const long long waited = clock64() - t0;
         if (waited > (1LL << 31)) {
             atomicCAS(err, 0, code);
@@ -1142,57 +1148,53 @@ constexpr int kChainThreads = 64 + kChainEpiWarps * 32;
 template <int NT>
 __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArgs g) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t s_wf[3], s_act[2], s_acc[2], s_rf[3], s_re[3], s_tf[2], s_te[2], s_md;
+    __shared__ __align__(8) uint64_t s_act[2], s_acc[2], s_acc_solo, s_rf[3], s_re[3], s_tf[2], s_te[2], s_b0;
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int planes = g.nprod > 1 ? 2 : 1;
     const int n_patch = g.n_patch;   // persistent CTAs: patch = blockIdx.x, blockIdx.x + gridDim.x, ...
     constexpr int KB3 = 2;                                   // 128 input channels of the max layer
-    constexpr uint32_t kActBytes = 2u * NT * kBlkBytes;      // one 64-channel activation buffer, both planes
     constexpr uint32_t kXBytes = 2u * NT * KB3 * kBlkBytes;  // the 128-channel activations, both planes
     constexpr uint32_t kTmemCols = NT == 1 ? 256 : 512;
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t XR = smem_base;
-    const uint32_t RR = smem_base + kXBytes;
-    const uint32_t ACT_A = RR, ACT_B = XR;
-    // weights of the (up to three) small layers are all prefetched at kernel start: slot 0 behind ACT_A,
-    // slots 1-2 in the upper half of X, which stays unused until the last small layer's epilogue -- and
-    // that runs after the MMAs that read the slot have completed
-    // The LAST small layer's slot must not alias X (its epilogue for one row tile writes X while the MMAs of
-    // the other tile still read the weights), so it lives behind ACT_A; earlier layers use the free part of X
-    // (k=128: X is only 64 KB, the second spare slot is in R).
-    auto wbuf = [&](int l) {
-        const int d = g.n_layers - 1 - l;
-        if (d == 0) return RR + kActBytes;
-        if (d == 1) return NT == 2 ? XR + kActBytes : RR + kActBytes + 2u * kBlkBytes;
-        return NT == 2 ? XR + kActBytes + 2u * kBlkBytes : XR + kActBytes;
-    };
+    const uint32_t XR = smem_base;             // B operand of the max-pool layer (written by the last small layer)
+    const uint32_t RR = smem_base + kXBytes;   // weight ring, 3 slots of [hi 16 KB | lo 16 KB]
     const int CT = g.n_ch / 128;
     const int L = g.n_layers;
     const int TPB = CT / 2;          // channel tiles per TMEM buffer and patch
-    const int total = CT * KB3;      // W3 ring stages per patch
-    // completions per patch of the ring barriers: slot s serves stages s, s+3, ...; s_re also gets the "region R is
-    // free" commit that ends the small layers.  n-th completion of a barrier <-> parity (n & 1)
-    auto stages_in_slot = [&](int s) { return (total - s + 2) / 3; };
+    // Activations of the small layers live in TENSOR MEMORY (A operand of tcgen05.mma), 64 columns per row tile in the
+    // packed form [hi 16 | lo 16] per 32 channels: the K=3 layer writes PING, every 64-wide layer's accumulator is
+    // converted in place into the next A operand (PONG, PING, ...); only the last small layer (64->128) goes to shared
+    // memory, as the N=256 B operand X of the max-pool loop.  PING / PONG sit in the max-pool phase's TMEM buffer 0,
+    // the last layer's 128-column accumulators in buffer 1.
+    auto ping = [&](int t) { return (uint32_t)(64 * t); };
+    auto pong = [&](int t) { return (uint32_t)(64 * NT + 64 * t); };
+    auto lastd = [&](int t) { return (uint32_t)(128 * NT + 128 * t); };
+    auto a_cols = [&](int l, int t) { return (l & 1) ? pong(t) : ping(t); };
+    auto d_cols = [&](int l, int t) { return l == L - 1 ? lastd(t) : ((l & 1) ? ping(t) : pong(t)); };
+    // ONE weight ring serves the whole kernel: per patch its entries are the small layers' weight blocks followed by the
+    // CT * KB3 stages of W3, and the ring position keeps running across patches (slot = pos % 3, parity = (pos / 3) & 1):
+    // the next patch's first-layer weights arrive while the current patch is still in its last channel tiles.
 #define CTL(slot) do { if (g.tl && patch == g.tl_cta) g.tl[slot] = clock64(); } while (0)
 
-    // the epilogue warps fetch their point before the set-up barrier so the DRAM latency overlaps the TMEM allocation
+    // phase P belongs to the eight warps that sit out the max-pool phase (column half 1); they fetch their point before
+    // the set-up barrier so the DRAM latency overlaps the TMEM allocation
     float px = 0.f, py = 0.f, pz = 0.f;
-    auto fetch_point = [&](long long patch) {   // epilogue warps that own a row in phases P/S
+    auto fetch_point = [&](long long patch) {
         const int j = (((warp - 2) >> 2) & 1) * 128 + (warp & 3) * 32 + lane;
         const float* base = g.patch + patch * 3LL * g.k;
         px = __ldg(base + j); py = __ldg(base + g.k + j); pz = __ldg(base + 2 * g.k + j);
     };
-    // phase P belongs to the eight warps that sit out the max-pool phase (column half 1)
     const bool p_warp = warp >= 10 && (((warp - 2) >> 2) & 1) < NT;
     if (p_warp && (int)blockIdx.x < n_patch) fetch_point(blockIdx.x);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 3; ++i) mbar_init(smem_u32(&s_wf[i]), 1);
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_act[i]), 8); mbar_init(smem_u32(&s_acc[i]), 1); }
         for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(&s_rf[i]), 1); mbar_init(smem_u32(&s_re[i]), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_tf[i]), 1); mbar_init(smem_u32(&s_te[i]), 4); }
-        mbar_init(smem_u32(&s_md), 1);   // "every MMA of the patch has completed": one phase per patch (a parity wait
-                                         // on s_tf would alias for a thread that does not follow each of its phases)
+        // "TMEM buffer 0 has been read for the last time in this patch": one phase per patch (a parity wait on s_te
+        // would alias for a thread that does not follow each of its phases)
+        mbar_init(smem_u32(&s_b0), 4);
+        mbar_init(smem_u32(&s_acc_solo), 1);   // first layer of row tile 1 in a multi-layer chain, see phase S
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -1203,127 +1205,121 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
-    // activation buffer read by small layer l (they alternate, and the last layer must read ACT_A because
-    // it writes X, which aliases ACT_B)
-    auto act_in = [&](int l) { return ((L - 1 - l) & 1) ? ACT_B : ACT_A; };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
             bool ok = true;
-            for (int it = 0, patch = blockIdx.x; patch < n_patch && ok; ++it, patch += gridDim.x) {
-            // regions R and X still feed the previous patch's max-pool layer until its last MMA has completed
-            if (it > 0) ok = mbar_wait(smem_u32(&s_md), (uint32_t)(it - 1) & 1u, g.err, 1);
-            if (!ok) break;
-            for (int l = 0; l < L; ++l) {
-                const uint32_t bar = smem_u32(&s_wf[l]);
-                mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
-                for (int pl = 0; pl < planes; ++pl)
-                    bulk_g2s(wbuf(l) + (uint32_t)pl * kBlkBytes,
-                             g.L[l].w + (size_t)pl * g.L[l].w_plane + (size_t)patch * g.L[l].w_patch_stride, kBlkBytes, bar);
-            }
-            for (int i = 0; i < total && ok; ++i) {
-                const int s = i % 3;
-                // first completion of s_re in a patch = "the small layers no longer read region R" (MMA warp)
-                ok = mbar_wait(smem_u32(&s_re[s]), (uint32_t)(it * (stages_in_slot(s) + 1) + i / 3) & 1u, g.err, 1);
-                if (!ok) break;
-                if (i == 0) CTL(43);
+            int pos = 0;
+            auto load_entry = [&](const bf16* src, size_t plane_elems) {
+                const int s = pos % 3;
+                ok = mbar_wait(smem_u32(&s_re[s]), ((uint32_t)(pos / 3) & 1u) ^ 1u, g.err, 1);
+                if (!ok) return;
                 const uint32_t bar = smem_u32(&s_rf[s]);
                 mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
                 for (int pl = 0; pl < planes; ++pl)
-                    bulk_g2s(RR + (uint32_t)s * (2u * kBlkBytes) + (uint32_t)pl * kBlkBytes,
-                             g.w3 + (size_t)pl * g.w3_plane + (size_t)i * kBlkElems, kBlkBytes, bar);
-            }
+                    bulk_g2s(RR + (uint32_t)s * (2u * kBlkBytes) + (uint32_t)pl * kBlkBytes, src + (size_t)pl * plane_elems, kBlkBytes, bar);
+                ++pos;
+            };
+            for (int it = 0, patch = blockIdx.x; patch < n_patch && ok; ++it, patch += gridDim.x) {
+                for (int l = 0; l < L && ok; ++l) load_entry(g.L[l].w + (size_t)patch * g.L[l].w_patch_stride, g.L[l].w_plane);
+                for (int i = 0; i < CT * KB3 && ok; ++i) {
+                    load_entry(g.w3 + (size_t)i * kBlkElems, g.w3_plane);
+                    if (i == 0) CTL(43);
+                    if (i == 2) CTL(47);
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
             bool ok = true;
-            // the row tiles are independent through all small layers, so they are software-pipelined: while the
-            // epilogue group of tile t turns layer l's accumulator into the next operand, the MMAs of the other
-            // tile run (per-tile barriers s_act[t] / s_acc[t])
+            int pos = 0;
             for (int it = 0, patch = blockIdx.x; patch < n_patch && ok; ++it, patch += gridDim.x) {
-            // the small layers accumulate in TMEM buffer 0, which the previous patch's max-pool epilogue may still read
-            if (it > 0) ok = mbar_wait(smem_u32(&s_te[0]), (uint32_t)(it * TPB - 1) & 1u, g.err, 4);
-            for (int l = 0; l < L && ok; ++l) {
-                ok = mbar_wait(smem_u32(&s_wf[l]), (uint32_t)it & 1u, g.err, 2);
-                if (!ok) break;
-                const uint32_t idesc = umma_idesc(g.L[l].n_out);
-                const uint32_t ain = act_in(l);
-                const uint32_t WBUF = wbuf(l);
-#pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    ok = ok && mbar_wait(smem_u32(&s_act[t]), (uint32_t)l & 1u, g.err, 5);
+                // the small layers accumulate in TMEM buffer 0, which the previous patch's max-pool epilogue may still read
+                if (it > 0) ok = mbar_wait(smem_u32(&s_te[0]), (uint32_t)(it * TPB - 1) & 1u, g.err, 4);
+                // the two row tiles are independent through all small layers, so they are software-pipelined: while the
+                // epilogue warps of tile t turn layer l's accumulator into the next operand, the MMAs of the other tile run
+                for (int l = 0; l < L && ok; ++l) {
+                    const int s = pos % 3;
+                    ok = mbar_wait(smem_u32(&s_rf[s]), (uint32_t)(pos / 3) & 1u, g.err, 2);
+                    // the last small layer accumulates in buffer 1
+                    if (ok && l == L - 1 && it > 0) ok = mbar_wait(smem_u32(&s_te[1]), (uint32_t)(it * TPB - 1) & 1u, g.err, 4);
                     if (!ok) break;
-                    tc_fence_after();
-                    CTL(4 + (l * 2 + t) * 3);
-                    const uint32_t a_hi = ain + (uint32_t)t * kBlkBytes, a_lo = ain + (uint32_t)(NT + t) * kBlkBytes;
-                    const uint32_t d = tmem_base + (uint32_t)t * 128u;
+                    const uint32_t idesc = umma_idesc(g.L[l].n_out);
+                    const uint32_t w_hi = RR + (uint32_t)s * (2u * kBlkBytes), w_lo = w_hi + kBlkBytes;
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t koff = (uint32_t)ks * 2 * kLBO;
-                        umma_bf16(d, umma_desc(a_hi + koff, kLBO, kSBO), umma_desc(WBUF + koff, kLBO, kSBO), idesc, ks ? 1u : 0u);
-                        if (g.nprod > 1) {
-                            umma_bf16(d, umma_desc(a_hi + koff, kLBO, kSBO), umma_desc(WBUF + kBlkBytes + koff, kLBO, kSBO), idesc, 1u);
-                            umma_bf16(d, umma_desc(a_lo + koff, kLBO, kSBO), umma_desc(WBUF + koff, kLBO, kSBO), idesc, 1u);
+                    for (int t = 0; t < NT; ++t) {
+                        ok = ok && mbar_wait(smem_u32(&s_act[t]), (uint32_t)l & 1u, g.err, 5);
+                        if (!ok) break;
+                        tc_fence_after();
+                        CTL(4 + (l * 2 + t) * 3);
+                        const uint32_t a = tmem_base + a_cols(l, t);
+                        const uint32_t d = tmem_base + d_cols(l, t);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            // k-step ks of the 64 input channels: 32-channel half ks >> 1, [hi 16 | lo 16] columns
+                            const uint32_t a_hi = a + (uint32_t)(ks >> 1) * 32u + (uint32_t)(ks & 1) * 8u, a_lo = a_hi + 16u;
+                            const uint32_t koff = (uint32_t)ks * 2 * kLBO;
+                            umma_bf16_ts(d, a_hi, umma_desc(w_hi + koff, kLBO, kSBO), idesc, ks ? 1u : 0u);
+                            if (g.nprod > 1) {
+                                umma_bf16_ts(d, a_hi, umma_desc(w_lo + koff, kLBO, kSBO), idesc, 1u);
+                                umma_bf16_ts(d, a_lo, umma_desc(w_hi + koff, kLBO, kSBO), idesc, 1u);
+                            }
                         }
+                        umma_commit(smem_u32((l == 0 && L > 1 && t == 1) ? &s_acc_solo : &s_acc[t]));
                     }
-                    umma_commit(smem_u32(&s_acc[t]));
+                    if (ok) umma_commit(smem_u32(&s_re[s]));   // the weights are dead once these MMAs have completed
+                    ++pos;
                 }
-            }
-            if (ok) {   // region R (ACT_A, WBUF) is dead once everything issued so far has completed
-                for (int s = 0; s < 3; ++s) umma_commit(smem_u32(&s_re[s]));
                 for (int t = 0; t < NT && ok; ++t)
-                    ok = mbar_wait(smem_u32(&s_act[t]), (uint32_t)L & 1u, g.err, 5);   // X written, TMEM drained
+                    ok = mbar_wait(smem_u32(&s_act[t]), (uint32_t)L & 1u, g.err, 5);   // X written
                 CTL(22);
-            }
-            const uint32_t idesc = umma_idesc(NT * 128);
-            const uint32_t lbo_b = (uint32_t)NT * kLBO;
-            for (int ct = 0; ct < CT && ok; ++ct) {
-                const int buf = ct & 1;
-                const uint32_t use = (uint32_t)(it * TPB + (ct >> 1));   // n-th tile into this buffer, across patches
-                if (use > 0) ok = mbar_wait(smem_u32(&s_te[buf]), (use - 1u) & 1u, g.err, 4);
-                if (!ok) break;
-                tc_fence_after();
-                for (int kb = 0; kb < KB3 && ok; ++kb) {
-                    const int i = ct * KB3 + kb;
-                    const int s = i % 3;
-                    ok = mbar_wait(smem_u32(&s_rf[s]), (uint32_t)(it * stages_in_slot(s) + i / 3) & 1u, g.err, 2);
+                const uint32_t idesc = umma_idesc(NT * 128);
+                const uint32_t lbo_b = (uint32_t)NT * kLBO;
+                for (int ct = 0; ct < CT && ok; ++ct) {
+                    const int buf = ct & 1;
+                    const uint32_t use = (uint32_t)(it * TPB + (ct >> 1));   // n-th tile into this buffer, across patches
+                    if (use > 0) ok = mbar_wait(smem_u32(&s_te[buf]), (use - 1u) & 1u, g.err, 4);
                     if (!ok) break;
                     tc_fence_after();
-                    if (i == 0) CTL(23);
-                    const uint32_t a_hi = RR + (uint32_t)s * (2u * kBlkBytes), a_lo = a_hi + kBlkBytes;
-                    const uint32_t b_hi = XR + (uint32_t)(0 * KB3 + kb) * (NT * kBlkBytes);
-                    const uint32_t b_lo = XR + (uint32_t)(1 * KB3 + kb) * (NT * kBlkBytes);
-                    const uint32_t d = tmem_base + (uint32_t)(buf * NT * 128);
+                    if (ct == 0) CTL(48);
+                    for (int kb = 0; kb < KB3 && ok; ++kb) {
+                        const int s = pos % 3;
+                        ok = mbar_wait(smem_u32(&s_rf[s]), (uint32_t)(pos / 3) & 1u, g.err, 2);
+                        if (!ok) break;
+                        tc_fence_after();
+                        if (ct == 0 && kb == 0) CTL(23);
+                        const uint32_t a_hi = RR + (uint32_t)s * (2u * kBlkBytes), a_lo = a_hi + kBlkBytes;
+                        const uint32_t b_hi = XR + (uint32_t)(0 * KB3 + kb) * (NT * kBlkBytes);
+                        const uint32_t b_lo = XR + (uint32_t)(1 * KB3 + kb) * (NT * kBlkBytes);
+                        const uint32_t d = tmem_base + (uint32_t)(buf * NT * 128);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t ka = (uint32_t)ks * 2 * kLBO, kbo = (uint32_t)ks * 2 * lbo_b;
-                        const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-                        umma_bf16(d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(b_hi + kbo, lbo_b, kSBO), idesc, first);
-                        if (g.nprod > 1) {
-                            umma_bf16(d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(b_lo + kbo, lbo_b, kSBO), idesc, 1u);
-                            umma_bf16(d, umma_desc(a_lo + ka, kLBO, kSBO), umma_desc(b_hi + kbo, lbo_b, kSBO), idesc, 1u);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint32_t ka = (uint32_t)ks * 2 * kLBO, kbo = (uint32_t)ks * 2 * lbo_b;
+                            const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+                            umma_bf16(d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(b_hi + kbo, lbo_b, kSBO), idesc, first);
+                            if (g.nprod > 1) {
+                                umma_bf16(d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(b_lo + kbo, lbo_b, kSBO), idesc, 1u);
+                                umma_bf16(d, umma_desc(a_lo + ka, kLBO, kSBO), umma_desc(b_hi + kbo, lbo_b, kSBO), idesc, 1u);
+                            }
                         }
+                        umma_commit(smem_u32(&s_re[s]));
+                        ++pos;
                     }
-                    umma_commit(smem_u32(&s_re[s]));
+                    if (ok) umma_commit(smem_u32(&s_tf[buf]));
+                    CTL(24 + (ct & 7));
                 }
-                if (ok) umma_commit(smem_u32(&s_tf[buf]));
-                CTL(24 + (ct & 7));
-            }
-            if (ok) umma_commit(smem_u32(&s_md));
             }
         }
     } else {
         // ===================== 16 epilogue warps =====================
-        // phases P/S: 4 lane quadrants x 2 row tiles x 2 column halves (the per-layer epilogue is the serial part of
-        // the prologue, so it gets every issue slot it can use); phase M: the column-half-0 warps only (max over all
-        // columns of a lane; the MMAs bound that phase)
+        // phase S: 4 lane quadrants x 2 row tiles x 2 column halves; phase M: the column-half-0 warps only (max over all
+        // columns of a lane; the MMAs bound that phase); phase P: the column-half-1 warps, meanwhile
         const int ew = warp - 2;
         const int q = warp & 3;                   // TMEM lane quadrant (hardware rule)
         const int grp = (ew >> 2) & 1;            // phases P/S: row tile; phase M: channel-tile parity
-        const int half = ew >> 3;                 // phases P/S: column half
+        const int half = ew >> 3;                 // phase S: column half
         const int lrow = q * 32 + lane;
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
         const bool active = grp < NT;             // owns a row of the patch in phases P/S
@@ -1336,9 +1332,8 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         for (int it = 0, patch = blockIdx.x; patch < n_patch && ok; ++it, patch += gridDim.x) {
         if (tl_lane && grp == 0) CTL(0);
         // ---- phase P ----
-        // done by the warps that have no share in the max-pool phase: they compute the first layer of the NEXT patch
-        // while the tensor core is still busy with this one, and only the stores wait for region R (the first
-        // activation buffer doubles as the previous patch's weight ring until its last MMA has completed)
+        // the first layer of the NEXT patch is computed while the tensor core is still busy with this one; only the
+        // tensor-memory stores wait until buffer 0 has been read for the last time
         if (p_warp) {
             const int j = grp * 128 + lrow;       // point index inside the patch
             float x = px, y = py, z = pz;
@@ -1356,16 +1351,18 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
             }
             uint32_t ph[32], pl[32];
             chain_first_layer(g, x, y, z, ph, pl);
-            if (it > 0) ok = mbar_wait(smem_u32(&s_md), (uint32_t)(it - 1) & 1u, g.err, 3);
+            if (it > 0) ok = mbar_wait(smem_u32(&s_b0), (uint32_t)(it - 1) & 1u, g.err, 3);
             if (!ok) break;
-            const uint32_t dst = act_in(0) + (uint32_t)grp * kBlkBytes + row_off;
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)c8 * 2048u), "r"(ph[4 * c8]), "r"(ph[4 * c8 + 1]), "r"(ph[4 * c8 + 2]), "r"(ph[4 * c8 + 3]) : "memory");
-                if (g.nprod > 1)
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)NT * kBlkBytes + (uint32_t)c8 * 2048u), "r"(pl[4 * c8]), "r"(pl[4 * c8 + 1]), "r"(pl[4 * c8 + 2]), "r"(pl[4 * c8 + 3]) : "memory");
+            tc_fence_after();
+            const uint32_t cols = tmem_base + tlane + ping(grp);
+            tmem_st16(cols, reinterpret_cast<const uint32_t(&)[16]>(ph[0]));
+            tmem_st16(cols + 32u, reinterpret_cast<const uint32_t(&)[16]>(ph[16]));
+            if (g.nprod > 1) {
+                tmem_st16(cols + 16u, reinterpret_cast<const uint32_t(&)[16]>(pl[0]));
+                tmem_st16(cols + 48u, reinterpret_cast<const uint32_t(&)[16]>(pl[16]));
             }
-            fence_async_smem();
+            tmem_st_wait();
+            tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_n(smem_u32(&s_act[grp]), 2u);   // the barrier counts the 8 warps of the S-phase epilogues
             if (lane == 0 && q == 0) CTL(2 + grp);
@@ -1374,60 +1371,92 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         for (int l = 0; l < L && ok && active; ++l) {
             const ChainLayer& Ly = g.L[l];
             const bool last = (l == L - 1);
+            // The warps that drained the previous patch's LAST channel tile (row tile 1, column half 0) come late to a
+            // new patch.  In a multi-layer chain its first layer does not wait for them: the column-half-1 warps of tile 1
+            // convert all 64 columns and arrive for both halves.
+            // That accumulator has a barrier of its own (one phase per patch), so that the late warps never have to
+            // follow a phase they take no part in: a parity wait two phases behind would alias.
+            const bool solo = (l == 0 && L > 1 && grp == 1);
+            if (solo && half == 0) continue;
             const long long grow = (long long)patch * k + grp * 128 + lrow;   // global row (point) index
-            const int cbeg = half * (Ly.n_out >> 1);
-            // everything that does not depend on the accumulator happens before the wait: the bias of the first 32
-            // columns (constant bank -> registers) and a branch-free form of the output address.  64-channel
-            // operand: block of 16 KB, 8-channel chunks 2 KB apart; X (last layer): [plane][kb][NT*128 rows]
+            const int cbeg = solo ? 0 : half * (Ly.n_out >> 1);
+            // everything that does not depend on the accumulator happens before the wait
             float bias_r[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) bias_r[i] = g.biasc[l][cbeg + i];
             const float floor_v = Ly.relu ? 0.f : -3.402823466e38f;
-            const uint32_t obase = (last ? XR + (uint32_t)grp * 2048u : act_in(l + 1) + (uint32_t)grp * kBlkBytes) + row_off;
-            const uint32_t bstride = last ? (uint32_t)NT * kBlkBytes : kBlkBytes;
-            const uint32_t cstride = last ? (uint32_t)NT * 2048u : 2048u;
-            const uint32_t lo_off = (last ? (uint32_t)KB3 : 1u) * (uint32_t)NT * kBlkBytes;
-            ok = mbar_wait(smem_u32(&s_acc[grp]), (uint32_t)(it * L + l) & 1u, g.err, 3);
+            if (solo) ok = mbar_wait(smem_u32(&s_acc_solo), (uint32_t)it & 1u, g.err, 3);
+            else if (grp == 1 && L > 1) ok = mbar_wait(smem_u32(&s_acc[1]), (uint32_t)(it * (L - 1) + l - 1) & 1u, g.err, 3);
+            else ok = mbar_wait(smem_u32(&s_acc[grp]), (uint32_t)(it * L + l) & 1u, g.err, 3);
             if (!ok) break;
             tc_fence_after();
             if (tl_lane) CTL(4 + (l * 2 + grp) * 3 + 1);
+            const uint32_t dcol = tmem_base + tlane + d_cols(l, grp);
+            if (!last) {
+                // 64-wide layer: this warp's 32 accumulator columns become [hi 16 | lo 16] packed columns, in place
 #pragma unroll 1
-            for (int c0 = cbeg; c0 < cbeg + (Ly.n_out >> 1); c0 += 32) {
-                tmem_ld32(tmem_base + tlane + (uint32_t)(grp * 128 + c0), v);
-                if (tl_lane && l == 0 && grp == 0) CTL(44);
+                for (int cb = cbeg; cb < (solo ? 64 : cbeg + 32); cb += 32) {
+                    uint32_t ph[16], pl[16];
+                    tmem_ld32(dcol + (uint32_t)cb, v);
+                    if (tl_lane && l == 0 && grp == 0) CTL(44);
 #pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) {
-                    uint32_t ph[4], pl[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int i0 = c8 * 8 + 2 * e;
-                        const float x0 = fmaxf(__uint_as_float(v[i0]) + bias_r[i0], floor_v);
-                        const float x1 = fmaxf(__uint_as_float(v[i0 + 1]) + bias_r[i0 + 1], floor_v);
+                    for (int e = 0; e < 16; ++e) {
+                        const float x0 = fmaxf(__uint_as_float(v[2 * e]) + bias_r[2 * e], floor_v);
+                        const float x1 = fmaxf(__uint_as_float(v[2 * e + 1]) + bias_r[2 * e + 1], floor_v);
                         split_pair(x0, x1, ph[e], pl[e]);
                     }
-                    const int col = c0 + c8 * 8;
-                    const uint32_t o = obase + (uint32_t)(col >> 6) * bstride + (uint32_t)((col & 63) >> 3) * cstride;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
-                    if (g.nprod > 1)
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + lo_off), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
-                    if (Ly.store_t) {
-                        const size_t go = tiled_offset(grow, col, 1);
-                        *reinterpret_cast<uint4*>(Ly.store_t + go) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                        if (g.nprod > 1) *reinterpret_cast<uint4*>(Ly.store_t + Ly.store_plane + go) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    tmem_st16(dcol + (uint32_t)cb, ph);
+                    if (g.nprod > 1) tmem_st16(dcol + (uint32_t)cb + 16u, pl);
+                    if (Ly.store_t) {   // x * T2 is also the head's input
+#pragma unroll
+                        for (int c8 = 0; c8 < 4; ++c8) {
+                            const size_t go = tiled_offset(grow, cb + c8 * 8, 1);
+                            *reinterpret_cast<uint4*>(Ly.store_t + go) = make_uint4(ph[4 * c8], ph[4 * c8 + 1], ph[4 * c8 + 2], ph[4 * c8 + 3]);
+                            if (g.nprod > 1)
+                                *reinterpret_cast<uint4*>(Ly.store_t + Ly.store_plane + go) = make_uint4(pl[4 * c8], pl[4 * c8 + 1], pl[4 * c8 + 2], pl[4 * c8 + 3]);
+                        }
+                    }
+                    if (solo && cb == 0) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) bias_r[i] = g.biasc[l][32 + i];
                     }
                 }
-                if (c0 + 32 < cbeg + (Ly.n_out >> 1)) {   // 128-channel layer: the second 32 columns' bias
+                tmem_st_wait();
+                if (tl_lane && l == 0 && grp == 0) CTL(45);
+            } else {
+                // last small layer (64 -> 128): X in shared memory, [plane][kb][NT*128 rows], k-chunk stride NT*2048
+                const uint32_t obase = XR + (uint32_t)grp * 2048u + row_off;
+                const uint32_t lo_off = (uint32_t)KB3 * NT * kBlkBytes;
+#pragma unroll 1
+                for (int c0 = cbeg; c0 < cbeg + (Ly.n_out >> 1); c0 += 32) {
+                    tmem_ld32(dcol + (uint32_t)c0, v);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) bias_r[i] = g.biasc[l][c0 + 32 + i];
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        uint32_t ph[4], pl[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int i0 = c8 * 8 + 2 * e;
+                            const float x0 = fmaxf(__uint_as_float(v[i0]) + bias_r[i0], floor_v);
+                            const float x1 = fmaxf(__uint_as_float(v[i0 + 1]) + bias_r[i0 + 1], floor_v);
+                            split_pair(x0, x1, ph[e], pl[e]);
+                        }
+                        const int col = c0 + c8 * 8;
+                        const uint32_t o = obase + (uint32_t)(col >> 6) * (NT * kBlkBytes) + (uint32_t)((col & 63) >> 3) * (NT * 2048u);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
+                        if (g.nprod > 1)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + lo_off), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
+                    }
+                    if (c0 + 32 < cbeg + (Ly.n_out >> 1)) {   // the second 32 columns' bias
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) bias_r[i] = g.biasc[l][c0 + 32 + i];
+                    }
                 }
+                fence_async_smem();
             }
-            if (tl_lane && l == 0 && grp == 0) CTL(45);
-            fence_async_smem();
-            if (tl_lane && l == 0 && grp == 0) CTL(46);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&s_act[grp]));
-            if (tl_lane) CTL(4 + (l * 2 + grp) * 3 + 2);
+            if (lane == 0) mbar_arrive_n(smem_u32(&s_act[grp]), solo ? 2u : 1u);
+            if (tl_lane || (solo && lane == 0 && q == 0)) CTL(4 + (l * 2 + grp) * 3 + 2);
         }
         // ---- phase M: group g takes the channel tiles of parity g ----
         for (int ct = grp; ct < CT && ok && half == 0; ct += 2) {
@@ -1446,7 +1475,10 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&s_te[buf]));
+            if (lane == 0) {
+                mbar_arrive(smem_u32(&s_te[buf]));
+                if (buf == 0 && ct + 2 >= CT) mbar_arrive(smem_u32(&s_b0));   // buffer 0's last tile of the patch
+            }
             const long long ch = (long long)ct * 128 + lrow;
             float r = mx + (g.bias3 ? g.bias3[ch] : 0.f);
             if (g.relu3) r = fmaxf(r, 0.f);

@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 
 CHAIN = {0: "entry", 1: "setup done", 2: "P done t0", 3: "P done t1", 22: "M start (X ready)", 23: "first W3 stage landed",
          44: "  L0 t0 epi: tmem_ld done", 45: "  L0 t0 epi: stores issued", 46: "  L0 t0 epi: proxy fence done",
-         40: "epi grp0 end", 41: "epi grp1 end", 42: "exit", 43: "TMA: ring free (first W3 issue)"}
+         40: "epi grp0 end", 41: "epi grp1 end", 42: "exit", 43: "TMA: W3 stage 0 issued", 47: "TMA: W3 stage 2 issued", 48: "mma: buffer 0 free for ct0"}
 for l in range(3):
     for t in range(2):
         b = 4 + (l * 2 + t) * 3
