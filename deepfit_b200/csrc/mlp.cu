@@ -66,24 +66,39 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded wait: a pipeline bug must never hang the GPU.  Returns false (and records `code`) on time-out.
+// PARK: pass a suspend-time hint, so the hardware parks the thread until the phase completes instead of letting it
+// spin through issue slots and power -- for waits that are long and not latency-critical (producers, idle warps); the
+// hand-offs on the MMA <-> epilogue critical path probe without it (the parked wake-up is measurably slower).
+template <bool PARK>
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
+    if (PARK) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(100000u)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
     return ok != 0;
 }
 // Bounded wait: a pipeline bug sets the error flag (dfb_model_status reports it) instead of hanging the GPU.  The
 // clock is only read once the first probe has failed, so a wait on a completed phase costs one instruction.
+template <bool PARK = false>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
-    if (mbar_try(bar, parity)) return true;
+    if (mbar_try<PARK>(bar, parity)) return true;
     const long long t0 = clock64();
     for (;;) {
-        if (mbar_try(bar, parity)) return true;
+        if (mbar_try<PARK>(bar, parity)) return true;
         const long long waited = clock64() - t0;
         if (waited > (1LL << 31)) {
             atomicCAS(err, 0, code);
@@ -771,7 +786,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             };
             auto load_w1 = [&](int c) {
                 const int s = c & 1;
-                if (!mbar_wait(smem_u32(&s_w1e[s]), ((uint32_t)(c >> 1) & 1u) ^ 1u, g.err, 1)) { ok = false; return; }
+                if (!mbar_wait<true>(smem_u32(&s_w1e[s]), ((uint32_t)(c >> 1) & 1u) ^ 1u, g.err, 1)) { ok = false; return; }
                 const uint32_t bar = smem_u32(&s_w1f[s]);
                 mbar_expect_tx(bar, (uint32_t)planes * 8192u);
                 bulk_g2s(W1R + (uint32_t)s * 16384u, g.w1c + (size_t)c * 8192, (uint32_t)planes * 8192u, bar);  // hi|lo contiguous
@@ -781,7 +796,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             // plane); a stage is half a block: k-chunks 4h..4h+3 = 16 KB per plane, contiguous
             auto load_w2 = [&](int c, int h) {
                 const int s = w2i % 3;
-                if (!mbar_wait(smem_u32(&s_w2e[s]), ((uint32_t)(w2i / 3) & 1u) ^ 1u, g.err, 1)) { ok = false; return; }
+                if (!mbar_wait<true>(smem_u32(&s_w2e[s]), ((uint32_t)(w2i / 3) & 1u) ^ 1u, g.err, 1)) { ok = false; return; }
                 const uint32_t bar = smem_u32(&s_w2f[s]);
                 if (g.dbg & 4) {   // experiment: no layer-2 weight traffic
                     mbar_arrive(bar);
@@ -1213,7 +1228,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
             int pos = 0;
             auto load_entry = [&](const bf16* src, size_t plane_elems) {
                 const int s = pos % 3;
-                ok = mbar_wait(smem_u32(&s_re[s]), ((uint32_t)(pos / 3) & 1u) ^ 1u, g.err, 1);
+                ok = mbar_wait<true>(smem_u32(&s_re[s]), ((uint32_t)(pos / 3) & 1u) ^ 1u, g.err, 1);
                 if (!ok) return;
                 const uint32_t bar = smem_u32(&s_rf[s]);
                 mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
@@ -1237,20 +1252,20 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
             int pos = 0;
             for (int it = 0, patch = blockIdx.x; patch < n_patch && ok; ++it, patch += gridDim.x) {
                 // the small layers accumulate in TMEM buffer 0, which the previous patch's max-pool epilogue may still read
-                if (it > 0) ok = mbar_wait(smem_u32(&s_te[0]), (uint32_t)(it * TPB - 1) & 1u, g.err, 4);
+                if (it > 0) ok = mbar_wait<true>(smem_u32(&s_te[0]), (uint32_t)(it * TPB - 1) & 1u, g.err, 4);
                 // the two row tiles are independent through all small layers, so they are software-pipelined: while the
                 // epilogue warps of tile t turn layer l's accumulator into the next operand, the MMAs of the other tile run
                 for (int l = 0; l < L && ok; ++l) {
                     const int s = pos % 3;
-                    ok = mbar_wait(smem_u32(&s_rf[s]), (uint32_t)(pos / 3) & 1u, g.err, 2);
+                    ok = mbar_wait<true>(smem_u32(&s_rf[s]), (uint32_t)(pos / 3) & 1u, g.err, 2);
                     // the last small layer accumulates in buffer 1
-                    if (ok && l == L - 1 && it > 0) ok = mbar_wait(smem_u32(&s_te[1]), (uint32_t)(it * TPB - 1) & 1u, g.err, 4);
+                    if (ok && l == L - 1 && it > 0) ok = mbar_wait<true>(smem_u32(&s_te[1]), (uint32_t)(it * TPB - 1) & 1u, g.err, 4);
                     if (!ok) break;
                     const uint32_t idesc = umma_idesc(g.L[l].n_out);
                     const uint32_t w_hi = RR + (uint32_t)s * (2u * kBlkBytes), w_lo = w_hi + kBlkBytes;
 #pragma unroll
                     for (int t = 0; t < NT; ++t) {
-                        ok = ok && mbar_wait(smem_u32(&s_act[t]), (uint32_t)l & 1u, g.err, 5);
+                        ok = ok && mbar_wait<true>(smem_u32(&s_act[t]), (uint32_t)l & 1u, g.err, 5);
                         if (!ok) break;
                         tc_fence_after();
                         CTL(4 + (l * 2 + t) * 3);
@@ -1273,20 +1288,20 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                     ++pos;
                 }
                 for (int t = 0; t < NT && ok; ++t)
-                    ok = mbar_wait(smem_u32(&s_act[t]), (uint32_t)L & 1u, g.err, 5);   // X written
+                    ok = mbar_wait<true>(smem_u32(&s_act[t]), (uint32_t)L & 1u, g.err, 5);   // X written
                 CTL(22);
                 const uint32_t idesc = umma_idesc(NT * 128);
                 const uint32_t lbo_b = (uint32_t)NT * kLBO;
                 for (int ct = 0; ct < CT && ok; ++ct) {
                     const int buf = ct & 1;
                     const uint32_t use = (uint32_t)(it * TPB + (ct >> 1));   // n-th tile into this buffer, across patches
-                    if (use > 0) ok = mbar_wait(smem_u32(&s_te[buf]), (use - 1u) & 1u, g.err, 4);
+                    if (use > 0) ok = mbar_wait<true>(smem_u32(&s_te[buf]), (use - 1u) & 1u, g.err, 4);
                     if (!ok) break;
                     tc_fence_after();
                     if (ct == 0) CTL(48);
                     for (int kb = 0; kb < KB3 && ok; ++kb) {
                         const int s = pos % 3;
-                        ok = mbar_wait(smem_u32(&s_rf[s]), (uint32_t)(pos / 3) & 1u, g.err, 2);
+                        ok = mbar_wait<true>(smem_u32(&s_rf[s]), (uint32_t)(pos / 3) & 1u, g.err, 2);
                         if (!ok) break;
                         tc_fence_after();
                         if (ct == 0 && kb == 0) CTL(23);
@@ -1351,7 +1366,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
             }
             uint32_t ph[32], pl[32];
             chain_first_layer(g, x, y, z, ph, pl);
-            if (it > 0) ok = mbar_wait(smem_u32(&s_b0), (uint32_t)(it - 1) & 1u, g.err, 3);
+            if (it > 0) ok = mbar_wait<true>(smem_u32(&s_b0), (uint32_t)(it - 1) & 1u, g.err, 3);
             if (!ok) break;
             tc_fence_after();
             const uint32_t cols = tmem_base + tlane + ping(grp);
@@ -1385,9 +1400,9 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
 #pragma unroll
             for (int i = 0; i < 32; ++i) bias_r[i] = g.biasc[l][cbeg + i];
             const float floor_v = Ly.relu ? 0.f : -3.402823466e38f;
-            if (solo) ok = mbar_wait(smem_u32(&s_acc_solo), (uint32_t)it & 1u, g.err, 3);
-            else if (grp == 1 && L > 1) ok = mbar_wait(smem_u32(&s_acc[1]), (uint32_t)(it * (L - 1) + l - 1) & 1u, g.err, 3);
-            else ok = mbar_wait(smem_u32(&s_acc[grp]), (uint32_t)(it * L + l) & 1u, g.err, 3);
+            if (solo) ok = mbar_wait<true>(smem_u32(&s_acc_solo), (uint32_t)it & 1u, g.err, 3);
+            else if (grp == 1 && L > 1) ok = mbar_wait<true>(smem_u32(&s_acc[1]), (uint32_t)(it * (L - 1) + l - 1) & 1u, g.err, 3);
+            else ok = mbar_wait<true>(smem_u32(&s_acc[grp]), (uint32_t)(it * L + l) & 1u, g.err, 3);
             if (!ok) break;
             tc_fence_after();
             if (tl_lane) CTL(4 + (l * 2 + grp) * 3 + 1);
@@ -1462,7 +1477,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         for (int ct = grp; ct < CT && ok && half == 0; ct += 2) {
             const int buf = ct & 1;                 // == grp
             const uint32_t use = (uint32_t)(it * TPB + (ct >> 1));
-            ok = mbar_wait(smem_u32(&s_tf[buf]), use & 1u, g.err, 3);
+            ok = mbar_wait<true>(smem_u32(&s_tf[buf]), use & 1u, g.err, 3);
             if (!ok) break;
             tc_fence_after();
             if (tl_lane) CTL(32 + (ct & 7));
