@@ -427,18 +427,19 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
                                 for (int e = 0; e < 8; ++e) dstf[e] = make_float4(f[4 * e], f[4 * e + 1], f[4 * e + 2], f[4 * e + 3]);
                             }
                         } else if (EPI == EPI_T2) {
-                            // output column = n*64 + kk (fc3 rows were permuted on the host): per-patch
-                            // B operand  T2^T[n][kk]  in tiled form, one 128-row block per patch
+                            // per-patch B operand  T2^T[n][kk]  in tiled form, one 128-row block per patch.  The host
+                            // permuted the fc3 rows so that output column c = (kk>>3)*512 + (n>>3)*64 + (n&7)*8 + (kk&7)
+                            // is the block's own memory order: a thread's 32 columns are 64 contiguous bytes per plane
 #pragma unroll
                             for (int c8 = 0; c8 < 4; ++c8) {
                                 const int col = (int)col0 + c8 * 8;
-                                const int n = col >> 6, kk = col & 63;
+                                const int n = (((col >> 6) & 7) << 3) | ((col >> 3) & 7), kk = (col >> 9) << 3;
                                 uint32_t ph[4], plo[4];
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
                                     split_pair(f[c8 * 8 + 2 * e], f[c8 * 8 + 2 * e + 1], ph[e], plo[e]);
                                 }
-                                const size_t o = (size_t)row * kBlkElems + (size_t)(kk >> 3) * 1024 + (size_t)(n >> 3) * 64 + (size_t)(n & 7) * 8;
+                                const size_t o = (size_t)row * kBlkElems + (size_t)(col >> 9) * 1024 + (size_t)(col & 511);
                                 *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                                 if (g.nprod > 1)
                                     *reinterpret_cast<uint4*>(g.out_t + g.out_plane + o) = make_uint4(plo[0], plo[1], plo[2], plo[3]);
@@ -2185,13 +2186,15 @@ extern "C" int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, d
             DFB_TRY(upload_head_w1_chunks(l.h_weight, 1088, 1024, &m->head_w1c, st));
             track(m->head_w1c);
         } else if (i == DFB_L_STN_FC3) {
-            // emit T2^T: output column n*64+kk takes the reference's row kk*64+n; +I is symmetric
+            // emit T2^T in the memory order of a tiled 64-row operand: output column
+            // (kk>>3)*512 + (n>>3)*64 + (n&7)*8 + (kk&7) takes the reference's row kk*64+n; +I is symmetric
             std::vector<int> perm(4096);
             std::vector<float> hb(4096);
             for (int n = 0; n < 64; ++n)
                 for (int kk = 0; kk < 64; ++kk) {
-                    perm[n * 64 + kk] = kk * 64 + n;
-                    hb[n * 64 + kk] = l.h_bias[kk * 64 + n] + (n == kk ? 1.f : 0.f);
+                    const int c = (kk >> 3) * 512 + (n >> 3) * 64 + (n & 7) * 8 + (kk & 7);
+                    perm[c] = kk * 64 + n;
+                    hb[c] = l.h_bias[kk * 64 + n] + (n == kk ? 1.f : 0.f);
                 }
             DFB_TRY(upload_pack(l.h_weight, 4096, 256, 0, 256, 256, m->L[i], st, perm.data()));
             track(m->L[i].w.p);
