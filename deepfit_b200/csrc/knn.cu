@@ -258,6 +258,60 @@ __device__ __forceinline__ void warp_bitonic_sort(double* sd, int* si, int cap, 
     }
 }
 
+// Tighten the list without sorting it: find, by bisection on the distance, a bound T with at least k (and at most a few
+// more) of the count entries <= T, then compact those to the front.  T is an UPPER bound of the k-th smallest key seen
+// so far, which is all the pruning needs (every true neighbour has d2 <= T; ties are kept, the final sort orders them).
+// Costs ~1 k instructions where a 512-entry bitonic sort costs ~7 k.  Returns the new count (>= k).
+__device__ __forceinline__ int warp_select_compact(double* sd, int* si, int count, int k, int lane, double& T) {
+    double vmin = __longlong_as_double(0x7ff0000000000000LL), vmax = 0.0;
+    for (int t = lane; t < count; t += 32) {
+        const double v = sd[t];
+        vmin = fmin(vmin, v);
+        vmax = fmax(vmax, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    double lo = vmin, hi = vmax;   // invariant: #(<= hi) >= k
+    for (int iter = 0; iter < 14 && lo < hi; ++iter) {
+        const double mid = lo + 0.5 * (hi - lo);
+        if (!(mid < hi)) break;      // resolution exhausted
+        int c = 0;
+        for (int t = lane; t < count; t += 32) c += (sd[t] <= mid) ? 1 : 0;
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (c >= k) {
+            hi = mid;
+            if (c <= k + 16) break;
+        } else {
+            lo = mid;
+        }
+    }
+    T = hi;
+    int n = 0;
+    for (int base = 0; base < count; base += 32) {
+        const int t = base + lane;
+        double v = 0.0;
+        int id = 0;
+        bool keep = false;
+        if (t < count) {
+            v = sd[t];
+            id = si[t];
+            keep = v <= hi;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        if (keep) {
+            const int pos = n + __popc(bal & ((1u << lane) - 1u));
+            sd[pos] = v;
+            si[pos] = id;
+        }
+        n += __popc(bal);
+        __syncwarp();
+    }
+    return n;
+}
+
 struct KnnArgs {
     const float4* sorted;
     const uint32_t* tab;
@@ -386,18 +440,26 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                     const unsigned bal = __ballot_sync(0xffffffffu, take);
                     if (bal == 0u) continue;
                     if (count + 32 > cap) {
-                        // pad, sort, keep the k best
-                        for (int t = count + lane; t < cap; t += 32) { sd[t] = INF; si[t] = 0x7fffffff; }
-                        __syncwarp();
-                        warp_bitonic_sort(sd, si, cap, lane);
-                        count = k;
-                        Td = sd[k - 1];
-                        Ti = si[k - 1];
-                        thr_incl = false;
+                        // the list is full: tighten the bound by selection; only if that cannot make room (a pile of
+                        // exact ties) pad, sort and keep exactly the k best
+                        double T;
+                        count = warp_select_compact(sd, si, count, k, lane, T);
+                        Td = T;
+                        Ti = 0x7fffffff;
+                        thr_incl = true;
                         full_once = true;
-                        __syncwarp();
+                        if (count + 32 > cap) {
+                            for (int t = count + lane; t < cap; t += 32) { sd[t] = INF; si[t] = 0x7fffffff; }
+                            __syncwarp();
+                            warp_bitonic_sort(sd, si, cap, lane);
+                            count = k;
+                            Td = sd[k - 1];
+                            Ti = si[k - 1];
+                            thr_incl = false;
+                            __syncwarp();
+                        }
                         // re-evaluate this batch against the tighter threshold
-                        take = (j < chi) && key_less(d2, pidx, Td, Ti);
+                        take = (j < chi) && (thr_incl ? !key_less(Td, Ti, d2, pidx) : key_less(d2, pidx, Td, Ti));
                         const unsigned bal2 = __ballot_sync(0xffffffffu, take);
                         if (bal2 == 0u) continue;
                         const int pos = count + __popc(bal2 & ((1u << lane) - 1u));
@@ -414,15 +476,14 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                 // once the own cell / the face neighbours are in and no threshold exists yet, pay one sort to
                 // get one: everything farther than the current k-th best is then rejected without insertion
                 if ((ci == 0 || ci == 6 || ci == 18) && !full_once && count >= k) {
-                    for (int t = count + lane; t < cap; t += 32) { sd[t] = INF; si[t] = 0x7fffffff; }
-                    __syncwarp();
-                    warp_bitonic_sort(sd, si, cap, lane);
-                    count = k;
-                    Td = sd[k - 1];
-                    Ti = si[k - 1];
-                    thr_incl = false;
+                    double T;
+                    count = warp_select_compact(sd, si, count, k, lane, T);
+                    if (T < Td) {   // never loosen a bound carried over from a failed level
+                        Td = T;
+                        Ti = 0x7fffffff;
+                        thr_incl = true;
+                    }
                     full_once = true;
-                    __syncwarp();
                 }
             }
             // final sort of what we have
