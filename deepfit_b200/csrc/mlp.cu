@@ -1136,7 +1136,8 @@ struct ChainArgs {
     const float* bias3;
     int relu3;
     int n_ch;                 // 1024
-    int n_patch;              // patches; the grid is min(n_patch, #SMs) persistent CTAs
+    int n_patch;              // work items (patches, or 256-point halves of k=512 patches); grid = min(n_patch, #SMs) persistent CTAs
+    int ipp;                  // items per patch: 1, or 2 for k = 512 (partial maxima go to out_f, chain_combine_kernel merges)
     bf16* out_t;              // tiled global-feature rows (patches)
     size_t out_plane;
     int out_KB;
@@ -1196,9 +1197,11 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
     // phase P belongs to the eight warps that sit out the max-pool phase (column half 1); they fetch their point before
     // the set-up barrier so the DRAM latency overlaps the TMEM allocation
     float px = 0.f, py = 0.f, pz = 0.f;
-    auto fetch_point = [&](long long patch) {
-        const int j = (((warp - 2) >> 2) & 1) * 128 + (warp & 3) * 32 + lane;
-        const float* base = g.patch + patch * 3LL * g.k;
+    // a work item is a patch, or (k = 512) one 256-point half of a patch: item -> (patch pi, first point j0)
+    const int ipp = g.ipp;
+    auto fetch_point = [&](long long item) {
+        const int j = (int)(item % ipp) * (NT * 128) + (((warp - 2) >> 2) & 1) * 128 + (warp & 3) * 32 + lane;
+        const float* base = g.patch + (item / ipp) * 3LL * g.k;
         px = __ldg(base + j); py = __ldg(base + g.k + j); pz = __ldg(base + 2 * g.k + j);
     };
     const bool p_warp = warp >= 10 && (((warp - 2) >> 2) & 1) < NT;
@@ -1238,7 +1241,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                 ++pos;
             };
             for (int it = 0, patch = blockIdx.x; patch < n_patch && ok; ++it, patch += gridDim.x) {
-                for (int l = 0; l < L && ok; ++l) load_entry(g.L[l].w + (size_t)patch * g.L[l].w_patch_stride, g.L[l].w_plane);
+                for (int l = 0; l < L && ok; ++l) load_entry(g.L[l].w + (size_t)(patch / ipp) * g.L[l].w_patch_stride, g.L[l].w_plane);
                 for (int i = 0; i < CT * KB3 && ok; ++i) {
                     load_entry(g.w3 + (size_t)i * kBlkElems, g.w3_plane);
                     if (i == 0) CTL(43);
@@ -1350,18 +1353,20 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         // ---- phase P ----
         // the first layer of the NEXT patch is computed while the tensor core is still busy with this one; only the
         // tensor-memory stores wait until buffer 0 has been read for the last time
+        const long long pi = patch / ipp;         // the patch this item belongs to
+        const int j0 = (patch % ipp) * (NT * 128);   // its first point
         if (p_warp) {
-            const int j = grp * 128 + lrow;       // point index inside the patch
+            const int j = j0 + grp * 128 + lrow;       // point index inside the patch
             float x = px, y = py, z = pz;
             if (patch + (int)gridDim.x < n_patch) fetch_point(patch + gridDim.x);   // next patch's point, in flight all along
             if (g.R) {
-                const float* r = g.R + (long long)patch * 9;
+                const float* r = g.R + pi * 9;
                 const float xr = fmaf(z, r[6], fmaf(y, r[3], x * r[0]));
                 const float yr = fmaf(z, r[7], fmaf(y, r[4], x * r[1]));
                 const float zr = fmaf(z, r[8], fmaf(y, r[5], x * r[2]));
                 x = xr; y = yr; z = zr;
                 if (g.pts_out) {
-                    float* po = g.pts_out + (long long)patch * 3LL * k;
+                    float* po = g.pts_out + pi * 3LL * k;
                     po[j] = x; po[k + j] = y; po[2 * k + j] = z;
                 }
             }
@@ -1394,7 +1399,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
             // follow a phase they take no part in: a parity wait two phases behind would alias.
             const bool solo = (l == 0 && L > 1 && grp == 1);
             if (solo && half == 0) continue;
-            const long long grow = (long long)patch * k + grp * 128 + lrow;   // global row (point) index
+            const long long grow = pi * k + j0 + grp * 128 + lrow;   // global row (point) index
             const int cbeg = solo ? 0 : half * (Ly.n_out >> 1);
             // everything that does not depend on the accumulator happens before the wait
             float bias_r[32];
@@ -1515,6 +1520,23 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
     __syncthreads();
     tc_fence_after();
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// k = 512: the chain kernel ran on 256-point halves (bias and ReLU are monotone, so they commute with the max);
+// the global feature of a patch is the max of its two partial vectors, re-split into the tiled bf16 planes.
+__global__ void chain_combine_kernel(const float* __restrict__ part, long long n_patch, int n_ch, int ipp, bf16* __restrict__ out_t,
+                                     size_t out_plane, int out_KB, int split) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_patch * n_ch) return;
+    const long long p = i / n_ch;
+    const int ch = (int)(i % n_ch);
+    float r = part[(p * ipp) * n_ch + ch];
+    for (int h = 1; h < ipp; ++h) r = fmaxf(r, part[(p * ipp + h) * n_ch + ch]);
+    bf16 hi, lo;
+    split_bf16(r, hi, lo);
+    const size_t o = tiled_offset(p, ch, out_KB);
+    out_t[o] = hi;
+    if (split) out_t[out_plane + o] = lo;
 }
 
 // --------------------------------------------------------------------------- small CUDA-core kernels
@@ -1705,6 +1727,7 @@ struct dfb_model {
     dfb::PackedLayer head_global;  // HEAD_CONV1 columns 0..1023  (bias = folded conv1 bias)
     dfb::PackedLayer head_point;   // HEAD_CONV1 columns 1024..1087 (no bias of its own)
     float* w_small[DFB_NUM_LAYERS] = {nullptr};  // raw fp32 weights of the CUDA-core layers
+    float* chain_part = nullptr;   // k = 512: fp32 [2 * max_batch, 1024] partial maxima of the half-patch work items
     std::vector<float> h_w_small[DFB_NUM_LAYERS];  // host copies of the two K=3 layers and of conv4
     dfb::bf16* head_w1c = nullptr;               // HEAD_CONV1 point part in 64-row chunks for the fused head
     dfb::PackedLayer head_w2_256;                // HEAD_CONV2 in 256-row blocks (N=256 MMAs of the fused head)
@@ -2004,7 +2027,15 @@ int launch_chain(const dfb_model* m, const float* patch, long long n_patch, cons
     a.out_t = gfeat.p; a.out_plane = gfeat.plane; a.out_KB = gfeat.KB;
     a.nprod = m->nprod; a.err = m->err;
     a.tl = timeline_region(sp.n_layers == 1 ? 0 : (sp.relu3 ? 1 : 2)); a.tl_cta = g_tl_cta;
-    const int NT = m->k / 128;
+    // k = 512: a patch's 256 KB of activations do not fit shared memory, so it is processed as two 256-point work items
+    const int ipp = m->k == 512 ? 2 : 1;
+    const int NT = m->k / 128 / ipp;
+    a.ipp = ipp;
+    if (ipp > 1) {
+        a.out_t = nullptr;
+        a.out_f = m->chain_part;
+    }
+    n_patch *= ipp;
     const size_t smem = (size_t)2 * NT * 2 * kBlkBytes + 96 * 1024;
     static bool attr_done[3] = {false, false, false};
     if (!attr_done[NT]) {
@@ -2020,6 +2051,12 @@ int launch_chain(const dfb_model* m, const float* patch, long long n_patch, cons
     if (NT == 1) chain_max_kernel<1><<<grid, kChainThreads, smem, st>>>(a);
     else chain_max_kernel<2><<<grid, kChainThreads, smem, st>>>(a);
     note_launch();
+    if (ipp > 1) {
+        const long long total = (n_patch / ipp) * a.n_ch;
+        chain_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m->chain_part, n_patch / ipp, a.n_ch, ipp, gfeat.p, gfeat.plane,
+                                                                              gfeat.KB, m->nprod > 1 ? 1 : 0);
+        note_launch();
+    }
     return check_cuda(cudaGetLastError(), "chain_max_kernel launch", __FILE__, __LINE__);
 }
 
@@ -2232,6 +2269,10 @@ extern "C" int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, d
     DFB_TRY(check_cuda(cudaMemsetAsync(m->t2blk.p, 0, m->t2blk.plane * 2 * sizeof(bf16), st), "memset", __FILE__, __LINE__));
     DFB_TRY(check_cuda(cudaMalloc(&m->f256_f, (size_t)Bp * 256 * sizeof(float)), "malloc", __FILE__, __LINE__)); track(m->f256_f);
     DFB_TRY(check_cuda(cudaMalloc(&m->hg, (size_t)Bp * 512 * sizeof(float)), "malloc", __FILE__, __LINE__)); track(m->hg);
+    if (m->k == 512) {
+        DFB_TRY(check_cuda(cudaMalloc(&m->chain_part, (size_t)Bp * 2 * 1024 * sizeof(float)), "malloc", __FILE__, __LINE__));
+        track(m->chain_part);
+    }
     DFB_TRY(check_cuda(cudaMalloc(&m->err, sizeof(int)), "malloc", __FILE__, __LINE__)); track(m->err);
     DFB_TRY(check_cuda(cudaMemsetAsync(m->err, 0, sizeof(int), st), "memset", __FILE__, __LINE__));
     DFB_TRY(check_cuda(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__));
@@ -2276,7 +2317,7 @@ extern "C" int dfb_model_forward(dfb_model* m, const float* d_patch, int64_t n, 
         float* trans = d_trans + s * 9;
         const unsigned pw_blocks = (unsigned)((rows + 127) / 128);
 
-        const bool use_chain = g_chain && (k == 128 || k == 256);
+        const bool use_chain = g_chain && (k == 128 || k == 256 || k == 512);
         const bool head_all = g_head_fused && g_head_l3;
         if (!use_chain || !head_all) DFB_RUN(ensure_unfused_buffers(m));
         if (use_chain) {
