@@ -258,36 +258,38 @@ __device__ __forceinline__ void warp_bitonic_sort(double* sd, int* si, int cap, 
     }
 }
 
-// Tighten the list without sorting it: find, by bisection on the distance, a bound T with at least k (and at most a few
-// more) of the count entries <= T, then compact those to the front.  T is an UPPER bound of the k-th smallest key seen
-// so far, which is all the pruning needs (every true neighbour has d2 <= T; ties are kept, the final sort orders them).
-// Costs ~1 k instructions where a 512-entry bitonic sort costs ~7 k.  Returns the new count (>= k).
+// Tighten the list without sorting it: find, by bisection, a bound T with at least k (and at most a few more) of the
+// count entries <= T, then compact those to the front.  T is an UPPER bound of the k-th smallest key seen so far, which
+// is all the pruning needs (every true neighbour has d2 <= T; ties are kept, the final sort orders them).  The bisection
+// runs on the BIT PATTERNS of the (non-negative) distances: they are monotone in the value and roughly logarithmic, so a
+// list that mixes a dense cluster with far points converges as fast as a uniform one, and as an integer binary search it
+// ends at the exact k-th value at the latest.  ~1 k instructions where a 512-entry bitonic sort costs ~7 k.
+// Returns the new count (>= k; larger than k + 16 only for exact ties).
 __device__ __forceinline__ int warp_select_compact(double* sd, int* si, int count, int k, int lane, double& T) {
-    double vmin = __longlong_as_double(0x7ff0000000000000LL), vmax = 0.0;
+    long long lo = 0x7ff0000000000000LL, hi = 0;
     for (int t = lane; t < count; t += 32) {
-        const double v = sd[t];
-        vmin = fmin(vmin, v);
-        vmax = fmax(vmax, v);
+        const long long v = __double_as_longlong(sd[t]);
+        lo = min(lo, v);
+        hi = max(hi, v);
     }
     for (int o = 16; o > 0; o >>= 1) {
-        vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-        vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    double lo = vmin, hi = vmax;   // invariant: #(<= hi) >= k
-    for (int iter = 0; iter < 14 && lo < hi; ++iter) {
-        const double mid = lo + 0.5 * (hi - lo);
-        if (!(mid < hi)) break;      // resolution exhausted
+    // invariant: #(<= hi) >= k and #(< lo) < k
+    for (int iter = 0; iter < 64 && lo < hi; ++iter) {
+        const long long mid = lo + ((hi - lo) >> 1);
         int c = 0;
-        for (int t = lane; t < count; t += 32) c += (sd[t] <= mid) ? 1 : 0;
+        for (int t = lane; t < count; t += 32) c += (__double_as_longlong(sd[t]) <= mid) ? 1 : 0;
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if (c >= k) {
             hi = mid;
             if (c <= k + 16) break;
         } else {
-            lo = mid;
+            lo = mid + 1;
         }
     }
-    T = hi;
+    T = __longlong_as_double(hi);
     int n = 0;
     for (int base = 0; base < count; base += 32) {
         const int t = base + lane;
@@ -297,7 +299,7 @@ __device__ __forceinline__ int warp_select_compact(double* sd, int* si, int coun
         if (t < count) {
             v = sd[t];
             id = si[t];
-            keep = v <= hi;
+            keep = __double_as_longlong(v) <= hi;
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         __syncwarp();
@@ -342,8 +344,10 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
     const int G = 1 << gpar.bits;
     const int k = a.k, cap = a.kcap;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    int level_hint = 0;   // consecutive queries of a warp are usually neighbours in density: start one level below
-                          // the level that answered the previous query (any level passing the margin test is exact)
+    int level_hint = 0;   // the level that answered the warp's previous query: the search starts there, first DOWN while
+                          // the finer block still holds enough points (a query that jumps from a sparse to a dense
+                          // region must not scan a coarse block), then up as usual.  Any level passing the margin test
+                          // is exact.
 
     for (long long qw = (long long)blockIdx.x * kKnnWarps + warp; qw < a.q_count; qw += (long long)gridDim.x * kKnnWarps) {
         const long long qi = a.query ? (long long)a.query[qw] : a.q_begin + qw;
@@ -359,7 +363,26 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
         int Ti = 0x7fffffff;
         bool thr_incl = true;
 
-        for (int l = level_hint; l <= gpar.bits; ++l) {
+        const long long need = min((long long)3 * k, gpar.n);
+        int l0 = level_hint;
+        while (l0 > 0) {   // population of the 27-cell block one level finer
+            const int lf = l0 - 1;
+            const int Gf = G >> lf;
+            const int fx = ix >> lf, fy = iy >> lf, fz = iz >> lf;
+            unsigned cnt = 0;
+            if (lane < 27) {
+                const int ex = fx + (lane % 3) - 1, ey = fy + ((lane / 3) % 3) - 1, ez = fz + (lane / 9) - 1;
+                if (ex >= 0 && ey >= 0 && ez >= 0 && ex < Gf && ey < Gf && ez < Gf) {
+                    const uint32_t m = morton3(ex, ey, ez);
+                    const int sh = 3 * lf;
+                    cnt = a.tab[((size_t)m + 1) << sh] - a.tab[(size_t)m << sh];
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if ((long long)cnt < need) break;
+            l0 = lf;
+        }
+        for (int l = l0; l <= gpar.bits; ++l) {
             const int Gl = G >> l;
             const int cx = ix >> l, cy = iy >> l, cz = iz >> l;
             // 27 neighbour cells, one per lane
@@ -396,7 +419,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
             unsigned total = hi - lo;
             for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
             const bool top = (l == gpar.bits);
-            if (!top && (long long)total < min((long long)3 * k, gpar.n)) continue;
+            if (!top && (long long)total < need) continue;
 
             // guaranteed-complete radius of the block (world units), strict
             double margin2 = INF;
@@ -499,7 +522,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                     if (a.out_dist) a.out_dist[qw * (long long)k + t] = sqrt(sd[t]);
                 }
                 if (a.out_rad && lane == 0) a.out_rad[qw] = sqrt(sd[k - 1]);
-                level_hint = l > 0 ? l - 1 : 0;
+                level_hint = l;
                 __syncwarp();
                 break;
             }
