@@ -264,7 +264,9 @@ __device__ __forceinline__ void warp_bitonic_sort(double* sd, int* si, int cap, 
 // runs on the BIT PATTERNS of the (non-negative) distances: they are monotone in the value and roughly logarithmic, so a
 // list that mixes a dense cluster with far points converges as fast as a uniform one, and as an integer binary search it
 // ends at the exact k-th value at the latest.  ~1 k instructions where a 512-entry bitonic sort costs ~7 k.
-// Returns the new count (>= k; larger than k + 16 only for exact ties).
+// Returns the new count (>= k; larger than k + 16 only for exact ties).  EXACT: run the search to its end, T is then
+// the k-th smallest distance itself and the new count is k unless distances tie across the cut.
+template <bool EXACT>
 __device__ __forceinline__ int warp_select_compact(double* sd, int* si, int count, int k, int lane, double& T) {
     long long lo = 0x7ff0000000000000LL, hi = 0;
     for (int t = lane; t < count; t += 32) {
@@ -284,7 +286,7 @@ __device__ __forceinline__ int warp_select_compact(double* sd, int* si, int coun
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if (c >= k) {
             hi = mid;
-            if (c <= k + 16) break;
+            if (!EXACT && c <= k + 16) break;
         } else {
             lo = mid + 1;
         }
@@ -343,6 +345,8 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
     const GridParams gpar = *a.gp;
     const int G = 1 << gpar.bits;
     const int k = a.k, cap = a.kcap;
+    int k2 = 32;               // size of the sorting network for exactly k entries
+    while (k2 < k) k2 <<= 1;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     int level_hint = 0;   // the level that answered the warp's previous query: the search starts there, first DOWN while
                           // the finer block still holds enough points (a query that jumps from a sparse to a dense
@@ -466,7 +470,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                         // the list is full: tighten the bound by selection; only if that cannot make room (a pile of
                         // exact ties) pad, sort and keep exactly the k best
                         double T;
-                        count = warp_select_compact(sd, si, count, k, lane, T);
+                        count = warp_select_compact<false>(sd, si, count, k, lane, T);
                         Td = T;
                         Ti = 0x7fffffff;
                         thr_incl = true;
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                 // get one: everything farther than the current k-th best is then rejected without insertion
                 if ((ci == 0 || ci == 6 || ci == 18) && !full_once && count >= k) {
                     double T;
-                    count = warp_select_compact(sd, si, count, k, lane, T);
+                    count = warp_select_compact<false>(sd, si, count, k, lane, T);
                     if (T < Td) {   // never loosen a bound carried over from a failed level
                         Td = T;
                         Ti = 0x7fffffff;
@@ -509,10 +513,18 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                     full_once = true;
                 }
             }
-            // final sort of what we have
-            for (int t = count + lane; t < cap; t += 32) { sd[t] = INF; si[t] = 0x7fffffff; }
+            // final sort of what we have.  With more than k entries, first cut the list to the k best exactly (selection
+            // on the distance; if distances tie across the cut the tied entries all stay and the full-size sort decides by
+            // index), so that the exact (d2, index) sort runs on half the network
+            int sort_n = cap;
+            if (count > k) {
+                double T;
+                count = warp_select_compact<true>(sd, si, count, k, lane, T);
+            }
+            if (count == k) sort_n = k2;
+            for (int t = count + lane; t < sort_n; t += 32) { sd[t] = INF; si[t] = 0x7fffffff; }
             __syncwarp();
-            warp_bitonic_sort(sd, si, cap, lane);
+            warp_bitonic_sort(sd, si, sort_n, lane);
             const bool have_k = count >= k;
             const double dk2 = have_k ? sd[k - 1] : INF;
             if (top || (have_k && dk2 < margin2)) {
