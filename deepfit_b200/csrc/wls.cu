@@ -249,20 +249,23 @@ struct WlsArgs {
     int* info;
 };
 
-template <int ORDER>
+// PPW = patches per warp iteration: 32 (every lane solves one system in phase 2) when there is enough work to fill the
+// GPU that way, 8 for smaller batches -- the fp64 accumulators cost ~230 registers per thread, so only ~8 warps fit an SM
+// and a 16 K-patch chunk would otherwise leave most of them without work.
+template <int ORDER, int PPW>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) wls_kernel(WlsArgs p) {
     using J = Jet<ORDER>;
     constexpr int M = J::M;
     __shared__ double s_mom[kWarpsPerBlock][32][kSlotStride];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane >> 3, sub = lane & 7;
-    const long long n_super = (p.n + 31) / 32;  // groups of 32 patches, one per warp iteration
+    const long long n_super = (p.n + PPW - 1) / PPW;  // groups of PPW patches, one per warp iteration
 
     for (long long sp = (long long)blockIdx.x * kWarpsPerBlock + warp; sp < n_super;
          sp += (long long)gridDim.x * kWarpsPerBlock) {
-        const long long base = sp * 32;
+        const long long base = sp * PPW;
         // ---------------- phase 1 ----------------
-        for (int round = 0; round < 8; ++round) {
+        for (int round = 0; round < PPW / 4; ++round) {
             long long pi = base + round * 4 + grp;
             const bool live = pi < p.n;
             if (!live) pi = p.n - 1;
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) wls_kernel(WlsArgs p) {
         __syncwarp();
         // ---------------- phase 2 ----------------
         const long long pi = base + lane;
-        if (pi < p.n) {
+        if (lane < PPW && pi < p.n) {
             const double* slot = s_mom[warp][lane];
             float h = 1.f;
             if (ORDER > 1) {
@@ -465,11 +468,14 @@ __global__ void __launch_bounds__(256) neighbor_normals_kernel(const float* __re
 
 template <int ORDER>
 int launch_wls(const WlsArgs& a, cudaStream_t st) {
-    const long long n_super = (a.n + 31) / 32;
-    long long blocks = (n_super + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const long long cap = (long long)sm_count() * 16;
+    const bool small = (a.n + 31) / 32 < (long long)sm_count() * 8 * 2;   // fewer 32-patch groups than two waves of warps
+    const int ppw = small ? 8 : 32;
+    const long long n_super = (a.n + ppw - 1) / ppw;
+    long long blocks = (n_super + kWarpsPerBlock - 1) / kWarpsPerBlock;
     if (blocks > cap) blocks = cap;
-    wls_kernel<ORDER><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+    if (small) wls_kernel<ORDER, 8><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+    else wls_kernel<ORDER, 32><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(a);
     note_launch();
     return check_cuda(cudaGetLastError(), "wls_kernel launch", __FILE__, __LINE__);
 }
