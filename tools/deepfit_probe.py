@@ -1,6 +1,7 @@
+"""DeepFit-mode throughput for a given (k, order) on a multi-surface cloud: python tools/deepfit_probe.py K ORDER POINTS [CHUNK]"""
 import sys, os, time, json
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from deepfit_b200 import synthetic
 from deepfit_b200.pipeline import NormalEstimator, model_from_state_dict
 from deepfit_b200.tutorial_utils import normalize_cloud

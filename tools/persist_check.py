@@ -1,6 +1,7 @@
+"""Persistent kernels vs one CTA per item, bit-equality on 700 patches (dfb_dbg_set keys 8 / 10): python tools/persist_check.py"""
 import sys, os
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from deepfit_b200 import _lib, ops
 from deepfit_b200.pipeline import model_from_state_dict
 from oracle import deepfit_oracle as O
