@@ -329,7 +329,7 @@ def main():
                          "traffic": 135.1e6 * args.chunk / 4096,   # captured at 4096 patches per launch; every term scales with the patch count
                          "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained" % which,
                          "note": "achieved = algorithmic FLOPs of the three chain kernels (222.6 MFLOP/patch at k=256) / their CUDA-event "
-                                 "time; parity precision bf16x3 executes 3x that on the tensor pipe, so the ceiling of frac is 0.333",
+                                 "time; parity precision bf16x3 executes 3x that on the tensor pipe, so frac tops out near 0.333 at the sustained clock the peak was measured at (short un-throttled runs exceed it)",
                          "launches": int(gm_n), "avg_launch_ms": gm_ms / gm_n if gm_n else None,
                          "share_of_network": gm_ms / net_ms if net_ms else None,
                          "network_tflops_algorithmic": (n_patches_timed * MLP_FLOP_PER_PATCH) / (net_ms * 1e-3) / 1e12 if net_ms else None},

@@ -469,7 +469,9 @@ __global__ void __launch_bounds__(256) neighbor_normals_kernel(const float* __re
 template <int ORDER>
 int launch_wls(const WlsArgs& a, cudaStream_t st) {
     const long long cap = (long long)sm_count() * 16;
-    const bool small = (a.n + 31) / 32 < (long long)sm_count() * 8 * 2;   // fewer 32-patch groups than two waves of warps
+    // fewer 32-patch groups than half a wave of warps; not for order 4, whose per-lane solve (M = 15) dominates and would
+    // run with a quarter of the lanes
+    const bool small = ORDER <= 3 && (a.n + 31) / 32 < (long long)sm_count() * 4;
     const int ppw = small ? 8 : 32;
     const long long n_super = (a.n + ppw - 1) / ppw;
     long long blocks = (n_super + kWarpsPerBlock - 1) / kWarpsPerBlock;

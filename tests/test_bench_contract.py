@@ -42,7 +42,7 @@ def test_own_arm_json_contract_small():
     assert line["e2e"]["h2d_bytes_per_step"] == 8192 * 12 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert line["gpu_launches"] > 0
     rf = line["roofline"]
-    assert rf["bound"] == "tensor" and rf["unit"] == "TFLOP/s" and 0 < rf["frac"] < 0.34 and rf["peak"] > 0
+    assert rf["bound"] == "tensor" and rf["unit"] == "TFLOP/s" and 0 < rf["frac"] < 0.6 and rf["peak"] > 0
     assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
     assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
