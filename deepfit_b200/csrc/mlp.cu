@@ -670,9 +670,8 @@ struct HeadArgs {
     long long* tl;       // timeline region or NULL
     int tl_cta;
     long long* cta_trace;  // NULL or [3 * gridDim.x]
-    int dbg;             // profiling experiments only (dfb_dbg_set key 6; results are garbage): bit 0 = epilogues skip
-                         // their math and stores, bit 1 = no layer-2 MMAs, bit 2 = no layer-2 weight loads,
-                         // bit 3 = no layer-1 MMAs
+    int dbg;             // profiling experiments only (dfb_dbg_set key 6; results are garbage): bit 1 = no layer-2 MMAs,
+                         // bit 2 = no layer-2 weight loads, bit 3 = no layer-1 MMAs
     int* err;
 };
 
@@ -2122,6 +2121,9 @@ extern "C" int dfb_model_profile_read(dfb_model* m, double* ms, int64_t* launche
     return DFB_OK;
 }
 
+// Debug / A-B switches (not part of the ABI header): 0 swap LBO/SBO (descriptor probe), 1 resident max-pool kernel,
+// 2 fused head, 4 layer 3 fused into the head, 5 fused chain kernels, 6 head experiment bits, 7 CTA / tile / patch whose
+// timeline is recorded (-1 off), 8 persistent head, 9 per-tile entry/exit trace of the head, 10 persistent chain.
 extern "C" DFB_API int dfb_dbg_set(int key, int value) {
     if (key == 0) dfb::g_swap_lbo_sbo = value;
     if (key == 1) dfb::g_max_resident = value;
