@@ -239,19 +239,21 @@ def test_forward_is_batch_independent_and_chunked():
         net.forward(torch.zeros(2, 3, 128, device="cuda"))
 
 
-def test_persistent_kernels_match_one_cta_per_tile(dbg_switch):
+@pytest.mark.parametrize("B,k", [(3000, 256), (1, 256), (149, 256), (333, 128), (600, 512)])
+def test_persistent_kernels_match_one_cta_per_tile(dbg_switch, B, k):
     """The fused kernels run as persistent CTAs (one per SM walking patches / tiles); with more work items than SMs
-    every barrier parity is exercised across iterations.  Results must be bit-identical to one CTA per item."""
+    every barrier parity is exercised across iterations (3000 patches = ~20 patches and ~40 head tiles per SM; the small
+    and odd sizes leave some CTAs with one item fewer or none; k = 128 has one row tile per patch, k = 512 two work items
+    per patch).  Results must be bit-identical to one CTA per item."""
     from deepfit_b200 import DeepFit as D
     from deepfit_b200 import ops
     from oracle import deepfit_oracle as O
     g = torch.Generator().manual_seed(3)
-    B = 3000                                           # ~20 patches and ~40 head tiles per SM
-    xy = torch.rand((B, 2, 256), generator=g) * 1.4 - 0.7
+    xy = torch.rand((B, 2, k), generator=g) * 1.4 - 0.7
     c = torch.rand((B, 3, 1), generator=g) - 0.5
     zz = 0.3 * (c[:, 0:1] * xy[:, 0:1] ** 2 + c[:, 1:2] * xy[:, 1:2] ** 2 + c[:, 2:3] * xy[:, 0:1] * xy[:, 1:2])
     patch = torch.cat([xy, zz], 1).cuda().contiguous()
-    net = ops.WeightNetwork(D.fold_batchnorm(O.seeded_state_dict(0)), 256, "sigmoid", "bf16x3", max_batch=3072)
+    net = ops.WeightNetwork(D.fold_batchnorm(O.seeded_state_dict(0)), k, "sigmoid", "bf16x3", max_batch=max(B, 128))
     out = {}
     for name, head_p, chain_p in (("per_item", 0, 0), ("persistent", 1, 1)):
         dbg_switch(8, head_p, 1)
@@ -261,7 +263,7 @@ def test_persistent_kernels_match_one_cta_per_tile(dbg_switch):
         out[name] = (w.clone(), trans.clone(), t2.clone())
     for a, b in zip(out["per_item"], out["persistent"]):
         assert torch.equal(a, b)
-    # and the whole batch against the fp32 torch restatement on a sample of patches from every wave
+    # and against the fp32 torch restatement on a sample of patches from every wave
     sel = torch.arange(0, B, 149)
     wr, tr, t2r, _ = O.weight_network(O.seeded_state_dict(0), patch[sel].cpu())
     assert (out["persistent"][0][sel].cpu() - wr).abs().max() < 2e-3
