@@ -322,11 +322,11 @@ def main():
                                                       "one CTA per patch, 3 per forward)",
                          "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s",
                          "frac": (achieved / tf_sus) if achieved else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum per launch of 4096 patches, mean over the three chain
-                         # kernels of one forward (13.2 / 13.4 / 378.8 MB), from profiles/r1_ncu_full_chain_and_head.csv;
-                         # algorithmic bytes: 12.6 MB of patches (+ 128 MB per-patch T2 operands read and 256 MB x*T2
-                         # written by the encoder chain)
-                         "traffic": 135.1e6 * args.chunk / 4096,   # captured at 4096 patches per launch; every term scales with the patch count
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch of 16 384 patches, mean over the three chain
+                         # kernels of one forward (69 / 70 / 1 679 MB), from profiles/r1_ncu_full_chain_and_head.csv; every
+                         # term scales with the patch count.  Algorithmic bytes: 50 MB of patches (+ 0.5 GB per-patch T2
+                         # operands read and 1 GB x*T2 written by the encoder chain)
+                         "traffic": 606.1e6 * args.chunk / 16384,
                          "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained" % which,
                          "note": "achieved = algorithmic FLOPs of the three chain kernels (222.6 MFLOP/patch at k=256) / their CUDA-event "
                                  "time; parity precision bf16x3 executes 3x that on the tensor pipe, so frac tops out near 0.333 at the sustained clock the peak was measured at (short un-throttled runs exceed it)",
