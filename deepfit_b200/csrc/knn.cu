@@ -552,6 +552,116 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ ball query
+// Fixed-radius neighbourhoods (reference dataset.py:289-291, cKDTree.query_ball_point): every point with
+// d2 <= r*r, d2 evaluated exactly like the kNN key.  One warp per query walks the 27-cell block of the finest grid
+// level whose guaranteed-complete radius covers r.  Two passes over the same traversal: COUNT, then (after an exclusive
+// scan of the counts on the caller's side) FILL at the query's offset -- in traversal order, which is deterministic;
+// callers that need a canonical order sort each segment by index.
+struct BallArgs {
+    const float4* sorted;
+    const uint32_t* tab;
+    const float* pts;
+    const GridParams* gp;
+    const int* query;
+    long long q_begin, q_count;
+    const double* radius;   // per query, or NULL -> r
+    double r;
+    long long* count;       // COUNT pass
+    const long long* offsets;   // FILL pass
+    int* out_idx;
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(kKnnWarps * 32) ball_kernel(BallArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const GridParams gpar = *a.gp;
+    const int G = 1 << gpar.bits;
+    for (long long qw = (long long)blockIdx.x * kKnnWarps + warp; qw < a.q_count; qw += (long long)gridDim.x * kKnnWarps) {
+        const long long qi = a.query ? (long long)a.query[qw] : a.q_begin + qw;
+        const float qxf = a.pts[qi * 3], qyf = a.pts[qi * 3 + 1], qzf = a.pts[qi * 3 + 2];
+        const double qx = qxf, qy = qyf, qz = qzf;
+        const double r = a.radius ? a.radius[qw] : a.r;
+        const double r2 = r * r;
+        const float ux = cell_coord(qxf, gpar.minx, gpar.inv_cell), uy = cell_coord(qyf, gpar.miny, gpar.inv_cell),
+                    uz = cell_coord(qzf, gpar.minz, gpar.inv_cell);
+        const int ix = cell_index(ux, G), iy = cell_index(uy, G), iz = cell_index(uz, G);
+        // finest level whose block is guaranteed to contain the ball (sides on the domain boundary impose no limit)
+        int l = 0;
+        for (; l < gpar.bits; ++l) {
+            const int Gl = G >> l;
+            const float w = (float)(1 << l);
+            const float uu[3] = {ux, uy, uz};
+            const int cc[3] = {ix >> l, iy >> l, iz >> l};
+            float mrg = 3.0e38f;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                if (cc[t] - 1 > 0) mrg = fminf(mrg, uu[t] - (float)(cc[t] - 1) * w - kCellSlack);
+                if (cc[t] + 2 < Gl) mrg = fminf(mrg, (float)(cc[t] + 2) * w - uu[t] - kCellSlack);
+            }
+            if (mrg >= 3.0e38f) break;
+            const double mm = (double)fmaxf(mrg, 0.f) * (double)gpar.cell * (1.0 - 1e-6);
+            if (mm > r) break;
+        }
+        const int Gl = G >> l;
+        const int cx = ix >> l, cy = iy >> l, cz = iz >> l;
+        uint32_t lo = 0, hi = 0;
+        float cmin2 = 0.f;
+        if (lane < 27) {
+            const int ex = cx + (lane % 3) - 1, ey = cy + ((lane / 3) % 3) - 1, ez = cz + (lane / 9) - 1;
+            if (ex >= 0 && ey >= 0 && ez >= 0 && ex < Gl && ey < Gl && ez < Gl) {
+                const uint32_t m = morton3(ex, ey, ez);
+                const int sh = 3 * l;
+                if (sh >= 30) {
+                    lo = 0;
+                    hi = (uint32_t)gpar.n;
+                } else {
+                    lo = a.tab[(size_t)m << sh];
+                    hi = a.tab[((size_t)m + 1) << sh];
+                }
+                const float w = (float)(1 << l);
+                float dd[3];
+                const float uu[3] = {ux, uy, uz};
+                const int ee[3] = {ex, ey, ez};
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const float c0 = (float)ee[t] * w, c1 = c0 + w;
+                    float d = 0.f;
+                    if (uu[t] < c0) d = c0 - uu[t] - kCellSlack;
+                    else if (uu[t] > c1) d = uu[t] - c1 - kCellSlack;
+                    dd[t] = fmaxf(d, 0.f);
+                }
+                const float dc = gpar.cell * (1.f - 1e-5f);
+                cmin2 = (dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]) * dc * dc * (1.f - 1e-5f);
+            }
+        }
+        long long n = 0;
+        int* out = FILL ? a.out_idx + a.offsets[qw] : nullptr;
+        for (int c = 0; c < 27; ++c) {
+            const uint32_t clo = __shfl_sync(0xffffffffu, lo, c), chi = __shfl_sync(0xffffffffu, hi, c);
+            const float cm2 = __shfl_sync(0xffffffffu, cmin2, c);
+            if (chi <= clo || (double)cm2 > r2) continue;
+            for (uint32_t j0 = clo; j0 < chi; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                bool in = false;
+                int pidx = 0;
+                if (j < chi) {
+                    const float4 p = __ldg(a.sorted + j);
+                    const double dx = (double)p.x - qx, dy = (double)p.y - qy, dz = (double)p.z - qz;
+                    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                    pidx = __float_as_int(p.w);
+                    in = d2 <= r2;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                if (FILL && in) out[n + __popc(bal & ((1u << lane) - 1u))] = pidx;
+                n += __popc(bal);
+            }
+        }
+        if (!FILL && lane == 0) a.count[qw] = n;
+    }
+}
+
 }  // namespace
 }  // namespace dfb
 
@@ -683,4 +793,44 @@ extern "C" int dfb_knn(const dfb_grid* grid, const int32_t* d_query, int64_t q_b
     knn_kernel<<<(unsigned)blocks, kKnnWarps * 32, smem, as_stream(stream)>>>(a);
     note_launch();
     return check_cuda(cudaGetLastError(), "knn_kernel launch", __FILE__, __LINE__);
+}
+
+namespace dfb {
+namespace {
+int ball_launch(bool fill, const dfb_grid* grid, const int32_t* d_query, int64_t q_begin, int64_t q_count, const double* d_radius,
+                double radius, int64_t* d_count, const int64_t* d_offsets, int32_t* d_idx, dfb_stream stream) {
+    DFB_REQUIRE(grid != nullptr, DFB_E_ARG, "dfb_ball_*: grid is NULL");
+    DFB_REQUIRE(q_count >= 0, DFB_E_ARG, "dfb_ball_*: negative query count");
+    DFB_REQUIRE(d_radius != nullptr || radius >= 0.0, DFB_E_ARG, "dfb_ball_*: negative radius");
+    DFB_REQUIRE(d_query != nullptr || (q_begin >= 0 && q_begin + q_count <= grid->n), DFB_E_ARG,
+                "dfb_ball_*: query range [%lld,%lld) outside the cloud", (long long)q_begin, (long long)(q_begin + q_count));
+    if (q_count == 0) return DFB_OK;
+    DFB_REQUIRE(fill ? (d_offsets != nullptr && d_idx != nullptr) : d_count != nullptr, DFB_E_ARG, "dfb_ball_*: NULL output");
+    BallArgs a;
+    a.sorted = grid->sorted; a.tab = grid->tab; a.pts = grid->pts; a.gp = grid->params;
+    a.query = d_query; a.q_begin = q_begin; a.q_count = q_count;
+    a.radius = d_radius; a.r = radius;
+    a.count = reinterpret_cast<long long*>(d_count);
+    a.offsets = reinterpret_cast<const long long*>(d_offsets);
+    a.out_idx = d_idx;
+    long long blocks = (q_count + kKnnWarps - 1) / kKnnWarps;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (fill) ball_kernel<true><<<(unsigned)blocks, kKnnWarps * 32, 0, as_stream(stream)>>>(a);
+    else ball_kernel<false><<<(unsigned)blocks, kKnnWarps * 32, 0, as_stream(stream)>>>(a);
+    note_launch();
+    return check_cuda(cudaGetLastError(), "ball_kernel launch", __FILE__, __LINE__);
+}
+}  // namespace
+}  // namespace dfb
+
+extern "C" int dfb_ball_count(const dfb_grid* grid, const int32_t* d_query, int64_t q_begin, int64_t q_count,
+                              const double* d_radius, double radius, int64_t* d_count, dfb_stream stream) {
+    return dfb::ball_launch(false, grid, d_query, q_begin, q_count, d_radius, radius, d_count, nullptr, nullptr, stream);
+}
+
+extern "C" int dfb_ball_fill(const dfb_grid* grid, const int32_t* d_query, int64_t q_begin, int64_t q_count,
+                             const double* d_radius, double radius, const int64_t* d_offsets, int32_t* d_idx,
+                             dfb_stream stream) {
+    return dfb::ball_launch(true, grid, d_query, q_begin, q_count, d_radius, radius, nullptr, d_offsets, d_idx, stream);
 }

@@ -81,6 +81,43 @@ class Grid:
                                            _stream(self.device)))
         return (idx, rad, dist) if return_dist else (idx, rad)
 
+    def ball_query(self, radius, q_begin: int = 0, q_count: Optional[int] = None, query: Optional[torch.Tensor] = None,
+                   sort: bool = True):
+        """Every point within ``radius`` (a float, or an f64 tensor with one radius per query) of points
+        ``q_begin .. q_begin+q_count`` (or of the int32 index tensor ``query``): the set
+        ``cKDTree.query_ball_point`` returns (reference dataset.py:289-291).  Returns
+        (offsets i64 [Q+1], idx i32 [offsets[-1]]): the neighbours of query q are ``idx[offsets[q]:offsets[q+1]]``,
+        ascending by point index when ``sort`` (the reference's order is the tree's traversal order)."""
+        if query is not None:
+            query = _chk(query, torch.int32, "query")
+            q_count = int(query.numel())
+        elif q_count is None:
+            q_count = self.n - q_begin
+        rad_t = None
+        r = 0.0
+        if isinstance(radius, torch.Tensor):
+            rad_t = _chk(radius, torch.float64, "radius")
+            if rad_t.numel() != q_count:
+                raise ValueError("radius tensor must hold one radius per query")
+        else:
+            r = float(radius)
+        lib = _lib.load()
+        count = torch.empty((q_count,), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.dfb_ball_count(self._h, _p(query), q_begin, q_count, _p(rad_t), r, _p(count), _stream(self.device)))
+            offsets = torch.zeros((q_count + 1,), dtype=torch.int64, device=self.device)
+            torch.cumsum(count, 0, out=offsets[1:])
+            total = int(offsets[-1].item()) if q_count else 0
+            idx = torch.empty((total,), dtype=torch.int32, device=self.device)
+            if total:
+                _lib.check(lib.dfb_ball_fill(self._h, _p(query), q_begin, q_count, _p(rad_t), r, _p(offsets), _p(idx),
+                                             _stream(self.device)))
+                if sort:   # canonical order: (query, index); not the hot path, so the library sort does it
+                    seg = torch.repeat_interleave(torch.arange(q_count, device=self.device), count)
+                    key = seg * int(self.n) + idx.long()
+                    idx = (torch.sort(key)[0] - seg * int(self.n)).to(torch.int32)
+        return offsets, idx
+
 
 def patch_pca(points: torch.Tensor, idx: torch.Tensor, rad: Optional[torch.Tensor], q_begin: int = 0,
               query: Optional[torch.Tensor] = None, scale: bool = True, pca: bool = True):

@@ -79,6 +79,19 @@ DFB_API int dfb_grid_destroy(dfb_grid* grid);
 DFB_API int dfb_knn(const dfb_grid* grid, const int32_t* d_query, int64_t q_begin, int64_t q_count, int32_t k,
             int32_t* d_idx, double* d_dist, double* d_rad, dfb_stream stream);
 
+/* Fixed-radius neighbourhoods: every point with d2 <= r*r (d2 as in dfb_knn), i.e. the SET that
+ * cKDTree.query_ball_point returns (reference dataset.py:289-291, neighbor_search_method='r'; the reference's
+ * element ORDER is the tree's traversal order and is not reproduced).  Two passes:
+ *   dfb_ball_count  d_count i64[q_count] = neighbours per query;
+ *   (caller: exclusive scan -> d_offsets i64[q_count], allocates d_idx i32[sum])
+ *   dfb_ball_fill   d_idx[d_offsets[q] ...] = the neighbour indices of query q, in a deterministic grid order.
+ * Radius: d_radius f64[q_count] per query, or NULL -> the scalar `radius` for all. */
+DFB_API int dfb_ball_count(const dfb_grid* grid, const int32_t* d_query, int64_t q_begin, int64_t q_count,
+                   const double* d_radius, double radius, int64_t* d_count, dfb_stream stream);
+DFB_API int dfb_ball_fill(const dfb_grid* grid, const int32_t* d_query, int64_t q_begin, int64_t q_count,
+                  const double* d_radius, double radius, const int64_t* d_offsets, int32_t* d_idx,
+                  dfb_stream stream);
+
 /* ------------------------------------------------------------------------------------------
  * Stage 2 -- patch centring, scaling and PCA alignment.
  * Replaces SinglePointCloudDataset.__getitem__ lines tutorial/tutorial_utils.py:23-30 and

@@ -131,3 +131,55 @@ def test_knn_full_size_properties():
         val, order = torch.sort(d2, stable=True)                         # stable => ties by ascending index
         assert bool((order[:k] == idx[j].long()).all()), "query %d" % j
         assert bool((torch.sqrt(val[:k]) == dist[j]).all())
+
+
+def _ball_sets(pts_np, q, radius):
+    from deepfit_b200 import ops
+    pts = torch.from_numpy(np.ascontiguousarray(pts_np)).cuda()
+    grid = ops.Grid(pts)
+    qt = torch.from_numpy(np.asarray(q, dtype=np.int32)).cuda()
+    rad = torch.from_numpy(np.asarray(radius, dtype=np.float64)).cuda() if np.ndim(radius) else float(radius)
+    off, idx = grid.ball_query(rad, query=qt)
+    off, idx = off.cpu().numpy(), idx.cpu().numpy()
+    return [idx[off[i]:off[i + 1]] for i in range(len(q))]
+
+
+@pytest.mark.parametrize("name", CLOUD_NAMES)
+def test_ball_query_matches_ckdtree_sets(clouds, name):
+    """neighbor_search_method='r' (reference dataset.py:289-291): the SET cKDTree.query_ball_point returns, for the
+    radii PCPNet uses (fractions of the bounding-box diagonal of the raw cloud), bit for bit."""
+    import scipy.spatial as spatial
+    pts = clouds[name]
+    tree = spatial.cKDTree(pts, 10)
+    bbdiag = float(np.linalg.norm(pts.max(0) - pts.min(0), 2))
+    rng = np.random.default_rng(17)
+    q = rng.choice(len(pts), 64, replace=False)
+    for frac in (0.01, 0.03, 0.05):
+        rad = bbdiag * frac
+        ours = _ball_sets(pts, q, rad)
+        for i, c in enumerate(q):
+            ref = np.sort(np.asarray(tree.query_ball_point(pts[c, :], rad), dtype=np.int32))
+            assert np.array_equal(ours[i], ref), (name, frac, int(c), len(ours[i]), len(ref))
+    # one radius per query
+    rads = bbdiag * rng.uniform(0.005, 0.06, size=len(q))
+    ours = _ball_sets(pts, q, rads)
+    for i, c in enumerate(q):
+        ref = np.sort(np.asarray(tree.query_ball_point(pts[c, :], float(rads[i])), dtype=np.int32))
+        assert np.array_equal(ours[i], ref)
+
+
+def test_ball_query_edge_cases():
+    import scipy.spatial as spatial
+    g = np.stack(np.meshgrid(np.arange(12), np.arange(12), np.arange(12), indexing="ij"), -1).reshape(-1, 3)
+    lattice = (g.astype(np.float32) * 0.125)
+    rng = np.random.default_rng(23)
+    base = rng.normal(size=(2000, 3)).astype(np.float32)
+    dup = np.concatenate([base, base])[rng.permutation(4000)]
+    for pts, radii in ((lattice, (0.0, 0.125, 0.125 * np.sqrt(2.0), 0.3, 10.0)), (dup, (0.0, 1e-9, 0.2, 100.0))):
+        tree = spatial.cKDTree(pts, 10)
+        q = rng.choice(len(pts), 48, replace=False)
+        for r in radii:
+            ours = _ball_sets(pts, q, float(r))
+            for i, c in enumerate(q):
+                ref = np.sort(np.asarray(tree.query_ball_point(pts[c, :], float(r)), dtype=np.int32))
+                assert np.array_equal(ours[i], ref), (float(r), int(c), len(ours[i]), len(ref))
