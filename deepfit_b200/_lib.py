@@ -26,7 +26,7 @@ PRECISION = {"bf16x3": 0, "bf16": 1}
 EXPORTS = [
     "dfb_abi_version", "dfb_last_error_string", "dfb_device_check",
     "dfb_grid_create", "dfb_grid_update", "dfb_grid_destroy", "dfb_knn", "dfb_ball_count", "dfb_ball_fill",
-    "dfb_patch_pca",
+    "dfb_patch_pca", "dfb_patch_pca_ragged",
     "dfb_model_create", "dfb_model_destroy", "dfb_model_forward", "dfb_model_status",
     "dfb_model_profile", "dfb_model_profile_read", "dfb_launch_count",
     "dfb_wls_fit", "dfb_principal_curvatures", "dfb_neighbor_normals",
@@ -86,6 +86,7 @@ def load():
     lib.dfb_ball_count.argtypes = [vp, vp, i64, i64, vp, C.c_double, vp, vp]
     lib.dfb_ball_fill.argtypes = [vp, vp, i64, i64, vp, C.c_double, vp, vp, vp]
     lib.dfb_patch_pca.argtypes = [vp, i64, vp, vp, i64, i64, i32, vp, i32, vp, vp, vp]
+    lib.dfb_patch_pca_ragged.argtypes = [vp, i64, vp, vp, vp, i64, i64, i32, vp, i32, vp, vp, vp]
     lib.dfb_model_create.argtypes = [C.POINTER(DfbModelDesc), vp, C.POINTER(vp)]
     lib.dfb_model_destroy.argtypes = [vp]
     lib.dfb_model_forward.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp]

@@ -27,6 +27,7 @@ struct PcaArgs {
     int scale, do_pca;
     float* patch;
     float* U;
+    const int* valid;   // NULL, or per patch the number of leading real neighbours: the rest are padding (zero rows)
 };
 
 __device__ __forceinline__ void jacobi_rotate(double (&A)[3][3], double (&V)[3][3], int p, int q) {
@@ -59,13 +60,14 @@ __global__ void __launch_bounds__(kPcaWarps * 32) pca_kernel(PcaArgs a) {
         const float cx = a.pts[ci * 3], cy = a.pts[ci * 3 + 1], cz = a.pts[ci * 3 + 2];
         const float r32 = a.scale ? (float)a.rad[qw] : 1.f;
         const int* row = a.idx + qw * (long long)k;
+        const int nv = a.valid ? min(max(a.valid[qw], 0), k) : k;   // rows >= nv are zero padding, outside mean / covariance
         float X[NPL], Y[NPL], Z[NPL];
         double sx = 0.0, sy = 0.0, sz = 0.0;
 #pragma unroll
         for (int t = 0; t < NPL; ++t) {
             const int j = lane + 32 * t;
             X[t] = Y[t] = Z[t] = 0.f;
-            if (j < k) {
+            if (j < nv) {
                 const long long pi = row[j];
                 float x = a.pts[pi * 3] - cx, y = a.pts[pi * 3 + 1] - cy, z = a.pts[pi * 3 + 2] - cz;
                 if (a.scale) {
@@ -86,11 +88,11 @@ __global__ void __launch_bounds__(kPcaWarps * 32) pca_kernel(PcaArgs a) {
             continue;
         }
         sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
-        const double mx = sx / k, my = sy / k, mz = sz / k;
+        const double mx = sx / max(nv, 1), my = sy / max(nv, 1), mz = sz / max(nv, 1);
         double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0;
 #pragma unroll
         for (int t = 0; t < NPL; ++t) {
-            if (lane + 32 * t < k) {
+            if (lane + 32 * t < nv) {
                 const double dx = X[t] - mx, dy = Y[t] - my, dz = Z[t] - mz;
                 c00 += dx * dx; c01 += dx * dy; c02 += dx * dz;
                 c11 += dy * dy; c12 += dy * dz; c22 += dz * dz;
@@ -155,9 +157,9 @@ __global__ void __launch_bounds__(kPcaWarps * 32) pca_kernel(PcaArgs a) {
 }  // namespace
 }  // namespace dfb
 
-extern "C" int dfb_patch_pca(const float* d_points, int64_t n_points, const int32_t* d_idx, const int32_t* d_query,
-                             int64_t q_begin, int64_t q_count, int32_t k, const double* d_rad, int32_t scale_by_rad,
-                             float* d_patch, float* d_U, dfb_stream stream) {
+extern "C" int dfb_patch_pca_ragged(const float* d_points, int64_t n_points, const int32_t* d_idx, const int32_t* d_valid,
+                                    const int32_t* d_query, int64_t q_begin, int64_t q_count, int32_t k, const double* d_rad,
+                                    int32_t scale_by_rad, float* d_patch, float* d_U, dfb_stream stream) {
     using namespace dfb;
     DFB_REQUIRE(k >= 1 && k <= 32 * kMaxPerLane, DFB_E_ARG, "dfb_patch_pca: k=%d out of range (1..1024)", k);
     DFB_REQUIRE(q_count >= 0, DFB_E_ARG, "dfb_patch_pca: negative q_count");
@@ -168,7 +170,7 @@ extern "C" int dfb_patch_pca(const float* d_points, int64_t n_points, const int3
                 "dfb_patch_pca: query range outside the cloud");
     int rc = dfb_device_check();
     if (rc) return rc;
-    PcaArgs a{d_points, d_idx, d_query, q_begin, q_count, k, d_rad, scale_by_rad & 1, (scale_by_rad & 2) ? 0 : 1, d_patch, d_U};
+    PcaArgs a{d_points, d_idx, d_query, q_begin, q_count, k, d_rad, scale_by_rad & 1, (scale_by_rad & 2) ? 0 : 1, d_patch, d_U, d_valid};
     long long blocks = (q_count + kPcaWarps - 1) / kPcaWarps;
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
@@ -180,4 +182,11 @@ extern "C" int dfb_patch_pca(const float* d_points, int64_t n_points, const int3
     else pca_kernel<32><<<(unsigned)blocks, kPcaWarps * 32, 0, st>>>(a);
     note_launch();
     return check_cuda(cudaGetLastError(), "pca_kernel launch", __FILE__, __LINE__);
+}
+
+extern "C" int dfb_patch_pca(const float* d_points, int64_t n_points, const int32_t* d_idx, const int32_t* d_query,
+                             int64_t q_begin, int64_t q_count, int32_t k, const double* d_rad, int32_t scale_by_rad,
+                             float* d_patch, float* d_U, dfb_stream stream) {
+    return dfb_patch_pca_ragged(d_points, n_points, d_idx, nullptr, d_query, q_begin, q_count, k, d_rad, scale_by_rad, d_patch, d_U,
+                                stream);
 }

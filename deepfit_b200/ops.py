@@ -120,8 +120,11 @@ class Grid:
 
 
 def patch_pca(points: torch.Tensor, idx: torch.Tensor, rad: Optional[torch.Tensor], q_begin: int = 0,
-              query: Optional[torch.Tensor] = None, scale: bool = True, pca: bool = True):
-    """(points[idx] - points[centre]) / rad, PCA-aligned.  Returns (patch f32 [Q,3,k], U f32 [Q,3,3])."""
+              query: Optional[torch.Tensor] = None, scale: bool = True, pca: bool = True,
+              valid: Optional[torch.Tensor] = None):
+    """(points[idx] - points[centre]) / rad, PCA-aligned.  Returns (patch f32 [Q,3,k], U f32 [Q,3,3]).
+    ``valid`` (i32 [Q]): only the first ``valid[q]`` neighbours of a row are real; the other rows of the patch are
+    zero padding outside the PCA (ball-query patches with fewer than k points)."""
     points = _chk(points, torch.float32, "points")
     idx = _chk(idx, torch.int32, "idx")
     q, k = int(idx.shape[0]), int(idx.shape[1])
@@ -129,12 +132,16 @@ def patch_pca(points: torch.Tensor, idx: torch.Tensor, rad: Optional[torch.Tenso
         rad = _chk(rad, torch.float64, "rad")
     if query is not None:
         query = _chk(query, torch.int32, "query")
+    if valid is not None:
+        valid = _chk(valid, torch.int32, "valid")
+        if valid.numel() != q:
+            raise ValueError("valid must hold one count per patch")
     patch = torch.empty((q, 3, k), dtype=torch.float32, device=points.device)
     U = torch.empty((q, 3, 3), dtype=torch.float32, device=points.device)
     flags = (1 if scale else 0) | (0 if pca else 2)
     with torch.cuda.device(points.device):
-        _lib.check(_lib.load().dfb_patch_pca(_p(points), int(points.shape[0]), _p(idx), _p(query), q_begin, q, k,
-                                             _p(rad), flags, _p(patch), _p(U), _stream(points.device)))
+        _lib.check(_lib.load().dfb_patch_pca_ragged(_p(points), int(points.shape[0]), _p(idx), _p(valid), _p(query), q_begin, q, k,
+                                                    _p(rad), flags, _p(patch), _p(U), _stream(points.device)))
     return patch, U
 
 

@@ -4,9 +4,14 @@ Mirrors the k-nearest-neighbour path of the reference's ``PointcloudPatchDataset
 raw un-normalised points, ``center='point'``, patch scaled by the k-th neighbour distance, optional PCA,
 optional sparse ``.pidx`` centres, sequential order) and the export loop of ``test_c_est.py:104-218``
 (per shape ``.normals [P,3] .curv [P,2] .weights [P,k] .beta [P,M] .trans [P,9]`` via ``np.savetxt``).
-Ball-query neighbourhoods, point tuples, density jitter and ground-truth features are training-time
-options and raise.  Unlike the reference nothing is written next to the input data (it drops ``.npy``
-copies into the dataset directory, dataset.py:227-264).
+``neighbor_search_method='r'`` (dataset.py:289-311, fixed-radius balls of ``patch_radius`` x bounding-box
+diagonal, random subsample when the ball holds more than ``points_per_patch`` points, zero padding when fewer) is
+supported for one scale; the ball is the exact set ``cKDTree.query_ball_point`` returns, but its elements are
+taken in ascending index order where the reference takes the tree's traversal order, so the seeded
+``RandomState`` subsample picks different members of the same ball (documented deviation: the traversal
+order of scipy's tree cannot be reproduced).  Point tuples, density jitter and ground-truth features are
+training-time options and raise.  Unlike the reference nothing is written next to the input data (it drops
+``.npy`` copies into the dataset directory, dataset.py:227-264).
 """
 from __future__ import annotations
 
@@ -25,8 +30,17 @@ class PointcloudPatchDataset:
     def __init__(self, root, shape_list_filename, patch_radius=None, points_per_patch=256, patch_features=(),
                  seed=None, identical_epochs=False, use_pca=False, center='point', point_tuple=1, cache_capacity=1,
                  point_count_std=0.0, sparse_patches=False, neighbor_search_method='k', device="cuda"):
-        if neighbor_search_method != 'k':
-            raise NotImplementedError("only neighbor_search_method='k' is built (ball query is next, SURVEY 8f-3)")
+        if neighbor_search_method not in ('k', 'r'):
+            raise ValueError("neighbor_search_method must be 'k' or 'r'")
+        if neighbor_search_method == 'r':
+            if patch_radius is None or len(patch_radius) != 1:
+                raise NotImplementedError("ball-query patches are built for exactly one patch_radius (one scale)")
+        self.neighbor_search_method = neighbor_search_method
+        self.patch_radius = None if patch_radius is None else [float(r) for r in patch_radius]
+        self.identical_epochs = bool(identical_epochs)
+        # rng for picking points in a patch, dataset.py:217-220
+        self.seed = int(np.random.randint(0, 2**32 - 1)) if seed is None else int(seed)
+        self.rng = np.random.RandomState(self.seed)
         if center != 'point':
             raise NotImplementedError("only center='point' is built (the pretrained configuration)")
         if point_tuple != 1 or point_count_std != 0.0:
@@ -49,6 +63,7 @@ class PointcloudPatchDataset:
                 self._pidx.append(None)
                 self.shape_patch_count.append(None)   # filled when the shape is loaded
         self._loaded = (-1, None, None)
+        self._bbdiag = {}
 
     def __len__(self):
         return sum(self._count(i) for i in range(len(self.shape_names)))
@@ -66,6 +81,7 @@ class PointcloudPatchDataset:
             if self._loaded[2] is not None:
                 self._loaded[2].close()
             self._loaded = (shape_ind, gpu, ops.Grid(gpu))
+            self._bbdiag[shape_ind] = float(np.linalg.norm(pts.max(0) - pts.min(0), 2))   # dataset.py:262
             if self.shape_patch_count[shape_ind] is None:
                 self.shape_patch_count[shape_ind] = int(gpu.shape[0])
         return self._loaded[1], self._loaded[2]
@@ -81,6 +97,8 @@ class PointcloudPatchDataset:
         pts, grid = self.load_shape(shape_ind)
         centres = self.centres(shape_ind)
         k = self.points_per_patch
+        if self.neighbor_search_method == 'r':
+            return self._ball_patches(shape_ind, pts, grid, centres, start, count)
         if centres is None:
             idx, rad = grid.query(k, q_begin=start, q_count=count)
             patch, trans = ops.patch_pca(pts, idx, rad, q_begin=start, pca=self.use_pca)
@@ -88,6 +106,43 @@ class PointcloudPatchDataset:
             q = centres[start:start + count].contiguous()
             idx, rad = grid.query(k, query=q)
             patch, trans = ops.patch_pca(pts, idx, rad, query=q, pca=self.use_pca)
+        return patch, trans, rad
+
+
+    def _ball_patches(self, shape_ind, pts, grid, centres, start, count):
+        """dataset.py:289-334 for neighbor_search_method='r': the ball of radius patch_radius * bbdiag, a seeded random
+        subset when it holds more than points_per_patch points, zero rows when fewer; scale = the radius."""
+        k = self.points_per_patch
+        rad_abs = self._bbdiag[shape_ind] * self.patch_radius[0]
+        if centres is None:
+            q_idx = np.arange(start, start + count, dtype=np.int64)
+            offsets, ball = grid.ball_query(rad_abs, q_begin=start, q_count=count)
+        else:
+            q = centres[start:start + count].contiguous()
+            q_idx = q.cpu().numpy().astype(np.int64)
+            offsets, ball = grid.ball_query(rad_abs, query=q)
+        off = offsets.cpu().numpy()
+        ball_h = ball.cpu().numpy()
+        sel = np.empty((count, k), dtype=np.int32)
+        valid = np.empty((count,), dtype=np.int32)
+        base = sum(self._count(i) for i in range(shape_ind))   # global patch index, for identical_epochs
+        for i in range(count):
+            inds = ball_h[off[i]:off[i + 1]]
+            if self.identical_epochs:
+                self.rng.seed((self.seed + base + start + i) % (2**32))
+            point_count = int(min(k, len(inds)))
+            if point_count < len(inds):
+                inds = inds[self.rng.choice(len(inds), point_count, replace=False)]
+            sel[i, :point_count] = inds
+            sel[i, point_count:] = q_idx[i]     # padding: the centre itself, i.e. a zero row after centring
+            valid[i] = point_count
+        idx = torch.from_numpy(sel).to(self.device)
+        valid_t = torch.from_numpy(valid).to(self.device)
+        rad = torch.full((count,), rad_abs, dtype=torch.float64, device=self.device)
+        if centres is None:
+            patch, trans = ops.patch_pca(pts, idx, rad, q_begin=start, pca=self.use_pca, valid=valid_t)
+        else:
+            patch, trans = ops.patch_pca(pts, idx, rad, query=q, pca=self.use_pca, valid=valid_t)
         return patch, trans, rad
 
 
@@ -153,7 +208,9 @@ def main(argv=None):
     params = torch.load(os.path.join(args.trained_model_path, 'DeepFit_params.pth'), weights_only=False)
     sd = torch.load(os.path.join(args.trained_model_path, 'DeepFit.pth'), map_location='cpu')
     model = model_from_state_dict(sd, params.points_per_patch, params.jet_order, params.weight_mode, args.precision, dev)
-    ds = PointcloudPatchDataset(args.indir, args.testset, points_per_patch=params.points_per_patch,
+    ds = PointcloudPatchDataset(args.indir, args.testset, patch_radius=getattr(params, 'patch_radius', None),
+                                points_per_patch=params.points_per_patch, seed=getattr(params, 'seed', None),
+                                identical_epochs=bool(getattr(params, 'identical_epochs', False)),
                                 use_pca=params.use_pca, sparse_patches=bool(args.sparse_patches),
                                 neighbor_search_method=params.neighbor_search, device=dev)
     estimate_shapes(ds, model, args.outdir, batch=args.batchSize, use_point_stn=bool(params.use_point_stn))

@@ -106,6 +106,13 @@ DFB_API int dfb_ball_fill(const dfb_grid* grid, const int32_t* d_query, int64_t 
 DFB_API int dfb_patch_pca(const float* d_points, int64_t n_points, const int32_t* d_idx, const int32_t* d_query,
                   int64_t q_begin, int64_t q_count, int32_t k, const double* d_rad, int32_t flags,
                   float* d_patch, float* d_U, dfb_stream stream);
+/* Same with ragged neighbourhoods (ball queries with fewer than k points, reference dataset.py:297-366): only the
+ * first d_valid[q] entries of a row of d_idx are real neighbours; the remaining rows of the patch are zero padding
+ * and take no part in the PCA mean / covariance.  d_valid == NULL -> every row is full. */
+DFB_API int dfb_patch_pca_ragged(const float* d_points, int64_t n_points, const int32_t* d_idx, const int32_t* d_valid,
+                         const int32_t* d_query, int64_t q_begin, int64_t q_count, int32_t k, const double* d_rad,
+                         int32_t scale_by_rad, float* d_patch, float* d_U, dfb_stream stream);
+
 
 /* ------------------------------------------------------------------------------------------
  * Stage 3 -- the point-weight network (QSTN + feature STN + PointNet encoder + weight head).

@@ -236,3 +236,59 @@ def test_cli_deepfit_mode_with_saved_model(clouds, tmp_path):
                           "--trained_model_path", str(mdir), "--k_neighbors", "256", "--ref-compat"])
     nrm2 = np.loadtxt(tmp_path / "out2" / "part.normals")
     assert O.unoriented_angle_deg(nrm, nrm2).max() > 0.1
+
+
+@pytest.mark.parametrize("use_pca", [False, True])
+def test_pcpnet_ball_query_patches(tmp_path, use_pca):
+    """neighbor_search_method='r' (reference dataset.py:289-366) on raw PCPNet-shaped clouds: the ball of
+    patch_radius x bounding-box diagonal, seeded RandomState subsample when it is larger than points_per_patch, zero
+    padding when smaller, PCA over the real points only.  The restatement below is the reference's code path with the
+    ball in ascending index order (the documented deviation: scipy's traversal order is not reproducible)."""
+    import scipy.spatial as spatial
+    from deepfit_b200 import pcpnet, synthetic
+    root = str(tmp_path / "pclouds")
+    names = synthetic.write_pcpnet_like(root, n_shapes=2, n_points=20000, n_sparse=150)
+    k, seed = 256, 3627473
+    for radius in (0.012, 0.06):          # ~60 points per ball (padding) and ~1500 (subsampling)
+        ds = pcpnet.PointcloudPatchDataset(root, "testset_synthetic.txt", patch_radius=[radius], points_per_patch=k,
+                                           seed=seed, use_pca=use_pca, sparse_patches=True, neighbor_search_method='r')
+        rng = np.random.RandomState(seed)
+        saw_pad = saw_sub = False
+        for si, name in enumerate(names):
+            patch, trans, rad = ds.patches(si, 0, 150)
+            patch, trans = patch.cpu(), trans.cpu()
+            pts = np.loadtxt(os.path.join(root, name + ".xyz")).astype("float32")
+            pidx = np.loadtxt(os.path.join(root, name + ".pidx")).astype("int")
+            tree = spatial.cKDTree(pts, 10)
+            bbdiag = float(np.linalg.norm(pts.max(0) - pts.min(0), 2))
+            r_abs = bbdiag * radius
+            assert float(rad[0]) == r_abs
+            for i, c in enumerate(pidx):
+                inds = np.sort(np.array(tree.query_ball_point(pts[c, :], r_abs)))
+                count = int(min(k, len(inds)))
+                if count < len(inds):
+                    inds = inds[rng.choice(len(inds), count, replace=False)]
+                    saw_sub = True
+                saw_pad = saw_pad or count < k
+                ref = torch.zeros(k, 3)
+                ref[:count] = torch.from_numpy(pts[inds, :]) - torch.from_numpy(pts[c, :])
+                ref[:count] = ref[:count] / r_abs
+                ours = patch[i].t()                                   # [k,3]
+                if not use_pca:
+                    assert torch.equal(ours, ref), (name, i, count)
+                    assert torch.equal(trans[i], torch.eye(3))
+                else:
+                    assert bool((ours[count:] == 0).all())            # padding stays exactly zero
+                    U = trans[i].double()
+                    assert (U.t() @ U - torch.eye(3, dtype=torch.float64)).abs().max() < 1e-6
+                    assert (ref.double() @ U - ours.double()).abs().max() < 2e-6
+                    cen = ref[:count].double() - ref[:count].double().mean(0)
+                    D = U.t() @ (cen.t() @ cen) @ U                  # frame of the REAL points only
+                    off = D - torch.diag(torch.diagonal(D))
+                    assert off.abs().max() < 1e-5 * (cen.t() @ cen).abs().max()
+        assert saw_pad if radius < 0.03 else saw_sub
+    # and the export loop runs on ball-query patches (classic fit; curvature scaled by the ball radius)
+    res = pcpnet.estimate_shapes(ds, None, str(tmp_path / "out"), jet_order=3, batch=64, write=False)
+    for name in names:
+        assert res[name]["normals"].shape == (150, 3) and np.isfinite(res[name]["normals"]).all()
+        assert np.isfinite(res[name]["curv"]).all()
