@@ -268,3 +268,27 @@ def test_persistent_kernels_match_one_cta_per_tile(dbg_switch, B, k):
     wr, tr, t2r, _ = O.weight_network(O.seeded_state_dict(0), patch[sel].cpu())
     assert (out["persistent"][0][sel].cpu() - wr).abs().max() < 2e-3
     assert (out["persistent"][1][sel].cpu() - tr).abs().max() < 2e-4
+
+
+@pytest.mark.parametrize("k", [128, 384, 512])
+def test_network_other_neighbourhood_sizes(k):
+    """k = 128 and 512 run the fused chain kernels (one tile / two 256-point work items per patch), k = 384 the generic
+    kernels; all against the fp32 torch restatement."""
+    from deepfit_b200 import DeepFit as D
+    from deepfit_b200 import ops
+    from oracle import deepfit_oracle as O
+    g = torch.Generator().manual_seed(11)
+    B = 40
+    xy = torch.rand((B, 2, k), generator=g) * 1.4 - 0.7
+    c = torch.rand((B, 3, 1), generator=g) - 0.5
+    zz = 0.3 * (c[:, 0:1] * xy[:, 0:1] ** 2 + c[:, 1:2] * xy[:, 1:2] ** 2 + c[:, 2:3] * xy[:, 0:1] * xy[:, 1:2])
+    patch = torch.cat([xy, zz], 1).contiguous()
+    sd = O.seeded_state_dict(0)
+    net = ops.WeightNetwork(D.fold_batchnorm(sd), k, "sigmoid", "bf16x3", max_batch=128)
+    w, trans, t2, pts = net.forward(patch.cuda(), want_trans2=True, want_points=True)
+    net.status()
+    wr, tr, t2r, pr = O.weight_network(sd, patch)
+    assert (trans.cpu() - tr).abs().max() < 2e-4
+    assert (t2.cpu() - t2r).abs().max() < 2e-3
+    assert (pts.cpu() - pr).abs().max() < 2e-4
+    assert (w.cpu() - wr).abs().max() < 2e-3
