@@ -678,7 +678,8 @@ struct HeadArgs {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Tail helpers of the fused head, templated on the column so that every bias / weight is a constant-bank operand.
-// 32 columns of the layer-2 accumulator -> bias, ReLU, bf16 hi/lo split -> layer 3's A operand in tensor memory
+// 32 columns of the layer-2 accumulator -> bias, ReLU, bf16 hi/lo split -> layer 3's A operand, IN PLACE: the 32 fp32
+// columns become [hi 16 | lo 16] packed columns
 template <int C0>
 __device__ __forceinline__ void head_convert32(const HeadArgs& g, uint32_t tmem_row) {
     uint32_t v[32], ph[16], pl[16];
@@ -689,35 +690,36 @@ __device__ __forceinline__ void head_convert32(const HeadArgs& g, uint32_t tmem_
         const float x1 = fmaxf(__uint_as_float(v[2 * e + 1]) + g.b2c[C0 + 2 * e + 1], 0.f);
         split_pair(x0, x1, ph[e], pl[e]);
     }
-    tmem_st16(tmem_row + 256u + (uint32_t)(C0 >> 1), ph);
-    if (g.nprod > 1) tmem_st16(tmem_row + 384u + (uint32_t)(C0 >> 1), pl);
+    tmem_st16(tmem_row + (uint32_t)C0, ph);
+    if (g.nprod > 1) tmem_st16(tmem_row + (uint32_t)C0 + 16u, pl);
     tmem_st_wait();
     tc_fence_before();
 }
-// partial ReLU(conv3) . w4 over 32 of the 128 layer-3 channels
+// partial ReLU(conv3) . w4 over 32 of the 128 layer-3 channels (D3 lives at columns [256,384))
 template <int C0>
 __device__ __forceinline__ float head_dot32(const HeadArgs& g, uint32_t tmem_row) {
     uint32_t v[32];
-    tmem_ld32(tmem_row + (uint32_t)C0, v);
+    tmem_ld32(tmem_row + 256u + (uint32_t)C0, v);
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) dot = fmaf(fmaxf(__uint_as_float(v[i]) + g.b3c[C0 + i], 0.f), g.w4c[C0 + i], dot);
     return dot;
 }
 
-// Fused head: 64->512 (+ per-patch global bias) -> 512->256 -> 256->128 -> 128->1 -> weight map, one 128-row tile per CTA.
-// The loop over the eight 64-channel chunks of layer 1 used to be bound by shared-memory bandwidth (operand reads of
-// both MMAs + TMA fills + the epilogue's stores: ~330 KB per chunk at 128 B/clk).  Now every A operand lives in
-// tensor memory: the tile of point features is loaded straight from global memory into TMEM once, each layer-1
-// accumulator is converted IN PLACE into the bf16 hi/lo A operand of layer 2, and layer 2's accumulator likewise
-// becomes layer 3's A operand.  Shared memory only holds streamed weights.
-//   TMEM (512 columns): D2 [0,256) | pf hi [256,288) lo [288,320) | three D1/h1 buffers of 64 columns [320,512)
-//                       tail: h2 hi [256,384) lo [384,512), D3 over D2's [0,128)
-//   smem (224 KB): W3A 32 KB (W3 k-block 0) | W1R 2 x 16 KB ring (W3 k-block 3 in the tail) | W3B 64 KB (W3 k-blocks
-//                  1, 2) | W2R 3 x 32 KB ring
+// Fused head: 64->512 (+ per-patch global bias) -> 512->256 -> 256->128 -> 128->1 -> weight map; persistent CTAs, one
+// 128-row tile per iteration.  Every A operand lives in tensor memory: the tile of point features is loaded straight
+// from global memory into TMEM, each layer-1 accumulator is converted IN PLACE into the bf16 hi/lo A operand of layer 2,
+// and layer 2's accumulator likewise (in place) into layer 3's.  Shared memory only holds streamed weights.
+// The layer-3 tail of a tile overlaps the prologue of the next one: while the layer-3 MMAs run, the (otherwise idle)
+// epilogue warps store the next tile's point features and convert its first layer-1 chunk.
+//   TMEM (512 columns): D2 / h2 [0,256) | D3 [256,384) | pf hi [384,416) lo [416,448) | D1/h1 buffer 0 [448,512);
+//                       D1/h1 buffers 1, 2 = [256,320), [320,384) share D3's columns (chunks 1.. start after the
+//                       previous tile's final dot)
+//   smem (224 KB): W3A 32 KB (W3 k-block 0) | W1R 2 x 16 KB ring | W3B 64 KB (W3 k-blocks 1, 2) | W2R 3 x 32 KB ring
+//                  (16 W2 stages per tile + the last W3 k-block as a 17th entry)
 __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs g) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) uint64_t s_pf, s_w1f[2], s_w1e[2], s_w2f[3], s_w2e[3], s_d1f[3], s_h1f[3], s_h1e[3], s_d2f, s_w3f[4], s_w3e, s_h2f[4], s_d3f;
+    __shared__ __align__(8) uint64_t s_pf, s_w1f[2], s_w1e[2], s_w2f[3], s_w2e[3], s_d1f[3], s_h1f[3], s_h1e[3], s_d2f, s_w3f[3], s_h2f[2], s_d3f, s_done;
     __shared__ uint32_t s_tmem;
     __shared__ float s_hg[512];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -728,12 +730,15 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
     const uint32_t W1R = smem_base + 32 * 1024;
     const uint32_t W3B = smem_base + 64 * 1024;
     const uint32_t W2R = smem_base + 128 * 1024;
-    auto w3_slot = [&](int kb) { return kb == 0 ? W3A : (kb == 3 ? W1R : W3B + (uint32_t)(kb - 1) * 32768u); };
+    auto w3_slot = [&](int kb) { return kb == 0 ? W3A : W3B + (uint32_t)(kb - 1) * 32768u; };
     constexpr uint32_t kTmemCols = 512;
-    constexpr uint32_t kPfHi = 256, kPfLo = 288, kBuf0 = 320;
+    constexpr uint32_t kD3 = 256, kPfHi = 384, kPfLo = 416;
+    auto buf_col = [&](int b) { return b == 0 ? 448u : (b == 1 ? 256u : 320u); };
+    // chunk c of a tile uses buffer c % 3: 3, 3 and 2 uses per tile; n-th use of a buffer <-> barrier parity n & 1
+    auto use_index = [&](int it, int c) { return (uint32_t)(it * ((c % 3) == 2 ? 2 : 3) + c / 3); };
 
-    // the epilogue warps fetch the tile's point features (and the per-patch bias) before the set-up barrier so the
-    // DRAM latency overlaps the TMEM allocation: warp (q, sub) takes rows 32q..32q+31, plane sub & 1, K half sub >> 1
+    // the epilogue warps fetch a tile's point features (and the per-patch bias) one tile ahead, into registers:
+    // warp (q, sub) takes rows 32q..32q+31, plane sub & 1, K half sub >> 1
     uint32_t pfr[16];
     float hg_reg = 0.f;
     auto fetch_tile = [&](long long tile) {   // epilogue warps only
@@ -757,11 +762,12 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
         for (int i = 0; i < 3; ++i) {
             mbar_init(smem_u32(&s_w2f[i]), 1); mbar_init(smem_u32(&s_w2e[i]), 1);
             mbar_init(smem_u32(&s_d1f[i]), 1); mbar_init(smem_u32(&s_h1f[i]), kHeadGroupWarps); mbar_init(smem_u32(&s_h1e[i]), 1);
+            mbar_init(smem_u32(&s_w3f[i]), 1);
         }
         mbar_init(smem_u32(&s_d2f), 1);
-        for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&s_w3f[i]), 1); mbar_init(smem_u32(&s_h2f[i]), kHeadEpiWarps); }
-        mbar_init(smem_u32(&s_w3e), 1);
+        for (int i = 0; i < 2; ++i) mbar_init(smem_u32(&s_h2f[i]), kHeadEpiWarps);
         mbar_init(smem_u32(&s_d3f), 1);
+        mbar_init(smem_u32(&s_done), kHeadEpiWarps);   // "the tile's last TMEM read is done" (D3 shares columns with D1 buffers 1, 2)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -791,10 +797,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 mbar_expect_tx(bar, (uint32_t)planes * 8192u);
                 bulk_g2s(W1R + (uint32_t)s * 16384u, g.w1c + (size_t)c * 8192, (uint32_t)planes * 8192u, bar);  // hi|lo contiguous
             };
-            int w2i = 0;   // runs across tiles: the W2 ring never stops
-            // W2 is packed in 256-row blocks (all 256 output channels of one 64-wide k-block = 32 KB per
-            // plane); a stage is half a block: k-chunks 4h..4h+3 = 16 KB per plane, contiguous
-            auto load_w2 = [&](int c, int h) {
+            int w2i = 0;   // runs across tiles: the W2 ring never stops (17 entries per tile when layer 3 is fused)
+            auto load_ring = [&](const bf16* src, size_t plane_elems) {   // one [hi 16 KB | lo 16 KB] entry
                 const int s = w2i % 3;
                 if (!mbar_wait<true>(smem_u32(&s_w2e[s]), ((uint32_t)(w2i / 3) & 1u) ^ 1u, g.err, 1)) { ok = false; return; }
                 const uint32_t bar = smem_u32(&s_w2f[s]);
@@ -805,17 +809,17 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 }
                 mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
                 for (int pl = 0; pl < planes; ++pl)
-                    bulk_g2s(W2R + (uint32_t)s * 32768u + (uint32_t)pl * kBlkBytes,
-                             g.w2 + (size_t)pl * g.w2_plane + (size_t)c * (2 * kBlkElems) + (size_t)h * kBlkElems, kBlkBytes, bar);
+                    bulk_g2s(W2R + (uint32_t)s * 32768u + (uint32_t)pl * kBlkBytes, src + (size_t)pl * plane_elems, kBlkBytes, bar);
                 ++w2i;
             };
+            // W2 is packed in 256-row blocks (all 256 output channels of one 64-wide k-block = 32 KB per
+            // plane); a stage is half a block: k-chunks 4h..4h+3 = 16 KB per plane, contiguous
+            auto load_w2 = [&](int c, int h) { load_ring(g.w2 + (size_t)c * (2 * kBlkElems) + (size_t)h * kBlkElems, g.w2_plane); };
             for (int it = 0, tile = blockIdx.x; tile < n_tiles && ok; ++it, tile += gridDim.x) {
-                const uint32_t ip = (uint32_t)it & 1u;
-                // the W2 ring is nobody else's: its first stages are fetched while the previous tile is still in its tail
+                // none of these rings is shared with layer 3 any more: the first chunks' weights arrive while the
+                // previous tile is still in its tail
                 load_w2(0, 0);
                 if (ok) load_w2(0, 1);
-                // W1R, W3A and W3B still hold the previous tile's W3 until its layer 3 has completed
-                if (ok && it > 0 && g.fuse_l3) ok = mbar_wait(smem_u32(&s_d3f), ip ^ 1u, g.err, 1);
                 if (ok) load_w1(0);
                 if (ok) load_w1(1);
                 if (ok) load_w1(2);
@@ -823,19 +827,15 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                     load_w2(c, 0);
                     if (ok) load_w2(c, 1);
                     if (ok && c + 2 < 8) load_w1(c + 2);
-                    if (ok && c == 1 && g.fuse_l3) {   // three W3 k-blocks have a home of their own; fetched once the
-                        load_w3(0);                   // loop's weights are on their way
-                        load_w3(1);
-                        load_w3(2);
+                    if (ok && c == 1 && g.fuse_l3) {
+                        // W3A / W3B hold the previous tile's W3 until its layer 3 has completed
+                        if (it > 0) ok = mbar_wait<true>(smem_u32(&s_d3f), (uint32_t)(it - 1) & 1u, g.err, 1);
+                        if (ok) { load_w3(0); load_w3(1); load_w3(2); }
                     }
                 }
                 if (g.fuse_l3 && ok) {
-                    // the W1 ring becomes the last W3 slot once every layer-1 MMA of the tile has completed
-                    ok = mbar_wait(smem_u32(&s_w3e), ip, g.err, 1);
-                    if (ok) {
-                        HTL(59);
-                        load_w3(3);
-                    }
+                    HTL(59);
+                    load_ring(g.w3 + (size_t)3 * kBlkElems, g.w3_plane);   // the last W3 k-block rides the W2 ring
                 }
             }
         }
@@ -846,19 +846,20 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             const uint32_t idesc64 = umma_idesc(64);
             bool ok = true;
             for (int it = 0, tile = blockIdx.x; tile < n_tiles && ok; ++it, tile += gridDim.x) {
-            // pf written => every epilogue warp has left the previous tile => its layer 3 no longer reads h2 / D1
-            ok = mbar_wait(smem_u32(&s_pf), (uint32_t)it & 1u, g.err, 2);
-            tc_fence_after();
-            HTL(2);
-            for (int c = 0; c < 8 && ok; ++c) {   // D1[cc % 3] = pf * W1chunk(c)^T, cc = chunk count across tiles
-                const int s = c & 1, b = (it * 8 + c) % 3;
-                const uint32_t u = (uint32_t)((it * 8 + c) / 3);
-                ok = mbar_wait(smem_u32(&s_w1f[s]), (uint32_t)(c >> 1) & 1u, g.err, 2);
+            for (int c = 0; c < 8 && ok; ++c) {   // D1[c % 3] = pf * W1chunk(c)^T
+                const int s = c & 1, b = c % 3;
+                const uint32_t u = use_index(it, c);
+                // chunk 0 only needs the point features (stored during the previous tile's tail) and buffer 0; the
+                // other two buffers share columns with the previous tile's D3
+                if (c == 0) ok = mbar_wait(smem_u32(&s_pf), (uint32_t)it & 1u, g.err, 2);
+                if (c == 1 && it > 0 && ok) ok = mbar_wait(smem_u32(&s_done), (uint32_t)(it - 1) & 1u, g.err, 2);
+                if (c == 0) HTL(2);
+                if (ok) ok = mbar_wait(smem_u32(&s_w1f[s]), (uint32_t)(c >> 1) & 1u, g.err, 2);
                 if (ok && u > 0) ok = mbar_wait(smem_u32(&s_h1e[b]), (u - 1u) & 1u, g.err, 4);   // layer 2 has read the buffer
                 if (!ok) break;
                 tc_fence_after();
                 HTL(4 + c * 6);
-                const uint32_t d = tmem_base + kBuf0 + (uint32_t)b * 64u;
+                const uint32_t d = tmem_base + buf_col(b);
                 const uint32_t w_hi = W1R + (uint32_t)s * 16384u, w_lo = w_hi + 8192u;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
@@ -874,7 +875,6 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 umma_commit(smem_u32(&s_w1e[s]));
                 umma_commit(smem_u32(&s_d1f[b]));
             }
-            if (ok && g.fuse_l3) umma_commit(smem_u32(&s_w3e));   // the W1 ring is free for the last W3 k-block
             }
         }
     } else if (warp == 1) {
@@ -886,18 +886,19 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             for (int it = 0, tile = blockIdx.x; tile < n_tiles && ok; ++it, tile += gridDim.x) {
             const uint32_t ip = (uint32_t)it & 1u;
             for (int c = 0; c < 8 && ok; ++c) {   // D2 += h1chunk(c) * W2[:, 64c..64c+64]^T, A = the converted D1 buffer
-                const int b = (it * 8 + c) % 3;
-                ok = mbar_wait(smem_u32(&s_h1f[b]), (uint32_t)((it * 8 + c) / 3) & 1u, g.err, 5);
+                const int b = c % 3;
+                ok = mbar_wait(smem_u32(&s_h1f[b]), use_index(it, c) & 1u, g.err, 5);
                 if (!ok) break;
                 HTL(4 + c * 6 + 4);
-                const uint32_t buf = tmem_base + kBuf0 + (uint32_t)b * 64u;
+                const uint32_t buf = tmem_base + buf_col(b);
                 for (int h = 0; h < 2 && ok; ++h) {
                     const int s = w2i % 3;
                     ok = mbar_wait(smem_u32(&s_w2f[s]), (uint32_t)(w2i / 3) & 1u, g.err, 2);
                     if (!ok) break;
                     tc_fence_after();
                     const uint32_t b_hi = W2R + (uint32_t)s * 32768u, b_lo = b_hi + kBlkBytes;
-                    const uint32_t d = tmem_base;   // one N=256 accumulator
+                    const uint32_t d = tmem_base;   // one N=256 accumulator (overwrites the previous tile's h2: the tensor
+                                                    // pipe runs this thread's MMAs in order, layer 3 of that tile first)
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
                         if (g.dbg & 2) break;
@@ -920,25 +921,38 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             if (ok && g.fuse_l3) {
                 const uint32_t idesc128 = umma_idesc(128);
                 for (int kb = 0; kb < 4 && ok; ++kb) {
-                    // k-blocks 2r, 2r+1 of h2 are written by all 16 epilogue warps in their round r, so layer 3 starts
-                    // while the second half of the layer-2 accumulator is still being converted; D3 overlays D2's
-                    // columns [0,128), which round 0 has read
+                    // k-blocks 2r, 2r+1 of h2 are converted (in place, inside D2) by all 16 epilogue warps in their round
+                    // r, so layer 3 starts while the second half of the layer-2 accumulator is still being converted
                     ok = mbar_wait(smem_u32(&s_h2f[kb >> 1]), ip, g.err, 5);
                     if (kb == 0) HTL(54);
-                    ok = ok && mbar_wait(smem_u32(&s_w3f[kb]), ip, g.err, 2);
+                    uint32_t b_hi;
+                    int s = 0;
+                    if (kb < 3) {
+                        ok = ok && mbar_wait(smem_u32(&s_w3f[kb]), ip, g.err, 2);
+                        b_hi = w3_slot(kb);
+                    } else {
+                        s = w2i % 3;
+                        ok = ok && mbar_wait(smem_u32(&s_w2f[s]), (uint32_t)(w2i / 3) & 1u, g.err, 2);
+                        b_hi = W2R + (uint32_t)s * 32768u;
+                    }
                     if (!ok) break;
                     tc_fence_after();
-                    const uint32_t a_hi = tmem_base + 256u + (uint32_t)kb * 32u, a_lo = a_hi + 128u;
-                    const uint32_t b_hi = w3_slot(kb), b_lo = b_hi + kBlkBytes;
-                    const uint32_t d = tmem_base;
+                    const uint32_t b_lo = b_hi + kBlkBytes;
+                    const uint32_t d = tmem_base + kD3;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
+                        // k-step ks of k-block kb: 32-channel group 2kb + (ks >> 1), [hi 16 | lo 16] columns
+                        const uint32_t a_hi = tmem_base + (uint32_t)(2 * kb + (ks >> 1)) * 32u + (uint32_t)(ks & 1) * 8u, a_lo = a_hi + 16u;
                         const uint32_t koff = (uint32_t)ks * 2 * kLBO;
-                        umma_bf16_ts(d, a_hi + (uint32_t)ks * 8u, umma_desc(b_hi + koff, kLBO, kSBO), idesc128, (kb == 0 && ks == 0) ? 0u : 1u);
+                        umma_bf16_ts(d, a_hi, umma_desc(b_hi + koff, kLBO, kSBO), idesc128, (kb == 0 && ks == 0) ? 0u : 1u);
                         if (g.nprod > 1) {
-                            umma_bf16_ts(d, a_hi + (uint32_t)ks * 8u, umma_desc(b_lo + koff, kLBO, kSBO), idesc128, 1u);
-                            umma_bf16_ts(d, a_lo + (uint32_t)ks * 8u, umma_desc(b_hi + koff, kLBO, kSBO), idesc128, 1u);
+                            umma_bf16_ts(d, a_hi, umma_desc(b_lo + koff, kLBO, kSBO), idesc128, 1u);
+                            umma_bf16_ts(d, a_lo, umma_desc(b_hi + koff, kLBO, kSBO), idesc128, 1u);
                         }
+                    }
+                    if (kb == 3) {
+                        umma_commit(smem_u32(&s_w2e[s]));
+                        ++w2i;
                     }
                 }
                 if (ok) umma_commit(smem_u32(&s_d3f));
@@ -953,53 +967,31 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
         const int q = warp & 3;
         const int grp = ew >> 3;
         const int half = (ew >> 2) & 1;
-        const int quarter = ew >> 2;           // column quarter for the final 256-column pass
+        const int quarter = ew >> 2;           // column quarter for the 256- and 128-column passes
         const int lrow = q * 32 + lane;
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
+        const uint32_t tmem_row = tmem_base + tlane;
         uint32_t v[32];
         bool ok = true;   // after a time-out the warp keeps walking its tiles (the named barriers need all 16 warps) but
                           // skips every wait and all the work
         const bool tl_lane = lane == 0 && (ew & 7) == 0;   // one stamping lane per epilogue group
-        for (int it = 0, tile = blockIdx.x; tile < n_tiles; ++it, tile += gridDim.x) {
-        const uint32_t ip = (uint32_t)it & 1u;
-        const long long row = (long long)tile * 128 + lrow;
-        if (tl_lane && grp == 0) {
-            HTL(0);
-            if (g.cta_trace && tile < 16384) {
-                uint32_t smid;
-                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-                g.cta_trace[3 * tile] = smid;
-                g.cta_trace[3 * tile + 1] = global_ns();
-            }
-        }
-        {   // the tile's point features (fetched during the previous tile) become the TMEM A operand of layer 1; every
-            // warp is past the previous tile's layer 3 here, so pf / h2 / D1 columns are free
-            s_hg[threadIdx.x - 96] = hg_reg;
-            asm volatile("bar.sync 1, %0;" ::"n"(kHeadEpiWarps * 32) : "memory");   // the 16 epilogue warps only
-            const int plane = quarter & 1, khalf = quarter >> 1;
-            if (plane < planes) {
-                tmem_st16(tmem_base + tlane + (plane ? kPfLo : kPfHi) + (uint32_t)khalf * 16u, pfr);
-                tmem_st_wait();
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&s_pf));
-            if (tile + (int)gridDim.x < n_tiles) fetch_tile(tile + gridDim.x);   // in flight for the whole tile
-        }
-        for (int c = grp; c < 8 && ok; c += 2) {
-            const int b = (it * 8 + c) % 3;
-            ok = mbar_wait(smem_u32(&s_d1f[b]), (uint32_t)((it * 8 + c) / 3) & 1u, g.err, 3);
-            if (!ok) break;
+        float hg_tile = 0.f;   // this thread's element of the bias vector of the tile whose prologue ran last
+        // bias + ReLU + split, in place: this warp's 32 accumulator columns of chunk c become [hi 16 | lo 16] packed columns
+        auto convert_chunk = [&](int it, int tile, int c, const float* bias32, bool bias_global) {
+            const int b = c % 3;
+            ok = mbar_wait(smem_u32(&s_d1f[b]), use_index(it, c) & 1u, g.err, 3);
+            if (!ok) return;
             tc_fence_after();
             if (tl_lane) HTL(4 + c * 6 + 1);
-            // bias + ReLU + split, in place: this warp's 32 accumulator columns become [hi 16 | lo 16] packed columns
-            const uint32_t cols = tmem_base + tlane + kBuf0 + (uint32_t)b * 64u + (uint32_t)half * 32u;
+            const uint32_t cols = tmem_row + buf_col(b) + (uint32_t)half * 32u;
             tmem_ld32(cols, v);
             uint32_t ph[16], pl[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-                const float x0 = fmaxf(__uint_as_float(v[2 * e]) + s_hg[c * 64 + half * 32 + 2 * e], 0.f);
-                const float x1 = fmaxf(__uint_as_float(v[2 * e + 1]) + s_hg[c * 64 + half * 32 + 2 * e + 1], 0.f);
+                const float b0 = bias_global ? __ldg(bias32 + 2 * e) : bias32[2 * e];
+                const float b1 = bias_global ? __ldg(bias32 + 2 * e + 1) : bias32[2 * e + 1];
+                const float x0 = fmaxf(__uint_as_float(v[2 * e]) + b0, 0.f);
+                const float x1 = fmaxf(__uint_as_float(v[2 * e + 1]) + b1, 0.f);
                 split_pair(x0, x1, ph[e], pl[e]);
             }
             tmem_st16(cols, ph);
@@ -1009,7 +1001,47 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_h1f[b]));
             if (tl_lane) HTL(4 + c * 6 + 3);
+        };
+        // A tile's prologue: its point features (fetched one tile ahead) become the TMEM A operand of layer 1, and group 0
+        // converts the first layer-1 chunk (bias straight from global memory: s_hg still belongs to the previous tile).
+        // Runs inside the previous tile's layer-3 tail; the columns it touches ([384,512)) are free there.
+        auto pro_store = [&](int it, int tile) {
+            if (tl_lane && grp == 0) HTL(0);
+            if (ok) {
+                const int plane = quarter & 1, khalf = quarter >> 1;
+                if (plane < planes) {
+                    tmem_st16(tmem_row + (plane ? kPfLo : kPfHi) + (uint32_t)khalf * 16u, pfr);
+                    tmem_st_wait();
+                }
+                tc_fence_before();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s_pf));
+            hg_tile = hg_reg;
+            if (tile + (int)gridDim.x < n_tiles) fetch_tile(tile + gridDim.x);   // in flight for a whole tile
+        };
+        auto pro_convert = [&](int it, int tile) {
+            if (grp == 0 && ok)
+                convert_chunk(it, tile, 0, g.hg + ((long long)tile * 128 / g.rows_per_patch) * 512 + half * 32, true);
+        };
+        bool pro_done = false;
+        for (int it = 0, tile = blockIdx.x; tile < n_tiles; ++it, tile += gridDim.x) {
+        const uint32_t ip = (uint32_t)it & 1u;
+        const long long row = (long long)tile * 128 + lrow;
+        if (tl_lane && grp == 0 && g.cta_trace && tile < 16384) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            g.cta_trace[3 * tile] = smid;
+            g.cta_trace[3 * tile + 1] = global_ns();
         }
+        if (!pro_done) {
+            pro_store(it, tile);
+            pro_convert(it, tile);
+        }
+        pro_done = false;
+        s_hg[threadIdx.x - 96] = hg_tile;
+        asm volatile("bar.sync 1, %0;" ::"n"(kHeadEpiWarps * 32) : "memory");   // the 16 epilogue warps only
+        for (int c = grp ? 1 : 2; c < 8 && ok; c += 2) convert_chunk(it, tile, c, s_hg + c * 64 + half * 32, false);
         if (ok) ok = mbar_wait(smem_u32(&s_d2f), ip, g.err, 3);
         tc_fence_after();
         if (tl_lane && grp == 0) HTL(52);
@@ -1017,7 +1049,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             if (ok) {   // h2 goes to HBM for a separate layer-3 launch (A/B-test path)
 #pragma unroll 1
                 for (int c0 = quarter * 64; c0 < quarter * 64 + 64; c0 += 32) {
-                    tmem_ld32(tmem_base + tlane + (uint32_t)c0, v);
+                    tmem_ld32(tmem_row + (uint32_t)c0, v);
                     if (row >= g.m_valid) continue;
 #pragma unroll
                     for (int c8 = 0; c8 < 4; ++c8) {
@@ -1034,11 +1066,14 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                         if (g.nprod > 1) *reinterpret_cast<uint4*>(g.out_t + g.out_plane + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                     }
                 }
+                tc_fence_before();
             }
         } else {
-            // h2 stays on chip as the A operand of layer 3.  Two rounds of 128 channels (32 per warp): layer 3 starts on
-            // k-blocks 0-1 while k-blocks 2-3 are still being converted.
-            const uint32_t tmem_row = tmem_base + tlane;
+            // the next tile's point features go to TMEM first: its first layer-1 chunk then slips into the tensor pipe
+            // ahead of this tile's layer 3 ([384,448) is free: every layer-1 MMA of this tile completed before D2 did)
+            const bool has_next = tile + (int)gridDim.x < n_tiles;
+            // h2 stays on chip as the A operand of layer 3, converted in place.  Two rounds of 128 channels (32 per warp):
+            // layer 3 starts on k-blocks 0-1 while k-blocks 2-3 are still being converted.
 #pragma unroll 1
             for (int r = 0; r < 2; ++r) {
                 if (ok) {
@@ -1057,6 +1092,14 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 if (lane == 0) mbar_arrive(smem_u32(&s_h2f[r]));
             }
             if (tl_lane && grp == 0) HTL(53);
+            // while layer 3 runs: the next tile's point features go to TMEM ([384,448) is free: every layer-1 MMA of this
+            // tile completed before D2 did), its first layer-1 chunk runs between this tile's layer-3 MMAs and becomes
+            // layer 2's first A operand
+            if (has_next) {
+                pro_store(it + 1, tile + gridDim.x);
+                pro_convert(it + 1, tile + gridDim.x);
+                pro_done = true;
+            }
             // ReLU(conv3) . w4: every warp takes 32 of the 128 layer-3 channels of its rows, the partial sums meet
             // in shared memory (s_hg is dead by now) and the column-quarter-0 warps finish the weight map
             if (ok) ok = mbar_wait(smem_u32(&s_d3f), ip, g.err, 3);
@@ -1070,6 +1113,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                     case 2: dot = head_dot32<64>(g, tmem_row); break;
                     default: dot = head_dot32<96>(g, tmem_row); break;
                 }
+                tc_fence_before();
             }
             s_hg[quarter * 128 + lrow] = dot;
             asm volatile("bar.sync 1, %0;" ::"n"(kHeadEpiWarps * 32) : "memory");   // the 16 epilogue warps only
@@ -1080,7 +1124,10 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             }
             if (tl_lane && grp == 0) HTL(57);
         }
-        // every warp is done with s_hg (bias vector, partial sums) and with D2 / D3 before any of them starts the next tile
+        // the tile's last TMEM read is done: chunks 1.. of the next tile may use the buffers that share D3's columns
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_done));
+        // every warp is done with s_hg (bias vector, partial sums) before any of them writes the next tile's
         asm volatile("bar.sync 1, %0;" ::"n"(kHeadEpiWarps * 32) : "memory");
         if (tl_lane && grp == 0 && g.cta_trace && tile < 16384) g.cta_trace[3 * tile + 2] = global_ns();
         }
