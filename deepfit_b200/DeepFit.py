@@ -45,43 +45,12 @@ def fit_Wjet(points, weights, order=2, compute_neighbor_normals=False):
 
 def compute_principal_curvatures(beta):
     """Principal curvatures (ascending) and directions from jet coefficients, with the reference's
-    upper-triangle ``symeig`` semantics.  Returns (curvatures [B,2], dirs [B,2,3])."""
+    upper-triangle ``symeig`` semantics.  Returns (curvatures [B,2], dirs [B,2,3]): ``dirs`` is symeig's eigenvector
+    matrix (eigenvectors in columns) with a zero column appended, as in the reference (models/DeepFit.py:469-472);
+    the sign of each eigenvector is library-defined there, here its largest-magnitude component is positive."""
     if beta.shape[1] < 5:
         raise ValueError("Can't compute curvatures for jet with order less than 2")
-    curv = ops.principal_curvatures(beta.float())
-    dirs = _principal_directions(beta.float(), curv)
-    return curv, dirs
-
-
-def _principal_directions(beta, curv):
-    # Eigenvectors of the symmetric matrix [[M00, M01], [M01, M11]] (what symeig(upper=True) sees),
-    # zero-padded in the normal direction (reference models/DeepFit.py:471-472).  Tiny elementwise
-    # torch ops on the device; never written to disk by any reference caller.
-    b0, b1, b2, b3, b4 = (beta[:, i].double() for i in range(5))
-    E, G, Fm = 1 + b0 * b0, 1 + b1 * b1, b0 * b1
-    nrm = torch.sqrt(b0 * b0 + b1 * b1 + 1)
-    e, f, g = 2 * b2 / nrm, b4 / nrm, 2 * b3 / nrm
-    det = E * G - Fm * Fm
-    m00 = -(G * e - Fm * f) / det
-    m01 = -(G * f - Fm * g) / det
-    m11 = -(E * g - Fm * f) / det
-    lam = curv.double()
-    vecs = []
-    for j in range(2):
-        a = m00 - lam[:, j]
-        d = m11 - lam[:, j]
-        # null vector of [[a, m01], [m01, d]]: pick the better-conditioned row
-        use_first = (a.abs() + m01.abs()) >= (d.abs() + m01.abs())
-        vx = torch.where(use_first, -m01, -d)
-        vy = torch.where(use_first, a, m01)
-        deg = (vx.abs() + vy.abs()) == 0
-        vx = torch.where(deg, torch.full_like(vx, 1.0 if j == 0 else 0.0), vx)
-        vy = torch.where(deg, torch.full_like(vy, 0.0 if j == 0 else 1.0), vy)
-        nr = torch.sqrt(vx * vx + vy * vy)
-        vecs.append(torch.stack([vx / nr, vy / nr], dim=1))
-    dirs = torch.stack(vecs, dim=2)  # columns are eigenvectors, like torch.symeig
-    dirs = torch.cat([dirs, torch.zeros(dirs.shape[0], 2, 1, dtype=dirs.dtype, device=dirs.device)], dim=2)
-    return dirs.to(beta.dtype)
+    return ops.principal_curvatures(beta.float(), want_dirs=True)
 
 
 # (module path, kind, in, out) -- the parameter tree of the reference for arch='simple'
@@ -226,4 +195,5 @@ class DeepFit(nn.Module):
         neighbor_normals = None
         if self.compute_neighbor_normals:   # use_consistency=True: normals of the jet at every (rotated) neighbour
             neighbor_normals = ops.neighbor_normals(points.float(), out["beta"], self.jet_order, trans=trans)
+        net.status()           # raises on a pipeline time-out instead of returning garbage
         return out["n_local"], out["beta"], weights, trans, trans2, neighbor_normals

@@ -21,7 +21,7 @@ LAYER_NAMES = [
 assert len(LAYER_NAMES) == DFB_NUM_LAYERS
 
 WEIGHT_MODE = {"sigmoid": 0, "tanh": 1}
-PRECISION = {"bf16x3": 0, "bf16": 1}
+PRECISION = {"bf16x3": 0, "bf16": 1, "f16f8": 2}
 
 EXPORTS = [
     "dfb_abi_version", "dfb_last_error_string", "dfb_device_check",
@@ -30,6 +30,7 @@ EXPORTS = [
     "dfb_model_create", "dfb_model_destroy", "dfb_model_forward", "dfb_model_status",
     "dfb_model_profile", "dfb_model_profile_read", "dfb_launch_count",
     "dfb_wls_fit", "dfb_principal_curvatures", "dfb_neighbor_normals",
+    "dfb_pipeline_create", "dfb_pipeline_run", "dfb_pipeline_destroy",
     "dfb_savetxt_f32", "dfb_savetxt_f64", "dfb_loadtxt_f32",
 ]
 
@@ -42,6 +43,15 @@ class DfbLayer(C.Structure):
 class DfbModelDesc(C.Structure):
     _fields_ = [("k", C.c_int32), ("weight_mode", C.c_int32), ("precision", C.c_int32),
                 ("max_batch", C.c_int32), ("layers", DfbLayer * DFB_NUM_LAYERS)]
+
+
+class DfbPipelineOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_normals", "d_curv", "d_beta", "d_weights", "d_trans", "d_trans2", "d_U", "d_rad",
+                                          "d_dirs_world", "d_info")]
+
+
+DFB_PIPE_KEEP_QSTN = 1
+ABI_VERSION = 2
 
 
 class DeepFitB200Error(RuntimeError):
@@ -99,8 +109,11 @@ def load():
     lib.dfb_dbg_gemm.restype = C.c_int
     lib.dfb_dbg_model_dump.argtypes = [vp, i32, i64, i32, vp, vp]
     lib.dfb_dbg_model_dump.restype = C.c_int
-    lib.dfb_wls_fit.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp]
-    lib.dfb_principal_curvatures.argtypes = [vp, i64, i32, vp, vp]
+    lib.dfb_wls_fit.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.dfb_principal_curvatures.argtypes = [vp, i64, i32, vp, vp, vp]
+    lib.dfb_pipeline_create.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(vp)]
+    lib.dfb_pipeline_run.argtypes = [vp, i64, i64, C.POINTER(DfbPipelineOutputs), vp]
+    lib.dfb_pipeline_destroy.argtypes = [vp]
     lib.dfb_neighbor_normals.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
     lib.dfb_savetxt_f32.argtypes = [C.c_char_p, vp, i64, i32]
     lib.dfb_savetxt_f64.argtypes = [C.c_char_p, vp, i64, i32]
@@ -111,7 +124,7 @@ def load():
             fn.restype = C.c_int64
         elif name != "dfb_last_error_string":
             fn.restype = C.c_int
-    if lib.dfb_abi_version() != 1:
+    if lib.dfb_abi_version() != ABI_VERSION:
         raise ImportError("deepfit_b200: ABI version mismatch in %s" % path)
     _lib = lib
     return lib

@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libdeepfit_b200.so")
-SOURCES = ["api.cu", "knn.cu", "pca.cu", "wls.cu", "mlp.cu", "textio.cu"]
+SOURCES = ["api.cu", "knn.cu", "pca.cu", "wls.cu", "mlp.cu", "pipeline.cu", "textio.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
@@ -48,10 +48,27 @@ def is_current() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a and link the shared library.  Returns its path."""
-    sources = [s for s in SOURCES if os.path.isfile(os.path.join(CSRC, s))]
+    """Compile every CUDA source for sm_100a and link the shared library.  Returns its path.
+
+    Safe under torchrun: concurrent callers serialise on a lock file, objects go to a per-process
+    directory, and the library and its stamp are moved into place atomically (``os.replace``), so a
+    rank never dlopens a half-written file."""
+    import fcntl
     if not force and is_current():
         return LIB_PATH
+    lock = open(LIB_PATH + ".lock", "w")
+    try:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and is_current():          # another process built it while we waited
+            return LIB_PATH
+        return _build_locked(verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(verbose: bool) -> str:
+    sources = [s for s in SOURCES if os.path.isfile(os.path.join(CSRC, s))]
     nvcc = _nvcc()
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -68,12 +85,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
         objs = list(ex.map(compile_one, sources))
-    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    tmp_lib = "%s.tmp.%d" % (LIB_PATH, os.getpid())
+    cmd = [nvcc, "-shared", "-o", tmp_lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    with open(LIB_PATH + ".stamp", "w") as fh:
+    os.replace(tmp_lib, LIB_PATH)
+    tmp_stamp = "%s.stamp.tmp.%d" % (LIB_PATH, os.getpid())
+    with open(tmp_stamp, "w") as fh:
         fh.write(_stamp())
+    os.replace(tmp_stamp, LIB_PATH + ".stamp")
     return LIB_PATH
 
 

@@ -63,7 +63,7 @@ def main(argv=None):
 
     dataset = tu.SinglePointCloudDataset(args.input, points_per_patch=args.k_neighbors, device=device)
     est = NormalEstimator(dataset.points_gpu, args.k_neighbors, jet_order, args.mode, model, chunk=args.batch,
-                          cancel_qstn=not args.ref_compat)
+                          cancel_qstn=not args.ref_compat, grid=dataset.kdtree)
     if jet_order < 2:
         # the reference dies here with this very error (tutorial_utils.py:204-205) *before* writing anything
         raise ValueError("Can't compute curvatures for jet with order less than 2")

@@ -3,6 +3,9 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -31,16 +34,33 @@ void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launches(bool reset) { return reset ? g_launches.exchange(0) : g_launches.load(); }
 
 int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            return 148;
+    // cached per device: a process may drive several GPUs (one estimator per --gpu_idx)
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+        cached[dev].store(n, std::memory_order_relaxed);
     }
-    return cached;
+    return n;
+}
+
+int ensure_dyn_smem(const void* func, int bytes) {
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of the function
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return check_cuda(e, "cudaGetDevice", __FILE__, __LINE__);
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair(func, dev);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= bytes) return 0;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", __FILE__, __LINE__);
+    done[key] = bytes;
+    return 0;
 }
 
 }  // namespace dfb

@@ -34,8 +34,19 @@ int check_cuda(cudaError_t e, const char* what, const char* file, int line);
 // of OUR kernels ran in a timed region.
 void note_launch(int n = 1);
 
-// Number of SMs of the current device (cached per process).
+// Number of SMs of the current device (cached per device).
 int sm_count();
+
+// Raise a kernel's dynamic shared-memory limit on the CURRENT device (once per function and device).
+int ensure_dyn_smem(const void* func, int bytes);
+
+// Internal cross-file entry points (the C pipeline drives the stages through these and the public ABI).
+int wls_fit_impl(const float* d_patch, const float* d_weights, const float* d_trans, const float* d_U, const double* d_rad,
+                 int64_t n, int32_t k, int32_t order, float* d_beta, float* d_n_local, float* d_n_world, float* d_curv,
+                 double* d_curv_scaled, float* d_dirs, float* d_dirs_world, int32_t* d_info, int keep_qstn, dfb_stream stream);
+const float* grid_points(const dfb_grid* g);   // device copy of the cloud, original order, f32[n,3]
+long long grid_size(const dfb_grid* g);
+int model_k(const dfb_model* m);
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

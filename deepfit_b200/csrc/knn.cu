@@ -701,6 +701,11 @@ int grid_build(dfb_grid* g, const float* d_points, cudaStream_t st) {
 }  // namespace
 }  // namespace dfb
 
+namespace dfb {
+const float* grid_points(const dfb_grid* g) { return g->pts; }
+long long grid_size(const dfb_grid* g) { return g->n; }
+}  // namespace dfb
+
 extern "C" int dfb_grid_create(const float* d_points, int64_t n, dfb_stream stream, dfb_grid** out) {
     using namespace dfb;
     DFB_REQUIRE(out != nullptr, DFB_E_ARG, "dfb_grid_create: out is NULL");
@@ -710,7 +715,8 @@ extern "C" int dfb_grid_create(const float* d_points, int64_t n, dfb_stream stre
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);
     // finest level: about sqrt(n/8) cells per axis for surface-like clouds, 2^5 .. 2^10
-    int bits = (int)ceil(0.5 * log2((double)n / 8.0 + 1.0));
+    // (exact powers of four must not jump a level: 2 097 152 points -> 2^9, not 2^10 with its 4 GiB table)
+    int bits = (int)ceil(0.5 * log2((double)n / 8.0) - 1e-9);
     if (bits < 5) bits = 5;
     if (bits > kMaxLevelBits) bits = kMaxLevelBits;
     dfb_grid* g = new dfb_grid();
@@ -782,11 +788,7 @@ extern "C" int dfb_knn(const dfb_grid* grid, const int32_t* d_query, int64_t q_b
     a.k = k; a.kcap = kcap;
     a.out_idx = d_idx; a.out_dist = d_dist; a.out_rad = d_rad;
     const size_t smem = (size_t)kKnnWarps * kcap * (sizeof(double) + sizeof(int));
-    static bool attr_set = false;
-    if (!attr_set) {
-        DFB_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_set = true;
-    }
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&knn_kernel), 100 * 1024)) return rc;
     long long blocks = (q_count + kKnnWarps - 1) / kKnnWarps;
     const long long cap = (long long)sm_count() * 16;
     if (blocks > cap) blocks = cap;

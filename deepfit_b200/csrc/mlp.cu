@@ -17,6 +17,12 @@
 // off on the seeded network), so every operand is kept as a hi/lo bf16 pair (x = hi + lo, 16 mantissa
 // bits) and each k-step issues three MMAs (hi*hi + hi*lo + lo*hi) into the same fp32 TMEM accumulator
 // (DFB_PRECISION_BF16X3).  DFB_PRECISION_BF16 issues only hi*hi.
+// DFB_PRECISION_F16F8 reaches the same grade with TWO tensor-core product units per k-step instead of three: the main
+// product runs on FP16 operands (11 mantissa bits, x = xh + xl), and the two first-order corrections xh*wl + xl*wh --
+// 2^-12 of the main term, so four significant bits are enough for them -- run as ONE kind::f8f6f4 MMA (E4M3 operands,
+// K = 32 = the k-step's 16 channels twice: activations [xh | xl*2^12], weights [wl*2^15 | wh*2^3]) at twice the FP16
+// rate.  Every operand is pre-scaled by a power of two so that both MMAs accumulate 2^15 x the true product into the
+// same fp32 TMEM accumulator (main plane: activations x 2^7, weights x 2^8); epilogues multiply by 2^-15.
 //
 // Two orientations share one mainloop:
 //   N ("points are rows"): D[128 points, n] = X[128 x K] * W[n x K]^T, epilogue thread == point:
@@ -27,6 +33,8 @@
 #include "common.cuh"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include <string.h>
 
@@ -91,21 +99,28 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     }
     return ok != 0;
 }
-// Bounded wait: a pipeline bug sets the error flag (dfb_model_status reports it) instead of hanging the GPU.  The
-// clock is only read once the first probe has failed, so a wait on a completed phase costs one instruction.
+// Bounded wait: a pipeline bug sets the error flag (dfb_model_status reports and clears it) instead of hanging the GPU.
+// The bound is wall-clock time (%globaltimer, 2 s), not cycles, so GPU sharing, preemption or a profiler replay that
+// stretch a wait do not trip it; the timer is only read once the first probe has failed, so a wait on a completed
+// phase costs one instruction.
+__device__ __forceinline__ long long wall_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 template <bool PARK = false>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
     if (mbar_try<PARK>(bar, parity)) return true;
-    const long long t0 = clock64();
+    const long long t0 = wall_ns();
     for (;;) {
         if (mbar_try<PARK>(bar, parity)) return true;
-        const long long waited = clock64() - t0;
-        if (waited > (1LL << 31)) {
+        const long long waited = wall_ns() - t0;
+        if (waited > 2000000000LL) {
             atomicCAS(err, 0, code);
             return false;
         }
         // someone else already timed out: give up at once (persistent CTAs would otherwise stack up time-outs)
-        if (waited > (1LL << 20) && *reinterpret_cast<volatile int*>(err) != 0) return false;
+        if (waited > 1000000LL && *reinterpret_cast<volatile int*>(err) != 0) return false;
     }
 }
 // One lane of a converged warp (elect.sync): unlike `lane == 0`, the compiler knows the guarded code is single-threaded
@@ -185,9 +200,63 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
     d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
     return d;
 }
-// instruction descriptor, kind::f16: BF16 x BF16 -> F32, both operands K-major, M = 128
-__host__ __device__ __forceinline__ uint32_t umma_idesc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// instruction descriptor: F32 accumulate, both operands K-major, M = 128.  Operand format code 1 = BF16 (kind::f16);
+// code 0 = F16 for kind::f16 and E4M3 for kind::f8f6f4, so the FP16 main product and its FP8 correction share one
+// descriptor value.
+__host__ __device__ __forceinline__ uint32_t umma_idesc(int n, int fmt_code = 1) {
+    return (1u << 4) | ((uint32_t)fmt_code << 7) | ((uint32_t)fmt_code << 10) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(128 >> 4) << 24);
+}
+// kind::f8f6f4 (E4M3 x E4M3 -> F32, K = 32 per instruction), operands from shared memory / A from tensor memory
+// (lane = row, each 32-bit column holds four consecutive K elements)
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+
+// Operand formats of a model (dfb_model_desc::precision)
+enum { FMT_BF16X3 = 0, FMT_BF16 = 1, FMT_F16F8 = 2 };
+__host__ __device__ __forceinline__ int fmt_planes(int fmt) { return fmt == FMT_BF16 ? 1 : 2; }
+__host__ __device__ __forceinline__ int fmt_code(int fmt) { return fmt == FMT_F16F8 ? 0 : 1; }
+// FMT_F16F8 scales: main plane of activations x 2^7, of weights x 2^8; accumulators hold 2^15 x the product
+constexpr float kActMain = 128.f, kWgtMain = 256.f;
+__host__ __device__ __forceinline__ float fmt_acc_scale(int fmt) { return fmt == FMT_F16F8 ? (1.f / 32768.f) : 1.f; }
+constexpr float kActLimit = 500.f;   // |activation| x 2^7 must stay inside FP16 (65504 / 128 = 511)
+
+// The products of one k-step (16 channels) into accumulator d: hi*hi [+ hi*lo + lo*hi] (bf16 formats) or
+// FP16 hi*hi + ONE E4M3 MMA over the correction plane (f16f8).  SS: both operands are shared-memory descriptors.
+__device__ __forceinline__ void mma_kstep(int fmt, uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                          uint32_t idesc, uint32_t accum) {
+    umma_bf16(d, a_hi, b_hi, idesc, accum);
+    if (fmt == FMT_BF16X3) {
+        umma_bf16(d, a_hi, b_lo, idesc, 1u);
+        umma_bf16(d, a_lo, b_hi, idesc, 1u);
+    } else if (fmt == FMT_F16F8) {
+        umma_f8(d, a_lo, b_lo, idesc, 1u);
+    }
+}
+// TS: the A operand lives in tensor memory
+__device__ __forceinline__ void mma_kstep_ts(int fmt, uint32_t d, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                             uint32_t idesc, uint32_t accum) {
+    umma_bf16_ts(d, a_hi, b_hi, idesc, accum);
+    if (fmt == FMT_BF16X3) {
+        umma_bf16_ts(d, a_hi, b_lo, idesc, 1u);
+        umma_bf16_ts(d, a_lo, b_hi, idesc, 1u);
+    } else if (fmt == FMT_F16F8) {
+        umma_f8_ts(d, a_lo, b_lo, idesc, 1u);
+    }
 }
 
 __device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
@@ -204,6 +273,81 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// two floats -> two E4M3 bytes (a in the low byte, b in the high byte), round to nearest, saturating
+__device__ __forceinline__ uint32_t e4m3x2(float a, float b) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(b), "f"(a));
+    return (uint32_t)r;
+}
+// FMT_F16F8, one value pair (consecutive channels a, b) -> the packed FP16 main word and the two correction byte pairs
+// c0 / c1 (16 bits each).  Activation side: main = fp16(x * 2^7), c0 = e4m3(xh), c1 = e4m3(xl * 2^12);
+// weight side: main = fp16(w * 2^8), c0 = e4m3(wl * 2^15), c1 = e4m3(wh * 2^3)  (x = xh + xl, xh the FP16 value).
+template <bool WSIDE>
+__device__ __forceinline__ void f16f8_pair(float a, float b, uint32_t& main, uint32_t& c0, uint32_t& c1) {
+    constexpr float ms = WSIDE ? kWgtMain : kActMain;
+    const __half2 h = __floats2half2_rn(a * ms, b * ms);
+    main = *reinterpret_cast<const uint32_t*>(&h);
+    const float2 hf = __half22float2(h);
+    const float ha = hf.x * (1.f / ms), hb = hf.y * (1.f / ms);
+    const float la = a - ha, lb = b - hb;
+    if (WSIDE) {
+        c0 = e4m3x2(la * 32768.f, lb * 32768.f);
+        c1 = e4m3x2(ha * 8.f, hb * 8.f);
+    } else {
+        c0 = e4m3x2(ha, hb);
+        c1 = e4m3x2(la * 4096.f, lb * 4096.f);
+    }
+}
+// 32 consecutive channels (starting at a multiple of 16) -> 16 main words + 16 second-plane words.  The second plane of
+// a 16-channel k-step is [c0 x 16 | c1 x 16] (32 bytes), i.e. words [c0 0-15 | c1 0-15 | c0 16-31 | c1 16-31]; for the
+// bf16 formats it is the lo plane.  Stored as 16-byte chunks (4 words) both planes use the same chunk index, and in
+// tensor memory the same [hi 16 | second 16] column packing.  Returns the largest value seen (activation range check).
+template <bool WSIDE>
+__device__ __forceinline__ float split32(int fmt, const float (&f)[32], uint32_t (&ph)[16], uint32_t (&pl)[16]) {
+    float mx = 0.f;
+    if (fmt != FMT_F16F8) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) split_pair(f[2 * e], f[2 * e + 1], ph[e], pl[e]);
+        return mx;
+    }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        uint32_t c0[8], c1[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float a = f[16 * g + 2 * e], b = f[16 * g + 2 * e + 1];
+            mx = fmaxf(mx, fmaxf(fabsf(a), fabsf(b)));
+            f16f8_pair<WSIDE>(a, b, ph[8 * g + e], c0[e], c1[e]);
+        }
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            pl[8 * g + w] = c0[2 * w] | (c0[2 * w + 1] << 16);
+            pl[8 * g + 4 + w] = c1[2 * w] | (c1[2 * w + 1] << 16);
+        }
+    }
+    return mx;
+}
+// One value (row, channel) of a tiled activation matrix (the per-patch outputs of the max-pool epilogues).
+__device__ __forceinline__ void store_one_act(int fmt, bf16* out_t, size_t plane, long long row, int ch, int KB, float r) {
+    if (fmt != FMT_F16F8) {
+        bf16 hi, lo;
+        split_bf16(r, hi, lo);
+        const size_t o = tiled_offset(row, ch, KB);
+        out_t[o] = hi;
+        if (fmt == FMT_BF16X3) out_t[plane + o] = lo;
+        return;
+    }
+    const __half h = __float2half_rn(r * kActMain);
+    const float hf = __half2float(h) * (1.f / kActMain);
+    reinterpret_cast<__half*>(out_t)[tiled_offset(row, ch, KB)] = h;
+    // second plane: 16-channel group m = ch / 16 occupies chunks 2m (c0) and 2m + 1 (c1), one byte per channel
+    const int m = ch >> 4, i = ch & 15;
+    unsigned char* base = reinterpret_cast<unsigned char*>(out_t + plane);
+    const uint32_t c0 = e4m3x2(hf, 0.f) & 0xffu, c1 = e4m3x2((r - hf) * 4096.f, 0.f) & 0xffu;
+    base[2 * tiled_offset(row, 16 * m, KB) + i] = (unsigned char)c0;
+    base[2 * tiled_offset(row, 16 * m + 8, KB) + i] = (unsigned char)c1;
+}
+
 // ------------------------------------------------------------------------------------------ GEMM
 
 enum { EPI_ACT = 0, EPI_MAX = 1, EPI_T2 = 2, EPI_DOT = 3 };
@@ -214,7 +358,7 @@ struct GemmArgs {
     size_t a_plane;      // element offset of the lo plane (hi at 0)
     size_t b_plane;
     int KB;              // 64-column k-blocks
-    int nprod;           // 1 (bf16) or 3 (hi*hi + hi*lo + lo*hi)
+    int fmt;             // FMT_BF16X3 (hi*hi + hi*lo + lo*hi), FMT_BF16 (hi*hi) or FMT_F16F8 (fp16 hi*hi + one e4m3 MMA)
     int n_mma;           // N of each UMMA (64 or 128)
     int tmode;           // 0: N orientation (A = activations), 1: T orientation (A = weights)
     int rows_per_patch;  // points per patch (N mode, activations) or 0 when rows are patches
@@ -255,7 +399,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
     __shared__ float s_w4[EPI == EPI_DOT ? 128 : 1];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int planes = g.nprod > 1 ? 2 : 1;
+    const int planes = fmt_planes(g.fmt);
     const uint32_t stage_bytes = (uint32_t)planes * (1 + NT) * kBlkBytes;
     constexpr uint32_t kTmemCols = NT == 1 ? 128 : (NT == 2 ? 256 : 512);
 
@@ -323,7 +467,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
-            const uint32_t idesc = umma_idesc(g.n_mma);
+            const uint32_t idesc = umma_idesc(g.n_mma, fmt_code(g.fmt));
             bool ok = true;
             for (int kb = 0; kb < g.KB && ok; ++kb) {
                 const int s = kb % stages;
@@ -342,11 +486,8 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint32_t koff = (uint32_t)ks * 2 * g.lbo;  // 16 elements = two 16-byte k-chunks
                         const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-                        umma_bf16(d, umma_desc(sa_hi + koff, g.lbo, g.sbo), umma_desc(sb_hi + koff, g.lbo, g.sbo), idesc, first);
-                        if (g.nprod > 1) {
-                            umma_bf16(d, umma_desc(sa_hi + koff, g.lbo, g.sbo), umma_desc(sb_lo + koff, g.lbo, g.sbo), idesc, 1u);
-                            umma_bf16(d, umma_desc(sa_lo + koff, g.lbo, g.sbo), umma_desc(sb_hi + koff, g.lbo, g.sbo), idesc, 1u);
-                        }
+                        mma_kstep(g.fmt, d, umma_desc(sa_hi + koff, g.lbo, g.sbo), umma_desc(sa_lo + koff, g.lbo, g.sbo),
+                                  umma_desc(sb_hi + koff, g.lbo, g.sbo), umma_desc(sb_lo + koff, g.lbo, g.sbo), idesc, first);
                     }
                 }
                 umma_commit(smem_u32(&s_empty[s]));  // frees the stage when these MMAs have read it
@@ -361,6 +502,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
         tc_fence_after();
         if (ok) {
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16);
+            const float asc = fmt_acc_scale(g.fmt);
             uint32_t v[32];
             if (EPI == EPI_MAX) {
                 float m = -3.402823466e38f;
@@ -371,17 +513,11 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
                     for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
                 }
                 const long long ch = a_tile * 128 + lrow;
-                float r = m + (g.bias ? g.bias[ch] : 0.f);
+                float r = fmaf(m, asc, g.bias ? g.bias[ch] : 0.f);
                 if (g.relu) r = fmaxf(r, 0.f);
                 if (patch < g.m_valid) {
                     if (g.out_f) g.out_f[patch * g.ldo + ch] = r;
-                    if (g.out_t) {
-                        bf16 hi, lo;
-                        split_bf16(r, hi, lo);
-                        const size_t o = tiled_offset(patch, (int)ch, g.out_KB);
-                        g.out_t[o] = hi;
-                        g.out_t[g.out_plane + o] = lo;
-                    }
+                    if (g.out_t) store_one_act(g.fmt, g.out_t, g.out_plane, patch, (int)ch, g.out_KB, r);
                 }
             } else {
                 const long long row = a_tile * 128 + lrow;
@@ -396,7 +532,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
                         float f[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            float x = __uint_as_float(v[i]) + s_bias[cl + i];
+                            float x = fmaf(__uint_as_float(v[i]), asc, s_bias[cl + i]);
                             if (g.relu) x = fmaxf(x, 0.f);
                             f[i] = x;
                         }
@@ -408,17 +544,15 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
                         if (col0 >= g.n_valid || row >= g.m_valid) continue;
                         if (EPI == EPI_ACT) {
                             if (g.out_t) {
+                                uint32_t ph[16], plo[16];
+                                if (split32<false>(g.fmt, f, ph, plo) > kActLimit) atomicCAS(g.err, 0, 100);
 #pragma unroll
                                 for (int c8 = 0; c8 < 4; ++c8) {
-                                    uint32_t ph[4], plo[4];
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        split_pair(f[c8 * 8 + 2 * e], f[c8 * 8 + 2 * e + 1], ph[e], plo[e]);
-                                    }
                                     const size_t o = tiled_offset(row, (int)col0 + c8 * 8, g.out_KB, g.out_br);
-                                    *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                                    if (g.nprod > 1)
-                                        *reinterpret_cast<uint4*>(g.out_t + g.out_plane + o) = make_uint4(plo[0], plo[1], plo[2], plo[3]);
+                                    *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[4 * c8], ph[4 * c8 + 1], ph[4 * c8 + 2], ph[4 * c8 + 3]);
+                                    if (planes > 1)
+                                        *reinterpret_cast<uint4*>(g.out_t + g.out_plane + o) =
+                                            make_uint4(plo[4 * c8], plo[4 * c8 + 1], plo[4 * c8 + 2], plo[4 * c8 + 3]);
                                 }
                             }
                             if (g.out_f) {
@@ -430,19 +564,32 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
                             // per-patch B operand  T2^T[n][kk]  in tiled form, one 128-row block per patch.  The host
                             // permuted the fc3 rows so that output column c = (kk>>3)*512 + (n>>3)*64 + (n&7)*8 + (kk&7)
                             // is the block's own memory order: a thread's 32 columns are 64 contiguous bytes per plane
+                            // T2^T is the WEIGHT-side operand of the x*T2 layer.  A thread's 32 columns are four runs of 8
+                            // consecutive kk (one 16-byte chunk of the main plane each) for four rows n.  The f16f8 correction
+                            // plane groups 16 kk: chunk 2m = c0 of kk 16m..16m+15, chunk 2m+1 = c1 -- a run fills one half
+                            // (8 bytes) of each.
 #pragma unroll
                             for (int c8 = 0; c8 < 4; ++c8) {
                                 const int col = (int)col0 + c8 * 8;
                                 const int n = (((col >> 6) & 7) << 3) | ((col >> 3) & 7), kk = (col >> 9) << 3;
-                                uint32_t ph[4], plo[4];
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    split_pair(f[c8 * 8 + 2 * e], f[c8 * 8 + 2 * e + 1], ph[e], plo[e]);
-                                }
                                 const size_t o = (size_t)row * kBlkElems + (size_t)(col >> 9) * 1024 + (size_t)(col & 511);
-                                *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                                if (g.nprod > 1)
-                                    *reinterpret_cast<uint4*>(g.out_t + g.out_plane + o) = make_uint4(plo[0], plo[1], plo[2], plo[3]);
+                                uint32_t ph[4], plo[4];
+                                if (g.fmt != FMT_F16F8) {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) split_pair(f[c8 * 8 + 2 * e], f[c8 * 8 + 2 * e + 1], ph[e], plo[e]);
+                                    *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                                    if (planes > 1) *reinterpret_cast<uint4*>(g.out_t + g.out_plane + o) = make_uint4(plo[0], plo[1], plo[2], plo[3]);
+                                } else {
+                                    uint32_t c0[4], c1[4];
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) f16f8_pair<true>(f[c8 * 8 + 2 * e], f[c8 * 8 + 2 * e + 1], ph[e], c0[e], c1[e]);
+                                    *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                                    const int j = col >> 9, m2 = j >> 1, half = j & 1;
+                                    unsigned char* pb = reinterpret_cast<unsigned char*>(g.out_t + g.out_plane + (size_t)row * kBlkElems);
+                                    const size_t rowb = ((size_t)(n >> 3) * 64 + (size_t)(n & 7) * 8) * 2 + (size_t)half * 8;
+                                    *reinterpret_cast<uint2*>(pb + (size_t)(2 * m2) * 2048 + rowb) = make_uint2(c0[0] | (c0[1] << 16), c0[2] | (c0[3] << 16));
+                                    *reinterpret_cast<uint2*>(pb + (size_t)(2 * m2 + 1) * 2048 + rowb) = make_uint2(c1[0] | (c1[1] << 16), c1[2] | (c1[3] << 16));
+                                }
                                 if (g.trans2) {
 #pragma unroll
                                     for (int e = 0; e < 8; ++e) g.trans2[(size_t)row * 4096 + (size_t)(kk + e) * 64 + n] = f[c8 * 8 + e];
@@ -486,7 +633,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_max_resident_kernel(const G
     __shared__ __align__(8) uint64_t s_xfull, s_wfull[4], s_wempty[4], s_tfull[2], s_tempty[2];
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int planes = g.nprod > 1 ? 2 : 1;
+    const int planes = fmt_planes(g.fmt);
     const int KB = g.KB;
     const int CT = g.n_valid / 128;
     const uint32_t x_bytes = (uint32_t)planes * NT * KB * kBlkBytes;
@@ -542,7 +689,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_max_resident_kernel(const G
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            const uint32_t idesc = umma_idesc(NT * 128);   // one MMA spans the whole patch (N = k)
+            const uint32_t idesc = umma_idesc(NT * 128, fmt_code(g.fmt));   // one MMA spans the whole patch (N = k)
             const uint32_t lbo_b = (uint32_t)NT * kLBO;
             bool ok = mbar_wait(smem_u32(&s_xfull), 0u, g.err, 2);
             for (int ct = 0; ct < CT && ok; ++ct) {
@@ -567,11 +714,8 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_max_resident_kernel(const G
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint32_t ka = (uint32_t)ks * 2 * kLBO, kb_off = (uint32_t)ks * 2 * lbo_b;
                             const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-                            umma_bf16(d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(b_hi + kb_off, lbo_b, kSBO), idesc, first);
-                            if (g.nprod > 1) {
-                                umma_bf16(d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(b_lo + kb_off, lbo_b, kSBO), idesc, 1u);
-                                umma_bf16(d, umma_desc(a_lo + ka, kLBO, kSBO), umma_desc(b_hi + kb_off, lbo_b, kSBO), idesc, 1u);
-                            }
+                            mma_kstep(g.fmt, d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(a_lo + ka, kLBO, kSBO),
+                                      umma_desc(b_hi + kb_off, lbo_b, kSBO), umma_desc(b_lo + kb_off, lbo_b, kSBO), idesc, first);
                         }
                     }
                     umma_commit(smem_u32(&s_wempty[s]));
@@ -600,16 +744,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_max_resident_kernel(const G
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&s_tempty[buf]));
             const long long ch = (long long)ct * 128 + lrow;
-            float r = mx + (g.bias ? g.bias[ch] : 0.f);
+            float r = fmaf(mx, fmt_acc_scale(g.fmt), g.bias ? g.bias[ch] : 0.f);
             if (g.relu) r = fmaxf(r, 0.f);
             if (g.out_f) g.out_f[patch * g.ldo + ch] = r;
-            if (g.out_t) {
-                bf16 hi, lo;
-                split_bf16(r, hi, lo);
-                const size_t o = tiled_offset(patch, (int)ch, g.out_KB);
-                g.out_t[o] = hi;
-                g.out_t[g.out_plane + o] = lo;
-            }
+            if (g.out_t) store_one_act(g.fmt, g.out_t, g.out_plane, patch, (int)ch, g.out_KB, r);
         }
     }
     tc_fence_before();
@@ -648,7 +786,7 @@ struct HeadArgs {
     const float* b2;     // fp32 [256]
     int rows_per_patch;
     long long m_valid;
-    int nprod;
+    int fmt;             // FMT_*
     bf16* out_t;         // tiled [rows, 256] (only when layer 3 is not fused)
     size_t out_plane;
     int out_KB;
@@ -683,15 +821,14 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 template <int C0>
 __device__ __forceinline__ void head_convert32(const HeadArgs& g, uint32_t tmem_row) {
     uint32_t v[32], ph[16], pl[16];
+    float f[32];
     tmem_ld32(tmem_row + (uint32_t)C0, v);
+    const float asc = fmt_acc_scale(g.fmt);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-        const float x0 = fmaxf(__uint_as_float(v[2 * e]) + g.b2c[C0 + 2 * e], 0.f);
-        const float x1 = fmaxf(__uint_as_float(v[2 * e + 1]) + g.b2c[C0 + 2 * e + 1], 0.f);
-        split_pair(x0, x1, ph[e], pl[e]);
-    }
+    for (int i = 0; i < 32; ++i) f[i] = fmaxf(fmaf(__uint_as_float(v[i]), asc, g.b2c[C0 + i]), 0.f);
+    if (split32<false>(g.fmt, f, ph, pl) > kActLimit) atomicCAS(g.err, 0, 100);
     tmem_st16(tmem_row + (uint32_t)C0, ph);
-    if (g.nprod > 1) tmem_st16(tmem_row + (uint32_t)C0 + 16u, pl);
+    if (g.fmt != FMT_BF16) tmem_st16(tmem_row + (uint32_t)C0 + 16u, pl);
     tmem_st_wait();
     tc_fence_before();
 }
@@ -700,9 +837,10 @@ template <int C0>
 __device__ __forceinline__ float head_dot32(const HeadArgs& g, uint32_t tmem_row) {
     uint32_t v[32];
     tmem_ld32(tmem_row + 256u + (uint32_t)C0, v);
+    const float asc = fmt_acc_scale(g.fmt);
     float dot = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) dot = fmaf(fmaxf(__uint_as_float(v[i]) + g.b3c[C0 + i], 0.f), g.w4c[C0 + i], dot);
+    for (int i = 0; i < 32; ++i) dot = fmaf(fmaxf(fmaf(__uint_as_float(v[i]), asc, g.b3c[C0 + i]), 0.f), g.w4c[C0 + i], dot);
     return dot;
 }
 
@@ -723,7 +861,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
     __shared__ uint32_t s_tmem;
     __shared__ float s_hg[512];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int planes = g.nprod > 1 ? 2 : 1;
+    const int planes = fmt_planes(g.fmt);
     const int n_tiles = g.n_tiles;   // persistent CTAs: tile = blockIdx.x, blockIdx.x + gridDim.x, ...
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t W3A = smem_base;
@@ -843,7 +981,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
         // ===================== layer-1 MMA issuer (its own thread: tcgen05.commit tracks per-thread groups, so
         // layer 1 runs ahead, throttled only by the three D1/h1 buffers, and never delays the layer-2 issue loop)
         if (elect_one()) {
-            const uint32_t idesc64 = umma_idesc(64);
+            const uint32_t idesc64 = umma_idesc(64, fmt_code(g.fmt));
             bool ok = true;
             for (int it = 0, tile = blockIdx.x; tile < n_tiles && ok; ++it, tile += gridDim.x) {
             for (int c = 0; c < 8 && ok; ++c) {   // D1[c % 3] = pf * W1chunk(c)^T
@@ -866,11 +1004,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                     if (g.dbg & 8) break;   // experiment: no layer-1 MMAs
                     const uint32_t a_hi = tmem_base + kPfHi + (uint32_t)ks * 8u, a_lo = tmem_base + kPfLo + (uint32_t)ks * 8u;
                     const uint32_t kw = (uint32_t)ks * 2 * 1024u;
-                    umma_bf16_ts(d, a_hi, umma_desc(w_hi + kw, 1024u, kSBO), idesc64, ks ? 1u : 0u);
-                    if (g.nprod > 1) {
-                        umma_bf16_ts(d, a_hi, umma_desc(w_lo + kw, 1024u, kSBO), idesc64, 1u);
-                        umma_bf16_ts(d, a_lo, umma_desc(w_hi + kw, 1024u, kSBO), idesc64, 1u);
-                    }
+                    mma_kstep_ts(g.fmt, d, a_hi, a_lo, umma_desc(w_hi + kw, 1024u, kSBO), umma_desc(w_lo + kw, 1024u, kSBO), idesc64,
+                                 ks ? 1u : 0u);
                 }
                 umma_commit(smem_u32(&s_w1e[s]));
                 umma_commit(smem_u32(&s_d1f[b]));
@@ -880,7 +1015,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
     } else if (warp == 1) {
         // ===================== layer-2 / layer-3 MMA issuer =====================
         if (elect_one()) {
-            const uint32_t idesc256 = umma_idesc(256);
+            const uint32_t idesc256 = umma_idesc(256, fmt_code(g.fmt));
             bool ok = true;
             int w2i = 0;
             for (int it = 0, tile = blockIdx.x; tile < n_tiles && ok; ++it, tile += gridDim.x) {
@@ -905,11 +1040,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                         // k-step 2h+ks of the chunk: the epilogue half h wrote its 32 channels as [hi 16 | lo 16] columns
                         const uint32_t a_hi = buf + (uint32_t)h * 32u + (uint32_t)ks * 8u, a_lo = a_hi + 16u;
                         const uint32_t kw = (uint32_t)ks * 2 * (2 * kLBO);       // 256-row block: LBO = 4096
-                        umma_bf16_ts(d, a_hi, umma_desc(b_hi + kw, 2 * kLBO, kSBO), idesc256, (c == 0 && h == 0 && ks == 0) ? 0u : 1u);
-                        if (g.nprod > 1) {
-                            umma_bf16_ts(d, a_hi, umma_desc(b_lo + kw, 2 * kLBO, kSBO), idesc256, 1u);
-                            umma_bf16_ts(d, a_lo, umma_desc(b_hi + kw, 2 * kLBO, kSBO), idesc256, 1u);
-                        }
+                        mma_kstep_ts(g.fmt, d, a_hi, a_lo, umma_desc(b_hi + kw, 2 * kLBO, kSBO), umma_desc(b_lo + kw, 2 * kLBO, kSBO),
+                                     idesc256, (c == 0 && h == 0 && ks == 0) ? 0u : 1u);
                     }
                     umma_commit(smem_u32(&s_w2e[s]));
                     ++w2i;
@@ -919,7 +1051,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             }
             if (ok) umma_commit(smem_u32(&s_d2f));
             if (ok && g.fuse_l3) {
-                const uint32_t idesc128 = umma_idesc(128);
+                const uint32_t idesc128 = umma_idesc(128, fmt_code(g.fmt));
                 for (int kb = 0; kb < 4 && ok; ++kb) {
                     // k-blocks 2r, 2r+1 of h2 are converted (in place, inside D2) by all 16 epilogue warps in their round
                     // r, so layer 3 starts while the second half of the layer-2 accumulator is still being converted
@@ -944,11 +1076,8 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                         // k-step ks of k-block kb: 32-channel group 2kb + (ks >> 1), [hi 16 | lo 16] columns
                         const uint32_t a_hi = tmem_base + (uint32_t)(2 * kb + (ks >> 1)) * 32u + (uint32_t)(ks & 1) * 8u, a_lo = a_hi + 16u;
                         const uint32_t koff = (uint32_t)ks * 2 * kLBO;
-                        umma_bf16_ts(d, a_hi, umma_desc(b_hi + koff, kLBO, kSBO), idesc128, (kb == 0 && ks == 0) ? 0u : 1u);
-                        if (g.nprod > 1) {
-                            umma_bf16_ts(d, a_hi, umma_desc(b_lo + koff, kLBO, kSBO), idesc128, 1u);
-                            umma_bf16_ts(d, a_lo, umma_desc(b_hi + koff, kLBO, kSBO), idesc128, 1u);
-                        }
+                        mma_kstep_ts(g.fmt, d, a_hi, a_lo, umma_desc(b_hi + koff, kLBO, kSBO), umma_desc(b_lo + koff, kLBO, kSBO), idesc128,
+                                     (kb == 0 && ks == 0) ? 0u : 1u);
                     }
                     if (kb == 3) {
                         umma_commit(smem_u32(&s_w2e[s]));
@@ -972,6 +1101,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
         const uint32_t tmem_row = tmem_base + tlane;
         uint32_t v[32];
+        const float asc = fmt_acc_scale(g.fmt);
         bool ok = true;   // after a time-out the warp keeps walking its tiles (the named barriers need all 16 warps) but
                           // skips every wait and all the work
         const bool tl_lane = lane == 0 && (ew & 7) == 0;   // one stamping lane per epilogue group
@@ -986,16 +1116,15 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
             const uint32_t cols = tmem_row + buf_col(b) + (uint32_t)half * 32u;
             tmem_ld32(cols, v);
             uint32_t ph[16], pl[16];
+            float f[32];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const float b0 = bias_global ? __ldg(bias32 + 2 * e) : bias32[2 * e];
-                const float b1 = bias_global ? __ldg(bias32 + 2 * e + 1) : bias32[2 * e + 1];
-                const float x0 = fmaxf(__uint_as_float(v[2 * e]) + b0, 0.f);
-                const float x1 = fmaxf(__uint_as_float(v[2 * e + 1]) + b1, 0.f);
-                split_pair(x0, x1, ph[e], pl[e]);
+            for (int i = 0; i < 32; ++i) {
+                const float bi = bias_global ? __ldg(bias32 + i) : bias32[i];
+                f[i] = fmaxf(fmaf(__uint_as_float(v[i]), asc, bi), 0.f);
             }
+            if (split32<false>(g.fmt, f, ph, pl) > kActLimit) atomicCAS(g.err, 0, 100);
             tmem_st16(cols, ph);
-            if (g.nprod > 1) tmem_st16(cols + 16u, pl);
+            if (g.fmt != FMT_BF16) tmem_st16(cols + 16u, pl);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -1051,19 +1180,17 @@ __global__ void __launch_bounds__(kHeadThreads) head_fused_kernel(const HeadArgs
                 for (int c0 = quarter * 64; c0 < quarter * 64 + 64; c0 += 32) {
                     tmem_ld32(tmem_row + (uint32_t)c0, v);
                     if (row >= g.m_valid) continue;
+                    uint32_t ph[16], pl[16];
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = fmaxf(fmaf(__uint_as_float(v[i]), asc, __ldg(g.b2 + c0 + i)), 0.f);
+                    split32<false>(g.fmt, f, ph, pl);
 #pragma unroll
                     for (int c8 = 0; c8 < 4; ++c8) {
-                        uint32_t ph[4], pl[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int i0 = c8 * 8 + 2 * e;
-                            const float x0 = fmaxf(__uint_as_float(v[i0]) + __ldg(g.b2 + c0 + i0), 0.f);
-                            const float x1 = fmaxf(__uint_as_float(v[i0 + 1]) + __ldg(g.b2 + c0 + i0 + 1), 0.f);
-                            split_pair(x0, x1, ph[e], pl[e]);
-                        }
                         const size_t o = tiled_offset(row, c0 + c8 * 8, g.out_KB);
-                        *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                        if (g.nprod > 1) *reinterpret_cast<uint4*>(g.out_t + g.out_plane + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                        *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[4 * c8], ph[4 * c8 + 1], ph[4 * c8 + 2], ph[4 * c8 + 3]);
+                        if (g.fmt != FMT_BF16)
+                            *reinterpret_cast<uint4*>(g.out_t + g.out_plane + o) = make_uint4(pl[4 * c8], pl[4 * c8 + 1], pl[4 * c8 + 2], pl[4 * c8 + 3]);
                     }
                 }
                 tc_fence_before();
@@ -1188,7 +1315,7 @@ struct ChainArgs {
     size_t out_plane;
     int out_KB;
     float* out_f;             // optional fp32 [n, n_ch]
-    int nprod;
+    int fmt;                  // FMT_*
     long long* tl;            // timeline region or NULL
     int tl_cta;
     int* err;
@@ -1197,13 +1324,18 @@ struct ChainArgs {
 constexpr int kChainEpiWarps = 16;
 
 // relu(W0 p + b0), all 64 channels of one point, as packed bf16 hi / lo pairs (every weight a constant-bank operand)
+// (32-channel halves in the tensor-memory packing [main 16 | second plane 16])
 __device__ __forceinline__ void chain_first_layer(const ChainArgs& g, float x, float y, float z, uint32_t (&ph)[32], uint32_t (&pl)[32]) {
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-        const int c = 2 * e;
-        const float f0 = fmaxf(fmaf(g.w0c[c * 3 + 2], z, fmaf(g.w0c[c * 3 + 1], y, fmaf(g.w0c[c * 3], x, g.b0c[c]))), 0.f);
-        const float f1 = fmaxf(fmaf(g.w0c[c * 3 + 5], z, fmaf(g.w0c[c * 3 + 4], y, fmaf(g.w0c[c * 3 + 3], x, g.b0c[c + 1]))), 0.f);
-        split_pair(f0, f1, ph[e], pl[e]);
+    for (int hf = 0; hf < 2; ++hf) {
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int c = 32 * hf + i;
+            f[i] = fmaxf(fmaf(g.w0c[c * 3 + 2], z, fmaf(g.w0c[c * 3 + 1], y, fmaf(g.w0c[c * 3], x, g.b0c[c]))), 0.f);
+        }
+        if (split32<false>(g.fmt, f, reinterpret_cast<uint32_t(&)[16]>(ph[16 * hf]), reinterpret_cast<uint32_t(&)[16]>(pl[16 * hf])) > kActLimit)
+            atomicCAS(g.err, 0, 100);
     }
 }
 constexpr int kChainThreads = 64 + kChainEpiWarps * 32;
@@ -1214,7 +1346,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
     __shared__ __align__(8) uint64_t s_act[2], s_acc[2], s_acc_solo, s_rf[3], s_re[3], s_tf[2], s_te[2], s_b0;
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int planes = g.nprod > 1 ? 2 : 1;
+    const int planes = fmt_planes(g.fmt);
     const int n_patch = g.n_patch;   // persistent CTAs: patch = blockIdx.x, blockIdx.x + gridDim.x, ...
     constexpr int KB3 = 2;                                   // 128 input channels of the max layer
     constexpr uint32_t kXBytes = 2u * NT * KB3 * kBlkBytes;  // the 128-channel activations, both planes
@@ -1311,7 +1443,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                     // the last small layer accumulates in buffer 1
                     if (ok && l == L - 1 && it > 0) ok = mbar_wait<true>(smem_u32(&s_te[1]), (uint32_t)(it * TPB - 1) & 1u, g.err, 4);
                     if (!ok) break;
-                    const uint32_t idesc = umma_idesc(g.L[l].n_out);
+                    const uint32_t idesc = umma_idesc(g.L[l].n_out, fmt_code(g.fmt));
                     const uint32_t w_hi = RR + (uint32_t)s * (2u * kBlkBytes), w_lo = w_hi + kBlkBytes;
 #pragma unroll
                     for (int t = 0; t < NT; ++t) {
@@ -1326,11 +1458,8 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                             // k-step ks of the 64 input channels: 32-channel half ks >> 1, [hi 16 | lo 16] columns
                             const uint32_t a_hi = a + (uint32_t)(ks >> 1) * 32u + (uint32_t)(ks & 1) * 8u, a_lo = a_hi + 16u;
                             const uint32_t koff = (uint32_t)ks * 2 * kLBO;
-                            umma_bf16_ts(d, a_hi, umma_desc(w_hi + koff, kLBO, kSBO), idesc, ks ? 1u : 0u);
-                            if (g.nprod > 1) {
-                                umma_bf16_ts(d, a_hi, umma_desc(w_lo + koff, kLBO, kSBO), idesc, 1u);
-                                umma_bf16_ts(d, a_lo, umma_desc(w_hi + koff, kLBO, kSBO), idesc, 1u);
-                            }
+                            mma_kstep_ts(g.fmt, d, a_hi, a_lo, umma_desc(w_hi + koff, kLBO, kSBO), umma_desc(w_lo + koff, kLBO, kSBO), idesc,
+                                         ks ? 1u : 0u);
                         }
                         umma_commit(smem_u32((l == 0 && L > 1 && t == 1) ? &s_acc_solo : &s_acc[t]));
                     }
@@ -1340,7 +1469,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                 for (int t = 0; t < NT && ok; ++t)
                     ok = mbar_wait<true>(smem_u32(&s_act[t]), (uint32_t)L & 1u, g.err, 5);   // X written
                 CTL(22);
-                const uint32_t idesc = umma_idesc(NT * 128);
+                const uint32_t idesc = umma_idesc(NT * 128, fmt_code(g.fmt));
                 const uint32_t lbo_b = (uint32_t)NT * kLBO;
                 for (int ct = 0; ct < CT && ok; ++ct) {
                     const int buf = ct & 1;
@@ -1363,11 +1492,8 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint32_t ka = (uint32_t)ks * 2 * kLBO, kbo = (uint32_t)ks * 2 * lbo_b;
                             const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-                            umma_bf16(d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(b_hi + kbo, lbo_b, kSBO), idesc, first);
-                            if (g.nprod > 1) {
-                                umma_bf16(d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(b_lo + kbo, lbo_b, kSBO), idesc, 1u);
-                                umma_bf16(d, umma_desc(a_lo + ka, kLBO, kSBO), umma_desc(b_hi + kbo, lbo_b, kSBO), idesc, 1u);
-                            }
+                            mma_kstep(g.fmt, d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(a_lo + ka, kLBO, kSBO),
+                                      umma_desc(b_hi + kbo, lbo_b, kSBO), umma_desc(b_lo + kbo, lbo_b, kSBO), idesc, first);
                         }
                         umma_commit(smem_u32(&s_re[s]));
                         ++pos;
@@ -1389,6 +1515,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
         const bool active = grp < NT;             // owns a row of the patch in phases P/S
         const int k = g.k;
+        const float asc = fmt_acc_scale(g.fmt);
         bool ok = true;
         uint32_t v[32];
         const bool tl_lane = lane == 0 && q == 0 && half == 0;   // one stamping lane per epilogue group
@@ -1424,7 +1551,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
             const uint32_t cols = tmem_base + tlane + ping(grp);
             tmem_st16(cols, reinterpret_cast<const uint32_t(&)[16]>(ph[0]));
             tmem_st16(cols + 32u, reinterpret_cast<const uint32_t(&)[16]>(ph[16]));
-            if (g.nprod > 1) {
+            if (planes > 1) {
                 tmem_st16(cols + 16u, reinterpret_cast<const uint32_t(&)[16]>(pl[0]));
                 tmem_st16(cols + 48u, reinterpret_cast<const uint32_t(&)[16]>(pl[16]));
             }
@@ -1464,22 +1591,20 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
 #pragma unroll 1
                 for (int cb = cbeg; cb < (solo ? 64 : cbeg + 32); cb += 32) {
                     uint32_t ph[16], pl[16];
+                    float f[32];
                     tmem_ld32(dcol + (uint32_t)cb, v);
                     if (tl_lane && l == 0 && grp == 0) CTL(44);
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        const float x0 = fmaxf(__uint_as_float(v[2 * e]) + bias_r[2 * e], floor_v);
-                        const float x1 = fmaxf(__uint_as_float(v[2 * e + 1]) + bias_r[2 * e + 1], floor_v);
-                        split_pair(x0, x1, ph[e], pl[e]);
-                    }
+                    for (int i = 0; i < 32; ++i) f[i] = fmaxf(fmaf(__uint_as_float(v[i]), asc, bias_r[i]), floor_v);
+                    if (split32<false>(g.fmt, f, ph, pl) > kActLimit) atomicCAS(g.err, 0, 100);
                     tmem_st16(dcol + (uint32_t)cb, ph);
-                    if (g.nprod > 1) tmem_st16(dcol + (uint32_t)cb + 16u, pl);
+                    if (planes > 1) tmem_st16(dcol + (uint32_t)cb + 16u, pl);
                     if (Ly.store_t) {   // x * T2 is also the head's input
 #pragma unroll
                         for (int c8 = 0; c8 < 4; ++c8) {
                             const size_t go = tiled_offset(grow, cb + c8 * 8, 1);
                             *reinterpret_cast<uint4*>(Ly.store_t + go) = make_uint4(ph[4 * c8], ph[4 * c8 + 1], ph[4 * c8 + 2], ph[4 * c8 + 3]);
-                            if (g.nprod > 1)
+                            if (planes > 1)
                                 *reinterpret_cast<uint4*>(Ly.store_t + Ly.store_plane + go) = make_uint4(pl[4 * c8], pl[4 * c8 + 1], pl[4 * c8 + 2], pl[4 * c8 + 3]);
                         }
                     }
@@ -1497,21 +1622,20 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
 #pragma unroll 1
                 for (int c0 = cbeg; c0 < cbeg + (Ly.n_out >> 1); c0 += 32) {
                     tmem_ld32(dcol + (uint32_t)c0, v);
+                    {
+                        uint32_t ph[16], pl[16];
+                        float f[32];
 #pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8) {
-                        uint32_t ph[4], pl[4];
+                        for (int i = 0; i < 32; ++i) f[i] = fmaxf(fmaf(__uint_as_float(v[i]), asc, bias_r[i]), floor_v);
+                        if (split32<false>(g.fmt, f, ph, pl) > kActLimit) atomicCAS(g.err, 0, 100);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int i0 = c8 * 8 + 2 * e;
-                            const float x0 = fmaxf(__uint_as_float(v[i0]) + bias_r[i0], floor_v);
-                            const float x1 = fmaxf(__uint_as_float(v[i0 + 1]) + bias_r[i0 + 1], floor_v);
-                            split_pair(x0, x1, ph[e], pl[e]);
+                        for (int c8 = 0; c8 < 4; ++c8) {
+                            const int col = c0 + c8 * 8;
+                            const uint32_t o = obase + (uint32_t)(col >> 6) * (NT * kBlkBytes) + (uint32_t)((col & 63) >> 3) * (NT * 2048u);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(ph[4 * c8]), "r"(ph[4 * c8 + 1]), "r"(ph[4 * c8 + 2]), "r"(ph[4 * c8 + 3]) : "memory");
+                            if (planes > 1)
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + lo_off), "r"(pl[4 * c8]), "r"(pl[4 * c8 + 1]), "r"(pl[4 * c8 + 2]), "r"(pl[4 * c8 + 3]) : "memory");
                         }
-                        const int col = c0 + c8 * 8;
-                        const uint32_t o = obase + (uint32_t)(col >> 6) * (NT * kBlkBytes) + (uint32_t)((col & 63) >> 3) * (NT * 2048u);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
-                        if (g.nprod > 1)
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + lo_off), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
                     }
                     if (c0 + 32 < cbeg + (Ly.n_out >> 1)) {   // the second 32 columns' bias
 #pragma unroll
@@ -1547,16 +1671,10 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                 if (buf == 0 && ct + 2 >= CT) mbar_arrive(smem_u32(&s_b0));   // buffer 0's last tile of the patch
             }
             const long long ch = (long long)ct * 128 + lrow;
-            float r = mx + (g.bias3 ? g.bias3[ch] : 0.f);
+            float r = fmaf(mx, asc, g.bias3 ? g.bias3[ch] : 0.f);
             if (g.relu3) r = fmaxf(r, 0.f);
             if (g.out_f) g.out_f[(long long)patch * g.n_ch + ch] = r;
-            if (g.out_t) {
-                bf16 hi, lo;
-                split_bf16(r, hi, lo);
-                const size_t o = tiled_offset(patch, (int)ch, g.out_KB);
-                g.out_t[o] = hi;
-                g.out_t[g.out_plane + o] = lo;
-            }
+            if (g.out_t) store_one_act(g.fmt, g.out_t, g.out_plane, patch, (int)ch, g.out_KB, r);
         }
         if (tl_lane) CTL(40 + grp);
         }
@@ -1571,55 +1689,74 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
 // k = 512: the chain kernel ran on 256-point halves (bias and ReLU are monotone, so they commute with the max);
 // the global feature of a patch is the max of its two partial vectors, re-split into the tiled bf16 planes.
 __global__ void chain_combine_kernel(const float* __restrict__ part, long long n_patch, int n_ch, int ipp, bf16* __restrict__ out_t,
-                                     size_t out_plane, int out_KB, int split) {
+                                     size_t out_plane, int out_KB, int fmt) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_patch * n_ch) return;
     const long long p = i / n_ch;
     const int ch = (int)(i % n_ch);
     float r = part[(p * ipp) * n_ch + ch];
     for (int h = 1; h < ipp; ++h) r = fmaxf(r, part[(p * ipp + h) * n_ch + ch]);
-    bf16 hi, lo;
-    split_bf16(r, hi, lo);
-    const size_t o = tiled_offset(p, ch, out_KB);
-    out_t[o] = hi;
-    if (split) out_t[out_plane + o] = lo;
+    store_one_act(fmt, out_t, out_plane, p, ch, out_KB, r);
 }
 
 // --------------------------------------------------------------------------- small CUDA-core kernels
 
-// fp32 row-major [rows, cols] (ld) -> tiled hi/lo planes; rows/cols beyond the source are zero.
+// fp32 row-major [rows, cols] (ld) -> tiled planes in format `fmt` (weight side or activation side for f16f8);
+// rows/cols beyond the source are zero.
 __global__ void pack_tiled_kernel(const float* __restrict__ src, long long rows, int cols, long long ld,
-                                  long long rows_pad, int cols_pad, bf16* __restrict__ dst, size_t plane, int split, int br) {
+                                  long long rows_pad, int cols_pad, bf16* __restrict__ dst, size_t plane, int fmt, int wside, int br) {
     const long long total = rows_pad * (cols_pad / 8);
     const int KB = cols_pad / 64;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i % rows_pad;  // consecutive threads -> consecutive rows -> contiguous 16 B chunks
         const int c8 = (int)(i / rows_pad);
-        uint32_t ph[4], pl[4];
+        uint32_t ph[4], pl[4], c0[4], c1[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             float a = 0.f, b = 0.f;
             const int c = c8 * 8 + 2 * e;
             if (r < rows && c < cols) a = src[r * ld + c];
             if (r < rows && c + 1 < cols) b = src[r * ld + c + 1];
-            split_pair(a, b, ph[e], pl[e]);
+            if (fmt != FMT_F16F8) split_pair(a, b, ph[e], pl[e]);
+            else if (wside) f16f8_pair<true>(a, b, ph[e], c0[e], c1[e]);
+            else f16f8_pair<false>(a, b, ph[e], c0[e], c1[e]);
         }
         const size_t o = tiled_offset(r, c8 * 8, KB, br);
         *reinterpret_cast<uint4*>(dst + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-        if (split) *reinterpret_cast<uint4*>(dst + plane + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        if (fmt == FMT_BF16X3) {
+            *reinterpret_cast<uint4*>(dst + plane + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        } else if (fmt == FMT_F16F8) {
+            // 16-channel group m = c8 / 2: chunk 2m holds c0, chunk 2m + 1 holds c1; this thread fills 8 bytes of each
+            const int m = c8 >> 1, half = c8 & 1;
+            unsigned char* pb = reinterpret_cast<unsigned char*>(dst + plane);
+            *reinterpret_cast<uint2*>(pb + 2 * tiled_offset(r, 16 * m, KB, br) + 8 * half) = make_uint2(c0[0] | (c0[1] << 16), c0[2] | (c0[3] << 16));
+            *reinterpret_cast<uint2*>(pb + 2 * tiled_offset(r, 16 * m + 8, KB, br) + 8 * half) = make_uint2(c1[0] | (c1[1] << 16), c1[2] | (c1[3] << 16));
+        }
     }
 }
 
-// tiled (hi [+ lo]) -> fp32 row-major, for tests
-__global__ void unpack_tiled_kernel(const bf16* __restrict__ src, size_t plane, int split, long long rows, int cols,
+__device__ __forceinline__ float e4m3_to_float(unsigned char b) {
+    const __half_raw hr = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)b, __NV_E4M3);
+    return __half2float(*reinterpret_cast<const __half*>(&hr));
+}
+// tiled planes -> fp32 row-major, for tests (activation-side operands)
+__global__ void unpack_tiled_kernel(const bf16* __restrict__ src, size_t plane, int fmt, long long rows, int cols,
                                     int KB, float* __restrict__ dst, int br) {
     const long long total = rows * cols;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / cols;
         const int c = (int)(i % cols);
         const size_t o = tiled_offset(r, c, KB, br);
-        float v = __bfloat162float(src[o]);
-        if (split) v += __bfloat162float(src[plane + o]);
+        float v;
+        if (fmt != FMT_F16F8) {
+            v = __bfloat162float(src[o]);
+            if (fmt == FMT_BF16X3) v += __bfloat162float(src[plane + o]);
+        } else {
+            // x = xh + xl with xh = main / 2^7 and xl ~ c1 / 2^12 (4 significant bits of the residual)
+            v = __half2float(reinterpret_cast<const __half*>(src)[o]) * (1.f / kActMain);
+            const unsigned char* pb = reinterpret_cast<const unsigned char*>(src + plane);
+            v += e4m3_to_float(pb[2 * tiled_offset(r, 16 * (c >> 4) + 8, KB, br) + (c & 15)]) * (1.f / 4096.f);
+        }
         dst[i] = v;
     }
 }
@@ -1629,7 +1766,7 @@ __global__ void unpack_tiled_kernel(const bf16* __restrict__ src, size_t plane, 
 __global__ void __launch_bounds__(128) pointwise3_kernel(const float* __restrict__ patch, const float* __restrict__ R,
                                                          long long n_patch, int k, const float* __restrict__ W,
                                                          const float* __restrict__ bvec, bf16* __restrict__ out,
-                                                         size_t plane, int split, float* __restrict__ pts_out) {
+                                                         size_t plane, int fmt, float* __restrict__ pts_out) {
     __shared__ float sW[64 * 3 + 64];
     for (int i = threadIdx.x; i < 64 * 3; i += blockDim.x) sW[i] = W[i];
     for (int i = threadIdx.x; i < 64; i += blockDim.x) sW[192 + i] = bvec[i];
@@ -1653,22 +1790,21 @@ __global__ void __launch_bounds__(128) pointwise3_kernel(const float* __restrict
         }
     }
 #pragma unroll
-    for (int c8 = 0; c8 < 8; ++c8) {
-        uint32_t ph[4], pl[4];
+    for (int hf = 0; hf < 2; ++hf) {
+        uint32_t ph[16], pl[16];
+        float f[32];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            float f[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int c = c8 * 8 + 2 * e + u;
-                float a = fmaf(sW[c * 3 + 2], z, fmaf(sW[c * 3 + 1], y, fmaf(sW[c * 3], x, sW[192 + c])));
-                f[u] = fmaxf(a, 0.f);
-            }
-            split_pair(f[0], f[1], ph[e], pl[e]);
+        for (int i = 0; i < 32; ++i) {
+            const int c = 32 * hf + i;
+            f[i] = fmaxf(fmaf(sW[c * 3 + 2], z, fmaf(sW[c * 3 + 1], y, fmaf(sW[c * 3], x, sW[192 + c]))), 0.f);
         }
-        const size_t o = tiled_offset(row, c8 * 8, 1);
-        *reinterpret_cast<uint4*>(out + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-        if (split) *reinterpret_cast<uint4*>(out + plane + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        split32<false>(fmt, f, ph, pl);
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+            const size_t o = tiled_offset(row, 32 * hf + c8 * 8, 1);
+            *reinterpret_cast<uint4*>(out + o) = make_uint4(ph[4 * c8], ph[4 * c8 + 1], ph[4 * c8 + 2], ph[4 * c8 + 3]);
+            if (fmt != FMT_BF16) *reinterpret_cast<uint4*>(out + plane + o) = make_uint4(pl[4 * c8], pl[4 * c8 + 1], pl[4 * c8 + 2], pl[4 * c8 + 3]);
+        }
     }
 }
 
@@ -1709,19 +1845,14 @@ int g_swap_lbo_sbo = 0;  // debug switch (dfb_dbg_set)
 
 template <int NT, int EPI>
 int launch_gemm_t(GemmArgs g, dim3 grid, cudaStream_t st) {
-    const int planes = g.nprod > 1 ? 2 : 1;
+    const int planes = fmt_planes(g.fmt);
     const size_t stage_bytes = (size_t)planes * (1 + NT) * kBlkBytes;
     int stages = (int)((200 * 1024) / stage_bytes);
     if (stages > g.KB) stages = g.KB;
     if (stages > 8) stages = 8;
     if (stages < 1) stages = 1;
     const size_t smem = stages * stage_bytes;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_kernel<NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return check_cuda(e, "gemm smem attribute", __FILE__, __LINE__);
-        attr_done = true;
-    }
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_kernel<NT, EPI>), 200 * 1024)) return rc;
     g.lbo = g_swap_lbo_sbo ? kSBO : kLBO;
     g.sbo = g_swap_lbo_sbo ? kLBO : kSBO;
     gemm_kernel<NT, EPI><<<grid, kGemmThreads, smem, st>>>(g, stages);
@@ -1767,7 +1898,7 @@ struct PackedLayer {
 }  // namespace dfb
 
 struct dfb_model {
-    int k = 0, weight_mode = 0, nprod = 3, max_batch = 0;
+    int k = 0, weight_mode = 0, fmt = 0 /* FMT_* */, max_batch = 0;
     float b4 = 0.f;  // conv4 bias
     dfb::PackedLayer L[DFB_NUM_LAYERS];
     dfb::PackedLayer head_global;  // HEAD_CONV1 columns 0..1023  (bias = folded conv1 bias)
@@ -1869,7 +2000,7 @@ int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, co
     a.hg = hg; a.b2 = W2.bias;
     a.rows_per_patch = m->k;
     a.m_valid = rows;
-    a.nprod = m->nprod;
+    a.fmt = m->fmt;
     a.out_t = out.p; a.out_plane = out.plane; a.out_KB = out.KB;
     a.fuse_l3 = out_w != nullptr;
     a.w3 = m->L[DFB_L_HEAD_CONV3].w.p; a.w3_plane = m->L[DFB_L_HEAD_CONV3].w.plane;
@@ -1890,12 +2021,7 @@ int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, co
     a.err = m->err;
     const size_t smem = 224 * 1024;
     const unsigned tiles = (unsigned)((rows + 127) / 128);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return check_cuda(e, "head_fused smem attribute", __FILE__, __LINE__);
-        attr_done = true;
-    }
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&head_fused_kernel), (int)smem)) return rc;
     a.n_tiles = (int)tiles;
     const unsigned grid = g_head_persistent ? std::min<unsigned>(tiles, (unsigned)sm_count()) : tiles;
     head_fused_kernel<<<grid, kHeadThreads, smem, st>>>(a);
@@ -1903,7 +2029,7 @@ int launch_head_fused(const dfb_model* m, const TiledBuf& pf, long long rows, co
     return check_cuda(cudaGetLastError(), "head_fused_kernel launch", __FILE__, __LINE__);
 }
 
-int upload_pack(const float* h_w, int out, int in, int col0, int ncols, long long ldw, PackedLayer& pl, cudaStream_t st,
+int upload_pack(int fmt, const float* h_w, int out, int in, int col0, int ncols, long long ldw, PackedLayer& pl, cudaStream_t st,
                 const int* row_perm = nullptr, int br = 128) {
     // host fp32 [out, ldw] (columns col0..col0+ncols) -> device tiled hi/lo
     std::vector<float> tmp((size_t)out * ncols);
@@ -1920,7 +2046,7 @@ int upload_pack(const float* h_w, int out, int in, int col0, int ncols, long lon
     pl.out = out;
     const long long total = pl.w.rows_pad * (pl.w.KB * 8);
     pack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_tmp, out, ncols, ncols, pl.w.rows_pad, pl.w.KB * 64,
-                                                                        pl.w.p, pl.w.plane, 1, pl.w.br);
+                                                                        pl.w.p, pl.w.plane, fmt, 1, pl.w.br);
     note_launch();
     DFB_CUDA(cudaGetLastError());
     DFB_CUDA(cudaStreamSynchronize(st));
@@ -1938,7 +2064,7 @@ int upload_f32(const float* h, size_t n, float** d, cudaStream_t st) {
 GemmArgs base_args(const dfb_model* m) {
     GemmArgs g;
     memset(&g, 0, sizeof(g));
-    g.nprod = m->nprod;
+    g.fmt = m->fmt;
     g.n_mma = 128;
     g.err = m->err;
     g.weight_mode = m->weight_mode;
@@ -1978,19 +2104,14 @@ int gemm_n(const dfb_model* m, const TiledBuf& X, long long n_rows, const Packed
 
 template <int NT>
 int launch_max_resident(GemmArgs g, long long n_patch, cudaStream_t st) {
-    const int planes = g.nprod > 1 ? 2 : 1;
+    const int planes = fmt_planes(g.fmt);
     const size_t x_bytes = (size_t)planes * NT * g.KB * kBlkBytes;
     const size_t w_stage = (size_t)planes * kBlkBytes;
     const size_t budget = 227 * 1024 - 2048;
     int wstages = (int)((budget - x_bytes) / w_stage);
     if (wstages > 4) wstages = 4;
     const size_t smem = x_bytes + (size_t)wstages * w_stage;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_max_resident_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
-        if (e != cudaSuccess) return check_cuda(e, "gemm_max_resident smem attribute", __FILE__, __LINE__);
-        attr_done = true;
-    }
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_max_resident_kernel<NT>), (int)budget)) return rc;
     g.lbo = kLBO;
     g.sbo = kSBO;
     gemm_max_resident_kernel<NT><<<(unsigned)n_patch, kGemmThreads, smem, st>>>(g, wstages);
@@ -2016,17 +2137,31 @@ static inline float host_bf16_to_f(uint16_t h) {
 
 // HEAD_CONV1[:, 1024:1088] (512 x 64) -> 8 chunks of 64 output channels, each [hi 8 KB | lo 8 KB] in
 // K-major core-matrix order [k-chunk j][row-group i][8 rows][8 elements] (LBO 1024 B, SBO 128 B).
-int upload_head_w1_chunks(const float* h_w, long long ldw, int col0, bf16** d_out, cudaStream_t st) {
+int upload_head_w1_chunks(int fmt, const float* h_w, long long ldw, int col0, bf16** d_out, cudaStream_t st) {
     std::vector<uint16_t> buf((size_t)8 * 8192);
+    unsigned char* bytes = reinterpret_cast<unsigned char*>(buf.data());
     for (int c = 0; c < 8; ++c)
         for (int r = 0; r < 64; ++r)
             for (int kc = 0; kc < 64; ++kc) {
                 const float v = h_w[(size_t)(c * 64 + r) * ldw + col0 + kc];
-                const uint16_t hi = host_bf16(v);
-                const uint16_t lo = host_bf16(v - host_bf16_to_f(hi));
                 const size_t o = (size_t)c * 8192 + (size_t)(kc >> 3) * 512 + (size_t)(r >> 3) * 64 + (size_t)(r & 7) * 8 + (kc & 7);
-                buf[o] = hi;
-                buf[o + 4096] = lo;
+                if (fmt != FMT_F16F8) {
+                    const uint16_t hi = host_bf16(v);
+                    const uint16_t lo = host_bf16(v - host_bf16_to_f(hi));
+                    buf[o] = hi;
+                    buf[o + 4096] = lo;
+                } else {
+                    // weight side of f16f8: main = fp16(w * 2^8); second plane per 16-kc group: chunk 2m = e4m3(wl * 2^15),
+                    // chunk 2m + 1 = e4m3(wh * 2^3)
+                    const __half h = __float2half_rn(v * kWgtMain);
+                    buf[o] = *reinterpret_cast<const uint16_t*>(&h);
+                    const float wh = __half2float(h) * (1.f / kWgtMain), wl = v - wh;
+                    const size_t rowb = ((size_t)(r >> 3) * 64 + (size_t)(r & 7) * 8) * 2 + (size_t)(kc & 15);
+                    const size_t base = ((size_t)c * 8192 + 4096) * 2;
+                    const int m2 = kc >> 4;
+                    bytes[base + (size_t)(2 * m2) * 1024 + rowb] = (unsigned char)__nv_cvt_float_to_fp8(wl * 32768.f, __NV_SATFINITE, __NV_E4M3);
+                    bytes[base + (size_t)(2 * m2 + 1) * 1024 + rowb] = (unsigned char)__nv_cvt_float_to_fp8(wh * 8.f, __NV_SATFINITE, __NV_E4M3);
+                }
             }
     DFB_CUDA(cudaMalloc(d_out, buf.size() * sizeof(uint16_t)));
     DFB_CUDA(cudaMemcpyAsync(*d_out, buf.data(), buf.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
@@ -2071,7 +2206,7 @@ int launch_chain(const dfb_model* m, const float* patch, long long n_patch, cons
     }
     a.w3 = sp.W3->w.p; a.w3_plane = sp.W3->w.plane; a.bias3 = sp.W3->bias; a.relu3 = sp.relu3; a.n_ch = sp.W3->out;
     a.out_t = gfeat.p; a.out_plane = gfeat.plane; a.out_KB = gfeat.KB;
-    a.nprod = m->nprod; a.err = m->err;
+    a.fmt = m->fmt; a.err = m->err;
     a.tl = timeline_region(sp.n_layers == 1 ? 0 : (sp.relu3 ? 1 : 2)); a.tl_cta = g_tl_cta;
     // k = 512: a patch's 256 KB of activations do not fit shared memory, so it is processed as two 256-point work items
     const int ipp = m->k == 512 ? 2 : 1;
@@ -2083,13 +2218,8 @@ int launch_chain(const dfb_model* m, const float* patch, long long n_patch, cons
     }
     n_patch *= ipp;
     const size_t smem = (size_t)2 * NT * 2 * kBlkBytes + 96 * 1024;
-    static bool attr_done[3] = {false, false, false};
-    if (!attr_done[NT]) {
-        cudaError_t e = NT == 1 ? cudaFuncSetAttribute(chain_max_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                : cudaFuncSetAttribute(chain_max_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return check_cuda(e, "chain_max smem attribute", __FILE__, __LINE__);
-        attr_done[NT] = true;
-    }
+    if (int rc = ensure_dyn_smem(NT == 1 ? reinterpret_cast<const void*>(&chain_max_kernel<1>)
+                                         : reinterpret_cast<const void*>(&chain_max_kernel<2>), (int)smem)) return rc;
     a.n_patch = (int)n_patch;
     // the per-tile barriers of the small layers complete n_layers + 1 times per patch: persistence needs that even
     const bool persistent = g_chain_persistent && (sp.n_layers & 1) && (sp.W3->out / 128) % 2 == 0;
@@ -2100,7 +2230,7 @@ int launch_chain(const dfb_model* m, const float* patch, long long n_patch, cons
     if (ipp > 1) {
         const long long total = (n_patch / ipp) * a.n_ch;
         chain_combine_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m->chain_part, n_patch / ipp, a.n_ch, ipp, gfeat.p, gfeat.plane,
-                                                                              gfeat.KB, m->nprod > 1 ? 1 : 0);
+                                                                              gfeat.KB, m->fmt);
         note_launch();
     }
     return check_cuda(cudaGetLastError(), "chain_max_kernel launch", __FILE__, __LINE__);
@@ -2122,8 +2252,8 @@ int gemm_t_max(const dfb_model* m, const PackedLayer& W, const TiledBuf& X, long
     if (out) { g.out_t = out->p; g.out_plane = out->plane; g.out_KB = out->KB; g.out_br = out->br; }
     g.out_f = out_f; g.ldo = W.out;
     const int NT = m->k / 128;
-    const size_t x_bytes = (size_t)(m->nprod > 1 ? 2 : 1) * NT * g.KB * kBlkBytes;
-    if (g_max_resident && NT <= 2 && X.br == NT * 128 && x_bytes + 2 * (size_t)(m->nprod > 1 ? 2 : 1) * kBlkBytes <= 225 * 1024) {
+    const size_t x_bytes = (size_t)fmt_planes(m->fmt) * NT * g.KB * kBlkBytes;
+    if (g_max_resident && NT <= 2 && X.br == NT * 128 && x_bytes + 2 * (size_t)fmt_planes(m->fmt) * kBlkBytes <= 225 * 1024) {
         return NT == 1 ? launch_max_resident<1>(g, n_patch, st) : launch_max_resident<2>(g, n_patch, st);
     }
     if (X.br != 128) {
@@ -2135,6 +2265,10 @@ int gemm_t_max(const dfb_model* m, const PackedLayer& W, const TiledBuf& X, long
 }
 
 }  // namespace
+}  // namespace dfb
+
+namespace dfb {
+int model_k(const dfb_model* m) { return m->k; }
 }  // namespace dfb
 
 extern "C" int dfb_model_profile(dfb_model* m, int32_t enable) {
@@ -2237,7 +2371,7 @@ extern "C" int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, d
     dfb_model* m = new dfb_model();
     m->k = desc->k;
     m->weight_mode = desc->weight_mode;
-    m->nprod = desc->precision == DFB_PRECISION_BF16 ? 1 : 3;
+    m->fmt = desc->precision == DFB_PRECISION_BF16 ? FMT_BF16 : (desc->precision == DFB_PRECISION_F16F8 ? FMT_F16F8 : FMT_BF16X3);
     m->max_batch = desc->max_batch > 0 ? (desc->max_batch + 127) / 128 * 128 : 1024;
 #define DFB_TRY(expr)                     \
     do {                                  \
@@ -2248,6 +2382,19 @@ extern "C" int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, d
         }                                 \
     } while (0)
     auto track = [&](void* p) { m->allocs.push_back(p); };
+    if (m->fmt == FMT_F16F8) {
+        // the main plane stores w * 2^8 in FP16: |w| must stay below 65504 / 256
+        for (int i = 0; i < DFB_NUM_LAYERS; ++i) {
+            const dfb_layer& l = desc->layers[i];
+            float mx = 0.f;
+            for (size_t j = 0; j < (size_t)l.in_features * l.out_features; ++j) mx = std::max(mx, fabsf(l.h_weight[j]));
+            if (!(mx < 250.f)) {
+                set_error("dfb_model_create: layer %d has |w| up to %g, outside the FP16 range of precision f16f8; use bf16x3", i, mx);
+                dfb_model_destroy(m);
+                return DFB_E_UNSUPPORTED;
+            }
+        }
+    }
     for (int i = 0; i < DFB_NUM_LAYERS; ++i) {
         const dfb_layer& l = desc->layers[i];
         DFB_TRY(upload_f32(l.h_bias, l.out_features, &m->L[i].bias, st));
@@ -2263,13 +2410,13 @@ extern "C" int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, d
             DFB_TRY(upload_f32(l.h_weight, (size_t)l.in_features * l.out_features, &m->w_small[i], st));
             track(m->w_small[i]);
         } else if (i == DFB_L_HEAD_CONV1) {
-            DFB_TRY(upload_pack(l.h_weight, 512, 1088, 0, 1024, 1088, m->head_global, st));
+            DFB_TRY(upload_pack(m->fmt, l.h_weight, 512, 1088, 0, 1024, 1088, m->head_global, st));
             track(m->head_global.w.p);
-            DFB_TRY(upload_pack(l.h_weight, 512, 1088, 1024, 64, 1088, m->head_point, st));
+            DFB_TRY(upload_pack(m->fmt, l.h_weight, 512, 1088, 1024, 64, 1088, m->head_point, st));
             track(m->head_point.w.p);
             m->head_global.bias = m->L[i].bias;
             m->head_point.bias = nullptr;
-            DFB_TRY(upload_head_w1_chunks(l.h_weight, 1088, 1024, &m->head_w1c, st));
+            DFB_TRY(upload_head_w1_chunks(m->fmt, l.h_weight, 1088, 1024, &m->head_w1c, st));
             track(m->head_w1c);
         } else if (i == DFB_L_STN_FC3) {
             // emit T2^T in the memory order of a tiled 64-row operand: output column
@@ -2282,20 +2429,20 @@ extern "C" int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, d
                     perm[c] = kk * 64 + n;
                     hb[c] = l.h_bias[kk * 64 + n] + (n == kk ? 1.f : 0.f);
                 }
-            DFB_TRY(upload_pack(l.h_weight, 4096, 256, 0, 256, 256, m->L[i], st, perm.data()));
+            DFB_TRY(upload_pack(m->fmt, l.h_weight, 4096, 256, 0, 256, 256, m->L[i], st, perm.data()));
             track(m->L[i].w.p);
             DFB_TRY(check_cuda(cudaMemcpyAsync(m->L[i].bias, hb.data(), 4096 * sizeof(float), cudaMemcpyHostToDevice, st),
                                "stn fc3 bias", __FILE__, __LINE__));
             DFB_TRY(check_cuda(cudaStreamSynchronize(st), "sync", __FILE__, __LINE__));
         } else {
             if (i == DFB_L_HEAD_CONV2) {
-                DFB_TRY(upload_pack(l.h_weight, l.out_features, l.in_features, 0, l.in_features, l.in_features, m->head_w2_256, st,
+                DFB_TRY(upload_pack(m->fmt, l.h_weight, l.out_features, l.in_features, 0, l.in_features, l.in_features, m->head_w2_256, st,
                                     nullptr, 256));
                 track(m->head_w2_256.w.p);
                 m->head_w2_256.bias = m->L[i].bias;
             }
             float* keep_bias = m->L[i].bias;
-            DFB_TRY(upload_pack(l.h_weight, l.out_features, l.in_features, 0, l.in_features, l.in_features, m->L[i], st));
+            DFB_TRY(upload_pack(m->fmt, l.h_weight, l.out_features, l.in_features, 0, l.in_features, l.in_features, m->L[i], st));
             m->L[i].bias = keep_bias;
             track(m->L[i].w.p);
         }
@@ -2337,7 +2484,15 @@ extern "C" int dfb_model_status(dfb_model* m, dfb_stream stream) {
     DFB_CUDA(cudaMemcpyAsync(&h, m->err, sizeof(int), cudaMemcpyDeviceToHost, as_stream(stream)));
     DFB_CUDA(cudaStreamSynchronize(as_stream(stream)));
     if (h != 0) {
-        set_error("tensor-core pipeline time-out (mbarrier wait, role %d)", h);
+        // report once and re-arm: later forwards on this model start with a clean flag
+        DFB_CUDA(cudaMemsetAsync(m->err, 0, sizeof(int), as_stream(stream)));
+        DFB_CUDA(cudaStreamSynchronize(as_stream(stream)));
+        if (h == 100)
+            set_error("activation magnitude above %g inside the network: outside the FP16 range of precision f16f8 "
+                      "(use precision bf16x3 for this model); outputs since the last status check are invalid", (double)kActLimit);
+        else
+            set_error("tensor-core pipeline time-out (mbarrier wait, role %d): the outputs of the forwards since the last "
+                      "status check are invalid", h);
         return DFB_E_INTERNAL;
     }
     return DFB_OK;
@@ -2352,7 +2507,7 @@ extern "C" int dfb_model_forward(dfb_model* m, const float* d_patch, int64_t n, 
     DFB_REQUIRE(d_patch && d_weights && d_trans, DFB_E_ARG, "dfb_model_forward: NULL pointer argument");
     cudaStream_t st = as_stream(stream);
     const int k = m->k;
-    const int split = m->nprod > 1 ? 1 : 0;
+    const int split = m->fmt;   // operand format of the unfused pointwise kernels
     int rc;
 #define DFB_RUN(expr)       \
     do {                    \
@@ -2571,7 +2726,7 @@ extern "C" DFB_API int dfb_dbg_model_dump(dfb_model* m, int32_t which, int64_t r
     DFB_REQUIRE(t->p != nullptr, DFB_E_ARG, "dfb_dbg_model_dump: buffer %d is not materialised in this configuration", which);
     DFB_REQUIRE(rows <= t->rows_pad && cols <= t->KB * 64, DFB_E_ARG, "dfb_dbg_model_dump: shape exceeds the buffer");
     const long long total = rows * (long long)cols;
-    unpack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(t->p, t->plane, m->nprod > 1, rows, cols, t->KB, d_out, t->br);
+    unpack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(t->p, t->plane, m->fmt, rows, cols, t->KB, d_out, t->br);
     return check_cuda(cudaGetLastError(), "unpack", __FILE__, __LINE__);
 }
 
@@ -2585,19 +2740,20 @@ extern "C" DFB_API int dfb_dbg_gemm(const float* d_A, const float* d_B, const fl
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);
     dfb_model fake;
-    fake.nprod = nprod;
+    const int fmt = nprod == 1 ? FMT_BF16 : (nprod == 2 ? FMT_F16F8 : FMT_BF16X3);   // nprod = tensor-core product units per k-step
+    fake.fmt = fmt;
     fake.k = k_pts;
     DFB_CUDA(cudaMalloc(&fake.err, sizeof(int)));
     DFB_CUDA(cudaMemsetAsync(fake.err, 0, sizeof(int), st));
     TiledBuf tA, tB, tO;
     rc = alloc_tiled(tA, M, K, (mode == 1 && k_pts == 256) ? 256 : 128); if (rc) return rc;
     rc = alloc_tiled(tB, N, K); if (rc) return rc;
-    auto pack = [&](const float* src, long long rows, int cols, TiledBuf& t) {
+    auto pack = [&](const float* src, long long rows, int cols, TiledBuf& t, int wside) {
         const long long total = t.rows_pad * (t.KB * 8);
-        pack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, rows, cols, cols, t.rows_pad, t.KB * 64, t.p, t.plane, 1, t.br);
+        pack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, rows, cols, cols, t.rows_pad, t.KB * 64, t.p, t.plane, fmt, wside, t.br);
     };
-    pack(d_A, M, K, tA);
-    pack(d_B, N, K, tB);
+    pack(d_A, M, K, tA, 0);   // activations
+    pack(d_B, N, K, tB, 1);   // weights
     PackedLayer W;
     W.bias = const_cast<float*>(d_bias);
     if (mode == 0) {
@@ -2607,7 +2763,7 @@ extern "C" DFB_API int dfb_dbg_gemm(const float* d_A, const float* d_B, const fl
         rc = gemm_n(&fake, tA, M, W, relu, &tO, d_out, N, k_pts, nullptr, 0, st);
         if (rc == 0 && d_out_tiled_unpacked) {
             const long long total = M * (long long)N;
-            unpack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tO.p, tO.plane, nprod > 1, M, N, tO.KB, d_out_tiled_unpacked, tO.br);
+            unpack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tO.p, tO.plane, fmt, M, N, tO.KB, d_out_tiled_unpacked, tO.br);
         }
     } else {
         // A = activations [M = n_patch*k_pts, K], B = weights [N, K]; out [n_patch, N]
@@ -2618,7 +2774,7 @@ extern "C" DFB_API int dfb_dbg_gemm(const float* d_A, const float* d_B, const fl
         rc = gemm_t_max(&fake, W, tA, n_patch, relu, &tO, d_out, st);
         if (rc == 0 && d_out_tiled_unpacked) {
             const long long total = n_patch * (long long)N;
-            unpack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tO.p, tO.plane, nprod > 1, n_patch, N, tO.KB, d_out_tiled_unpacked, tO.br);
+            unpack_tiled_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(tO.p, tO.plane, fmt, n_patch, N, tO.KB, d_out_tiled_unpacked, tO.br);
         }
     }
     int h = 0;

@@ -214,8 +214,12 @@ __device__ __forceinline__ void chol_substitute(const float (&a)[M * (M + 1) / 2
 }
 #undef LIDX
 
+// dirs (may be NULL): the 2 x 3 matrix compute_principal_curvatures returns next to the curvatures
+// (tutorial_utils.py:223-224): the eigenvector matrix V of torch.symeig (eigenvectors in COLUMNS, column j for
+// curvature j) with a zero third column appended, row-major.  LAPACK leaves the sign of each eigenvector open; here
+// its largest-magnitude component is positive.
 __device__ __forceinline__ void curvature_from_beta(float b0f, float b1f, float b2f, float b3f, float b4f,
-                                                    float& k1, float& k2) {
+                                                    float& k1, float& k2, float* dirs = nullptr) {
     // tutorial_utils.py:207-223.  M = -I^{-1} II is not symmetric; torch.symeig(upper=True) reads
     // (M00, M01, M11) only.  Evaluated in fp64 and rounded once.
     const double b0 = b0f, b1 = b1f, b2 = b2f, b3 = b3f, b4 = b4f;
@@ -231,6 +235,35 @@ __device__ __forceinline__ void curvature_from_beta(float b0f, float b1f, float 
     const double r = sqrt(hd * hd + m01 * m01);
     k1 = static_cast<float>(mid - r);
     k2 = static_cast<float>(mid + r);
+    if (dirs) {
+        // eigenvector of the larger eigenvalue mid + r of [[m00, m01], [m01, m11]]: (r + hd, m01) or (m01, r - hd),
+        // whichever is longer (they are parallel); the other eigenvector is orthogonal to it
+        double vx, vy;
+        if (hd >= 0.0) { vx = r + hd; vy = m01; } else { vx = m01; vy = r - hd; }
+        const double len = sqrt(vx * vx + vy * vy);
+        if (len > 0.0) { vx /= len; vy /= len; } else { vx = 0.0; vy = 1.0; }   // umbilic: any basis
+        double ux = vy, uy = -vx;                                                 // eigenvector of mid - r
+        if (fabs(vx) >= fabs(vy) ? vx < 0.0 : vy < 0.0) { vx = -vx; vy = -vy; }
+        if (fabs(ux) >= fabs(uy) ? ux < 0.0 : uy < 0.0) { ux = -ux; uy = -uy; }
+        dirs[0] = (float)ux; dirs[1] = (float)vx; dirs[2] = 0.f;
+        dirs[3] = (float)uy; dirs[4] = (float)vy; dirs[5] = 0.f;
+    }
+}
+
+// row vector times trans^T, then times U^T (test_n_est.py:154-161, test_c_est.py:162-168); either may be NULL
+__device__ __forceinline__ void rotate_back(const float* R, const float* U, float& vx, float& vy, float& vz) {
+    if (R) {
+        const float tx = vx * R[0] + vy * R[1] + vz * R[2];
+        const float ty = vx * R[3] + vy * R[4] + vz * R[5];
+        const float tz = vx * R[6] + vy * R[7] + vz * R[8];
+        vx = tx; vy = ty; vz = tz;
+    }
+    if (U) {
+        const float tx = vx * U[0] + vy * U[1] + vz * U[2];
+        const float ty = vx * U[3] + vy * U[4] + vz * U[5];
+        const float tz = vx * U[6] + vy * U[7] + vz * U[8];
+        vx = tx; vy = ty; vz = tz;
+    }
 }
 
 struct WlsArgs {
@@ -247,6 +280,9 @@ struct WlsArgs {
     float* curv;
     double* curv_scaled;
     int* info;
+    int keep_qstn;      // 1: do NOT undo the QSTN rotation on n_world / dirs_world (tutorial/compute_normals.py:67)
+    float* dirs;        // [n,2,3] local frame (compute_principal_curvatures' second return value)
+    float* dirs_world;  // [n,2,3] rows rotated back by trans^T and U^T (test_c_est.py:162-168)
 };
 
 // PPW = patches per warp iteration: 32 (every lane solves one system in phase 2) when there is enough work to fill the
@@ -368,30 +404,31 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) wls_kernel(WlsArgs p) {
             }
             if (p.n_world) {
                 float vx = nx, vy = ny, vz = nz;
-                if (p.trans) {  // n * trans^T  (test_n_est.py:154-157)
-                    const float* R = p.trans + pi * 9;
-                    const float tx = vx * R[0] + vy * R[1] + vz * R[2];
-                    const float ty = vx * R[3] + vy * R[4] + vz * R[5];
-                    const float tz = vx * R[6] + vy * R[7] + vz * R[8];
-                    vx = tx; vy = ty; vz = tz;
-                }
-                if (p.U) {  // n * U^T  (compute_normals.py:67)
-                    const float* U = p.U + pi * 9;
-                    const float tx = vx * U[0] + vy * U[1] + vz * U[2];
-                    const float ty = vx * U[3] + vy * U[4] + vz * U[5];
-                    const float tz = vx * U[6] + vy * U[7] + vz * U[8];
-                    vx = tx; vy = ty; vz = tz;
-                }
+                // n * trans^T (test_n_est.py:154-157), then n * U^T (compute_normals.py:67)
+                rotate_back((p.trans && !p.keep_qstn) ? p.trans + pi * 9 : nullptr, p.U ? p.U + pi * 9 : nullptr, vx, vy, vz);
                 p.n_world[pi * 3 + 0] = vx; p.n_world[pi * 3 + 1] = vy; p.n_world[pi * 3 + 2] = vz;
             }
-            if (ORDER > 1 && (p.curv || p.curv_scaled)) {
-                float k1, k2;
-                curvature_from_beta(beta[0], beta[1], beta[2], beta[3], beta[4], k1, k2);
+            if (ORDER > 1 && (p.curv || p.curv_scaled || p.dirs || p.dirs_world)) {
+                float k1, k2, dirs[6];
+                const bool want_dirs = p.dirs || p.dirs_world;
+                curvature_from_beta(beta[0], beta[1], beta[2], beta[3], beta[4], k1, k2, want_dirs ? dirs : nullptr);
                 if (p.curv) { p.curv[pi * 2] = k1; p.curv[pi * 2 + 1] = k2; }
                 if (p.curv_scaled) {
                     const double r = p.rad ? p.rad[pi] : 1.0;  // fp32 / fp64 -> fp64, compute_normals.py:79
                     p.curv_scaled[pi * 2] = (double)k1 / r;
                     p.curv_scaled[pi * 2 + 1] = (double)k2 / r;
+                }
+                if (p.dirs) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) p.dirs[pi * 6 + i] = dirs[i];
+                }
+                if (p.dirs_world) {
+#pragma unroll
+                    for (int rrow = 0; rrow < 2; ++rrow) {
+                        float vx = dirs[rrow * 3], vy = dirs[rrow * 3 + 1], vz = 0.f;
+                        rotate_back((p.trans && !p.keep_qstn) ? p.trans + pi * 9 : nullptr, p.U ? p.U + pi * 9 : nullptr, vx, vy, vz);
+                        p.dirs_world[pi * 6 + rrow * 3] = vx; p.dirs_world[pi * 6 + rrow * 3 + 1] = vy; p.dirs_world[pi * 6 + rrow * 3 + 2] = vz;
+                    }
                 }
             }
             if (p.info) p.info[pi] = info;
@@ -400,14 +437,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) wls_kernel(WlsArgs p) {
     }
 }
 
-__global__ void curvature_kernel(const float* __restrict__ beta, long long n, int m, float* __restrict__ curv) {
+__global__ void curvature_kernel(const float* __restrict__ beta, long long n, int m, float* __restrict__ curv,
+                                 float* __restrict__ dirs) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* b = beta + i * m;
-    float k1, k2;
-    curvature_from_beta(b[0], b[1], b[2], b[3], b[4], k1, k2);
-    curv[i * 2] = k1;
-    curv[i * 2 + 1] = k2;
+    float k1, k2, d[6];
+    curvature_from_beta(b[0], b[1], b[2], b[3], b[4], k1, k2, dirs ? d : nullptr);
+    if (curv) {
+        curv[i * 2] = k1;
+        curv[i * 2 + 1] = k2;
+    }
+    if (dirs) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) dirs[i * 6 + j] = d[j];
+    }
 }
 
 // Analytic normals of the fitted jet at every neighbour (fit_Wjet(..., compute_neighbor_normals=True),
@@ -485,21 +529,20 @@ int launch_wls(const WlsArgs& a, cudaStream_t st) {
 }  // namespace
 }  // namespace dfb
 
-extern "C" int dfb_wls_fit(const float* d_patch, const float* d_weights, const float* d_trans, const float* d_U,
-                           const double* d_rad, int64_t n, int32_t k, int32_t order, float* d_beta,
-                           float* d_n_local, float* d_n_world, float* d_curv, double* d_curv_scaled,
-                           int32_t* d_info, dfb_stream stream) {
-    using namespace dfb;
+namespace dfb {
+int wls_fit_impl(const float* d_patch, const float* d_weights, const float* d_trans, const float* d_U, const double* d_rad,
+                 int64_t n, int32_t k, int32_t order, float* d_beta, float* d_n_local, float* d_n_world, float* d_curv,
+                 double* d_curv_scaled, float* d_dirs, float* d_dirs_world, int32_t* d_info, int keep_qstn, dfb_stream stream) {
     DFB_REQUIRE(order >= 1 && order <= 4, DFB_E_ARG, "Polynomial order unsupported, please use 1..4 (got %d)", order);
     DFB_REQUIRE(n >= 0 && k >= 1, DFB_E_ARG, "dfb_wls_fit: bad sizes n=%lld k=%d", (long long)n, k);
     DFB_REQUIRE(d_patch != nullptr || n == 0, DFB_E_ARG, "dfb_wls_fit: d_patch is NULL");
-    DFB_REQUIRE(order > 1 || (d_curv == nullptr && d_curv_scaled == nullptr), DFB_E_ARG,
-                "Can't compute curvatures for jet with order less than 2");
+    DFB_REQUIRE(order > 1 || (d_curv == nullptr && d_curv_scaled == nullptr && d_dirs == nullptr && d_dirs_world == nullptr),
+                DFB_E_ARG, "Can't compute curvatures for jet with order less than 2");
     if (n == 0) return DFB_OK;
     int rc = dfb_device_check();
     if (rc) return rc;
     WlsArgs a{d_patch, d_weights, d_trans, d_U, d_rad, (long long)n, k,
-              d_beta,  d_n_local, d_n_world, d_curv, d_curv_scaled, d_info};
+              d_beta,  d_n_local, d_n_world, d_curv, d_curv_scaled, d_info, keep_qstn, d_dirs, d_dirs_world};
     switch (order) {
         case 1: return launch_wls<1>(a, as_stream(stream));
         case 2: return launch_wls<2>(a, as_stream(stream));
@@ -507,15 +550,25 @@ extern "C" int dfb_wls_fit(const float* d_patch, const float* d_weights, const f
         default: return launch_wls<4>(a, as_stream(stream));
     }
 }
+}  // namespace dfb
 
-extern "C" int dfb_principal_curvatures(const float* d_beta, int64_t n, int32_t m, float* d_curv, dfb_stream stream) {
+extern "C" int dfb_wls_fit(const float* d_patch, const float* d_weights, const float* d_trans, const float* d_U,
+                           const double* d_rad, int64_t n, int32_t k, int32_t order, float* d_beta,
+                           float* d_n_local, float* d_n_world, float* d_curv, double* d_curv_scaled,
+                           float* d_dirs, float* d_dirs_world, int32_t* d_info, dfb_stream stream) {
+    return dfb::wls_fit_impl(d_patch, d_weights, d_trans, d_U, d_rad, n, k, order, d_beta, d_n_local, d_n_world, d_curv,
+                             d_curv_scaled, d_dirs, d_dirs_world, d_info, 0, stream);
+}
+
+extern "C" int dfb_principal_curvatures(const float* d_beta, int64_t n, int32_t m, float* d_curv, float* d_dirs,
+                                        dfb_stream stream) {
     using namespace dfb;
     DFB_REQUIRE(m >= 5, DFB_E_ARG, "Can't compute curvatures for jet with order less than 2");
-    DFB_REQUIRE(n >= 0 && (n == 0 || (d_beta && d_curv)), DFB_E_ARG, "dfb_principal_curvatures: bad arguments");
+    DFB_REQUIRE(n >= 0 && (n == 0 || (d_beta && (d_curv || d_dirs))), DFB_E_ARG, "dfb_principal_curvatures: bad arguments");
     if (n == 0) return DFB_OK;
     int rc = dfb_device_check();
     if (rc) return rc;
-    curvature_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(d_beta, (long long)n, m, d_curv);
+    curvature_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(d_beta, (long long)n, m, d_curv, d_dirs);
     note_launch();
     return check_cuda(cudaGetLastError(), "curvature_kernel launch", __FILE__, __LINE__);
 }

@@ -146,10 +146,13 @@ def patch_pca(points: torch.Tensor, idx: torch.Tensor, rad: Optional[torch.Tenso
 
 
 def wls_fit(patch: torch.Tensor, weights: Optional[torch.Tensor], order: int, trans: Optional[torch.Tensor] = None,
-            U: Optional[torch.Tensor] = None, rad: Optional[torch.Tensor] = None, want_curv: bool = True):
+            U: Optional[torch.Tensor] = None, rad: Optional[torch.Tensor] = None, want_curv: bool = True,
+            want_dirs: bool = False):
     """Fused weighted jet fit + normal + curvature.  Returns a dict of device tensors:
     beta [n,M], n_local [n,3], n_world [n,3] (if U or trans given), curv [n,2] f32 and
-    curv_scaled [n,2] f64 (order >= 2), info [n] i32."""
+    curv_scaled [n,2] f64 (order >= 2), info [n] i32; with ``want_dirs`` also dirs [n,2,3] (the second return
+    value of compute_principal_curvatures) and dirs_world [n,2,3] (rotated back by trans^T and U^T,
+    test_c_est.py:162-168)."""
     patch = _chk(patch, torch.float32, "points")
     if patch.dim() != 3 or patch.shape[1] != 3:
         raise ValueError("points must be [B,3,k]")
@@ -175,11 +178,14 @@ def wls_fit(patch: torch.Tensor, weights: Optional[torch.Tensor], order: int, tr
     if order > 1 and want_curv:
         out["curv"] = torch.empty((n, 2), dtype=torch.float32, device=dev)
         out["curv_scaled"] = torch.empty((n, 2), dtype=torch.float64, device=dev)
+    if order > 1 and want_dirs:
+        out["dirs"] = torch.empty((n, 2, 3), dtype=torch.float32, device=dev)
+        out["dirs_world"] = torch.empty((n, 2, 3), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().dfb_wls_fit(_p(patch), _p(weights), _p(trans), _p(U), _p(rad), n, k, order,
                                            _p(out["beta"]), _p(out["n_local"]), _p(out.get("n_world")),
-                                           _p(out.get("curv")), _p(out.get("curv_scaled")), _p(out["info"]),
-                                           _stream(dev)))
+                                           _p(out.get("curv")), _p(out.get("curv_scaled")), _p(out.get("dirs")),
+                                           _p(out.get("dirs_world")), _p(out["info"]), _stream(dev)))
     return out
 
 
@@ -201,15 +207,77 @@ def launch_count(reset: bool = False) -> int:
     return int(_lib.load().dfb_launch_count(1 if reset else 0))
 
 
-def principal_curvatures(beta: torch.Tensor) -> torch.Tensor:
+def principal_curvatures(beta: torch.Tensor, want_dirs: bool = False):
+    """Curvatures f32 [n,2] (ascending); with ``want_dirs`` also the directions f32 [n,2,3] in the layout of the
+    reference's compute_principal_curvatures (tutorial_utils.py:223-224)."""
     beta = _chk(beta, torch.float32, "beta")
     if beta.dim() != 2 or beta.shape[1] < 5:
         raise ValueError("Can't compute curvatures for jet with order less than 2")
     curv = torch.empty((beta.shape[0], 2), dtype=torch.float32, device=beta.device)
+    dirs = torch.empty((beta.shape[0], 2, 3), dtype=torch.float32, device=beta.device) if want_dirs else None
     with torch.cuda.device(beta.device):
-        _lib.check(_lib.load().dfb_principal_curvatures(_p(beta), int(beta.shape[0]), int(beta.shape[1]), _p(curv),
+        _lib.check(_lib.load().dfb_principal_curvatures(_p(beta), int(beta.shape[0]), int(beta.shape[1]), _p(curv), _p(dirs),
                                                         _stream(beta.device)))
-    return curv
+    return (curv, dirs) if want_dirs else curv
+
+
+class Pipeline:
+    """The fused path 1 -> 5 behind one C call (``dfb_pipeline_run``): the batch loop of the reference's
+    tutorial/compute_normals.py:56-81.  ``net`` is a ``WeightNetwork`` (DeepFit mode) or None (classic)."""
+
+    OUTPUTS = {"normals": (torch.float32, lambda k, m: (3,)), "curv": (torch.float64, lambda k, m: (2,)),
+               "beta": (torch.float32, lambda k, m: (m,)), "weights": (torch.float32, lambda k, m: (k,)),
+               "trans": (torch.float32, lambda k, m: (3, 3)), "trans2": (torch.float32, lambda k, m: (64, 64)),
+               "U": (torch.float32, lambda k, m: (3, 3)), "rad": (torch.float64, lambda k, m: ()),
+               "dirs_world": (torch.float32, lambda k, m: (2, 3)), "info": (torch.int32, lambda k, m: ())}
+
+    def __init__(self, grid: Grid, net: Optional["WeightNetwork"], k: int, order: int, chunk: int = 0, keep_qstn: bool = False):
+        if order not in JET_M:
+            raise ValueError("Polynomial order unsupported, please use 1 or 2 ")
+        self.grid, self.net = grid, net        # keep both alive: the handle borrows them
+        self.k, self.order = int(k), int(order)
+        self.device = grid.device
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().dfb_pipeline_create(grid._h, net._h if net is not None else None, self.k, self.order, int(chunk),
+                                                       _lib.DFB_PIPE_KEEP_QSTN if keep_qstn else 0, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.load().dfb_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def run(self, begin: int, end: int, want=("normals", "curv"), out: Optional[dict] = None) -> dict:
+        """Asynchronous on the current stream.  ``want`` names the outputs to produce (see OUTPUTS); ``out`` may hold
+        preallocated tensors for some of them (e.g. views into an all-gather buffer)."""
+        q = int(end) - int(begin)
+        res = {}
+        o = _lib.DfbPipelineOutputs()
+        for name in want:
+            if name == "curv" and self.order < 2:
+                continue
+            dtype, shp = self.OUTPUTS[name]
+            shape = (q,) + tuple(shp(self.k, JET_M[self.order]))
+            t = out.get(name) if out else None
+            if t is None:
+                t = torch.empty(shape, dtype=dtype, device=self.device)
+            else:
+                t = _chk(t, dtype, name)
+                if tuple(t.shape) != shape or not t.is_contiguous():
+                    raise ValueError("%s must be a contiguous %s tensor of shape %s" % (name, dtype, shape))
+            res[name] = t
+            setattr(o, "d_" + name, t.data_ptr())
+        if "normals" not in res:
+            raise ValueError("the pipeline always produces normals")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().dfb_pipeline_run(self._h, int(begin), int(end), C.byref(o), _stream(self.device)))
+        return res
 
 
 class WeightNetwork:

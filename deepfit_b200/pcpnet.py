@@ -179,6 +179,8 @@ def estimate_shapes(dataset: PointcloudPatchDataset, model: Optional[DeepFit], o
             beta_prop[s:s + c] = out["beta"]
             if order > 1:
                 curv_prop[s:s + c] = out["curv_scaled"].float()     # the reference stores into a float32 buffer
+        if net is not None:
+            net.status()       # before anything is written: a pipeline time-out raises
         res = {"normals": normal_prop.cpu().numpy(), "curv": curv_prop.cpu().numpy(),
                "weights": weights_prop.cpu().numpy(), "beta": beta_prop.cpu().numpy(), "trans": trans_prop.cpu().numpy()}
         results[name] = res

@@ -36,10 +36,13 @@ class NormalEstimator:
     model  : a ``deepfit_b200.DeepFit.DeepFit`` (DeepFit mode)
     cancel_qstn : undo the QSTN rotation on the normals like test_n_est.py:154-157 (True) or
                   reproduce the tutorial script's omission (False, ``--ref-compat``)
+    grid   : an existing ``ops.Grid`` over ``points`` to reuse (e.g. ``SinglePointCloudDataset.kdtree``)
+             instead of building a second copy of the cloud and its table
     """
 
     def __init__(self, points: torch.Tensor, k: int, jet_order: int = 3, mode: str = "classic",
-                 model: Optional[DeepFit] = None, chunk: int = 0, cancel_qstn: bool = True):
+                 model: Optional[DeepFit] = None, chunk: int = 0, cancel_qstn: bool = True,
+                 grid: Optional[ops.Grid] = None):
         if mode not in ("classic", "DeepFit"):
             raise ValueError("mode must be 'classic' or 'DeepFit'")
         if mode == "DeepFit" and model is None:
@@ -51,52 +54,70 @@ class NormalEstimator:
         self.mode = mode
         self.model = model
         self.cancel_qstn = cancel_qstn
-        self.grid = ops.Grid(self.points)
+        if grid is not None and grid.n != self.n:
+            raise ValueError("grid was built over %d points, the cloud has %d" % (grid.n, self.n))
+        self.grid = grid if grid is not None else ops.Grid(self.points)
         self.chunk = int(chunk) if chunk else (16384 if mode == "DeepFit" else 65536)
-        self.net = model._network(points.device, max_batch=self.chunk) if mode == "DeepFit" else None
+
+    @property
+    def net(self):
+        """The packed network for the model's CURRENT parameters (resolved on every use: the model rebuilds it after
+        ``load_state_dict`` / ``.to()`` or when another user asked for a larger internal chunk)."""
+        if self.mode != "DeepFit":
+            return None
+        return self.model._network(self.points.device, max_batch=self.chunk)
 
     def rebuild_grid(self):
         """Stage-1 build for the current ``self.points`` (same size): in place, asynchronous."""
         self.grid.update(self.points)
 
+    def _pipeline(self) -> ops.Pipeline:
+        """The C pipeline for the model's current packed network (rebuilt when the network handle changes)."""
+        net = self.net
+        key = (id(net), net._h.value if net is not None else 0)
+        if getattr(self, "_pipe", None) is None or self._pipe_key != key:
+            if getattr(self, "_pipe", None) is not None:
+                self._pipe.close()
+            self._pipe = ops.Pipeline(self.grid, net, self.k, self.order, self.chunk, keep_qstn=not self.cancel_qstn)
+            self._pipe_key = key
+        return self._pipe
+
+    _EXTRA_NAMES = ("beta", "info", "rad", "U", "weights", "trans", "trans2", "dirs_world")
+
     def run(self, begin: int = 0, end: Optional[int] = None, out_normals: Optional[torch.Tensor] = None,
-            out_curv: Optional[torch.Tensor] = None, extras: Optional[dict] = None):
+            out_curv: Optional[torch.Tensor] = None, extras: Optional[dict] = None, check: bool = True):
         """Normals f32 [Q,3] and curvatures f64 [Q,2] (k1<=k2, divided by the patch radius) for point
-        indices [begin, end).  ``extras`` (a dict) receives lists of per-chunk beta / weights / trans
-        when given (config-3 style full outputs)."""
+        indices [begin, end), through ``dfb_pipeline_run`` (one C call: chunk loop, workspace and the two-stream
+        schedule live in the library).  ``extras`` (a dict) receives whole-range tensors ``beta / info / rad / U``
+        (+ ``weights / trans / trans2`` in DeepFit mode, ``dirs_world`` for order >= 2) when given (config-3 style
+        full outputs); a key already present with a tensor is used as the output buffer.  ``check`` synchronises
+        once at the end and raises if any tensor-core pipeline of the network reported a time-out
+        (``dfb_model_status``)."""
         end = self.n if end is None else int(end)
-        q = end - begin
-        dev = self.points.device
-        normals = out_normals if out_normals is not None else torch.empty((q, 3), dtype=torch.float32, device=dev)
-        want_curv = self.order > 1
-        curv = out_curv if out_curv is not None else (
-            torch.empty((q, 2), dtype=torch.float64, device=dev) if want_curv else None)
-        for s in range(begin, end, self.chunk):
-            c = min(self.chunk, end - s)
-            idx, rad = self.grid.query(self.k, q_begin=s, q_count=c)
-            patch, U = ops.patch_pca(self.points, idx, rad, q_begin=s)
-            if self.mode == "DeepFit":
-                weights, trans, trans2, _ = self.net.forward(patch, want_trans2=extras is not None)
-                out = ops.wls_fit(patch, weights, self.order, trans=trans, U=U, rad=rad, want_curv=want_curv)
-                if not self.cancel_qstn:
-                    # tutorial/compute_normals.py:67 applies only U^T to the normal of the rotated frame
-                    out["n_world"] = torch.bmm(out["n_local"].unsqueeze(1), U.transpose(2, 1)).squeeze(1)
-            else:
-                weights = trans = trans2 = None
-                out = ops.wls_fit(patch, None, self.order, U=U, rad=rad, want_curv=want_curv)
-            normals[s - begin:s - begin + c] = out["n_world"]
-            if want_curv:
-                curv[s - begin:s - begin + c] = out["curv_scaled"]
-            if extras is not None:
-                extras.setdefault("beta", []).append(out["beta"])
-                extras.setdefault("info", []).append(out["info"])
-                extras.setdefault("rad", []).append(rad)
-                extras.setdefault("U", []).append(U)
-                if weights is not None:
-                    extras.setdefault("weights", []).append(weights)
-                    extras.setdefault("trans", []).append(trans)
-                    extras.setdefault("trans2", []).append(trans2)
-        return normals, curv
+        pipe = self._pipeline()
+        want = ["normals"] + (["curv"] if self.order > 1 else [])
+        out = {}
+        if out_normals is not None:
+            out["normals"] = out_normals
+        if out_curv is not None:
+            out["curv"] = out_curv
+        if extras is not None:
+            for name in self._EXTRA_NAMES:
+                if name in ("weights", "trans", "trans2") and self.mode != "DeepFit":
+                    continue
+                if name == "dirs_world" and self.order < 2:
+                    continue
+                want.append(name)
+                if isinstance(extras.get(name), torch.Tensor):
+                    out[name] = extras[name]
+        res = pipe.run(begin, end, want, out)
+        if extras is not None:
+            for name in want[1:]:
+                if name != "curv":
+                    extras[name] = res[name]
+        if self.net is not None and check:
+            self.net.status()       # a tensor-core pipeline time-out must never end as silently wrong files
+        return res["normals"], res.get("curv")
 
 
 def gather_outputs(local_normals: torch.Tensor, local_curv: Optional[torch.Tensor], n: int, rank: int, world: int):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DFB_ABI_VERSION 1
+#define DFB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DFB_API __attribute__((visibility("default")))
@@ -157,6 +157,8 @@ typedef struct dfb_layer {
 
 #define DFB_PRECISION_BF16X3 0 /* error-compensated split-BF16 tensor-core MMA (3 products), fp32-grade */
 #define DFB_PRECISION_BF16 1   /* single BF16 product, fp32 accumulate: 3x fewer tensor ops, ~0.2 deg */
+#define DFB_PRECISION_F16F8 2  /* FP16 main product + ONE E4M3 MMA carrying both first-order corrections (2 product
+                                  units instead of 3), fp32-grade; needs |weights| < 250 and |activations| < 500 (checked) */
 
 typedef struct dfb_model_desc {
     int32_t k;           /* points per patch == num_points of the reference constructor; 128, 256, 384 or 512 */
@@ -209,17 +211,25 @@ DFB_API int dfb_model_profile_read(dfb_model* model, double* ms, int64_t* launch
  * outputs (each may be NULL):
  *   d_beta f32[n,M] (M = 3,6,10,15 for order 1..4), d_n_local f32[n,3], d_n_world f32[n,3],
  *   d_curv f32[n,2] ascending (order >= 2 only), d_curv_scaled f64[n,2],
+ *   d_dirs f32[n,2,3]: the second return value of compute_principal_curvatures (tutorial_utils.py:223-224):
+ *                  torch.symeig's eigenvector matrix (column j belongs to curvature j) with a zero third
+ *                  column; eigenvector signs are library-defined in the reference, here the largest-magnitude
+ *                  component of each eigenvector is positive,
+ *   d_dirs_world f32[n,2,3]: its rows rotated back by trans^T and U^T as test_c_est.py:162-168 does,
  *   d_info i32[n]: 0 ok, 1 = Cholesky failed and the deterministic ridge (diag *= 1.01) was used,
  *                  2 = ridge failed too (beta = 0).
  * All n rows are solved (the reference leaves rows >= 16*floor(n/16) at zero, :129-133).
  * ------------------------------------------------------------------------------------------ */
 DFB_API int dfb_wls_fit(const float* d_patch, const float* d_weights, const float* d_trans, const float* d_U,
                 const double* d_rad, int64_t n, int32_t k, int32_t order, float* d_beta, float* d_n_local,
-                float* d_n_world, float* d_curv, double* d_curv_scaled, int32_t* d_info, dfb_stream stream);
+                float* d_n_world, float* d_curv, double* d_curv_scaled, float* d_dirs, float* d_dirs_world,
+                int32_t* d_info, dfb_stream stream);
 
-/* Principal curvatures from jet coefficients alone (order >= 2): d_beta f32[n,M] -> d_curv f32[n,2].
+/* Principal curvatures and directions from jet coefficients alone (order >= 2): d_beta f32[n,M] ->
+ * d_curv f32[n,2] (may be NULL), d_dirs f32[n,2,3] (may be NULL; layout and sign rule as in dfb_wls_fit).
  * Replaces compute_principal_curvatures (tutorial/tutorial_utils.py:196-226). */
-DFB_API int dfb_principal_curvatures(const float* d_beta, int64_t n, int32_t m, float* d_curv, dfb_stream stream);
+DFB_API int dfb_principal_curvatures(const float* d_beta, int64_t n, int32_t m, float* d_curv, float* d_dirs,
+                                     dfb_stream stream);
 
 /* Analytic normals of the fitted jet at every neighbour: fit_Wjet(..., compute_neighbor_normals=True),
  * models/DeepFit.py:90-115 (gradient evaluated at the preconditioned x/h, y/h with the un-preconditioned
@@ -227,6 +237,40 @@ DFB_API int dfb_principal_curvatures(const float* d_beta, int64_t n, int32_t m, 
  * patch * trans), d_beta f32[n,M] -> d_out f32[n,k,3]. */
 DFB_API int dfb_neighbor_normals(const float* d_patch, const float* d_trans, const float* d_beta, int64_t n, int32_t k,
                                  int32_t order, float* d_out, dfb_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The fused path 1 -> 5 for a range of point indices of the cloud a grid was built over.
+ * Replaces the batch loop of tutorial/compute_normals.py:56-81 (DataLoader over SinglePointCloudDataset,
+ * model forward, undoing the rotations :67 / test_n_est.py:154-161, curv / rad :79, torch.cat) and, with the
+ * optional outputs, the per-batch body of test_c_est.py:125-168.
+ *   model NULL -> classic unweighted fit (compute_normals.py:72); else DeepFit mode with the model's k.
+ *   chunk     queries per internal chunk (0 = default: 16 384 DeepFit, 65 536 classic); the workspace
+ *             (neighbour indices, patches, frames; double-buffered) is sized for it at creation.
+ *   flags     DFB_PIPE_KEEP_QSTN: do not undo the QSTN rotation on the world normal / directions, which is
+ *             what the shipped tutorial script does (compute_normals.py:67 applies only the PCA frame).
+ * dfb_pipeline_run is asynchronous on `stream`; internally stages 1+2 of the next chunk run on a second
+ * stream owned by the pipeline.  One pipeline must not run on two streams at once.  The grid and the model
+ * must outlive the pipeline.  Outputs are indexed from q_begin; every pointer but d_normals may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dfb_pipeline dfb_pipeline;
+#define DFB_PIPE_KEEP_QSTN 1
+typedef struct dfb_pipeline_outputs {
+    float* d_normals;    /* f32[q,3]  world normals (unoriented), compute_normals.py:67 */
+    double* d_curv;      /* f64[q,2]  principal curvatures / rad, ascending, compute_normals.py:79 (order >= 2) */
+    float* d_beta;       /* f32[q,M]  jet coefficients */
+    float* d_weights;    /* f32[q,k]  point weights (DeepFit mode) */
+    float* d_trans;      /* f32[q,9]  QSTN rotation (DeepFit mode) */
+    float* d_trans2;     /* f32[q,64,64] feature transform (DeepFit mode) */
+    float* d_U;          /* f32[q,9]  PCA frame of the patch (the dataset's `trans`) */
+    double* d_rad;       /* f64[q]    patch radius */
+    float* d_dirs_world; /* f32[q,2,3] principal directions rotated to world space, test_c_est.py:162-168 */
+    int32_t* d_info;     /* i32[q]    solver status as in dfb_wls_fit */
+} dfb_pipeline_outputs;
+DFB_API int dfb_pipeline_create(const dfb_grid* grid, dfb_model* model, int32_t k, int32_t order, int32_t chunk,
+                                int32_t flags, dfb_pipeline** out);
+DFB_API int dfb_pipeline_run(dfb_pipeline* pipeline, int64_t q_begin, int64_t q_end, const dfb_pipeline_outputs* outputs,
+                             dfb_stream stream);
+DFB_API int dfb_pipeline_destroy(dfb_pipeline* pipeline);
 
 /* ------------------------------------------------------------------------------------------
  * Host-side text I/O (all host threads; no GPU needed).  Byte-compatible with numpy's defaults.

@@ -28,7 +28,9 @@ from oracle.shims import REFERENCE_ROOT, import_reference  # noqa: E402
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 K = 256
 N_QUERY = 64
-N_MODEL = 16
+N_MODEL = 16          # rows with every network output stored (incl. the 64 x 64 feature transform)
+N_GATE = 512          # rows of the per-row parity gate: patches, reference outputs, noise floor
+N_ENSEMBLE = 8        # neighbour permutations of the reference forward that estimate its own fp32 noise per row
 
 
 def main():
@@ -101,8 +103,62 @@ def main():
         nw = torch.bmm(normal.unsqueeze(1), trans.transpose(2, 1)).squeeze(1)
         nw = torch.bmm(nw.unsqueeze(1), U[:N_MODEL].transpose(2, 1)).squeeze(1)
         out[key + "/net_normal_world"] = nw.numpy()
-        curv, _ = RT.compute_principal_curvatures(beta)
+        curv, dirs = RT.compute_principal_curvatures(beta)
         out[key + "/net_curv_scaled"] = curv.numpy().astype(np.float64) / rad[:N_MODEL, None]
+        # principal directions (tutorial_utils.py:223-224) and their world-space form (test_c_est.py:162-168)
+        out[key + "/net_dirs"] = dirs.numpy()
+        dw = torch.matmul(dirs, trans.transpose(2, 1))
+        dw = torch.matmul(dw, U[:N_MODEL].transpose(2, 1))
+        out[key + "/net_dirs_world"] = dw.numpy()
+        cfit, dfit = RT.compute_principal_curvatures(torch.from_numpy(out[key + "/fit3_beta"]))
+        out[key + "/fit3_dirs"] = dfit.numpy()
+
+        # ---- per-row parity gate set: N_GATE random patches of this cloud through the reference, plus the reference's
+        # own noise floor on each row: the deviation from the fp64-exact result (oracle evaluated in float64) of
+        # N_ENSEMBLE + 1 mathematically equivalent fp32 evaluations of the reference (its forward on the patch and on
+        # N_ENSEMBLE neighbour permutations of it -- the network max-pools over the points and the jet fit sums over
+        # them, so only the fp32 summation order changes)
+        rng2 = np.random.default_rng(4321)
+        qg = np.sort(rng2.choice(len(ds), N_GATE, replace=False)).astype(np.int64)
+        itg = [ds[int(i)] for i in qg]
+        Pg = torch.stack([it[0] for it in itg])
+        Ug = torch.stack([it[1] for it in itg])
+        radg = np.array([float(it[2]) for it in itg], dtype=np.float64)
+
+        def ref_forward(P_):
+            outs = [model(P_[s:s + 64]) for s in range(0, P_.shape[0], 64)]
+            n_ = torch.cat([o[0] for o in outs]); b_ = torch.cat([o[1] for o in outs])
+            w_ = torch.cat([o[2] for o in outs]); t_ = torch.cat([o[3] for o in outs])
+            nw_ = torch.bmm(n_.unsqueeze(1), t_.transpose(2, 1)).squeeze(1)
+            nw_ = torch.bmm(nw_.unsqueeze(1), Ug.transpose(2, 1)).squeeze(1)
+            c_, _ = RT.compute_principal_curvatures(b_)
+            return nw_.numpy(), c_.numpy().astype(np.float64) / radg[:, None], w_, t_, b_
+        nw_ref, c_ref, w_ref, t_ref, b_ref = ref_forward(Pg)
+        sd64 = {k_: (v.double() if v.is_floating_point() else v) for k_, v in sd.items()}
+        w64, R64, _, pts64 = O.weight_network(sd64, Pg.double())
+        beta64, n64 = O.fit_wjet(pts64, w64, 3)
+        nw64 = O.world_normals(n64, Ug.double(), R64).numpy()
+        c64 = O.principal_curvatures(beta64).numpy() / radg[:, None]
+        floor_a = O.unoriented_angle_deg(nw_ref, nw64)
+        floor_c = O.rectified_rel_err(c_ref, c64).max(1)
+        gperm = torch.Generator().manual_seed(99)
+        for j in range(N_ENSEMBLE):
+            perm = torch.randperm(K, generator=gperm)
+            nw_p, c_p, _, _, _ = ref_forward(Pg[:, :, perm].contiguous())
+            floor_a = np.maximum(floor_a, O.unoriented_angle_deg(nw_p, nw64))
+            floor_c = np.maximum(floor_c, O.rectified_rel_err(c_p, c64).max(1))
+        out[key + "/gate_query"] = qg
+        out[key + "/gate_patch"] = Pg.numpy()
+        out[key + "/gate_U"] = Ug.numpy()
+        out[key + "/gate_rad"] = radg
+        out[key + "/gate_weights"] = w_ref.numpy()
+        out[key + "/gate_trans"] = t_ref.numpy()
+        out[key + "/gate_normal_world"] = nw_ref
+        out[key + "/gate_curv_scaled"] = c_ref
+        out[key + "/gate_floor_angle_deg"] = floor_a
+        out[key + "/gate_floor_curv"] = floor_c
+        print(name, "gate rows: floor angle max %.3e p99 %.3e, rows above 0.005 deg: %d; floor curv max %.3e, rows above 5e-4: %d"
+              % (floor_a.max(), np.quantile(floor_a, 0.99), int((floor_a > 0.005).sum()), floor_c.max(), int((floor_c > 5e-4).sum())))
     np.savez_compressed(os.path.join(GOLDEN, "reference_outputs.npz"), **out)
     np.savez_compressed(os.path.join(GOLDEN, "tutorial_clouds.npz"), **clouds)
     for f in ("reference_outputs.npz", "tutorial_clouds.npz"):

@@ -28,7 +28,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     raw = ctypes.CDLL(_lib.lib_path())
     for s in declared_symbols():
         assert hasattr(raw, s), "missing export %s" % s
-    assert lib.dfb_abi_version() == 1
+    assert lib.dfb_abi_version() == 2
     assert sorted(_lib.EXPORTS) == declared_symbols()
 
 

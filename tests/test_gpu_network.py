@@ -32,6 +32,12 @@ def _bf16(x):
     return x.to(torch.bfloat16).to(torch.float32)
 
 
+# nprod = tensor-core product units per k-step: 3 = split bf16 (hi*hi + hi*lo + lo*hi), 1 = single bf16,
+# 2 = f16f8 (fp16 main product + one e4m3 MMA carrying both first-order corrections)
+GEMM_TOL = {3: 2 ** -13, 2: 2 ** -12, 1: 2 ** -9}          # relative to the largest sum of |products|
+RESPLIT_TOL = {3: 2 ** -15, 2: 2 ** -14, 1: 2 ** -7}       # the re-split tiled output, relative to the largest value
+
+
 def _ref(A, Bm, bias, relu, nprod):
     if nprod == 1:
         A, Bm = _bf16(A), _bf16(Bm)
@@ -46,7 +52,7 @@ def _ref(A, Bm, bias, relu, nprod):
 GEMM_SHAPES = [(256, 128, 64), (384, 256, 128), (256, 512, 512), (512, 64, 64), (128, 128, 1024), (1024, 256, 256)]
 
 
-@pytest.mark.parametrize("nprod", [3, 1])
+@pytest.mark.parametrize("nprod", [3, 2, 1])
 @pytest.mark.parametrize("shape", GEMM_SHAPES, ids=lambda s: "M%dN%dK%d" % s)
 def test_umma_gemm_points_as_rows(shape, nprod):
     M, N, K = shape
@@ -57,18 +63,18 @@ def test_umma_gemm_points_as_rows(shape, nprod):
     out, out_t = _dbg_gemm(A, Bm, bias, 0, nprod, 1, 128)
     ref = _ref(A, Bm, bias, True, nprod)
     # error model: split-bf16 keeps 16 mantissa bits per operand (2^-16 relative per product, plus the
-    # dropped lo*lo term), plain bf16 keeps 8; both accumulate in fp32
+    # dropped lo*lo term), plain bf16 keeps 8, f16f8 11 bits + corrections good to 2^-4 of 2^-12; all accumulate in fp32
     mag = (A.abs().double() @ Bm.abs().double().t()).max().item()
-    tol = mag * (2 ** -13 if nprod == 3 else 2 ** -9)
+    tol = mag * GEMM_TOL[nprod]
     err = (out.double() - ref).abs().max().item()
     assert err < tol, "GEMM mismatch: max err %g (tol %g); sample out %s ref %s" % (
         err, tol, out[0, :4].tolist(), ref[0, :4].tolist())
     # the re-split tiled output (next layer's operand) carries the same values to 2^-16 relative
-    tol_t = tol + (ref.abs().max().item() * (2 ** -15 if nprod == 3 else 2 ** -7))
+    tol_t = tol + ref.abs().max().item() * RESPLIT_TOL[nprod]
     assert (out_t.double() - ref).abs().max().item() < tol_t
 
 
-@pytest.mark.parametrize("nprod", [3, 1])
+@pytest.mark.parametrize("nprod", [3, 2, 1])
 @pytest.mark.parametrize("N", [256, 1024])
 @pytest.mark.parametrize("k_pts", [128, 256, 512])
 def test_umma_gemm_channels_as_rows_with_maxpool(k_pts, N, nprod):
@@ -81,9 +87,9 @@ def test_umma_gemm_channels_as_rows_with_maxpool(k_pts, N, nprod):
     full = _ref(A, W, None, False, nprod).reshape(n_patch, k_pts, N)
     ref = full.max(1)[0] + bias.double()
     mag = (A.abs().double() @ W.abs().double().t()).max().item()
-    tol = mag * (2 ** -13 if nprod == 3 else 2 ** -9)
+    tol = mag * GEMM_TOL[nprod]
     assert (out.double() - ref).abs().max().item() < tol
-    assert (out_t.double() - ref).abs().max().item() < tol + ref.abs().max().item() * (2 ** -15 if nprod == 3 else 2 ** -7)
+    assert (out_t.double() - ref).abs().max().item() < tol + ref.abs().max().item() * RESPLIT_TOL[nprod]
 
 
 def _torch_network(layers, P, mode):
@@ -150,7 +156,7 @@ def dbg_switch():
 
 
 @pytest.mark.parametrize("variant", ["fused", "fused_l12_only", "unfused"])
-@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8", "bf16"])
 def test_network_stage_by_stage_vs_torch(golden, precision, variant, dbg_switch):
     from deepfit_b200 import DeepFit as D
     from deepfit_b200 import ops
@@ -167,7 +173,7 @@ def test_network_stage_by_stage_vs_torch(golden, precision, variant, dbg_switch)
     net = ops.WeightNetwork(layers, 256, "sigmoid", precision, max_batch=128)
     w, trans, trans2, pts = net.forward(P, want_trans2=True, want_points=True)
     net.status()
-    ref = _torch_network(layers, P, "fp32" if precision == "bf16x3" else "bf16")
+    ref = _torch_network(layers, P, "bf16" if precision == "bf16" else "fp32")
     B, k = 16, 256
     report = {}
     for which, nm, rows, cols in [(0, "x64a", B * k, 64), (1, "x64b", B * k, 64), (2, "x64c", B * k, 64),
@@ -184,36 +190,67 @@ def test_network_stage_by_stage_vs_torch(golden, precision, variant, dbg_switch)
     report["trans2"] = (trans2 - ref["trans2"]).abs().max().item()
     report["weights"] = (w - ref["weights"]).abs().max().item()
     report["pts"] = (pts - torch.bmm(P.transpose(1, 2), ref["trans"]).transpose(1, 2)).abs().max().item()
-    tol = 3e-4 if precision == "bf16x3" else 6e-2
+    tol = {"bf16x3": 3e-4, "f16f8": 6e-4, "bf16": 6e-2}[precision]
     bad = {k_: v for k_, v in report.items() if not v < tol}
     assert not bad, "stage errors (relative to stage max): %s" % report
 
 
+PARITY_PRECISIONS = ["bf16x3", "f16f8"]
+
+
+@pytest.mark.parametrize("precision", PARITY_PRECISIONS)
 @pytest.mark.parametrize("name", CLOUD_NAMES)
-def test_deepfit_forward_matches_reference_golden(golden, name):
-    """DeepFit.forward drop-in vs the reference module (eval mode) on the reference's own patches."""
+def test_deepfit_forward_matches_reference_golden(golden, name, precision):
+    """DeepFit.forward drop-in vs the reference module (eval mode) on the reference's own patches: every output."""
     from deepfit_b200.pipeline import model_from_state_dict
     from oracle import deepfit_oracle as O
     P = torch.from_numpy(golden[name + "/patch"][:16]).cuda()
-    U = torch.from_numpy(golden[name + "/U"][:16])
-    rad = golden[name + "/rad"][:16]
-    model = model_from_state_dict(O.seeded_state_dict(0), 256, 3, "sigmoid", "bf16x3")
+    model = model_from_state_dict(O.seeded_state_dict(0), 256, 3, "sigmoid", precision)
     normal, beta, weights, trans, trans2, nn_ = model(P)
-    model._net.status()
     assert nn_ is None
     assert tuple(normal.shape) == (16, 3) and tuple(beta.shape) == (16, 10) and tuple(weights.shape) == (16, 256)
     assert tuple(trans.shape) == (16, 3, 3) and tuple(trans2.shape) == (16, 64, 64)
-    assert (weights.cpu() - torch.from_numpy(golden[name + "/net_weights"])).abs().max() < 2e-3
-    assert (trans.cpu() - torch.from_numpy(golden[name + "/net_trans"])).abs().max() < 1e-4
-    assert (trans2.cpu() - torch.from_numpy(golden[name + "/net_trans2"])).abs().max() < 1e-4
+    dw = (weights.cpu() - torch.from_numpy(golden[name + "/net_weights"])).abs().max().item()
+    dt = (trans.cpu() - torch.from_numpy(golden[name + "/net_trans"])).abs().max().item()
+    dt2 = (trans2.cpu() - torch.from_numpy(golden[name + "/net_trans2"])).abs().max().item()
+    print("%s %s: max |dw| %.2e, |dtrans| %.2e, |dtrans2| %.2e" % (name, precision, dw, dt, dt2))
+    assert dw < 5e-4 and dt < 1e-4 and dt2 < 1e-4
+
+
+@pytest.mark.parametrize("precision", PARITY_PRECISIONS)
+@pytest.mark.parametrize("name", CLOUD_NAMES)
+def test_deepfit_forward_per_row_gate(golden, name, precision):
+    """BASELINE.json's gates (0.01 deg unoriented, 1e-3 rectified-relative curvature) on 512 patches per cloud against
+    the unmodified reference's outputs, PER ROW: gate_i = max(gate, 2 x floor_i), where floor_i is the reference's own
+    fp32 noise on that row -- the largest deviation from the fp64-exact result among 9 mathematically equivalent fp32
+    evaluations of the reference (its forward on the patch and on 8 neighbour permutations of it; generated by
+    oracle/make_golden.py).  On the smooth cloud no row is relaxed; on the lidar cloud (scan lines -> ill-conditioned
+    fits) a few percent are.  The achieved maxima are printed."""
+    from deepfit_b200.pipeline import model_from_state_dict
+    from oracle import deepfit_oracle as O
+    P = torch.from_numpy(golden[name + "/gate_patch"]).cuda()
+    U = torch.from_numpy(golden[name + "/gate_U"])
+    rad = golden[name + "/gate_rad"]
+    model = model_from_state_dict(O.seeded_state_dict(0), 256, 3, "sigmoid", precision)
+    normal, beta, weights, trans, trans2, _ = model(P)
+    dw = (weights.cpu() - torch.from_numpy(golden[name + "/gate_weights"])).abs().max().item()
+    dt = (trans.cpu() - torch.from_numpy(golden[name + "/gate_trans"])).abs().max().item()
     nw = O.world_normals(normal.cpu(), U, trans.cpu()).numpy()
-    ang = O.unoriented_angle_deg(nw, golden[name + "/net_normal_world"])
-    # 0.01 deg is BASELINE.json's gate.  On the noisy lidar cloud the reference's own fp32 summation-order
-    # noise (folded vs unfolded BN, both fp32, on CPU) already reaches 0.023 deg, so the gate there is 0.05.
-    assert ang.max() <= (0.01 if name == "Boxy_smooth100k" else 0.05), "max angular deviation %g deg" % ang.max()
-    curv = model_curv(beta, rad)
-    err = O.rectified_rel_err(curv, golden[name + "/net_curv_scaled"])
-    assert err.max() <= (1e-3 if name == "Boxy_smooth100k" else 5e-3), "max curvature error %g" % err.max()
+    ang = O.unoriented_angle_deg(nw, golden[name + "/gate_normal_world"])
+    cerr = O.rectified_rel_err(model_curv(beta, rad), golden[name + "/gate_curv_scaled"]).max(1)
+    gate_a = np.maximum(0.01, 2 * golden[name + "/gate_floor_angle_deg"])
+    gate_c = np.maximum(1e-3, 2 * golden[name + "/gate_floor_curv"])
+    strict_a, strict_c = gate_a <= 0.01, gate_c <= 1e-3
+    print("%s %s: %d rows; max |dw| %.2e |dtrans| %.2e; angle max %.3e deg on the %d strict rows (gate 0.01), worst "
+          "angle/gate %.2f over all rows; curvature max %.3e on the %d strict rows (gate 1e-3), worst err/gate %.2f"
+          % (name, precision, len(ang), dw, dt, ang[strict_a].max(), int(strict_a.sum()), (ang / gate_a).max(),
+             cerr[strict_c].max(), int(strict_c.sum()), (cerr / gate_c).max()))
+    assert dw < 5e-4, dw
+    assert dt < 1e-4, dt
+    assert (ang <= gate_a).all(), "rows over their gate: %s" % np.nonzero(ang > gate_a)[0][:10]
+    assert (cerr <= gate_c).all(), "rows over their gate: %s" % np.nonzero(cerr > gate_c)[0][:10]
+    if name == "Boxy_smooth100k":
+        assert strict_a.all() and strict_c.all()     # the smooth cloud needs no relaxation at all
 
 
 def model_curv(beta, rad):
@@ -239,8 +276,9 @@ def test_forward_is_batch_independent_and_chunked():
         net.forward(torch.zeros(2, 3, 128, device="cuda"))
 
 
+@pytest.mark.parametrize("precision", PARITY_PRECISIONS)
 @pytest.mark.parametrize("B,k", [(3000, 256), (1, 256), (149, 256), (333, 128), (600, 512)])
-def test_persistent_kernels_match_one_cta_per_tile(dbg_switch, B, k):
+def test_persistent_kernels_match_one_cta_per_tile(dbg_switch, B, k, precision):
     """The fused kernels run as persistent CTAs (one per SM walking patches / tiles); with more work items than SMs
     every barrier parity is exercised across iterations (3000 patches = ~20 patches and ~40 head tiles per SM; the small
     and odd sizes leave some CTAs with one item fewer or none; k = 128 has one row tile per patch, k = 512 two work items
@@ -253,7 +291,7 @@ def test_persistent_kernels_match_one_cta_per_tile(dbg_switch, B, k):
     c = torch.rand((B, 3, 1), generator=g) - 0.5
     zz = 0.3 * (c[:, 0:1] * xy[:, 0:1] ** 2 + c[:, 1:2] * xy[:, 1:2] ** 2 + c[:, 2:3] * xy[:, 0:1] * xy[:, 1:2])
     patch = torch.cat([xy, zz], 1).cuda().contiguous()
-    net = ops.WeightNetwork(D.fold_batchnorm(O.seeded_state_dict(0)), k, "sigmoid", "bf16x3", max_batch=max(B, 128))
+    net = ops.WeightNetwork(D.fold_batchnorm(O.seeded_state_dict(0)), k, "sigmoid", precision, max_batch=max(B, 128))
     out = {}
     for name, head_p, chain_p in (("per_item", 0, 0), ("persistent", 1, 1)):
         dbg_switch(8, head_p, 1)
@@ -266,12 +304,13 @@ def test_persistent_kernels_match_one_cta_per_tile(dbg_switch, B, k):
     # and against the fp32 torch restatement on a sample of patches from every wave
     sel = torch.arange(0, B, 149)
     wr, tr, t2r, _ = O.weight_network(O.seeded_state_dict(0), patch[sel].cpu())
-    assert (out["persistent"][0][sel].cpu() - wr).abs().max() < 2e-3
+    assert (out["persistent"][0][sel].cpu() - wr).abs().max() < 5e-4
     assert (out["persistent"][1][sel].cpu() - tr).abs().max() < 2e-4
 
 
+@pytest.mark.parametrize("precision", PARITY_PRECISIONS)
 @pytest.mark.parametrize("k", [128, 384, 512])
-def test_network_other_neighbourhood_sizes(k):
+def test_network_other_neighbourhood_sizes(k, precision):
     """k = 128 and 512 run the fused chain kernels (one tile / two 256-point work items per patch), k = 384 the generic
     kernels; all against the fp32 torch restatement."""
     from deepfit_b200 import DeepFit as D
@@ -284,11 +323,11 @@ def test_network_other_neighbourhood_sizes(k):
     zz = 0.3 * (c[:, 0:1] * xy[:, 0:1] ** 2 + c[:, 1:2] * xy[:, 1:2] ** 2 + c[:, 2:3] * xy[:, 0:1] * xy[:, 1:2])
     patch = torch.cat([xy, zz], 1).contiguous()
     sd = O.seeded_state_dict(0)
-    net = ops.WeightNetwork(D.fold_batchnorm(sd), k, "sigmoid", "bf16x3", max_batch=128)
+    net = ops.WeightNetwork(D.fold_batchnorm(sd), k, "sigmoid", precision, max_batch=128)
     w, trans, t2, pts = net.forward(patch.cuda(), want_trans2=True, want_points=True)
     net.status()
     wr, tr, t2r, pr = O.weight_network(sd, patch)
     assert (trans.cpu() - tr).abs().max() < 2e-4
     assert (t2.cpu() - t2r).abs().max() < 2e-3
     assert (pts.cpu() - pr).abs().max() < 2e-4
-    assert (w.cpu() - wr).abs().max() < 2e-3
+    assert (w.cpu() - wr).abs().max() < 5e-4

@@ -42,30 +42,106 @@ def test_classic_pipeline_vs_oracle_on_tutorial_cloud(clouds, tmp_path):
     assert rad == ref["rad"][0] and len(ds) == 100000
 
 
-def test_deepfit_pipeline_vs_oracle(clouds):
-    """DeepFit mode end to end.  The network is fed OUR PCA frame, so the oracle runs the reference
-    algebra on our patches (the sign-alignment protocol of SURVEY.md section 8c)."""
+_ORACLE_CACHE = {}
+
+
+def _oracle_on_our_patches(name, sd, patch, U, rad, n_perm=3):
+    """Reference algebra (oracle, fp32) on OUR patches + its per-row fp32 noise floor: the largest deviation from the
+    fp64-exact result among the fp32 forward and n_perm neighbour permutations of it (same rule as the golden gate set)."""
+    from oracle import deepfit_oracle as O
+    if name in _ORACLE_CACHE:
+        return _ORACLE_CACHE[name]
+    with torch.no_grad():
+        P, Uc, radc = patch.cpu(), U.cpu(), rad.cpu()
+
+        def fwd(Pp, s=sd, dt=torch.float32):
+            n, beta, w, trans, t2, _ = O.deepfit_forward(s, Pp.to(dt), 3)
+            return (O.world_normals(n, Uc.to(dt), trans).numpy(),
+                    (O.principal_curvatures(beta).double() / radc[:, None]).numpy())
+        ref_n, ref_c = fwd(P)
+        sd64 = {k_: (v.double() if v.is_floating_point() else v) for k_, v in sd.items()}
+        ex_n, ex_c = fwd(P, sd64, torch.float64)
+        fa = O.unoriented_angle_deg(ref_n, ex_n)
+        fc = O.rectified_rel_err(ref_c, ex_c).max(1)
+        g = torch.Generator().manual_seed(5)
+        for _ in range(n_perm):
+            pn, pc = fwd(P[:, :, torch.randperm(P.shape[2], generator=g)].contiguous())
+            fa = np.maximum(fa, O.unoriented_angle_deg(pn, ex_n))
+            fc = np.maximum(fc, O.rectified_rel_err(pc, ex_c).max(1))
+    _ORACLE_CACHE[name] = (ref_n, ref_c, fa, fc)
+    return _ORACLE_CACHE[name]
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+@pytest.mark.parametrize("name", ["Boxy_smooth100k", "0000000000"])
+def test_deepfit_pipeline_vs_oracle(clouds, name, precision):
+    """DeepFit mode end to end on both tutorial clouds (smooth CAD surface and noisy lidar scan).  The network is fed
+    OUR PCA frame, so the oracle runs the reference algebra on our patches (the sign-alignment protocol of SURVEY.md
+    section 8c).  Gates per row: max(0.01 deg, 2 x the reference's own fp32 noise on that row) and the same for 1e-3
+    on the curvatures; no row of the smooth cloud is relaxed."""
     from deepfit_b200 import ops
     from deepfit_b200.pipeline import NormalEstimator, model_from_state_dict
     from oracle import deepfit_oracle as O
-    raw = clouds["Boxy_smooth100k"]
+    raw = clouds[name]
     pts_np = O.normalize_cloud(raw)[0]
     pts = torch.from_numpy(pts_np).cuda()
     sd = O.seeded_state_dict(0)
-    model = model_from_state_dict(sd, 256, 3, "sigmoid", "bf16x3")
-    est = NormalEstimator(pts, 256, mode="DeepFit", model=model, chunk=1024)
-    normals, curv = est.run(1000, 1000 + 1536)
-    est.net.status()
-    idx, rad = est.grid.query(256, q_begin=1000, q_count=1536)
-    patch, U = ops.patch_pca(pts, idx, rad, q_begin=1000)
-    with torch.no_grad():
-        n, beta, w, trans, t2, _ = O.deepfit_forward(sd, patch.cpu(), 3)
-        ref_n = O.world_normals(n, U.cpu(), trans).numpy()
-        ref_c = (O.principal_curvatures(beta).double() / rad.cpu()[:, None]).numpy()
+    model = model_from_state_dict(sd, 256, 3, "sigmoid", precision)
+    est = NormalEstimator(pts, 256, mode="DeepFit", model=model, chunk=256)
+    begin, count = 1000, 640                      # 2.5 chunks: ragged tail, both halves of the double buffer
+    normals, curv = est.run(begin, begin + count)
+    idx, rad = est.grid.query(256, q_begin=begin, q_count=count)
+    patch, U = ops.patch_pca(pts, idx, rad, q_begin=begin)
+    ref_n, ref_c, fa, fc = _oracle_on_our_patches(name, sd, patch, U, rad)
     ang = O.unoriented_angle_deg(normals.cpu().numpy(), ref_n)
-    assert ang.max() <= 0.01, "max angular deviation %g deg (p99 %g)" % (ang.max(), np.quantile(ang, 0.99))
-    err = O.rectified_rel_err(curv.cpu().numpy(), ref_c)
-    assert err.max() <= 1e-3, "max curvature error %g" % err.max()
+    err = O.rectified_rel_err(curv.cpu().numpy(), ref_c).max(1)
+    gate_a, gate_c = np.maximum(0.01, 2 * fa), np.maximum(1e-3, 2 * fc)
+    print("%s %s: angle max %.3e deg (worst angle/gate %.2f, %d of %d rows relaxed); curvature max %.3e (worst err/gate %.2f, "
+          "%d rows relaxed)" % (name, precision, ang.max(), (ang / gate_a).max(), int((gate_a > 0.01).sum()), count, err.max(),
+                                (err / gate_c).max(), int((gate_c > 1e-3).sum())))
+    assert (ang <= gate_a).all(), "max angular deviation %g deg (p99 %g)" % (ang.max(), np.quantile(ang, 0.99))
+    assert (err <= gate_c).all(), "max curvature error %g" % err.max()
+    if name == "Boxy_smooth100k":
+        assert (gate_a <= 0.01).all() and (gate_c <= 1e-3).all()
+
+
+@pytest.mark.parametrize("mode", ["classic", "DeepFit"])
+def test_pipeline_call_equals_stage_calls(clouds, mode):
+    """dfb_pipeline_run (chunk loop + two-stream schedule inside the library) is bit-identical to calling the five
+    stages one by one, for every optional output, over ragged chunking; DFB_PIPE_KEEP_QSTN reproduces the tutorial
+    script's omission (compute_normals.py:67)."""
+    from deepfit_b200 import ops
+    from deepfit_b200.pipeline import NormalEstimator, model_from_state_dict
+    from oracle import deepfit_oracle as O
+    pts = torch.from_numpy(O.normalize_cloud(clouds["0000000000"])[0]).cuda()
+    k, order = 256, 3
+    model = model_from_state_dict(O.seeded_state_dict(1), k, order, "sigmoid", "bf16x3") if mode == "DeepFit" else None
+    est = NormalEstimator(pts, k, order, mode, model, chunk=300)
+    begin, end = 777, 777 + 1000                  # 3 chunks of 300 + a tail of 100
+    extras = {}
+    normals, curv = est.run(begin, end, extras=extras)
+    torch.cuda.synchronize()
+    idx, rad = est.grid.query(k, q_begin=begin, q_count=end - begin)
+    patch, U = ops.patch_pca(pts, idx, rad, q_begin=begin)
+    if mode == "DeepFit":
+        w, trans, t2, _ = est.net.forward(patch, want_trans2=True)
+        out = ops.wls_fit(patch, w, order, trans=trans, U=U, rad=rad, want_dirs=True)
+        assert torch.equal(extras["weights"], w) and torch.equal(extras["trans"], trans) and torch.equal(extras["trans2"], t2)
+    else:
+        out = ops.wls_fit(patch, None, order, U=U, rad=rad, want_dirs=True)
+        assert "weights" not in extras
+    assert torch.equal(normals, out["n_world"]) and torch.equal(curv, out["curv_scaled"])
+    assert torch.equal(extras["beta"], out["beta"]) and torch.equal(extras["info"], out["info"])
+    assert torch.equal(extras["U"], U) and torch.equal(extras["rad"], rad)
+    assert torch.equal(extras["dirs_world"], out["dirs_world"])
+    # a second run re-uses the workspace and the events
+    n2, c2 = est.run(begin, end)
+    assert torch.equal(n2, normals) and torch.equal(c2, curv)
+    if mode == "DeepFit":
+        est2 = NormalEstimator(pts, k, order, mode, model, chunk=300, cancel_qstn=False, grid=est.grid)
+        n3, _ = est2.run(begin, end)
+        expect = torch.bmm(out["n_local"].unsqueeze(1), U.transpose(2, 1)).squeeze(1)
+        assert (n3 - expect).abs().max().item() < 1e-6
 
 
 def test_cli_writes_reference_format(clouds, tmp_path):
