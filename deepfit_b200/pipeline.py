@@ -2,9 +2,8 @@
 
 This is the loop of the reference's ``tutorial/compute_normals.py:56-81`` without the DataLoader: the
 cloud and the grid stay resident in HBM, queries are processed in chunks of point indices, and no
-intermediate leaves the device.  ``shard_range`` / ``gather_outputs`` implement the multi-GPU
-contract: each rank owns a contiguous point-index range of the replicated cloud and a single
-all-gather assembles the outputs in file order.
+intermediate leaves the device.  The multi-GPU contract (contiguous point-index shards of the replicated
+cloud, outputs written in place into the all-gather buffers) lives in ``deepfit_b200.sharding``.
 """
 from __future__ import annotations
 
@@ -14,17 +13,7 @@ import torch
 
 from . import ops
 from .DeepFit import DeepFit, fold_batchnorm
-
-
-def shard_range(n: int, rank: int, world: int):
-    """Contiguous, balanced point-index range [begin, end) of ``rank`` (first n % world ranks get one more)."""
-    base, rem = divmod(int(n), int(world))
-    begin = rank * base + min(rank, rem)
-    return begin, begin + base + (1 if rank < rem else 0)
-
-
-def shard_capacity(n: int, world: int) -> int:
-    return (int(n) + int(world) - 1) // int(world)
+from .sharding import GatherBuffers, gather_outputs, shard_capacity, shard_range  # noqa: F401  (re-exported)
 
 
 class NormalEstimator:
@@ -120,37 +109,6 @@ class NormalEstimator:
         return res["normals"], res.get("curv")
 
 
-def gather_outputs(local_normals: torch.Tensor, local_curv: Optional[torch.Tensor], n: int, rank: int, world: int):
-    """All-gather per-rank outputs (ranges from ``shard_range``) into file order on every rank.
-
-    One collective: normals (3 x f32) and curvatures (2 x f64) are packed into one f64 [cap,5] buffer
-    per rank (padded to the common capacity), gathered with ``all_gather_into_tensor`` (NCCL over
-    NVLink on GPUs, gloo in the CPU tests), then the ragged tail is dropped."""
-    import torch.distributed as dist
-
-    cap = shard_capacity(n, world)
-    dev = local_normals.device
-    cols = 5 if local_curv is not None else 3
-    buf = torch.zeros((cap, cols), dtype=torch.float64, device=dev)
-    m = local_normals.shape[0]
-    buf[:m, :3] = local_normals.double()  # exact: f32 -> f64 -> f32 round trip is lossless
-    if local_curv is not None:
-        buf[:m, 3:] = local_curv
-    if world == 1:
-        full = buf.unsqueeze(0)
-    else:
-        full = torch.empty((world, cap, cols), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(full.view(world * cap, cols), buf)
-    pieces = []
-    for r in range(world):
-        b, e = shard_range(n, r, world)
-        pieces.append(full[r, :e - b])
-    allv = torch.cat(pieces, 0)
-    normals = allv[:, :3].float()
-    curv = allv[:, 3:].contiguous() if local_curv is not None else None
-    return normals, curv
-
-
 def model_from_state_dict(state_dict, num_points: int, jet_order: int = 3, weight_mode: str = "sigmoid",
                           precision: str = "bf16x3", device="cuda") -> DeepFit:
     m = DeepFit(k=1, num_points=num_points, use_point_stn=True, use_feat_stn=True, point_tuple=1, sym_op="max",
@@ -161,5 +119,5 @@ def model_from_state_dict(state_dict, num_points: int, jet_order: int = 3, weigh
     return m
 
 
-__all__ = ["NormalEstimator", "shard_range", "shard_capacity", "gather_outputs", "model_from_state_dict",
+__all__ = ["NormalEstimator", "GatherBuffers", "shard_range", "shard_capacity", "gather_outputs", "model_from_state_dict",
            "fold_batchnorm"]

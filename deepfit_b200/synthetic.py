@@ -160,3 +160,70 @@ def synthetic_state_dict(seed: int = 0, num_points: int = 256, jet_order: int = 
     sd["conv4.bias"] = ((sd["conv4.bias"].double() - a.mean()) * scale).float()
     sd["conv4.weight"] = (sd["conv4.weight"].double() * scale).float()
     return sd
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Device-side generators for the large named workloads (10 M / 100 M points): same surfaces as above, sampled with a
+# seeded torch.Generator on the GPU so that no rank spends minutes in numpy or ships gigabytes over PCIe.  Inputs of
+# the benchmark, not part of the hot path.  (The Philox stream differs from numpy's, so these clouds are NOT
+# point-for-point the numpy ones; the tests at small sizes use the numpy generators.)
+def device_cloud(kind: str, n: int, seed: int, device="cuda", noise: float = 0.0):
+    """float32 [n,3] on ``device``, normalised to the unit sphere like tutorial_utils.py:14-15 (mean in fp64).
+    kind: 'torus' (config 1/2 shape), 'sphere', 'multi' (config 4: sphere + torus + saddle sheet + cylinder in a common
+    box), 'density' (config 5: lidar-like 1/r^2 density falloff on a wavy ground sheet)."""
+    import math
+
+    import torch
+    g = torch.Generator(device=device).manual_seed(int(seed))
+    f64 = dict(dtype=torch.float64, device=device, generator=g)
+
+    def rnd(m):
+        return torch.rand(m, **f64)
+
+    def torus(m, R, r):
+        u, v = rnd(m) * (2 * math.pi), rnd(m) * (2 * math.pi)
+        cu, su, cv, sv = torch.cos(u), torch.sin(u), torch.cos(v), torch.sin(v)
+        return torch.stack([(R + r * cv) * cu, (R + r * cv) * su, r * sv], 1), torch.stack([cv * cu, cv * su, sv], 1)
+
+    def sphere(m, rad):
+        v = torch.randn((m, 3), **f64)
+        v = v / v.norm(dim=1, keepdim=True)
+        return v * rad, v
+
+    if kind == "torus":
+        p, nrm = torus(n, 1.0, 0.3)
+    elif kind == "sphere":
+        p, nrm = sphere(n, 1.0)
+    elif kind == "multi":
+        m = n // 4
+        a, na = sphere(m, 0.6)
+        a[:, 0] += 1.5
+        b, nb = torus(m, 0.8, 0.25)
+        b[:, 0] -= 1.5
+        xy = rnd((m, 2)) * 2 - 1
+        c = torch.stack([xy[:, 0], xy[:, 1] + 2.0, 0.4 * (xy[:, 0] ** 2 - xy[:, 1] ** 2)], 1)
+        gx, gy = 0.8 * xy[:, 0], -0.8 * xy[:, 1]
+        nc = torch.stack([-gx, -gy, torch.ones_like(gx)], 1)
+        nc = nc / nc.norm(dim=1, keepdim=True)
+        m2 = n - 3 * m
+        t, h = rnd(m2) * (2 * math.pi), rnd(m2) * 2 - 1
+        d = torch.stack([0.5 * torch.cos(t), 0.5 * torch.sin(t) - 2.0, h], 1)
+        nd = torch.stack([torch.cos(t), torch.sin(t), torch.zeros_like(t)], 1)
+        p, nrm = torch.cat([a, b, c, d]), torch.cat([na, nb, nc, nd])
+        perm = torch.randperm(n, device=device, generator=g)      # file order must not follow the surfaces
+        p, nrm = p[perm], nrm[perm]
+    elif kind == "density":
+        r = 1.0 / (rnd(n) * 0.98 + 0.02)                          # heavy near the sensor, out to 50 units
+        th = rnd(n) * (2 * math.pi)
+        x, y = r * torch.cos(th), r * torch.sin(th)
+        z = 0.3 * torch.sin(0.4 * x) * torch.cos(0.3 * y) + 0.02 * torch.randn(n, **f64)
+        p, nrm = torch.stack([x, y, z], 1), None
+    else:
+        raise ValueError("unknown cloud kind %r" % kind)
+    if noise > 0 and nrm is not None:
+        bb = (p.max(0)[0] - p.min(0)[0]).norm()
+        p = p + nrm * (torch.randn((n, 1), **f64) * (noise * bb))
+    p32 = p.float()
+    bbdiag = (p32.max(0)[0] - p32.min(0)[0]).double().norm()
+    mean = p32.double().mean(0)
+    return ((p32.double() - mean) / (0.5 * bbdiag)).float().contiguous()

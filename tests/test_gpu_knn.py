@@ -133,6 +133,64 @@ def test_knn_full_size_properties():
         assert bool((torch.sqrt(val[:k]) == dist[j]).all())
 
 
+def _bruteforce_rows(pts, queries, k):
+    """Exact kNN of a few queries over a LARGE cloud by brute force in torch fp64 on the device (library ops as the
+    checker): key (d2 accumulated x -> y -> z without contraction, index).  Returns (idx i64 [Q,k], dist f64 [Q,k])."""
+    px, py, pz = pts[:, 0].double(), pts[:, 1].double(), pts[:, 2].double()
+    out_i = torch.empty((queries.numel(), k), dtype=torch.int64, device=pts.device)
+    out_d = torch.empty((queries.numel(), k), dtype=torch.float64, device=pts.device)
+    for j in range(queries.numel()):
+        c = int(queries[j])
+        dx = px - px[c]
+        d2 = dx * dx
+        dy = py - py[c]
+        d2 = d2 + dy * dy
+        dz = pz - pz[c]
+        d2 = d2 + dz * dz
+        kth = torch.topk(d2, k, largest=False)[0].max()
+        cand = torch.nonzero(d2 <= kth).flatten()            # every member of the tie group at the k-th place included
+        v = d2[cand]                                          # cand ascending => a stable sort by value breaks ties by index
+        order = torch.argsort(v, stable=True)[:k]
+        out_i[j] = cand[order]
+        out_d[j] = torch.sqrt(v[order])
+    return out_i, out_d
+
+
+@pytest.mark.parametrize("kind,n,seed,ks", [("multi", 10_000_000, 4321, (256, 512)), ("density", 32_000_000, 9876, (256,))],
+                         ids=["config4_multi_10M", "config5_density_32M"])
+def test_knn_exact_at_named_sizes(kind, n, seed, ks):
+    """BASELINE configs 4 / 5 at size: the 10 M-point multi-surface scan (k = 256 and 512) and a
+    32 M-point variable-density scan (1/r^2 falloff: cell occupancies from a handful to tens of thousands), 256 random
+    queries each plus the 64 queries in the densest cell region, bit-equal -- indices and fp64 distances -- to an fp64
+    brute force over the whole cloud; size-independent properties on a contiguous slab of queries."""
+    from deepfit_b200 import ops, synthetic
+    pts = synthetic.device_cloud(kind, n, seed, "cuda")
+    grid = ops.Grid(pts)
+    rng = np.random.default_rng(5)
+    sample = torch.from_numpy(rng.choice(n, 256, replace=False).astype(np.int64)).cuda()
+    # the points nearest to the cloud's densest spot (the sensor ring of the density scan / anywhere for the multi scan)
+    centre = pts[torch.randint(0, n, (1,), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))]
+    if kind == "density":
+        r2 = (pts[:, 0].double() ** 2 + pts[:, 1].double() ** 2)
+        centre = pts[torch.argmin(r2)][None]
+    dense = torch.topk(((pts - centre) ** 2).sum(1), 64, largest=False)[1]
+    sample = torch.cat([sample, dense])
+    for k in ks:
+        idx, rad, dist = grid.query(k, query=sample.int(), return_dist=True)
+        ref_i, ref_d = _bruteforce_rows(pts, sample, k)
+        assert bool((idx.long() == ref_i).all()), "k=%d: rows %s differ" % (k, torch.nonzero((idx.long() != ref_i).any(1)).flatten()[:8].tolist())
+        assert bool((dist == ref_d).all()) and bool((rad == ref_d[:, -1]).all())
+        # properties on a slab of consecutive queries through the range form of the call (what the pipeline uses)
+        s = n // 3
+        idx, rad, dist = grid.query(k, q_begin=s, q_count=100_000, return_dist=True)
+        assert bool((dist[:, 1:] >= dist[:, :-1]).all()) and bool((dist[:, 0] == 0).all()) and bool((rad == dist[:, -1]).all())
+        srt = torch.sort(idx.long(), dim=1)[0]
+        assert bool((srt[:, 1:] != srt[:, :-1]).all())
+        sub = torch.arange(s, s + 100_000, 3125, device="cuda")
+        ref_i, ref_d = _bruteforce_rows(pts, sub, k)
+        assert bool((idx[sub - s].long() == ref_i).all()) and bool((dist[sub - s] == ref_d).all())
+
+
 def _ball_sets(pts_np, q, radius):
     from deepfit_b200 import ops
     pts = torch.from_numpy(np.ascontiguousarray(pts_np)).cuda()

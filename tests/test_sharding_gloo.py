@@ -31,6 +31,18 @@ def _worker(rank, world, port, n, tmp):
     ok = torch.equal(nn, normals) and torch.equal(cc, curv)
     nn2, cc2 = gather_outputs(normals[b:e].clone(), None, n, rank, world)
     ok = ok and torch.equal(nn2, normals) and cc2 is None
+    # the hot-path form: each rank writes its range straight into its slot, the gather is in place, nothing is widened
+    from deepfit_b200.sharding import GatherBuffers
+    bufs = GatherBuffers(n, world, "cpu")
+    vn, vc = bufs.local_views(rank)
+    ok = ok and vn.shape[0] == e - b and vn.dtype == torch.float32 and vc.dtype == torch.float64
+    ok = ok and vn.data_ptr() == bufs.normals[rank * bufs.cap:].data_ptr()
+    vn.copy_(normals[b:e])
+    vc.copy_(curv[b:e])
+    bufs.all_gather(rank)
+    fn, fc = bufs.file_order()
+    ok = ok and torch.equal(fn, normals) and torch.equal(fc, curv)
+    ok = ok and bufs.bytes_per_rank() == bufs.cap * 28
     with open(os.path.join(tmp, "ok%d" % rank), "w") as fh:
         fh.write("1" if ok else "0")
     dist.barrier()

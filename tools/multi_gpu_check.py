@@ -21,18 +21,22 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from deepfit_b200 import synthetic
-    from deepfit_b200.pipeline import NormalEstimator, gather_outputs, model_from_state_dict, shard_range
+    from deepfit_b200.pipeline import NormalEstimator, model_from_state_dict
+    from deepfit_b200.sharding import GatherBuffers, shard_range
     from deepfit_b200.tutorial_utils import normalize_cloud
     from deepfit_b200.synthetic import synthetic_state_dict
     n = 30011  # deliberately not divisible by the world size
     pts = torch.from_numpy(np.ascontiguousarray(normalize_cloud(synthetic.torus_cloud(n, seed=5, noise=0.003))[0])).cuda()
     ok = True
     for mode in ("classic", "DeepFit"):
-        model = model_from_state_dict(synthetic_state_dict(0), 256, 3, "sigmoid", "bf16x3", "cuda") if mode == "DeepFit" else None
+        model = model_from_state_dict(synthetic_state_dict(0), 256, 3, "sigmoid", "f16f8", "cuda") if mode == "DeepFit" else None
         est = NormalEstimator(pts, 256, 3, mode, model, chunk=2048)
         b, e = shard_range(n, rank, world)
-        nl, cl = est.run(b, e)
-        ng, cg = gather_outputs(nl, cl, n, rank, world)
+        bufs = GatherBuffers(n, world, pts.device)
+        vn, vc = bufs.local_views(rank)
+        est.run(b, e, out_normals=vn, out_curv=vc)      # written in place into the rank's slot of the gather buffers
+        bufs.all_gather(rank)
+        ng, cg = bufs.file_order()
         nf, cf = est.run(0, n)
         same = torch.equal(ng, nf) and torch.equal(cg, cf)
         print("rank %d/%d %s: shard [%d,%d) gathered == whole-cloud: %s" % (rank, world, mode, b, e, same), flush=True)
