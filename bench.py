@@ -394,7 +394,8 @@ def main():
     ap.add_argument("--points", type=int, default=0, help="points per GPU (weak) or in total (strong); 0 = the workload's size")
     ap.add_argument("--cloud", type=str, default="", help="override the workload's surface: torus | sphere | multi | density")
     ap.add_argument("--order", type=int, default=0, help="jet order of the classic workload (config2)")
-    ap.add_argument("--precision", type=str, default="f16f8", help="f16f8 | bf16x3 (both parity grade) | bf16")
+    ap.add_argument("--precision", type=str, default="f16x3",
+                    help="f16x3 (parity mode: split FP16, 3 products, 22-bit operands) | bf16x3 | f16f8 | bf16 (faster approximations)")
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--ref-sample", type=int, default=2048)
     ap.add_argument("--e2e-steps", type=int, default=-1, help="steps of the end-to-end region (default: same as --steps)")
@@ -538,6 +539,7 @@ def main():
         d["chunk_points"] = c
         return d, patch
     est.points = pts
+    staged_pass()                       # first pass pays the allocator's cudaMallocs for these shapes
     stages, patch0 = staged_pass()
 
     e2e_steps = args.steps if args.e2e_steps < 0 else args.e2e_steps
@@ -553,8 +555,10 @@ def main():
         line = {
             "metric": metric_name(mode, ORDER, K), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-            "dtype": {"f16f8": "f16f8 (fp16 tensor-core MMA + one e4m3 correction MMA per k-step, fp32 accumulate; fp32-grade)",
-                      "bf16x3": "bf16x3 (split-bf16 tensor-core MMA, fp32 accumulate; fp32-grade)", "bf16": "bf16"}[args.precision]
+            "dtype": {"f16x3": "f16x3 (split-FP16 tensor-core MMA, three products per k-step, fp32 accumulate; fp32-grade: the parity mode)",
+                      "f16f8": "f16f8 (fp16 tensor-core MMA + one e4m3 correction MMA per k-step, fp32 accumulate; weights 3e-4 off)",
+                      "bf16x3": "bf16x3 (split-bf16 tensor-core MMA, three products per k-step, fp32 accumulate; weights 1e-4 off)",
+                      "bf16": "bf16"}[args.precision]
             if mode == "DeepFit" else "f64 moments / f32 solve",
             "data": "synthetic" if cloud != "boxy" else "tutorial cloud (tests/golden), seeded weights",
             "config": {"workload": workload_text(args, cloud, n_total, K, ORDER, mode, scaling, world),
@@ -578,7 +582,7 @@ def main():
             gm_ms, gm_n = prof["gemm_max_128x1024"]
             achieved = (n_patches_timed * chain_flop_per_patch(K)) / (gm_ms * 1e-3) / 1e12 if gm_ms > 0 else None
             net_ms = sum(v[0] for v in prof.values())
-            units = {"bf16x3": 3, "f16f8": 2, "bf16": 1}[args.precision]
+            units = {"f16x3": 3, "bf16x3": 3, "f16f8": 2, "bf16": 1}[args.precision]
             line["roofline"] = {
                 "bound": "tensor", "kernel": "chain_max_kernel<k/128> (points -> 64 -> [64 -> 64 ->] 128 -> 1024 + max-pool, persistent, "
                                              "3 launches per forward)",
@@ -589,9 +593,10 @@ def main():
                 "traffic_note": "see profiles/ (r2 ncu --set full capture of the same kernels); per launch of 16 384 patches",
                 "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained" % which,
                 "note": "achieved = algorithmic FLOPs of the three chain kernels (%.1f MFLOP/patch at k=%d) / their CUDA-event time. "
-                        "Precision %s executes %d tensor-core product unit(s) per algorithmic product (f16f8: one FP16 MMA + one "
-                        "E4M3 MMA at twice the rate = 2 units), so frac tops out near %.3f at the sustained clock the peak was "
-                        "measured at" % (chain_flop_per_patch(K) / 1e6, K, args.precision, units, 1.0 / units),
+                        "Precision %s executes %d tensor-core MMA(s) per algorithmic product (fp32-grade products need 22-bit "
+                        "operands = split FP16, hi*hi + hi*lo + lo*hi), so frac tops out near %.3f at the sustained clock the peak "
+                        "was measured at; executed_frac = frac x that count" % (chain_flop_per_patch(K) / 1e6, K, args.precision, units, 1.0 / units),
+                "executed_frac": (achieved * units / tf_sus) if achieved else None,
                 "product_units": units,
                 "launches": int(gm_n), "avg_launch_ms": gm_ms / gm_n if gm_n else None,
                 "share_of_network": gm_ms / net_ms if net_ms else None,

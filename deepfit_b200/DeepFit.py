@@ -117,7 +117,7 @@ class _Node(nn.Module):
 class DeepFit(nn.Module):
     def __init__(self, k=1, num_points=500, use_point_stn=False, use_feat_stn=False, point_tuple=1,
                  sym_op='max', arch=None, n_gaussians=5, jet_order=2, weight_mode="tanh",
-                 use_consistency=False, precision="bf16x3"):
+                 use_consistency=False, precision="f16x3"):
         super().__init__()
         if arch == '3dmfv':
             raise NotImplementedError("arch='3dmfv' (Fisher-vector encoder) is outside the hot path; the "

@@ -21,7 +21,7 @@ LAYER_NAMES = [
 assert len(LAYER_NAMES) == DFB_NUM_LAYERS
 
 WEIGHT_MODE = {"sigmoid": 0, "tanh": 1}
-PRECISION = {"bf16x3": 0, "bf16": 1, "f16f8": 2}
+PRECISION = {"bf16x3": 0, "bf16": 1, "f16f8": 2, "f16x3": 3}
 
 EXPORTS = [
     "dfb_abi_version", "dfb_last_error_string", "dfb_device_check",

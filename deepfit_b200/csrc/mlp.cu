@@ -227,12 +227,19 @@ __device__ __forceinline__ void umma_f8_ts(uint32_t tmem_d, uint32_t tmem_a, uin
 }
 
 // Operand formats of a model (dfb_model_desc::precision)
-enum { FMT_BF16X3 = 0, FMT_BF16 = 1, FMT_F16F8 = 2 };
+// FMT_F16X3: the split of FMT_BF16X3 on FP16 planes -- x * 2^7 = xh + xl, w * 2^8 = wh + wl with all four FP16 (the
+// residuals reach into FP16's subnormals, spacing 2^-24 of the scaled value), three kind::f16 MMAs hi*hi + hi*lo + lo*hi:
+// 22 mantissa bits per operand, i.e. fp32-grade products (the dropped lo*lo term is 2^-22 of the product) at the tensor
+// cost of bf16x3, whose 16-bit operands leave the weights 1e-4 off -- enough to break the 1e-3 curvature gate on
+// ill-conditioned lidar patches (oracle/studies/gate_rows_sensitivity.py).  Same plane layout as bf16x3.
+enum { FMT_BF16X3 = 0, FMT_BF16 = 1, FMT_F16F8 = 2, FMT_F16X3 = 3 };
 __host__ __device__ __forceinline__ int fmt_planes(int fmt) { return fmt == FMT_BF16 ? 1 : 2; }
-__host__ __device__ __forceinline__ int fmt_code(int fmt) { return fmt == FMT_F16F8 ? 0 : 1; }
-// FMT_F16F8 scales: main plane of activations x 2^7, of weights x 2^8; accumulators hold 2^15 x the product
+__host__ __device__ __forceinline__ int fmt_code(int fmt) { return (fmt == FMT_F16F8 || fmt == FMT_F16X3) ? 0 : 1; }
+__host__ __device__ __forceinline__ bool fmt_is_f16(int fmt) { return fmt == FMT_F16F8 || fmt == FMT_F16X3; }
+__host__ __device__ __forceinline__ bool fmt_three(int fmt) { return fmt == FMT_BF16X3 || fmt == FMT_F16X3; }
+// FMT_F16F8 / FMT_F16X3 scales: main plane of activations x 2^7, of weights x 2^8; accumulators hold 2^15 x the product
 constexpr float kActMain = 128.f, kWgtMain = 256.f;
-__host__ __device__ __forceinline__ float fmt_acc_scale(int fmt) { return fmt == FMT_F16F8 ? (1.f / 32768.f) : 1.f; }
+__host__ __device__ __forceinline__ float fmt_acc_scale(int fmt) { return fmt_is_f16(fmt) ? (1.f / 32768.f) : 1.f; }
 constexpr float kActLimit = 500.f;   // |activation| x 2^7 must stay inside FP16 (65504 / 128 = 511)
 
 // The products of one k-step (16 channels) into accumulator d: hi*hi [+ hi*lo + lo*hi] (bf16 formats) or
@@ -240,7 +247,7 @@ constexpr float kActLimit = 500.f;   // |activation| x 2^7 must stay inside FP16
 __device__ __forceinline__ void mma_kstep(int fmt, uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
                                           uint32_t idesc, uint32_t accum) {
     umma_bf16(d, a_hi, b_hi, idesc, accum);
-    if (fmt == FMT_BF16X3) {
+    if (fmt_three(fmt)) {
         umma_bf16(d, a_hi, b_lo, idesc, 1u);
         umma_bf16(d, a_lo, b_hi, idesc, 1u);
     } else if (fmt == FMT_F16F8) {
@@ -251,7 +258,7 @@ __device__ __forceinline__ void mma_kstep(int fmt, uint32_t d, uint64_t a_hi, ui
 __device__ __forceinline__ void mma_kstep_ts(int fmt, uint32_t d, uint32_t a_hi, uint32_t a_lo, uint64_t b_hi, uint64_t b_lo,
                                              uint32_t idesc, uint32_t accum) {
     umma_bf16_ts(d, a_hi, b_hi, idesc, accum);
-    if (fmt == FMT_BF16X3) {
+    if (fmt_three(fmt)) {
         umma_bf16_ts(d, a_hi, b_lo, idesc, 1u);
         umma_bf16_ts(d, a_lo, b_hi, idesc, 1u);
     } else if (fmt == FMT_F16F8) {
@@ -271,6 +278,24 @@ __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint3
     const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xffff0000u);
     const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
     lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// FMT_F16X3: scaled FP16 hi / lo pair of two values (x * scale = hi + lo, scale 2^7 activation side, 2^8 weight side)
+template <bool WSIDE>
+__device__ __forceinline__ void split_pair_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+    constexpr float ms = WSIDE ? 256.f : 128.f;
+    const float as = a * ms, bs = b * ms;
+    const __half2 h = __floats2half2_rn(as, bs);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(as - hf.x, bs - hf.y);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// the two-plane 16-bit formats (bf16x3, bf16, f16x3) behind one call
+template <bool WSIDE>
+__device__ __forceinline__ void split_pair_fmt(int fmt, float a, float b, uint32_t& hi, uint32_t& lo) {
+    if (fmt == FMT_F16X3) split_pair_f16<WSIDE>(a, b, hi, lo);
+    else split_pair(a, b, hi, lo);
 }
 
 // two floats -> two E4M3 bytes (a in the low byte, b in the high byte), round to nearest, saturating
@@ -305,6 +330,14 @@ __device__ __forceinline__ void f16f8_pair(float a, float b, uint32_t& main, uin
 template <bool WSIDE>
 __device__ __forceinline__ float split32(int fmt, const float (&f)[32], uint32_t (&ph)[16], uint32_t (&pl)[16]) {
     float mx = 0.f;
+    if (fmt == FMT_F16X3) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            mx = fmaxf(mx, fmaxf(fabsf(f[2 * e]), fabsf(f[2 * e + 1])));
+            split_pair_f16<WSIDE>(f[2 * e], f[2 * e + 1], ph[e], pl[e]);
+        }
+        return mx;
+    }
     if (fmt != FMT_F16F8) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) split_pair(f[2 * e], f[2 * e + 1], ph[e], pl[e]);
@@ -329,6 +362,14 @@ __device__ __forceinline__ float split32(int fmt, const float (&f)[32], uint32_t
 }
 // One value (row, channel) of a tiled activation matrix (the per-patch outputs of the max-pool epilogues).
 __device__ __forceinline__ void store_one_act(int fmt, bf16* out_t, size_t plane, long long row, int ch, int KB, float r) {
+    if (fmt == FMT_F16X3) {
+        const float rs = r * kActMain;
+        const __half h = __float2half_rn(rs);
+        const size_t o = tiled_offset(row, ch, KB);
+        reinterpret_cast<__half*>(out_t)[o] = h;
+        reinterpret_cast<__half*>(out_t)[plane + o] = __float2half_rn(rs - __half2float(h));
+        return;
+    }
     if (fmt != FMT_F16F8) {
         bf16 hi, lo;
         split_bf16(r, hi, lo);
@@ -358,7 +399,7 @@ struct GemmArgs {
     size_t a_plane;      // element offset of the lo plane (hi at 0)
     size_t b_plane;
     int KB;              // 64-column k-blocks
-    int fmt;             // FMT_BF16X3 (hi*hi + hi*lo + lo*hi), FMT_BF16 (hi*hi) or FMT_F16F8 (fp16 hi*hi + one e4m3 MMA)
+    int fmt;             // FMT_BF16X3 / FMT_F16X3 (hi*hi + hi*lo + lo*hi), FMT_BF16 (hi*hi) or FMT_F16F8 (fp16 hi*hi + one e4m3 MMA)
     int n_mma;           // N of each UMMA (64 or 128)
     int tmode;           // 0: N orientation (A = activations), 1: T orientation (A = weights)
     int rows_per_patch;  // points per patch (N mode, activations) or 0 when rows are patches
@@ -576,7 +617,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
                                 uint32_t ph[4], plo[4];
                                 if (g.fmt != FMT_F16F8) {
 #pragma unroll
-                                    for (int e = 0; e < 4; ++e) split_pair(f[c8 * 8 + 2 * e], f[c8 * 8 + 2 * e + 1], ph[e], plo[e]);
+                                    for (int e = 0; e < 4; ++e) split_pair_fmt<true>(g.fmt, f[c8 * 8 + 2 * e], f[c8 * 8 + 2 * e + 1], ph[e], plo[e]);
                                     *reinterpret_cast<uint4*>(g.out_t + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                                     if (planes > 1) *reinterpret_cast<uint4*>(g.out_t + g.out_plane + o) = make_uint4(plo[0], plo[1], plo[2], plo[3]);
                                 } else {
@@ -1717,13 +1758,16 @@ __global__ void pack_tiled_kernel(const float* __restrict__ src, long long rows,
             const int c = c8 * 8 + 2 * e;
             if (r < rows && c < cols) a = src[r * ld + c];
             if (r < rows && c + 1 < cols) b = src[r * ld + c + 1];
-            if (fmt != FMT_F16F8) split_pair(a, b, ph[e], pl[e]);
+            if (fmt == FMT_F16X3) {
+                if (wside) split_pair_f16<true>(a, b, ph[e], pl[e]);
+                else split_pair_f16<false>(a, b, ph[e], pl[e]);
+            } else if (fmt != FMT_F16F8) split_pair(a, b, ph[e], pl[e]);
             else if (wside) f16f8_pair<true>(a, b, ph[e], c0[e], c1[e]);
             else f16f8_pair<false>(a, b, ph[e], c0[e], c1[e]);
         }
         const size_t o = tiled_offset(r, c8 * 8, KB, br);
         *reinterpret_cast<uint4*>(dst + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-        if (fmt == FMT_BF16X3) {
+        if (fmt_three(fmt)) {
             *reinterpret_cast<uint4*>(dst + plane + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
         } else if (fmt == FMT_F16F8) {
             // 16-channel group m = c8 / 2: chunk 2m holds c0, chunk 2m + 1 holds c1; this thread fills 8 bytes of each
@@ -1748,7 +1792,10 @@ __global__ void unpack_tiled_kernel(const bf16* __restrict__ src, size_t plane, 
         const int c = (int)(i % cols);
         const size_t o = tiled_offset(r, c, KB, br);
         float v;
-        if (fmt != FMT_F16F8) {
+        if (fmt == FMT_F16X3) {
+            v = (__half2float(reinterpret_cast<const __half*>(src)[o]) + __half2float(reinterpret_cast<const __half*>(src)[plane + o])) *
+                (1.f / kActMain);
+        } else if (fmt != FMT_F16F8) {
             v = __bfloat162float(src[o]);
             if (fmt == FMT_BF16X3) v += __bfloat162float(src[plane + o]);
         } else {
@@ -2145,7 +2192,13 @@ int upload_head_w1_chunks(int fmt, const float* h_w, long long ldw, int col0, bf
             for (int kc = 0; kc < 64; ++kc) {
                 const float v = h_w[(size_t)(c * 64 + r) * ldw + col0 + kc];
                 const size_t o = (size_t)c * 8192 + (size_t)(kc >> 3) * 512 + (size_t)(r >> 3) * 64 + (size_t)(r & 7) * 8 + (kc & 7);
-                if (fmt != FMT_F16F8) {
+                if (fmt == FMT_F16X3) {
+                    const float vs = v * kWgtMain;
+                    const __half h = __float2half_rn(vs);
+                    const __half l = __float2half_rn(vs - __half2float(h));
+                    buf[o] = *reinterpret_cast<const uint16_t*>(&h);
+                    buf[o + 4096] = *reinterpret_cast<const uint16_t*>(&l);
+                } else if (fmt != FMT_F16F8) {
                     const uint16_t hi = host_bf16(v);
                     const uint16_t lo = host_bf16(v - host_bf16_to_f(hi));
                     buf[o] = hi;
@@ -2371,7 +2424,10 @@ extern "C" int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, d
     dfb_model* m = new dfb_model();
     m->k = desc->k;
     m->weight_mode = desc->weight_mode;
-    m->fmt = desc->precision == DFB_PRECISION_BF16 ? FMT_BF16 : (desc->precision == DFB_PRECISION_F16F8 ? FMT_F16F8 : FMT_BF16X3);
+    DFB_REQUIRE(desc->precision >= DFB_PRECISION_BF16X3 && desc->precision <= DFB_PRECISION_F16X3, DFB_E_ARG,
+                "dfb_model_create: unknown precision %d", desc->precision);
+    static const int fmt_of[4] = {FMT_BF16X3, FMT_BF16, FMT_F16F8, FMT_F16X3};
+    m->fmt = fmt_of[desc->precision];
     m->max_batch = desc->max_batch > 0 ? (desc->max_batch + 127) / 128 * 128 : 1024;
 #define DFB_TRY(expr)                     \
     do {                                  \
@@ -2382,14 +2438,14 @@ extern "C" int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, d
         }                                 \
     } while (0)
     auto track = [&](void* p) { m->allocs.push_back(p); };
-    if (m->fmt == FMT_F16F8) {
+    if (fmt_is_f16(m->fmt)) {
         // the main plane stores w * 2^8 in FP16: |w| must stay below 65504 / 256
         for (int i = 0; i < DFB_NUM_LAYERS; ++i) {
             const dfb_layer& l = desc->layers[i];
             float mx = 0.f;
             for (size_t j = 0; j < (size_t)l.in_features * l.out_features; ++j) mx = std::max(mx, fabsf(l.h_weight[j]));
             if (!(mx < 250.f)) {
-                set_error("dfb_model_create: layer %d has |w| up to %g, outside the FP16 range of precision f16f8; use bf16x3", i, mx);
+                set_error("dfb_model_create: layer %d has |w| up to %g, outside the FP16 range of precisions f16x3 / f16f8; use bf16x3", i, mx);
                 dfb_model_destroy(m);
                 return DFB_E_UNSUPPORTED;
             }
@@ -2488,7 +2544,7 @@ extern "C" int dfb_model_status(dfb_model* m, dfb_stream stream) {
         DFB_CUDA(cudaMemsetAsync(m->err, 0, sizeof(int), as_stream(stream)));
         DFB_CUDA(cudaStreamSynchronize(as_stream(stream)));
         if (h == 100)
-            set_error("activation magnitude above %g inside the network: outside the FP16 range of precision f16f8 "
+            set_error("activation magnitude above %g inside the network: outside the FP16 range of precisions f16x3 / f16f8 "
                       "(use precision bf16x3 for this model); outputs since the last status check are invalid", (double)kActLimit);
         else
             set_error("tensor-core pipeline time-out (mbarrier wait, role %d): the outputs of the forwards since the last "
@@ -2740,7 +2796,8 @@ extern "C" DFB_API int dfb_dbg_gemm(const float* d_A, const float* d_B, const fl
     if (rc) return rc;
     cudaStream_t st = as_stream(stream);
     dfb_model fake;
-    const int fmt = nprod == 1 ? FMT_BF16 : (nprod == 2 ? FMT_F16F8 : FMT_BF16X3);   // nprod = tensor-core product units per k-step
+    // nprod = tensor-core product units per k-step; 4 selects the split-FP16 form of the three-product scheme
+    const int fmt = nprod == 1 ? FMT_BF16 : (nprod == 2 ? FMT_F16F8 : (nprod == 4 ? FMT_F16X3 : FMT_BF16X3));
     fake.fmt = fmt;
     fake.k = k_pts;
     DFB_CUDA(cudaMalloc(&fake.err, sizeof(int)));

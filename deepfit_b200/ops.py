@@ -284,7 +284,7 @@ class WeightNetwork:
     """Device-resident, pre-packed weight network (stage 3).  ``layers`` is a list of
     (weight fp32 [out,in], bias fp32 [out]) CPU tensors in ``_lib.LAYER_NAMES`` order, BN folded."""
 
-    def __init__(self, layers, k: int, weight_mode: str = "sigmoid", precision: str = "bf16x3", max_batch: int = 0,
+    def __init__(self, layers, k: int, weight_mode: str = "sigmoid", precision: str = "f16x3", max_batch: int = 0,
                  device=None):
         if weight_mode not in _lib.WEIGHT_MODE:
             raise NotImplementedError(

@@ -203,7 +203,7 @@ def main(argv=None):
     ap.add_argument('--sparse_patches', type=int, default=False, help='evaluate on the .pidx subset')
     ap.add_argument('--batchSize', type=int, default=4096)
     ap.add_argument('--gpu_idx', type=int, default=0)
-    ap.add_argument('--precision', type=str, default='bf16x3')
+    ap.add_argument('--precision', type=str, default='f16x3')
     args = ap.parse_args(argv)
     dev = torch.device("cuda:%d" % args.gpu_idx)
     torch.cuda.set_device(dev)

@@ -110,7 +110,7 @@ class NormalEstimator:
 
 
 def model_from_state_dict(state_dict, num_points: int, jet_order: int = 3, weight_mode: str = "sigmoid",
-                          precision: str = "bf16x3", device="cuda") -> DeepFit:
+                          precision: str = "f16x3", device="cuda") -> DeepFit:
     m = DeepFit(k=1, num_points=num_points, use_point_stn=True, use_feat_stn=True, point_tuple=1, sym_op="max",
                 arch="simple", jet_order=jet_order, weight_mode=weight_mode, precision=precision)
     m.load_state_dict(state_dict)

@@ -27,7 +27,7 @@ def _build_client(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+@pytest.mark.parametrize("precision", ["f16x3", "bf16x3", "f16f8"])
 def test_c_client_runs_deepfit_mode_through_the_pipeline(tmp_path, precision):
     """dfb_model_create + dfb_pipeline_create + one dfb_pipeline_run from compiled code == NormalEstimator.run, bit for bit."""
     from deepfit_b200 import DeepFit as D

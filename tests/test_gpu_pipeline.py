@@ -72,13 +72,14 @@ def _oracle_on_our_patches(name, sd, patch, U, rad, n_perm=3):
     return _ORACLE_CACHE[name]
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+@pytest.mark.parametrize("precision", ["f16x3", "bf16x3", "f16f8"])
 @pytest.mark.parametrize("name", ["Boxy_smooth100k", "0000000000"])
 def test_deepfit_pipeline_vs_oracle(clouds, name, precision):
     """DeepFit mode end to end on both tutorial clouds (smooth CAD surface and noisy lidar scan).  The network is fed
     OUR PCA frame, so the oracle runs the reference algebra on our patches (the sign-alignment protocol of SURVEY.md
     section 8c).  Gates per row: max(0.01 deg, 2 x the reference's own fp32 noise on that row) and the same for 1e-3
-    on the curvatures; no row of the smooth cloud is relaxed."""
+    on the curvatures; no row of the smooth cloud is relaxed.  f16x3 is the parity mode (every gate on every row);
+    the approximate modes bf16x3 / f16f8 get 2x / 4x the curvature gate on the lidar cloud (see test_gpu_network.py)."""
     from deepfit_b200 import ops
     from deepfit_b200.pipeline import NormalEstimator, model_from_state_dict
     from oracle import deepfit_oracle as O
@@ -100,7 +101,8 @@ def test_deepfit_pipeline_vs_oracle(clouds, name, precision):
           "%d rows relaxed)" % (name, precision, ang.max(), (ang / gate_a).max(), int((gate_a > 0.01).sum()), count, err.max(),
                                 (err / gate_c).max(), int((gate_c > 1e-3).sum())))
     assert (ang <= gate_a).all(), "max angular deviation %g deg (p99 %g)" % (ang.max(), np.quantile(ang, 0.99))
-    assert (err <= gate_c).all(), "max curvature error %g" % err.max()
+    cf = {"f16x3": 1.0, "bf16x3": 2.0, "f16f8": 4.0}[precision] if name == "0000000000" else 1.0
+    assert (err <= cf * gate_c).all(), "max curvature error / gate %g" % (err / gate_c).max()
     if name == "Boxy_smooth100k":
         assert (gate_a <= 0.01).all() and (gate_c <= 1e-3).all()
 
@@ -115,7 +117,7 @@ def test_pipeline_call_equals_stage_calls(clouds, mode):
     from oracle import deepfit_oracle as O
     pts = torch.from_numpy(O.normalize_cloud(clouds["0000000000"])[0]).cuda()
     k, order = 256, 3
-    model = model_from_state_dict(O.seeded_state_dict(1), k, order, "sigmoid", "bf16x3") if mode == "DeepFit" else None
+    model = model_from_state_dict(O.seeded_state_dict(1), k, order, "sigmoid", "f16x3") if mode == "DeepFit" else None
     est = NormalEstimator(pts, k, order, mode, model, chunk=300)
     begin, end = 777, 777 + 1000                  # 3 chunks of 300 + a tail of 100
     extras = {}
@@ -169,7 +171,7 @@ def test_deepfit_order4_k512_stress_shape(clouds):
     pts_np = O.normalize_cloud(clouds["Boxy_smooth100k"])[0]
     pts = torch.from_numpy(pts_np).cuda()
     sd = O.seeded_state_dict(2)
-    model = model_from_state_dict(sd, 512, 4, "sigmoid", "bf16x3")
+    model = model_from_state_dict(sd, 512, 4, "sigmoid", "f16x3")
     est = NormalEstimator(pts, 512, mode="DeepFit", model=model, chunk=128)
     begin, count = 40000, 192
     normals, curv = est.run(begin, begin + count)
@@ -224,7 +226,7 @@ def test_pcpnet_style_full_outputs(tmp_path):
     root = str(tmp_path / "pclouds")
     names = synthetic.write_pcpnet_like(root, n_shapes=3, n_points=6000, n_sparse=200)
     sd = O.seeded_state_dict(0)
-    model = model_from_state_dict(sd, 256, 3, "sigmoid", "bf16x3")
+    model = model_from_state_dict(sd, 256, 3, "sigmoid", "f16x3")
     ds = pcpnet.PointcloudPatchDataset(root, "testset_synthetic.txt", points_per_patch=256, use_pca=True,
                                        sparse_patches=True, neighbor_search_method='k')
     assert ds.shape_names == names and ds.shape_patch_count == [200, 200, 200]
@@ -263,7 +265,7 @@ def test_deepfit_k128_single_tile_patches(clouds):
     pts_np = O.normalize_cloud(clouds["Boxy_smooth100k"])[0]
     pts = torch.from_numpy(pts_np).cuda()
     sd = O.seeded_state_dict(3)
-    model = model_from_state_dict(sd, 128, 2, "tanh", "bf16x3")
+    model = model_from_state_dict(sd, 128, 2, "tanh", "f16x3")
     est = NormalEstimator(pts, 128, mode="DeepFit", model=model, chunk=256)
     begin, count = 7000, 301          # odd tile count in the last chunk: exercises the non-cluster head kernel too
     normals, curv = est.run(begin, begin + count)
@@ -303,7 +305,7 @@ def test_cli_deepfit_mode_with_saved_model(clouds, tmp_path):
     crv = np.loadtxt(tmp_path / "out" / "part.curv")
     assert nrm.shape == (6000, 3) and crv.shape == (6000, 2)
     ds = tu.SinglePointCloudDataset(str(inp), 256)
-    model = model_from_state_dict(sd, 256, 3, "sigmoid", "bf16x3")
+    model = model_from_state_dict(sd, 256, 3, "sigmoid", "f16x3")
     n2, c2 = NormalEstimator(ds.points_gpu, 256, mode="DeepFit", model=model).run()
     assert np.array_equal(nrm.astype(np.float32), n2.cpu().numpy())       # '%.18e' round-trips exactly
     assert np.array_equal(crv, c2.cpu().numpy())

@@ -8,7 +8,7 @@ from deepfit_b200.tutorial_utils import normalize_cloud
 k, order, n = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 pts = torch.from_numpy(np.ascontiguousarray(normalize_cloud(synthetic.multi_surface_cloud(n))[0])).cuda()
 sd = synthetic.synthetic_state_dict(0, k, order)
-model = model_from_state_dict(sd, k, order, "sigmoid", "bf16x3")
+model = model_from_state_dict(sd, k, order, "sigmoid", "f16x3")
 est = NormalEstimator(pts, k, order, "DeepFit", model, chunk=int(sys.argv[4]) if len(sys.argv) > 4 else 0)
 q = min(n, 131072)
 est.net.profile(True)   # creates its event pool now, outside the timed region

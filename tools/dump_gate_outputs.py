@@ -19,7 +19,7 @@ def main():
     layers = D.fold_batchnorm(O.seeded_state_dict(0))
     for name in ("Boxy_smooth100k", "0000000000"):
         P = torch.from_numpy(golden[name + "/gate_patch"]).cuda()
-        for precision in ("bf16x3", "f16f8"):
+        for precision in ("f16x3", "bf16x3", "f16f8"):
             net = ops.WeightNetwork(layers, 256, "sigmoid", precision, max_batch=512)
             w, trans, _, pts = net.forward(P, want_trans2=False, want_points=True)
             net.status()

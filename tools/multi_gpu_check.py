@@ -29,7 +29,7 @@ def main():
     pts = torch.from_numpy(np.ascontiguousarray(normalize_cloud(synthetic.torus_cloud(n, seed=5, noise=0.003))[0])).cuda()
     ok = True
     for mode in ("classic", "DeepFit"):
-        model = model_from_state_dict(synthetic_state_dict(0), 256, 3, "sigmoid", "f16f8", "cuda") if mode == "DeepFit" else None
+        model = model_from_state_dict(synthetic_state_dict(0), 256, 3, "sigmoid", "f16x3", "cuda") if mode == "DeepFit" else None
         est = NormalEstimator(pts, 256, 3, mode, model, chunk=2048)
         b, e = shard_range(n, rank, world)
         bufs = GatherBuffers(n, world, pts.device)

@@ -13,7 +13,7 @@ xy = torch.rand((B, 2, 256), generator=g) * 1.4 - 0.7
 c = torch.rand((B, 3, 1), generator=g) - 0.5
 zz = 0.3 * (c[:, 0:1] * xy[:, 0:1] ** 2 + c[:, 1:2] * xy[:, 1:2] ** 2 + c[:, 2:3] * xy[:, 0:1] * xy[:, 1:2])
 patch = torch.cat([xy, zz], 1).cuda().contiguous()
-model = model_from_state_dict(sd, 256, 3, "sigmoid", "bf16x3")
+model = model_from_state_dict(sd, 256, 3, "sigmoid", "f16x3")
 net = model._network(patch.device, 1024)
 res = {}
 for name, k8, k10 in (("both off", 0, 0), ("head persistent", 1, 0), ("chain persistent", 0, 1), ("both", 1, 1)):

@@ -7,7 +7,7 @@ from deepfit_b200.pipeline import NormalEstimator, model_from_state_dict
 from deepfit_b200.tutorial_utils import normalize_cloud
 k, order, n, chunk = (int(a) for a in sys.argv[1:5])
 pts = torch.from_numpy(np.ascontiguousarray(normalize_cloud(synthetic.multi_surface_cloud(n))[0])).cuda()
-model = model_from_state_dict(synthetic.synthetic_state_dict(0, k, order), k, order, "sigmoid", "bf16x3")
+model = model_from_state_dict(synthetic.synthetic_state_dict(0, k, order), k, order, "sigmoid", "f16x3")
 est = NormalEstimator(pts, k, order, "DeepFit", model, chunk=chunk)
 for rep in range(3):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]

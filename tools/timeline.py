@@ -39,7 +39,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cta", type=int, default=2000)
     ap.add_argument("--batch", type=int, default=4096)
-    ap.add_argument("--precision", type=str, default="bf16x3")
+    ap.add_argument("--precision", type=str, default="f16x3")
     args = ap.parse_args()
     from deepfit_b200 import _lib
     from deepfit_b200.pipeline import model_from_state_dict
