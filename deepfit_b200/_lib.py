@@ -25,7 +25,7 @@ PRECISION = {"bf16x3": 0, "bf16": 1, "f16f8": 2, "f16x3": 3}
 
 EXPORTS = [
     "dfb_abi_version", "dfb_last_error_string", "dfb_device_check",
-    "dfb_grid_create", "dfb_grid_update", "dfb_grid_destroy", "dfb_knn", "dfb_ball_count", "dfb_ball_fill",
+    "dfb_grid_create", "dfb_grid_update", "dfb_grid_destroy", "dfb_grid_morton_order", "dfb_knn", "dfb_ball_count", "dfb_ball_fill",
     "dfb_patch_pca", "dfb_patch_pca_ragged",
     "dfb_model_create", "dfb_model_destroy", "dfb_model_forward", "dfb_model_status",
     "dfb_model_profile", "dfb_model_profile_read", "dfb_launch_count",
@@ -92,6 +92,7 @@ def load():
     lib.dfb_grid_create.argtypes = [vp, i64, vp, C.POINTER(vp)]
     lib.dfb_grid_destroy.argtypes = [vp]
     lib.dfb_grid_update.argtypes = [vp, vp, vp]
+    lib.dfb_grid_morton_order.argtypes = [vp, i64, i64, vp, vp]
     lib.dfb_knn.argtypes = [vp, vp, i64, i64, i32, vp, vp, vp, vp]
     lib.dfb_ball_count.argtypes = [vp, vp, i64, i64, vp, C.c_double, vp, vp]
     lib.dfb_ball_fill.argtypes = [vp, vp, i64, i64, vp, C.c_double, vp, vp, vp]

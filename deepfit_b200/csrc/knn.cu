@@ -229,7 +229,73 @@ __global__ void scatter_kernel(const float* __restrict__ pts, long long n, const
     sorted[pos] = make_float4(pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2], __int_as_float((int)i));
 }
 
+// Indices of the points with q_begin <= index < q_end in MORTON order (the order of the sorted copy): an order-preserving
+// stream compaction of the sorted array in three launches (per-block counts, one-block exclusive scan, scatter).
+// Spatially ordered query lists are what makes consecutive queries share their candidate cells (dfb_knn).
+constexpr int kOrderBlock = 1024;
+__global__ void __launch_bounds__(kOrderBlock) order_count_kernel(const float4* __restrict__ sorted, long long n, int q0, int q1,
+                                                                    uint32_t* __restrict__ counts) {
+    __shared__ uint32_t s_w[kOrderBlock / 32];
+    const long long i = (long long)blockIdx.x * kOrderBlock + threadIdx.x;
+    bool in = false;
+    if (i < n) {
+        const int id = __float_as_int(sorted[i].w);
+        in = id >= q0 && id < q1;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, in);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t v = s_w[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) counts[blockIdx.x] = v;
+    }
+}
+__global__ void __launch_bounds__(kOrderBlock) order_scatter_kernel(const float4* __restrict__ sorted, long long n, int q0, int q1,
+                                                                      const uint32_t* __restrict__ base, int* __restrict__ out) {
+    __shared__ uint32_t s_w[kOrderBlock / 32];
+    const long long i = (long long)blockIdx.x * kOrderBlock + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    bool in = false;
+    int id = 0;
+    if (i < n) {
+        id = __float_as_int(sorted[i].w);
+        in = id >= q0 && id < q1;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, in);
+    if (lane == 0) s_w[w] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x < 32) {   // exclusive scan of the 32 warp counts
+        const uint32_t v = s_w[threadIdx.x];
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (threadIdx.x >= o) x += y;
+        }
+        s_w[threadIdx.x] = x - v;
+    }
+    __syncthreads();
+    if (in) out[base[blockIdx.x] + s_w[w] + __popc(bal & ((1u << lane) - 1u))] = id;
+}
+
 // ---------------------------------------------------------------------------------------- query
+
+// Warp reductions whose result the compiler KNOWS to be warp-uniform (REDUX, one instruction): a butterfly of xor-shuffles
+// yields the same value in every lane too, but the compiler cannot prove it, so every branch on such a value makes the
+// code that follows "potentially divergent" and each later shuffle / vote is wrapped in a WARPSYNC.COLLECTIVE sequence
+// (5 instructions instead of 1; 190 sites in this kernel).
+__device__ __forceinline__ int warp_sum_uniform(int v) { return (int)__reduce_add_sync(0xffffffffu, (unsigned)v); }
+// minimum / maximum of non-negative 64-bit patterns
+__device__ __forceinline__ long long warp_min_uniform(long long v) {
+    const unsigned h = __reduce_min_sync(0xffffffffu, (unsigned)(v >> 32));
+    const unsigned l = __reduce_min_sync(0xffffffffu, (unsigned)(v >> 32) == h ? (unsigned)v : 0xffffffffu);
+    return (long long)(((unsigned long long)h << 32) | l);
+}
+__device__ __forceinline__ long long warp_max_uniform(long long v) {
+    const unsigned h = __reduce_max_sync(0xffffffffu, (unsigned)(v >> 32));
+    const unsigned l = __reduce_max_sync(0xffffffffu, (unsigned)(v >> 32) == h ? (unsigned)v : 0u);
+    return (long long)(((unsigned long long)h << 32) | l);
+}
 
 struct Key {
     double d2;
@@ -258,14 +324,17 @@ __device__ __forceinline__ void warp_bitonic_sort(double* sd, int* si, int cap, 
     }
 }
 
-// Tighten the list without sorting it: find, by bisection, a bound T with at least k (and at most a few more) of the
-// count entries <= T, then compact those to the front.  T is an UPPER bound of the k-th smallest key seen so far, which
-// is all the pruning needs (every true neighbour has d2 <= T; ties are kept, the final sort orders them).  The bisection
-// runs on the BIT PATTERNS of the (non-negative) distances: they are monotone in the value and roughly logarithmic, so a
-// list that mixes a dense cluster with far points converges as fast as a uniform one, and as an integer binary search it
-// ends at the exact k-th value at the latest.  ~1 k instructions where a 512-entry bitonic sort costs ~7 k.
-// Returns the new count (>= k; larger than k + 16 only for exact ties).  EXACT: run the search to its end, T is then
-// the k-th smallest distance itself and the new count is k unless distances tie across the cut.
+// Tighten the list without sorting it: find a bound T with at least k (and at most a few more) of the count entries
+// <= T, then compact those to the front.  T is an UPPER bound of the k-th smallest key seen so far, which is all the
+// pruning needs (every true neighbour has d2 <= T; ties are kept, the final sort orders them).
+// The search keeps a bracket (a, b] of BIT PATTERNS (monotone in the non-negative distances) with #(<= a) < k <= #(<= b)
+// and places the next probe by linear interpolation of the counts in VALUE space: squared distances to the points of a
+// surface or a volume are close to uniformly / polynomially distributed, so two or three probes usually land inside the
+// [k, k + 16] window where 10+ bisection steps were needed (the bisection loop was half of the kernel's instructions).
+// A probe that fails to shrink the bracket from the same side twice falls back to the midpoint of the bit patterns, and
+// as an integer search the loop ends at the exact k-th value at the latest.
+// Returns the new count (>= k; larger than k + 16 only for exact ties).  EXACT: run the search until exactly k entries
+// are <= T (or the bracket is one bit pattern wide: distances tie across the cut and the tied entries all stay).
 template <bool EXACT>
 __device__ __forceinline__ int warp_select_compact(double* sd, int* si, int count, int k, int lane, double& T) {
     long long lo = 0x7ff0000000000000LL, hi = 0;
@@ -274,24 +343,43 @@ __device__ __forceinline__ int warp_select_compact(double* sd, int* si, int coun
         lo = min(lo, v);
         hi = max(hi, v);
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    }
-    // invariant: #(<= hi) >= k and #(< lo) < k
-    for (int iter = 0; iter < 64 && lo < hi; ++iter) {
-        const long long mid = lo + ((hi - lo) >> 1);
-        int c = 0;
-        for (int t = lane; t < count; t += 32) c += (__double_as_longlong(sd[t]) <= mid) ? 1 : 0;
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (c >= k) {
-            hi = mid;
-            if (!EXACT && c <= k + 16) break;
-        } else {
-            lo = mid + 1;
+    lo = warp_min_uniform(lo);
+    hi = warp_max_uniform(hi);
+    // bracket: #(<= a) = ca < k <= cb = #(<= b)
+    long long a = lo - 1, b = hi;
+    int ca = 0, cb = count;
+    const int want = EXACT ? k : min(k + 8, count);
+    int same_side = 0;   // +n: the last n probes moved b, -n: moved a
+    if (!(EXACT ? cb == k : cb <= k + 16)) {
+        for (int iter = 0; iter < 96 && b - a > 1; ++iter) {
+            long long mid;
+            if (same_side >= 2 || same_side <= -2 || iter >= 12) {
+                mid = a + ((b - a) >> 1);
+                same_side = 0;
+            } else {
+                const double av = __longlong_as_double(max(a, 0LL)), bv = __longlong_as_double(b);
+                const double g = av + (bv - av) * ((double)(want - ca) / (double)(cb - ca));
+                mid = __double_as_longlong(g);
+                mid = max(a + 1, min(b - 1, mid));
+            }
+            int c = 0;
+            for (int t = lane; t < count; t += 32) c += (__double_as_longlong(sd[t]) <= mid) ? 1 : 0;
+            c = warp_sum_uniform(c);
+            if (c >= k) {
+                b = mid;
+                cb = c;
+                same_side = same_side > 0 ? same_side + 1 : 1;
+                if (EXACT ? c == k : c <= k + 16) break;
+            } else {
+                a = mid;
+                ca = c;
+                same_side = same_side < 0 ? same_side - 1 : -1;
+            }
         }
     }
+    hi = b;
     T = __longlong_as_double(hi);
+    if (cb == count) return count;   // nothing to drop
     int n = 0;
     for (int base = 0; base < count; base += 32) {
         const int t = base + lane;
@@ -316,6 +404,117 @@ __device__ __forceinline__ int warp_select_compact(double* sd, int* si, int coun
     return n;
 }
 
+// Ascending sort by (d2, index) of 32 * E entries held in registers, E consecutive positions per lane (position
+// lane * E + r): the strides below E are compare-exchanges between registers of one lane, the others one xor-shuffle of
+// the three key words.  d2 travels as its bit pattern (monotone for non-negative doubles) and a comparison is one 96-bit
+// integer compare of (d2, index).  Replaces the shared-memory network for the final exactly-k sort (a quarter of the
+// kernel's instructions and the source of its bank conflicts).  The (size, stride) loops stay ROLLED -- one inter-lane
+// stage body plus log2(E) intra-lane bodies, a few hundred instructions: the fully unrolled network (19 K instructions)
+// thrashed the instruction cache (50 % of the stall samples were no-instruction stalls).
+__device__ __forceinline__ bool key_less_bits(long long a, int ai, long long b, int bi) {
+    const unsigned __int128 ka = ((unsigned __int128)(unsigned long long)a << 32) | (unsigned)ai;
+    const unsigned __int128 kb = ((unsigned __int128)(unsigned long long)b << 32) | (unsigned)bi;
+    return ka < kb;
+}
+
+template <int E>
+__device__ __forceinline__ void warp_sort_regs(long long (&d)[E], int (&id)[E], int lane) {
+    constexpr int N = 32 * E;
+    const int base = lane * E;
+#pragma unroll 1
+    for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll 1
+        for (int stride = size >> 1; stride >= E; stride >>= 1) {
+            const int m = stride / E;
+            // every position of this lane has the same (e & stride) and (e & size) bits
+            const bool keep_min = ((base & stride) == 0) == ((base & size) == 0);
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                const long long od = __shfl_xor_sync(0xffffffffu, d[r], m);
+                const int oi = __shfl_xor_sync(0xffffffffu, id[r], m);
+                // keys are distinct (equal keys are identical padding entries, for which the choice does not matter)
+                if (key_less_bits(od, oi, d[r], id[r]) == keep_min) { d[r] = od; id[r] = oi; }
+            }
+        }
+#pragma unroll
+        for (int st = E >> 1; st > 0; st >>= 1) {
+            if (st <= (size >> 1)) {
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    if ((r & st) == 0) {
+                        const int r2 = r + st;
+                        const bool asc = ((base + r) & size) == 0;
+                        if (key_less_bits(d[r2], id[r2], d[r], id[r]) == asc) {
+                            const long long td = d[r]; d[r] = d[r2]; d[r2] = td;
+                            const int ti = id[r]; id[r] = id[r2]; id[r2] = ti;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Final step of a query whose list holds exactly k entries: register sort, then either the outputs (the k-th distance
+// lies strictly inside the block's guaranteed margin, or the block is the whole cloud) or the k-th key for the retry one
+// level up.  Deliberately NOT inlined: inside the query loop the compiler multiplies the sort's live ranges across its
+// cloned loop bodies (227 registers at E = 8); as a function it needs 40.
+struct SortResult {
+    long long kd;   // bit pattern of the k-th squared distance
+    int kid;        // its index
+    int accepted;
+};
+template <int E>
+__device__ __forceinline__ SortResult sort_emit(const double* sd, const int* si, int k, int lane, bool top, double margin2, int* oi,
+                                             double* odist, double* orad) {
+    long long kd[E];
+    int kid[E];
+    // the list is unordered, so the conflict-free striped read may land anywhere
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const int t = r * 32 + lane;
+        kd[r] = t < k ? __double_as_longlong(sd[t]) : 0x7ff0000000000000LL;
+        kid[r] = t < k ? si[t] : 0x7fffffff;
+    }
+    warp_sort_regs<E>(kd, kid, lane);
+    SortResult res;
+    res.kd = 0;
+    res.kid = 0;
+    // position k - 1 sits in lane (k - 1) / E: the lane's last entry with position < k.  (Written as a monotone select
+    // chain: picking register (k - 1) % E by comparison makes the compiler index the arrays dynamically, i.e. move them
+    // to local memory.)
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+        const bool below = lane * E + r < k;
+        res.kd = below ? kd[r] : res.kd;
+        res.kid = below ? kid[r] : res.kid;
+    }
+    res.kd = __shfl_sync(0xffffffffu, res.kd, (k - 1) / E);
+    res.kid = __shfl_sync(0xffffffffu, res.kid, (k - 1) / E);
+    const double dk2 = __longlong_as_double(res.kd);
+    res.accepted = (top || dk2 < margin2) ? 1 : 0;
+    if (res.accepted) {
+        if ((k % E) == 0 && E >= 4) {   // every lane holds a whole, 16-byte aligned run
+            if (lane * E < k) {
+#pragma unroll
+                for (int r = 0; r + 3 < E; r += 4)
+                    *reinterpret_cast<int4*>(oi + lane * E + r) = make_int4(kid[r], kid[r + 1], kid[r + 2], kid[r + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < E; ++r)
+                if (lane * E + r < k) oi[lane * E + r] = kid[r];
+        }
+        if (odist) {
+#pragma unroll
+            for (int r = 0; r < E; ++r)
+                if (lane * E + r < k) odist[lane * E + r] = sqrt(__longlong_as_double(kd[r]));
+        }
+        if (orad && lane == 0) *orad = sqrt(dk2);
+    }
+    return res;
+}
+
 struct KnnArgs {
     const float4* sorted;
     const uint32_t* tab;
@@ -337,9 +536,17 @@ constexpr int kKnnWarps = 4;
 __device__ __constant__ unsigned char c_cell_order[27] = {13, 12, 14, 10, 16, 4, 22, 9, 11, 15, 17, 3, 5, 21, 23, 1, 7, 19, 25,
                                                           0, 2, 6, 8, 18, 20, 24, 26};
 
-__global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
+// E = register entries per lane of the final sort (32 * E = the power of two >= k); 0: shared-memory network only
+#ifdef DFB_KNN_MINB   // A/B builds only (tools/build_variant.sh)
+#define DFB_KNN_BOUNDS __launch_bounds__(kKnnWarps * 32, DFB_KNN_MINB)
+#else
+#define DFB_KNN_BOUNDS __launch_bounds__(kKnnWarps * 32)
+#endif
+template <int E>
+__global__ void DFB_KNN_BOUNDS knn_kernel(KnnArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a broadcast: tells the compiler that it (and every loop bound derived from it) is warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     double* sd = reinterpret_cast<double*>(smem_raw) + (size_t)warp * a.kcap;
     int* si = reinterpret_cast<int*>(smem_raw + (size_t)kKnnWarps * a.kcap * sizeof(double)) + (size_t)warp * a.kcap;
     const GridParams gpar = *a.gp;
@@ -353,7 +560,15 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                           // region must not scan a coarse block), then up as usual.  Any level passing the margin test
                           // is exact.
 
-    for (long long qw = (long long)blockIdx.x * kKnnWarps + warp; qw < a.q_count; qw += (long long)gridDim.x * kKnnWarps) {
+    // Each warp takes a contiguous run of queries: consecutive queries of a spatially ordered list share their block of
+    // cells, so the level hint and the radius hint below come from a neighbour.
+    double prev_k2 = -1.0;   // k-th squared distance of the warp's previous query (< 0: none yet)
+    int pcx = 0, pcy = 0, pcz = 0;   // its cell at level_hint
+    const long long n_warps = (long long)gridDim.x * kKnnWarps;
+    const long long per_warp = (a.q_count + n_warps - 1) / n_warps;
+    const long long q_first = ((long long)blockIdx.x * kKnnWarps + warp) * per_warp;
+    const long long q_last = min(a.q_count, q_first + per_warp);
+    for (long long qw = q_first; qw < q_last; ++qw) {
         const long long qi = a.query ? (long long)a.query[qw] : a.q_begin + qw;
         const float qxf = a.pts[qi * 3], qyf = a.pts[qi * 3 + 1], qzf = a.pts[qi * 3 + 2];
         const double qx = qxf, qy = qyf, qz = qzf;
@@ -363,9 +578,23 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
 
         // threshold: candidates must satisfy key <= T when thr_incl (carried over from a failed
         // level) or key < T otherwise (T = current k-th best of the list)
+        // Radius hint: the previous query's k-th distance (x 1.5 in d2) as a first inclusive threshold.  It is a GUESS,
+        // not a bound: if fewer than k points of the block pass it, the level is scanned again without it.  When k or
+        // more pass, the k nearest points of the block are among them, so everything downstream is unchanged.  A
+        // good guess rejects most candidates before insertion, so the list never fills and no intermediate
+        // selection runs.
         double Td = INF;
         int Ti = 0x7fffffff;
         bool thr_incl = true;
+        bool guessed = false;
+        // only from a neighbour (same or adjacent cell of the level that answered it): in a spatially ordered query list
+        // that is almost every query, in a random one almost none -- there the hint would be the radius of an unrelated
+        // region and a wrong guess costs a second scan
+        if (prev_k2 > 0.0 && abs((ix >> level_hint) - pcx) <= 1 && abs((iy >> level_hint) - pcy) <= 1 &&
+            abs((iz >> level_hint) - pcz) <= 1) {
+            Td = prev_k2 * 1.5;
+            guessed = true;
+        }
 
         const long long need = min((long long)3 * k, gpar.n);
         int l0 = level_hint;
@@ -382,7 +611,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                     cnt = a.tab[((size_t)m + 1) << sh] - a.tab[(size_t)m << sh];
                 }
             }
-            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
             if ((long long)cnt < need) break;
             l0 = lf;
         }
@@ -421,7 +650,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                 }
             }
             unsigned total = hi - lo;
-            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            total = __reduce_add_sync(0xffffffffu, total);
             const bool top = (l == gpar.bits);
             if (!top && (long long)total < need) continue;
 
@@ -452,19 +681,26 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                 const float cm2 = __shfl_sync(0xffffffffu, cmin2, c);
                 if (chi <= clo) continue;
                 if ((double)cm2 > Td) continue;
-                for (uint32_t j0 = clo; j0 < chi; j0 += 32) {
-                    const uint32_t j = j0 + lane;
-                    bool take = false;
-                    double d2 = 0.0;
-                    int pidx = 0;
-                    if (j < chi) {
-                        const float4 p = __ldg(a.sorted + j);
-                        const double dx = (double)p.x - qx, dy = (double)p.y - qy, dz = (double)p.z - qz;
-                        d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                        pidx = __float_as_int(p.w);
-                        take = thr_incl ? !key_less(Td, Ti, d2, pidx) : key_less(d2, pidx, Td, Ti);
-                    }
-                    const unsigned bal = __ballot_sync(0xffffffffu, take);
+                // Three loads in flight per lane (a rotating register queue in a ROLLED loop, so the body exists once):
+                // the stream comes from L2 (600+ cycles) and with one load per iteration the warp spent most of a
+                // query waiting on memory.
+                const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                uint32_t j = clo + lane;
+                float4 n0 = j < chi ? __ldg(a.sorted + j) : zero4;
+                float4 n1 = j + 32 < chi ? __ldg(a.sorted + j + 32) : zero4;
+                float4 n2 = j + 64 < chi ? __ldg(a.sorted + j + 64) : zero4;
+#pragma unroll 1
+                for (uint32_t j0 = clo; j0 < chi; j0 += 32, j += 32) {
+                    const float4 p = n0;
+                    n0 = n1;
+                    n1 = n2;
+                    n2 = j + 96 < chi ? __ldg(a.sorted + j + 96) : zero4;
+                    const bool valid = j < chi;
+                    const double dx = (double)p.x - qx, dy = (double)p.y - qy, dz = (double)p.z - qz;
+                    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                    const int pidx = __float_as_int(p.w);
+                    bool take = valid && (thr_incl ? !key_less(Td, Ti, d2, pidx) : key_less(d2, pidx, Td, Ti));
+                    unsigned bal = __ballot_sync(0xffffffffu, take);
                     if (bal == 0u) continue;
                     if (count + 32 > cap) {
                         // the list is full: tighten the bound by selection; only if that cannot make room (a pile of
@@ -486,14 +722,9 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                             __syncwarp();
                         }
                         // re-evaluate this batch against the tighter threshold
-                        take = (j < chi) && (thr_incl ? !key_less(Td, Ti, d2, pidx) : key_less(d2, pidx, Td, Ti));
-                        const unsigned bal2 = __ballot_sync(0xffffffffu, take);
-                        if (bal2 == 0u) continue;
-                        const int pos = count + __popc(bal2 & ((1u << lane) - 1u));
-                        if (take) { sd[pos] = d2; si[pos] = pidx; }
-                        count += __popc(bal2);
-                        __syncwarp();
-                        continue;
+                        take = valid && (thr_incl ? !key_less(Td, Ti, d2, pidx) : key_less(d2, pidx, Td, Ti));
+                        bal = __ballot_sync(0xffffffffu, take);
+                        if (bal == 0u) continue;
                     }
                     const int pos = count + __popc(bal & ((1u << lane) - 1u));
                     if (take) { sd[pos] = d2; si[pos] = pidx; }
@@ -516,11 +747,39 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
             // final sort of what we have.  With more than k entries, first cut the list to the k best exactly (selection
             // on the distance; if distances tie across the cut the tied entries all stay and the full-size sort decides by
             // index), so that the exact (d2, index) sort runs on half the network
-            int sort_n = cap;
+            if (guessed) {
+                guessed = false;
+                if (count < k) {   // the radius hint was too small here: same level again, without it
+                    Td = INF;
+                    Ti = 0x7fffffff;
+                    thr_incl = true;
+                    --l;
+                    continue;
+                }
+            }
             if (count > k) {
                 double T;
                 count = warp_select_compact<true>(sd, si, count, k, lane, T);
             }
+            if (E > 0 && count == k) {
+                __syncwarp();
+                const SortResult sr = sort_emit<(E > 0 ? E : 1)>(sd, si, k, lane, top, margin2, a.out_idx + qw * (long long)k,
+                                                                 a.out_dist ? a.out_dist + qw * (long long)k : nullptr,
+                                                                 a.out_rad ? a.out_rad + qw : nullptr);
+                if (sr.accepted) {
+                    prev_k2 = __longlong_as_double(sr.kd);
+                    level_hint = l;
+                    pcx = cx; pcy = cy; pcz = cz;
+                    __syncwarp();
+                    break;
+                }
+                Td = __longlong_as_double(sr.kd);
+                Ti = sr.kid;
+                thr_incl = true;
+                __syncwarp();
+                continue;
+            }
+            int sort_n = cap;
             if (count == k) sort_n = k2;
             for (int t = count + lane; t < sort_n; t += 32) { sd[t] = INF; si[t] = 0x7fffffff; }
             __syncwarp();
@@ -534,7 +793,9 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(KnnArgs a) {
                     if (a.out_dist) a.out_dist[qw * (long long)k + t] = sqrt(sd[t]);
                 }
                 if (a.out_rad && lane == 0) a.out_rad[qw] = sqrt(sd[k - 1]);
+                prev_k2 = sd[k - 1];
                 level_hint = l;
+                pcx = cx; pcy = cy; pcz = cz;
                 __syncwarp();
                 break;
             }
@@ -578,7 +839,15 @@ __global__ void __launch_bounds__(kKnnWarps * 32) ball_kernel(BallArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const GridParams gpar = *a.gp;
     const int G = 1 << gpar.bits;
-    for (long long qw = (long long)blockIdx.x * kKnnWarps + warp; qw < a.q_count; qw += (long long)gridDim.x * kKnnWarps) {
+    // Each warp takes a contiguous run of queries: consecutive queries of a spatially ordered list share their block of
+    // cells, so the level hint and the radius hint below come from a neighbour.
+    double prev_k2 = -1.0;   // k-th squared distance of the warp's previous query (< 0: none yet)
+    int pcx = 0, pcy = 0, pcz = 0;   // its cell at level_hint
+    const long long n_warps = (long long)gridDim.x * kKnnWarps;
+    const long long per_warp = (a.q_count + n_warps - 1) / n_warps;
+    const long long q_first = ((long long)blockIdx.x * kKnnWarps + warp) * per_warp;
+    const long long q_last = min(a.q_count, q_first + per_warp);
+    for (long long qw = q_first; qw < q_last; ++qw) {
         const long long qi = a.query ? (long long)a.query[qw] : a.q_begin + qw;
         const float qxf = a.pts[qi * 3], qyf = a.pts[qi * 3 + 1], qzf = a.pts[qi * 3 + 2];
         const double qx = qxf, qy = qyf, qz = qzf;
@@ -675,6 +944,7 @@ struct dfb_grid {
     uint32_t* tab = nullptr;           // device, 8^bits + 1 entries
     uint32_t* code = nullptr;          // device, per-point Morton code (build scratch)
     uint32_t* sums = nullptr;          // device, scan scratch
+    uint32_t* order_cnt = nullptr;     // device, per-block counts of dfb_grid_morton_order
     unsigned* bb = nullptr;            // device, ordered-int bounding box (6)
     dfb::GridParams* params = nullptr; // device
 };
@@ -730,6 +1000,7 @@ extern "C" int dfb_grid_create(const float* d_points, int64_t n, dfb_stream stre
         (e = cudaMalloc(&g->tab, (g->ncell + 1) * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&g->code, (size_t)n * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&g->sums, (size_t)g->ntile * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&g->order_cnt, (size_t)((n + kOrderBlock - 1) / kOrderBlock) * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&g->bb, 6 * sizeof(unsigned))) != cudaSuccess ||
         (e = cudaMalloc(&g->params, sizeof(GridParams))) != cudaSuccess) {
         dfb_grid_destroy(g);
@@ -764,10 +1035,27 @@ extern "C" int dfb_grid_destroy(dfb_grid* g) {
     cudaFree(g->tab);
     cudaFree(g->code);
     cudaFree(g->sums);
+    cudaFree(g->order_cnt);
     cudaFree(g->bb);
     cudaFree(g->params);
     delete g;
     return DFB_OK;
+}
+
+extern "C" int dfb_grid_morton_order(const dfb_grid* g, int64_t q_begin, int64_t q_end, int32_t* d_out, dfb_stream stream) {
+    using namespace dfb;
+    DFB_REQUIRE(g != nullptr, DFB_E_ARG, "dfb_grid_morton_order: grid is NULL");
+    DFB_REQUIRE(q_begin >= 0 && q_end >= q_begin && q_end <= g->n, DFB_E_ARG,
+                "dfb_grid_morton_order: range [%lld,%lld) outside the cloud", (long long)q_begin, (long long)q_end);
+    if (q_end == q_begin) return DFB_OK;
+    DFB_REQUIRE(d_out != nullptr, DFB_E_ARG, "dfb_grid_morton_order: d_out is NULL");
+    cudaStream_t st = as_stream(stream);
+    const long long nb = (g->n + kOrderBlock - 1) / kOrderBlock;
+    order_count_kernel<<<(unsigned)nb, kOrderBlock, 0, st>>>(g->sorted, g->n, (int)q_begin, (int)q_end, g->order_cnt);
+    scan_sums_serial<<<1, 1024, 0, st>>>(g->order_cnt, nb);
+    order_scatter_kernel<<<(unsigned)nb, kOrderBlock, 0, st>>>(g->sorted, g->n, (int)q_begin, (int)q_end, g->order_cnt, d_out);
+    note_launch(3);
+    return check_cuda(cudaGetLastError(), "dfb_grid_morton_order kernels", __FILE__, __LINE__);
 }
 
 extern "C" int dfb_knn(const dfb_grid* grid, const int32_t* d_query, int64_t q_begin, int64_t q_count, int32_t k,
@@ -788,11 +1076,29 @@ extern "C" int dfb_knn(const dfb_grid* grid, const int32_t* d_query, int64_t q_b
     a.k = k; a.kcap = kcap;
     a.out_idx = d_idx; a.out_dist = d_dist; a.out_rad = d_rad;
     const size_t smem = (size_t)kKnnWarps * kcap * (sizeof(double) + sizeof(int));
-    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&knn_kernel), 100 * 1024)) return rc;
-    long long blocks = (q_count + kKnnWarps - 1) / kKnnWarps;
-    const long long cap = (long long)sm_count() * 16;
-    if (blocks > cap) blocks = cap;
-    knn_kernel<<<(unsigned)blocks, kKnnWarps * 32, smem, as_stream(stream)>>>(a);
+    int k2 = 32;
+    while (k2 < k) k2 <<= 1;
+    // every warp works through a contiguous run of queries (at least 2): exactly one wave of resident CTAs, so that
+    // all of them finish together
+    long long blocks = (q_count + 2 * kKnnWarps - 1) / (2 * kKnnWarps);
+#define DFB_KNN_LAUNCH(E)                                                                                         \
+    do {                                                                                                          \
+        if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(&knn_kernel<E>), 100 * 1024)) return rc;       \
+        int per_sm = 0;                                                                                           \
+        DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, knn_kernel<E>, kKnnWarps * 32, smem));    \
+        const long long cap = (long long)sm_count() * (per_sm > 0 ? per_sm : 1);                                  \
+        if (blocks > cap) blocks = cap;                                                                           \
+        knn_kernel<E><<<(unsigned)blocks, kKnnWarps * 32, smem, as_stream(stream)>>>(a);                          \
+    } while (0)
+    switch (k2) {
+        case 32: DFB_KNN_LAUNCH(1); break;
+        case 64: DFB_KNN_LAUNCH(2); break;
+        case 128: DFB_KNN_LAUNCH(4); break;
+        case 256: DFB_KNN_LAUNCH(8); break;
+        case 512: DFB_KNN_LAUNCH(16); break;
+        default: DFB_KNN_LAUNCH(0); break;
+    }
+#undef DFB_KNN_LAUNCH
     note_launch();
     return check_cuda(cudaGetLastError(), "knn_kernel launch", __FILE__, __LINE__);
 }

@@ -64,6 +64,15 @@ class Grid:
         except Exception:  # noqa: BLE001 - interpreter shutdown
             pass
 
+    def morton_order(self, q_begin: int = 0, q_end: Optional[int] = None) -> torch.Tensor:
+        """The point indices ``q_begin .. q_end`` in the grid's spatial (Morton) order, int32 [q_end - q_begin]: a query
+        list in which consecutive queries share their neighbourhood cells."""
+        q_end = self.n if q_end is None else int(q_end)
+        out = torch.empty((max(q_end - q_begin, 0),), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().dfb_grid_morton_order(self._h, q_begin, q_end, _p(out), _stream(self.device)))
+        return out
+
     def query(self, k: int, q_begin: int = 0, q_count: Optional[int] = None, query: Optional[torch.Tensor] = None,
               return_dist: bool = False):
         """kNN of points ``q_begin .. q_begin+q_count`` (or of the int32 index tensor ``query``).

@@ -66,6 +66,11 @@ DFB_API int dfb_grid_create(const float* d_points, int64_t n, dfb_stream stream,
 /* Rebuild in place for a new cloud of the SAME size (no allocation, no host synchronisation). */
 DFB_API int dfb_grid_update(dfb_grid* grid, const float* d_points, dfb_stream stream);
 DFB_API int dfb_grid_destroy(dfb_grid* grid);
+/* The point indices i with q_begin <= i < q_end in the grid's spatial (Morton) order: d_out int32[q_end - q_begin].
+ * The reference visits queries in file order (tutorial/compute_normals.py:56, DataLoader without shuffle); queries are
+ * independent, so a caller may visit them in any order -- in this one consecutive queries share their neighbourhood
+ * cells, which is what dfb_knn's hints exploit (dfb_pipeline_run does so and scatters the results back to file order). */
+DFB_API int dfb_grid_morton_order(const dfb_grid* grid, int64_t q_begin, int64_t q_end, int32_t* d_out, dfb_stream stream);
 
 /* Exact k nearest neighbours of q_count query points.  Queries are points of the cloud:
  * d_query == NULL -> point indices q_begin .. q_begin+q_count-1, else d_query[0..q_count) (q_begin ignored).

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--order", type=int, default=3)
     ap.add_argument("--queries", type=int, default=1_000_000)
     ap.add_argument("--chunk", type=int, default=65536)
+    ap.add_argument("--morton", action="store_true", help="visit the queries in the grid's Morton order (explicit query lists)")
     args = ap.parse_args()
     from deepfit_b200 import ops, synthetic
     from deepfit_b200.tutorial_utils import normalize_cloud
@@ -48,6 +49,7 @@ def main():
     ops.wls_fit(patch, None, args.order, U=U, rad=rad)
     del idx, rad, dist, patch, U
     torch.cuda.synchronize()
+    order = grid.morton_order(0, q) if args.morton else None
     stage = {"knn": 0.0, "pca": 0.0, "wls": 0.0}
     worst_knn_chunk = 0.0
     ok = True
@@ -55,9 +57,10 @@ def main():
         c = min(args.chunk, q - s)
         a, b, d, f = ev(), ev(), ev(), ev()
         a.record()
-        idx, rad, dist = grid.query(args.k, q_begin=s, q_count=c, return_dist=True)
+        qlist = order[s:s + c] if args.morton else None
+        idx, rad, dist = grid.query(args.k, q_begin=s, q_count=c, query=qlist, return_dist=True)
         b.record()
-        patch, U = ops.patch_pca(pts, idx, rad, q_begin=s)
+        patch, U = ops.patch_pca(pts, idx, rad, q_begin=s, query=qlist)
         d.record()
         out = ops.wls_fit(patch, None, args.order, U=U, rad=rad)
         f.record()
@@ -72,7 +75,7 @@ def main():
             ok = ok and bool((srt[:, 1:] != srt[:, :-1]).all())
             ok = ok and bool(torch.isfinite(out["n_world"]).all())
     total = sum(stage.values())
-    print(json.dumps({"cloud": args.cloud, "points": args.points, "k": args.k, "order": args.order, "queries": q,
+    print(json.dumps({"cloud": args.cloud, "points": args.points, "k": args.k, "order": args.order, "queries": q, "morton": bool(args.morton),
                       "grid_build_ms": round(t_grid, 3), "stage_ms": {k_: round(v, 2) for k_, v in stage.items()},
                       "queries_per_s_classic": q / (total * 1e-3), "knn_queries_per_s": q / (stage["knn"] * 1e-3),
                       "worst_knn_chunk_ms": round(worst_knn_chunk, 2), "properties_ok": ok}))
