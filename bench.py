@@ -428,7 +428,7 @@ def main():
             _lib.load().dfb_dbg_set(int(kv.split(":")[0]), int(kv.split(":")[1]))
 
     cloud, n_total, K, ORDER, mode, scaling = resolve_workload(args, world)
-    chunk = args.chunk or (16384 if mode == "DeepFit" else 65536)
+    chunk = args.chunk or (16384 if mode == "DeepFit" else 262144)
     # the cloud: small workloads come from the host generators (numpy); the 10 M / 100 M ones are sampled on the device
     if cloud == "boxy" or n_total <= 4_000_000:
         pts_host = torch.from_numpy(make_cloud_host(cloud, n_total)).pin_memory()

@@ -51,6 +51,7 @@ class DfbPipelineOutputs(C.Structure):
 
 
 DFB_PIPE_KEEP_QSTN = 1
+DFB_PIPE_FILE_ORDER = 2
 ABI_VERSION = 2
 
 

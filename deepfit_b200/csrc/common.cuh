@@ -43,7 +43,8 @@ int ensure_dyn_smem(const void* func, int bytes);
 // Internal cross-file entry points (the C pipeline drives the stages through these and the public ABI).
 int wls_fit_impl(const float* d_patch, const float* d_weights, const float* d_trans, const float* d_U, const double* d_rad,
                  int64_t n, int32_t k, int32_t order, float* d_beta, float* d_n_local, float* d_n_world, float* d_curv,
-                 double* d_curv_scaled, float* d_dirs, float* d_dirs_world, int32_t* d_info, int keep_qstn, dfb_stream stream);
+                 double* d_curv_scaled, float* d_dirs, float* d_dirs_world, int32_t* d_info, int keep_qstn, dfb_stream stream,
+                 const int32_t* d_out_row = nullptr, int64_t out_base = 0);
 const float* grid_points(const dfb_grid* g);   // device copy of the cloud, original order, f32[n,3]
 long long grid_size(const dfb_grid* g);
 int model_k(const dfb_model* m);

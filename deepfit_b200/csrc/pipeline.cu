@@ -10,7 +10,35 @@
 // stream owned by the pipeline while stages 3-5 (network, jet fit) of chunk i run on the caller's stream; the
 // neighbourhood buffers are double-buffered and handed over with events, so the search fills the SMs the persistent
 // tensor-core kernels leave idle in their tails instead of serialising in front of them.
+//
+// Visiting order: queries are independent, so the range is walked in the grid's spatial (Morton) order
+// (dfb_grid_morton_order) -- consecutive queries then share their neighbourhood cells, which dfb_knn's level and radius
+// hints turn into 1.5x the search rate -- and every result is written to its FILE-order row (the jet-fit kernel scatters
+// its own outputs; the pass-through outputs go through a row-scatter kernel).  DFB_PIPE_FILE_ORDER restores the
+// reference's visiting order (tutorial/compute_normals.py:56, DataLoader without shuffle); results are bit-identical.
 #include "common.cuh"
+
+namespace {
+// dst[(out_row[i] - base) * row + j] = src[i * row + j]
+template <typename T>
+__global__ void scatter_rows_kernel(const T* __restrict__ src, long long rows, int row, const int* __restrict__ out_row, long long base,
+                                    T* __restrict__ dst) {
+    const long long n = rows * row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / row;
+        dst[((long long)out_row[r] - base) * row + (i - r * row)] = src[i];
+    }
+}
+template <typename T>
+int scatter_rows(const T* src, long long rows, int row, const int* out_row, long long base, T* dst, cudaStream_t st) {
+    const long long n = rows * row;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    scatter_rows_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(src, rows, row, out_row, base, dst);
+    dfb::note_launch();
+    return dfb::check_cuda(cudaGetLastError(), "scatter_rows_kernel launch", __FILE__, __LINE__);
+}
+}  // namespace
 
 struct dfb_pipeline {
     const dfb_grid* grid = nullptr;
@@ -25,6 +53,9 @@ struct dfb_pipeline {
     float* U[2] = {nullptr, nullptr};
     float* weights = nullptr;     // [chunk,k]   (network -> jet fit, caller's stream only)
     float* trans = nullptr;       // [chunk,9]
+    float* trans2 = nullptr;      // [chunk,4096] staging, only when trans2 is requested in Morton order
+    int32_t* qorder = nullptr;    // the query range in Morton order (capacity qorder_cap)
+    long long qorder_cap = 0;
     int device = 0;
 };
 
@@ -40,6 +71,8 @@ extern "C" int dfb_pipeline_destroy(dfb_pipeline* p) {
     }
     cudaFree(p->weights);
     cudaFree(p->trans);
+    cudaFree(p->trans2);
+    cudaFree(p->qorder);
     if (p->ev_start) cudaEventDestroy(p->ev_start);
     if (p->side) cudaStreamDestroy(p->side);
     delete p;
@@ -65,7 +98,7 @@ extern "C" int dfb_pipeline_create(const dfb_grid* grid, dfb_model* model, int32
     p->model = model;
     p->k = k;
     p->order = order;
-    p->chunk = chunk > 0 ? chunk : (model ? 16384 : 65536);
+    p->chunk = chunk > 0 ? chunk : (model ? 16384 : 262144);
     p->flags = flags;
     cudaError_t e = cudaGetDevice(&p->device);
     int lo = 0, hi = 0;
@@ -112,6 +145,20 @@ extern "C" int dfb_pipeline_run(dfb_pipeline* p, int64_t q_begin, int64_t q_end,
     const long long n_pts = grid_size(p->grid);
     const long long n_chunks = (q_end - q_begin + p->chunk - 1) / p->chunk;
 
+    // the visiting order (on the caller's stream, before the side stream is released)
+    const bool morton = !(p->flags & DFB_PIPE_FILE_ORDER);
+    if (morton) {
+        if (p->qorder_cap < q_end - q_begin) {
+            DFB_CUDA(cudaFree(p->qorder));   // synchronises: no earlier run can still be reading it
+            p->qorder = nullptr;
+            p->qorder_cap = 0;
+            DFB_CUDA(cudaMalloc(&p->qorder, (size_t)(q_end - q_begin) * sizeof(int32_t)));
+            p->qorder_cap = q_end - q_begin;
+        }
+        if (o->d_trans2 && !p->trans2) DFB_CUDA(cudaMalloc(&p->trans2, (size_t)p->chunk * 4096 * sizeof(float)));
+        int rc0 = dfb_grid_morton_order(p->grid, q_begin, q_end, p->qorder, stream);
+        if (rc0) return rc0;
+    }
     // the side stream starts after everything already queued on the caller's stream (e.g. a grid update)
     DFB_CUDA(cudaEventRecord(p->ev_start, main_st));
     DFB_CUDA(cudaStreamWaitEvent(p->side, p->ev_start, 0));
@@ -121,9 +168,10 @@ extern "C" int dfb_pipeline_run(dfb_pipeline* p, int64_t q_begin, int64_t q_end,
         const long long s = q_begin + ci * p->chunk;
         const long long c = (q_end - s < p->chunk) ? (q_end - s) : p->chunk;
         if (ci >= 2) DFB_CUDA(cudaStreamWaitEvent(p->side, p->ev_free[b], 0));   // chunk ci-2 has been consumed
-        int rc = dfb_knn(p->grid, nullptr, s, c, k, p->idx[b], nullptr, p->rad[b], p->side);
+        const int32_t* ql = morton ? p->qorder + (s - q_begin) : nullptr;
+        int rc = dfb_knn(p->grid, ql, s, c, k, p->idx[b], nullptr, p->rad[b], p->side);
         if (rc) return rc;
-        rc = dfb_patch_pca(pts, n_pts, p->idx[b], nullptr, s, c, k, p->rad[b], 1, p->patch[b], p->U[b], p->side);
+        rc = dfb_patch_pca(pts, n_pts, p->idx[b], ql, s, c, k, p->rad[b], 1, p->patch[b], p->U[b], p->side);
         if (rc) return rc;
         DFB_CUDA(cudaEventRecord(p->ev_ready[b], p->side));
         return 0;
@@ -143,19 +191,33 @@ extern "C" int dfb_pipeline_run(dfb_pipeline* p, int64_t q_begin, int64_t q_end,
         DFB_CUDA(cudaStreamWaitEvent(main_st, p->ev_ready[b], 0));
         float* w = nullptr;
         float* tr = nullptr;
+        const int32_t* rows = morton ? p->qorder + off : nullptr;   // file-order row of every patch of the chunk
         if (p->model) {
-            w = o->d_weights ? o->d_weights + off * k : p->weights;
-            tr = o->d_trans ? o->d_trans + off * 9 : p->trans;
-            rc = dfb_model_forward(p->model, p->patch[b], c, w, tr, o->d_trans2 ? o->d_trans2 + off * 4096 : nullptr, nullptr, main_st);
+            // in Morton order the network writes chunk-local staging rows, scattered below when they are outputs
+            w = (o->d_weights && !morton) ? o->d_weights + off * k : p->weights;
+            tr = (o->d_trans && !morton) ? o->d_trans + off * 9 : p->trans;
+            float* t2 = o->d_trans2 ? (morton ? p->trans2 : o->d_trans2 + off * 4096) : nullptr;
+            rc = dfb_model_forward(p->model, p->patch[b], c, w, tr, t2, nullptr, main_st);
             if (rc) return rc;
+            if (morton) {
+                if (o->d_weights && (rc = scatter_rows(w, c, k, rows, q_begin, o->d_weights, main_st))) return rc;
+                if (o->d_trans && (rc = scatter_rows(tr, c, 9, rows, q_begin, o->d_trans, main_st))) return rc;
+                if (o->d_trans2 && (rc = scatter_rows(t2, c, 4096, rows, q_begin, o->d_trans2, main_st))) return rc;
+            }
         }
-        rc = wls_fit_impl(p->patch[b], w, tr, p->U[b], p->rad[b], c, k, p->order, o->d_beta ? o->d_beta + off * M : nullptr, nullptr,
-                          o->d_normals + off * 3, nullptr, (p->order > 1 && o->d_curv) ? o->d_curv + off * 2 : nullptr, nullptr,
-                          o->d_dirs_world ? o->d_dirs_world + off * 6 : nullptr, o->d_info ? o->d_info + off : nullptr,
-                          (p->flags & DFB_PIPE_KEEP_QSTN) ? 1 : 0, main_st);
+        const long long oo = morton ? 0 : off;   // with a row list the jet fit takes the base pointers
+        rc = wls_fit_impl(p->patch[b], w, tr, p->U[b], p->rad[b], c, k, p->order, o->d_beta ? o->d_beta + oo * M : nullptr, nullptr,
+                          o->d_normals + oo * 3, nullptr, (p->order > 1 && o->d_curv) ? o->d_curv + oo * 2 : nullptr, nullptr,
+                          o->d_dirs_world ? o->d_dirs_world + oo * 6 : nullptr, o->d_info ? o->d_info + oo : nullptr,
+                          (p->flags & DFB_PIPE_KEEP_QSTN) ? 1 : 0, main_st, rows, q_begin);
         if (rc) return rc;
-        if (o->d_rad) DFB_CUDA(cudaMemcpyAsync(o->d_rad + off, p->rad[b], (size_t)c * sizeof(double), cudaMemcpyDeviceToDevice, main_st));
-        if (o->d_U) DFB_CUDA(cudaMemcpyAsync(o->d_U + off * 9, p->U[b], (size_t)c * 9 * sizeof(float), cudaMemcpyDeviceToDevice, main_st));
+        if (morton) {
+            if (o->d_rad && (rc = scatter_rows(p->rad[b], c, 1, rows, q_begin, o->d_rad, main_st))) return rc;
+            if (o->d_U && (rc = scatter_rows(p->U[b], c, 9, rows, q_begin, o->d_U, main_st))) return rc;
+        } else {
+            if (o->d_rad) DFB_CUDA(cudaMemcpyAsync(o->d_rad + off, p->rad[b], (size_t)c * sizeof(double), cudaMemcpyDeviceToDevice, main_st));
+            if (o->d_U) DFB_CUDA(cudaMemcpyAsync(o->d_U + off * 9, p->U[b], (size_t)c * 9 * sizeof(float), cudaMemcpyDeviceToDevice, main_st));
+        }
         DFB_CUDA(cudaEventRecord(p->ev_free[b], main_st));
     }
     return DFB_OK;

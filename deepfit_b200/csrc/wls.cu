@@ -9,13 +9,14 @@
 // upper-triangle entries of A^T W A, each point contributes to the (2n+1)(2n+2)/2 distinct moments
 // sum w x^a y^b (a+b <= 2n) and the (n+1)(n+2)/2 moments sum w z x^a y^b (a+b <= n).
 //   phase 1: 8 lanes per patch (4 patches per warp, 128-bit coalesced loads of the planar
-//            x/y/z/w rows), register accumulators, 3 xor-shuffle steps, totals parked in shared
-//            memory; 8 rounds fill 32 patch slots per warp.
-//   phase 2: one lane per patch: CGAL-style preconditioning applied to the moments, XtX/XtY
-//            assembled in the reference's column order, unblocked fp32 Cholesky + two triangular
-//            solves in registers, two steps of iterative refinement against the fp64 residual,
-//            D_inv, normal, closed-form curvature on the upper triangle of -I^{-1} II (what
-//            torch.symeig(upper=True) sees), back-rotation by trans^T and U^T.
+//            x/y/z/w rows, the next chunk prefetched), register accumulators, 3 xor-shuffle steps,
+//            totals parked in shared memory.  The moments are SPLIT BETWEEN THE TWO WARPS of a
+//            CTA by the parity of the x power: all 38 (order 3) fp64 accumulators in one thread
+//            cost 233 registers, i.e. 8 warps per SM and an FP64 pipe 34 % busy behind exposed
+//            load latency; half of them (plus the powers that half needs, +9 % fp64 work) fit
+//            ~100 registers.  Both warps read the same rows (the second read hits L1 / L2).
+//   phase 2: one lane per patch (each warp solves half of the CTA's batch): CGAL-style
+//            preconditioning applied to the moments, XtX/XtY
 // Numerics: a moment matrix, unlike the Gram matrix A^T W A the reference forms, is not backward
 // stable in fp32 -- entry-wise rounding acts on the solution with cond(XtX) (up to 4e5 at order 4 on
 // the lidar tutorial cloud) instead of cond(A).  The moments are therefore accumulated in fp64
@@ -28,7 +29,6 @@ namespace dfb {
 namespace {
 
 constexpr int kWarpsPerBlock = 2;
-constexpr int kSlotStride = 65;  // doubles per patch slot (62 used at order 4), odd => conflict-free
 
 template <int ORDER>
 struct Jet {
@@ -39,6 +39,9 @@ struct Jet {
     __host__ __device__ static constexpr int mi(int a, int b) { return a * (D + 1) - a * (a - 1) / 2 + b; }
     __host__ __device__ static constexpr int zi(int a, int b) { return a * (ORDER + 1) - a * (a - 1) / 2 + b; }
 };
+// doubles per patch slot: the moments + sum|x|, sum|y|, rounded up to an odd count (conflict-free for one lane per slot)
+template <int ORDER>
+constexpr int slot_stride() { return (Jet<ORDER>::NM + Jet<ORDER>::NZ + 2) | 1; }
 
 // Column monomials (power of x, power of y) in the reference's column order, DeepFit.py:51-76.
 template <int ORDER>
@@ -54,38 +57,53 @@ __device__ __forceinline__ constexpr int coly(int i) {
     return t[ORDER - 1][i];
 }
 
+// Which warp of the CTA accumulates what (PAR = warp index): the moments sum w x^a y^b go by the parity of a; of the
+// sum w z x^a y^b the odd warp also takes a = 0, which evens out the two halves (order 3: 31 vs 28 fp64 operations per
+// point where an unsplit thread does 54).
+template <int PAR>
+__host__ __device__ constexpr bool owns_m(int a) { return (a & 1) == PAR; }
+template <int PAR>
+__host__ __device__ constexpr bool owns_z(int a) { return PAR == 1 ? ((a & 1) == 1 || a == 0) : ((a & 1) == 0 && a >= 2); }
+
 template <int ORDER>
 struct Acc {
-    double m[Jet<ORDER>::NM];
+    double m[Jet<ORDER>::NM];   // only the entries this warp owns are ever touched (the others cost no register)
     double zm[Jet<ORDER>::NZ];
-    float sax, say;  // sum |x|, sum |y|
+    float sax, say;  // sum |x|, sum |y|   (odd warp)
     float nvalid;    // number of weights > 1e-3
 };
 
-template <int ORDER>
+template <int ORDER, int PAR>
 __device__ __forceinline__ void acc_point(Acc<ORDER>& A, float x, float y, float z, float w, float wraw) {
     using J = Jet<ORDER>;
     double xp[J::D + 1], yp[J::D + 1];
     const double xd = x, yd = y, zd = z;
+    const double x2 = xd * xd;
     xp[0] = w;
+    xp[1] = xp[0] * xd;
+#pragma unroll
+    for (int a = 2; a <= J::D; ++a) xp[a] = xp[a - 2] * x2;   // each parity chain on its own; unused powers are dead code
     yp[0] = 1.0;
+    yp[1] = yd;
 #pragma unroll
-    for (int a = 1; a <= J::D; ++a) {
-        xp[a] = xp[a - 1] * xd;
-        yp[a] = yp[a - 1] * yd;
+    for (int b = 2; b <= J::D; ++b) yp[b] = yp[b - 1] * yd;
+#pragma unroll
+    for (int a = 0; a <= J::D; ++a) {
+        if (!owns_m<PAR>(a)) continue;
+#pragma unroll
+        for (int b = 0; b <= J::D - a; ++b) A.m[J::mi(a, b)] = b == 0 ? A.m[J::mi(a, b)] + xp[a] : fma(xp[a], yp[b], A.m[J::mi(a, b)]);
     }
-#pragma unroll
-    for (int a = 0; a <= J::D; ++a)
-#pragma unroll
-        for (int b = 0; b <= J::D - a; ++b) A.m[J::mi(a, b)] = fma(xp[a], yp[b], A.m[J::mi(a, b)]);
 #pragma unroll
     for (int a = 0; a <= ORDER; ++a) {
+        if (!owns_z<PAR>(a)) continue;
         const double xz = xp[a] * zd;
 #pragma unroll
-        for (int b = 0; b <= ORDER - a; ++b) A.zm[J::zi(a, b)] = fma(xz, yp[b], A.zm[J::zi(a, b)]);
+        for (int b = 0; b <= ORDER - a; ++b) A.zm[J::zi(a, b)] = b == 0 ? A.zm[J::zi(a, b)] + xz : fma(xz, yp[b], A.zm[J::zi(a, b)]);
     }
-    A.sax += fabsf(x);
-    A.say += fabsf(y);
+    if (PAR == 1) {
+        A.sax += fabsf(x);
+        A.say += fabsf(y);
+    }
     A.nvalid += (wraw > 1e-3f) ? 1.f : 0.f;
 }
 
@@ -98,7 +116,7 @@ __device__ __forceinline__ void rotate(const float* R, float& x, float& y, float
 }
 
 // Accumulate one patch with the 8 lanes of a group.  sub = lane & 7.
-template <int ORDER>
+template <int ORDER, int PAR>
 __device__ __forceinline__ void acc_patch(Acc<ORDER>& A, const float* __restrict__ px, const float* __restrict__ pw,
                                           const float* R, int k, int sub, bool use_w) {
 #pragma unroll
@@ -113,24 +131,36 @@ __device__ __forceinline__ void acc_patch(Acc<ORDER>& A, const float* __restrict
         const float4* y4 = reinterpret_cast<const float4*>(py);
         const float4* z4 = reinterpret_cast<const float4*>(pz);
         const float4* w4 = reinterpret_cast<const float4*>(pw);
-        for (int c = sub; c < (k >> 2); c += 8) {
-            float4 X = __ldg(x4 + c), Y = __ldg(y4 + c), Z = __ldg(z4 + c);
-            float4 W = pw ? __ldg(w4 + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        const int nc = k >> 2;
+        // the next chunk's loads are in flight while this one is accumulated
+        float4 Xn = one4, Yn = one4, Zn = one4, Wn = one4;
+        if (sub < nc) {
+            Xn = __ldg(x4 + sub); Yn = __ldg(y4 + sub); Zn = __ldg(z4 + sub);
+            if (pw) Wn = __ldg(w4 + sub);
+        }
+        for (int c = sub; c < nc; c += 8) {
+            float4 X = Xn, Y = Yn, Z = Zn;
+            const float4 W = Wn;
+            if (c + 8 < nc) {
+                Xn = __ldg(x4 + c + 8); Yn = __ldg(y4 + c + 8); Zn = __ldg(z4 + c + 8);
+                if (pw) Wn = __ldg(w4 + c + 8);
+            }
             if (R) {
                 rotate(R, X.x, Y.x, Z.x); rotate(R, X.y, Y.y, Z.y);
                 rotate(R, X.z, Y.z, Z.z); rotate(R, X.w, Y.w, Z.w);
             }
-            acc_point<ORDER>(A, X.x, Y.x, Z.x, use_w ? W.x : 1.f, W.x);
-            acc_point<ORDER>(A, X.y, Y.y, Z.y, use_w ? W.y : 1.f, W.y);
-            acc_point<ORDER>(A, X.z, Y.z, Z.z, use_w ? W.z : 1.f, W.z);
-            acc_point<ORDER>(A, X.w, Y.w, Z.w, use_w ? W.w : 1.f, W.w);
+            acc_point<ORDER, PAR>(A, X.x, Y.x, Z.x, use_w ? W.x : 1.f, W.x);
+            acc_point<ORDER, PAR>(A, X.y, Y.y, Z.y, use_w ? W.y : 1.f, W.y);
+            acc_point<ORDER, PAR>(A, X.z, Y.z, Z.z, use_w ? W.z : 1.f, W.z);
+            acc_point<ORDER, PAR>(A, X.w, Y.w, Z.w, use_w ? W.w : 1.f, W.w);
         }
     } else {
         for (int j = sub; j < k; j += 8) {
             float x = __ldg(px + j), y = __ldg(py + j), z = __ldg(pz + j);
             const float w = pw ? __ldg(pw + j) : 1.f;
             if (R) rotate(R, x, y, z);
-            acc_point<ORDER>(A, x, y, z, use_w ? w : 1.f, w);
+            acc_point<ORDER, PAR>(A, x, y, z, use_w ? w : 1.f, w);
         }
     }
 }
@@ -148,25 +178,38 @@ __device__ __forceinline__ double group8_sum(double v) {
     return v;
 }
 
-template <int ORDER>
+// the group's totals of the moments this warp owns -> the patch's slot (lane j of the group stores every 8th of them)
+template <int ORDER, int PAR>
 __device__ __forceinline__ void reduce_store(Acc<ORDER>& A, double* slot, int sub) {
     using J = Jet<ORDER>;
+    int n = 0;   // running count of owned entries (compile-time after unrolling)
 #pragma unroll
-    for (int i = 0; i < J::NM; ++i) {
-        const double t = group8_sum(A.m[i]);
-        if ((i & 7) == sub) slot[i] = t;
+    for (int a = 0; a <= J::D; ++a) {
+        if (!owns_m<PAR>(a)) continue;
+#pragma unroll
+        for (int b = 0; b <= J::D - a; ++b) {
+            const double t = group8_sum(A.m[J::mi(a, b)]);
+            if ((n & 7) == sub) slot[J::mi(a, b)] = t;
+            ++n;
+        }
     }
 #pragma unroll
-    for (int i = 0; i < J::NZ; ++i) {
-        const double t = group8_sum(A.zm[i]);
-        if ((i & 7) == sub) slot[J::NM + i] = t;
+    for (int a = 0; a <= ORDER; ++a) {
+        if (!owns_z<PAR>(a)) continue;
+#pragma unroll
+        for (int b = 0; b <= ORDER - a; ++b) {
+            const double t = group8_sum(A.zm[J::zi(a, b)]);
+            if ((n & 7) == sub) slot[J::NM + J::zi(a, b)] = t;
+            ++n;
+        }
     }
-    A.sax = group8_sum(A.sax);
-    A.say = group8_sum(A.say);
-    A.nvalid = group8_sum(A.nvalid);
-    if (sub == 0) {
-        slot[J::NM + J::NZ] = A.sax;
-        slot[J::NM + J::NZ + 1] = A.say;
+    if (PAR == 1) {
+        A.sax = group8_sum(A.sax);
+        A.say = group8_sum(A.say);
+        if (sub == 0) {
+            slot[J::NM + J::NZ] = A.sax;
+            slot[J::NM + J::NZ + 1] = A.say;
+        }
     }
 }
 
@@ -283,25 +326,29 @@ struct WlsArgs {
     int keep_qstn;      // 1: do NOT undo the QSTN rotation on n_world / dirs_world (tutorial/compute_normals.py:67)
     float* dirs;        // [n,2,3] local frame (compute_principal_curvatures' second return value)
     float* dirs_world;  // [n,2,3] rows rotated back by trans^T and U^T (test_c_est.py:162-168)
+    const int* out_row; // optional: patch i writes its outputs to row out_row[i] - out_base (queries visited in another order)
+    long long out_base;
 };
 
-// PPW = patches per warp iteration: 32 (every lane solves one system in phase 2) when there is enough work to fill the
-// GPU that way, 8 for smaller batches -- the fp64 accumulators cost ~230 registers per thread, so only ~8 warps fit an SM
-// and a 16 K-patch chunk would otherwise leave most of them without work.
-template <int ORDER, int PPW>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) wls_kernel(WlsArgs p) {
+// PPC = patches per CTA iteration (phase 1: both warps walk all of them, each for its half of the moments; phase 2: each
+// warp solves PPC / 2 systems, one per lane): 64 when there is enough work to fill the GPU that way, 16 for small batches.
+#ifndef DFB_WLS_MINB
+#define DFB_WLS_MINB 8   // 128 registers: phase 1 needs exactly that at order 3; the per-lane solve of phase 2 spills a little
+#endif
+template <int ORDER, int PPC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, DFB_WLS_MINB) wls_kernel(WlsArgs p) {
     using J = Jet<ORDER>;
     constexpr int M = J::M;
-    __shared__ double s_mom[kWarpsPerBlock][32][kSlotStride];
+    constexpr int SS = slot_stride<ORDER>();
+    __shared__ double s_mom[PPC][SS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane >> 3, sub = lane & 7;
-    const long long n_super = (p.n + PPW - 1) / PPW;  // groups of PPW patches, one per warp iteration
+    const long long n_super = (p.n + PPC - 1) / PPC;  // groups of PPC patches, one per CTA iteration
 
-    for (long long sp = (long long)blockIdx.x * kWarpsPerBlock + warp; sp < n_super;
-         sp += (long long)gridDim.x * kWarpsPerBlock) {
-        const long long base = sp * PPW;
+    for (long long sp = blockIdx.x; sp < n_super; sp += gridDim.x) {
+        const long long base = sp * PPC;
         // ---------------- phase 1 ----------------
-        for (int round = 0; round < PPW / 4; ++round) {
+        for (int round = 0; round < PPC / 4; ++round) {
             long long pi = base + round * 4 + grp;
             const bool live = pi < p.n;
             if (!live) pi = p.n - 1;
@@ -314,18 +361,28 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) wls_kernel(WlsArgs p) {
                 for (int i = 0; i < 9; ++i) R[i] = __ldg(p.trans + pi * 9 + i);
             }
             Acc<ORDER> A;
-            acc_patch<ORDER>(A, px, pw, has_R ? R : nullptr, p.k, sub, true);
-            // zero-weight guard, DeepFit.py:37-39: weights -> 1 unless more than 18 exceed 1e-3
-            bool redo = false;
-            if (pw) redo = group8_sum(A.nvalid) <= 18.f;
-            if (__any_sync(0xffffffffu, redo)) acc_patch<ORDER>(A, px, pw, has_R ? R : nullptr, p.k, sub, !redo);
-            reduce_store<ORDER>(A, s_mom[warp][round * 4 + grp], sub);
+            // zero-weight guard, DeepFit.py:37-39: weights -> 1 unless more than 18 exceed 1e-3 (both warps count)
+            if (warp == 0) {
+                acc_patch<ORDER, 0>(A, px, pw, has_R ? R : nullptr, p.k, sub, true);
+                bool redo = false;
+                if (pw) redo = group8_sum(A.nvalid) <= 18.f;
+                if (__any_sync(0xffffffffu, redo)) acc_patch<ORDER, 0>(A, px, pw, has_R ? R : nullptr, p.k, sub, !redo);
+                reduce_store<ORDER, 0>(A, s_mom[round * 4 + grp], sub);
+            } else {
+                acc_patch<ORDER, 1>(A, px, pw, has_R ? R : nullptr, p.k, sub, true);
+                bool redo = false;
+                if (pw) redo = group8_sum(A.nvalid) <= 18.f;
+                if (__any_sync(0xffffffffu, redo)) acc_patch<ORDER, 1>(A, px, pw, has_R ? R : nullptr, p.k, sub, !redo);
+                reduce_store<ORDER, 1>(A, s_mom[round * 4 + grp], sub);
+            }
         }
-        __syncwarp();
+        __syncthreads();
         // ---------------- phase 2 ----------------
-        const long long pi = base + lane;
-        if (lane < PPW && pi < p.n) {
-            const double* slot = s_mom[warp][lane];
+        const int sl = warp * (PPC / 2) + lane;   // this lane's slot of the batch
+        const long long pi = base + sl;
+        if (lane < PPC / 2 && pi < p.n) {
+            const double* slot = s_mom[sl];
+            const long long po = p.out_row ? (long long)p.out_row[pi] - p.out_base : pi;   // output row
             float h = 1.f;
             if (ORDER > 1) {
                 // DeepFit.py:43-46 (fp32, like the reference)
@@ -394,46 +451,46 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) wls_kernel(WlsArgs p) {
 
             if (p.beta) {
 #pragma unroll
-                for (int i = 0; i < M; ++i) p.beta[pi * M + i] = beta[i];
+                for (int i = 0; i < M; ++i) p.beta[po * M + i] = beta[i];
             }
             // normal, DeepFit.py:88
             const float inv_n = 1.f / fmaxf(sqrtf(fmaf(beta[0], beta[0], fmaf(beta[1], beta[1], 1.f))), 1e-12f);
             const float nx = -beta[0] * inv_n, ny = -beta[1] * inv_n, nz = inv_n;
             if (p.n_local) {
-                p.n_local[pi * 3 + 0] = nx; p.n_local[pi * 3 + 1] = ny; p.n_local[pi * 3 + 2] = nz;
+                p.n_local[po * 3 + 0] = nx; p.n_local[po * 3 + 1] = ny; p.n_local[po * 3 + 2] = nz;
             }
             if (p.n_world) {
                 float vx = nx, vy = ny, vz = nz;
                 // n * trans^T (test_n_est.py:154-157), then n * U^T (compute_normals.py:67)
                 rotate_back((p.trans && !p.keep_qstn) ? p.trans + pi * 9 : nullptr, p.U ? p.U + pi * 9 : nullptr, vx, vy, vz);
-                p.n_world[pi * 3 + 0] = vx; p.n_world[pi * 3 + 1] = vy; p.n_world[pi * 3 + 2] = vz;
+                p.n_world[po * 3 + 0] = vx; p.n_world[po * 3 + 1] = vy; p.n_world[po * 3 + 2] = vz;
             }
             if (ORDER > 1 && (p.curv || p.curv_scaled || p.dirs || p.dirs_world)) {
                 float k1, k2, dirs[6];
                 const bool want_dirs = p.dirs || p.dirs_world;
                 curvature_from_beta(beta[0], beta[1], beta[2], beta[3], beta[4], k1, k2, want_dirs ? dirs : nullptr);
-                if (p.curv) { p.curv[pi * 2] = k1; p.curv[pi * 2 + 1] = k2; }
+                if (p.curv) { p.curv[po * 2] = k1; p.curv[po * 2 + 1] = k2; }
                 if (p.curv_scaled) {
                     const double r = p.rad ? p.rad[pi] : 1.0;  // fp32 / fp64 -> fp64, compute_normals.py:79
-                    p.curv_scaled[pi * 2] = (double)k1 / r;
-                    p.curv_scaled[pi * 2 + 1] = (double)k2 / r;
+                    p.curv_scaled[po * 2] = (double)k1 / r;
+                    p.curv_scaled[po * 2 + 1] = (double)k2 / r;
                 }
                 if (p.dirs) {
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) p.dirs[pi * 6 + i] = dirs[i];
+                    for (int i = 0; i < 6; ++i) p.dirs[po * 6 + i] = dirs[i];
                 }
                 if (p.dirs_world) {
 #pragma unroll
                     for (int rrow = 0; rrow < 2; ++rrow) {
                         float vx = dirs[rrow * 3], vy = dirs[rrow * 3 + 1], vz = 0.f;
                         rotate_back((p.trans && !p.keep_qstn) ? p.trans + pi * 9 : nullptr, p.U ? p.U + pi * 9 : nullptr, vx, vy, vz);
-                        p.dirs_world[pi * 6 + rrow * 3] = vx; p.dirs_world[pi * 6 + rrow * 3 + 1] = vy; p.dirs_world[pi * 6 + rrow * 3 + 2] = vz;
+                        p.dirs_world[po * 6 + rrow * 3] = vx; p.dirs_world[po * 6 + rrow * 3 + 1] = vy; p.dirs_world[po * 6 + rrow * 3 + 2] = vz;
                     }
                 }
             }
-            if (p.info) p.info[pi] = info;
+            if (p.info) p.info[po] = info;
         }
-        __syncwarp();
+        __syncthreads();   // the slots are rewritten by the next iteration
     }
 }
 
@@ -512,16 +569,16 @@ __global__ void __launch_bounds__(256) neighbor_normals_kernel(const float* __re
 
 template <int ORDER>
 int launch_wls(const WlsArgs& a, cudaStream_t st) {
-    const long long cap = (long long)sm_count() * 16;
-    // fewer 32-patch groups than half a wave of warps; not for order 4, whose per-lane solve (M = 15) dominates and would
-    // run with a quarter of the lanes
-    const bool small = ORDER <= 3 && (a.n + 31) / 32 < (long long)sm_count() * 4;
-    const int ppw = small ? 8 : 32;
-    const long long n_super = (a.n + ppw - 1) / ppw;
-    long long blocks = (n_super + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    // 64 patches per CTA iteration when that still gives every SM several CTAs' worth of iterations; 16 otherwise (a
+    // 16 K-patch chunk of the DeepFit path): phase 2 then runs on a quarter of the lanes, but the GPU is filled
+    const bool small = (a.n + 63) / 64 < (long long)sm_count() * 16;
+    const int ppc = small ? 16 : 64;
+    const long long n_super = (a.n + ppc - 1) / ppc;
+    long long blocks = n_super;
+    const long long cap = (long long)sm_count() * 32;
     if (blocks > cap) blocks = cap;
-    if (small) wls_kernel<ORDER, 8><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(a);
-    else wls_kernel<ORDER, 32><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+    if (small) wls_kernel<ORDER, 16><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+    else wls_kernel<ORDER, 64><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(a);
     note_launch();
     return check_cuda(cudaGetLastError(), "wls_kernel launch", __FILE__, __LINE__);
 }
@@ -532,7 +589,8 @@ int launch_wls(const WlsArgs& a, cudaStream_t st) {
 namespace dfb {
 int wls_fit_impl(const float* d_patch, const float* d_weights, const float* d_trans, const float* d_U, const double* d_rad,
                  int64_t n, int32_t k, int32_t order, float* d_beta, float* d_n_local, float* d_n_world, float* d_curv,
-                 double* d_curv_scaled, float* d_dirs, float* d_dirs_world, int32_t* d_info, int keep_qstn, dfb_stream stream) {
+                 double* d_curv_scaled, float* d_dirs, float* d_dirs_world, int32_t* d_info, int keep_qstn, dfb_stream stream,
+                 const int32_t* d_out_row, int64_t out_base) {
     DFB_REQUIRE(order >= 1 && order <= 4, DFB_E_ARG, "Polynomial order unsupported, please use 1..4 (got %d)", order);
     DFB_REQUIRE(n >= 0 && k >= 1, DFB_E_ARG, "dfb_wls_fit: bad sizes n=%lld k=%d", (long long)n, k);
     DFB_REQUIRE(d_patch != nullptr || n == 0, DFB_E_ARG, "dfb_wls_fit: d_patch is NULL");
@@ -542,7 +600,8 @@ int wls_fit_impl(const float* d_patch, const float* d_weights, const float* d_tr
     int rc = dfb_device_check();
     if (rc) return rc;
     WlsArgs a{d_patch, d_weights, d_trans, d_U, d_rad, (long long)n, k,
-              d_beta,  d_n_local, d_n_world, d_curv, d_curv_scaled, d_info, keep_qstn, d_dirs, d_dirs_world};
+              d_beta,  d_n_local, d_n_world, d_curv, d_curv_scaled, d_info, keep_qstn, d_dirs, d_dirs_world,
+              d_out_row, (long long)out_base};
     switch (order) {
         case 1: return launch_wls<1>(a, as_stream(stream));
         case 2: return launch_wls<2>(a, as_stream(stream));
@@ -557,7 +616,7 @@ extern "C" int dfb_wls_fit(const float* d_patch, const float* d_weights, const f
                            float* d_n_local, float* d_n_world, float* d_curv, double* d_curv_scaled,
                            float* d_dirs, float* d_dirs_world, int32_t* d_info, dfb_stream stream) {
     return dfb::wls_fit_impl(d_patch, d_weights, d_trans, d_U, d_rad, n, k, order, d_beta, d_n_local, d_n_world, d_curv,
-                             d_curv_scaled, d_dirs, d_dirs_world, d_info, 0, stream);
+                             d_curv_scaled, d_dirs, d_dirs_world, d_info, 0, stream, nullptr, 0);
 }
 
 extern "C" int dfb_principal_curvatures(const float* d_beta, int64_t n, int32_t m, float* d_curv, float* d_dirs,

@@ -240,7 +240,10 @@ class Pipeline:
                "U": (torch.float32, lambda k, m: (3, 3)), "rad": (torch.float64, lambda k, m: ()),
                "dirs_world": (torch.float32, lambda k, m: (2, 3)), "info": (torch.int32, lambda k, m: ())}
 
-    def __init__(self, grid: Grid, net: Optional["WeightNetwork"], k: int, order: int, chunk: int = 0, keep_qstn: bool = False):
+    def __init__(self, grid: Grid, net: Optional["WeightNetwork"], k: int, order: int, chunk: int = 0, keep_qstn: bool = False,
+                 file_order: bool = False):
+        """``file_order``: visit the queries in file order like the reference instead of the grid's Morton order (same
+        results; the neighbour search is slower)."""
         if order not in JET_M:
             raise ValueError("Polynomial order unsupported, please use 1 or 2 ")
         self.grid, self.net = grid, net        # keep both alive: the handle borrows them
@@ -249,7 +252,8 @@ class Pipeline:
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().dfb_pipeline_create(grid._h, net._h if net is not None else None, self.k, self.order, int(chunk),
-                                                       _lib.DFB_PIPE_KEEP_QSTN if keep_qstn else 0, C.byref(self._h)))
+                                                       (_lib.DFB_PIPE_KEEP_QSTN if keep_qstn else 0) |
+                                                       (_lib.DFB_PIPE_FILE_ORDER if file_order else 0), C.byref(self._h)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

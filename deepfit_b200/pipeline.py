@@ -31,7 +31,7 @@ class NormalEstimator:
 
     def __init__(self, points: torch.Tensor, k: int, jet_order: int = 3, mode: str = "classic",
                  model: Optional[DeepFit] = None, chunk: int = 0, cancel_qstn: bool = True,
-                 grid: Optional[ops.Grid] = None):
+                 grid: Optional[ops.Grid] = None, file_order: bool = False):
         if mode not in ("classic", "DeepFit"):
             raise ValueError("mode must be 'classic' or 'DeepFit'")
         if mode == "DeepFit" and model is None:
@@ -43,10 +43,11 @@ class NormalEstimator:
         self.mode = mode
         self.model = model
         self.cancel_qstn = cancel_qstn
+        self.file_order = file_order    # visit queries in file order (the reference's) instead of Morton order; same results
         if grid is not None and grid.n != self.n:
             raise ValueError("grid was built over %d points, the cloud has %d" % (grid.n, self.n))
         self.grid = grid if grid is not None else ops.Grid(self.points)
-        self.chunk = int(chunk) if chunk else (16384 if mode == "DeepFit" else 65536)
+        self.chunk = int(chunk) if chunk else (16384 if mode == "DeepFit" else 262144)
 
     @property
     def net(self):
@@ -67,7 +68,8 @@ class NormalEstimator:
         if getattr(self, "_pipe", None) is None or self._pipe_key != key:
             if getattr(self, "_pipe", None) is not None:
                 self._pipe.close()
-            self._pipe = ops.Pipeline(self.grid, net, self.k, self.order, self.chunk, keep_qstn=not self.cancel_qstn)
+            self._pipe = ops.Pipeline(self.grid, net, self.k, self.order, self.chunk, keep_qstn=not self.cancel_qstn,
+                                      file_order=self.file_order)
             self._pipe_key = key
         return self._pipe
 

@@ -255,7 +255,7 @@ DFB_API int dfb_neighbor_normals(const float* d_patch, const float* d_trans, con
  * model forward, undoing the rotations :67 / test_n_est.py:154-161, curv / rad :79, torch.cat) and, with the
  * optional outputs, the per-batch body of test_c_est.py:125-168.
  *   model NULL -> classic unweighted fit (compute_normals.py:72); else DeepFit mode with the model's k.
- *   chunk     queries per internal chunk (0 = default: 16 384 DeepFit, 65 536 classic); the workspace
+ *   chunk     queries per internal chunk (0 = default: 16 384 DeepFit, 262 144 classic); the workspace
  *             (neighbour indices, patches, frames; double-buffered) is sized for it at creation.
  *   flags     DFB_PIPE_KEEP_QSTN: do not undo the QSTN rotation on the world normal / directions, which is
  *             what the shipped tutorial script does (compute_normals.py:67 applies only the PCA frame).
@@ -265,6 +265,8 @@ DFB_API int dfb_neighbor_normals(const float* d_patch, const float* d_trans, con
  * ------------------------------------------------------------------------------------------ */
 typedef struct dfb_pipeline dfb_pipeline;
 #define DFB_PIPE_KEEP_QSTN 1
+#define DFB_PIPE_FILE_ORDER 2 /* visit the queries in file order (the reference's) instead of the grid's Morton order;
+                                 same results, slower neighbour search */
 typedef struct dfb_pipeline_outputs {
     float* d_normals;    /* f32[q,3]  world normals (unoriented), compute_normals.py:67 */
     double* d_curv;      /* f64[q,2]  principal curvatures / rad, ascending, compute_normals.py:79 (order >= 2) */

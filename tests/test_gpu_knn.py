@@ -202,6 +202,33 @@ def _ball_sets(pts_np, q, radius):
     return [idx[off[i]:off[i + 1]] for i in range(len(q))]
 
 
+def test_morton_order_is_a_permutation_of_the_range(clouds):
+    """dfb_grid_morton_order: every index of [begin, end) exactly once, in the order of the grid's sorted copy (so
+    consecutive entries are spatial neighbours); and a query list in that order returns the same rows as file order."""
+    from deepfit_b200 import ops
+    pts_np = _normalize(clouds["0000000000"])
+    pts = torch.from_numpy(pts_np).cuda()
+    grid = ops.Grid(pts)
+    n = len(pts_np)
+    whole = grid.morton_order()
+    assert torch.equal(torch.sort(whole.long())[0], torch.arange(n, device="cuda"))
+    for b, e in ((0, 1), (12345, 12345), (777, 40000), (n - 5000, n)):
+        part = grid.morton_order(b, e)
+        assert part.numel() == e - b
+        keep = whole[(whole >= b) & (whole < e)]
+        assert torch.equal(part, keep)              # the sub-range keeps the whole cloud's relative order
+    # spatial coherence: consecutive entries are far closer than random pairs
+    p = pts[whole.long()]
+    step = (p[1:] - p[:-1]).norm(dim=1).median().item()
+    rnd = (pts[torch.randperm(n, device="cuda")[: n - 1]] - pts[:-1]).norm(dim=1).median().item()
+    assert step < 0.05 * rnd
+    part = grid.morton_order(777, 3000)
+    idx_m, rad_m = grid.query(256, query=part)
+    idx_f, rad_f = grid.query(256, q_begin=777, q_count=3000 - 777)
+    inv = (part.long() - 777)
+    assert torch.equal(idx_m, idx_f[inv]) and torch.equal(rad_m, rad_f[inv])
+
+
 @pytest.mark.parametrize("name", CLOUD_NAMES)
 def test_ball_query_matches_ckdtree_sets(clouds, name):
     """neighbor_search_method='r' (reference dataset.py:289-291): the SET cKDTree.query_ball_point returns, for the

@@ -107,18 +107,20 @@ def test_deepfit_pipeline_vs_oracle(clouds, name, precision):
         assert (gate_a <= 0.01).all() and (gate_c <= 1e-3).all()
 
 
+@pytest.mark.parametrize("file_order", [False, True], ids=["morton_order", "file_order"])
 @pytest.mark.parametrize("mode", ["classic", "DeepFit"])
-def test_pipeline_call_equals_stage_calls(clouds, mode):
+def test_pipeline_call_equals_stage_calls(clouds, mode, file_order):
     """dfb_pipeline_run (chunk loop + two-stream schedule inside the library) is bit-identical to calling the five
-    stages one by one, for every optional output, over ragged chunking; DFB_PIPE_KEEP_QSTN reproduces the tutorial
-    script's omission (compute_normals.py:67)."""
+    stages one by one in file order, for every optional output, over ragged chunking -- whether the pipeline visits the
+    queries in the grid's Morton order (default; results scattered back to their file-order rows) or in file order;
+    DFB_PIPE_KEEP_QSTN reproduces the tutorial script's omission (compute_normals.py:67)."""
     from deepfit_b200 import ops
     from deepfit_b200.pipeline import NormalEstimator, model_from_state_dict
     from oracle import deepfit_oracle as O
     pts = torch.from_numpy(O.normalize_cloud(clouds["0000000000"])[0]).cuda()
     k, order = 256, 3
     model = model_from_state_dict(O.seeded_state_dict(1), k, order, "sigmoid", "f16x3") if mode == "DeepFit" else None
-    est = NormalEstimator(pts, k, order, mode, model, chunk=300)
+    est = NormalEstimator(pts, k, order, mode, model, chunk=300, file_order=file_order)
     begin, end = 777, 777 + 1000                  # 3 chunks of 300 + a tail of 100
     extras = {}
     normals, curv = est.run(begin, end, extras=extras)
