@@ -523,9 +523,13 @@ def main():
         est.rebuild_grid()
         evs[1].record()
         c = min(chunk, end - begin)
-        idx, rad = est.grid.query(K, q_begin=begin, q_count=c)
+        # the pipeline visits the queries in the grid's Morton order; so does this split
+        qlist = est.grid.morton_order(begin, end)[:c].contiguous()
+        torch.cuda.synchronize()
+        evs[1].record()
+        idx, rad = est.grid.query(K, query=qlist)
         evs[2].record()
-        patch, U = ops.patch_pca(pts, idx, rad, q_begin=begin)
+        patch, U = ops.patch_pca(pts, idx, rad, query=qlist)
         evs[3].record()
         w = trans = None
         if est.net is not None:
