@@ -179,6 +179,19 @@ def use_all_host_threads():
     return torch.get_num_threads()
 
 
+def ncu_traffic(kernel: str, patches_per_launch: int) -> dict:
+    """`roofline.traffic` = DRAM bytes per launch of `kernel` from the committed ncu capture, or null when there is none."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as fh:
+            t = json.load(fh)[kernel]
+        return {"traffic": t["dram_bytes_per_launch"] * patches_per_launch / t["patches_per_launch"],
+                "traffic_source": "%s: mean dram__bytes_read.sum + dram__bytes_write.sum of %d launches of %d patches under "
+                                  "`ncu --set full`, scaled to %d patches per launch; not measured in this run"
+                                  % (t["source"], t["launches_captured"], t["patches_per_launch"], patches_per_launch)}
+    except (OSError, KeyError, ValueError):
+        return {"traffic": None, "traffic_source": "no committed ncu capture (profiles/ncu_traffic.json)"}
+
+
 def resolve_workload(args, world):
     cloud, points, k, order, mode, scaling = WORKLOADS[args.workload]
     if args.points:
@@ -591,10 +604,10 @@ def main():
                 "bound": "tensor", "kernel": "chain_max_kernel<k/128> (points -> 64 -> [64 -> 64 ->] 128 -> 1024 + max-pool, persistent, "
                                              "3 launches per forward)",
                 "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s", "frac": (achieved / tf_sus) if achieved else None,
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch: NOT measured in this run (needs ncu); the figure
-                # from the last committed `ncu --set full` capture is quoted with its source
-                "traffic": None,
-                "traffic_note": "see profiles/ (r2 ncu --set full capture of the same kernels); per launch of 16 384 patches",
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch: the counters need ncu, so this run cannot measure
+                # them; the committed `ncu --set full` capture of the same kernels is quoted (profiles/ncu_traffic.json,
+                # written by tools/ncu_traffic.py), scaled to this run's patches per launch, with its source
+                **ncu_traffic("chain_max_kernel", min(chunk, end - begin)),
                 "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained" % which,
                 "note": "achieved = algorithmic FLOPs of the three chain kernels (%.1f MFLOP/patch at k=%d) / their CUDA-event time. "
                         "Precision %s executes %d tensor-core MMA(s) per algorithmic product (fp32-grade products need 22-bit "
@@ -610,7 +623,8 @@ def main():
             b = 3180 if K == 256 else 12 * K + 108
             line["roofline"] = {"bound": "hbm", "kernel": "wls_kernel<order> (fused jet fit + normal + curvature)",
                                 "achieved": stages["chunk_points"] * b / (stages["wls_ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                                "traffic": None, "peak_source": "%s MEASURED_PEAKS.json hbm_gbs" % which,
+                                **ncu_traffic("wls_kernel", stages["chunk_points"]),
+                                "peak_source": "%s MEASURED_PEAKS.json hbm_gbs" % which,
                                 "note": "classic path: %d algorithmic bytes per patch (SURVEY 8d); kNN (instruction-bound) dominates "
                                         "this path's time, see stages_one_chunk" % b}
             line["roofline"]["frac"] = line["roofline"]["achieved"] / hbm

@@ -17,9 +17,18 @@
 //           strictly inside the block's guaranteed margin; otherwise retry one level up with the
 //           k-th key as the starting threshold.  The top level covers the whole cloud, so the
 //           search always terminates with the exact answer.
+//   sub-grids (variable density): a finest cell holding more than kHeavy points gets 1 .. 5 levels of its own below
+//           the dense table (8^S sub-cells, S from its population, the table in a pool, found through a hash of the
+//           cell's Morton code); its points are counting-sorted a second time by their sub-cell code, so every
+//           sub-cell of every sub-level is again one contiguous range.  Queries descend into these "negative" levels
+//           the same way they move between the dense ones; a neighbouring cell that is not subdivided (that deep)
+//           contributes its finest available ancestor's range once.  Uniform clouds have no heavy cell and never
+//           leave the dense levels.
 #include "common.cuh"
 
 #include <math.h>
+
+#include <algorithm>
 
 namespace dfb {
 namespace {
@@ -45,7 +54,35 @@ struct GridParams {
     float cell;      // finest cell edge
     int bits;        // finest level has 2^bits cells per axis
     long long n;
+    int sub_levels;  // deepest sub-grid below the dense table (0: no heavy cell)
+    int n_heavy;     // cells with a sub-grid
+    unsigned long long pool_used;   // entries of the sub-table pool handed out
 };
+
+// ---- sub-grids of heavy cells
+constexpr int kHeavy = 512;          // a finest cell with more points than this is subdivided
+constexpr int kMaxSub = 5;           // at most 5 levels (32768 sub-cells)
+// levels for a cell of c points: about 32 points per occupied sub-cell of a surface-like cloud (4^S occupied sub-cells)
+__host__ __device__ __forceinline__ int sub_levels_for(uint32_t c) {
+    int S = 1;
+    while (S < kMaxSub && (32u << (2 * S)) < c) ++S;
+    return S;
+}
+// hash of cell code -> (S, pool offset): open addressing, entry = (code + 1) << 34 | S << 31 | offset (0 = empty)
+__device__ __forceinline__ uint32_t sub_hash(uint32_t m, uint32_t mask) { return (m * 2654435761u) >> 7 & mask; }
+__device__ __forceinline__ bool sub_find(const unsigned long long* __restrict__ ht, uint32_t mask, uint32_t m, int& S, uint32_t& off) {
+    uint32_t h = sub_hash(m, mask);
+    for (;;) {
+        const unsigned long long e = __ldg(ht + h);
+        if (e == 0ull) return false;
+        if ((uint32_t)(e >> 34) == m + 1u) {
+            S = (int)((e >> 31) & 7ull);
+            off = (uint32_t)(e & 0x7fffffffull);
+            return true;
+        }
+        h = (h + 1u) & mask;
+    }
+}
 
 // Continuous cell coordinate of a point at the finest level.  Build and query share this function,
 // so cell membership is consistent and monotone in the coordinate.
@@ -110,6 +147,9 @@ __global__ void params_kernel(unsigned* __restrict__ bb6, GridParams* __restrict
     gp->inv_cell = (float)(1 << bits) / ext;
     gp->cell = ext / (float)(1 << bits);
     gp->n = n;
+    gp->sub_levels = 0;
+    gp->n_heavy = 0;
+    gp->pool_used = 0ull;
     for (int a = 0; a < 3; ++a) { bb6[a] = 0xffffffffu; bb6[3 + a] = 0u; }  // re-arm for the next build
 }
 
@@ -227,6 +267,104 @@ __global__ void scatter_kernel(const float* __restrict__ pts, long long n, const
     if (i >= n) return;
     const uint32_t pos = atomicAdd(tab + 1 + code[i], 1u);
     sorted[pos] = make_float4(pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2], __int_as_float((int)i));
+}
+
+// ---- second sort: the points of heavy cells by sub-cell code
+struct SubBuild {
+    const float4* in;             // sorted by finest dense cell (scatter_kernel)
+    float4* out;                  // same, heavy cells ordered by sub-cell code as well
+    long long n;
+    const uint32_t* code;         // dense Morton code per ORIGINAL point index
+    const uint32_t* tab;
+    GridParams* gp;
+    unsigned long long* ht;
+    uint32_t ht_mask;
+    uint32_t* pool;
+    unsigned long long pool_cap;
+    uint32_t* heavy;              // list of heavy cell codes
+    uint32_t heavy_cap;
+};
+// sub-cell code (3 S bits) of a point inside its dense cell
+__device__ __forceinline__ uint32_t sub_code(const GridParams& g, float x, float y, float z, int S) {
+    const int Gs = (1 << g.bits) << S;
+    const float sc = (float)(1 << S);
+    const uint32_t msk = (1u << S) - 1u;
+    const int fx = cell_index(cell_coord(x, g.minx, g.inv_cell) * sc, Gs), fy = cell_index(cell_coord(y, g.miny, g.inv_cell) * sc, Gs),
+              fz = cell_index(cell_coord(z, g.minz, g.inv_cell) * sc, Gs);
+    return morton3((uint32_t)fx & msk, (uint32_t)fy & msk, (uint32_t)fz & msk);
+}
+// the first point of every heavy cell registers the cell: pool space, hash entry, list entry
+__global__ void sub_mark_kernel(SubBuild b) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    const uint32_t m = b.code[__float_as_int(b.in[i].w)];
+    const uint32_t lo = b.tab[m];
+    if ((long long)lo != i) return;
+    const uint32_t c = b.tab[m + 1] - lo;
+    if (c <= (uint32_t)kHeavy) return;
+    const int S = sub_levels_for(c);
+    const unsigned long long cells = (1ull << (3 * S)) + 1ull;
+    const unsigned long long off = atomicAdd(&b.gp->pool_used, cells);
+    if (off + cells > b.pool_cap || off + cells > 0x7fffffffull) return;   // no room: the cell stays undivided
+    const uint32_t slot = (uint32_t)atomicAdd(&b.gp->n_heavy, 1);
+    if (slot >= b.heavy_cap) return;
+    b.heavy[slot] = m;
+    atomicMax(&b.gp->sub_levels, S);
+    const unsigned long long e = ((unsigned long long)(m + 1u) << 34) | ((unsigned long long)S << 31) | off;
+    uint32_t h = sub_hash(m, b.ht_mask);
+    while (atomicCAS(b.ht + h, 0ull, e) != 0ull) h = (h + 1u) & b.ht_mask;
+}
+__global__ void sub_count_kernel(SubBuild b) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    const float4 p = b.in[i];
+    const uint32_t m = b.code[__float_as_int(p.w)];
+    if (b.tab[m + 1] - b.tab[m] <= (uint32_t)kHeavy) return;
+    int S;
+    uint32_t off;
+    if (!sub_find(b.ht, b.ht_mask, m, S, off)) return;
+    atomicAdd(b.pool + off + 1 + sub_code(*b.gp, p.x, p.y, p.z, S), 1u);
+}
+// one CTA per heavy cell: exclusive scan of its sub-cell counts, based at the cell's first point
+__global__ void __launch_bounds__(256) sub_scan_kernel(SubBuild b) {
+    __shared__ uint32_t s_part[256];
+    const int nh = min(b.gp->n_heavy, (int)b.heavy_cap);
+    for (int hi = blockIdx.x; hi < nh; hi += gridDim.x) {
+        const uint32_t m = b.heavy[hi];
+        int S;
+        uint32_t off;
+        if (!sub_find(b.ht, b.ht_mask, m, S, off)) continue;
+        const int cells = 1 << (3 * S);
+        uint32_t* t = b.pool + off + 1;
+        const int per = (cells + 255) / 256;
+        const int j0 = threadIdx.x * per;
+        uint32_t sum = 0;
+        for (int j = j0; j < min(cells, j0 + per); ++j) sum += t[j];
+        s_part[threadIdx.x] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t run = b.tab[m];
+            for (int q = 0; q < 256; ++q) { const uint32_t v = s_part[q]; s_part[q] = run; run += v; }
+            b.pool[off] = b.tab[m];
+        }
+        __syncthreads();
+        uint32_t run = s_part[threadIdx.x];
+        for (int j = j0; j < min(cells, j0 + per); ++j) { const uint32_t v = t[j]; t[j] = run; run += v; }
+        __syncthreads();
+    }
+}
+__global__ void sub_scatter_kernel(SubBuild b) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n) return;
+    const float4 p = b.in[i];
+    const uint32_t m = b.code[__float_as_int(p.w)];
+    long long pos = i;
+    if (b.tab[m + 1] - b.tab[m] > (uint32_t)kHeavy) {
+        int S;
+        uint32_t off;
+        if (sub_find(b.ht, b.ht_mask, m, S, off)) pos = atomicAdd(b.pool + off + 1 + sub_code(*b.gp, p.x, p.y, p.z, S), 1u);
+    }
+    b.out[pos] = p;
 }
 
 // Indices of the points with q_begin <= index < q_end in MORTON order (the order of the sorted copy): an order-preserving
@@ -518,6 +656,9 @@ __device__ __forceinline__ SortResult sort_emit(const double* sd, const int* si,
 struct KnnArgs {
     const float4* sorted;
     const uint32_t* tab;
+    const unsigned long long* ht;   // sub-grid hash (cell code -> levels, pool offset)
+    uint32_t ht_mask;
+    const uint32_t* pool;           // sub-grid tables
     const float* pts;  // original order, f32[n,3]
     const GridParams* gp;
     const int* query;
@@ -536,6 +677,71 @@ constexpr int kKnnWarps = 4;
 __device__ __constant__ unsigned char c_cell_order[27] = {13, 12, 14, 10, 16, 4, 22, 9, 11, 15, 17, 3, 5, 21, 23, 1, 7, 19, 25,
                                                           0, 2, 6, 8, 18, 20, 24, 26};
 
+// Range of the sorted array and conservative squared distance (world units) of cell (ex, ey, ez) of level l, one of the
+// 27 cells of the block whose first cell is (bx, by, bz) (may be -1).  l >= 0: dense table.  l < 0: sub-level -l of the
+// finest cells; where the parent cell is not subdivided that deep, the finest available ancestor stands in for all of the
+// block's cells it contains and is returned by the first of them only (the others return an empty range).
+__device__ __forceinline__ void block_cell(const KnnArgs& a, const GridParams& gpar, int G, int l, int ex, int ey, int ez, int bx,
+                                           int by, int bz, float ux, float uy, float uz, uint32_t& lo, uint32_t& hi, float& cmin2) {
+    lo = hi = 0u;
+    cmin2 = 0.f;
+    const int Gl = l >= 0 ? (G >> l) : (G << -l);
+    if (ex < 0 || ey < 0 || ez < 0 || ex >= Gl || ey >= Gl || ez >= Gl) return;
+    float w;            // box edge in finest-dense-cell units
+    int ee[3] = {ex, ey, ez};
+    if (l >= 0) {
+        const uint32_t m = morton3(ex, ey, ez);
+        const int sh = 3 * l;
+        if (sh >= 30) {  // single top-level cell
+            lo = 0;
+            hi = (uint32_t)gpar.n;
+        } else {
+            lo = a.tab[(size_t)m << sh];
+            hi = a.tab[((size_t)m + 1) << sh];
+        }
+        w = (float)(1 << l);
+    } else {
+        const int sl = -l;
+        const uint32_t m = morton3(ex >> sl, ey >> sl, ez >> sl);
+        int S = 0;
+        uint32_t off = 0;
+        const bool found = sub_find(a.ht, a.ht_mask, m, S, off);
+        const int d = found ? min(S, sl) : 0;    // depth of the finest available ancestor (sl: the cell itself)
+        const int r = sl - d;
+        if (r > 0) {
+            const int bb[3] = {max(bx, 0), max(by, 0), max(bz, 0)};
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                if (ee[t] != bb[t] && ((ee[t] - 1) >> r) == (ee[t] >> r)) return;   // an earlier cell of the block owns the ancestor
+                ee[t] >>= r;
+            }
+        }
+        if (d == 0) {
+            lo = a.tab[m];
+            hi = a.tab[m + 1];
+        } else {
+            const uint32_t msk = (1u << d) - 1u;
+            const uint32_t sm = morton3((uint32_t)ee[0] & msk, (uint32_t)ee[1] & msk, (uint32_t)ee[2] & msk);
+            const int sh = 3 * (S - d);
+            lo = a.pool[off + (sm << sh)];
+            hi = a.pool[off + ((sm + 1u) << sh)];
+        }
+        w = 1.f / (float)(1 << d);
+    }
+    const float uu[3] = {ux, uy, uz};
+    float dd[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const float c0 = (float)ee[t] * w, c1 = c0 + w;
+        float dv = 0.f;
+        if (uu[t] < c0) dv = c0 - uu[t] - kCellSlack;
+        else if (uu[t] > c1) dv = uu[t] - c1 - kCellSlack;
+        dd[t] = fmaxf(dv, 0.f);
+    }
+    const float dc = gpar.cell * (1.f - 1e-5f);
+    cmin2 = (dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]) * dc * dc * (1.f - 1e-5f);
+}
+
 // E = register entries per lane of the final sort (32 * E = the power of two >= k); 0: shared-memory network only
 #ifdef DFB_KNN_MINB   // A/B builds only (tools/build_variant.sh)
 #define DFB_KNN_BOUNDS __launch_bounds__(kKnnWarps * 32, DFB_KNN_MINB)
@@ -551,6 +757,8 @@ __global__ void DFB_KNN_BOUNDS knn_kernel(KnnArgs a) {
     int* si = reinterpret_cast<int*>(smem_raw + (size_t)kKnnWarps * a.kcap * sizeof(double)) + (size_t)warp * a.kcap;
     const GridParams gpar = *a.gp;
     const int G = 1 << gpar.bits;
+    const int SM = gpar.sub_levels;           // levels below the dense table (0 for clouds without heavy cells)
+    const float fsc = (float)(1 << SM);
     const int k = a.k, cap = a.kcap;
     int k2 = 32;               // size of the sorting network for exactly k entries
     while (k2 < k) k2 <<= 1;
@@ -574,7 +782,8 @@ __global__ void DFB_KNN_BOUNDS knn_kernel(KnnArgs a) {
         const double qx = qxf, qy = qyf, qz = qzf;
         const float ux = cell_coord(qxf, gpar.minx, gpar.inv_cell), uy = cell_coord(qyf, gpar.miny, gpar.inv_cell),
                     uz = cell_coord(qzf, gpar.minz, gpar.inv_cell);
-        const int ix = cell_index(ux, G), iy = cell_index(uy, G), iz = cell_index(uz, G);
+        // cell coordinates at the deepest sub-level; the cell of level l (-SM <= l <= bits) is (fx, fy, fz) >> (l + SM)
+        const int fx = cell_index(ux * fsc, G << SM), fy = cell_index(uy * fsc, G << SM), fz = cell_index(uz * fsc, G << SM);
 
         // threshold: candidates must satisfy key <= T when thr_incl (carried over from a failed
         // level) or key < T otherwise (T = current k-th best of the list)
@@ -590,65 +799,37 @@ __global__ void DFB_KNN_BOUNDS knn_kernel(KnnArgs a) {
         // only from a neighbour (same or adjacent cell of the level that answered it): in a spatially ordered query list
         // that is almost every query, in a random one almost none -- there the hint would be the radius of an unrelated
         // region and a wrong guess costs a second scan
-        if (prev_k2 > 0.0 && abs((ix >> level_hint) - pcx) <= 1 && abs((iy >> level_hint) - pcy) <= 1 &&
-            abs((iz >> level_hint) - pcz) <= 1) {
+        if (prev_k2 > 0.0 && abs((fx >> (level_hint + SM)) - pcx) <= 1 && abs((fy >> (level_hint + SM)) - pcy) <= 1 &&
+            abs((fz >> (level_hint + SM)) - pcz) <= 1) {
             Td = prev_k2 * 1.5;
             guessed = true;
         }
 
         const long long need = min((long long)3 * k, gpar.n);
         int l0 = level_hint;
-        while (l0 > 0) {   // population of the 27-cell block one level finer
+        while (l0 > -SM) {   // population of the 27-cell block one level finer
             const int lf = l0 - 1;
-            const int Gf = G >> lf;
-            const int fx = ix >> lf, fy = iy >> lf, fz = iz >> lf;
+            const int bx = (fx >> (lf + SM)) - 1, by = (fy >> (lf + SM)) - 1, bz = (fz >> (lf + SM)) - 1;
             unsigned cnt = 0;
             if (lane < 27) {
-                const int ex = fx + (lane % 3) - 1, ey = fy + ((lane / 3) % 3) - 1, ez = fz + (lane / 9) - 1;
-                if (ex >= 0 && ey >= 0 && ez >= 0 && ex < Gf && ey < Gf && ez < Gf) {
-                    const uint32_t m = morton3(ex, ey, ez);
-                    const int sh = 3 * lf;
-                    cnt = a.tab[((size_t)m + 1) << sh] - a.tab[(size_t)m << sh];
-                }
+                uint32_t flo, fhi;
+                float fc;
+                block_cell(a, gpar, G, lf, bx + (lane % 3), by + ((lane / 3) % 3), bz + (lane / 9), bx, by, bz, ux, uy, uz, flo, fhi, fc);
+                cnt = fhi - flo;
             }
             cnt = __reduce_add_sync(0xffffffffu, cnt);
             if ((long long)cnt < need) break;
             l0 = lf;
         }
         for (int l = l0; l <= gpar.bits; ++l) {
-            const int Gl = G >> l;
-            const int cx = ix >> l, cy = iy >> l, cz = iz >> l;
+            const int Gl = l >= 0 ? (G >> l) : (G << -l);
+            const int cx = fx >> (l + SM), cy = fy >> (l + SM), cz = fz >> (l + SM);
             // 27 neighbour cells, one per lane
             uint32_t lo = 0, hi = 0;
             float cmin2 = 0.f;  // conservative squared distance from the query to the cell (world units)
-            if (lane < 27) {
-                const int ex = cx + (lane % 3) - 1, ey = cy + ((lane / 3) % 3) - 1, ez = cz + (lane / 9) - 1;
-                if (ex >= 0 && ey >= 0 && ez >= 0 && ex < Gl && ey < Gl && ez < Gl) {
-                    const uint32_t m = morton3(ex, ey, ez);
-                    const int sh = 3 * l;
-                    if (sh >= 30) {  // single top-level cell
-                        lo = 0;
-                        hi = (uint32_t)gpar.n;
-                    } else {
-                        lo = a.tab[(size_t)m << sh];
-                        hi = a.tab[((size_t)m + 1) << sh];
-                    }
-                    const float w = (float)(1 << l);
-                    float dd[3];
-                    const float uu[3] = {ux, uy, uz};
-                    const int ee[3] = {ex, ey, ez};
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) {
-                        const float c0 = (float)ee[t] * w, c1 = c0 + w;
-                        float d = 0.f;
-                        if (uu[t] < c0) d = c0 - uu[t] - kCellSlack;
-                        else if (uu[t] > c1) d = uu[t] - c1 - kCellSlack;
-                        dd[t] = fmaxf(d, 0.f);
-                    }
-                    const float dc = gpar.cell * (1.f - 1e-5f);
-                    cmin2 = (dd[0] * dd[0] + dd[1] * dd[1] + dd[2] * dd[2]) * dc * dc * (1.f - 1e-5f);
-                }
-            }
+            if (lane < 27)
+                block_cell(a, gpar, G, l, cx + (lane % 3) - 1, cy + ((lane / 3) % 3) - 1, cz + (lane / 9) - 1, cx - 1, cy - 1, cz - 1,
+                           ux, uy, uz, lo, hi, cmin2);
             unsigned total = hi - lo;
             total = __reduce_add_sync(0xffffffffu, total);
             const bool top = (l == gpar.bits);
@@ -657,7 +838,7 @@ __global__ void DFB_KNN_BOUNDS knn_kernel(KnnArgs a) {
             // guaranteed-complete radius of the block (world units), strict
             double margin2 = INF;
             if (!top) {
-                const float w = (float)(1 << l);
+                const float w = l >= 0 ? (float)(1 << l) : 1.f / (float)(1 << -l);
                 float mrg = 3.0e38f;
                 const float uu[3] = {ux, uy, uz};
                 const int cc[3] = {cx, cy, cz};
@@ -940,7 +1121,14 @@ struct dfb_grid {
     size_t ncell = 0;
     long long ntile = 0;
     float* pts = nullptr;              // device copy, original order
-    float4* sorted = nullptr;          // device, Morton order (x, y, z, original index)
+    float4* sorted = nullptr;          // device, Morton order (x, y, z, original index), heavy cells by sub-cell code too
+    float4* sorted_tmp = nullptr;      // device, build scratch: sorted by finest dense cell only
+    unsigned long long* ht = nullptr;  // device, sub-grid hash
+    uint32_t ht_size = 0;
+    uint32_t* pool = nullptr;          // device, sub-grid tables
+    unsigned long long pool_cap = 0;
+    uint32_t* heavy = nullptr;         // device, list of heavy cells
+    uint32_t heavy_cap = 0;
     uint32_t* tab = nullptr;           // device, 8^bits + 1 entries
     uint32_t* code = nullptr;          // device, per-point Morton code (build scratch)
     uint32_t* sums = nullptr;          // device, scan scratch
@@ -964,8 +1152,17 @@ int grid_build(dfb_grid* g, const float* d_points, cudaStream_t st) {
     scan_tile_sums<<<(unsigned)g->ntile, kScanThreads, 0, st>>>(g->tab + 1, (long long)g->ncell, g->sums);
     scan_sums_serial<<<1, 1024, 0, st>>>(g->sums, g->ntile);
     scan_apply<<<(unsigned)g->ntile, kScanThreads, 0, st>>>(g->tab + 1, (long long)g->ncell, g->sums);
-    scatter_kernel<<<nb, 256, 0, st>>>(g->pts, n, g->code, g->tab, g->sorted);
-    note_launch(7);
+    scatter_kernel<<<nb, 256, 0, st>>>(g->pts, n, g->code, g->tab, g->sorted_tmp);
+    // second sort inside heavy cells (sub-grids); clouds without heavy cells pay one copy of the sorted array
+    DFB_CUDA(cudaMemsetAsync(g->ht, 0, (size_t)g->ht_size * sizeof(unsigned long long), st));
+    DFB_CUDA(cudaMemsetAsync(g->pool, 0, (size_t)g->pool_cap * sizeof(uint32_t), st));
+    SubBuild sb{g->sorted_tmp, g->sorted, n, g->code, g->tab, g->params, g->ht, g->ht_size - 1, g->pool, g->pool_cap, g->heavy,
+                g->heavy_cap};
+    sub_mark_kernel<<<nb, 256, 0, st>>>(sb);
+    sub_count_kernel<<<nb, 256, 0, st>>>(sb);
+    sub_scan_kernel<<<(unsigned)std::min<long long>((long long)g->heavy_cap, (long long)sm_count() * 8), 256, 0, st>>>(sb);
+    sub_scatter_kernel<<<nb, 256, 0, st>>>(sb);
+    note_launch(11);
     return check_cuda(cudaGetLastError(), "grid build kernels", __FILE__, __LINE__);
 }
 }  // namespace
@@ -994,9 +1191,19 @@ extern "C" int dfb_grid_create(const float* d_points, int64_t n, dfb_stream stre
     g->bits = bits;
     g->ncell = (size_t)1 << (3 * bits);
     g->ntile = (long long)((g->ncell + kScanTile - 1) / kScanTile);
+    // sub-grids: at most n / kHeavy heavy cells; a cell of c points takes 8^S + 1 <= 4 c + 1 table entries, usually about
+    // c: room for 2 n (a cell that finds the pool full stays undivided, which costs speed, not exactness)
+    g->heavy_cap = (uint32_t)(n / kHeavy + 1);
+    g->ht_size = 1024;
+    while ((unsigned long long)g->ht_size < 4ull * g->heavy_cap) g->ht_size <<= 1;
+    g->pool_cap = std::min<unsigned long long>(2ull * (unsigned long long)n + 65536ull, 0x7fffffffull);
     cudaError_t e;
     if ((e = cudaMalloc(&g->pts, (size_t)n * 3 * sizeof(float))) != cudaSuccess ||
         (e = cudaMalloc(&g->sorted, (size_t)n * sizeof(float4))) != cudaSuccess ||
+        (e = cudaMalloc(&g->sorted_tmp, (size_t)n * sizeof(float4))) != cudaSuccess ||
+        (e = cudaMalloc(&g->ht, (size_t)g->ht_size * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMalloc(&g->pool, (size_t)g->pool_cap * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc(&g->heavy, (size_t)g->heavy_cap * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&g->tab, (g->ncell + 1) * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&g->code, (size_t)n * sizeof(uint32_t))) != cudaSuccess ||
         (e = cudaMalloc(&g->sums, (size_t)g->ntile * sizeof(uint32_t))) != cudaSuccess ||
@@ -1032,6 +1239,10 @@ extern "C" int dfb_grid_destroy(dfb_grid* g) {
     if (!g) return DFB_OK;
     cudaFree(g->pts);
     cudaFree(g->sorted);
+    cudaFree(g->sorted_tmp);
+    cudaFree(g->ht);
+    cudaFree(g->pool);
+    cudaFree(g->heavy);
     cudaFree(g->tab);
     cudaFree(g->code);
     cudaFree(g->sums);
@@ -1072,6 +1283,7 @@ extern "C" int dfb_knn(const dfb_grid* grid, const int32_t* d_query, int64_t q_b
     while (kcap < 2 * k) kcap <<= 1;
     KnnArgs a;
     a.sorted = grid->sorted; a.tab = grid->tab; a.pts = grid->pts; a.gp = grid->params;
+    a.ht = grid->ht; a.ht_mask = grid->ht_size - 1; a.pool = grid->pool;
     a.query = d_query; a.q_begin = q_begin; a.q_count = q_count;
     a.k = k; a.kcap = kcap;
     a.out_idx = d_idx; a.out_dist = d_dist; a.out_rad = d_rad;

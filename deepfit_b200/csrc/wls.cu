@@ -25,6 +25,8 @@
 // solution of the fp32 inputs to ~1e-9, i.e. at most the reference's own rounding error away from it.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace dfb {
 namespace {
 
@@ -330,6 +332,120 @@ struct WlsArgs {
     long long out_base;
 };
 
+// Phase 2 for one patch (one lane): preconditioned normal equations from the patch's moment slot, Cholesky + two steps
+// of fp64-residual refinement, D_inv, normal, curvatures, principal directions, back-rotation; outputs to row po.
+template <int ORDER>
+__device__ __forceinline__ void solve_and_emit(const WlsArgs& p, const double* slot, long long pi, long long po) {
+    using J = Jet<ORDER>;
+    constexpr int M = J::M;
+    float h = 1.f;
+    if (ORDER > 1) {
+        // DeepFit.py:43-46 (fp32, like the reference)
+        const float invk = 1.f / (float)p.k;
+        h = ((float)slot[J::NM + J::NZ] * invk + (float)slot[J::NM + J::NZ + 1] * invk) * 0.5f;
+        if (fabsf(h) < 1e-4f) h = 0.1f;
+    }
+    const double ih = 1.0 / (double)h;
+    double ihp[J::D + 1];
+    ihp[0] = 1.0;
+#pragma unroll
+    for (int a = 1; a <= J::D; ++a) ihp[a] = ihp[a - 1] * ih;
+
+    double bsol[M];  // solution of the preconditioned system, refined in fp64
+    int info = 0;
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        float a[M * (M + 1) / 2];
+        float rhs[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const int ax = colx<ORDER>(i) + colx<ORDER>(j), by = coly<ORDER>(i) + coly<ORDER>(j);
+                double v = slot[J::mi(ax, by)] * ihp[ax + by];
+                if (attempt == 1 && i == j) v *= 1.01;
+                a[i * (i + 1) / 2 + j] = (float)v;
+            }
+            rhs[i] = (float)(slot[J::NM + J::zi(colx<ORDER>(i), coly<ORDER>(i))] * ihp[colx<ORDER>(i) + coly<ORDER>(i)]);
+        }
+        const bool ok = chol_factor<M>(a);
+        if (!ok) {
+            info = attempt + 1;
+            continue;
+        }
+        chol_substitute<M>(a, rhs);
+#pragma unroll
+        for (int i = 0; i < M; ++i) bsol[i] = (double)rhs[i];
+        // iterative refinement: residual of the (possibly ridged) fp64 system, correction through the
+        // fp32 factor; contracts by ~cond * 2^-24 per step
+#pragma unroll 1
+        for (int it = 0; it < 2; ++it) {
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                double r = slot[J::NM + J::zi(colx<ORDER>(i), coly<ORDER>(i))] * ihp[colx<ORDER>(i) + coly<ORDER>(i)];
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    const int ax = colx<ORDER>(i) + colx<ORDER>(j), by = coly<ORDER>(i) + coly<ORDER>(j);
+                    double v = slot[J::mi(ax, by)] * ihp[ax + by];
+                    if (attempt == 1 && i == j) v *= 1.01;
+                    r = fma(-v, bsol[j], r);
+                }
+                rhs[i] = (float)r;
+            }
+            chol_substitute<M>(a, rhs);
+#pragma unroll
+            for (int i = 0; i < M; ++i) bsol[i] += (double)rhs[i];
+        }
+        break;
+    }
+    float beta[M];
+    // D_inv, DeepFit.py:85-86
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+        beta[i] = (info == 2) ? 0.f : (float)(bsol[i] * ihp[colx<ORDER>(i) + coly<ORDER>(i)]);
+
+    if (p.beta) {
+#pragma unroll
+        for (int i = 0; i < M; ++i) p.beta[po * M + i] = beta[i];
+    }
+    // normal, DeepFit.py:88
+    const float inv_n = 1.f / fmaxf(sqrtf(fmaf(beta[0], beta[0], fmaf(beta[1], beta[1], 1.f))), 1e-12f);
+    const float nx = -beta[0] * inv_n, ny = -beta[1] * inv_n, nz = inv_n;
+    if (p.n_local) {
+        p.n_local[po * 3 + 0] = nx; p.n_local[po * 3 + 1] = ny; p.n_local[po * 3 + 2] = nz;
+    }
+    if (p.n_world) {
+        float vx = nx, vy = ny, vz = nz;
+        // n * trans^T (test_n_est.py:154-157), then n * U^T (compute_normals.py:67)
+        rotate_back((p.trans && !p.keep_qstn) ? p.trans + pi * 9 : nullptr, p.U ? p.U + pi * 9 : nullptr, vx, vy, vz);
+        p.n_world[po * 3 + 0] = vx; p.n_world[po * 3 + 1] = vy; p.n_world[po * 3 + 2] = vz;
+    }
+    if (ORDER > 1 && (p.curv || p.curv_scaled || p.dirs || p.dirs_world)) {
+        float k1, k2, dirs[6];
+        const bool want_dirs = p.dirs || p.dirs_world;
+        curvature_from_beta(beta[0], beta[1], beta[2], beta[3], beta[4], k1, k2, want_dirs ? dirs : nullptr);
+        if (p.curv) { p.curv[po * 2] = k1; p.curv[po * 2 + 1] = k2; }
+        if (p.curv_scaled) {
+            const double r = p.rad ? p.rad[pi] : 1.0;  // fp32 / fp64 -> fp64, compute_normals.py:79
+            p.curv_scaled[po * 2] = (double)k1 / r;
+            p.curv_scaled[po * 2 + 1] = (double)k2 / r;
+        }
+        if (p.dirs) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) p.dirs[po * 6 + i] = dirs[i];
+        }
+        if (p.dirs_world) {
+#pragma unroll
+            for (int rrow = 0; rrow < 2; ++rrow) {
+                float vx = dirs[rrow * 3], vy = dirs[rrow * 3 + 1], vz = 0.f;
+                rotate_back((p.trans && !p.keep_qstn) ? p.trans + pi * 9 : nullptr, p.U ? p.U + pi * 9 : nullptr, vx, vy, vz);
+                p.dirs_world[po * 6 + rrow * 3] = vx; p.dirs_world[po * 6 + rrow * 3 + 1] = vy; p.dirs_world[po * 6 + rrow * 3 + 2] = vz;
+            }
+        }
+    }
+    if (p.info) p.info[po] = info;
+}
+
 // PPC = patches per CTA iteration (phase 1: both warps walk all of them, each for its half of the moments; phase 2: each
 // warp solves PPC / 2 systems, one per lane): 64 when there is enough work to fill the GPU that way, 16 for small batches.
 #ifndef DFB_WLS_MINB
@@ -380,117 +496,208 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, DFB_WLS_MINB) wls_kernel(
         // ---------------- phase 2 ----------------
         const int sl = warp * (PPC / 2) + lane;   // this lane's slot of the batch
         const long long pi = base + sl;
-        if (lane < PPC / 2 && pi < p.n) {
-            const double* slot = s_mom[sl];
-            const long long po = p.out_row ? (long long)p.out_row[pi] - p.out_base : pi;   // output row
-            float h = 1.f;
-            if (ORDER > 1) {
-                // DeepFit.py:43-46 (fp32, like the reference)
-                const float invk = 1.f / (float)p.k;
-                h = ((float)slot[J::NM + J::NZ] * invk + (float)slot[J::NM + J::NZ + 1] * invk) * 0.5f;
-                if (fabsf(h) < 1e-4f) h = 0.1f;
-            }
-            const double ih = 1.0 / (double)h;
-            double ihp[J::D + 1];
-            ihp[0] = 1.0;
-#pragma unroll
-            for (int a = 1; a <= J::D; ++a) ihp[a] = ihp[a - 1] * ih;
-
-            double bsol[M];  // solution of the preconditioned system, refined in fp64
-            int info = 0;
-#pragma unroll 1
-            for (int attempt = 0; attempt < 2; ++attempt) {
-                float a[M * (M + 1) / 2];
-                float rhs[M];
-#pragma unroll
-                for (int i = 0; i < M; ++i) {
-#pragma unroll
-                    for (int j = 0; j <= i; ++j) {
-                        const int ax = colx<ORDER>(i) + colx<ORDER>(j), by = coly<ORDER>(i) + coly<ORDER>(j);
-                        double v = slot[J::mi(ax, by)] * ihp[ax + by];
-                        if (attempt == 1 && i == j) v *= 1.01;
-                        a[i * (i + 1) / 2 + j] = (float)v;
-                    }
-                    rhs[i] = (float)(slot[J::NM + J::zi(colx<ORDER>(i), coly<ORDER>(i))] * ihp[colx<ORDER>(i) + coly<ORDER>(i)]);
-                }
-                const bool ok = chol_factor<M>(a);
-                if (!ok) {
-                    info = attempt + 1;
-                    continue;
-                }
-                chol_substitute<M>(a, rhs);
-#pragma unroll
-                for (int i = 0; i < M; ++i) bsol[i] = (double)rhs[i];
-                // iterative refinement: residual of the (possibly ridged) fp64 system, correction through the
-                // fp32 factor; contracts by ~cond * 2^-24 per step
-#pragma unroll 1
-                for (int it = 0; it < 2; ++it) {
-#pragma unroll
-                    for (int i = 0; i < M; ++i) {
-                        double r = slot[J::NM + J::zi(colx<ORDER>(i), coly<ORDER>(i))] * ihp[colx<ORDER>(i) + coly<ORDER>(i)];
-#pragma unroll
-                        for (int j = 0; j < M; ++j) {
-                            const int ax = colx<ORDER>(i) + colx<ORDER>(j), by = coly<ORDER>(i) + coly<ORDER>(j);
-                            double v = slot[J::mi(ax, by)] * ihp[ax + by];
-                            if (attempt == 1 && i == j) v *= 1.01;
-                            r = fma(-v, bsol[j], r);
-                        }
-                        rhs[i] = (float)r;
-                    }
-                    chol_substitute<M>(a, rhs);
-#pragma unroll
-                    for (int i = 0; i < M; ++i) bsol[i] += (double)rhs[i];
-                }
-                break;
-            }
-            float beta[M];
-            // D_inv, DeepFit.py:85-86
-#pragma unroll
-            for (int i = 0; i < M; ++i)
-                beta[i] = (info == 2) ? 0.f : (float)(bsol[i] * ihp[colx<ORDER>(i) + coly<ORDER>(i)]);
-
-            if (p.beta) {
-#pragma unroll
-                for (int i = 0; i < M; ++i) p.beta[po * M + i] = beta[i];
-            }
-            // normal, DeepFit.py:88
-            const float inv_n = 1.f / fmaxf(sqrtf(fmaf(beta[0], beta[0], fmaf(beta[1], beta[1], 1.f))), 1e-12f);
-            const float nx = -beta[0] * inv_n, ny = -beta[1] * inv_n, nz = inv_n;
-            if (p.n_local) {
-                p.n_local[po * 3 + 0] = nx; p.n_local[po * 3 + 1] = ny; p.n_local[po * 3 + 2] = nz;
-            }
-            if (p.n_world) {
-                float vx = nx, vy = ny, vz = nz;
-                // n * trans^T (test_n_est.py:154-157), then n * U^T (compute_normals.py:67)
-                rotate_back((p.trans && !p.keep_qstn) ? p.trans + pi * 9 : nullptr, p.U ? p.U + pi * 9 : nullptr, vx, vy, vz);
-                p.n_world[po * 3 + 0] = vx; p.n_world[po * 3 + 1] = vy; p.n_world[po * 3 + 2] = vz;
-            }
-            if (ORDER > 1 && (p.curv || p.curv_scaled || p.dirs || p.dirs_world)) {
-                float k1, k2, dirs[6];
-                const bool want_dirs = p.dirs || p.dirs_world;
-                curvature_from_beta(beta[0], beta[1], beta[2], beta[3], beta[4], k1, k2, want_dirs ? dirs : nullptr);
-                if (p.curv) { p.curv[po * 2] = k1; p.curv[po * 2 + 1] = k2; }
-                if (p.curv_scaled) {
-                    const double r = p.rad ? p.rad[pi] : 1.0;  // fp32 / fp64 -> fp64, compute_normals.py:79
-                    p.curv_scaled[po * 2] = (double)k1 / r;
-                    p.curv_scaled[po * 2 + 1] = (double)k2 / r;
-                }
-                if (p.dirs) {
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) p.dirs[po * 6 + i] = dirs[i];
-                }
-                if (p.dirs_world) {
-#pragma unroll
-                    for (int rrow = 0; rrow < 2; ++rrow) {
-                        float vx = dirs[rrow * 3], vy = dirs[rrow * 3 + 1], vz = 0.f;
-                        rotate_back((p.trans && !p.keep_qstn) ? p.trans + pi * 9 : nullptr, p.U ? p.U + pi * 9 : nullptr, vx, vy, vz);
-                        p.dirs_world[po * 6 + rrow * 3] = vx; p.dirs_world[po * 6 + rrow * 3 + 1] = vy; p.dirs_world[po * 6 + rrow * 3 + 2] = vz;
-                    }
-                }
-            }
-            if (p.info) p.info[po] = info;
-        }
+        if (lane < PPC / 2 && pi < p.n)
+            solve_and_emit<ORDER>(p, s_mom[sl], pi, p.out_row ? (long long)p.out_row[pi] - p.out_base : pi);
         __syncthreads();   // the slots are rewritten by the next iteration
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same kernel with its input STAGED THROUGH SHARED MEMORY by the TMA engine (cp.async.bulk + mbarrier): a ring of
+// kStages stages, each one "round" = 4 patches x up to 256 points (x, y, z and weight rows, 1 KB bulk copies), filled
+// two rounds ahead by one elected lane.  With register loads the warps sat on exposed DRAM latency (ncu: a quarter of
+// the stall samples on the first use of the loaded chunk, FP64 pipe 43 % busy); here the bytes in flight per SM are
+// set by the ring, not by registers and occupancy, both warps read each byte from shared memory (the second read cost
+// an L1 / L2 request before), and patches longer than 256 points stream through the same stages chunk by chunk.
+constexpr int kStages = 3;
+constexpr int kChunkPts = 256;                         // points per patch and round
+constexpr int kStageFloats = 4 * 4 * kChunkPts;        // 4 patches x (x, y, z, w) rows: 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded (2 s of wall clock): a protocol bug must end as a launch failure, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        if (mbar_try(bar, parity)) return;
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > 2000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// one chunk (len points, a multiple of 4) of one patch from its staged rows; 8 lanes, sub = lane & 7
+template <int ORDER, int PAR>
+__device__ __forceinline__ void acc_chunk_smem(Acc<ORDER>& A, const float* sx, const float* sw, const float* R, int len, int sub,
+                                               bool has_w) {
+    const float4* x4 = reinterpret_cast<const float4*>(sx);
+    const float4* y4 = reinterpret_cast<const float4*>(sx + kChunkPts);
+    const float4* z4 = reinterpret_cast<const float4*>(sx + 2 * kChunkPts);
+    const float4* w4 = reinterpret_cast<const float4*>(sw);
+    const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    const int nc = len >> 2;
+    float4 Xn = one4, Yn = one4, Zn = one4, Wn = one4;
+    if (sub < nc) {
+        Xn = x4[sub]; Yn = y4[sub]; Zn = z4[sub];
+        if (has_w) Wn = w4[sub];
+    }
+    for (int c = sub; c < nc; c += 8) {
+        float4 X = Xn, Y = Yn, Z = Zn;
+        const float4 W = Wn;
+        if (c + 8 < nc) {
+            Xn = x4[c + 8]; Yn = y4[c + 8]; Zn = z4[c + 8];
+            if (has_w) Wn = w4[c + 8];
+        }
+        if (R) {
+            rotate(R, X.x, Y.x, Z.x); rotate(R, X.y, Y.y, Z.y);
+            rotate(R, X.z, Y.z, Z.z); rotate(R, X.w, Y.w, Z.w);
+        }
+        acc_point<ORDER, PAR>(A, X.x, Y.x, Z.x, W.x, W.x);
+        acc_point<ORDER, PAR>(A, X.y, Y.y, Z.y, W.y, W.y);
+        acc_point<ORDER, PAR>(A, X.z, Y.z, Z.z, W.z, W.z);
+        acc_point<ORDER, PAR>(A, X.w, Y.w, Z.w, W.w, W.w);
+    }
+}
+
+template <int ORDER, int PAR>
+__device__ __forceinline__ void staged_phase1(const WlsArgs& p, double (*s_mom)[slot_stride<ORDER>()], const float* ring,
+                                              uint64_t* full, uint64_t* empty, long long base, int ppc, int nch, long long& g,
+                                              int lane) {
+    const int grp = lane >> 3, sub = lane & 7;
+    const bool has_R = p.trans != nullptr, has_w = p.weights != nullptr;
+    for (int round = 0; round < ppc / 4; ++round) {
+        long long pi = base + round * 4 + grp;
+        if (pi >= p.n) pi = p.n - 1;
+        float R[9];
+        if (has_R) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) R[i] = __ldg(p.trans + pi * 9 + i);
+        }
+        Acc<ORDER> A;
+#pragma unroll
+        for (int i = 0; i < Jet<ORDER>::NM; ++i) A.m[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < Jet<ORDER>::NZ; ++i) A.zm[i] = 0.0;
+        A.sax = A.say = A.nvalid = 0.f;
+        for (int c = 0; c < nch; ++c, ++g) {
+            const int st = (int)(g % kStages);
+            mbar_wait(smem_u32(&full[st]), (uint32_t)(g / kStages) & 1u);
+            const float* sp = ring + (size_t)st * kStageFloats + grp * (4 * kChunkPts);
+            const int len = min(kChunkPts, p.k - c * kChunkPts);
+            acc_chunk_smem<ORDER, PAR>(A, sp, sp + 3 * kChunkPts, has_R ? R : nullptr, len, sub, has_w);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&empty[st]));
+        }
+        // zero-weight guard, DeepFit.py:37-39 (weights -> 1 unless more than 18 exceed 1e-3): practically never taken
+        // (sigmoid / tanh weights are >= 0.005), so the affected patches are simply accumulated again from global memory
+        if (has_w) {
+            const bool redo = group8_sum(A.nvalid) <= 18.f;
+            if (__any_sync(0xffffffffu, redo))
+                acc_patch<ORDER, PAR>(A, p.patch + pi * 3LL * p.k, p.weights + pi * (long long)p.k, has_R ? R : nullptr, p.k, sub, !redo);
+        }
+        reduce_store<ORDER, PAR>(A, s_mom[round * 4 + grp], sub);
+    }
+}
+
+template <int ORDER, int PPC>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, DFB_WLS_MINB) wls_kernel_staged(WlsArgs p) {
+    constexpr int SS = slot_stride<ORDER>();
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    float* ring = reinterpret_cast<float*>(dyn_smem);
+    __shared__ double s_mom[PPC][SS];
+    __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n_super = (p.n + PPC - 1) / PPC;
+    const int nch = (p.k + kChunkPts - 1) / kChunkPts;           // chunks per patch
+    const int rounds_per_it = (PPC / 4) * nch;
+    const long long n_it = blockIdx.x < n_super ? (n_super - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long n_rounds = n_it * rounds_per_it;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(smem_u32(&full[i]), 1);
+            mbar_init(smem_u32(&empty[i]), kWarpsPerBlock);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const bool has_w = p.weights != nullptr;
+    // the producer: round r of this CTA -> (iteration, patch quad, chunk) -> 12 or 16 row copies of <= 1 KB
+    auto issue = [&](long long r) {
+        const int st = (int)(r % kStages);
+        if (r >= kStages) mbar_wait(smem_u32(&empty[st]), (uint32_t)(r / kStages - 1) & 1u);
+        const long long it = r / rounds_per_it;
+        const int rr = (int)(r % rounds_per_it);
+        const int quad = rr / nch, c = rr % nch;
+        const long long base = ((long long)blockIdx.x + it * gridDim.x) * PPC + quad * 4;
+        const int len = min(kChunkPts, p.k - c * kChunkPts);
+        const uint32_t bytes = (uint32_t)len * 4u;
+        const uint32_t bar = smem_u32(&full[st]);
+        mbar_expect_tx(bar, bytes * 4u * (has_w ? 4u : 3u));
+        const uint32_t dst0 = smem_u32(ring + (size_t)st * kStageFloats);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            long long pi = base + j;
+            if (pi >= p.n) pi = p.n - 1;
+            const float* src = p.patch + pi * 3LL * p.k + c * kChunkPts;
+            const uint32_t dst = dst0 + (uint32_t)(j * 4 * kChunkPts * 4);
+            bulk_g2s(dst, src, bytes, bar);
+            bulk_g2s(dst + kChunkPts * 4, src + p.k, bytes, bar);
+            bulk_g2s(dst + 2 * kChunkPts * 4, src + 2 * p.k, bytes, bar);
+            if (has_w) bulk_g2s(dst + 3 * kChunkPts * 4, p.weights + pi * (long long)p.k + c * kChunkPts, bytes, bar);
+        }
+    };
+    const bool producer = threadIdx.x == 0;
+    if (producer)
+        for (long long r = 0; r < kStages - 1 && r < n_rounds; ++r) issue(r);
+    long long g = 0;        // rounds consumed by this warp
+    long long issued = kStages - 1;
+    for (long long it = 0; it < n_it; ++it) {
+        const long long base = ((long long)blockIdx.x + it * gridDim.x) * PPC;
+        // ---------------- phase 1 (the producer lane tops the ring up before each of its rounds) ----------------
+        // The refill is interleaved at quad granularity: before quad q of this iteration the producer issues every round
+        // up to (rounds consumed so far) + kStages - 1.
+        for (int quad = 0; quad < PPC / 4; ++quad) {
+            if (producer) {
+                const long long upto = min(n_rounds, g + kStages);   // this warp has consumed every round below g
+                for (; issued < upto; ++issued) issue(issued);
+            }
+            __syncwarp();
+            if (warp == 0) staged_phase1<ORDER, 0>(p, s_mom + quad * 4, ring, full, empty, base + quad * 4, 4, nch, g, lane);
+            else staged_phase1<ORDER, 1>(p, s_mom + quad * 4, ring, full, empty, base + quad * 4, 4, nch, g, lane);
+        }
+        __syncthreads();
+        // ---------------- phase 2 ----------------
+        const int sl = warp * (PPC / 2) + lane;
+        const long long pi = base + sl;
+        if (lane < PPC / 2 && pi < p.n)
+            solve_and_emit<ORDER>(p, s_mom[sl], pi, p.out_row ? (long long)p.out_row[pi] - p.out_base : pi);
+        __syncthreads();
     }
 }
 
@@ -577,7 +784,24 @@ int launch_wls(const WlsArgs& a, cudaStream_t st) {
     long long blocks = n_super;
     const long long cap = (long long)sm_count() * 32;
     if (blocks > cap) blocks = cap;
-    if (small) wls_kernel<ORDER, 16><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+    // TMA-staged input: measured (profiles/r2_wls_staged_ab.log) 20 % faster at order 1, where the kernel waits on its
+    // loads, and 10-50 % slower at orders 2-4, where the FP64 pipe is the limiter and the ring's 48 KB cost resident warps:
+    // default for order 1 only (DFB_WLS_STAGED=0 / 1 forces either kernel for A/B runs).  Bulk copies need 16-byte
+    // aligned rows, and the ring holds at most kStages chunks of a patch.
+    static const int force_staged = [] { const char* e = getenv("DFB_WLS_STAGED"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    const bool want_staged = force_staged >= 0 ? force_staged == 1 : ORDER == 1;
+    const bool staged = want_staged && a.k % 4 == 0 && a.k <= kChunkPts * (kStages - 1) &&
+                        (reinterpret_cast<uintptr_t>(a.patch) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.weights) & 15) == 0;
+    if (staged) {
+        constexpr int kRingBytes = kStages * kStageFloats * 4;
+        if (small) {
+            cudaFuncSetAttribute(wls_kernel_staged<ORDER, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes);
+            wls_kernel_staged<ORDER, 16><<<(unsigned)blocks, kWarpsPerBlock * 32, kRingBytes, st>>>(a);
+        } else {
+            cudaFuncSetAttribute(wls_kernel_staged<ORDER, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes);
+            wls_kernel_staged<ORDER, 64><<<(unsigned)blocks, kWarpsPerBlock * 32, kRingBytes, st>>>(a);
+        }
+    } else if (small) wls_kernel<ORDER, 16><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(a);
     else wls_kernel<ORDER, 64><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(a);
     note_launch();
     return check_cuda(cudaGetLastError(), "wls_kernel launch", __FILE__, __LINE__);

@@ -147,47 +147,86 @@ class PointcloudPatchDataset:
 
 
 def estimate_shapes(dataset: PointcloudPatchDataset, model: Optional[DeepFit], output_dir: str, jet_order: int = 3,
-                    batch: int = 4096, use_point_stn: bool = True, write: bool = True):
+                    batch: int = 4096, use_point_stn: bool = True, write: bool = True, timings: Optional[dict] = None,
+                    use_pipeline: bool = True, keep_results: bool = True):
     """Run every shape of the dataset and export the five per-shape files of test_c_est.py:201-210.
     ``model=None`` runs the classic unweighted fit (weights file of ones, identity trans).
-    Returns {shape_name: dict of numpy arrays}."""
+    Returns {shape_name: dict of numpy arrays} (empty when ``keep_results`` is False: 20 dense 100 k-point shapes
+    hold 2 GB of weights).
+
+    Dense k-nearest-neighbour shapes with PCA (the pretrained configuration) go through the C pipeline
+    (``dfb_pipeline_run`` with every optional output: one call per shape, 16 384-query chunks, two streams);
+    sparse ``.pidx`` centres, ball-query patches and ``use_pca=False`` take the stage-by-stage loop below.  Both give the
+    same bits (tests/test_gpu_config3.py).  ``timings`` (a dict) accumulates seconds spent in ``load`` (text -> device +
+    grid), ``compute`` (kNN ... curvature, device-synchronised) and ``export`` (device -> host + text files)."""
+    import time
     if write:
         os.makedirs(output_dir, exist_ok=True)
     results = {}
     k = dataset.points_per_patch
-    net = model._network(dataset.device, max_batch=batch) if model is not None else None
     order = model.jet_order if model is not None else jet_order
+    dev = dataset.device
+
+    def tick(name, t0):
+        if timings is not None:
+            torch.cuda.synchronize(dev)
+            timings[name] = timings.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
     for si, name in enumerate(dataset.shape_names):
+        t0 = time.perf_counter()
+        pts, grid = dataset.load_shape(si)
         n_patch = dataset._count(si)
-        normal_prop = torch.zeros((n_patch, 3), dtype=torch.float32, device=dataset.device)
-        curv_prop = torch.zeros((n_patch, 2), dtype=torch.float32, device=dataset.device)
-        weights_prop = torch.ones((n_patch, k), dtype=torch.float32, device=dataset.device)
-        beta_prop = torch.zeros((n_patch, ops.JET_M[order]), dtype=torch.float32, device=dataset.device)
-        trans_prop = torch.eye(3, device=dataset.device).reshape(1, 9).repeat(n_patch, 1)
-        for s in range(0, n_patch, batch):
-            c = min(batch, n_patch - s)
-            patch, data_trans, rad = dataset.patches(si, s, c)
-            if net is not None:
-                weights, trans, _, _ = net.forward(patch, want_trans2=False)
-                out = ops.wls_fit(patch, weights, order, trans=trans if use_point_stn else None,
-                                  U=data_trans if dataset.use_pca else None, rad=rad)
-                weights_prop[s:s + c] = weights
-                trans_prop[s:s + c] = trans.reshape(c, 9)
+        t0 = tick("load", t0)
+        dense_knn = dataset.neighbor_search_method == 'k' and not dataset.sparse_patches and dataset.use_pca
+        if use_pipeline and dense_knn and (model is None or use_point_stn):
+            from .pipeline import NormalEstimator
+            est = NormalEstimator(pts, k, jet_order=order, mode="classic" if model is None else "DeepFit", model=model,
+                                  grid=grid)
+            extras = {}
+            normal_prop, curv64 = est.run(extras=extras, want_extras=("beta", "weights", "trans"))
+            beta_prop = extras["beta"]
+            curv_prop = curv64.float() if curv64 is not None else torch.zeros((n_patch, 2), dtype=torch.float32, device=dev)
+            if model is not None:
+                weights_prop, trans_prop = extras["weights"], extras["trans"].reshape(n_patch, 9)
             else:
-                out = ops.wls_fit(patch, None, order, U=data_trans if dataset.use_pca else None, rad=rad)
-            normal_prop[s:s + c] = out["n_world"] if "n_world" in out else out["n_local"]
-            beta_prop[s:s + c] = out["beta"]
-            if order > 1:
-                curv_prop[s:s + c] = out["curv_scaled"].float()     # the reference stores into a float32 buffer
-        if net is not None:
-            net.status()       # before anything is written: a pipeline time-out raises
+                weights_prop = torch.ones((n_patch, k), dtype=torch.float32, device=dev)
+                trans_prop = torch.eye(3, device=dev).reshape(1, 9).repeat(n_patch, 1)
+            est._pipe.close()
+        else:
+            net = model._network(dev, max_batch=batch) if model is not None else None
+            normal_prop = torch.zeros((n_patch, 3), dtype=torch.float32, device=dev)
+            curv_prop = torch.zeros((n_patch, 2), dtype=torch.float32, device=dev)
+            weights_prop = torch.ones((n_patch, k), dtype=torch.float32, device=dev)
+            beta_prop = torch.zeros((n_patch, ops.JET_M[order]), dtype=torch.float32, device=dev)
+            trans_prop = torch.eye(3, device=dev).reshape(1, 9).repeat(n_patch, 1)
+            for s in range(0, n_patch, batch):
+                c = min(batch, n_patch - s)
+                patch, data_trans, rad = dataset.patches(si, s, c)
+                if net is not None:
+                    weights, trans, _, _ = net.forward(patch, want_trans2=False)
+                    out = ops.wls_fit(patch, weights, order, trans=trans if use_point_stn else None,
+                                      U=data_trans if dataset.use_pca else None, rad=rad)
+                    weights_prop[s:s + c] = weights
+                    trans_prop[s:s + c] = trans.reshape(c, 9)
+                else:
+                    out = ops.wls_fit(patch, None, order, U=data_trans if dataset.use_pca else None, rad=rad)
+                normal_prop[s:s + c] = out["n_world"] if "n_world" in out else out["n_local"]
+                beta_prop[s:s + c] = out["beta"]
+                if order > 1:
+                    curv_prop[s:s + c] = out["curv_scaled"].float()     # the reference stores into a float32 buffer
+            if net is not None:
+                net.status()       # before anything is written: a pipeline time-out raises
+        t0 = tick("compute", t0)
         res = {"normals": normal_prop.cpu().numpy(), "curv": curv_prop.cpu().numpy(),
                "weights": weights_prop.cpu().numpy(), "beta": beta_prop.cpu().numpy(), "trans": trans_prop.cpu().numpy()}
-        results[name] = res
+        if keep_results:
+            results[name] = res
         if write:
             for ext, arr in res.items():
                 savetxt(os.path.join(output_dir, name + '.' + ext), arr)
             print('saved normals for ' + name)
+        tick("export", t0)
     return results
 
 

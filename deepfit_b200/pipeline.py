@@ -76,12 +76,14 @@ class NormalEstimator:
     _EXTRA_NAMES = ("beta", "info", "rad", "U", "weights", "trans", "trans2", "dirs_world")
 
     def run(self, begin: int = 0, end: Optional[int] = None, out_normals: Optional[torch.Tensor] = None,
-            out_curv: Optional[torch.Tensor] = None, extras: Optional[dict] = None, check: bool = True):
+            out_curv: Optional[torch.Tensor] = None, extras: Optional[dict] = None, check: bool = True,
+            want_extras: Optional[tuple] = None):
         """Normals f32 [Q,3] and curvatures f64 [Q,2] (k1<=k2, divided by the patch radius) for point
         indices [begin, end), through ``dfb_pipeline_run`` (one C call: chunk loop, workspace and the two-stream
         schedule live in the library).  ``extras`` (a dict) receives whole-range tensors ``beta / info / rad / U``
         (+ ``weights / trans / trans2`` in DeepFit mode, ``dirs_world`` for order >= 2) when given (config-3 style
-        full outputs); a key already present with a tensor is used as the output buffer.  ``check`` synchronises
+        full outputs; ``want_extras`` narrows the list -- trans2 alone is 16 KB per point); a key already present with a
+        tensor is used as the output buffer.  ``check`` synchronises
         once at the end and raises if any tensor-core pipeline of the network reported a time-out
         (``dfb_model_status``)."""
         end = self.n if end is None else int(end)
@@ -93,7 +95,9 @@ class NormalEstimator:
         if out_curv is not None:
             out["curv"] = out_curv
         if extras is not None:
-            for name in self._EXTRA_NAMES:
+            for name in (self._EXTRA_NAMES if want_extras is None else want_extras):
+                if name not in self._EXTRA_NAMES:
+                    raise ValueError("unknown output %r" % (name,))
                 if name in ("weights", "trans", "trans2") and self.mode != "DeepFit":
                     continue
                 if name == "dirs_world" and self.order < 2:

@@ -72,6 +72,17 @@ def _adversarial_clouds():
     yield "planar_sheet", np.concatenate([rng.random((20000, 2)), np.zeros((20000, 1))], 1).astype(np.float32), 100
     yield "collinear", np.stack([np.linspace(0, 1, 5000), np.zeros(5000), np.zeros(5000)], 1).astype(np.float32), 33
     yield "k1024", rng.normal(size=(20000, 3)).astype(np.float32), 1024
+    # sub-grids of heavy cells (csrc/knn.cu): blobs three and six orders of magnitude denser than their surroundings,
+    # queries on both sides of the heavy / light boundary; exact ties and duplicates inside a heavy cell; k = 512
+    nested = np.concatenate([rng.normal(scale=1.0, size=(20000, 3)), rng.normal(scale=0.05, size=(20000, 3)) + 0.3,
+                             rng.normal(scale=0.002, size=(20000, 3)) + 0.3, rng.normal(scale=0.0005, size=(6000, 3)) - 0.7])
+    yield "nested_density", nested.astype(np.float32), 256
+    yield "nested_density_k512", nested.astype(np.float32), 512
+    lat = (g.astype(np.float32) * 1e-4 + 0.5)
+    yield "heavy_cell_lattice_ties", np.concatenate([lat, lat[:1000], rng.random((8000, 3)).astype(np.float32)])[rng.permutation(13096)], 40
+    yield "heavy_cell_identical_points", np.concatenate([np.full((2000, 3), 0.25, np.float32), rng.random((6000, 3)).astype(np.float32)]), 300
+    sheet = np.concatenate([rng.random((40000, 2)) * 0.01 + 0.4, rng.normal(scale=1e-5, size=(40000, 1))], 1)
+    yield "dense_thin_sheet_in_sparse_box", np.concatenate([sheet, rng.random((4000, 3))]).astype(np.float32), 128
 
 
 @pytest.mark.parametrize("case", list(_adversarial_clouds()), ids=lambda c: c[0])
