@@ -743,11 +743,12 @@ __device__ __forceinline__ void block_cell(const KnnArgs& a, const GridParams& g
 }
 
 // E = register entries per lane of the final sort (32 * E = the power of two >= k); 0: shared-memory network only
-#ifdef DFB_KNN_MINB   // A/B builds only (tools/build_variant.sh)
-#define DFB_KNN_BOUNDS __launch_bounds__(kKnnWarps * 32, DFB_KNN_MINB)
-#else
-#define DFB_KNN_BOUNDS __launch_bounds__(kKnnWarps * 32)
+// 4 CTAs per SM = 128 registers: left to itself the compiler settles on 96 registers and spills 156 bytes in the cell
+// scan (measured -3 % on uniform clouds, profiles/r2_knn_subgrid_ab.log); DFB_KNN_MINB overrides for A/B builds
+#ifndef DFB_KNN_MINB
+#define DFB_KNN_MINB 4
 #endif
+#define DFB_KNN_BOUNDS __launch_bounds__(kKnnWarps * 32, DFB_KNN_MINB)
 template <int E>
 __global__ void DFB_KNN_BOUNDS knn_kernel(KnnArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
