@@ -9,8 +9,9 @@ diagonal, random subsample when the ball holds more than ``points_per_patch`` po
 supported for one scale; the ball is the exact set ``cKDTree.query_ball_point`` returns, but its elements are
 taken in ascending index order where the reference takes the tree's traversal order, so the seeded
 ``RandomState`` subsample picks different members of the same ball (documented deviation: the traversal
-order of scipy's tree cannot be reproduced).  Point tuples, density jitter and ground-truth features are
-training-time options and raise.  Unlike the reference nothing is written next to the input data (it drops
+order of scipy's tree cannot be reproduced).  Ground-truth patch features ('normal', 'neighbor_normals',
+'max_curvature', 'min_curvature', rotated into the PCA frame like dataset.py:368-372) come with ``items()``, the
+batched ``__getitem__``.  Point tuples and density jitter are training-time options and raise.  Unlike the reference nothing is written next to the input data (it drops
 ``.npy`` copies into the dataset directory, dataset.py:227-264).
 """
 from __future__ import annotations
@@ -41,6 +42,18 @@ class PointcloudPatchDataset:
         # rng for picking points in a patch, dataset.py:217-220
         self.seed = int(np.random.randint(0, 2**32 - 1)) if seed is None else int(seed)
         self.rng = np.random.RandomState(self.seed)
+        # ground-truth features returned next to the patch, dataset.py:197-205
+        self.patch_features = tuple(patch_features)
+        self.include_normals = self.include_curvatures = self.include_neighbor_normals = False
+        for pfeat in self.patch_features:
+            if pfeat == 'normal':
+                self.include_normals = True
+            elif pfeat in ('max_curvature', 'min_curvature'):
+                self.include_curvatures = True
+            elif pfeat == 'neighbor_normals':
+                self.include_neighbor_normals = True
+            else:
+                raise ValueError('Unknown patch feature: %s' % (pfeat))
         if center != 'point':
             raise NotImplementedError("only center='point' is built (the pretrained configuration)")
         if point_tuple != 1 or point_count_std != 0.0:
@@ -64,6 +77,7 @@ class PointcloudPatchDataset:
                 self.shape_patch_count.append(None)   # filled when the shape is loaded
         self._loaded = (-1, None, None)
         self._bbdiag = {}
+        self._gt = {}
 
     def __len__(self):
         return sum(self._count(i) for i in range(len(self.shape_names)))
@@ -82,6 +96,13 @@ class PointcloudPatchDataset:
                 self._loaded[2].close()
             self._loaded = (shape_ind, gpu, ops.Grid(gpu))
             self._bbdiag[shape_ind] = float(np.linalg.norm(pts.max(0) - pts.min(0), 2))   # dataset.py:262
+            # ground-truth normals / curvatures of the shape (dataset.py:13-34, 236-247), only when a feature asks for them
+            self._gt = {}
+            base = os.path.join(self.root, self.shape_names[shape_ind])
+            if self.include_normals or self.include_neighbor_normals:
+                self._gt["normals"] = torch.from_numpy(np.ascontiguousarray(load_xyz(base + '.normals'))).to(self.device)
+            if self.include_curvatures:
+                self._gt["curv"] = torch.from_numpy(np.loadtxt(base + '.curv').astype('float32').reshape(-1, 2)).to(self.device)
             if self.shape_patch_count[shape_ind] is None:
                 self.shape_patch_count[shape_ind] = int(gpu.shape[0])
         return self._loaded[1], self._loaded[2]
@@ -90,15 +111,17 @@ class PointcloudPatchDataset:
         p = self._pidx[shape_ind]
         return None if p is None else torch.from_numpy(p.astype(np.int32)).to(self.device)
 
-    def patches(self, shape_ind, start, count):
+    def patches(self, shape_ind, start, count, return_index=False):
         """Patches ``start .. start+count`` of a shape (in ``.pidx`` order when sparse):
         (patch f32 [B,3,k], trans f32 [B,3,3], patch_scale f64 [B]) -- the reference returns [k,3] per item
-        and its callers transpose (test_c_est.py:131)."""
+        and its callers transpose (test_c_est.py:131).  ``return_index`` appends the neighbour indices i32 [B,k] and
+        the number of real (non-padding) rows per patch i32 [B]."""
         pts, grid = self.load_shape(shape_ind)
         centres = self.centres(shape_ind)
         k = self.points_per_patch
         if self.neighbor_search_method == 'r':
-            return self._ball_patches(shape_ind, pts, grid, centres, start, count)
+            out = self._ball_patches(shape_ind, pts, grid, centres, start, count)
+            return out if return_index else out[:3]
         if centres is None:
             idx, rad = grid.query(k, q_begin=start, q_count=count)
             patch, trans = ops.patch_pca(pts, idx, rad, q_begin=start, pca=self.use_pca)
@@ -106,7 +129,33 @@ class PointcloudPatchDataset:
             q = centres[start:start + count].contiguous()
             idx, rad = grid.query(k, query=q)
             patch, trans = ops.patch_pca(pts, idx, rad, query=q, pca=self.use_pca)
+        if return_index:
+            return patch, trans, rad, idx, torch.full((count,), k, dtype=torch.int32, device=self.device)
         return patch, trans, rad
+
+    def items(self, shape_ind, start, count):
+        """The batched ``__getitem__`` of the reference (dataset.py:268-417) for patches ``start .. start+count`` of a
+        shape: ``(patch_pts f32 [B,k,3],) + features in patch_features order + (trans f32 [B,3,3], patch_scale f64 [B])``.
+        Features: 'normal' f32 [B,3] and 'neighbor_normals' f32 [B,k,3] are the shape's ground-truth normals of the centre /
+        of the patch points, rotated into the PCA frame when ``use_pca`` (:368-372; padding rows of ball patches stay zero);
+        'max_curvature' / 'min_curvature' f32 [B,1] are the ground-truth curvatures times the absolute patch radius (:343-349)."""
+        patch, trans, scale, idx, valid = self.patches(shape_ind, start, count, return_index=True)
+        centres = self.centres(shape_ind)
+        c = (torch.arange(start, start + count, device=self.device) if centres is None else centres[start:start + count]).long()
+        feats = {}
+        if self.include_normals:
+            n = self._gt["normals"][c]
+            feats['normal'] = torch.bmm(n[:, None, :], trans)[:, 0] if self.use_pca else n
+        if self.include_neighbor_normals:
+            nn = self._gt["normals"][idx.long()]
+            nn = nn * (torch.arange(self.points_per_patch, device=self.device)[None, :] < valid[:, None])[..., None]
+            feats['neighbor_normals'] = torch.bmm(nn, trans) if self.use_pca else nn
+        if self.include_curvatures:
+            if self.patch_radius is None:
+                raise ValueError("curvature features are scaled by patch_radius x bounding-box diagonal: pass patch_radius")
+            cv = self._gt["curv"][c] * float(self._bbdiag[shape_ind] * self.patch_radius[0])
+            feats['max_curvature'], feats['min_curvature'] = cv[:, 0:1], cv[:, 1:2]
+        return (patch.transpose(1, 2).contiguous(),) + tuple(feats[f] for f in self.patch_features) + (trans, scale)
 
 
     def _ball_patches(self, shape_ind, pts, grid, centres, start, count):
@@ -143,7 +192,7 @@ class PointcloudPatchDataset:
             patch, trans = ops.patch_pca(pts, idx, rad, q_begin=start, pca=self.use_pca, valid=valid_t)
         else:
             patch, trans = ops.patch_pca(pts, idx, rad, query=q, pca=self.use_pca, valid=valid_t)
-        return patch, trans, rad
+        return patch, trans, rad, idx, valid_t
 
 
 def estimate_shapes(dataset: PointcloudPatchDataset, model: Optional[DeepFit], output_dir: str, jet_order: int = 3,

@@ -142,6 +142,22 @@ def dataset_item(points32: np.ndarray, center: int, k: int, idx=None, dist=None)
     return aligned.t().contiguous(), U, rad
 
 
+def pcpnet_patch_features(normals32, curv32, center: int, idx, U: torch.Tensor | None, patch_radius_abs: float):
+    """Ground-truth features PointcloudPatchDataset.__getitem__ returns next to a patch (dataset.py:338-349, 368-372):
+    normal f32 [3] and neighbor_normals f32 [k,3] = the shape's normals of the centre / of the patch points, times the
+    PCA frame ``U`` when use_pca; (max_curvature, min_curvature) = curv[center] * absolute patch radius."""
+    out = {}
+    if normals32 is not None:
+        n = torch.from_numpy(normals32[center, :])
+        nn = torch.from_numpy(normals32[np.asarray(idx, dtype=np.int64), :])
+        out["normal"] = torch.matmul(n, U) if U is not None else n
+        out["neighbor_normals"] = torch.matmul(nn, U) if U is not None else nn
+    if curv32 is not None:
+        c = torch.from_numpy(curv32[center, :]) * patch_radius_abs
+        out["max_curvature"], out["min_curvature"] = c[0:1], c[1:2]
+    return out
+
+
 # ----------------------------------------------------------------------------------------
 # Stage 3: the weight network -- models/DeepFit.py:157-441 (eval-mode BatchNorm)
 # ----------------------------------------------------------------------------------------

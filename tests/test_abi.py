@@ -98,3 +98,40 @@ def test_text_io_is_byte_compatible_with_numpy(tmp_path):
     assert got.shape == ref.shape and np.array_equal(got, ref)
     np.savetxt(tmp_path / "sci.xyz", pts * 1e-3)           # scientific notation, 18 digits
     assert np.array_equal(tu.loadtxt_f32(tmp_path / "sci.xyz"), np.loadtxt(tmp_path / "sci.xyz").astype("float32"))
+
+
+def test_savetxt_exact_formatter_rounding_cases(tmp_path):
+    """'%.18e' without printf (csrc/textio.cu: exact 128-bit integer arithmetic on float32-origin values): random bit
+    patterns over the whole fast range, every neighbour of a power of ten, exponents where the rounding carries, signed
+    zeros, and the fallbacks (subnormals, huge values, nan / inf, true doubles, three-digit exponents)."""
+    import numpy as np
+    from deepfit_b200 import tutorial_utils as tu
+    rng = np.random.default_rng(7)
+
+    def same(a):
+        tu.savetxt(tmp_path / "ours.txt", a)
+        np.savetxt(tmp_path / "numpy.txt", a)
+        return open(tmp_path / "ours.txt", "rb").read() == open(tmp_path / "numpy.txt", "rb").read()
+
+    bits = rng.integers(0x2c800000, 0x4c000000, size=600_000, dtype=np.uint32)
+    bits[::2] |= 0x80000000
+    assert same(bits.view(np.float32).reshape(-1, 3))
+    near = []
+    for kexp in range(-12, 9):
+        v = np.float32(10.0 ** kexp)
+        lo = hi = v
+        near.append(v)
+        for _ in range(5):
+            lo = np.nextafter(lo, np.float32(0)); hi = np.nextafter(hi, np.float32(np.inf))
+            near += [lo, hi]
+    near = np.array(near, dtype=np.float32)
+    assert same(np.resize(near, (len(near) // 3) * 3).reshape(-1, 3))
+    for e in (113, 127, 149):       # a stride through every mantissa of three binades
+        b = (np.uint32(e) << np.uint32(23)) | np.arange(0, 1 << 23, 37, dtype=np.uint32)
+        a = b.view(np.float32)
+        assert same(np.resize(a, (len(a) // 3) * 3).reshape(-1, 3))
+    special = np.array([[0.0, -0.0, 1.0], [0.1, 0.5, -2.0], [1e-38, 3e38, 1.0 / 3], [16777215, 16777216, 8388608],
+                        [9.9999999e5, 0.99999994, 1e-7], [2.0 ** -37, 2.0 ** -38, 2.0 ** 24], [1e-45, -1e-45, 65504.0]], dtype=np.float32)
+    assert same(special)
+    assert same(special.astype(np.float64))                                   # doubles that are exact float32 values
+    assert same(np.array([[np.nan, np.inf, -np.inf], [1e-300, -1e300, 5e-324], [1e-99, 9.999e-100, 1e100], [0.1, 1.0 / 3, 1e99]]))

@@ -107,3 +107,41 @@ def test_config3_dense_pipeline_equals_stage_loop(tmp_path):
     for name in names:
         for key in ("normals", "curv", "weights", "beta", "trans"):
             assert np.array_equal(a[name][key], b[name][key]), (name, key)
+
+
+@pytest.mark.parametrize("use_pca", [True, False])
+def test_pcpnet_items_with_ground_truth_features(tmp_path, use_pca):
+    """items() = the reference's batched __getitem__ (dataset.py:268-417): ground-truth normal, neighbour normals and
+    curvatures next to the patch, rotated into the patch's PCA frame, against the oracle restatement (which is pinned
+    on the unmodified reference by tests/test_oracle.py::test_oracle_equals_reference_pcpnet_patch_features)."""
+    from deepfit_b200 import pcpnet, synthetic
+    from oracle import deepfit_oracle as O
+    root = str(tmp_path / "pclouds")
+    names = synthetic.write_pcpnet_like(root, n_shapes=2, n_points=5000, n_sparse=64)
+    rng = np.random.default_rng(0)
+    for name in names:
+        np.savetxt(root + "/" + name + ".curv", rng.normal(size=(5000, 2)), fmt="%.6f")
+    feats = ['normal', 'max_curvature', 'neighbor_normals', 'min_curvature']
+    ds = pcpnet.PointcloudPatchDataset(root, "testset_synthetic.txt", patch_radius=[0.05], points_per_patch=256,
+                                       patch_features=feats, use_pca=use_pca, sparse_patches=True, neighbor_search_method='k')
+    with pytest.raises(ValueError):
+        pcpnet.PointcloudPatchDataset(root, "testset_synthetic.txt", patch_features=['colour'])
+    for si, name in enumerate(names):
+        pts = np.loadtxt(root + "/" + name + ".xyz").astype("float32")
+        nrm = np.loadtxt(root + "/" + name + ".normals").astype("float32")
+        cur = np.loadtxt(root + "/" + name + ".curv").astype("float32")
+        pidx = np.loadtxt(root + "/" + name + ".pidx").astype("int64")
+        rad_abs = float(np.linalg.norm(pts.max(0) - pts.min(0), 2)) * 0.05
+        patch, normal, cmax, nn, cmin, trans, scale = ds.items(si, 0, 64)
+        assert patch.shape == (64, 256, 3) and nn.shape == (64, 256, 3) and cmax.shape == (64, 1) and trans.shape == (64, 3, 3)
+        p2, t2, s2, idx, valid = ds.patches(si, 0, 64, return_index=True)
+        assert torch.equal(patch, p2.transpose(1, 2)) and torch.equal(trans, t2) and bool((valid == 256).all())
+        if not use_pca:
+            assert torch.equal(trans, torch.eye(3, device="cuda").expand(64, 3, 3))
+        ref_idx, ref_dist = O.knn_bruteforce(pts, pidx[:64], 256)
+        assert np.array_equal(idx.cpu().numpy(), ref_idx.astype(np.int32))
+        for j in range(64):
+            f = O.pcpnet_patch_features(nrm, cur, int(pidx[j]), ref_idx[j], trans[j].cpu() if use_pca else None, rad_abs)
+            assert torch.allclose(normal[j].cpu(), f["normal"], atol=1e-6, rtol=0)
+            assert torch.allclose(nn[j].cpu(), f["neighbor_normals"], atol=1e-6, rtol=0)
+            assert torch.equal(cmax[j].cpu(), f["max_curvature"]) and torch.equal(cmin[j].cpu(), f["min_curvature"])

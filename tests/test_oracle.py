@@ -148,3 +148,37 @@ def test_oracle_equals_reference_pcpnet_dataset(tmp_path):
         p, U, rad = O.dataset_item(pts, int(pidx[pi]), 256)
         assert rad == float(scale)
         assert torch.equal(p.t(), patch) and torch.equal(U, trans)
+
+
+@pytest.mark.skipif(not shims.reference_available(), reason="/root/reference is only present in the authoring container")
+def test_oracle_equals_reference_pcpnet_patch_features(tmp_path):
+    """dataset.py:338-372: ground-truth normal / neighbour normals / curvatures returned with a patch."""
+    import sys
+    from deepfit_b200 import synthetic
+    shims.apply_shims()
+    root = str(tmp_path)
+    names = synthetic.write_pcpnet_like(root, n_shapes=1, n_points=3000, n_sparse=20)
+    rng = np.random.default_rng(0)
+    np.savetxt(tmp_path / (names[0] + ".curv"), rng.normal(size=(3000, 2)), fmt="%.6f")
+    sys.path.insert(0, shims.REFERENCE_ROOT)
+    try:
+        import importlib
+        ref_dataset = importlib.import_module("dataset")
+    finally:
+        sys.path.remove(shims.REFERENCE_ROOT)
+    feats = ['normal', 'neighbor_normals', 'max_curvature', 'min_curvature']
+    ds = ref_dataset.PointcloudPatchDataset(root=root, shape_list_filename="testset_synthetic.txt", patch_radius=[0.05],
+                                            points_per_patch=256, patch_features=feats, seed=1, use_pca=True, center="point",
+                                            point_tuple=1, cache_capacity=2, sparse_patches=True, neighbor_search_method="k")
+    pts = np.loadtxt(tmp_path / (names[0] + ".xyz")).astype("float32")
+    nrm = np.loadtxt(tmp_path / (names[0] + ".normals")).astype("float32")
+    cur = np.loadtxt(tmp_path / (names[0] + ".curv")).astype("float32")
+    pidx = np.loadtxt(tmp_path / (names[0] + ".pidx")).astype("int64")
+    rad_abs = float(np.linalg.norm(pts.max(0) - pts.min(0), 2)) * 0.05
+    for gi in (0, 5, 19):
+        patch, normal, nn, cmax, cmin, trans, scale = ds[gi]
+        idx, dist = O.knn_ckdtree(pts, [int(pidx[gi])], 256)
+        f = O.pcpnet_patch_features(nrm, cur, int(pidx[gi]), idx[0], trans, rad_abs)
+        assert torch.equal(f["normal"], normal) and torch.equal(f["max_curvature"], cmax) and torch.equal(f["min_curvature"], cmin)
+        # the neighbour order of the tree query is arbitrary among ties only; compare as sets of rows
+        assert torch.equal(torch.sort(f["neighbor_normals"], dim=0)[0], torch.sort(nn, dim=0)[0])
