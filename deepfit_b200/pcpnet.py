@@ -92,9 +92,14 @@ class PointcloudPatchDataset:
         if self._loaded[0] != shape_ind:
             pts = load_xyz(os.path.join(self.root, self.shape_names[shape_ind] + '.xyz'))
             gpu = torch.from_numpy(np.ascontiguousarray(pts, dtype=np.float32)).to(self.device)
-            if self._loaded[2] is not None:
-                self._loaded[2].close()
-            self._loaded = (shape_ind, gpu, ops.Grid(gpu))
+            grid = self._loaded[2]
+            if grid is not None and grid.n == int(gpu.shape[0]):
+                grid.update(gpu)            # same size (PCPNet's 100 k-point shapes): rebuilt in place, nothing allocated
+            else:
+                if grid is not None:
+                    grid.close()
+                grid = ops.Grid(gpu)
+            self._loaded = (shape_ind, gpu, grid)
             self._bbdiag[shape_ind] = float(np.linalg.norm(pts.max(0) - pts.min(0), 2))   # dataset.py:262
             # ground-truth normals / curvatures of the shape (dataset.py:13-34, 236-247), only when a feature asks for them
             self._gt = {}
@@ -197,7 +202,7 @@ class PointcloudPatchDataset:
 
 def estimate_shapes(dataset: PointcloudPatchDataset, model: Optional[DeepFit], output_dir: str, jet_order: int = 3,
                     batch: int = 4096, use_point_stn: bool = True, write: bool = True, timings: Optional[dict] = None,
-                    use_pipeline: bool = True, keep_results: bool = True):
+                    use_pipeline: bool = True, keep_results: bool = True, on_shape=None):
     """Run every shape of the dataset and export the five per-shape files of test_c_est.py:201-210.
     ``model=None`` runs the classic unweighted fit (weights file of ones, identity trans).
     Returns {shape_name: dict of numpy arrays} (empty when ``keep_results`` is False: 20 dense 100 k-point shapes
@@ -207,7 +212,8 @@ def estimate_shapes(dataset: PointcloudPatchDataset, model: Optional[DeepFit], o
     (``dfb_pipeline_run`` with every optional output: one call per shape, 16 384-query chunks, two streams);
     sparse ``.pidx`` centres, ball-query patches and ``use_pca=False`` take the stage-by-stage loop below.  Both give the
     same bits (tests/test_gpu_config3.py).  ``timings`` (a dict) accumulates seconds spent in ``load`` (text -> device +
-    grid), ``compute`` (kNN ... curvature, device-synchronised) and ``export`` (device -> host + text files)."""
+    grid), ``compute`` (kNN ... curvature, device-synchronised) and ``export`` (device -> host + text files).
+    ``on_shape(name, arrays)`` is called after each shape's files are written (outside the timings)."""
     import time
     if write:
         os.makedirs(output_dir, exist_ok=True)
@@ -222,6 +228,18 @@ def estimate_shapes(dataset: PointcloudPatchDataset, model: Optional[DeepFit], o
             timings[name] = timings.get(name, 0.0) + time.perf_counter() - t0
         return time.perf_counter()
 
+    est = None          # the C pipeline and its workspace are kept while consecutive shapes share their grid object
+    host = {}           # pinned staging buffers of the five outputs, grown on demand
+
+    def to_host(key, t):
+        t = t.contiguous()
+        buf = host.get(key)
+        if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
+            buf = host[key] = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+        view = buf[:t.numel()].view(t.shape)
+        view.copy_(t, non_blocking=True)
+        return view
+
     for si, name in enumerate(dataset.shape_names):
         t0 = time.perf_counter()
         pts, grid = dataset.load_shape(si)
@@ -230,8 +248,12 @@ def estimate_shapes(dataset: PointcloudPatchDataset, model: Optional[DeepFit], o
         dense_knn = dataset.neighbor_search_method == 'k' and not dataset.sparse_patches and dataset.use_pca
         if use_pipeline and dense_knn and (model is None or use_point_stn):
             from .pipeline import NormalEstimator
-            est = NormalEstimator(pts, k, jet_order=order, mode="classic" if model is None else "DeepFit", model=model,
-                                  grid=grid)
+            if est is None or est.grid is not grid:
+                if est is not None and getattr(est, "_pipe", None) is not None:
+                    est._pipe.close()
+                est = NormalEstimator(pts, k, jet_order=order, mode="classic" if model is None else "DeepFit", model=model,
+                                      grid=grid)
+            est.points = pts
             extras = {}
             normal_prop, curv64 = est.run(extras=extras, want_extras=("beta", "weights", "trans"))
             beta_prop = extras["beta"]
@@ -241,7 +263,6 @@ def estimate_shapes(dataset: PointcloudPatchDataset, model: Optional[DeepFit], o
             else:
                 weights_prop = torch.ones((n_patch, k), dtype=torch.float32, device=dev)
                 trans_prop = torch.eye(3, device=dev).reshape(1, 9).repeat(n_patch, 1)
-            est._pipe.close()
         else:
             net = model._network(dev, max_batch=batch) if model is not None else None
             normal_prop = torch.zeros((n_patch, 3), dtype=torch.float32, device=dev)
@@ -267,10 +288,12 @@ def estimate_shapes(dataset: PointcloudPatchDataset, model: Optional[DeepFit], o
             if net is not None:
                 net.status()       # before anything is written: a pipeline time-out raises
         t0 = tick("compute", t0)
-        res = {"normals": normal_prop.cpu().numpy(), "curv": curv_prop.cpu().numpy(),
-               "weights": weights_prop.cpu().numpy(), "beta": beta_prop.cpu().numpy(), "trans": trans_prop.cpu().numpy()}
+        res = {"normals": to_host("normals", normal_prop), "curv": to_host("curv", curv_prop), "weights": to_host("weights", weights_prop),
+               "beta": to_host("beta", beta_prop), "trans": to_host("trans", trans_prop)}
+        torch.cuda.synchronize(dev)
+        res = {key: v.numpy() for key, v in res.items()}      # views of the pinned buffers, valid until the next shape
         if keep_results:
-            results[name] = res
+            results[name] = {key: v.copy() for key, v in res.items()}
         if write:
             for ext, arr in res.items():
                 savetxt(os.path.join(output_dir, name + '.' + ext), arr)

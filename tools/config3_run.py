@@ -48,25 +48,23 @@ def main():
     one.shape_patch_count = one.shape_patch_count[:1]
     pcpnet.estimate_shapes(one, model, out_dir, write=False, keep_results=False)
     timings = {}
-    exported = 0
-    finite = True
-    t0 = time.perf_counter()
-    # shape by shape, so that the 1.3 GB of exports per shape can be removed as we go
-    for si in range(len(names)):
-        sub = pcpnet.PointcloudPatchDataset(os.path.join(args.root, "pclouds"), "testset_synthetic.txt", points_per_patch=256,
-                                            use_pca=True, sparse_patches=False, neighbor_search_method='k', device=dev)
-        sub.shape_names = [names[si]]
-        sub.shape_patch_count = [None]
-        sub._pidx = [None]
-        res = pcpnet.estimate_shapes(sub, model, out_dir, write=not args.no_write, timings=timings, keep_results=True)
-        r = res[names[si]]
-        finite = finite and all(np.isfinite(r[key]).all() for key in r)
+    state = {"exported": 0, "finite": True, "other_s": 0.0}
+
+    def on_shape(name, arrays):
+        # not part of the path: the run's own sanity check, and the 0.7 GB of exports per shape removed as we go
+        t = time.perf_counter()
+        state["finite"] = state["finite"] and all(bool(np.isfinite(a).all()) for a in arrays.values())
         if not args.no_write:
             for ext in ("normals", "curv", "weights", "beta", "trans"):
-                f = os.path.join(out_dir, names[si] + "." + ext)
-                exported += os.path.getsize(f)
+                f = os.path.join(out_dir, name + "." + ext)
+                state["exported"] += os.path.getsize(f)
                 os.remove(f)
-    wall = time.perf_counter() - t0
+        state["other_s"] += time.perf_counter() - t
+
+    t0 = time.perf_counter()
+    pcpnet.estimate_shapes(ds, model, out_dir, write=not args.no_write, timings=timings, keep_results=False, on_shape=on_shape)
+    exported, finite = state["exported"], state["finite"]
+    wall = time.perf_counter() - t0 - state["other_s"]
     model._net.status()
     n_total = args.shapes * args.points
     print(json.dumps({
