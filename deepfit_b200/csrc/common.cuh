@@ -46,6 +46,10 @@ int wls_fit_impl(const float* d_patch, const float* d_weights, const float* d_tr
                  double* d_curv_scaled, float* d_dirs, float* d_dirs_world, int32_t* d_info, int keep_qstn, dfb_stream stream,
                  const int32_t* d_out_row = nullptr, int64_t out_base = 0);
 const float* grid_points(const dfb_grid* g);   // device copy of the cloud, original order, f32[n,3]
+const float4* grid_points4(const dfb_grid* g); // the same values as float4 (x, y, z, 0): one 16-byte load per gathered point
+int patch_pca_impl(const float* d_points, const float4* d_points4, int64_t n_points, const int32_t* d_idx, const int32_t* d_valid,
+                   const int32_t* d_query, int64_t q_begin, int64_t q_count, int32_t k, const double* d_rad, int32_t scale_by_rad,
+                   float* d_patch, float* d_U, double* d_cov, dfb_stream stream);
 long long grid_size(const dfb_grid* g);
 int model_k(const dfb_model* m);
 

@@ -269,6 +269,14 @@ __global__ void scatter_kernel(const float* __restrict__ pts, long long n, const
     sorted[pos] = make_float4(pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2], __int_as_float((int)i));
 }
 
+// After the build the scratch array is free: it keeps the cloud as float4 in ORIGINAL order (grid_points4), so that
+// the patch gather of stage 2 costs one 16-byte load per neighbour instead of three 4-byte ones.
+__global__ void points4_kernel(const float* __restrict__ pts, long long n, float4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = make_float4(pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2], 0.f);
+}
+
 // ---- second sort: the points of heavy cells by sub-cell code
 struct SubBuild {
     const float4* in;             // sorted by finest dense cell (scatter_kernel)
@@ -1123,7 +1131,8 @@ struct dfb_grid {
     long long ntile = 0;
     float* pts = nullptr;              // device copy, original order
     float4* sorted = nullptr;          // device, Morton order (x, y, z, original index), heavy cells by sub-cell code too
-    float4* sorted_tmp = nullptr;      // device, build scratch: sorted by finest dense cell only
+    float4* sorted_tmp = nullptr;      // device, build scratch (sorted by finest dense cell only); after the build: the
+                                       // cloud as float4 in original order (grid_points4)
     unsigned long long* ht = nullptr;  // device, sub-grid hash
     uint32_t ht_size = 0;
     uint32_t* pool = nullptr;          // device, sub-grid tables
@@ -1163,7 +1172,8 @@ int grid_build(dfb_grid* g, const float* d_points, cudaStream_t st) {
     sub_count_kernel<<<nb, 256, 0, st>>>(sb);
     sub_scan_kernel<<<(unsigned)std::min<long long>((long long)g->heavy_cap, (long long)sm_count() * 8), 256, 0, st>>>(sb);
     sub_scatter_kernel<<<nb, 256, 0, st>>>(sb);
-    note_launch(11);
+    points4_kernel<<<nb, 256, 0, st>>>(g->pts, n, g->sorted_tmp);
+    note_launch(12);
     return check_cuda(cudaGetLastError(), "grid build kernels", __FILE__, __LINE__);
 }
 }  // namespace
@@ -1171,6 +1181,7 @@ int grid_build(dfb_grid* g, const float* d_points, cudaStream_t st) {
 
 namespace dfb {
 const float* grid_points(const dfb_grid* g) { return g->pts; }
+const float4* grid_points4(const dfb_grid* g) { return g->sorted_tmp; }
 long long grid_size(const dfb_grid* g) { return g->n; }
 }  // namespace dfb
 

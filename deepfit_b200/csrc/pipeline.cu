@@ -11,12 +11,21 @@
 // neighbourhood buffers are double-buffered and handed over with events, so the search fills the SMs the persistent
 // tensor-core kernels leave idle in their tails instead of serialising in front of them.
 //
+// Classic mode (no network) splits stage 2: the gather kernel writes the centred / scaled patch UNROTATED plus its
+// covariance, a one-thread-per-patch kernel turns the covariance into the PCA frame U (the serial fp64 Jacobi sweeps ran
+// 32 times redundantly per patch inside the fused warp-per-patch kernel), and the jet-fit kernel applies U while it reads
+// the patch, through the per-patch rotation input it has for the QSTN -- the same fmaf chain as the fused kernel's, so
+// the results are bit-identical (DFB_PIPE_FUSED_PCA=1 restores the fused kernel for A/B runs).  In DeepFit mode the
+// network needs the rotated patch, so the fused kernel stays.  Both gather through the grid's float4 copy of the cloud.
+//
 // Visiting order: queries are independent, so the range is walked in the grid's spatial (Morton) order
 // (dfb_grid_morton_order) -- consecutive queries then share their neighbourhood cells, which dfb_knn's level and radius
 // hints turn into 1.5x the search rate -- and every result is written to its FILE-order row (the jet-fit kernel scatters
 // its own outputs; the pass-through outputs go through a row-scatter kernel).  DFB_PIPE_FILE_ORDER restores the
 // reference's visiting order (tutorial/compute_normals.py:56, DataLoader without shuffle); results are bit-identical.
 #include "common.cuh"
+
+#include <stdlib.h>
 
 namespace {
 // dst[(out_row[i] - base) * row + j] = src[i * row + j]
@@ -51,6 +60,8 @@ struct dfb_pipeline {
     double* rad[2] = {nullptr, nullptr};
     float* patch[2] = {nullptr, nullptr};
     float* U[2] = {nullptr, nullptr};
+    double* cov[2] = {nullptr, nullptr};   // classic mode: [chunk,6] patch covariances (split stage 2)
+    bool split_pca = false, gather4 = true;
     float* weights = nullptr;     // [chunk,k]   (network -> jet fit, caller's stream only)
     float* trans = nullptr;       // [chunk,9]
     float* trans2 = nullptr;      // [chunk,4096] staging, only when trans2 is requested in Morton order
@@ -66,6 +77,7 @@ extern "C" int dfb_pipeline_destroy(dfb_pipeline* p) {
         cudaFree(p->rad[b]);
         cudaFree(p->patch[b]);
         cudaFree(p->U[b]);
+        cudaFree(p->cov[b]);
         if (p->ev_ready[b]) cudaEventDestroy(p->ev_ready[b]);
         if (p->ev_free[b]) cudaEventDestroy(p->ev_free[b]);
     }
@@ -100,6 +112,12 @@ extern "C" int dfb_pipeline_create(const dfb_grid* grid, dfb_model* model, int32
     p->order = order;
     p->chunk = chunk > 0 ? chunk : (model ? 16384 : 262144);
     p->flags = flags;
+    {
+        const char* e1 = getenv("DFB_PIPE_FUSED_PCA");
+        p->split_pca = model == nullptr && !(e1 && e1[0] == '1');
+        const char* e2 = getenv("DFB_PIPE_GATHER3");      // A/B: gather through the f32[n,3] array (three loads per point)
+        p->gather4 = !(e2 && e2[0] == '1');
+    }
     cudaError_t e = cudaGetDevice(&p->device);
     int lo = 0, hi = 0;
     if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least priority
@@ -113,6 +131,7 @@ extern "C" int dfb_pipeline_create(const dfb_grid* grid, dfb_model* model, int32
         if (e == cudaSuccess) e = cudaMalloc(&p->rad[b], c * sizeof(double));
         if (e == cudaSuccess) e = cudaMalloc(&p->patch[b], c * 3 * k * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&p->U[b], c * 9 * sizeof(float));
+        if (e == cudaSuccess && p->split_pca) e = cudaMalloc(&p->cov[b], c * 6 * sizeof(double));
     }
     if (e == cudaSuccess && model) {
         e = cudaMalloc(&p->weights, c * k * sizeof(float));
@@ -142,6 +161,7 @@ extern "C" int dfb_pipeline_run(dfb_pipeline* p, int64_t q_begin, int64_t q_end,
     static const int kM[5] = {0, 3, 6, 10, 15};
     const int M = kM[p->order];
     const float* pts = grid_points(p->grid);
+    const float4* pts4 = p->gather4 ? grid_points4(p->grid) : nullptr;
     const long long n_pts = grid_size(p->grid);
     const long long n_chunks = (q_end - q_begin + p->chunk - 1) / p->chunk;
 
@@ -171,7 +191,8 @@ extern "C" int dfb_pipeline_run(dfb_pipeline* p, int64_t q_begin, int64_t q_end,
         const int32_t* ql = morton ? p->qorder + (s - q_begin) : nullptr;
         int rc = dfb_knn(p->grid, ql, s, c, k, p->idx[b], nullptr, p->rad[b], p->side);
         if (rc) return rc;
-        rc = dfb_patch_pca(pts, n_pts, p->idx[b], ql, s, c, k, p->rad[b], 1, p->patch[b], p->U[b], p->side);
+        rc = patch_pca_impl(pts, pts4, n_pts, p->idx[b], nullptr, ql, s, c, k, p->rad[b], 1, p->patch[b], p->U[b],
+                            p->split_pca ? p->cov[b] : nullptr, p->side);
         if (rc) return rc;
         DFB_CUDA(cudaEventRecord(p->ev_ready[b], p->side));
         return 0;
@@ -206,10 +227,11 @@ extern "C" int dfb_pipeline_run(dfb_pipeline* p, int64_t q_begin, int64_t q_end,
             }
         }
         const long long oo = morton ? 0 : off;   // with a row list the jet fit takes the base pointers
-        rc = wls_fit_impl(p->patch[b], w, tr, p->U[b], p->rad[b], c, k, p->order, o->d_beta ? o->d_beta + oo * M : nullptr, nullptr,
+        // split stage 2 (classic): the patch is unrotated, U enters as the rotation applied on the fly and undone on the outputs
+        rc = wls_fit_impl(p->patch[b], w, p->split_pca ? p->U[b] : tr, p->split_pca ? nullptr : p->U[b], p->rad[b], c, k, p->order, o->d_beta ? o->d_beta + oo * M : nullptr, nullptr,
                           o->d_normals + oo * 3, nullptr, (p->order > 1 && o->d_curv) ? o->d_curv + oo * 2 : nullptr, nullptr,
                           o->d_dirs_world ? o->d_dirs_world + oo * 6 : nullptr, o->d_info ? o->d_info + oo : nullptr,
-                          (p->flags & DFB_PIPE_KEEP_QSTN) ? 1 : 0, main_st, rows, q_begin);
+                          (!p->split_pca && (p->flags & DFB_PIPE_KEEP_QSTN)) ? 1 : 0, main_st, rows, q_begin);
         if (rc) return rc;
         if (morton) {
             if (o->d_rad && (rc = scatter_rows(p->rad[b], c, 1, rows, q_begin, o->d_rad, main_st))) return rc;

@@ -219,6 +219,50 @@ def test_classic_orders_on_synthetic_sphere_and_torus():
         assert torch.equal(normals, n2) and (curv is None or torch.equal(curv, c2))
 
 
+@pytest.mark.parametrize("kind", ["torus", "sphere"])
+def test_config2_classic_orders_at_named_size(kind):
+    """BASELINE config 2 at its named size: classic (unweighted) jet orders 1-4, k=256, on the 1 M-point noisy
+    torus / sphere (seed 1234, sigma 0.005 bbdiag) through the C pipeline; 512 random centres against the oracle
+    (cKDTree neighbours, reference fit) with the per-row gate max(gate, 2 x |reference fp32 - fp64-exact|)."""
+    from deepfit_b200 import synthetic
+    from deepfit_b200.pipeline import NormalEstimator
+    from deepfit_b200.tutorial_utils import normalize_cloud
+    from oracle import deepfit_oracle as O
+    gen = synthetic.torus_cloud if kind == "torus" else synthetic.sphere_cloud
+    pts = np.ascontiguousarray(normalize_cloud(gen(1_000_000, seed=1234, noise=0.005))[0], dtype=np.float32)
+    dev = torch.from_numpy(pts).cuda()
+    q = np.sort(np.random.default_rng(7).choice(len(pts), 512, replace=False))
+    idx, dist = O.knn_ckdtree(pts, q, 256, workers=-1)
+    dist, idx = O.canonicalize_knn(dist, idx)
+    items = [O.dataset_item(pts, int(c), 256, idx[j], dist[j]) for j, c in enumerate(q)]
+    P = torch.stack([it[0] for it in items])
+    U = torch.stack([it[1] for it in items])
+    rad = torch.tensor([it[2] for it in items], dtype=torch.float64)
+    for order in (1, 2, 3, 4):
+        est = NormalEstimator(dev, 256, jet_order=order, mode="classic")
+        normals, curv = est.run()
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(normals).all()) and (curv is None) == (order == 1)
+        with torch.no_grad():
+            beta, n = O.fit_wjet(P, torch.ones_like(P[:, 0]), order)
+            beta64, n64 = O.fit_wjet(P.double(), torch.ones_like(P[:, 0]).double(), order)
+            ref_n, ex_n = O.world_normals(n, U).numpy(), O.world_normals(n64, U.double()).numpy()
+        floor = O.unoriented_angle_deg(ref_n, ex_n)
+        ang = O.unoriented_angle_deg(normals.cpu().numpy()[q], ref_n)
+        assert (ang <= np.maximum(0.01, 2 * floor)).all(), "order %d: max angular deviation %g deg" % (order, ang.max())
+        if order > 1:
+            assert bool(torch.isfinite(curv).all())
+            ref_c = (O.principal_curvatures(beta).double() / rad[:, None]).numpy()
+            ex_c = (O.principal_curvatures(beta64).double() / rad[:, None]).numpy()
+            cfloor = O.rectified_rel_err(ref_c, ex_c).max(1)
+            c = curv.cpu().numpy()[q]
+            # the PCA z-axis sign is library-defined in the reference: (k1,k2) -> (-k2,-k1) when it flips
+            flipped = np.stack([-c[:, 1], -c[:, 0]], 1)
+            err = np.minimum(O.rectified_rel_err(c, ref_c).max(1), O.rectified_rel_err(flipped, ref_c).max(1))
+            assert (err <= np.maximum(1e-3, 2 * cfloor)).all(), "order %d: max curvature error %g" % (order, err.max())
+        print("config2 %s order %d: max angle %.2e deg" % (kind, order, ang.max()))
+
+
 def test_pcpnet_style_full_outputs(tmp_path):
     """BASELINE config 3 at a reduced size: multi-shape dataset with sparse .pidx centres on RAW points, full
     test_c_est.py exports, against the oracle on the same neighbourhoods."""
