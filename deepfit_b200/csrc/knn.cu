@@ -443,6 +443,15 @@ __device__ __forceinline__ long long warp_max_uniform(long long v) {
     return (long long)(((unsigned long long)h << 32) | l);
 }
 
+// The kernel body is far larger than the instruction cache (6 300 SASS instructions = 100 KB at k = 256; ncu: 17 % of the
+// stall samples are instruction fetches), and the selection and the shared-memory sorting network were inlined at three
+// and two call sites: as real functions they exist once (DFB_KNN_INLINE_HELPERS restores the inlining for A/B builds).
+#ifdef DFB_KNN_INLINE_HELPERS
+#define DFB_KNN_HELPER __device__ __forceinline__
+#else
+#define DFB_KNN_HELPER __device__ __noinline__
+#endif
+
 struct Key {
     double d2;
     int idx;
@@ -450,7 +459,7 @@ struct Key {
 __device__ __forceinline__ bool key_less(double a, int ai, double b, int bi) { return a < b || (a == b && ai < bi); }
 
 // Ascending bitonic sort of cap (power of two) entries held in shared memory by one warp.
-__device__ __forceinline__ void warp_bitonic_sort(double* sd, int* si, int cap, int lane) {
+DFB_KNN_HELPER void warp_bitonic_sort(double* sd, int* si, int cap, int lane) {
     for (int size = 2; size <= cap; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int t = lane; t < (cap >> 1); t += 32) {
@@ -482,7 +491,7 @@ __device__ __forceinline__ void warp_bitonic_sort(double* sd, int* si, int cap, 
 // Returns the new count (>= k; larger than k + 16 only for exact ties).  EXACT: run the search until exactly k entries
 // are <= T (or the bracket is one bit pattern wide: distances tie across the cut and the tied entries all stay).
 template <bool EXACT>
-__device__ __forceinline__ int warp_select_compact(double* sd, int* si, int count, int k, int lane, double& T) {
+DFB_KNN_HELPER int warp_select_compact(double* sd, int* si, int count, int k, int lane, double& T) {
     long long lo = 0x7ff0000000000000LL, hi = 0;
     for (int t = lane; t < count; t += 32) {
         const long long v = __double_as_longlong(sd[t]);
@@ -661,6 +670,108 @@ __device__ __forceinline__ SortResult sort_emit(const double* sd, const int* si,
     return res;
 }
 
+// The same final step without a sorting network.  The k squared distances of a neighbourhood spread almost evenly over
+// [0, d_k^2] (a ball on a surface holds points in proportion to r^2), so floor(d2 * k / d_k^2) is a nearly perfect,
+// MONOTONE hash into k buckets: a counting sort by bucket (shared-memory atomics, one warp scan) leaves every entry
+// within a few places of its final position, and the exact (d2, index) rank inside a bucket is a loop over its one or
+// two members.  About 400 warp instructions where the 36-stage bitonic network of 256 entries with 96-bit keys took
+// 4.4 k (ncu: 36 % of the kernel's instructions).  Exact for any input: the bucket function is monotone in d2 (fp64
+// product, truncation and clamp all are), ties and crowded buckets are ranked by full key comparison; a neighbourhood
+// that piles more than kBucketMax entries into one bucket (a cluster plus a few far points, a lattice shell) takes the
+// kernel's general shared-memory sorting network instead (return code 2).  The acceptance test needs only the largest key, so a level that fails it is not sorted at
+// all.  The histogram / bucket ends take 32 E ints of shared memory per warp next to the list; the bucket-ordered copy goes
+// to the list's upper halves sd[k, 2k) / si[k, 2k), free once the list has been cut to exactly k entries.
+constexpr int kBucketMax = 12;
+__device__ __forceinline__ int bucket_of(double d2, double scale, int kb) { return min(kb, (int)(d2 * scale)); }
+template <int E>
+__device__ __noinline__ SortResult bucket_emit(double* sd, int* si, int* h, int k, int lane, bool top, double margin2, int* oi,
+                                               double* odist, double* orad) {
+    long long hi = 0;
+#pragma unroll 4
+    for (int t = lane; t < k; t += 32) hi = max(hi, __double_as_longlong(sd[t]));
+    hi = warp_max_uniform(hi);
+    SortResult res;
+    res.kd = hi;
+    res.kid = 0;
+    const double dk2 = __longlong_as_double(hi);
+    res.accepted = (top || dk2 < margin2) ? 1 : 0;
+    if (!res.accepted) {   // the retry one level up starts from the largest key
+        int mi = -1;
+        for (int t = lane; t < k; t += 32) mi = __double_as_longlong(sd[t]) == hi ? max(mi, si[t]) : mi;
+        res.kid = __reduce_max_sync(0xffffffffu, mi);
+        return res;
+    }
+    for (int t = lane; t < 32 * E; t += 32) h[t] = 0;
+    __syncwarp();
+    const double scale = hi > 0 ? (double)k / dk2 : 0.0;
+    const int kb = k - 1;
+#pragma unroll 4
+    for (int t = lane; t < k; t += 32) atomicAdd(&h[bucket_of(sd[t], scale, kb)], 1);
+    __syncwarp();
+    // exclusive scan of the counts, E consecutive buckets per lane: h[b] = start of bucket b; the placement pass then
+    // advances every h[b] to the END of its bucket
+    int c[E];
+    int sum = 0, maxc = 0;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+        c[j] = h[lane * E + j];
+        maxc = max(maxc, c[j]);
+        sum += c[j];
+    }
+    maxc = __reduce_max_sync(0xffffffffu, maxc);
+    if (maxc > kBucketMax) {   // the list itself is untouched so far: the caller's shared-memory network sorts it
+        res.accepted = 2;
+        return res;
+    }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    int run = incl - sum;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+        h[lane * E + j] = run;
+        run += c[j];
+    }
+    __syncwarp();
+    // placement: the list copied in bucket order into the free upper halves sd[k, 2k), si[k, 2k) (order inside a bucket
+    // arbitrary)
+    double* td = sd + k;
+    int* ti = si + k;
+#pragma unroll 4
+    for (int t = lane; t < k; t += 32) {
+        const double d = sd[t];
+        const int pos = atomicAdd(&h[bucket_of(d, scale, kb)], 1);
+        td[pos] = d;
+        ti[pos] = si[t];
+    }
+    __syncwarp();
+    // exact rank inside the bucket, then straight to the output row (ranks follow the positions closely, so the stores
+    // of a warp stay nearly contiguous)
+#pragma unroll 2
+    for (int p = lane; p < k; p += 32) {
+        const double dd = td[p];
+        const long long d = __double_as_longlong(dd);
+        const int id = ti[p];
+        const int b = bucket_of(dd, scale, kb);
+        const int s = b > 0 ? h[b - 1] : 0, e = h[b];
+        int rank = p;
+        if (e - s > 1) {
+            rank = s;
+            for (int j = s; j < e; ++j) {
+                const long long dj = __double_as_longlong(td[j]);
+                rank += (dj < d || (dj == d && ti[j] < id)) ? 1 : 0;
+            }
+        }
+        oi[rank] = id;
+        if (odist) odist[rank] = sqrt(dd);
+    }
+    if (orad && lane == 0) *orad = sqrt(dk2);
+    return res;
+}
+
 struct KnnArgs {
     const float4* sorted;
     const uint32_t* tab;
@@ -757,6 +868,17 @@ __device__ __forceinline__ void block_cell(const KnnArgs& a, const GridParams& g
 #define DFB_KNN_MINB 4
 #endif
 #define DFB_KNN_BOUNDS __launch_bounds__(kKnnWarps * 32, DFB_KNN_MINB)
+// Final step of a query: counting sort by distance bucket from k = 256 up (E >= 8), the register sorting network below
+// that (measured, profiles/r2_knn_bucket_ab.log); -DDFB_KNN_BUCKET_MIN_E=99 / =1 force one of them for A/B builds.
+#ifndef DFB_KNN_BUCKET_MIN_E
+#define DFB_KNN_BUCKET_MIN_E 8
+#endif
+template <int E>
+__device__ __forceinline__ SortResult final_emit(double* sd, int* si, int* h, int k, int lane, bool top, double margin2, int* oi,
+                                                 double* odist, double* orad) {
+    if constexpr (E >= DFB_KNN_BUCKET_MIN_E) return bucket_emit<E>(sd, si, h, k, lane, top, margin2, oi, odist, orad);
+    else return sort_emit<E>(sd, si, k, lane, top, margin2, oi, odist, orad);
+}
 template <int E>
 __global__ void DFB_KNN_BOUNDS knn_kernel(KnnArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -764,6 +886,7 @@ __global__ void DFB_KNN_BOUNDS knn_kernel(KnnArgs a) {
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     double* sd = reinterpret_cast<double*>(smem_raw) + (size_t)warp * a.kcap;
     int* si = reinterpret_cast<int*>(smem_raw + (size_t)kKnnWarps * a.kcap * sizeof(double)) + (size_t)warp * a.kcap;
+    int* sh = reinterpret_cast<int*>(smem_raw + (size_t)kKnnWarps * a.kcap * (sizeof(double) + sizeof(int))) + warp * (32 * E);
     const GridParams gpar = *a.gp;
     const int G = 1 << gpar.bits;
     const int SM = gpar.sub_levels;           // levels below the dense table (0 for clouds without heavy cells)
@@ -953,21 +1076,24 @@ __global__ void DFB_KNN_BOUNDS knn_kernel(KnnArgs a) {
             }
             if (E > 0 && count == k) {
                 __syncwarp();
-                const SortResult sr = sort_emit<(E > 0 ? E : 1)>(sd, si, k, lane, top, margin2, a.out_idx + qw * (long long)k,
+                const SortResult sr = final_emit<(E > 0 ? E : 1)>(sd, si, sh, k, lane, top, margin2, a.out_idx + qw * (long long)k,
                                                                  a.out_dist ? a.out_dist + qw * (long long)k : nullptr,
                                                                  a.out_rad ? a.out_rad + qw : nullptr);
-                if (sr.accepted) {
+                if (sr.accepted == 1) {
                     prev_k2 = __longlong_as_double(sr.kd);
                     level_hint = l;
                     pcx = cx; pcy = cy; pcz = cz;
                     __syncwarp();
                     break;
                 }
-                Td = __longlong_as_double(sr.kd);
-                Ti = sr.kid;
-                thr_incl = true;
-                __syncwarp();
-                continue;
+                if (sr.accepted == 0) {
+                    Td = __longlong_as_double(sr.kd);
+                    Ti = sr.kid;
+                    thr_incl = true;
+                    __syncwarp();
+                    continue;
+                }
+                // 2: crowded buckets -- the general path below sorts the (untouched) list
             }
             int sort_n = cap;
             if (count == k) sort_n = k2;
@@ -1299,9 +1425,10 @@ extern "C" int dfb_knn(const dfb_grid* grid, const int32_t* d_query, int64_t q_b
     a.query = d_query; a.q_begin = q_begin; a.q_count = q_count;
     a.k = k; a.kcap = kcap;
     a.out_idx = d_idx; a.out_dist = d_dist; a.out_rad = d_rad;
-    const size_t smem = (size_t)kKnnWarps * kcap * (sizeof(double) + sizeof(int));
     int k2 = 32;
     while (k2 < k) k2 <<= 1;
+    // the candidate list (d2 and index, kcap entries per warp) + the bucket histogram of the final step (k2 ints per warp)
+    const size_t smem = (size_t)kKnnWarps * (kcap * (sizeof(double) + sizeof(int)) + (k2 <= 512 && k2 / 32 >= DFB_KNN_BUCKET_MIN_E ? k2 : 0) * sizeof(int));
     // every warp works through a contiguous run of queries (at least 2): exactly one wave of resident CTAs, so that
     // all of them finish together
     long long blocks = (q_count + 2 * kKnnWarps - 1) / (2 * kKnnWarps);
