@@ -490,8 +490,9 @@ DFB_KNN_HELPER void warp_bitonic_sort(double* sd, int* si, int cap, int lane) {
 // as an integer search the loop ends at the exact k-th value at the latest.
 // Returns the new count (>= k; larger than k + 16 only for exact ties).  EXACT: run the search until exactly k entries
 // are <= T (or the bracket is one bit pattern wide: distances tie across the cut and the tied entries all stay).
-template <bool EXACT>
-DFB_KNN_HELPER int warp_select_compact(double* sd, int* si, int count, int k, int lane, double& T) {
+// One function with EXACT as a run-time flag: two instantiations were 1 300 instructions of a kernel that does not fit
+// the instruction cache.
+DFB_KNN_HELPER int warp_select_compact(double* sd, int* si, int count, int k, int lane, double& T, bool EXACT) {
     long long lo = 0x7ff0000000000000LL, hi = 0;
     for (int t = lane; t < count; t += 32) {
         const long long v = __double_as_longlong(sd[t]);
@@ -682,12 +683,16 @@ __device__ __forceinline__ SortResult sort_emit(const double* sd, const int* si,
 // all.  The histogram / bucket ends take 32 E ints of shared memory per warp next to the list; the bucket-ordered copy goes
 // to the list's upper halves sd[k, 2k) / si[k, 2k), free once the list has been cut to exactly k entries.
 constexpr int kBucketMax = 12;
+#ifndef DFB_KNN_BU
+#define DFB_KNN_BU 2
+#endif
+constexpr int kBucketUnroll = DFB_KNN_BU;
 __device__ __forceinline__ int bucket_of(double d2, double scale, int kb) { return min(kb, (int)(d2 * scale)); }
 template <int E>
 __device__ __noinline__ SortResult bucket_emit(double* sd, int* si, int* h, int k, int lane, bool top, double margin2, int* oi,
                                                double* odist, double* orad) {
     long long hi = 0;
-#pragma unroll 4
+#pragma unroll (kBucketUnroll)
     for (int t = lane; t < k; t += 32) hi = max(hi, __double_as_longlong(sd[t]));
     hi = warp_max_uniform(hi);
     SortResult res;
@@ -705,7 +710,7 @@ __device__ __noinline__ SortResult bucket_emit(double* sd, int* si, int* h, int 
     __syncwarp();
     const double scale = hi > 0 ? (double)k / dk2 : 0.0;
     const int kb = k - 1;
-#pragma unroll 4
+#pragma unroll (kBucketUnroll)
     for (int t = lane; t < k; t += 32) atomicAdd(&h[bucket_of(sd[t], scale, kb)], 1);
     __syncwarp();
     // exclusive scan of the counts, E consecutive buckets per lane: h[b] = start of bucket b; the placement pass then
@@ -740,7 +745,7 @@ __device__ __noinline__ SortResult bucket_emit(double* sd, int* si, int* h, int 
     // arbitrary)
     double* td = sd + k;
     int* ti = si + k;
-#pragma unroll 4
+#pragma unroll (kBucketUnroll)
     for (int t = lane; t < k; t += 32) {
         const double d = sd[t];
         const int pos = atomicAdd(&h[bucket_of(d, scale, kb)], 1);
@@ -800,7 +805,25 @@ __device__ __constant__ unsigned char c_cell_order[27] = {13, 12, 14, 10, 16, 4,
 // 27 cells of the block whose first cell is (bx, by, bz) (may be -1).  l >= 0: dense table.  l < 0: sub-level -l of the
 // finest cells; where the parent cell is not subdivided that deep, the finest available ancestor stands in for all of the
 // block's cells it contains and is returned by the first of them only (the others return an empty range).
-__device__ __forceinline__ void block_cell(const KnnArgs& a, const GridParams& gpar, int G, int l, int ex, int ey, int ez, int bx,
+#ifdef DFB_KNN_BLOCKCELL_NOINLINE
+#define DFB_KNN_BLOCKCELL __device__ __noinline__
+#else
+#define DFB_KNN_BLOCKCELL __device__ __forceinline__
+#endif
+// While a radius guess from the neighbouring query is active the bound is tight already (1.5 x its k-th d2): the early
+// selection after the own cell / the face neighbours would re-derive what the guess gives (-DDFB_KNN_SELECT_GUESSED
+// restores it for A/B builds).
+#ifdef DFB_KNN_SELECT_GUESSED
+#define DFB_KNN_SKIP_GUESSED
+#else
+#define DFB_KNN_SKIP_GUESSED !guessed &&
+#endif
+#ifdef DFB_KNN_EXPECT
+#define DFB_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define DFB_UNLIKELY(x) (x)
+#endif
+DFB_KNN_BLOCKCELL void block_cell(const KnnArgs& a, const GridParams& gpar, int G, int l, int ex, int ey, int ez, int bx,
                                            int by, int bz, float ux, float uy, float uz, uint32_t& lo, uint32_t& hi, float& cmin2) {
     lo = hi = 0u;
     cmin2 = 0.f;
@@ -862,12 +885,14 @@ __device__ __forceinline__ void block_cell(const KnnArgs& a, const GridParams& g
 }
 
 // E = register entries per lane of the final sort (32 * E = the power of two >= k); 0: shared-memory network only
-// 4 CTAs per SM = 128 registers: left to itself the compiler settles on 96 registers and spills 156 bytes in the cell
-// scan (measured -3 % on uniform clouds, profiles/r2_knn_subgrid_ab.log); DFB_KNN_MINB overrides for A/B builds
+// Register budget: 6 CTAs per SM (80 registers, 24 warps) up to k = 256 -- the kernel is bound by per-warp latency, and
+// since the final step became a counting sort the extra warps outweigh the ~200 bytes of spills (measured +10 .. +14 %
+// over 128 registers, profiles/r2_knn_bucket_ab.log; with the sorting network 96 registers lost 3 %); k = 512 fits only
+// three CTAs of shared memory and keeps 128 registers.  DFB_KNN_MINB overrides for A/B builds.
 #ifndef DFB_KNN_MINB
-#define DFB_KNN_MINB 4
+#define DFB_KNN_MINB 6
 #endif
-#define DFB_KNN_BOUNDS __launch_bounds__(kKnnWarps * 32, DFB_KNN_MINB)
+#define DFB_KNN_BOUNDS __launch_bounds__(kKnnWarps * 32, (E >= 16 ? 4 : DFB_KNN_MINB))
 // Final step of a query: counting sort by distance bucket from k = 256 up (E >= 8), the register sorting network below
 // that (measured, profiles/r2_knn_bucket_ab.log); -DDFB_KNN_BUCKET_MIN_E=99 / =1 force one of them for A/B builds.
 #ifndef DFB_KNN_BUCKET_MIN_E
@@ -1015,11 +1040,11 @@ __global__ void DFB_KNN_BOUNDS knn_kernel(KnnArgs a) {
                     bool take = valid && (thr_incl ? !key_less(Td, Ti, d2, pidx) : key_less(d2, pidx, Td, Ti));
                     unsigned bal = __ballot_sync(0xffffffffu, take);
                     if (bal == 0u) continue;
-                    if (count + 32 > cap) {
+                    if (DFB_UNLIKELY(count + 32 > cap)) {
                         // the list is full: tighten the bound by selection; only if that cannot make room (a pile of
                         // exact ties) pad, sort and keep exactly the k best
                         double T;
-                        count = warp_select_compact<false>(sd, si, count, k, lane, T);
+                        count = warp_select_compact(sd, si, count, k, lane, T, false);
                         Td = T;
                         Ti = 0x7fffffff;
                         thr_incl = true;
@@ -1046,9 +1071,9 @@ __global__ void DFB_KNN_BOUNDS knn_kernel(KnnArgs a) {
                 }
                 // once the own cell / the face neighbours are in and no threshold exists yet, pay one sort to
                 // get one: everything farther than the current k-th best is then rejected without insertion
-                if ((ci == 0 || ci == 6 || ci == 18) && !full_once && count >= k) {
+                if ((ci == 0 || ci == 6 || ci == 18) && !full_once && DFB_KNN_SKIP_GUESSED count >= k) {
                     double T;
-                    count = warp_select_compact<false>(sd, si, count, k, lane, T);
+                    count = warp_select_compact(sd, si, count, k, lane, T, false);
                     if (T < Td) {   // never loosen a bound carried over from a failed level
                         Td = T;
                         Ti = 0x7fffffff;
@@ -1062,7 +1087,7 @@ __global__ void DFB_KNN_BOUNDS knn_kernel(KnnArgs a) {
             // index), so that the exact (d2, index) sort runs on half the network
             if (guessed) {
                 guessed = false;
-                if (count < k) {   // the radius hint was too small here: same level again, without it
+                if (DFB_UNLIKELY(count < k)) {   // the radius hint was too small here: same level again, without it
                     Td = INF;
                     Ti = 0x7fffffff;
                     thr_incl = true;
@@ -1072,7 +1097,7 @@ __global__ void DFB_KNN_BOUNDS knn_kernel(KnnArgs a) {
             }
             if (count > k) {
                 double T;
-                count = warp_select_compact<true>(sd, si, count, k, lane, T);
+                count = warp_select_compact(sd, si, count, k, lane, T, true);
             }
             if (E > 0 && count == k) {
                 __syncwarp();
