@@ -31,7 +31,8 @@ def _nvcc() -> str:
 def _stamp() -> str:
     h = hashlib.sha256()
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
-    files.append(os.path.join(HERE, "..", "include", "deepfit_b200.h"))
+    inc = os.path.join(HERE, "..", "include")
+    files += [os.path.join(inc, f) for f in sorted(os.listdir(inc)) if f.endswith(".h")]
     for f in files:
         with open(f, "rb") as fh:
             h.update(fh.read())

@@ -31,6 +31,7 @@
 //      the max-pool over the patch's points is a register max over TMEM columns, so the
 //      [k,1024] activations of the three 128->1024 layers never leave the SM.
 #include "common.cuh"
+#include "../../include/deepfit_b200_debug.h"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -2355,7 +2356,7 @@ extern "C" int dfb_model_profile_read(dfb_model* m, double* ms, int64_t* launche
     return DFB_OK;
 }
 
-// Debug / A-B switches (not part of the ABI header): 0 swap LBO/SBO (descriptor probe), 1 resident max-pool kernel,
+// Debug / A-B switches (declared in include/deepfit_b200_debug.h, not in the ABI header): 0 swap LBO/SBO (descriptor probe), 1 resident max-pool kernel,
 // 2 fused head, 4 layer 3 fused into the head, 5 fused chain kernels, 6 head experiment bits, 7 CTA / tile / patch whose
 // timeline is recorded (-1 off), 8 persistent head, 9 per-tile entry/exit trace of the head, 10 persistent chain.
 extern "C" DFB_API int dfb_dbg_set(int key, int value) {

@@ -9,8 +9,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "deepfit_b200.h")).read()
+def declared_symbols(header="deepfit_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     return sorted(set(re.findall(r"DFB_API\s+[\w\s\*]+?\b(dfb_\w+)\s*\(", text)))
 
 
@@ -30,6 +30,20 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert hasattr(raw, s), "missing export %s" % s
     assert lib.dfb_abi_version() == 2
     assert sorted(_lib.EXPORTS) == declared_symbols()
+
+
+def test_library_exports_nothing_undeclared():
+    """Every dynamic symbol of the .so is declared in include/: the boundary in deepfit_b200.h, the process-global
+    test / profiling hooks (dfb_dbg_*) in deepfit_b200_debug.h and nowhere else."""
+    import subprocess
+    from deepfit_b200 import _lib
+    _lib.load()
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.lib_path()], capture_output=True, text=True, check=True).stdout
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l and not l.split()[-1].startswith("_"))
+    debug = declared_symbols("deepfit_b200_debug.h")
+    assert debug and all(s.startswith("dfb_dbg_") for s in debug)
+    assert not [s for s in declared_symbols() if s.startswith("dfb_dbg_")]
+    assert exported == sorted(declared_symbols() + debug)
 
 
 def test_no_cpu_fallback_without_device():
