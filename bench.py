@@ -396,6 +396,25 @@ def library_baseline(sd, patch, order, iters=3):
     return res
 
 
+def mix_layers(precision):
+    """The chain layers a precision runs with the hi*hi product only (f16mix), by name; None for the other modes."""
+    name, _, layers = precision.partition(":")
+    if name != "f16mix":
+        return None
+    return sorted(layers.split("+")) if layers else ["qstn_max", "stn_max"]
+
+
+def chain_product_units(precision):
+    """Tensor-core MMAs executed per algorithmic product, averaged over the MACs of the three chain kernels (per point:
+    128 -> 1024 = 131 072 in each chain; small tensor-core layers 8 192 QSTN, 12 288 feature STN, 16 384 encoder)."""
+    name = precision.partition(":")[0]
+    if name != "f16mix":
+        return {"f16x3": 3, "bf16x3": 3, "f16f8": 2, "bf16": 1}[name]
+    macs = {"qstn_small": 8192, "qstn_max": 131072, "stn_small": 12288, "stn_max": 131072, "enc_small": 16384, "enc_max": 131072}
+    single = set(mix_layers(precision))
+    return sum(m * (1 if l in single else 3) for l, m in macs.items()) / sum(macs.values())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -408,7 +427,8 @@ def main():
     ap.add_argument("--cloud", type=str, default="", help="override the workload's surface: torus | sphere | multi | density")
     ap.add_argument("--order", type=int, default=0, help="jet order of the classic workload (config2)")
     ap.add_argument("--precision", type=str, default="f16x3",
-                    help="f16x3 (parity mode: split FP16, 3 products, 22-bit operands) | bf16x3 | f16f8 | bf16 (faster approximations)")
+                    help="f16x3 (split FP16, 3 products, 22-bit operands) | f16mix[:layer+layer] (f16x3 operands, the named chain "
+                         "layers with the hi*hi product only; default layers: qstn_max+stn_max) | bf16x3 | f16f8 | bf16 (approximations)")
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--ref-sample", type=int, default=2048)
     ap.add_argument("--e2e-steps", type=int, default=-1, help="steps of the end-to-end region (default: same as --steps)")
@@ -575,12 +595,15 @@ def main():
             "dtype": {"f16x3": "f16x3 (split-FP16 tensor-core MMA, three products per k-step, fp32 accumulate; fp32-grade: the parity mode)",
                       "f16f8": "f16f8 (fp16 tensor-core MMA + one e4m3 correction MMA per k-step, fp32 accumulate; weights 3e-4 off)",
                       "bf16x3": "bf16x3 (split-bf16 tensor-core MMA, three products per k-step, fp32 accumulate; weights 1e-4 off)",
-                      "bf16": "bf16"}[args.precision]
+                      "f16mix": "f16mix (f16x3 operands and products everywhere except the chain layers of config.precision_mix, which issue "
+                                "only the FP16 hi*hi product; fp32 accumulate)",
+                      "bf16": "bf16"}[args.precision.partition(":")[0]]
             if mode == "DeepFit" else "f64 moments / f32 solve",
             "data": "synthetic" if cloud != "boxy" else "tutorial cloud (tests/golden), seeded weights",
             "config": {"workload": workload_text(args, cloud, n_total, K, ORDER, mode, scaling, world),
                        "points_total": n_total, "points_this_rank": end - begin, "k": K, "jet_order": ORDER,
                        "precision": args.precision if mode == "DeepFit" else None,
+                       "precision_mix": mix_layers(args.precision) if mode == "DeepFit" else None,
                        "chunk": chunk, "l2": "256 MiB flush buffer written before every step",
                        "sharding": "contiguous point-index ranges, replicated cloud+grid, outputs written in place into the all-gather "
                                    "buffers, one in-place all-gather per dtype (f32 normals 12 B/pt, f64 curvatures 16 B/pt)",
@@ -599,7 +622,7 @@ def main():
             gm_ms, gm_n = prof["gemm_max_128x1024"]
             achieved = (n_patches_timed * chain_flop_per_patch(K)) / (gm_ms * 1e-3) / 1e12 if gm_ms > 0 else None
             net_ms = sum(v[0] for v in prof.values())
-            units = {"f16x3": 3, "bf16x3": 3, "f16f8": 2, "bf16": 1}[args.precision]
+            units = chain_product_units(args.precision)
             line["roofline"] = {
                 "bound": "tensor", "kernel": "chain_max_kernel<k/128> (points -> 64 -> [64 -> 64 ->] 128 -> 1024 + max-pool, persistent, "
                                              "3 launches per forward)",
@@ -610,8 +633,8 @@ def main():
                 **ncu_traffic("chain_max_kernel", min(chunk, end - begin)),
                 "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained" % which,
                 "note": "achieved = algorithmic FLOPs of the three chain kernels (%.1f MFLOP/patch at k=%d) / their CUDA-event time. "
-                        "Precision %s executes %d tensor-core MMA(s) per algorithmic product (fp32-grade products need 22-bit "
-                        "operands = split FP16, hi*hi + hi*lo + lo*hi), so frac tops out near %.3f at the sustained clock the peak "
+                        "Precision %s executes %.3g tensor-core MMA(s) per algorithmic product of these kernels (22-bit operands = split "
+                        "FP16, hi*hi + hi*lo + lo*hi; f16mix: one product in the layers of config.precision_mix), so frac tops out near %.3f at the sustained clock the peak "
                         "was measured at; executed_frac = frac x that count" % (chain_flop_per_patch(K) / 1e6, K, args.precision, units, 1.0 / units),
                 "executed_frac": (achieved * units / tf_sus) if achieved else None,
                 "product_units": units,

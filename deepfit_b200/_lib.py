@@ -21,7 +21,23 @@ LAYER_NAMES = [
 assert len(LAYER_NAMES) == DFB_NUM_LAYERS
 
 WEIGHT_MODE = {"sigmoid": 0, "tanh": 1}
-PRECISION = {"bf16x3": 0, "bf16": 1, "f16f8": 2, "f16x3": 3}
+PRECISION = {"bf16x3": 0, "bf16": 1, "f16f8": 2, "f16x3": 3, "f16mix": 4}
+# DFB_MIX_* bits of include/deepfit_b200.h: the chain layers that "f16mix" runs with the hi*hi product only
+MIX_BITS = {"qstn_small": 1, "qstn_max": 2, "stn_small": 4, "stn_max": 8, "enc_small": 16, "enc_max": 32}
+
+
+def precision_code(precision: str) -> int:
+    """'f16x3' ... or 'f16mix' / 'f16mix:qstn_max+stn_max' (an explicit DFB_MIX_* mask, for the precision ladder)."""
+    name, _, layers = precision.partition(":")
+    if name not in PRECISION or (layers and name != "f16mix"):
+        raise ValueError("precision must be one of %s (f16mix optionally as 'f16mix:<layer>+<layer>' with layers %s)"
+                         % (sorted(PRECISION), sorted(MIX_BITS)))
+    mask = 0
+    for layer in filter(None, layers.split("+")):
+        if layer not in MIX_BITS:
+            raise ValueError("unknown f16mix layer %r; known: %s" % (layer, sorted(MIX_BITS)))
+        mask |= MIX_BITS[layer]
+    return PRECISION[name] | (mask << 8)
 
 EXPORTS = [
     "dfb_abi_version", "dfb_last_error_string", "dfb_device_check",

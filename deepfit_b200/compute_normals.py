@@ -33,7 +33,7 @@ def build_parser():
     parser.add_argument('--compute_curvatures', type=bool, default=True, help='true | false indicator to compute curvatures')
     parser.add_argument('--ref-compat', action='store_true',
                         help='do not cancel the QSTN rotation on the normals (what the reference script does)')
-    parser.add_argument('--precision', type=str, default='f16x3', help='f16x3 (fp32-grade, default) | bf16x3 | f16f8 (faster, weights 1e-4 .. 3e-4 off) | bf16 (fastest, ~0.2 deg)')
+    parser.add_argument('--precision', type=str, default='f16x3', help='f16x3 (fp32-grade, default) | bf16x3 | f16f8 | f16mix (faster, weights 1e-4 .. 4e-4 off) | bf16 (fastest, ~0.2 deg)')
     parser.add_argument('--batch', type=int, default=0, help='query points per chunk (0 = auto)')
     return parser
 

@@ -234,6 +234,10 @@ __device__ __forceinline__ void umma_f8_ts(uint32_t tmem_d, uint32_t tmem_a, uin
 // cost of bf16x3, whose 16-bit operands leave the weights 1e-4 off -- enough to break the 1e-3 curvature gate on
 // ill-conditioned lidar patches (oracle/studies/gate_rows_sensitivity.py).  Same plane layout as bf16x3.
 enum { FMT_BF16X3 = 0, FMT_BF16 = 1, FMT_F16F8 = 2, FMT_F16X3 = 3 };
+// A per-layer product count on FMT_F16X3 operands (precision ladder, DFB_PRECISION_F16MIX): same planes, same scales,
+// only the hi*hi product of a k-step is issued (11-bit operands).  Never a model's format -- only ever passed to
+// mma_kstep / mma_kstep_ts by a kernel whose operands are FMT_F16X3.
+constexpr int FMT_F16X1 = 4;
 __host__ __device__ __forceinline__ int fmt_planes(int fmt) { return fmt == FMT_BF16 ? 1 : 2; }
 __host__ __device__ __forceinline__ int fmt_code(int fmt) { return (fmt == FMT_F16F8 || fmt == FMT_F16X3) ? 0 : 1; }
 __host__ __device__ __forceinline__ bool fmt_is_f16(int fmt) { return fmt == FMT_F16F8 || fmt == FMT_F16X3; }
@@ -1358,6 +1362,7 @@ struct ChainArgs {
     int out_KB;
     float* out_f;             // optional fp32 [n, n_ch]
     int fmt;                  // FMT_*
+    int fmt_small, fmt_max;   // products of the small layers / of the max-pool layer: fmt, or FMT_F16X1 (hi*hi only) on f16x3 operands
     long long* tl;            // timeline region or NULL
     int tl_cta;
     int* err;
@@ -1450,20 +1455,22 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
         if (elect_one()) {
             bool ok = true;
             int pos = 0;
-            auto load_entry = [&](const bf16* src, size_t plane_elems) {
+            // a layer that only issues hi*hi products never reads its weights' lo plane: it is not fetched
+            const int planes_small = g.fmt_small == FMT_F16X1 ? 1 : planes, planes_max = g.fmt_max == FMT_F16X1 ? 1 : planes;
+            auto load_entry = [&](const bf16* src, size_t plane_elems, int np) {
                 const int s = pos % 3;
                 ok = mbar_wait<true>(smem_u32(&s_re[s]), ((uint32_t)(pos / 3) & 1u) ^ 1u, g.err, 1);
                 if (!ok) return;
                 const uint32_t bar = smem_u32(&s_rf[s]);
-                mbar_expect_tx(bar, (uint32_t)planes * kBlkBytes);
-                for (int pl = 0; pl < planes; ++pl)
+                mbar_expect_tx(bar, (uint32_t)np * kBlkBytes);
+                for (int pl = 0; pl < np; ++pl)
                     bulk_g2s(RR + (uint32_t)s * (2u * kBlkBytes) + (uint32_t)pl * kBlkBytes, src + (size_t)pl * plane_elems, kBlkBytes, bar);
                 ++pos;
             };
             for (int it = 0, patch = blockIdx.x; patch < n_patch && ok; ++it, patch += gridDim.x) {
-                for (int l = 0; l < L && ok; ++l) load_entry(g.L[l].w + (size_t)(patch / ipp) * g.L[l].w_patch_stride, g.L[l].w_plane);
+                for (int l = 0; l < L && ok; ++l) load_entry(g.L[l].w + (size_t)(patch / ipp) * g.L[l].w_patch_stride, g.L[l].w_plane, planes_small);
                 for (int i = 0; i < CT * KB3 && ok; ++i) {
-                    load_entry(g.w3 + (size_t)i * kBlkElems, g.w3_plane);
+                    load_entry(g.w3 + (size_t)i * kBlkElems, g.w3_plane, planes_max);
                     if (i == 0) CTL(43);
                     if (i == 2) CTL(47);
                 }
@@ -1500,7 +1507,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                             // k-step ks of the 64 input channels: 32-channel half ks >> 1, [hi 16 | lo 16] columns
                             const uint32_t a_hi = a + (uint32_t)(ks >> 1) * 32u + (uint32_t)(ks & 1) * 8u, a_lo = a_hi + 16u;
                             const uint32_t koff = (uint32_t)ks * 2 * kLBO;
-                            mma_kstep_ts(g.fmt, d, a_hi, a_lo, umma_desc(w_hi + koff, kLBO, kSBO), umma_desc(w_lo + koff, kLBO, kSBO), idesc,
+                            mma_kstep_ts(g.fmt_small, d, a_hi, a_lo, umma_desc(w_hi + koff, kLBO, kSBO), umma_desc(w_lo + koff, kLBO, kSBO), idesc,
                                          ks ? 1u : 0u);
                         }
                         umma_commit(smem_u32((l == 0 && L > 1 && t == 1) ? &s_acc_solo : &s_acc[t]));
@@ -1534,7 +1541,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                         for (int ks = 0; ks < 4; ++ks) {
                             const uint32_t ka = (uint32_t)ks * 2 * kLBO, kbo = (uint32_t)ks * 2 * lbo_b;
                             const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-                            mma_kstep(g.fmt, d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(a_lo + ka, kLBO, kSBO),
+                            mma_kstep(g.fmt_max, d, umma_desc(a_hi + ka, kLBO, kSBO), umma_desc(a_lo + ka, kLBO, kSBO),
                                       umma_desc(b_hi + kbo, lbo_b, kSBO), umma_desc(b_lo + kbo, lbo_b, kSBO), idesc, first);
                         }
                         umma_commit(smem_u32(&s_re[s]));
@@ -1661,6 +1668,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                 // last small layer (64 -> 128): X in shared memory, [plane][kb][NT*128 rows], k-chunk stride NT*2048
                 const uint32_t obase = XR + (uint32_t)grp * 2048u + row_off;
                 const uint32_t lo_off = (uint32_t)KB3 * NT * kBlkBytes;
+                const bool x_lo = planes > 1 && g.fmt_max != FMT_F16X1;   // a hi*hi-only max-pool layer never reads X's lo plane
 #pragma unroll 1
                 for (int c0 = cbeg; c0 < cbeg + (Ly.n_out >> 1); c0 += 32) {
                     tmem_ld32(dcol + (uint32_t)c0, v);
@@ -1675,7 +1683,7 @@ __global__ void __launch_bounds__(kChainThreads) chain_max_kernel(const ChainArg
                             const int col = c0 + c8 * 8;
                             const uint32_t o = obase + (uint32_t)(col >> 6) * (NT * kBlkBytes) + (uint32_t)((col & 63) >> 3) * (NT * 2048u);
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o), "r"(ph[4 * c8]), "r"(ph[4 * c8 + 1]), "r"(ph[4 * c8 + 2]), "r"(ph[4 * c8 + 3]) : "memory");
-                            if (planes > 1)
+                            if (x_lo)
                                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o + lo_off), "r"(pl[4 * c8]), "r"(pl[4 * c8 + 1]), "r"(pl[4 * c8 + 2]), "r"(pl[4 * c8 + 3]) : "memory");
                         }
                     }
@@ -1947,6 +1955,7 @@ struct PackedLayer {
 
 struct dfb_model {
     int k = 0, weight_mode = 0, fmt = 0 /* FMT_* */, max_batch = 0;
+    int x1_mask = 0;  // DFB_PRECISION_F16MIX: chain layers that issue only the hi*hi product (DFB_MIX_* bits)
     float b4 = 0.f;  // conv4 bias
     dfb::PackedLayer L[DFB_NUM_LAYERS];
     dfb::PackedLayer head_global;  // HEAD_CONV1 columns 0..1023  (bias = folded conv1 bias)
@@ -2261,7 +2270,10 @@ int launch_chain(const dfb_model* m, const float* patch, long long n_patch, cons
     a.w3 = sp.W3->w.p; a.w3_plane = sp.W3->w.plane; a.bias3 = sp.W3->bias; a.relu3 = sp.relu3; a.n_ch = sp.W3->out;
     a.out_t = gfeat.p; a.out_plane = gfeat.plane; a.out_KB = gfeat.KB;
     a.fmt = m->fmt; a.err = m->err;
-    a.tl = timeline_region(sp.n_layers == 1 ? 0 : (sp.relu3 ? 1 : 2)); a.tl_cta = g_tl_cta;
+    const int chain_id = sp.n_layers == 1 ? 0 : (sp.relu3 ? 1 : 2);   // QSTN, feature STN, encoder
+    a.fmt_small = ((m->x1_mask >> (2 * chain_id)) & 1) ? FMT_F16X1 : m->fmt;
+    a.fmt_max = ((m->x1_mask >> (2 * chain_id + 1)) & 1) ? FMT_F16X1 : m->fmt;
+    a.tl = timeline_region(chain_id); a.tl_cta = g_tl_cta;
     // k = 512: a patch's 256 KB of activations do not fit shared memory, so it is processed as two 256-point work items
     const int ipp = m->k == 512 ? 2 : 1;
     const int NT = m->k / 128 / ipp;
@@ -2425,10 +2437,13 @@ extern "C" int dfb_model_create(const dfb_model_desc* desc, dfb_stream stream, d
     dfb_model* m = new dfb_model();
     m->k = desc->k;
     m->weight_mode = desc->weight_mode;
-    DFB_REQUIRE(desc->precision >= DFB_PRECISION_BF16X3 && desc->precision <= DFB_PRECISION_F16X3, DFB_E_ARG,
+    const int precision = desc->precision & 0xff, mix_mask = (desc->precision >> 8) & DFB_MIX_ALL;
+    DFB_REQUIRE(precision >= DFB_PRECISION_BF16X3 && precision <= DFB_PRECISION_F16MIX && (desc->precision >> 8) == mix_mask &&
+                    (mix_mask == 0 || precision == DFB_PRECISION_F16MIX), DFB_E_ARG,
                 "dfb_model_create: unknown precision %d", desc->precision);
-    static const int fmt_of[4] = {FMT_BF16X3, FMT_BF16, FMT_F16F8, FMT_F16X3};
-    m->fmt = fmt_of[desc->precision];
+    static const int fmt_of[5] = {FMT_BF16X3, FMT_BF16, FMT_F16F8, FMT_F16X3, FMT_F16X3};
+    m->fmt = fmt_of[precision];
+    if (precision == DFB_PRECISION_F16MIX) m->x1_mask = mix_mask ? mix_mask : DFB_MIX_DEFAULT;
     m->max_batch = desc->max_batch > 0 ? (desc->max_batch + 127) / 128 * 128 : 1024;
 #define DFB_TRY(expr)                     \
     do {                                  \

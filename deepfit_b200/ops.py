@@ -303,14 +303,13 @@ class WeightNetwork:
             raise NotImplementedError(
                 "weight_mode %r: the reference's softmax branch is a batch-axis softmax (models/DeepFit.py:310) "
                 "and is not reproduced" % weight_mode)
-        if precision not in _lib.PRECISION:
-            raise ValueError("precision must be one of %s" % sorted(_lib.PRECISION))
+        precision_code = _lib.precision_code(precision)
         self.device = torch.device(device if device is not None else "cuda")
         self.k = int(k)
         desc = _lib.DfbModelDesc()
         desc.k = self.k
         desc.weight_mode = _lib.WEIGHT_MODE[weight_mode]
-        desc.precision = _lib.PRECISION[precision]
+        desc.precision = precision_code
         desc.max_batch = int(max_batch)
         keep = []
         assert len(layers) == _lib.DFB_NUM_LAYERS

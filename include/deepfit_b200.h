@@ -171,6 +171,21 @@ typedef struct dfb_layer {
 #define DFB_PRECISION_F16X3 3  /* split FP16, 3 products, 22-bit operands: |dw| at the reference's own fp32 noise; THE
                                   parity mode (default); same range requirements as F16F8 (checked) */
 
+#define DFB_PRECISION_F16MIX 4 /* F16X3 operands everywhere, but the chain layers named by a DFB_MIX_* mask issue only the
+                                  hi*hi product (11-bit operands, a third of the tensor work): the per-layer precision
+                                  ladder.  precision = DFB_PRECISION_F16MIX | (mask << 8); mask 0 = DFB_MIX_DEFAULT, which
+                                  is 1.21x faster than F16X3 with |dw| 4e-4: passes both gates on smooth clouds (0.17 /
+                                  0.53 of the gates), up to 7x over the curvature gate on ill-conditioned lidar patches,
+                                  where no single-product layer passes (measured: profiles/r2_mix_probe.log) */
+#define DFB_MIX_QSTN_SMALL 1   /* QSTN chain 64 -> 128 */
+#define DFB_MIX_QSTN_MAX 2     /* QSTN chain 128 -> 1024 + max-pool */
+#define DFB_MIX_STN_SMALL 4    /* feature-STN chain 64 -> 64 -> 128 (and 3 -> 64 -> 64 recomputed in front of it) */
+#define DFB_MIX_STN_MAX 8      /* feature-STN chain 128 -> 1024 + max-pool */
+#define DFB_MIX_ENC_SMALL 16   /* encoder chain 64 -> 64, x * T2, 64 -> 128 */
+#define DFB_MIX_ENC_MAX 32     /* encoder chain 128 -> 1024 + max-pool */
+#define DFB_MIX_ALL 63
+#define DFB_MIX_DEFAULT (DFB_MIX_QSTN_MAX | DFB_MIX_STN_MAX)
+
 typedef struct dfb_model_desc {
     int32_t k;           /* points per patch == num_points of the reference constructor; 128, 256, 384 or 512 */
     int32_t weight_mode; /* DFB_WEIGHT_MODE_* */

@@ -46,6 +46,21 @@ def test_library_exports_nothing_undeclared():
     assert exported == sorted(declared_symbols() + debug)
 
 
+def test_precision_codes():
+    """dfb_model_desc.precision: the mode in the low byte, a DFB_MIX_* layer mask above it (f16mix only)."""
+    from deepfit_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "deepfit_b200.h")).read()
+    for name, code in _lib.PRECISION.items():
+        assert re.search(r"#define DFB_PRECISION_%s %d\b" % (name.upper(), code), header), name
+    for name, bit in _lib.MIX_BITS.items():
+        assert re.search(r"#define DFB_MIX_%s %d\b" % (name.upper(), bit), header), name
+    assert _lib.precision_code("f16x3") == 3 and _lib.precision_code("f16mix") == 4
+    assert _lib.precision_code("f16mix:qstn_max+stn_max") == 4 | (10 << 8)
+    for bad in ("f16x3:qstn_max", "f16mix:head", "fp32"):
+        with pytest.raises(ValueError):
+            _lib.precision_code(bad)
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():

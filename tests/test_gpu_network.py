@@ -158,7 +158,7 @@ def dbg_switch():
 
 
 @pytest.mark.parametrize("variant", ["fused", "fused_l12_only", "unfused"])
-@pytest.mark.parametrize("precision", ["f16x3", "bf16x3", "f16f8", "bf16"])
+@pytest.mark.parametrize("precision", ["f16x3", "bf16x3", "f16f8", "f16mix", "bf16"])
 def test_network_stage_by_stage_vs_torch(golden, precision, variant, dbg_switch):
     from deepfit_b200 import DeepFit as D
     from deepfit_b200 import ops
@@ -192,7 +192,7 @@ def test_network_stage_by_stage_vs_torch(golden, precision, variant, dbg_switch)
     report["trans2"] = (trans2 - ref["trans2"]).abs().max().item()
     report["weights"] = (w - ref["weights"]).abs().max().item()
     report["pts"] = (pts - torch.bmm(P.transpose(1, 2), ref["trans"]).transpose(1, 2)).abs().max().item()
-    tol = {"f16x3": 2e-5, "bf16x3": 3e-4, "f16f8": 6e-4, "bf16": 6e-2}[precision]
+    tol = {"f16x3": 2e-5, "bf16x3": 3e-4, "f16f8": 6e-4, "f16mix": 6e-4, "bf16": 6e-2}[precision]
     print(precision, variant, {k_: "%.1e" % v for k_, v in report.items()})
     bad = {k_: v for k_, v in report.items() if not v < tol}
     assert not bad, "stage errors (relative to stage max): %s" % report
@@ -202,13 +202,23 @@ def test_network_stage_by_stage_vs_torch(golden, precision, variant, dbg_switch)
 # f16f8 (16- / 15-bit operands) are faster approximations: their weights are 1e-4 / 3e-4 off the reference's, which the
 # normals tolerate (gate holds) but the curvatures of ill-conditioned lidar patches do not (measured up to 1.2x / 2.9x the
 # gate); their tests document that bound instead of claiming parity.
+#
+# f16mix is the per-layer precision ladder VERDICT r1 asked for, measured on the GPU (tools/mix_probe.py,
+# profiles/r2_mix_probe.log): f16x3 operands everywhere, but the 128 -> 1024 max-pool layers of the QSTN and feature-STN
+# chains (42 % of the network's MACs) issue the FP16 hi*hi product only.  +21 % throughput; every gate of the smooth cloud
+# holds (normals 0.17, curvatures 0.53 of their gates), but NO single-product layer survives the lidar cloud: its
+# ill-conditioned rows sit at 0.62 of the curvature gate already in f16x3 (the reference's own fp32 noise), and one
+# 11-bit layer moves 7-18 of the 512 rows over it (QSTN max layer alone 6.4x, feature-STN max layer alone 3.1x, both
+# 7.1x; the encoder's 46x; normals 1.04x on one row).  An approximation for CAD-like clouds, not a parity mode.
 PARITY_PRECISIONS = ["f16x3"]
 ALL_PRECISIONS = ["f16x3", "bf16x3", "f16f8"]
-WEIGHT_TOL = {"f16x3": 5e-5, "bf16x3": 3e-4, "f16f8": 6e-4}
-LIDAR_CURV_FACTOR = {"f16x3": 1.0, "bf16x3": 2.0, "f16f8": 4.0}     # allowed multiple of the per-row curvature gate
+GATE_PRECISIONS = ALL_PRECISIONS + ["f16mix"]
+WEIGHT_TOL = {"f16x3": 5e-5, "bf16x3": 3e-4, "f16f8": 6e-4, "f16mix": 6e-4}
+LIDAR_CURV_FACTOR = {"f16x3": 1.0, "bf16x3": 2.0, "f16f8": 4.0, "f16mix": 10.0}     # allowed multiple of the per-row curvature gate
+LIDAR_ANGLE_FACTOR = {"f16mix": 1.5}                                                # ... of the per-row normal gate (default 1)
 
 
-@pytest.mark.parametrize("precision", ALL_PRECISIONS)
+@pytest.mark.parametrize("precision", GATE_PRECISIONS)
 @pytest.mark.parametrize("name", CLOUD_NAMES)
 def test_deepfit_forward_matches_reference_golden(golden, name, precision):
     """DeepFit.forward drop-in vs the reference module (eval mode) on the reference's own patches: every output."""
@@ -227,7 +237,7 @@ def test_deepfit_forward_matches_reference_golden(golden, name, precision):
     assert dw < WEIGHT_TOL[precision] and dt < 1e-4 and dt2 < 1e-4
 
 
-@pytest.mark.parametrize("precision", ALL_PRECISIONS)
+@pytest.mark.parametrize("precision", GATE_PRECISIONS)
 @pytest.mark.parametrize("name", CLOUD_NAMES)
 def test_deepfit_forward_per_row_gate(golden, name, precision):
     """BASELINE.json's gates (0.01 deg unoriented, 1e-3 rectified-relative curvature) on 512 patches per cloud against
@@ -259,11 +269,36 @@ def test_deepfit_forward_per_row_gate(golden, name, precision):
              cerr[strict_c].max(), int(strict_c.sum()), (cerr / gate_c).max()))
     assert dw < WEIGHT_TOL[precision], dw
     assert dt < 1e-4, dt
-    assert (ang <= gate_a).all(), "rows over their gate: %s" % np.nonzero(ang > gate_a)[0][:10]
+    af = LIDAR_ANGLE_FACTOR.get(precision, 1.0) if name == "0000000000" else 1.0
+    assert (ang <= af * gate_a).all(), "rows over their gate: %s" % np.nonzero(ang > af * gate_a)[0][:10]
     cf = LIDAR_CURV_FACTOR[precision] if name == "0000000000" else 1.0
     assert (cerr <= cf * gate_c).all(), "rows over their gate: %s" % np.nonzero(cerr > cf * gate_c)[0][:10]
     if name == "Boxy_smooth100k":
         assert strict_a.all() and strict_c.all()     # the smooth cloud needs no relaxation at all
+
+
+def test_f16mix_layer_masks():
+    """'f16mix' == its default layer set spelled out, bit for bit; 'f16mix' with a layer the ladder does not run
+    single-product by default differs from it; an empty set cannot be spelled (mask 0 means the default)."""
+    from deepfit_b200 import DeepFit as D
+    from deepfit_b200 import ops
+    from oracle import deepfit_oracle as O
+    g = torch.Generator().manual_seed(5)
+    patch = (torch.rand((200, 3, 256), generator=g) - 0.5).cuda()
+    layers = D.fold_batchnorm(O.seeded_state_dict(0))
+    out = {}
+    for p in ("f16mix", "f16mix:qstn_max+stn_max", "f16mix:qstn_max", "f16x3"):
+        net = ops.WeightNetwork(layers, 256, "sigmoid", p, max_batch=256)
+        w, trans, t2, _ = net.forward(patch, want_trans2=True)
+        net.status()
+        out[p] = (w.clone(), trans.clone(), t2.clone())
+        net.close()
+    for a, b in zip(out["f16mix"], out["f16mix:qstn_max+stn_max"]):
+        assert torch.equal(a, b)
+    assert not torch.equal(out["f16mix"][0], out["f16mix:qstn_max"][0])
+    assert not torch.equal(out["f16mix:qstn_max"][1], out["f16x3"][1])          # the QSTN rotation feels its max layer
+    assert torch.equal(out["f16mix:qstn_max"][1], out["f16mix"][1])            # ... and nothing of the feature STN's
+    assert (out["f16mix"][0] - out["f16x3"][0]).abs().max() < 2e-3
 
 
 def model_curv(beta, rad):
