@@ -6,9 +6,10 @@
 cd "$GRAFT_REPO_ROOT" || exit 1
 O=gpurun_out/r2L; mkdir -p $O
 B="--no-cpu-baseline --no-library-baseline"
-timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > $O/pytest_gpu.log 2>&1; echo "pytest rc $?"; tail -2 $O/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider > $O/pytest_gpu.log 2>&1; echo "pytest rc $?"; tail -12 $O/pytest_gpu.log
 python __graft_entry__.py smoke > $O/smoke.log 2>&1; echo "smoke rc $?"; tail -1 $O/smoke.log
 timeout 600 python bench.py --steps 10 > $O/bench_default.jsonl 2> $O/bench_default.err; echo "bench default rc $?"
+timeout 300 python bench.py --steps 10 --precision f16mix $B > $O/bench_f16mix.jsonl 2> $O/bench_f16mix.err; echo "bench f16mix rc $?"
 python bench.py --steps 1 --warmup 1 --points 32768 $B > $O/bench_small.jsonl 2>&1; echo "small rc $?"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches.csv python bench.py --steps 1 --warmup 1 --points 32768 $B > $O/ncu1.log 2>&1; echo "ncu list rc $?"
 ncu --set full --clock-control none --import-source on -k regex:"chain_max|head_fused" -s 8 -c 8 -o $O/full -f python bench.py --steps 1 --warmup 1 --points 32768 $B > $O/ncu2.log 2>&1; echo "ncu full rc $?"
@@ -23,4 +24,4 @@ ncu -i $O/stages.ncu-rep --page raw --csv > $O/stages_raw.csv 2>/dev/null; echo 
 rm -f $O/stages.ncu-rep
 timeout 200 python tools/timeline.py --precision f16x3 --batch 16384 --cta 2000 > $O/timeline_f16x3.log 2>&1; echo "timeline rc $?"
 timeout 500 python bench.py --workload config4 --steps 1 --warmup 1 $B > $O/bench_config4.jsonl 2> $O/bench_config4.err; echo "bench config4 rc $?"
-for f in default boxy config2_o1 config2_o2 config2_o3 config2_o4 config4; do cut -c1-200 $O/bench_$f.jsonl; tail -1 $O/bench_$f.err; done
+for f in default f16mix boxy config2_o1 config2_o2 config2_o3 config2_o4 config4; do cut -c1-200 $O/bench_$f.jsonl; tail -1 $O/bench_$f.err; done
