@@ -428,6 +428,7 @@ struct GemmArgs {
     // EPI_T2
     float* trans2;       // fp32 [patch,64,64], may be NULL
     uint32_t lbo, sbo;   // descriptor strides (debug-switchable)
+    int cf;              // three-product formats: keep the corrections' truncations small, see gemm_kernel (0 off, 1 on)
     int* err;
 };
 
@@ -447,7 +448,21 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int planes = fmt_planes(g.fmt);
     const uint32_t stage_bytes = (uint32_t)planes * (1 + NT) * kBlkBytes;
-    constexpr uint32_t kTmemCols = NT == 1 ? 128 : (NT == 2 ? 256 : 512);
+    // tcgen05.mma accumulates in fp32 with TRUNCATION (measured: tools/tc_accum_probe.py, -0.5 ulp of the accumulator per
+    // MMA): every MMA into a grown accumulator costs the same half ulp whether it adds a main product or a 2^-11 times
+    // smaller correction, so a K-long three-product sum pays 3K/16 half ulps.  Kept apart from the main products the
+    // corrections' truncations are 2^-11 times smaller and the sum pays K/16: the per-patch FC layers (K = 1024 / 512 /
+    // 256) carried a third of the network's weight noise (oracle/studies/noise_sources.py; |dw| 2.7e-5 -> 1.9e-5 and the
+    // QSTN rotation 1.0e-6 -> 4.5e-7 on the GPU, profiles/r2_fc_corrections_ab.log).  Two forms:
+    //   split (NT <= 2, not the max-pool epilogue): hi*lo + lo*hi accumulate in a SECOND set of TMEM columns, added to the
+    //         main accumulator (fp32, round to nearest) by the epilogue -- one pass over K, no extra operand traffic;
+    //   two passes over K otherwise: the corrections of every k-step while the accumulator is still 2^-11 of its final
+    //         size, then the hi*hi products.
+    const bool cf = g.cf && fmt_three(g.fmt);
+    const bool split = cf && NT <= 2 && EPI != EPI_MAX;
+    const int passes = (cf && !split) ? 2 : 1;
+    const uint32_t kTmemCols = (NT == 1 ? 128u : (NT == 2 ? 256u : 512u)) * (split ? 2u : 1u);
+    const uint32_t corr_cols = (uint32_t)NT * 128u;   // split: column offset of the correction accumulators
 
     // tile coordinates
     long long a_tile, b_tile0, patch;
@@ -492,9 +507,10 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (elect_one()) {
-            for (int kb = 0; kb < g.KB; ++kb) {
-                const int s = kb % stages;
-                const uint32_t it = (uint32_t)(kb / stages);
+            for (int i = 0; i < g.KB * passes; ++i) {
+                const int kb = i % g.KB;
+                const int s = i % stages;
+                const uint32_t it = (uint32_t)(i / stages);
                 if (!mbar_wait(smem_u32(&s_empty[s]), (it & 1u) ^ 1u, g.err, 1)) break;
                 const uint32_t full = smem_u32(&s_full[s]);
                 mbar_expect_tx(full, stage_bytes);
@@ -515,9 +531,9 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
         if (elect_one()) {
             const uint32_t idesc = umma_idesc(g.n_mma, fmt_code(g.fmt));
             bool ok = true;
-            for (int kb = 0; kb < g.KB && ok; ++kb) {
-                const int s = kb % stages;
-                const uint32_t it = (uint32_t)(kb / stages);
+            for (int i = 0; i < g.KB * passes && ok; ++i) {
+                const int s = i % stages;
+                const uint32_t it = (uint32_t)(i / stages);
                 ok = mbar_wait(smem_u32(&s_full[s]), it & 1u, g.err, 2);
                 if (!ok) break;
                 tc_fence_after();
@@ -531,9 +547,21 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint32_t koff = (uint32_t)ks * 2 * g.lbo;  // 16 elements = two 16-byte k-chunks
-                        const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-                        mma_kstep(g.fmt, d, umma_desc(sa_hi + koff, g.lbo, g.sbo), umma_desc(sa_lo + koff, g.lbo, g.sbo),
-                                  umma_desc(sb_hi + koff, g.lbo, g.sbo), umma_desc(sb_lo + koff, g.lbo, g.sbo), idesc, first);
+                        const uint32_t first = (i == 0 && ks == 0) ? 0u : 1u;
+                        const uint64_t da_hi = umma_desc(sa_hi + koff, g.lbo, g.sbo), da_lo = umma_desc(sa_lo + koff, g.lbo, g.sbo);
+                        const uint64_t db_hi = umma_desc(sb_hi + koff, g.lbo, g.sbo), db_lo = umma_desc(sb_lo + koff, g.lbo, g.sbo);
+                        if (split) {
+                            umma_bf16(d, da_hi, db_hi, idesc, first);
+                            umma_bf16(d + corr_cols, da_hi, db_lo, idesc, first);
+                            umma_bf16(d + corr_cols, da_lo, db_hi, idesc, 1u);
+                        } else if (passes == 1) {
+                            mma_kstep(g.fmt, d, da_hi, da_lo, db_hi, db_lo, idesc, first);
+                        } else if (i < g.KB) {      // pass 0: hi*lo + lo*hi of every k-step
+                            umma_bf16(d, da_hi, db_lo, idesc, first);
+                            umma_bf16(d, da_lo, db_hi, idesc, 1u);
+                        } else {                    // pass 1: hi*hi of every k-step
+                            umma_bf16(d, da_hi, db_hi, idesc, 1u);
+                        }
                     }
                 }
                 umma_commit(smem_u32(&s_empty[s]));  // frees the stage when these MMAs have read it
@@ -573,6 +601,12 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_kernel(const GemmArgs g, co
 #pragma unroll 1
                     for (int c0 = 0; c0 < g.n_mma; c0 += 32) {
                         tmem_ld32(tbase + (uint32_t)(t * 128 + c0), v);
+                        if (split) {
+                            uint32_t vc[32];
+                            tmem_ld32(tbase + corr_cols + (uint32_t)(t * 128 + c0), vc);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(vc[i]));
+                        }
                         const int cl = t * 128 + c0;                                   // column inside the CTA
                         const long long col0 = (long long)blockIdx.y * NT * 128 + cl;  // global output column
                         float f[32];
@@ -2118,10 +2152,13 @@ int upload_f32(const float* h, size_t n, float** d, cudaStream_t st) {
     return 0;
 }
 
+int g_gemm_cf = 1;  // dfb_dbg_set key 11: 0 = one pass over K, products in hh, hl, lh order per k-step
+
 GemmArgs base_args(const dfb_model* m) {
     GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.fmt = m->fmt;
+    g.cf = g_gemm_cf;
     g.n_mma = 128;
     g.err = m->err;
     g.weight_mode = m->weight_mode;
@@ -2383,6 +2420,7 @@ extern "C" DFB_API int dfb_dbg_set(int key, int value) {
     if (key == 8) dfb::g_head_persistent = value;
     if (key == 9) dfb::g_cta_trace_on = value;
     if (key == 10) dfb::g_chain_persistent = value;
+    if (key == 11) dfb::g_gemm_cf = value;
     return DFB_OK;
 }
 

@@ -21,7 +21,8 @@ extern "C" {
  * kernel (0 = one CTA per (patch, channel tile)), 2 fused head (0 = separate 64->512 / 512->256 launches), 4 layer 3
  * fused into the head, 5 fused chain kernels (0 = pointwise / small-GEMM / max-pool launches), 6 head experiment bits
  * (results are garbage), 7 CTA whose timeline is recorded (-1 off), 8 persistent head, 9 per-tile entry/exit trace of
- * the head, 10 persistent chain.  Every default is the product path. */
+ * the head, 10 persistent chain, 11 corrections-first product order in the generic GEMM kernel (0 = hh, hl, lh per
+ * k-step in one pass over K).  Every default is the product path. */
 DFB_API int dfb_dbg_set(int key, int value);
 
 /* (SM id, entry ns, exit ns) of the first n_cta CTAs of the last traced head launch (key 9).  Synchronises the device. */

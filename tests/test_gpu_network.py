@@ -214,7 +214,8 @@ PARITY_PRECISIONS = ["f16x3"]
 ALL_PRECISIONS = ["f16x3", "bf16x3", "f16f8"]
 GATE_PRECISIONS = ALL_PRECISIONS + ["f16mix"]
 WEIGHT_TOL = {"f16x3": 5e-5, "bf16x3": 3e-4, "f16f8": 6e-4, "f16mix": 6e-4}
-LIDAR_CURV_FACTOR = {"f16x3": 1.0, "bf16x3": 2.0, "f16f8": 4.0, "f16mix": 10.0}     # allowed multiple of the per-row curvature gate
+LIDAR_CURV_FACTOR = {"f16x3": 1.0, "bf16x3": 3.0, "f16f8": 4.0, "f16mix": 10.0}     # allowed multiple of the per-row curvature gate
+#                    measured:        0.62           1.2 - 2.0      2.9           7.1        (bf16x3 moves with the accumulation order)
 LIDAR_ANGLE_FACTOR = {"f16mix": 1.5}                                                # ... of the per-row normal gate (default 1)
 
 

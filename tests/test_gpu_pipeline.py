@@ -45,9 +45,11 @@ def test_classic_pipeline_vs_oracle_on_tutorial_cloud(clouds, tmp_path):
 _ORACLE_CACHE = {}
 
 
-def _oracle_on_our_patches(name, sd, patch, U, rad, n_perm=3):
+def _oracle_on_our_patches(name, sd, patch, U, rad, n_perm=3, n_fresh=0):
     """Reference algebra (oracle, fp32) on OUR patches + its per-row fp32 noise floor: the largest deviation from the
-    fp64-exact result among the fp32 forward and n_perm neighbour permutations of it (same rule as the golden gate set)."""
+    fp64-exact result among the fp32 forward and n_perm neighbour permutations of it (same rule as the golden gate set).
+    n_fresh > 0 adds a fifth element: the reference measured against ITSELF under those gates -- the worst (angle, curvature)
+    error / gate of n_fresh further permutations (not used for the floors) against the unpermuted forward."""
     from oracle import deepfit_oracle as O
     if name in _ORACLE_CACHE:
         return _ORACLE_CACHE[name]
@@ -68,7 +70,16 @@ def _oracle_on_our_patches(name, sd, patch, U, rad, n_perm=3):
             pn, pc = fwd(P[:, :, torch.randperm(P.shape[2], generator=g)].contiguous())
             fa = np.maximum(fa, O.unoriented_angle_deg(pn, ex_n))
             fc = np.maximum(fc, O.rectified_rel_err(pc, ex_c).max(1))
-    _ORACLE_CACHE[name] = (ref_n, ref_c, fa, fc)
+        out = (ref_n, ref_c, fa, fc)
+        if n_fresh:
+            gate_a, gate_c = np.maximum(0.01, 2 * fa), np.maximum(1e-3, 2 * fc)
+            ra = rc = 0.0
+            for _ in range(n_fresh):
+                pn, pc = fwd(P[:, :, torch.randperm(P.shape[2], generator=g)].contiguous())
+                ra = max(ra, float((O.unoriented_angle_deg(pn, ref_n) / gate_a).max()))
+                rc = max(rc, float((O.rectified_rel_err(pc, ref_c).max(1) / gate_c).max()))
+            out = out + ((ra, rc),)
+    _ORACLE_CACHE[name] = out
     return _ORACLE_CACHE[name]
 
 
@@ -107,6 +118,48 @@ def test_deepfit_pipeline_vs_oracle(clouds, name, precision):
     assert (err <= cf * gate_c).all(), "max curvature error / gate %g" % (err / gate_c).max()
     if name == "Boxy_smooth100k":
         assert (gate_a <= 0.01).all() and (gate_c <= 1e-3).all()
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("name", ["Boxy_smooth100k", "0000000000"])
+def test_deepfit_pipeline_other_weight_sets(clouds, name, seed):
+    """The pretrained blob is missing from the reference checkout, so every other parity test rests on ONE seeded
+    state_dict (seed 0, the one the golden vectors were generated with).  Same end-to-end check as
+    test_deepfit_pipeline_vs_oracle in the parity mode under two more weight sets, the oracle (reference algebra,
+    fp32) and the per-row fp32 noise floors evaluated on the fly.
+
+    Every row must hold its normal gate.  For the curvature the statement is: every row holds its gate, OR the reference
+    itself does not -- on the lidar cloud two fp32 evaluations of the REFERENCE that differ only in the order of the
+    neighbours disagree by 1.1-2.7x the per-row gate on their worst row (floors from 3 permutations; 0.8-1.1x with 16:
+    oracle/studies/floor_estimate.py, profiles/r2_floor_estimate_seeds.txt), so a row of ours may exceed its gate by no
+    more than the reference exceeds it against itself, measured here on 3 fresh permutations.  Measured: smooth cloud
+    0.04 / 0.07 of the gate; lidar cloud 0.44 (seed 1) and 1.00 (seed 2: one strict row of 384 whose network weights are
+    below 0.02 for 133 of its 256 neighbours; 1.28 before the FC layers' corrections were kept out of the main
+    accumulator, csrc/mlp.cu gemm_kernel), the reference against itself 1.3-2.7 there."""
+    from deepfit_b200 import ops
+    from deepfit_b200.pipeline import NormalEstimator, model_from_state_dict
+    from oracle import deepfit_oracle as O
+    pts = torch.from_numpy(O.normalize_cloud(clouds[name])[0]).cuda()
+    sd = O.seeded_state_dict(seed)
+    model = model_from_state_dict(sd, 256, 3, "sigmoid", "f16x3")
+    est = NormalEstimator(pts, 256, mode="DeepFit", model=model, chunk=256)
+    begin, count = 40000 + 1000 * seed, 384
+    normals, curv = est.run(begin, begin + count)
+    idx, rad = est.grid.query(256, q_begin=begin, q_count=count)
+    patch, U = ops.patch_pca(pts, idx, rad, q_begin=begin)
+    ref_n, ref_c, fa, fc, (self_a, self_c) = _oracle_on_our_patches("%s/seed%d" % (name, seed), sd, patch, U, rad, n_fresh=3)
+    ang = O.unoriented_angle_deg(normals.cpu().numpy(), ref_n)
+    err = O.rectified_rel_err(curv.cpu().numpy(), ref_c).max(1)
+    gate_a, gate_c = np.maximum(0.01, 2 * fa), np.maximum(1e-3, 2 * fc)
+    print("%s seed %d: angle max %.3e deg (worst angle/gate %.2f, %d of %d rows relaxed); curvature max %.3e (worst err/gate "
+          "%.2f, %d rows relaxed, %d over); the reference against itself: %.2f / %.2f"
+          % (name, seed, ang.max(), (ang / gate_a).max(), int((gate_a > 0.01).sum()), count, err.max(), (err / gate_c).max(),
+             int((gate_c > 1e-3).sum()), int((err > gate_c).sum()), self_a, self_c))
+    assert (ang <= gate_a).all(), "max angular deviation %g deg, worst angle/gate %g" % (ang.max(), (ang / gate_a).max())
+    assert (err <= max(1.0, self_c) * gate_c).all() and (err > gate_c).sum() <= 1, \
+        "max curvature error / gate %g (the reference against itself: %g)" % ((err / gate_c).max(), self_c)
+    if name == "Boxy_smooth100k":
+        assert (gate_a <= 0.01).all() and (gate_c <= 1e-3).all() and (err <= gate_c).all()
 
 
 @pytest.mark.parametrize("file_order", [False, True], ids=["morton_order", "file_order"])

@@ -23,6 +23,11 @@ def main():
     from oracle import deepfit_oracle as O
     golden = np.load(os.path.join(ROOT, "tests", "golden", "reference_outputs.npz"))
     sd = O.seeded_state_dict(0)
+    for kv in filter(None, os.environ.get("DFB_DBG", "").split(",")):     # kernel A/B switches, e.g. DFB_DBG=11:0 (bench.py's format)
+        from deepfit_b200 import _lib
+        key, val = kv.split(":")
+        _lib.load().dfb_dbg_set(int(key), int(val))
+        print("dfb_dbg_set(%s, %s)" % (key, val))
     for precision in sys.argv[1:]:
         model = model_from_state_dict(sd, 256, 3, "sigmoid", precision)
         verdict = True
