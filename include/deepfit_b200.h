@@ -168,8 +168,10 @@ typedef struct dfb_layer {
 #define DFB_PRECISION_F16F8 2  /* FP16 main product + ONE E4M3 MMA carrying both first-order corrections (2 product
                                   units): |dw| 3e-4; passes on smooth clouds, up to 2.9x over the curvature gate on lidar
                                   patches; needs |weights| < 250 and |activations| < 500 (checked) */
-#define DFB_PRECISION_F16X3 3  /* split FP16, 3 products, 22-bit operands: |dw| at the reference's own fp32 noise; THE
-                                  parity mode (default); same range requirements as F16F8 (checked) */
+#define DFB_PRECISION_F16X3 3  /* split FP16, 3 products, 22-bit operands: |dw| 2e-5, which is the tensor core's truncating
+                                  fp32 accumulate, not the operands (the reference's own fp32 network is 2e-6 from the
+                                  fp64 one); THE parity mode (default): every per-row gate holds;
+                                  same range requirements as F16F8 (checked) */
 
 #define DFB_PRECISION_F16MIX 4 /* F16X3 operands everywhere, but the chain layers named by a DFB_MIX_* mask issue only the
                                   hi*hi product (11-bit operands, a third of the tensor work): the per-layer precision
