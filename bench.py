@@ -301,9 +301,28 @@ def spot_check(est, pts, begin, normals, curv, k, order, mode, sd_cpu, n_check=2
         ang = O.unoriented_angle_deg(normals[:n_check].cpu().numpy(), ref_n)
         res = {"points": n_check, "knn_exact_vs_fp64_bruteforce": knn_ok, "max_angle_deg": float(ang.max()),
                "median_angle_deg": float(np.median(ang))}
+        # the same reference algebra evaluated in float64: how far the REFERENCE's fp32 result is from the exact one on
+        # each of these rows (its noise floor), and the per-row gates of the parity tests, max(gate, 2 x floor)
+        p64, U64 = patch.cpu().double(), U.cpu().double()
+        if mode == "DeepFit":
+            sd64 = {k_: (v.double() if v.is_floating_point() else v) for k_, v in sd_cpu.items()}
+            n64, beta64, _, trans64, _, _ = O.deepfit_forward(sd64, p64, order)
+            ex_n = O.world_normals(n64, U64, trans64).numpy()
+        else:
+            beta64, n64 = O.fit_wjet(p64, torch.ones(n_check, k, dtype=torch.float64), order)
+            ex_n = O.world_normals(n64, U64).numpy()
+        gate_a = np.maximum(0.01, 2 * O.unoriented_angle_deg(ref_n, ex_n))
+        res["worst_angle_over_row_gate"] = float((ang / gate_a).max())
         if order > 1:
             ref_c = (O.principal_curvatures(beta).double() / rad.cpu()[:, None]).numpy()
-            res["max_curv_err"] = float(O.rectified_rel_err(curv[:n_check].cpu().numpy(), ref_c).max())
+            ex_c = (O.principal_curvatures(beta64).double() / rad.cpu()[:, None]).numpy()
+            ours_c = curv[:n_check].cpu().numpy()
+            err = O.rectified_rel_err(ours_c, ref_c).max(1)
+            floor_c = O.rectified_rel_err(ref_c, ex_c).max(1)
+            res["max_curv_err"] = float(err.max())
+            res["worst_curv_over_row_gate"] = float((err / np.maximum(1e-3, 2 * floor_c)).max())
+            res["max_curv_err_reference_vs_fp64"] = float(floor_c.max())
+            res["max_curv_err_ours_vs_fp64"] = float(O.rectified_rel_err(ours_c, ex_c).max())
     res["all_finite"] = bool(torch.isfinite(normals).all()) and (curv is None or bool(torch.isfinite(curv).all()))
     return res
 
