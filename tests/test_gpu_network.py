@@ -76,6 +76,33 @@ def test_umma_gemm_points_as_rows(shape, nprod):
     assert (out_t.double() - ref).abs().max().item() < tol_t
 
 
+def test_tensor_core_accumulate_truncates_and_corrections_apart(dbg_switch):
+    """What bounds the parity mode's accuracy: tcgen05.mma TRUNCATES its fp32 accumulator after
+    every MMA.  Operands exact in split FP16, C against the float64 sum, in units of 2^-24 of sum|products|:
+    positive operands (a growing accumulator) show a negative bias that grows with the number of MMAs (K = 1024, three
+    products per k-step: -121 measured; a round-to-nearest accumulate would be unbiased within +-2); keeping the
+    hi*lo + lo*hi corrections out of the main accumulator (dfb_dbg_set key 11, the product default for this kernel) takes
+    their truncations away: -88, and on signed operands the largest error drops from 8.0 to 3.3."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    M, N, K = 256, 128, 1024
+    A = (torch.rand(M, K, device="cuda", generator=g) + 0.5) / 32
+    Bm = (torch.rand(N, K, device="cuda", generator=g) + 0.5) / 32
+    sign = (torch.randint(0, 2, (M, K), device="cuda", generator=g) * 2 - 1).float()
+    stats = {}
+    for name, a in (("positive", A), ("signed", A * sign)):
+        ref = a.double() @ Bm.double().t()
+        scale = a.abs().double() @ Bm.abs().double().t()
+        for apart in (0, 1):
+            dbg_switch(11, apart, 1)
+            out, _ = _dbg_gemm(a.contiguous(), Bm.contiguous(), None, 0, 4, 0, 128)
+            rel = (out.double() - ref) / scale * 2 ** 24
+            stats[name, apart] = (rel.mean().item(), rel.abs().max().item())
+    print({"%s, corrections %s" % (k_[0], "apart" if k_[1] else "in the accumulator"): "mean %+.1f max %.1f" % v for k_, v in stats.items()})
+    assert stats["positive", 0][0] < -60 and stats["positive", 1][0] < -40            # truncation, not rounding
+    assert stats["positive", 1][0] > 0.85 * stats["positive", 0][0]                    # ... fewer of them
+    assert stats["signed", 1][1] < 0.6 * stats["signed", 0][1]
+
+
 @pytest.mark.parametrize("nprod", NPRODS)
 @pytest.mark.parametrize("N", [256, 1024])
 @pytest.mark.parametrize("k_pts", [128, 256, 512])
