@@ -22,6 +22,18 @@ def _run(args, timeout):
     return json.loads(lines[0])
 
 
+def test_precision_bookkeeping_of_the_roofline_note():
+    """executed MMAs per algorithmic product of the chain kernels, per precision (what executed_frac multiplies by)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.chain_product_units("f16x3") == 3 and bench.chain_product_units("f16f8") == 2 and bench.chain_product_units("bf16") == 1
+    assert bench.mix_layers("f16x3") is None and bench.mix_layers("f16mix") == ["qstn_max", "stn_max"]
+    assert bench.mix_layers("f16mix:enc_max+qstn_small") == ["enc_max", "qstn_small"]
+    u = bench.chain_product_units("f16mix")            # two of the three 128 -> 1024 layers at one product
+    assert abs(u - (3 * (131072 + 8192 + 12288 + 16384) + 2 * 131072) / (3 * 131072 + 8192 + 12288 + 16384)) < 1e-12
+    assert 1.7 < u < 1.9 and bench.chain_product_units("f16mix:qstn_max+stn_max+enc_max") < 1.2
+
+
 def test_reference_arm_json_contract():
     line = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--points", "4096", "--ref-sample", "64"], 600)
     assert COMMON <= set(line)
