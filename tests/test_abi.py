@@ -129,6 +129,70 @@ def test_text_io_is_byte_compatible_with_numpy(tmp_path):
     assert np.array_equal(tu.loadtxt_f32(tmp_path / "sci.xyz"), np.loadtxt(tmp_path / "sci.xyz").astype("float32"))
 
 
+def test_loadtxt_exact_parser_cases(tmp_path):
+    """loadtxt without strtod on the common path (csrc/textio.cu: 64-bit digit gathering, one exact double operation for
+    <= 15 digits, x87 extended precision with a midpoint guard for numpy's own 19-digit lines, strtod for the rest): every
+    digit count in both notations, float32 rounding midpoints and their double neighbours written with 17-19 digits
+    (where a double off by one ulp would flip the float), decimal strings AT midpoints of two doubles, the syntax numpy
+    accepts (comments, blank lines, tabs / commas / CRLF, no trailing newline, signs, nan / inf, subnormals, overlong
+    mantissas), the multi-threaded path (> 1 MiB), and the errors."""
+    import numpy as np
+    from decimal import Decimal, getcontext
+    from deepfit_b200 import _lib
+    from deepfit_b200 import tutorial_utils as tu
+    rng = np.random.default_rng(3)
+
+    def same(path):
+        ref = np.loadtxt(path, ndmin=2).astype("float32")
+        got = tu.loadtxt_f32(path)
+        return got.shape == ref.shape and np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    for nd in list(range(1, 22)) + [25]:
+        vals = rng.standard_normal((600, 3)) * 10.0 ** rng.integers(-12, 12, size=(600, 3))
+        np.savetxt(tmp_path / "e.txt", vals, fmt="%%.%de" % (nd - 1))
+        assert same(tmp_path / "e.txt"), "%d significant digits, scientific" % nd
+    for nd in (0, 1, 3, 6, 9, 15, 17, 20):
+        vals = rng.standard_normal((600, 3)) * 10.0 ** rng.integers(-3, 6, size=(600, 3))
+        np.savetxt(tmp_path / "f.txt", vals, fmt="%%.%df" % nd)
+        assert same(tmp_path / "f.txt"), "%d decimals, fixed" % nd
+    for dtype, span in ((np.float32, 8), (np.float64, 30)):                      # numpy's own format, threaded path
+        a = (rng.standard_normal((30000, 3)) * 10.0 ** rng.integers(-span, span, size=(30000, 3))).astype(dtype)
+        np.savetxt(tmp_path / "np.txt", a)
+        assert os.path.getsize(tmp_path / "np.txt") > (1 << 20) and same(tmp_path / "np.txt")
+    f = rng.integers(0x30000000, 0x50000000, size=4000, dtype=np.uint32).view(np.float32)
+    mid = (f.astype(np.float64) + np.nextafter(f, np.float32(np.inf)).astype(np.float64)) / 2
+    for fmt in ("%.16e", "%.17e", "%.18e"):
+        np.savetxt(tmp_path / "m.txt", np.stack([mid, np.nextafter(mid, np.inf), np.nextafter(mid, -np.inf)], 1), fmt=fmt)
+        assert same(tmp_path / "m.txt"), fmt
+    getcontext().prec = 60
+    rows = []
+    for x in rng.standard_normal(1500) * 10.0 ** rng.integers(-6, 6, size=1500):
+        x = float(x)
+        m = (Decimal(x) + Decimal(float(np.nextafter(x, np.inf)))) / 2
+        rows.append(" ".join((format(m, ".18e"), format(m, ".17e"), format(m + Decimal(10) ** (m.adjusted() - 18), ".18e"))))
+    open(tmp_path / "d.txt", "w").write("\n".join(rows) + "\n")
+    assert same(tmp_path / "d.txt")
+    txt = ("# header\n\n  1.5\t-2.25 ,+3e2 # tail\n\r\n0.000 -0.0 00012.50\r\n1e-320 1e30 1.7976931348623157e308\nnan inf -inf\n"
+           "4.9e-324 2.2250738585072014e-308 123456789012345678901234567890e-20\n.5 5. 1.e3")
+    open(tmp_path / "s.txt", "w").write(txt)
+    want = np.array([[float(t) for t in ln.split("#")[0].replace(",", " ").split()]
+                     for ln in txt.replace("\r", "").split("\n") if ln.split("#")[0].strip()], dtype=np.float64)
+    with np.errstate(over="ignore"):
+        want = want.astype(np.float32)
+    got = tu.loadtxt_f32(tmp_path / "s.txt")
+    assert got.shape == want.shape == (6, 3) and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    open(tmp_path / "r.txt", "w").write("1 2 3\n4 5\n")
+    with pytest.raises(_lib.DeepFitB200Error):
+        tu.loadtxt_f32(tmp_path / "r.txt")
+    for bad in ("1 2 x\n", "1 2 3\n4 5 6 7\n", "1 2 3\n4 y 6\n"):
+        open(tmp_path / "x.txt", "w").write(bad)
+        with pytest.raises(_lib.DeepFitB200Error):
+            tu.loadtxt_f32(tmp_path / "x.txt")
+    with pytest.raises(_lib.DeepFitB200Error):
+        tu.loadtxt_f32(tmp_path / "missing.txt")
+    open(tmp_path / "c.txt", "w").write("# nothing\n")
+    assert tu.loadtxt_f32(tmp_path / "c.txt").shape == (0, 0)
+
+
 def test_savetxt_exact_formatter_rounding_cases(tmp_path):
     """'%.18e' without printf (csrc/textio.cu: exact 128-bit integer arithmetic on float32-origin values): random bit
     patterns over the whole fast range, every neighbour of a power of ten, exponents where the rounding carries, signed
