@@ -24,7 +24,7 @@ import torch
 
 from . import ops
 from .DeepFit import DeepFit
-from .tutorial_utils import load_xyz, savetxt
+from .tutorial_utils import load_xyz, savetxt, loadtxt_f32
 
 
 class PointcloudPatchDataset:
@@ -107,7 +107,7 @@ class PointcloudPatchDataset:
             if self.include_normals or self.include_neighbor_normals:
                 self._gt["normals"] = torch.from_numpy(np.ascontiguousarray(load_xyz(base + '.normals'))).to(self.device)
             if self.include_curvatures:
-                self._gt["curv"] = torch.from_numpy(np.loadtxt(base + '.curv').astype('float32').reshape(-1, 2)).to(self.device)
+                self._gt["curv"] = torch.from_numpy(np.ascontiguousarray(loadtxt_f32(base + '.curv')).reshape(-1, 2)).to(self.device)
             if self.shape_patch_count[shape_ind] is None:
                 self.shape_patch_count[shape_ind] = int(gpu.shape[0])
         return self._loaded[1], self._loaded[2]
