@@ -113,15 +113,82 @@ inline int format_e18_f32(float xf, char* out) {
     *o++ = g_digits2[2 * ak + 1];
     return (int)(o - out);
 }
+// The same for a true double (curv / rad, compute_normals.py:79, is one): m < 2^53, so m * 5^p fits 128 bits up to p = 31,
+// i.e. 1e-13 <= |x| < 1e19 -- every curvature this pipeline writes; the rest falls back.
+inline int format_e18_f64(double x, char* out) {
+    uint64_t bits;
+    memcpy(&bits, &x, 8);
+    const bool neg = (bits >> 63) != 0;
+    const int ex = (int)((bits >> 52) & 0x7ffu);
+    uint64_t m = bits & ((1ull << 52) - 1);
+    char* o = out;
+    if (ex == 0 && m == 0) {   // +-0
+        if (neg) *o++ = '-';
+        memcpy(o, "0.000000000000000000e+00", 24);
+        return (int)(o - out) + 24;
+    }
+    if (ex == 0 || ex == 0x7ff) return 0;   // subnormal, inf, nan
+    m |= 1ull << 52;
+    const int s = 1075 - ex;                // x = m * 2^-s
+    const int msb = ex - 1023;              // x in [2^msb, 2^(msb+1))
+    int k = (int)((msb * 1233) >> 12);      // floor(msb * log10(2)) within one for |msb| < 2^11 (arithmetic shift)
+    unsigned long long Q = 0;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        const int p = 18 - k;               // want x * 10^p in [10^18, 10^19)
+        if (p < 0 || p > 31) return 0;      // 2^53 * 5^31 < 2^125
+        const u128 V = (u128)m * g_pow5.v[p];
+        const int sh = p - s;               // x * 10^p = V * 2^sh
+        u128 q;
+        bool up = false;
+        if (sh >= 0) {
+            if (sh > 60 || (V >> (126 - sh)) != 0) return 0;
+            q = V << sh;
+        } else {
+            const int r = -sh;
+            if (r >= 127) return 0;
+            q = V >> r;
+            const u128 rem = V & (((u128)1 << r) - 1), half = (u128)1 << (r - 1);
+            up = rem > half || (rem == half && (q & 1));
+        }
+        const u128 lo = (u128)1000000000000000000ull, hi = lo * 10;
+        if (q >= hi) { ++k; continue; }
+        if (q < lo) { --k; continue; }
+        Q = (unsigned long long)q + (up ? 1ull : 0ull);
+        if (Q == 10000000000000000000ull) { Q = 1000000000000000000ull; ++k; }
+        break;
+    }
+    if (Q == 0 || k < -99 || k > 99) return 0;
+    if (neg) *o++ = '-';
+    char d[20];
+    unsigned long long t = Q;
+    for (int i = 17; i >= 1; i -= 2) {
+        const unsigned two = (unsigned)(t % 100);
+        t /= 100;
+        d[i] = g_digits2[2 * two];
+        d[i + 1] = g_digits2[2 * two + 1];
+    }
+    d[0] = (char)('0' + (int)t);
+    *o++ = d[0];
+    *o++ = '.';
+    memcpy(o, d + 1, 18);
+    o += 18;
+    *o++ = 'e';
+    int ak = k;
+    if (ak < 0) { *o++ = '-'; ak = -ak; } else *o++ = '+';
+    *o++ = g_digits2[2 * ak];
+    *o++ = g_digits2[2 * ak + 1];
+    return (int)(o - out);
+}
 inline int format_e18(float x, char* buf, size_t cap) {
     const int n = format_e18_f32(x, buf);
     return n ? n : snprintf(buf, cap, "%.18e", (double)x);
 }
 inline int format_e18(double x, char* buf, size_t cap) {
-    // a double that is exactly a float32 (the f64 buffers of this pipeline mostly are not: curv / rad are true doubles)
-    const float f = (float)x;
+    int n = format_e18_f64(x, buf);
+    if (n) return n;
+    const float f = (float)x;   // a double that is exactly a float32: the narrower mantissa reaches further down (2^-37)
     if ((double)f == x) {
-        const int n = format_e18_f32(f, buf);
+        n = format_e18_f32(f, buf);
         if (n) return n;
     }
     return snprintf(buf, cap, "%.18e", x);

@@ -194,9 +194,10 @@ def test_loadtxt_exact_parser_cases(tmp_path):
 
 
 def test_savetxt_exact_formatter_rounding_cases(tmp_path):
-    """'%.18e' without printf (csrc/textio.cu: exact 128-bit integer arithmetic on float32-origin values): random bit
-    patterns over the whole fast range, every neighbour of a power of ten, exponents where the rounding carries, signed
-    zeros, and the fallbacks (subnormals, huge values, nan / inf, true doubles, three-digit exponents)."""
+    """'%.18e' without printf (csrc/textio.cu: exact 128-bit integer arithmetic on float32-origin values and on true
+    doubles): random bit patterns over the whole fast ranges, every neighbour of a power of ten, exponents where the
+    rounding carries, exact ties, signed zeros, and the fallbacks (subnormals, huge / tiny values, nan / inf, three-digit
+    exponents)."""
     import numpy as np
     from deepfit_b200 import tutorial_utils as tu
     rng = np.random.default_rng(7)
@@ -228,3 +229,15 @@ def test_savetxt_exact_formatter_rounding_cases(tmp_path):
     assert same(special)
     assert same(special.astype(np.float64))                                   # doubles that are exact float32 values
     assert same(np.array([[np.nan, np.inf, -np.inf], [1e-300, -1e300, 5e-324], [1e-99, 9.999e-100, 1e100], [0.1, 1.0 / 3, 1e99]]))
+    # true doubles (curv / rad is one): the same integer arithmetic on a 53-bit mantissa, 1e-13 <= |x| < 1e19
+    ex = rng.integers(1023 - 60, 1023 + 70, size=(150_000, 2), dtype=np.uint64)
+    man = rng.integers(0, 1 << 52, size=(150_000, 2), dtype=np.uint64)
+    sgn = rng.integers(0, 2, size=(150_000, 2), dtype=np.uint64)
+    assert same(((sgn << np.uint64(63)) | (ex << np.uint64(52)) | man).view(np.float64))
+    ex = rng.integers(1, 2046, size=(20_000, 2), dtype=np.uint64)              # every normal binade (fallbacks included)
+    assert same(((ex << np.uint64(52)) | man[:20_000]).view(np.float64))
+    p10 = np.array([10.0 ** k_ for k_ in range(-14, 20)])
+    assert same(np.stack([np.nextafter(p10, 0), p10, np.nextafter(p10, np.inf)], 1))
+    assert same(np.array([[m_ * 2.0 ** e for m_ in (1, 3, 5, 7, 9, 11, 4503599627370497.0)] for e in range(-45, 64)]))   # exact ties
+    assert same(np.array([[float("9.9999999999999995e%d" % k_), float("1.00000000000000005e%d" % k_)] for k_ in range(-13, 19)]))
+    assert same(np.array([[1e-13, 9.999999999999999e-14], [1e19, 9.999999999999998e18], [2.2e-308, 1.7976931348623157e308]]))
