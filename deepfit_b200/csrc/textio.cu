@@ -343,6 +343,7 @@ inline const char* parse_number(const char* s, const char* end, double* out) {
             *out = neg ? -r : r;
             return s;
         }
+#if (defined(__x86_64__) || defined(__i386__)) && defined(__LDBL_MANT_DIG__) && __LDBL_MANT_DIG__ == 64   // x87 extended only
         if (e10 >= -27 && e10 <= 27) {
             const long double d = (long double)w;                  // exact: 64-bit significand
             const long double r = e10 < 0 ? d / kPow10L.v[-e10] : d * kPow10L.v[e10];
@@ -355,6 +356,7 @@ inline const char* parse_number(const char* s, const char* end, double* out) {
                 return s;
             }
         }
+#endif
     }
     // fallback: strtod on a NUL-terminated copy of the token
     char buf[128];
